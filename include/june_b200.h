@@ -1,0 +1,294 @@
+/*
+ * june_b200.h -- C ABI of the B200-native replacement for JUNE's per-timestep hot path
+ * (`Simulator.do_timestep`, reference june/simulator.py:346-626).
+ *
+ * The reference has no FFI: its only extension point is overriding the Python method
+ * `Simulator.do_timestep` (june/simulator.py:192,256,273 are cls-polymorphic; the
+ * `ActivityManager` class attribute at :80 swaps the placement stage).  This header is the
+ * boundary a maintainer binds from that override with ctypes.  Plain
+ * pointers and sizes only; no torch / CUDA types in any signature.  Pointers named `d_*` are
+ * device addresses (e.g. `torch.Tensor.data_ptr()`); everything else is host memory owned by
+ * the caller and only borrowed for the duration of the call.
+ *
+ * The very same ABI (prefix `jo_` instead of `jb_`) is exported by the CPU oracle in
+ * oracle/june_oracle.c; that library is test infrastructure and is never loaded by the product.
+ *
+ * Threading: one host thread per world (= per GPU / rank).  All work is enqueued on one
+ * library-owned CUDA stream per world; `jb_step` returns after enqueue, `jb_sync`/`jb_fetch_*`
+ * wait.  Errors: every function returns 0 on success or a JB_E* code; `jb_last_error()` gives
+ * the message (mapped to `SimulatorError` by the Python host, like the reference's
+ * june/activity/activity_manager.py:400-402 and june/simulator.py:588-607).
+ */
+#ifndef JUNE_B200_H
+#define JUNE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------------- */
+#define JB_OK 0
+#define JB_EINVAL 1   /* bad argument / inconsistent world description            */
+#define JB_ECUDA 2    /* CUDA runtime failure (message in jb_last_error)          */
+#define JB_ENOACT 3   /* "Some people do not have an activity in this timestep"   */
+#define JB_ECAP 4     /* a device buffer capacity was exceeded                    */
+#define JB_ENOGPU 5   /* no usable CUDA device: the product path has NO fallback  */
+
+/* ---- activities, in the reference's hierarchy order (activity_manager.py:24-33) ------- */
+#define JB_ACT_MEDICAL 0   /* medical_facility */
+#define JB_ACT_COMMUTE 1   /* commute          */
+#define JB_ACT_PRIMARY 2   /* primary_activity */
+#define JB_ACT_LEISURE 3   /* leisure          */
+#define JB_ACT_RESIDENCE 4 /* residence        */
+#define JB_ACT_NONE 7      /* dead / nowhere   */
+#define JB_N_ACT 5
+
+/* ---- per-person state byte (`pstate`) -------------------------------------------------- */
+#define JB_PS_ACT_MASK 0x07u /* activity chosen in the current step                        */
+#define JB_PS_INFECTED 0x08u /* person.infection is not None (person.py:155-157)           */
+#define JB_PS_DEAD 0x10u     /* person.dead                                                */
+#define JB_PS_SEVERE 0x20u   /* infection.tag in severe_symptoms_stay_at_home_stage        */
+#define JB_PS_MEDICAL 0x40u  /* person.subgroups.medical_facility is not None              */
+#define JB_PS_SPARE 0x80u
+
+/* ---- registered-member info word (`reg_info`, uint16) ---------------------------------- */
+/* bits 0-7: local subgroup index inside the group; bits 8-10: activity that feeds the slot */
+#define JB_INFO_LSG(x) ((x) & 0xFFu)
+#define JB_INFO_ACT(x) (((x) >> 8) & 0x7u)
+#define JB_MAKE_INFO(lsg, act) ((uint16_t)(((act) << 8) | (lsg)))
+
+/* ---- group info word (`grp_info`, uint32) ---------------------------------------------- */
+/* bits 0-7 beta index (row of JbStepParams.beta), 8-15 beta-scale index (company sector),
+ * 16-31 region index */
+#define JB_GINFO_BETA(x) ((x) & 0xFFu)
+#define JB_GINFO_SCALE(x) (((x) >> 8) & 0xFFu)
+#define JB_GINFO_REGION(x) ((x) >> 16)
+
+/* ---- supergroup kinds (select the kernel specialisation) ------------------------------- */
+#define JB_KIND_MATRIX 0 /* fixed contact matrix of dim<=JB_MAX_DIM (interactive.py:179-180) */
+#define JB_KIND_SCHOOL 1 /* per-school matrix from 32x32 table + years[] (school.py:462-485) */
+
+#define JB_MAX_DIM 8        /* largest fixed contact matrix (university 5x5)               */
+#define JB_SCHOOL_DIM 32    /* school.py:436-438: teachers + ages 0..30                    */
+#define JB_MAX_LSG 255      /* subgroups per group                                         */
+#define JB_MAX_STAGES 8     /* longest covid19.yaml trajectory has 7 stages                */
+#define JB_MAX_SUPERGROUPS 32
+#define JB_MAX_VARIANTS 4
+#define JB_N_TPAR 5         /* transmission parameters per infection                       */
+
+/* transmission profile types (infection_selector.py:130-143) */
+#define JB_TRANS_CONSTANT 0 /* par0 = probability                                          */
+#define JB_TRANS_GAMMA 1    /* par = shape, shift, scale, norm (transmission.py:109-160)   */
+#define JB_TRANS_XNEXP 2    /* par = n, alpha, time_first_infectious, norm, norm_time      */
+
+/* completion-time distribution types (trajectory_maker.py:43-58) */
+#define JB_DIST_CONSTANT 0    /* p0 = value                      */
+#define JB_DIST_EXPONENTIAL 1 /* p0 = loc, p1 = scale            */
+#define JB_DIST_BETA 2        /* p0 = a, p1 = b, p2 = loc, p3 = scale */
+#define JB_DIST_LOGNORMAL 3   /* p0 = s, p1 = loc, p2 = scale    */
+#define JB_DIST_NORMAL 4      /* p0 = loc, p1 = scale            */
+#define JB_DIST_EXPONWEIB 5   /* p0 = a, p1 = c, p2 = loc, p3 = scale */
+
+typedef struct {
+  int32_t type;
+  double p[4];
+} JbDist;
+
+/* One supergroup = one contiguous range of groups of one spec, processed in this order
+ * (reference: simulator.py:399-455 iterates supergroups in activity-hierarchy order). */
+typedef struct {
+  uint32_t first_group, n_groups;
+  int32_t kind;          /* JB_KIND_*                                                      */
+  int32_t dim;           /* contact matrix dimension                                       */
+  int32_t cm_offset;     /* offset (in doubles) of the dim*dim row-major matrix in `cm`    */
+  int32_t activity;      /* activity whose presence in the step activates this supergroup  */
+  int32_t launch_mode;   /* 0 = one thread per group, 1 = one warp per group               */
+  int32_t has_dynamic;   /* groups of this supergroup may receive dynamic members          */
+} JbSupergroup;
+
+/* Disease description: symptom trajectories + transmission sampler + outcome table.
+ * (covid19.yaml; trajectory_maker.py:215-227; infection_selector.py:280-332;
+ *  health_index.py:151-182) */
+typedef struct {
+  int32_t n_tags;                 /* number of outcome slots (max tag value + 1), <= 16     */
+  int32_t tag_recovered_mask;     /* bit (tag+2) set if tag is a recovered_stage            */
+  int32_t tag_dead_mask;          /* bit (tag+2) set if tag is a fatality_stage             */
+  int32_t tag_hospital_mask;      /* hospitalised_stage                                     */
+  int32_t tag_icu_mask;           /* intensive_care_stage                                   */
+  int32_t tag_severe_mask;        /* severe_symptoms_stay_at_home_stage                     */
+  int32_t tag_exposed;            /* default_lowest_stage value                             */
+  int32_t n_traj;                 /* number of trajectories                                 */
+  int32_t traj_max_tag[16];       /* most severe tag of trajectory k (its key)              */
+  int32_t traj_n_stages[16];
+  int32_t traj_stage_tag[16][JB_MAX_STAGES];
+  JbDist traj_stage_time[16][JB_MAX_STAGES];
+  int32_t trans_type;             /* JB_TRANS_*                                             */
+  JbDist trans_par[6];            /* gamma: max_infectiousness, shape, rate, shift          */
+                                  /* xnexp: max_probability, smearing_time_first_infectious,
+                                            smearing_peak_position, alpha, norm_time       */
+                                  /* constant: probability                                  */
+  /* cumulative outcome probabilities cum[pop(2: gp,ch)][sex(2: f,m)][age(100)][n_tags]     */
+  const double* health_index_cum;
+  uint32_t infection_id;          /* adler32(class name), infection.py:42-47                */
+} JbDisease;
+
+/* Everything needed to create a world.  Index spaces: persons [0,n_people) are residents of
+ * this domain; [n_people, n_people+n_halo) are "halo" persons owned by another domain that are
+ * registered members of groups here (the device form of mpi_wrapper.py:169-190 visitors). */
+typedef struct {
+  uint32_t abi_version;
+  uint32_t n_people, n_halo, n_groups, n_members, n_supergroups, n_regions, n_super_areas;
+  uint32_t n_variants, n_beta, n_scale, n_cm_doubles, n_school_years;
+  uint32_t slot_capacity;          /* infection slots; 0 -> n_people                        */
+  uint32_t newinf_capacity;        /* new infections per step; 0 -> n_people + n_halo       */
+  uint64_t person_id_base;         /* global id of local person 0                           */
+  /* persons (length n_people) */
+  const uint8_t* age;              /* 0..99                                                 */
+  const uint8_t* sex;              /* 0 = f, 1 = m                                          */
+  const uint8_t* care_home_resident; /* 1 if residence is a care_home (health_index.py:160) */
+  const uint8_t* has_activity;     /* bit a set: person has a static subgroup for activity a */
+  const uint32_t* super_area;      /* person's home super area                              */
+  /* super areas */
+  const int32_t* sa_hospital;      /* closest_hospitals[0] as a group index, or -1          */
+  const uint16_t* sa_region;
+  /* groups, laid out supergroup after supergroup */
+  const uint32_t* grp_offset;      /* n_groups + 1, CSR into reg_member                     */
+  const uint32_t* grp_info;        /* JB_GINFO_*                                            */
+  const uint32_t* grp_aux;         /* school: (years offset << 8) | n_years ; else 0        */
+  const uint32_t* reg_member;      /* n_members person indices (local or halo)              */
+  const uint16_t* reg_info;        /* n_members JB_MAKE_INFO(lsg, act)                      */
+  const uint8_t* school_years;     /* n_school_years                                        */
+  const JbSupergroup* supergroups;
+  const double* cm;                /* all processed raw contact matrices                    */
+  const double* beta_scale;        /* n_scale multipliers (company.py:309-313); [0] = 1.0   */
+  JbDisease disease;
+} JbWorldDesc;
+
+/* Per-step inputs (the h2d payload of every step). */
+typedef struct {
+  double now;                 /* timer.now, days                                            */
+  double delta_time;          /* timer.duration, days                                       */
+  uint32_t step;              /* step ordinal (Philox counter word)                         */
+  uint32_t activity_mask;     /* bit a set if activity a is in timer.activities             */
+  uint64_t seed;              /* Philox key                                                 */
+  uint32_t flags;             /* JB_STEP_*                                                  */
+  uint32_t _pad;
+  /* processed beta per (beta index, region): get_processed_beta, interactive.py:154-177,
+   * household.py:256-309, school.py:487-522.  Row-major [n_beta][n_regions]. */
+  const double* beta;
+} JbStepParams;
+
+#define JB_STEP_SEVERE_STAY_HOME 0x1u /* SevereSymptomsStayHome active (individual_policies.py:121-149) */
+#define JB_STEP_HOSPITALISATION 0x2u  /* Hospitalisation active (medical_care_policies.py:413-526)     */
+#define JB_STEP_INJECT_UNIFORMS 0x4u  /* Bernoulli draws come from jb_inject_uniforms               */
+#define JB_STEP_NO_NEW_INFECTIONS 0x8u /* do not create infections on device (host uploads rows)    */
+#define JB_STEP_RECORD_LAMBDA 0x10u   /* keep per-person Lambda of this step for jb_fetch_lambda   */
+
+/* Per-step outputs (the d2h payload of every step). */
+typedef struct {
+  uint32_t n_new_infections;
+  uint32_t n_infected;        /* currently infected after the health update                 */
+  uint32_t n_dead_total;
+  uint32_t n_recovered_step;
+  uint32_t n_deaths_step;
+  uint32_t n_hospitalised;    /* currently in ward + icu                                    */
+  uint32_t n_icu;
+  uint32_t n_draws;           /* Bernoulli draws consumed (== injected uniforms consumed)   */
+  uint32_t n_no_activity;     /* >0 -> JB_ENOACT                                            */
+  uint32_t n_slots_used;
+  uint32_t n_halo_infected;   /* new infections of halo persons (to be sent home)           */
+  uint32_t _pad;
+} JbStepStats;
+
+/* One host-created infection (jb_upload_infections), mirroring the fields the reference's
+ * checkpoint stores (hdf5_savers/infection_savers/{transmission,symptoms}_saver.py). */
+typedef struct {
+  uint32_t person;            /* local person index                                         */
+  uint32_t variant;           /* variant index                                              */
+  double start_time;
+  double tpar[JB_N_TPAR];
+  double probability;         /* transmission.probability at upload time                    */
+  int32_t n_stages;
+  int32_t stage;
+  int32_t max_tag;
+  int32_t tag;
+  double traj_time[JB_MAX_STAGES];
+  int32_t traj_tag[JB_MAX_STAGES];
+} JbInfectionRow;
+
+typedef struct JbWorld JbWorld;
+
+const char* jb_last_error(void);
+int jb_abi_version(void);
+int jb_device_count(void);
+
+/* Create a device-resident world on CUDA device `device`.  Copies everything it needs. */
+int jb_world_create(const JbWorldDesc* desc, int device, JbWorld** out);
+void jb_world_destroy(JbWorld* w);
+
+/* Replace person state wholesale (n_people entries each; NULL = keep).  `susceptibility` is
+ * [n_variants][n_people].  Used for initial immunity (immunity_setter) and checkpoint restore. */
+int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const double* susceptibility);
+
+/* Test mode: uniforms consumed by the Bernoulli draws in the reference's traversal order
+ * (interaction.py:554-569,:636: one `random()` per susceptible of every group that must
+ * timestep).  Copied to the device; consumed from index 0 by the next jb_step. */
+int jb_inject_uniforms(JbWorld* w, const double* u, size_t n);
+
+/* Infect people now using the device-side sampler (InfectionSelector._make_infection,
+ * infection_selector.py:146-204): seeding (infection_seed.py:209-278). */
+int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* variants, size_t n,
+              double time, uint64_t seed, uint32_t step);
+
+/* Install host-created infections (the reference's own sampler, or a checkpoint). */
+int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size_t n);
+
+/* One do_timestep: placement -> halo pack (if n_halo) ... -> interaction -> new infections ->
+ * health update.  Split in two halves so that the host can run the NCCL halo exchange
+ * between them (single-GPU callers use jb_step).
+ *   jb_step_begin : placement + pack outbound halo state into d_send (may be NULL)
+ *   jb_step_end   : unpack inbound halo state from d_recv, interaction, infection, health;
+ *                   writes infected-abroad bytes into d_ret_send (may be NULL)
+ *   jb_step_finish: applies d_ret_recv (infections of our residents abroad), health update.
+ */
+int jb_step(JbWorld* w, const JbStepParams* params, JbStepStats* stats_out);
+int jb_step_begin(JbWorld* w, const JbStepParams* params, void* d_send);
+int jb_step_interact(JbWorld* w, const void* d_recv, void* d_ret_send);
+int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* stats_out);
+
+/* Halo wiring (multi-GPU).  `out_person[i]` is the local person whose state is sent in
+ * outbound slot i; slots are grouped by destination rank by the caller.  Inbound slot j
+ * fills halo person n_people + j.  Record sizes in bytes are returned by jb_halo_record_size. */
+int jb_set_halo(JbWorld* w, const uint32_t* out_person, size_t n_out);
+size_t jb_halo_record_size(void);   /* bytes per person in d_send / d_recv       */
+size_t jb_halo_return_size(void);   /* bytes per person in d_ret_send / d_ret_recv */
+
+int jb_sync(JbWorld* w);
+
+/* Readback (synchronises).  `cap` = capacity of the caller's arrays, `*n` = entries written. */
+int jb_fetch_new_infections(JbWorld* w, uint32_t* member, uint32_t* variant, size_t cap, size_t* n);
+int jb_fetch_person_state(JbWorld* w, uint8_t* pstate, int8_t* tag, double* trans_prob,
+                          double* susceptibility, int32_t* medical);
+int jb_fetch_lambda(JbWorld* w, double* lambda_out); /* n_people + n_halo, NaN where no draw */
+int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap, size_t* n);
+/* per-region summary: counts[n_regions][JB_N_SUMMARY] (records_writer.py:151-164) */
+#define JB_N_SUMMARY 8
+int jb_fetch_summary(JbWorld* w, uint32_t* counts);
+
+/* Kernel timing hooks for bench.py: CUDA-event time (ms) of the interaction kernels and of
+ * the whole step, measured on the library's stream, accumulated since the last reset. */
+int jb_timing_enable(JbWorld* w, int on);
+int jb_timing_read(JbWorld* w, double* interaction_ms, double* step_ms, uint64_t* n_steps,
+                   uint64_t* n_launches, int reset);
+/* Algorithmic bytes of the interaction kernels for the last step. */
+int jb_last_step_bytes(JbWorld* w, uint64_t* interaction_bytes, uint64_t* step_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JUNE_B200_H */

@@ -1,0 +1,181 @@
+"""ctypes binding of ``libjune_b200.so`` (C ABI: ``include/june_b200.h``).
+
+The product path has NO CPU fallback: if the shared library is missing, or no CUDA device is
+usable, creating a device world raises.  The same structures are reused by the tests to drive
+the CPU oracle (``oracle/libjune_oracle.so``, prefix ``jo_``) -- the oracle is never loaded from
+inside this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional
+
+import numpy as np
+
+from .world import MAX_STAGES, N_TPAR
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjune_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+ABI_VERSION = 1
+
+JB_OK, JB_EINVAL, JB_ECUDA, JB_ENOACT, JB_ECAP, JB_ENOGPU = 0, 1, 2, 3, 4, 5
+STEP_SEVERE_STAY_HOME, STEP_HOSPITALISATION, STEP_INJECT_UNIFORMS = 0x1, 0x2, 0x4
+STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA = 0x8, 0x10
+
+
+class SimulatorError(BaseException):
+    """Same base class as the reference's ``june.exc.SimulatorError`` (``exc.py:13``)."""
+
+
+class JbDist(C.Structure):
+    _fields_ = [("type", C.c_int32), ("p", C.c_double * 4)]
+
+
+class JbSupergroup(C.Structure):
+    _fields_ = [("first_group", C.c_uint32), ("n_groups", C.c_uint32), ("kind", C.c_int32), ("dim", C.c_int32),
+                ("cm_offset", C.c_int32), ("activity", C.c_int32), ("launch_mode", C.c_int32),
+                ("has_dynamic", C.c_int32)]
+
+
+class JbDisease(C.Structure):
+    _fields_ = [("n_tags", C.c_int32), ("tag_recovered_mask", C.c_int32), ("tag_dead_mask", C.c_int32),
+                ("tag_hospital_mask", C.c_int32), ("tag_icu_mask", C.c_int32), ("tag_severe_mask", C.c_int32),
+                ("tag_exposed", C.c_int32), ("n_traj", C.c_int32),
+                ("traj_max_tag", C.c_int32 * 16), ("traj_n_stages", C.c_int32 * 16),
+                ("traj_stage_tag", (C.c_int32 * MAX_STAGES) * 16),
+                ("traj_stage_time", (JbDist * MAX_STAGES) * 16),
+                ("trans_type", C.c_int32), ("trans_par", JbDist * 6),
+                ("health_index_cum", C.c_void_p), ("infection_id", C.c_uint32)]
+
+
+class JbWorldDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32),
+                ("n_people", C.c_uint32), ("n_halo", C.c_uint32), ("n_groups", C.c_uint32), ("n_members", C.c_uint32),
+                ("n_supergroups", C.c_uint32), ("n_regions", C.c_uint32), ("n_super_areas", C.c_uint32),
+                ("n_variants", C.c_uint32), ("n_beta", C.c_uint32), ("n_scale", C.c_uint32),
+                ("n_cm_doubles", C.c_uint32), ("n_school_years", C.c_uint32),
+                ("slot_capacity", C.c_uint32), ("newinf_capacity", C.c_uint32),
+                ("person_id_base", C.c_uint64),
+                ("age", C.c_void_p), ("sex", C.c_void_p), ("care_home_resident", C.c_void_p),
+                ("has_activity", C.c_void_p), ("super_area", C.c_void_p),
+                ("sa_hospital", C.c_void_p), ("sa_region", C.c_void_p),
+                ("grp_offset", C.c_void_p), ("grp_info", C.c_void_p), ("grp_aux", C.c_void_p),
+                ("reg_member", C.c_void_p), ("reg_info", C.c_void_p), ("school_years", C.c_void_p),
+                ("supergroups", C.c_void_p), ("cm", C.c_void_p), ("beta_scale", C.c_void_p),
+                ("disease", JbDisease)]
+
+
+class JbStepParams(C.Structure):
+    _fields_ = [("now", C.c_double), ("delta_time", C.c_double), ("step", C.c_uint32), ("activity_mask", C.c_uint32),
+                ("seed", C.c_uint64), ("flags", C.c_uint32), ("_pad", C.c_uint32), ("beta", C.c_void_p)]
+
+
+class JbStepStats(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "n_new_infections", "n_infected", "n_dead_total", "n_recovered_step", "n_deaths_step", "n_hospitalised",
+        "n_icu", "n_draws", "n_no_activity", "n_slots_used", "n_halo_infected", "_pad")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if not n.startswith("_")}
+
+
+class JbInfectionRow(C.Structure):
+    _fields_ = [("person", C.c_uint32), ("variant", C.c_uint32), ("start_time", C.c_double),
+                ("tpar", C.c_double * N_TPAR), ("probability", C.c_double),
+                ("n_stages", C.c_int32), ("stage", C.c_int32), ("max_tag", C.c_int32), ("tag", C.c_int32),
+                ("traj_time", C.c_double * MAX_STAGES), ("traj_tag", C.c_int32 * MAX_STAGES)]
+
+
+# every entry point include/june_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "last_error", "abi_version", "device_count", "world_create", "world_destroy", "set_person_state",
+    "inject_uniforms", "infect", "upload_infections", "step", "step_begin", "step_interact", "step_finish",
+    "set_halo", "halo_record_size", "halo_return_size", "sync", "fetch_new_infections", "fetch_person_state",
+    "fetch_lambda", "fetch_infections", "fetch_summary", "timing_enable", "timing_read", "last_step_bytes",
+]
+
+
+def nvcc_command(out_path: str = LIB_PATH) -> List[str]:
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+            "-Xcompiler", "-fPIC", "-o", out_path, os.path.join(CSRC, "june_b200.cu")]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "june_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
+    """Declare argument / return types of all ABI functions on ``lib`` (``jb_`` or ``jo_``)."""
+    def f(name):
+        return getattr(lib, prefix + name)
+    vp, u32p, u8p, dp = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_double)
+    f("last_error").restype = C.c_char_p
+    f("last_error").argtypes = []
+    f("abi_version").restype = C.c_int
+    f("device_count").restype = C.c_int
+    f("world_create").argtypes = [C.POINTER(JbWorldDesc), C.c_int, C.POINTER(vp)]
+    f("world_destroy").argtypes = [vp]
+    f("world_destroy").restype = None
+    f("set_person_state").argtypes = [vp, vp, vp]
+    f("inject_uniforms").argtypes = [vp, vp, C.c_size_t]
+    f("infect").argtypes = [vp, vp, vp, C.c_size_t, C.c_double, C.c_uint64, C.c_uint32]
+    f("upload_infections").argtypes = [vp, C.POINTER(JbInfectionRow), C.c_size_t]
+    f("step").argtypes = [vp, C.POINTER(JbStepParams), C.POINTER(JbStepStats)]
+    f("step_begin").argtypes = [vp, C.POINTER(JbStepParams), vp]
+    f("step_interact").argtypes = [vp, vp, vp]
+    f("step_finish").argtypes = [vp, vp, C.POINTER(JbStepStats)]
+    f("set_halo").argtypes = [vp, vp, C.c_size_t]
+    f("halo_record_size").restype = C.c_size_t
+    f("halo_return_size").restype = C.c_size_t
+    f("sync").argtypes = [vp]
+    f("fetch_new_infections").argtypes = [vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    f("fetch_person_state").argtypes = [vp, vp, vp, vp, vp, vp]
+    f("fetch_lambda").argtypes = [vp, vp]
+    f("fetch_infections").argtypes = [vp, C.POINTER(JbInfectionRow), C.c_size_t, C.POINTER(C.c_size_t)]
+    f("fetch_summary").argtypes = [vp, vp]
+    f("timing_enable").argtypes = [vp, C.c_int]
+    f("timing_read").argtypes = [vp, dp, dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+    f("last_step_bytes").argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp])):
+        if hasattr(lib, prefix + extra):
+            getattr(lib, prefix + extra).argtypes = args
+    if hasattr(lib, prefix + "halo_record_size_w"):
+        getattr(lib, prefix + "halo_record_size_w").restype = C.c_size_t
+    if hasattr(lib, prefix + "stream_handle"):
+        getattr(lib, prefix + "stream_handle").restype = vp
+    return lib
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load ``libjune_b200.so``.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(june_b200 has no CPU fallback)")
+        _lib = bind(C.CDLL(LIB_PATH), "jb_")
+        if _lib.jb_abi_version() != ABI_VERSION:
+            raise RuntimeError("libjune_b200.so ABI version mismatch: rebuild")
+    return _lib
+
+
+def ptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)

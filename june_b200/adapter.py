@@ -1,0 +1,216 @@
+"""World compiler: walk a reference ``World`` / ``Domain`` object graph ONCE and emit the
+struct-of-arrays form the device consumes (``june_b200.world.WorldSoA``).
+
+Duck-typed on purpose: it needs no ``import june``.  It reads exactly the attributes the
+reference hot path reads:
+
+* ``world.people`` (iterable of persons with ``id, age, sex, area, subgroups, dead``;
+  ``june/demography/person.py:35-81``),
+* ``getattr(world, supergroup_name).members`` (``june/simulator.py:404``), each group having
+  ``spec, id, subgroups, super_area`` (+ ``sector`` for companies/schools, ``years`` for schools;
+  ``june/groups/company.py:309-313``, ``june/groups/school.py:418-522``),
+* ``world.super_areas.members`` with ``region`` and ``closest_hospitals``
+  (``june/policy/medical_care_policies.py:454``).
+
+See INTEGRATION.md for how a reference ``Simulator`` subclass uses it.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from .world import (ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, ACTIVITY_CODES, KIND_MATRIX, KIND_SCHOOL, BetaRule,
+                    Supergroup, WorldSoA, make_ginfo, make_info)
+
+# activity hierarchy, june/activity/activity_manager.py:24-33 (activities without device support
+# in this round are listed so that the supergroup order stays the reference's)
+ACTIVITY_HIERARCHY = ["medical_facility", "commute", "primary_activity", "leisure", "residence"]
+
+_SINGULAR_SPEC = {
+    "households": "household", "companies": "company", "schools": "school", "hospitals": "hospital",
+    "care_homes": "care_home", "universities": "university", "pubs": "pub", "cinemas": "cinema",
+    "groceries": "grocery", "gyms": "gym", "city_transports": "city_transport",
+    "inter_city_transports": "inter_city_transport",
+}
+
+
+def supergroup_order(activity_to_super_groups: Dict[str, Sequence[str]]) -> List[Tuple[str, str]]:
+    """(supergroup name, activity) in the order ``Simulator.do_timestep`` visits them when all
+    activities are active (``activity_manager.py:172-188`` + ``simulator.py:399-409``)."""
+    out = []
+    seen = set()
+    for act in ACTIVITY_HIERARCHY:
+        for name in activity_to_super_groups.get(act, []):
+            if "visits" in name or name in seen:
+                continue
+            seen.add(name)
+            out.append((name, act))
+    return out
+
+
+def school_beta_key(sector) -> str:
+    # school.py:493-498
+    if sector is None:
+        return "school"
+    if "secondary" in sector:
+        return "secondary_school"
+    return "primary_school"
+
+
+def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sector_betas: Dict[str, float],
+                  thread_mode_specs=("household",)) -> WorldSoA:
+    people = list(world.people)
+    n = len(people)
+    pidx = {id(p): i for i, p in enumerate(people)}
+
+    super_areas = list(world.super_areas.members) if hasattr(world.super_areas, "members") else list(world.super_areas)
+    sa_idx = {id(sa): i for i, sa in enumerate(super_areas)}
+    region_names: List[str] = []
+    sa_region = np.zeros(len(super_areas), np.uint16)
+    for i, sa in enumerate(super_areas):
+        name = getattr(getattr(sa, "region", None), "name", None) or "region"
+        if name not in region_names:
+            region_names.append(name)
+        sa_region[i] = region_names.index(name)
+
+    # ---- groups, supergroup after supergroup ---------------------------------------------
+    beta_rules: List[BetaRule] = []
+
+    def beta_index(rule: BetaRule) -> int:
+        for i, r in enumerate(beta_rules):
+            if r.key == rule.key and r.fallback == rule.fallback and r.uses_tier == rule.uses_tier:
+                return i
+        beta_rules.append(rule)
+        return len(beta_rules) - 1
+
+    scales: List[float] = [1.0]
+
+    def scale_index(x: float) -> int:
+        for i, s in enumerate(scales):
+            if s == x:
+                return i
+        scales.append(float(x))
+        return len(scales) - 1
+
+    supergroups: List[Supergroup] = []
+    groups = []          # reference group objects in device order
+    gidx: Dict[int, int] = {}
+    beta_i: List[int] = []
+    scale_i: List[int] = []
+    region_i: List[int] = []
+    aux: List[int] = []
+    years_flat: List[int] = []
+    for name, act in supergroup_order(activity_to_super_groups):
+        sg_obj = getattr(world, name, None)
+        if sg_obj is None:
+            continue
+        members = [g for g in sg_obj.members if not getattr(g, "external", False)]
+        if not members:
+            continue
+        spec = members[0].spec
+        first = len(groups)
+        kind = KIND_SCHOOL if spec == "school" else KIND_MATRIX
+        if spec == "household":
+            # household / household_visits / care_visits must be consecutive rows (household.py:280-291)
+            hb = beta_index(BetaRule("household", None, False))
+            beta_index(BetaRule("household_visits", None, False))
+            beta_index(BetaRule("care_visits", None, False))
+        for g in members:
+            gidx[id(g)] = len(groups)
+            groups.append(g)
+            sa = getattr(g, "super_area", None)
+            region_i.append(int(sa_region[sa_idx[id(sa)]]) if sa is not None and id(sa) in sa_idx else 0)
+            sc = 0
+            a = 0
+            if spec == "household":
+                b = hb
+            elif spec == "school":
+                key = school_beta_key(getattr(g, "sector", None))
+                b = beta_index(BetaRule(key, "school" if key != "school" else None, True))
+                yrs = list(g.years)
+                assert len(yrs) == len(g.subgroups) - 1, "school years must match its classes"
+                assert len(yrs) < 256
+                a = (len(years_flat) << 8) | len(yrs)
+                years_flat.extend(int(y) for y in yrs)
+            elif spec == "company":
+                b = beta_index(BetaRule("company", None, True))
+                sc = scale_index(float(sector_betas.get(getattr(g, "sector", None), 1.0)))
+            else:
+                b = beta_index(BetaRule(spec, None, True))
+            beta_i.append(b)
+            scale_i.append(sc)
+            aux.append(a)
+        has_dyn = 1 if spec == "hospital" else 0
+        supergroups.append(Supergroup(name=name, spec=spec, activity=ACTIVITY_CODES[act], first_group=first,
+                                      n_groups=len(members), kind=kind,
+                                      launch_mode=0 if spec in thread_mode_specs else 1, has_dynamic=has_dyn))
+
+    # ---- registered members -----------------------------------------------------------------
+    lsg_of: Dict[int, Tuple[int, int]] = {}
+    for gi, g in enumerate(groups):
+        for li, sub in enumerate(g.subgroups):
+            lsg_of[id(sub)] = (gi, li)
+    rows = []
+    has_activity = np.zeros(n, np.uint8)
+    ch = np.zeros(n, np.uint8)
+    age = np.zeros(n, np.uint8)
+    sex = np.zeros(n, np.uint8)
+    psa = np.zeros(n, np.uint32)
+    person_ids = np.zeros(n, np.int64)
+    for i, p in enumerate(people):
+        age[i] = min(int(p.age), 255)
+        sex[i] = 1 if p.sex == "m" else 0
+        person_ids[i] = int(p.id)
+        area = getattr(p, "area", None)
+        if area is not None and id(area.super_area) in sa_idx:
+            psa[i] = sa_idx[id(area.super_area)]
+        for act_name, act in (("residence", ACT_RESIDENCE), ("primary_activity", ACT_PRIMARY)):
+            sub = getattr(p.subgroups, act_name, None) if p.subgroups is not None else None
+            if sub is None:
+                continue
+            has_activity[i] |= 1 << act
+            if getattr(sub, "external", False):
+                raise NotImplementedError("external subgroups: compile the whole world, then partition (june_b200.domains)")
+            key = lsg_of.get(id(sub))
+            if key is None:
+                continue  # subgroup of a supergroup that is not simulated
+            rows.append((key[0], key[1], i, act))
+            if act == ACT_RESIDENCE and sub.group.spec == "care_home":
+                ch[i] = 1
+    rows.sort()
+    g_arr = np.array([r[0] for r in rows], np.int64)
+    reg_member = np.array([r[2] for r in rows], np.uint32)
+    reg_info = make_info(np.array([r[1] for r in rows], np.uint16), np.array([r[3] for r in rows], np.uint16)).astype(np.uint16)
+    counts = np.bincount(g_arr, minlength=len(groups)) if len(rows) else np.zeros(len(groups), np.int64)
+    grp_offset = np.zeros(len(groups) + 1, np.uint32)
+    grp_offset[1:] = np.cumsum(counts)
+
+    sa_hospital = np.full(len(super_areas), -1, np.int32)
+    for i, sa in enumerate(super_areas):
+        hs = getattr(sa, "closest_hospitals", None)
+        if hs:
+            sa_hospital[i] = gidx.get(id(hs[0]), -1)
+
+    w = WorldSoA(
+        age=age, sex=sex, care_home_resident=ch, has_activity=has_activity, super_area=psa,
+        sa_hospital=sa_hospital, sa_region=sa_region, region_names=region_names,
+        grp_offset=grp_offset, grp_info=make_ginfo(np.array(beta_i, np.uint32), np.array(scale_i, np.uint32),
+                                                   np.array(region_i, np.uint32)).astype(np.uint32),
+        grp_aux=np.array(aux, np.uint32), reg_member=reg_member, reg_info=reg_info,
+        school_years=np.array(years_flat, np.uint8), supergroups=supergroups, beta_rules=beta_rules,
+        beta_scale=np.array(scales, np.float64), person_ids=person_ids,
+        group_ids=np.array([int(g.id) for g in groups], np.int64),
+    )
+    w.validate()
+    return w
+
+
+def group_index_map(world_soa: WorldSoA, world) -> Dict[Tuple[str, int], int]:
+    """(spec, reference group id) -> device group index."""
+    out = {}
+    for sg in world_soa.supergroups:
+        for k in range(sg.n_groups):
+            gi = sg.first_group + k
+            out[(sg.spec, int(world_soa.group_ids[gi]))] = gi
+    return out

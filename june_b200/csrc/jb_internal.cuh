@@ -1,0 +1,138 @@
+// Internal declarations shared by the translation units of libjune_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/june_b200.h"
+
+// ---- device counters (uint32 array `counters`) -------------------------------------------
+enum {
+  CNT_NEWINF = 0,      // new infections appended this step (local + halo)
+  CNT_NOACT,           // persons without any activity this step
+  CNT_DRAWS,           // Bernoulli draws consumed this step
+  CNT_DYN,             // dynamic members appended this step
+  CNT_RECOVERED_STEP,
+  CNT_DEATHS_STEP,
+  CNT_HALO_INF,
+  CNT_OVERFLOW,        // a capacity was exceeded
+  CNT_STEP_END,        // ---- everything above is zeroed at the start of every step ----
+  CNT_SLOTS_HW = CNT_STEP_END,  // infection slot high-water mark
+  CNT_DEAD_TOTAL,
+  CNT_INFECTED,        // currently infected / in hospital / in icu: recomputed by k_health,
+  CNT_HOSP,            // zeroed (3 consecutive words) right before it
+  CNT_ICU,
+  CNT_N
+};
+
+#define JB_TAG_BIT(tag) (1 << ((tag) + 2))
+
+// Arguments of the interaction (group) kernels; passed by value as a __grid_constant__.
+struct GroupArgs {
+  const uint32_t* grp_off;
+  const uint32_t* grp_info;
+  const uint32_t* grp_aux;
+  const uint32_t* reg_member;
+  const uint16_t* reg_info;
+  const uint8_t* pstate;
+  const uint8_t* pvar;
+  const double* susc;
+  const double* trans;
+  const uint32_t* halo_gid;
+  const uint8_t* school_years;
+  const double* cm;
+  const double* beta;
+  const double* beta_scale;
+  const uint64_t* dyn_key;   // sorted dynamic members (or null)
+  const uint32_t* dyn_off;   // per group offsets into dyn_key (or null)
+  uint32_t g0, g1;
+  int dim, kind, L;
+  uint32_t N, NP;
+  int V, R;
+  double dt;
+  uint64_t seed;
+  uint32_t step;
+  uint32_t gid_base;
+  uint32_t* counters;
+  uint32_t* newinf_member;
+  uint8_t* newinf_var;
+  uint32_t newinf_cap;
+  double* lambda;            // null unless JB_STEP_RECORD_LAMBDA
+  const double* inject;      // null unless JB_STEP_INJECT_UNIFORMS
+  uint32_t n_inject;
+  const uint32_t* draw_base; // exclusive scan of draw_cnt (inject mode)
+  uint32_t* draw_cnt;
+  int mode;                  // 0 = interact, 1 = only count draws per group
+};
+
+struct DiseaseDev {
+  int n_tags, rec_mask, dead_mask, hosp_mask, icu_mask, severe_mask, tag_exposed, n_traj;
+  int traj_max_tag[16];
+  int traj_n_stages[16];
+  int traj_stage_tag[16][JB_MAX_STAGES];
+  JbDist traj_stage_time[16][JB_MAX_STAGES];
+  int trans_type;
+  JbDist trans_par[6];
+};
+
+struct JbWorld {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint32_t N = 0, H = 0, NP = 0, G = 0, M = 0, V = 1, R = 1, SA = 0, C = 0, newinf_cap = 0;
+  uint32_t n_beta = 0, n_scale = 0, n_out = 0;
+  uint64_t id_base = 0;
+  std::vector<JbSupergroup> sgs;
+  std::vector<int> sg_L;          // max local subgroups per supergroup
+  DiseaseDev dis_host;
+  // static device arrays
+  uint8_t *age = nullptr, *sex = nullptr, *ch = nullptr, *phas = nullptr, *school_years = nullptr;
+  uint32_t *psa = nullptr, *grp_off = nullptr, *grp_info = nullptr, *grp_aux = nullptr, *reg_member = nullptr;
+  uint16_t *reg_info = nullptr, *sa_region = nullptr;
+  int32_t* sa_hospital = nullptr;
+  double *cm = nullptr, *beta_scale = nullptr, *hi_cum = nullptr;
+  DiseaseDev* dis = nullptr;
+  // person state
+  uint8_t *pstate = nullptr, *pvar = nullptr;
+  int8_t* ptag = nullptr;
+  double *susc = nullptr, *trans = nullptr;
+  int32_t *pmed = nullptr, *pslot = nullptr;
+  uint32_t* halo_gid = nullptr;
+  uint32_t* out_person = nullptr;
+  // infection slots
+  int32_t* inf_person = nullptr;
+  double *inf_start = nullptr, *inf_par = nullptr, *inf_next = nullptr, *traj_time = nullptr;
+  uint8_t *inf_stage = nullptr, *inf_nst = nullptr, *inf_var = nullptr;
+  int8_t *inf_tag = nullptr, *inf_maxtag = nullptr, *traj_tag = nullptr;
+  // per step
+  uint32_t* counters = nullptr;
+  uint32_t* newinf_member = nullptr;
+  uint8_t* newinf_var = nullptr;
+  double* beta = nullptr;
+  double* lambda = nullptr;
+  double* inject = nullptr;
+  size_t inject_cap = 0, n_inject = 0;
+  uint32_t *draw_cnt = nullptr, *draw_base = nullptr;
+  uint64_t *dyn_key = nullptr, *dyn_key_alt = nullptr;
+  uint32_t* dyn_off = nullptr;
+  uint32_t dyn_cap = 0;
+  bool any_dynamic = false;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  // pinned host staging
+  double* h_beta = nullptr;
+  uint32_t* h_counters = nullptr;
+  // step in flight
+  JbStepParams cur;
+  bool in_step = false;
+  // timing
+  bool timing = false;
+  cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr, ev_int0 = nullptr, ev_int1 = nullptr;
+  double acc_int_ms = 0, acc_step_ms = 0;
+  uint64_t acc_steps = 0, acc_launches = 0;
+  bool ev_pending = false;
+  uint64_t last_int_bytes = 0, last_step_bytes = 0;
+  uint64_t launches = 0;
+};
+
+void jb_set_error(const std::string& msg);

@@ -1,0 +1,697 @@
+// Hand-written sm_100a kernels of the JUNE per-timestep hot path.
+//
+//   k_place          ActivityManager.move_people_to_active_subgroups   (activity_manager.py:255-402)
+//   k_groups_thread  Interaction.time_step_for_group, small groups     (interaction.py:516-641)
+//   k_groups_warp    same, one warp per group (companies, schools, hospitals, care homes, ...)
+//   k_newinf         InfectionSelector._make_infection                 (infection_selector.py:146-332)
+//   k_health         Epidemiology.update_health_status                 (epidemiology.py:217-303)
+//   k_halo_pack/unpack, k_halo_return   MovablePeople exchange         (mpi_wrapper.py:145-293)
+//
+// All of them are HBM-bound streams / gathers of byte, int and fp64 data: there is no dense
+// contraction anywhere (largest "matrix" is a <=60x60 lookup), so no tensor cores are used.
+#pragma once
+#include <math.h>
+
+#include "jb_internal.cuh"
+#include "jb_rng.cuh"
+
+#define JB_FULL 0xFFFFFFFFu
+
+// ------------------------------------------------------------------------------------------
+// Stage A: placement.  One thread per resident.  The reference walks the activity hierarchy
+// and takes the first activity with a non-None subgroup (activity_manager.py:380-398); stay-home
+// policies reduce the activity list to (medical_facility, residence)
+// (individual_policies.py:87-119).  Here the chosen activity is written into the low bits of the
+// person's state byte; fixed-membership subgroups test that byte instead of being scattered
+// into.  People whose subgroup is dynamic (hospital patients) are appended to the dynamic list.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_place(uint8_t* __restrict__ pstate, const uint8_t* __restrict__ phas, const int32_t* __restrict__ pmed,
+        uint64_t* __restrict__ dyn_key, uint32_t dyn_cap, uint32_t* __restrict__ counters, uint32_t N,
+        uint32_t activity_mask, uint32_t flags) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  uint32_t st = pstate[p];
+  uint32_t act = JB_ACT_NONE;
+  if (!(st & JB_PS_DEAD)) {
+    uint32_t allowed = activity_mask;
+    if ((flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE))
+      allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
+    uint32_t has = phas[p];
+    if (st & JB_PS_MEDICAL) has |= 1u << JB_ACT_MEDICAL;
+    uint32_t cand = allowed & has;
+    if (cand) {
+      act = __ffs(cand) - 1;  // hierarchy order == bit order
+      if (act == JB_ACT_MEDICAL) {
+        uint32_t med = (uint32_t)pmed[p];  // (hospital group << 8) | local subgroup
+        uint32_t i = atomicAdd(&counters[CNT_DYN], 1u);
+        if (i < dyn_cap)
+          dyn_key[i] = ((uint64_t)(med >> 8) << 36) | ((uint64_t)(med & 0xFFu) << 28) | (uint64_t)p;
+        else
+          atomicAdd(&counters[CNT_OVERFLOW], 1u);
+      }
+    } else {
+      atomicAdd(&counters[CNT_NOACT], 1u);
+    }
+  }
+  pstate[p] = (uint8_t)((st & ~JB_PS_ACT_MASK) | act);
+}
+
+// Per-group offsets into the sorted dynamic-member list (lower bound of group g).
+__global__ void k_dyn_offsets(const uint64_t* __restrict__ key, uint32_t n_cap, const uint32_t* __restrict__ counters,
+                              uint32_t* __restrict__ dyn_off, uint32_t g0, uint32_t g1) {
+  uint32_t g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > g1) return;
+  uint32_t n = min(counters[CNT_DYN], n_cap);
+  uint64_t target = (uint64_t)g << 36;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (key[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  dyn_off[g] = lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage B: interaction.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t jb_gid(const GroupArgs& a, uint32_t p) {
+  return p < a.N ? a.gid_base + p : a.halo_gid[p - a.N];
+}
+
+// Append one new infection.
+__device__ __forceinline__ void jb_emit(const GroupArgs& a, uint32_t p, uint32_t v) {
+  uint32_t i = atomicAdd(&a.counters[CNT_NEWINF], 1u);
+  if (i < a.newinf_cap) {
+    a.newinf_member[i] = p;
+    a.newinf_var[i] = (uint8_t)v;
+  } else {
+    atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+  }
+}
+
+// Bernoulli draw + variant choice for one susceptible (interaction.py:610-641).
+template <int VM>
+__device__ __forceinline__ void jb_draw(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
+                                        uint32_t ordinal) {
+  double u;
+  if (a.inject) {
+    u = ordinal < a.n_inject ? a.inject[ordinal] : 2.0;
+  } else {
+    u = jb_bernoulli_uniform(a.seed, a.step, jb_gid(a, p));
+  }
+  if (a.lambda) a.lambda[p] = lam;
+  if (u < 1.0 - exp(-lam)) {
+    uint32_t v = 0;
+    if (VM > 1 && a.V > 1) {
+      // np.random.choice(ids, p=lam_v/lam): inverse CDF on a second, independent uniform
+      double u2 = jb_variant_uniform(a.seed, a.step, jb_gid(a, p)) * lam;
+      double c = 0.0;
+      v = a.V - 1;
+      for (int k = 0; k < a.V; ++k) {
+        c += lam_v[k];
+        if (u2 < c) { v = k; break; }
+      }
+    }
+    jb_emit(a, p, v);
+  }
+}
+
+// One thread per group: fixed contact matrix with dim <= 4, static members only (households).
+// Sums run left to right in member order, exactly like the reference's Python `sum`
+// (interaction.py:463-467).
+template <int VM>
+__global__ void __launch_bounds__(256) k_groups_thread(const __grid_constant__ GroupArgs a) {
+  uint32_t g = a.g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.g1) return;
+  const uint32_t b = a.grp_off[g], e = a.grp_off[g + 1];
+  int n[4] = {0, 0, 0, 0};
+  double T[VM][4];
+#pragma unroll
+  for (int v = 0; v < VM; ++v)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) T[v][k] = 0.0;
+  int nsus = 0, ninf = 0;
+  for (uint32_t m = b; m < e; ++m) {
+    uint32_t p = a.reg_member[m];
+    uint32_t info = a.reg_info[m];
+    uint32_t st = a.pstate[p];
+    if ((st & JB_PS_ACT_MASK) != JB_INFO_ACT(info)) continue;
+    int l = JB_INFO_LSG(info);
+    if (st & JB_PS_INFECTED) {
+      double t = a.trans[p];
+      int v = (VM > 1) ? a.pvar[p] : 0;
+      ++ninf;
+#pragma unroll
+      for (int vv = 0; vv < VM; ++vv)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (vv == v && k == l) T[vv][k] += t;
+    } else {
+      ++nsus;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n[k] += (k == l);
+  }
+  const bool must = nsus > 0 && ninf > 0;  // interactive.py:136
+  if (a.mode == 1) {
+    a.draw_cnt[g] = must ? nsus : 0;
+    return;
+  }
+  if (!must) return;
+  const uint32_t gi = a.grp_info[g];
+  const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+  double row[VM][4];
+#pragma unroll
+  for (int v = 0; v < VM; ++v) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double s = 0.0;
+      if (i < a.dim) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < a.dim && T[v][j] != 0.0) {
+            int nn = (i == j) ? max(1, n[j] - 1) : n[j];  // interaction.py:469-471
+            s += a.cm[i * a.dim + j] * T[v][j] / (double)nn * beta * a.dt;
+          }
+        }
+      }
+      row[v][i] = s;
+    }
+  }
+  uint32_t ord = a.inject ? a.draw_base[g] : 0u;
+  for (uint32_t m = b; m < e; ++m) {
+    uint32_t p = a.reg_member[m];
+    uint32_t info = a.reg_info[m];
+    uint32_t st = a.pstate[p];
+    if ((st & JB_PS_ACT_MASK) != JB_INFO_ACT(info)) continue;
+    if (st & JB_PS_INFECTED) continue;
+    int l = JB_INFO_LSG(info);
+    double lam_v[VM];
+    double lam = 0.0;
+#pragma unroll
+    for (int v = 0; v < VM; ++v) {
+      double r = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k == l) r = row[v][k];
+      double s = (v < a.V) ? a.susc[(size_t)v * a.NP + p] : 0.0;
+      lam_v[v] = r * s;
+      lam += lam_v[v];
+    }
+    jb_draw<VM>(a, p, lam_v, lam, ord);
+    ++ord;
+  }
+  atomicAdd(&a.counters[CNT_DRAWS], (uint32_t)nsus);
+}
+
+// ---- warp-per-group kernel ---------------------------------------------------------------
+// Contact matrix element for (susceptible subgroup i, infector subgroup j).
+__device__ __forceinline__ double jb_cm_elem(const GroupArgs& a, int i, int j, const uint8_t* years, int n_years) {
+  if (a.kind == JB_KIND_MATRIX) return a.cm[i * a.dim + j];
+  // school.py:462-485 on the 32x32 table built by school.py:424-460
+  const double* c = a.cm;
+  if (i == j) return i != 0 ? c[1 * JB_SCHOOL_DIM + 1] : c[0];
+  if (i == 0) return c[0 * JB_SCHOOL_DIM + 1] / (double)n_years;
+  if (j == 0) return c[1 * JB_SCHOOL_DIM + 0] / (double)n_years;
+  int yi = years[i - 1] + 1, yj = years[j - 1] + 1;
+  double x = c[yi * JB_SCHOOL_DIM + yj];
+  return yi == yj ? x / 4.0 : x;
+}
+
+// Inclusive segmented scan over a warp for keys that are contiguous (sorted) in lane order.
+template <typename Tv>
+__device__ __forceinline__ Tv jb_seg_scan(Tv val, uint32_t key, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    Tv up = __shfl_up_sync(JB_FULL, val, off);
+    uint32_t kup = __shfl_up_sync(JB_FULL, key, off);
+    if (lane >= off && kup == key) val += up;
+  }
+  return val;
+}
+
+struct JbMember {
+  uint32_t p, lsg;
+  bool present, infected;
+};
+
+// Member `idx` of group (static registered slots first, then the sorted dynamic members).
+__device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t idx, uint32_t b, uint32_t ns,
+                                                   uint32_t db, uint32_t ntot) {
+  JbMember mbr;
+  mbr.p = 0; mbr.lsg = 0xFFFFu; mbr.present = false; mbr.infected = false;
+  if (idx >= ntot) return mbr;
+  uint32_t st;
+  if (idx < ns) {
+    uint32_t m = b + idx;
+    mbr.p = a.reg_member[m];
+    uint32_t info = a.reg_info[m];
+    st = a.pstate[mbr.p];
+    mbr.lsg = JB_INFO_LSG(info);
+    mbr.present = (st & JB_PS_ACT_MASK) == JB_INFO_ACT(info);
+  } else {
+    uint64_t k = a.dyn_key[db + (idx - ns)];
+    mbr.p = (uint32_t)(k & 0x0FFFFFFFull);
+    mbr.lsg = (uint32_t)((k >> 28) & 0xFFull);
+    st = a.pstate[mbr.p];
+    mbr.present = true;
+  }
+  mbr.infected = (st & JB_PS_INFECTED) != 0;
+  return mbr;
+}
+
+// Shared memory per warp: n[L] u32 | sus_static[L] u32 | sus_dyn[L] u32 | pad | T[V*L] f64 | row[V*L] f64
+__host__ __device__ inline size_t jb_warp_smem_bytes(int L, int V) {
+  size_t ints = ((size_t)3 * L + 1) & ~(size_t)1;
+  return ints * 4 + (size_t)2 * V * L * 8;
+}
+
+template <int VM>
+__global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ GroupArgs a) {
+  extern __shared__ __align__(8) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t g = a.g0 + blockIdx.x * (blockDim.x >> 5) + wib;
+  if (g >= a.g1) return;
+  const int L = a.L, V = (VM > 1) ? a.V : 1;
+  unsigned char* base = smem_raw + (size_t)wib * jb_warp_smem_bytes(L, V);
+  uint32_t* n_l = (uint32_t*)base;
+  uint32_t* ss_l = n_l + L;   // susceptibles among static members, per subgroup
+  uint32_t* sd_l = ss_l + L;  // susceptibles among dynamic members
+  double* T_l = (double*)(base + ((((size_t)3 * L + 1) & ~(size_t)1) * 4));
+  double* row_l = T_l + (size_t)V * L;
+
+  const uint32_t b = a.grp_off[g], ns = a.grp_off[g + 1] - b;
+  uint32_t db = 0, nd = 0;
+  if (a.dyn_off) { db = a.dyn_off[g]; nd = a.dyn_off[g + 1] - db; }
+  const uint32_t ntot = ns + nd;
+  if (ntot == 0) {
+    if (a.mode == 1 && lane == 0) a.draw_cnt[g] = 0;
+    return;
+  }
+  // number of local subgroups of this group
+  int Lg = a.dim;
+  const uint8_t* years = nullptr;
+  int n_years = 0;
+  if (a.kind == JB_KIND_SCHOOL) {
+    uint32_t aux = a.grp_aux[g];
+    n_years = aux & 0xFFu;
+    years = a.school_years + (aux >> 8);
+    Lg = n_years + 1;
+  }
+  for (int i = lane; i < Lg; i += 32) {
+    n_l[i] = 0; ss_l[i] = 0; sd_l[i] = 0;
+    for (int v = 0; v < V; ++v) T_l[v * L + i] = 0.0;
+  }
+  __syncwarp();
+
+  // ---- pass 1: subgroup sizes and summed transmission probabilities ----------------------
+  // Static and dynamic members are walked in separate batches so that the subgroup keys stay
+  // sorted inside every 32-wide batch (needed by the segmented scan).
+  uint32_t nsus = 0, ninf = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    const uint32_t lo = phase ? ns : 0u, hi = phase ? ntot : ns;
+    for (uint32_t it = lo; it < hi; it += 32) {
+      const uint32_t idx = it + lane;
+      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, db, ntot);
+      const uint32_t key = mb.lsg;
+      const uint32_t sus = (mb.present && !mb.infected) ? 1u : 0u;
+      uint32_t packed = (mb.present ? 1u : 0u) | (sus << 16);
+      packed = jb_seg_scan<uint32_t>(packed, key, lane);
+      const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
+      const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
+      if (tail) {
+        n_l[key] += packed & 0xFFFFu;
+        if (phase == 0) ss_l[key] += packed >> 16; else sd_l[key] += packed >> 16;
+      }
+      nsus += __popc(__ballot_sync(JB_FULL, sus));
+      const bool inf = mb.present && mb.infected;
+      const uint32_t infm = __ballot_sync(JB_FULL, inf);
+      ninf += __popc(infm);
+      if (infm) {
+        const double t = inf ? a.trans[mb.p] : 0.0;
+        const int pv = (VM > 1 && inf) ? a.pvar[mb.p] : 0;
+        for (int v = 0; v < V; ++v) {
+          double tv = (pv == v) ? t : 0.0;
+          tv = jb_seg_scan<double>(tv, key, lane);
+          if (tail) T_l[v * L + key] += tv;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  const bool must = nsus > 0 && ninf > 0;
+  if (a.mode == 1) {
+    if (lane == 0) a.draw_cnt[g] = must ? nsus : 0;
+    return;
+  }
+  if (!must) return;
+
+  // ---- infector tensor row sums (interaction.py:451-478, :619) ---------------------------
+  const uint32_t gi = a.grp_info[g];
+  const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+  for (int i = lane; i < Lg; i += 32) {
+    for (int v = 0; v < V; ++v) {
+      double s = 0.0;
+      for (int j = 0; j < Lg; ++j) {
+        double t = T_l[v * L + j];
+        if (t != 0.0) {
+          int nj = (int)n_l[j];
+          int nn = (i == j) ? max(1, nj - 1) : nj;
+          s += jb_cm_elem(a, i, j, years, n_years) * t / (double)nn * beta * a.dt;
+        }
+      }
+      row_l[v * L + i] = s;
+    }
+  }
+  __syncwarp();
+  // injected-uniform ordinals: susceptibles are numbered subgroup by subgroup, static members
+  // before dynamic ones (interactive.py:86-131 dict insertion order)
+  uint32_t ord_base = 0;
+  if (a.inject) {
+    ord_base = a.draw_base[g];
+    if (lane == 0) {
+      uint32_t run = 0;
+      for (int i = 0; i < Lg; ++i) {
+        uint32_t s_ = ss_l[i], d_ = sd_l[i];
+        ss_l[i] = run; run += s_;
+        sd_l[i] = run; run += d_;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- pass 2: one Bernoulli draw per susceptible ----------------------------------------
+  for (int phase = 0; phase < 2; ++phase) {
+    const uint32_t lo = phase ? ns : 0u, hi = phase ? ntot : ns;
+    uint32_t* run = phase ? sd_l : ss_l;
+    for (uint32_t it = lo; it < hi; it += 32) {
+      const uint32_t idx = it + lane;
+      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, db, ntot);
+      const bool sus = mb.present && !mb.infected && mb.lsg < (uint32_t)Lg;
+      uint32_t ordinal = 0;
+      if (a.inject) {
+        const uint32_t key = mb.lsg;
+        const uint32_t incl = jb_seg_scan<uint32_t>(sus ? 1u : 0u, key, lane);
+        const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
+        const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
+        if (sus) ordinal = ord_base + run[key] + incl - 1;
+        __syncwarp();
+        if (tail) run[key] += incl;
+        __syncwarp();
+      }
+      if (sus) {
+        double lam_v[VM];
+        double lam = 0.0;
+#pragma unroll
+        for (int v = 0; v < VM; ++v) {
+          double r = 0.0, s = 0.0;
+          if (v < V) { r = row_l[v * L + mb.lsg]; s = a.susc[(size_t)v * a.NP + mb.p]; }
+          lam_v[v] = r * s;
+          lam += lam_v[v];
+        }
+        jb_draw<VM>(a, mb.p, lam_v, lam, ordinal);
+      }
+    }
+  }
+  if (lane == 0) atomicAdd(&a.counters[CNT_DRAWS], nsus);
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage C1: create infections (InfectionSelector._make_infection).
+// ------------------------------------------------------------------------------------------
+struct NewInfArgs {
+  const uint32_t* member;   // person indices (local, or >= N for halo: skipped here)
+  const uint8_t* variant;
+  const uint32_t* count_dev;  // number of entries (device) or null -> count_host
+  uint32_t count_host;
+  uint32_t cap;
+  uint32_t N, NP, C;
+  int V;
+  uint32_t gid_base;
+  double now;
+  uint64_t seed;
+  uint32_t step;
+  const uint8_t* age; const uint8_t* sex; const uint8_t* ch;
+  const double* hi_cum;
+  const DiseaseDev* dis;
+  uint8_t* pstate; uint8_t* pvar; int8_t* ptag; double* susc; double* trans; int32_t* pslot;
+  int32_t* inf_person; double* inf_start; double* inf_par; double* inf_next; double* traj_time;
+  uint8_t* inf_stage; uint8_t* inf_nst; uint8_t* inf_var; int8_t* inf_tag; int8_t* inf_maxtag; int8_t* traj_tag;
+  uint32_t* counters;
+  uint8_t* halo_ret;        // per halo person: variant+1 if infected here (or null)
+};
+
+__global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a) {
+  const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap) : a.count_host;
+  const DiseaseDev& D = *a.dis;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = a.member[i];
+    const uint32_t var = a.variant ? a.variant[i] : 0u;
+    if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
+      if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
+      atomicAdd(&a.counters[CNT_HALO_INF], 1u);
+      continue;
+    }
+    uint32_t st = a.pstate[p];
+    if (st & (JB_PS_INFECTED | JB_PS_DEAD)) continue;  // cannot happen within a step; guards seeding
+    const uint32_t slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);
+    if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
+    JbStream rs;
+    jb_stream_init(rs, a.seed, a.step, a.gid_base + p, JB_STREAM_NEWINF);
+    // symptoms: max_severity -> outcome slot (symptoms.py:47,110-120; health_index.py:151-182)
+    const double max_sev = jb_stream_next(rs);
+    const int age = a.age[p] > 99 ? 99 : a.age[p];
+    const int pop = (a.ch[p] && age >= 50) ? 1 : 0;
+    const double* cum = a.hi_cum + ((size_t)(pop * 2 + a.sex[p]) * 100 + age) * D.n_tags;
+    int idx = 0;
+    while (idx < D.n_tags && cum[idx] < max_sev) ++idx;  // np.searchsorted(side="left")
+    if (idx >= D.n_tags) idx = D.n_tags - 1;  // residual mass of a cumsum ending at 1-eps
+    int k = 0;
+    for (int t = 0; t < D.n_traj; ++t)
+      if (D.traj_max_tag[t] == idx) k = t;
+    // trajectory: cumulative stage start times (trajectory_maker.py:215-227)
+    const int nst = D.traj_n_stages[k];
+    double cumt = 0.0, t_exposed = 0.0;
+    for (int s = 0; s < JB_MAX_STAGES; ++s) {
+      double tt = 1e300;
+      int tg = 0;
+      if (s < nst) {
+        tt = cumt;
+        tg = D.traj_stage_tag[k][s];
+        cumt += jb_sample_dist(rs, D.traj_stage_time[k][s].type, D.traj_stage_time[k][s].p);
+      }
+      if (s == 1) t_exposed = tt;
+      a.traj_time[(size_t)s * a.C + slot] = tt;
+      a.traj_tag[(size_t)s * a.C + slot] = (int8_t)tg;
+    }
+    // transmission (infection_selector.py:280-332)
+    double par[JB_N_TPAR] = {0, 0, 0, 0, 0};
+    if (D.trans_type == JB_TRANS_GAMMA) {
+      double max_inf = jb_sample_dist(rs, D.trans_par[0].type, D.trans_par[0].p);
+      double shape = jb_sample_dist(rs, D.trans_par[1].type, D.trans_par[1].p);
+      double rate = jb_sample_dist(rs, D.trans_par[2].type, D.trans_par[2].p);
+      double shift = jb_sample_dist(rs, D.trans_par[3].type, D.trans_par[3].p) + t_exposed;
+      par[0] = shape; par[1] = shift; par[2] = 1.0 / rate; par[3] = max_inf;
+    } else if (D.trans_type == JB_TRANS_XNEXP) {
+      double tfi = jb_sample_dist(rs, D.trans_par[1].type, D.trans_par[1].p) + t_exposed;
+      double peak = t_exposed - tfi + jb_sample_dist(rs, D.trans_par[2].type, D.trans_par[2].p);
+      double maxp = jb_sample_dist(rs, D.trans_par[0].type, D.trans_par[0].p);
+      double norm_time = jb_sample_dist(rs, D.trans_par[4].type, D.trans_par[4].p);
+      double nn = peak / jb_sample_dist(rs, D.trans_par[3].type, D.trans_par[3].p);
+      double alpha = jb_sample_dist(rs, D.trans_par[3].type, D.trans_par[3].p);
+      double max_tau = nn * alpha * norm_time / norm_time;  // transmission_xnexp.py:119-121
+      par[0] = nn; par[1] = alpha; par[2] = tfi; par[4] = norm_time;
+      par[3] = maxp / (pow(max_tau, nn) * exp(-max_tau / alpha));
+    } else {
+      par[0] = jb_sample_dist(rs, D.trans_par[0].type, D.trans_par[0].p);
+    }
+    for (int q = 0; q < JB_N_TPAR; ++q) a.inf_par[(size_t)q * a.C + slot] = par[q];
+    a.inf_person[slot] = (int32_t)p;
+    a.inf_start[slot] = a.now;
+    a.inf_next[slot] = a.traj_time[(size_t)1 * a.C + slot];
+    a.inf_stage[slot] = 0;
+    a.inf_nst[slot] = (uint8_t)nst;
+    a.inf_var[slot] = (uint8_t)var;
+    a.inf_tag[slot] = (int8_t)D.tag_exposed;
+    a.inf_maxtag[slot] = (int8_t)idx;
+    a.pslot[p] = (int32_t)slot;
+    a.pvar[p] = (uint8_t)var;
+    a.ptag[p] = (int8_t)D.tag_exposed;
+    a.trans[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
+    // immunity.add_immunity(infection.immunity_ids()) (infection_selector.py:160-162)
+    for (int v = 0; v < a.V; ++v) a.susc[(size_t)v * a.NP + p] = 0.0;
+    a.pstate[p] = (uint8_t)(st | JB_PS_INFECTED);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage C2: health update for every active infection slot (epidemiology.py:217-303).
+// ------------------------------------------------------------------------------------------
+struct HealthArgs {
+  uint32_t C;
+  double t_now;       // timer.now + timer.duration
+  uint32_t flags;
+  const DiseaseDev* dis;
+  int32_t* inf_person; const double* inf_start; const double* inf_par; double* inf_next; const double* traj_time;
+  uint8_t* inf_stage; const uint8_t* inf_nst; int8_t* inf_tag; const int8_t* traj_tag;
+  uint8_t* pstate; int8_t* ptag; double* trans; int32_t* pmed; int32_t* pslot; uint8_t* phas;
+  const uint32_t* psa; const int32_t* sa_hospital;
+  uint32_t* counters;
+};
+
+__device__ __forceinline__ double jb_gamma_pdf(double x, double a, double loc, double scale) {
+  // transmission.py:47-75
+  if (x < loc) return 0.0;
+  double z = (x - loc) / scale;
+  return 1.0 / tgamma(a) * pow(z, a - 1.0) * exp(-z) / scale;
+}
+
+__global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthArgs a) {
+  const uint32_t hw = min(a.counters[CNT_SLOTS_HW], a.C);
+  const DiseaseDev& D = *a.dis;
+  uint32_t c_inf = 0, c_hosp = 0, c_icu = 0;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < hw; s += gridDim.x * blockDim.x) {
+    const int32_t p = a.inf_person[s];
+    if (p < 0) continue;
+    const double t = a.t_now - a.inf_start[s];
+    // transmission.update_infection_probability (infection.py:91)
+    double prob;
+    if (D.trans_type == JB_TRANS_GAMMA) {
+      prob = a.inf_par[(size_t)3 * a.C + s] *
+             jb_gamma_pdf(t, a.inf_par[s], a.inf_par[(size_t)1 * a.C + s], a.inf_par[(size_t)2 * a.C + s]);
+      a.trans[p] = prob;
+    } else if (D.trans_type == JB_TRANS_XNEXP) {
+      double tfi = a.inf_par[(size_t)2 * a.C + s];
+      prob = 0.0;
+      if (t > tfi) {
+        double tau = (t - tfi) / a.inf_par[(size_t)4 * a.C + s];
+        prob = a.inf_par[(size_t)3 * a.C + s] * (pow(tau, a.inf_par[s]) * exp(-tau / a.inf_par[(size_t)1 * a.C + s]));
+      }
+      a.trans[p] = prob;
+    }
+    // symptoms.update_trajectory_stage: at most one stage per call (symptoms.py:152-154)
+    int stage = a.inf_stage[s];
+    int tag = a.inf_tag[s];
+    const int nst = a.inf_nst[s];
+    if (stage + 1 < nst && t > a.inf_next[s]) {
+      ++stage;
+      tag = a.traj_tag[(size_t)stage * a.C + s];
+      a.inf_stage[s] = (uint8_t)stage;
+      a.inf_tag[s] = (int8_t)tag;
+      a.inf_next[s] = (stage + 1 < JB_MAX_STAGES) ? a.traj_time[(size_t)(stage + 1) * a.C + s] : 1e300;
+    }
+    const int bit = JB_TAG_BIT(tag);
+    uint32_t st = a.pstate[p];
+    // Hospitalisation.apply (medical_care_policies.py:413-526; hospital.py:62-122)
+    if (a.flags & JB_STEP_HOSPITALISATION) {
+      if (bit & D.hosp_mask) {
+        int32_t hg;
+        if (st & JB_PS_MEDICAL) hg = a.pmed[p] >> 8; else hg = a.sa_hospital[a.psa[p]];
+        if (hg >= 0) {
+          int lsg = (bit & D.icu_mask) ? 2 : 1;
+          a.pmed[p] = (hg << 8) | lsg;
+          st |= JB_PS_MEDICAL;
+        }
+      } else if ((st & JB_PS_MEDICAL) && !(bit & D.dead_mask)) {
+        a.pmed[p] = -1;
+        st &= ~JB_PS_MEDICAL;
+      }
+    }
+    if (bit & D.severe_mask) st |= JB_PS_SEVERE; else st &= ~JB_PS_SEVERE;
+    if (bit & D.rec_mask) {  // Epidemiology.recover (epidemiology.py:197-215)
+      st &= ~(JB_PS_INFECTED | JB_PS_SEVERE);
+      a.inf_person[s] = -1;
+      a.pslot[p] = -1;
+      a.trans[p] = 0.0;
+      atomicAdd(&a.counters[CNT_RECOVERED_STEP], 1u);
+    } else if (bit & D.dead_mask) {  // bury_the_dead (epidemiology.py:168-195)
+      st &= ~(JB_PS_INFECTED | JB_PS_SEVERE | JB_PS_MEDICAL);
+      st |= JB_PS_DEAD;
+      a.inf_person[s] = -1;
+      a.pslot[p] = -1;
+      a.pmed[p] = -1;
+      a.phas[p] = 0;
+      a.trans[p] = 0.0;
+      atomicAdd(&a.counters[CNT_DEATHS_STEP], 1u);
+      atomicAdd(&a.counters[CNT_DEAD_TOTAL], 1u);
+    } else {
+      ++c_inf;
+      if (st & JB_PS_MEDICAL) { ++c_hosp; if (bit & D.icu_mask) ++c_icu; }
+    }
+    a.ptag[p] = (int8_t)tag;
+    a.pstate[p] = (uint8_t)st;
+  }
+  // block-level reduction of the "current" counters
+  c_inf = __reduce_add_sync(JB_FULL, c_inf);
+  c_hosp = __reduce_add_sync(JB_FULL, c_hosp);
+  c_icu = __reduce_add_sync(JB_FULL, c_icu);
+  if ((threadIdx.x & 31) == 0) {
+    if (c_inf) atomicAdd(&a.counters[CNT_INFECTED], c_inf);
+    if (c_hosp) atomicAdd(&a.counters[CNT_HOSP], c_hosp);
+    if (c_icu) atomicAdd(&a.counters[CNT_ICU], c_icu);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Halo exchange kernels (the device form of MovablePeople, mpi_wrapper.py:145-293).
+// Record: 8 bytes header {pstate, variant, 6 pad} + max(1,V) doubles
+// (infected: [0] = transmission probability; else: susceptibility per variant).
+// ------------------------------------------------------------------------------------------
+__global__ void k_halo_pack(const uint32_t* __restrict__ out_person, uint32_t n_out, const uint8_t* __restrict__ pstate,
+                            const uint8_t* __restrict__ pvar, const double* __restrict__ susc,
+                            const double* __restrict__ trans, uint32_t NP, int V, unsigned char* __restrict__ send) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  uint32_t p = out_person[i];
+  size_t rec = 8 + (size_t)8 * V;
+  unsigned char* r = send + (size_t)i * rec;
+  uint32_t st = pstate[p];
+  uint64_t hdr = (uint64_t)st | ((uint64_t)pvar[p] << 8);
+  *(uint64_t*)r = hdr;
+  double* d = (double*)(r + 8);
+  if (st & JB_PS_INFECTED) {
+    d[0] = trans[p];
+    for (int v = 1; v < V; ++v) d[v] = 0.0;
+  } else {
+    for (int v = 0; v < V; ++v) d[v] = susc[(size_t)v * NP + p];
+  }
+}
+
+__global__ void k_halo_unpack(const unsigned char* __restrict__ recv, uint32_t H, uint32_t N, uint32_t NP, int V,
+                              uint8_t* __restrict__ pstate, uint8_t* __restrict__ pvar, double* __restrict__ susc,
+                              double* __restrict__ trans, uint8_t* __restrict__ halo_ret) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H) return;
+  size_t rec = 8 + (size_t)8 * V;
+  const unsigned char* r = recv + (size_t)j * rec;
+  uint64_t hdr = *(const uint64_t*)r;
+  const double* d = (const double*)(r + 8);
+  uint32_t p = N + j;
+  uint32_t st = (uint32_t)(hdr & 0xFFu);
+  pstate[p] = (uint8_t)st;
+  pvar[p] = (uint8_t)((hdr >> 8) & 0xFFu);
+  if (st & JB_PS_INFECTED) {
+    trans[p] = d[0];
+  } else {
+    for (int v = 0; v < V; ++v) susc[(size_t)v * NP + p] = d[v];
+  }
+  if (halo_ret) halo_ret[j] = 0;
+}
+
+// Returned bytes (variant+1 per outbound slot) -> list of residents to infect.
+__global__ void k_halo_return(const uint8_t* __restrict__ ret, const uint32_t* __restrict__ out_person, uint32_t n_out,
+                              uint32_t* __restrict__ member, uint8_t* __restrict__ variant, uint32_t cap,
+                              uint32_t* __restrict__ counter) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  uint32_t v = ret[i];
+  if (!v) return;
+  uint32_t k = atomicAdd(counter, 1u);
+  if (k < cap) { member[k] = out_person[i]; variant[k] = (uint8_t)(v - 1); }
+}
+
+__global__ void k_fill_f64(double* x, size_t n, double v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}

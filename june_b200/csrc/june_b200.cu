@@ -1,0 +1,759 @@
+// libjune_b200.so -- C ABI (include/june_b200.h) over the kernels in jb_kernels.cuh.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "jb_kernels.cuh"
+
+static thread_local std::string g_err;
+void jb_set_error(const std::string& msg) { g_err = msg; }
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      jb_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+      return JB_ECUDA;                                                                        \
+    }                                                                                         \
+  } while (0)
+
+#define REQUIRE(cond, msg)                                                                    \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      jb_set_error(msg);                                                                      \
+      return JB_EINVAL;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void**)p, n * sizeof(T)));
+  return JB_OK;
+}
+template <typename T>
+static int dev_upload(T** p, const T* src, size_t n, cudaStream_t s) {
+  int rc = dev_alloc(p, n);
+  if (rc) return rc;
+  if (n && src) CK(cudaMemcpyAsync(*p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  return JB_OK;
+}
+#define TRY(x)            \
+  do {                    \
+    int rc_ = (x);        \
+    if (rc_) return rc_;  \
+  } while (0)
+
+extern "C" const char* jb_last_error(void) { return g_err.c_str(); }
+extern "C" int jb_abi_version(void) { return JB_ABI_VERSION; }
+extern "C" int jb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+extern "C" size_t jb_halo_record_size(void) { return 0; }  // depends on V: see jb_halo_record_size_w
+extern "C" size_t jb_halo_return_size(void) { return 1; }
+extern "C" size_t jb_halo_record_size_w(JbWorld* w) { return 8 + (size_t)8 * w->V; }
+
+static void copy_disease(const JbDisease& d, DiseaseDev& o) {
+  memset(&o, 0, sizeof(o));
+  o.n_tags = d.n_tags;
+  o.rec_mask = d.tag_recovered_mask;
+  o.dead_mask = d.tag_dead_mask;
+  o.hosp_mask = d.tag_hospital_mask;
+  o.icu_mask = d.tag_icu_mask;
+  o.severe_mask = d.tag_severe_mask;
+  o.tag_exposed = d.tag_exposed;
+  o.n_traj = d.n_traj;
+  for (int k = 0; k < 16; ++k) {
+    o.traj_max_tag[k] = d.traj_max_tag[k];
+    o.traj_n_stages[k] = d.traj_n_stages[k];
+    for (int s = 0; s < JB_MAX_STAGES; ++s) {
+      o.traj_stage_tag[k][s] = d.traj_stage_tag[k][s];
+      o.traj_stage_time[k][s] = d.traj_stage_time[k][s];
+    }
+  }
+  o.trans_type = d.trans_type;
+  for (int k = 0; k < 6; ++k) o.trans_par[k] = d.trans_par[k];
+}
+
+extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) {
+  if (!d || !out) { jb_set_error("null argument"); return JB_EINVAL; }
+  *out = nullptr;
+  REQUIRE(d->abi_version == JB_ABI_VERSION, "ABI version mismatch");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    jb_set_error("no CUDA device: june_b200 has no CPU fallback");
+    return JB_ENOGPU;
+  }
+  REQUIRE(device >= 0 && device < ndev, "bad device index");
+  REQUIRE(d->n_variants >= 1 && d->n_variants <= JB_MAX_VARIANTS, "n_variants out of range");
+  REQUIRE(d->n_supergroups >= 1 && d->n_supergroups <= JB_MAX_SUPERGROUPS, "n_supergroups out of range");
+  REQUIRE(d->n_people + (uint64_t)d->n_halo < (1ull << 28), "n_people + n_halo must be < 2^28");
+  REQUIRE(d->n_groups < (1u << 23), "n_groups must be < 2^23 per domain");
+  REQUIRE(d->disease.n_tags >= 1 && d->disease.n_tags <= 16 && d->disease.n_traj >= 1 && d->disease.n_traj <= 16,
+          "disease table sizes out of range");
+  CK(cudaSetDevice(device));
+  JbWorld* w = new JbWorld();
+  w->device = device;
+  CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  cudaStream_t s = w->stream;
+  w->N = d->n_people; w->H = d->n_halo; w->NP = w->N + w->H; w->G = d->n_groups; w->M = d->n_members;
+  w->V = d->n_variants; w->R = std::max(1u, d->n_regions); w->SA = d->n_super_areas;
+  w->n_beta = d->n_beta; w->n_scale = d->n_scale; w->id_base = d->person_id_base;
+  w->C = d->slot_capacity ? d->slot_capacity : std::max(1u, w->N);
+  w->newinf_cap = d->newinf_capacity ? d->newinf_capacity : std::max(1u, w->NP);
+  w->sgs.assign(d->supergroups, d->supergroups + d->n_supergroups);
+  copy_disease(d->disease, w->dis_host);
+
+  // validate supergroups + compute the max local-subgroup count (shared-memory sizing)
+  std::vector<uint8_t> years(d->school_years, d->school_years + d->n_school_years);
+  uint32_t expect = 0;
+  for (size_t k = 0; k < w->sgs.size(); ++k) {
+    const JbSupergroup& sg = w->sgs[k];
+    REQUIRE(sg.first_group == expect, "supergroups must tile the group range contiguously");
+    expect += sg.n_groups;
+    int L = sg.dim;
+    if (sg.kind == JB_KIND_SCHOOL) {
+      REQUIRE(sg.dim == JB_SCHOOL_DIM, "school supergroup needs the 32x32 table");
+      L = 1;
+      for (uint32_t g = sg.first_group; g < sg.first_group + sg.n_groups; ++g) {
+        uint32_t aux = d->grp_aux[g];
+        L = std::max<int>(L, (int)(aux & 0xFF) + 1);
+        REQUIRE((aux >> 8) + (aux & 0xFF) <= d->n_school_years, "school years out of range");
+      }
+    } else {
+      REQUIRE(sg.dim >= 1 && sg.dim <= JB_MAX_DIM, "contact matrix dimension out of range");
+      if (sg.launch_mode == 0) REQUIRE(sg.dim <= 4 && !sg.has_dynamic, "thread-per-group mode needs dim<=4, static members");
+    }
+    REQUIRE(sg.cm_offset >= 0 && (uint32_t)(sg.cm_offset + sg.dim * sg.dim) <= d->n_cm_doubles, "cm offset out of range");
+    REQUIRE(sg.activity >= 0 && sg.activity < JB_N_ACT, "bad supergroup activity");
+    w->sg_L.push_back(L);
+    if (sg.has_dynamic) w->any_dynamic = true;
+  }
+  REQUIRE(expect == w->G, "supergroups do not cover all groups");
+
+  TRY(dev_upload(&w->age, d->age, w->N, s));
+  TRY(dev_upload(&w->sex, d->sex, w->N, s));
+  TRY(dev_upload(&w->ch, d->care_home_resident, w->N, s));
+  TRY(dev_upload(&w->phas, d->has_activity, w->N, s));
+  TRY(dev_upload(&w->psa, d->super_area, w->N, s));
+  TRY(dev_upload(&w->sa_hospital, d->sa_hospital, w->SA, s));
+  TRY(dev_upload(&w->sa_region, d->sa_region, w->SA, s));
+  TRY(dev_upload(&w->grp_off, d->grp_offset, (size_t)w->G + 1, s));
+  TRY(dev_upload(&w->grp_info, d->grp_info, w->G, s));
+  TRY(dev_upload(&w->grp_aux, d->grp_aux, w->G, s));
+  TRY(dev_upload(&w->reg_member, d->reg_member, w->M, s));
+  TRY(dev_upload(&w->reg_info, d->reg_info, w->M, s));
+  TRY(dev_upload(&w->school_years, d->school_years, d->n_school_years, s));
+  TRY(dev_upload(&w->cm, d->cm, d->n_cm_doubles, s));
+  TRY(dev_upload(&w->beta_scale, d->beta_scale, d->n_scale, s));
+  TRY(dev_upload(&w->hi_cum, d->disease.health_index_cum, (size_t)400 * d->disease.n_tags, s));
+  TRY(dev_upload(&w->dis, &w->dis_host, 1, s));
+
+  TRY(dev_alloc(&w->pstate, w->NP));
+  TRY(dev_alloc(&w->pvar, w->NP));
+  TRY(dev_alloc(&w->ptag, w->N));
+  TRY(dev_alloc(&w->susc, (size_t)w->V * w->NP));
+  TRY(dev_alloc(&w->trans, w->NP));
+  TRY(dev_alloc(&w->pmed, w->N));
+  TRY(dev_alloc(&w->pslot, w->N));
+  TRY(dev_alloc(&w->halo_gid, w->H));
+  CK(cudaMemsetAsync(w->pstate, JB_ACT_NONE, w->NP, s));
+  CK(cudaMemsetAsync(w->pvar, 0, w->NP, s));
+  CK(cudaMemsetAsync(w->ptag, 0xFF, w->N, s));  // -1 = healthy
+  CK(cudaMemsetAsync(w->trans, 0, (size_t)w->NP * 8, s));
+  CK(cudaMemsetAsync(w->pmed, 0xFF, (size_t)w->N * 4, s));
+  CK(cudaMemsetAsync(w->pslot, 0xFF, (size_t)w->N * 4, s));
+  CK(cudaMemsetAsync(w->halo_gid, 0, (size_t)std::max(1u, w->H) * 4, s));
+  {
+    size_t n = (size_t)w->V * w->NP;
+    k_fill_f64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w->susc, n, 1.0);
+  }
+  const size_t C = w->C;
+  TRY(dev_alloc(&w->inf_person, C));
+  TRY(dev_alloc(&w->inf_start, C));
+  TRY(dev_alloc(&w->inf_par, C * JB_N_TPAR));
+  TRY(dev_alloc(&w->inf_next, C));
+  TRY(dev_alloc(&w->traj_time, C * JB_MAX_STAGES));
+  TRY(dev_alloc(&w->inf_stage, C));
+  TRY(dev_alloc(&w->inf_nst, C));
+  TRY(dev_alloc(&w->inf_var, C));
+  TRY(dev_alloc(&w->inf_tag, C));
+  TRY(dev_alloc(&w->inf_maxtag, C));
+  TRY(dev_alloc(&w->traj_tag, C * JB_MAX_STAGES));
+  CK(cudaMemsetAsync(w->inf_person, 0xFF, C * 4, s));
+
+  TRY(dev_alloc(&w->counters, CNT_N));
+  CK(cudaMemsetAsync(w->counters, 0, CNT_N * 4, s));
+  TRY(dev_alloc(&w->newinf_member, w->newinf_cap));
+  TRY(dev_alloc(&w->newinf_var, w->newinf_cap));
+  TRY(dev_alloc(&w->beta, (size_t)w->n_beta * w->R));
+  TRY(dev_alloc(&w->draw_cnt, (size_t)w->G + 1));
+  TRY(dev_alloc(&w->draw_base, (size_t)w->G + 1));
+  if (w->any_dynamic) {
+    w->dyn_cap = std::max<uint32_t>(4096u, w->N / 32);
+    TRY(dev_alloc(&w->dyn_key, w->dyn_cap));
+    TRY(dev_alloc(&w->dyn_key_alt, w->dyn_cap));
+    TRY(dev_alloc(&w->dyn_off, (size_t)w->G + 2));
+  }
+  {
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b1, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)std::max(1u, w->dyn_cap), 0, 64, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(w->G + 1), s);
+    w->cub_tmp_bytes = std::max(b1, b2) + 256;
+    CK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
+  }
+  CK(cudaMallocHost((void**)&w->h_beta, sizeof(double) * std::max<size_t>(1, (size_t)w->n_beta * w->R)));
+  CK(cudaMallocHost((void**)&w->h_counters, sizeof(uint32_t) * CNT_N));
+  CK(cudaEventCreate(&w->ev_step0));
+  CK(cudaEventCreate(&w->ev_step1));
+  CK(cudaEventCreate(&w->ev_int0));
+  CK(cudaEventCreate(&w->ev_int1));
+  // the warp kernel may need > 48 KB of dynamic shared memory for very large schools
+  CK(cudaFuncSetAttribute(k_groups_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups_warp<JB_MAX_VARIANTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaStreamSynchronize(s));
+  *out = w;
+  return JB_OK;
+}
+
+extern "C" void jb_world_destroy(JbWorld* w) {
+  if (!w) return;
+  cudaSetDevice(w->device);
+  cudaStreamSynchronize(w->stream);
+  void* ptrs[] = {w->age, w->sex, w->ch, w->phas, w->school_years, w->psa, w->grp_off, w->grp_info, w->grp_aux,
+                  w->reg_member, w->reg_info, w->sa_region, w->sa_hospital, w->cm, w->beta_scale, w->hi_cum, w->dis,
+                  w->pstate, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
+                  w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
+                  w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->counters, w->newinf_member, w->newinf_var,
+                  w->beta, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_key, w->dyn_key_alt, w->dyn_off,
+                  w->cub_tmp};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (w->h_beta) cudaFreeHost(w->h_beta);
+  if (w->h_counters) cudaFreeHost(w->h_counters);
+  if (w->ev_step0) cudaEventDestroy(w->ev_step0);
+  if (w->ev_step1) cudaEventDestroy(w->ev_step1);
+  if (w->ev_int0) cudaEventDestroy(w->ev_int0);
+  if (w->ev_int1) cudaEventDestroy(w->ev_int1);
+  cudaStreamDestroy(w->stream);
+  delete w;
+}
+
+extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const double* susceptibility) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  if (pstate) CK(cudaMemcpyAsync(w->pstate, pstate, w->N, cudaMemcpyHostToDevice, w->stream));
+  if (susceptibility)
+    for (uint32_t v = 0; v < w->V; ++v)
+      CK(cudaMemcpyAsync(w->susc + (size_t)v * w->NP, susceptibility + (size_t)v * w->N, (size_t)w->N * 8,
+                         cudaMemcpyHostToDevice, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  return JB_OK;
+}
+
+extern "C" int jb_inject_uniforms(JbWorld* w, const double* u, size_t n) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  if (n > w->inject_cap) {
+    CK(cudaStreamSynchronize(w->stream));
+    if (w->inject) cudaFree(w->inject);
+    w->inject_cap = n + n / 2 + 16;
+    CK(cudaMalloc((void**)&w->inject, w->inject_cap * 8));
+  }
+  if (n) CK(cudaMemcpyAsync(w->inject, u, n * 8, cudaMemcpyHostToDevice, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  w->n_inject = n;
+  return JB_OK;
+}
+
+static NewInfArgs make_newinf_args(JbWorld* w) {
+  NewInfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = w->N; a.NP = w->NP; a.C = w->C; a.V = (int)w->V; a.gid_base = (uint32_t)w->id_base;
+  a.age = w->age; a.sex = w->sex; a.ch = w->ch; a.hi_cum = w->hi_cum; a.dis = w->dis;
+  a.pstate = w->pstate; a.pvar = w->pvar; a.ptag = w->ptag; a.susc = w->susc; a.trans = w->trans; a.pslot = w->pslot;
+  a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
+  a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_var = w->inf_var;
+  a.inf_tag = w->inf_tag; a.inf_maxtag = w->inf_maxtag; a.traj_tag = w->traj_tag; a.counters = w->counters;
+  return a;
+}
+
+extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* variants, size_t n, double time,
+                         uint64_t seed, uint32_t step) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  if (n == 0) return JB_OK;
+  CK(cudaSetDevice(w->device));
+  uint32_t* d_p = nullptr;
+  uint8_t* d_v = nullptr;
+  std::vector<uint8_t> v8(n, 0);
+  for (size_t i = 0; i < n; ++i) {
+    REQUIRE(persons[i] < w->N, "jb_infect: person index out of range");
+    if (variants) { REQUIRE(variants[i] < w->V, "jb_infect: variant out of range"); v8[i] = (uint8_t)variants[i]; }
+  }
+  TRY(dev_upload(&d_p, persons, n, w->stream));
+  TRY(dev_upload(&d_v, v8.data(), n, w->stream));
+  NewInfArgs a = make_newinf_args(w);
+  a.member = d_p; a.variant = d_v; a.count_dev = nullptr; a.count_host = (uint32_t)n; a.cap = (uint32_t)n;
+  a.now = time; a.seed = seed; a.step = step;
+  unsigned blocks = (unsigned)std::min<size_t>((n + 127) / 128, 148 * 8);
+  k_newinf<<<blocks, 128, 0, w->stream>>>(a);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(w->stream));
+  cudaFree(d_p);
+  cudaFree(d_v);
+  return JB_OK;
+}
+
+extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size_t n) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  if (n == 0) return JB_OK;
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  uint32_t hw = 0;
+  CK(cudaMemcpy(&hw, w->counters + CNT_SLOTS_HW, 4, cudaMemcpyDeviceToHost));
+  REQUIRE((size_t)hw + n <= w->C, "jb_upload_infections: slot capacity exceeded");
+  const size_t C = w->C;
+  // Host-side scatter through small staging vectors (cold path: seeding / checkpoint restore / tests).
+  std::vector<int32_t> person(n);
+  std::vector<double> start(n), next(n), par(n * JB_N_TPAR), tt(n * JB_MAX_STAGES);
+  std::vector<uint8_t> stage(n), nst(n), var(n);
+  std::vector<int8_t> tag(n), maxtag(n), ttag(n * JB_MAX_STAGES);
+  for (size_t i = 0; i < n; ++i) {
+    const JbInfectionRow& r = rows[i];
+    REQUIRE(r.person < w->N, "jb_upload_infections: person out of range");
+    REQUIRE(r.n_stages >= 1 && r.n_stages <= JB_MAX_STAGES && r.stage >= 0 && r.stage < r.n_stages, "bad stages");
+    REQUIRE(r.variant < w->V, "bad variant");
+    person[i] = (int32_t)r.person; start[i] = r.start_time;
+    stage[i] = (uint8_t)r.stage; nst[i] = (uint8_t)r.n_stages; var[i] = (uint8_t)r.variant;
+    tag[i] = (int8_t)r.tag; maxtag[i] = (int8_t)r.max_tag;
+    next[i] = (r.stage + 1 < r.n_stages) ? r.traj_time[r.stage + 1] : 1e300;
+    for (int q = 0; q < JB_N_TPAR; ++q) par[(size_t)q * n + i] = r.tpar[q];
+    for (int q = 0; q < JB_MAX_STAGES; ++q) {
+      tt[(size_t)q * n + i] = q < r.n_stages ? r.traj_time[q] : 1e300;
+      ttag[(size_t)q * n + i] = q < r.n_stages ? (int8_t)r.traj_tag[q] : 0;
+    }
+  }
+  CK(cudaMemcpy(w->inf_person + hw, person.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->inf_start + hw, start.data(), n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->inf_next + hw, next.data(), n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->inf_stage + hw, stage.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->inf_nst + hw, nst.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->inf_var + hw, var.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->inf_tag + hw, tag.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->inf_maxtag + hw, maxtag.data(), n, cudaMemcpyHostToDevice));
+  for (int q = 0; q < JB_N_TPAR; ++q)
+    CK(cudaMemcpy(w->inf_par + (size_t)q * C + hw, par.data() + (size_t)q * n, n * 8, cudaMemcpyHostToDevice));
+  for (int q = 0; q < JB_MAX_STAGES; ++q) {
+    CK(cudaMemcpy(w->traj_time + (size_t)q * C + hw, tt.data() + (size_t)q * n, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->traj_tag + (size_t)q * C + hw, ttag.data() + (size_t)q * n, n, cudaMemcpyHostToDevice));
+  }
+  // per-person side: element-wise copies (cold path)
+  for (size_t i = 0; i < n; ++i) {
+    const JbInfectionRow& r = rows[i];
+    uint8_t st = 0;
+    CK(cudaMemcpy(&st, w->pstate + r.person, 1, cudaMemcpyDeviceToHost));
+    st |= JB_PS_INFECTED;
+    if (JB_TAG_BIT(r.tag) & w->dis_host.severe_mask) st |= JB_PS_SEVERE;
+    CK(cudaMemcpy(w->pstate + r.person, &st, 1, cudaMemcpyHostToDevice));
+    int32_t slot = (int32_t)(hw + i);
+    int8_t tg = (int8_t)r.tag;
+    uint8_t vr = (uint8_t)r.variant;
+    double zero = 0.0;
+    CK(cudaMemcpy(w->pslot + r.person, &slot, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->ptag + r.person, &tg, 1, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->pvar + r.person, &vr, 1, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->trans + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
+    for (uint32_t v = 0; v < w->V; ++v)
+      CK(cudaMemcpy(w->susc + (size_t)v * w->NP + r.person, &zero, 8, cudaMemcpyHostToDevice));
+  }
+  hw += (uint32_t)n;
+  CK(cudaMemcpy(w->counters + CNT_SLOTS_HW, &hw, 4, cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
+extern "C" int jb_set_halo(JbWorld* w, const uint32_t* out_person, size_t n_out) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  for (size_t i = 0; i < n_out; ++i) REQUIRE(out_person[i] < w->N, "jb_set_halo: person out of range");
+  if (w->out_person) cudaFree(w->out_person);
+  TRY(dev_upload(&w->out_person, out_person, n_out, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  w->n_out = (uint32_t)n_out;
+  return JB_OK;
+}
+
+extern "C" int jb_set_halo_gids(JbWorld* w, const uint32_t* gids, size_t n) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(n == w->H, "jb_set_halo_gids: need n_halo entries");
+  CK(cudaSetDevice(w->device));
+  if (n) CK(cudaMemcpy(w->halo_gid, gids, n * 4, cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
+// ---- the step ----------------------------------------------------------------------------
+static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
+  GroupArgs a;
+  memset(&a, 0, sizeof(a));
+  const JbStepParams& p = w->cur;
+  a.grp_off = w->grp_off; a.grp_info = w->grp_info; a.grp_aux = w->grp_aux;
+  a.reg_member = w->reg_member; a.reg_info = w->reg_info;
+  a.pstate = w->pstate; a.pvar = w->pvar; a.susc = w->susc; a.trans = w->trans; a.halo_gid = w->halo_gid;
+  a.school_years = w->school_years; a.cm = w->cm + sg.cm_offset; a.beta = w->beta; a.beta_scale = w->beta_scale;
+  a.dyn_key = sg.has_dynamic ? w->dyn_key : nullptr;
+  a.dyn_off = sg.has_dynamic ? w->dyn_off : nullptr;
+  a.g0 = sg.first_group; a.g1 = sg.first_group + sg.n_groups;
+  a.dim = sg.dim; a.kind = sg.kind; a.L = L;
+  a.N = w->N; a.NP = w->NP; a.V = (int)w->V; a.R = (int)w->R;
+  a.dt = p.delta_time; a.seed = p.seed; a.step = p.step; a.gid_base = (uint32_t)w->id_base;
+  a.counters = w->counters; a.newinf_member = w->newinf_member; a.newinf_var = w->newinf_var;
+  a.newinf_cap = w->newinf_cap;
+  a.lambda = (p.flags & JB_STEP_RECORD_LAMBDA) ? w->lambda : nullptr;
+  if (p.flags & JB_STEP_INJECT_UNIFORMS) {
+    a.inject = w->inject; a.n_inject = (uint32_t)w->n_inject; a.draw_base = w->draw_base;
+  }
+  a.draw_cnt = w->draw_cnt;
+  a.mode = 0;
+  return a;
+}
+
+static int launch_groups(JbWorld* w, int mode) {
+  for (size_t k = 0; k < w->sgs.size(); ++k) {
+    const JbSupergroup& sg = w->sgs[k];
+    if (sg.n_groups == 0) continue;
+    if (!(w->cur.activity_mask & (1u << sg.activity))) continue;
+    GroupArgs a = make_group_args(w, sg, w->sg_L[k]);
+    a.mode = mode;
+    if (sg.launch_mode == 0) {
+      unsigned blocks = (sg.n_groups + 255) / 256;
+      if (w->V == 1) k_groups_thread<1><<<blocks, 256, 0, w->stream>>>(a);
+      else k_groups_thread<JB_MAX_VARIANTS><<<blocks, 256, 0, w->stream>>>(a);
+    } else {
+      const int wpb = 4;
+      size_t smem = jb_warp_smem_bytes(a.L, (int)w->V) * wpb;
+      unsigned blocks = (sg.n_groups + wpb - 1) / wpb;
+      if (w->V == 1) k_groups_warp<1><<<blocks, wpb * 32, smem, w->stream>>>(a);
+      else k_groups_warp<JB_MAX_VARIANTS><<<blocks, wpb * 32, smem, w->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    w->launches++;
+  }
+  return JB_OK;
+}
+
+extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
+  if (!w || !p) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(!w->in_step, "jb_step_begin: previous step not finished");
+  REQUIRE(p->beta != nullptr, "JbStepParams.beta is null");
+  REQUIRE(p->delta_time > 0.0, "delta_time must be positive");
+  CK(cudaSetDevice(w->device));
+  cudaStream_t s = w->stream;
+  w->cur = *p;
+  if (w->timing) {
+    if (w->ev_pending) {
+      CK(cudaEventSynchronize(w->ev_step1));
+      float a = 0, b = 0;
+      CK(cudaEventElapsedTime(&a, w->ev_int0, w->ev_int1));
+      CK(cudaEventElapsedTime(&b, w->ev_step0, w->ev_step1));
+      w->acc_int_ms += a; w->acc_step_ms += b; w->acc_steps++;
+      w->ev_pending = false;
+    }
+    CK(cudaEventRecord(w->ev_step0, s));
+  }
+  memcpy(w->h_beta, p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
+  CK(cudaMemcpyAsync(w->beta, w->h_beta, sizeof(double) * (size_t)w->n_beta * w->R, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(w->counters, 0, CNT_STEP_END * 4, s));
+  if (w->any_dynamic) CK(cudaMemsetAsync(w->dyn_key, 0xFF, (size_t)w->dyn_cap * 8, s));
+  if (p->flags & JB_STEP_RECORD_LAMBDA) {
+    if (!w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
+    k_fill_f64<<<(w->NP + 255) / 256, 256, 0, s>>>(w->lambda, w->NP, std::numeric_limits<double>::quiet_NaN());
+    w->launches++;
+  }
+  if (w->N) {
+    k_place<<<(w->N + 255) / 256, 256, 0, s>>>(w->pstate, w->phas, w->pmed, w->dyn_key, w->dyn_cap, w->counters,
+                                               w->N, p->activity_mask, p->flags);
+    CK(cudaGetLastError());
+    w->launches++;
+  }
+  if (w->n_out && d_send) {
+    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->pstate, w->pvar, w->susc, w->trans,
+                                                       w->NP, (int)w->V, (unsigned char*)d_send);
+    CK(cudaGetLastError());
+    w->launches++;
+  }
+  w->in_step = true;
+  return JB_OK;
+}
+
+extern "C" int jb_step_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(w->in_step, "jb_step_interact without jb_step_begin");
+  CK(cudaSetDevice(w->device));
+  cudaStream_t s = w->stream;
+  const JbStepParams& p = w->cur;
+  if (w->H && d_recv) {
+    k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
+                                                     w->pstate, w->pvar, w->susc, w->trans, (uint8_t*)d_ret_send);
+    CK(cudaGetLastError());
+    w->launches++;
+  }
+  if (w->any_dynamic) {
+    size_t tmp = w->cub_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortKeys(w->cub_tmp, tmp, w->dyn_key, w->dyn_key_alt, (int)w->dyn_cap, 0, 64, s));
+    std::swap(w->dyn_key, w->dyn_key_alt);
+    w->launches += 4;
+    for (const JbSupergroup& sg : w->sgs) {
+      if (!sg.has_dynamic || !sg.n_groups) continue;
+      k_dyn_offsets<<<(sg.n_groups + 1 + 127) / 128, 128, 0, s>>>(w->dyn_key, w->dyn_cap, w->counters, w->dyn_off,
+                                                                 sg.first_group, sg.first_group + sg.n_groups);
+      CK(cudaGetLastError());
+      w->launches++;
+    }
+  }
+  if (w->timing) CK(cudaEventRecord(w->ev_int0, s));
+  if (p.flags & JB_STEP_INJECT_UNIFORMS) {
+    CK(cudaMemsetAsync(w->draw_cnt, 0, ((size_t)w->G + 1) * 4, s));
+    TRY(launch_groups(w, 1));
+    size_t tmp = w->cub_tmp_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->draw_cnt, w->draw_base, (int)(w->G + 1), s));
+    w->launches += 2;
+  }
+  TRY(launch_groups(w, 0));
+  if (w->timing) CK(cudaEventRecord(w->ev_int1, s));
+  // create infections for residents infected here; flag halo persons for their home domain
+  if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS) || w->H) {
+    NewInfArgs a = make_newinf_args(w);
+    a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_NEWINF;
+    a.cap = w->newinf_cap; a.now = p.now; a.seed = p.seed; a.step = p.step;
+    a.halo_ret = (uint8_t*)d_ret_send;
+    if (p.flags & JB_STEP_NO_NEW_INFECTIONS) a.N = 0;  // only route halo infections
+    k_newinf<<<148 * 2, 128, 0, s>>>(a);
+    CK(cudaGetLastError());
+    w->launches++;
+  }
+  return JB_OK;
+}
+
+extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* out) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(w->in_step, "jb_step_finish without jb_step_begin");
+  CK(cudaSetDevice(w->device));
+  cudaStream_t s = w->stream;
+  const JbStepParams& p = w->cur;
+  if (w->n_out && d_ret_recv) {
+    // residents infected abroad: reuse the tail of the new-infection list
+    // (tell_domains_to_infect, epidemiology.py:359-401)
+    uint32_t* member = w->newinf_member;
+    uint8_t* variant = w->newinf_var;
+    CK(cudaMemsetAsync(w->counters + CNT_HALO_INF, 0, 4, s));
+    k_halo_return<<<(w->n_out + 255) / 256, 256, 0, s>>>((const uint8_t*)d_ret_recv, w->out_person, w->n_out, member,
+                                                         variant, w->newinf_cap, w->counters + CNT_HALO_INF);
+    NewInfArgs a = make_newinf_args(w);
+    a.member = member; a.variant = variant; a.count_dev = w->counters + CNT_HALO_INF;
+    a.cap = w->newinf_cap; a.now = p.now; a.seed = p.seed; a.step = p.step;
+    if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS)) k_newinf<<<148, 128, 0, s>>>(a);
+    CK(cudaGetLastError());
+    w->launches += 2;
+  }
+  CK(cudaMemsetAsync(w->counters + CNT_INFECTED, 0, 3 * 4, s));
+  {
+    HealthArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C = w->C; a.t_now = p.now + p.delta_time; a.flags = p.flags; a.dis = w->dis;
+    a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
+    a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
+    a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
+    a.pslot = w->pslot; a.phas = w->phas; a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.counters = w->counters;
+    k_health<<<148 * 4, 256, 0, s>>>(a);
+    CK(cudaGetLastError());
+    w->launches++;
+  }
+  CK(cudaMemcpyAsync(w->h_counters, w->counters, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+  if (w->timing) { CK(cudaEventRecord(w->ev_step1, s)); w->ev_pending = true; }
+  w->in_step = false;
+  if (out) {
+    CK(cudaStreamSynchronize(s));
+    const uint32_t* c = w->h_counters;
+    memset(out, 0, sizeof(*out));
+    out->n_new_infections = c[CNT_NEWINF];
+    out->n_infected = c[CNT_INFECTED];
+    out->n_dead_total = c[CNT_DEAD_TOTAL];
+    out->n_recovered_step = c[CNT_RECOVERED_STEP];
+    out->n_deaths_step = c[CNT_DEATHS_STEP];
+    out->n_hospitalised = c[CNT_HOSP];
+    out->n_icu = c[CNT_ICU];
+    out->n_draws = c[CNT_DRAWS];
+    out->n_no_activity = c[CNT_NOACT];
+    out->n_slots_used = c[CNT_SLOTS_HW];
+    out->n_halo_infected = c[CNT_HALO_INF];
+    if (c[CNT_NOACT]) {
+      jb_set_error("Attention! Some people do not have an activity in this timestep.");
+      return JB_ENOACT;
+    }
+    if (c[CNT_OVERFLOW]) {
+      jb_set_error("a device buffer capacity was exceeded (dynamic members / new infections / slots)");
+      return JB_ECAP;
+    }
+  }
+  return JB_OK;
+}
+
+extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
+  TRY(jb_step_begin(w, p, nullptr));
+  TRY(jb_step_interact(w, nullptr, nullptr));
+  return jb_step_finish(w, nullptr, out);
+}
+
+extern "C" int jb_sync(JbWorld* w) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  return JB_OK;
+}
+
+extern "C" void* jb_stream_handle(JbWorld* w) { return w ? (void*)w->stream : nullptr; }
+
+// ---- readback ----------------------------------------------------------------------------
+extern "C" int jb_fetch_new_infections(JbWorld* w, uint32_t* member, uint32_t* variant, size_t cap, size_t* n) {
+  if (!w || !n) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  uint32_t cnt = 0;
+  CK(cudaMemcpy(&cnt, w->counters + CNT_NEWINF, 4, cudaMemcpyDeviceToHost));
+  cnt = std::min(cnt, w->newinf_cap);
+  *n = cnt;
+  REQUIRE(cnt <= cap, "jb_fetch_new_infections: caller buffer too small");
+  if (cnt == 0) return JB_OK;
+  std::vector<uint32_t> m(cnt);
+  std::vector<uint8_t> v(cnt);
+  CK(cudaMemcpy(m.data(), w->newinf_member, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(v.data(), w->newinf_var, cnt, cudaMemcpyDeviceToHost));
+  // the device appends in arbitrary order: return sorted by member index
+  std::vector<uint32_t> order(cnt);
+  for (uint32_t i = 0; i < cnt; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return m[x] < m[y]; });
+  for (uint32_t i = 0; i < cnt; ++i) {
+    member[i] = m[order[i]];
+    if (variant) variant[i] = v[order[i]];
+  }
+  return JB_OK;
+}
+
+extern "C" int jb_fetch_person_state(JbWorld* w, uint8_t* pstate, int8_t* tag, double* trans_prob,
+                                     double* susceptibility, int32_t* medical) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  if (pstate) CK(cudaMemcpy(pstate, w->pstate, w->N, cudaMemcpyDeviceToHost));
+  if (tag) CK(cudaMemcpy(tag, w->ptag, w->N, cudaMemcpyDeviceToHost));
+  if (trans_prob) CK(cudaMemcpy(trans_prob, w->trans, (size_t)w->N * 8, cudaMemcpyDeviceToHost));
+  if (susceptibility)
+    for (uint32_t v = 0; v < w->V; ++v)
+      CK(cudaMemcpy(susceptibility + (size_t)v * w->N, w->susc + (size_t)v * w->NP, (size_t)w->N * 8,
+                    cudaMemcpyDeviceToHost));
+  if (medical) CK(cudaMemcpy(medical, w->pmed, (size_t)w->N * 4, cudaMemcpyDeviceToHost));
+  return JB_OK;
+}
+
+extern "C" int jb_fetch_lambda(JbWorld* w, double* out) {
+  if (!w || !out) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(w->lambda != nullptr, "no step ran with JB_STEP_RECORD_LAMBDA");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  CK(cudaMemcpy(out, w->lambda, (size_t)w->NP * 8, cudaMemcpyDeviceToHost));
+  return JB_OK;
+}
+
+extern "C" int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap, size_t* n) {
+  if (!w || !n) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  uint32_t hw = 0;
+  CK(cudaMemcpy(&hw, w->counters + CNT_SLOTS_HW, 4, cudaMemcpyDeviceToHost));
+  hw = std::min<uint32_t>(hw, w->C);
+  const size_t C = w->C;
+  std::vector<int32_t> person(hw);
+  std::vector<double> start(hw), par((size_t)hw * JB_N_TPAR), tt((size_t)hw * JB_MAX_STAGES), trans(w->N);
+  std::vector<uint8_t> stage(hw), nst(hw), var(hw);
+  std::vector<int8_t> tag(hw), maxtag(hw), ttag((size_t)hw * JB_MAX_STAGES);
+  if (hw) {
+    CK(cudaMemcpy(person.data(), w->inf_person, (size_t)hw * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(start.data(), w->inf_start, (size_t)hw * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(stage.data(), w->inf_stage, hw, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nst.data(), w->inf_nst, hw, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(var.data(), w->inf_var, hw, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tag.data(), w->inf_tag, hw, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(maxtag.data(), w->inf_maxtag, hw, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < JB_N_TPAR; ++q)
+      CK(cudaMemcpy(par.data() + (size_t)q * hw, w->inf_par + (size_t)q * C, (size_t)hw * 8, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < JB_MAX_STAGES; ++q) {
+      CK(cudaMemcpy(tt.data() + (size_t)q * hw, w->traj_time + (size_t)q * C, (size_t)hw * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(ttag.data() + (size_t)q * hw, w->traj_tag + (size_t)q * C, hw, cudaMemcpyDeviceToHost));
+    }
+    CK(cudaMemcpy(trans.data(), w->trans, (size_t)w->N * 8, cudaMemcpyDeviceToHost));
+  }
+  size_t k = 0;
+  for (uint32_t s = 0; s < hw; ++s) {
+    if (person[s] < 0) continue;
+    if (k < cap && rows) {
+      JbInfectionRow& r = rows[k];
+      memset(&r, 0, sizeof(r));
+      r.person = (uint32_t)person[s]; r.variant = var[s]; r.start_time = start[s];
+      for (int q = 0; q < JB_N_TPAR; ++q) r.tpar[q] = par[(size_t)q * hw + s];
+      r.probability = trans[person[s]];
+      r.n_stages = nst[s]; r.stage = stage[s]; r.max_tag = maxtag[s]; r.tag = tag[s];
+      for (int q = 0; q < JB_MAX_STAGES; ++q) { r.traj_time[q] = tt[(size_t)q * hw + s]; r.traj_tag[q] = ttag[(size_t)q * hw + s]; }
+    }
+    ++k;
+  }
+  *n = k;
+  REQUIRE(!rows || k <= cap, "jb_fetch_infections: caller buffer too small");
+  if (rows) std::sort(rows, rows + k, [](const JbInfectionRow& a, const JbInfectionRow& b) { return a.person < b.person; });
+  return JB_OK;
+}
+
+extern "C" int jb_fetch_summary(JbWorld* w, uint32_t* counts) {
+  if (!w || !counts) { jb_set_error("null argument"); return JB_EINVAL; }
+  jb_set_error("jb_fetch_summary: not implemented in this round");
+  return JB_EINVAL;
+}
+
+extern "C" int jb_timing_enable(JbWorld* w, int on) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  w->timing = on != 0;
+  return JB_OK;
+}
+
+extern "C" int jb_timing_read(JbWorld* w, double* interaction_ms, double* step_ms, uint64_t* n_steps,
+                              uint64_t* n_launches, int reset) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  if (w->ev_pending) {
+    CK(cudaEventSynchronize(w->ev_step1));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, w->ev_int0, w->ev_int1));
+    CK(cudaEventElapsedTime(&b, w->ev_step0, w->ev_step1));
+    w->acc_int_ms += a; w->acc_step_ms += b; w->acc_steps++;
+    w->ev_pending = false;
+  }
+  if (interaction_ms) *interaction_ms = w->acc_int_ms;
+  if (step_ms) *step_ms = w->acc_step_ms;
+  if (n_steps) *n_steps = w->acc_steps;
+  if (n_launches) *n_launches = w->launches;
+  if (reset) { w->acc_int_ms = w->acc_step_ms = 0; w->acc_steps = 0; w->launches = 0; }
+  return JB_OK;
+}
+
+extern "C" int jb_last_step_bytes(JbWorld* w, uint64_t* interaction_bytes, uint64_t* step_bytes) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  if (interaction_bytes) *interaction_bytes = w->last_int_bytes;
+  if (step_bytes) *step_bytes = w->last_step_bytes;
+  return JB_OK;
+}

@@ -1,0 +1,260 @@
+"""``DeviceWorld``: a world resident in HBM behind the C ABI of ``libjune_b200.so``.
+
+``Engine`` is the ABI-generic part (fills ``JbWorldDesc`` from numpy arrays and wraps every
+entry point); ``DeviceWorld`` binds it to the CUDA library.  The tests bind the same ``Engine``
+to the CPU oracle library, which exports the identical ABI with the ``jo_`` prefix.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (JbDisease, JbDist, JbInfectionRow, JbStepParams, JbStepStats, JbSupergroup, JbWorldDesc,
+                   SimulatorError, ptr)
+from .disease import DiseaseConfig, health_index_cum
+from .interaction import Interaction
+from .world import KIND_SCHOOL, MAX_STAGES, N_TPAR, SCHOOL_DIM, WorldSoA
+
+
+def fill_disease(dc: DiseaseConfig, hi_cum: np.ndarray) -> JbDisease:
+    d = JbDisease()
+    d.n_tags = dc.n_tags
+    d.tag_recovered_mask = dc.tag_mask("recovered_stage")
+    d.tag_dead_mask = dc.tag_mask("fatality_stage")
+    d.tag_hospital_mask = dc.tag_mask("hospitalised_stage")
+    d.tag_icu_mask = dc.tag_mask("intensive_care_stage")
+    d.tag_severe_mask = dc.tag_mask("severe_symptoms_stay_at_home_stage")
+    d.tag_exposed = dc.symptom_tags[dc.default_lowest_stage]
+    table = dc.trajectory_table()
+    assert len(table) <= 16
+    d.n_traj = len(table)
+    for k, (max_tag, stages) in enumerate(table):
+        d.traj_max_tag[k] = max_tag
+        d.traj_n_stages[k] = len(stages)
+        for s, (tag, code, p) in enumerate(stages):
+            d.traj_stage_tag[k][s] = tag
+            d.traj_stage_time[k][s].type = code
+            for q in range(4):
+                d.traj_stage_time[k][s].p[q] = p[q]
+    ttype, pars = dc.transmission_table()
+    d.trans_type = ttype
+    for k, (code, p) in enumerate(pars):
+        d.trans_par[k].type = code
+        for q in range(4):
+            d.trans_par[k].p[q] = p[q]
+    assert hi_cum.shape == (2, 2, 100, dc.n_tags) and hi_cum.dtype == np.float64
+    d.health_index_cum = hi_cum.ctypes.data
+    d.infection_id = dc.infection_id
+    return d
+
+
+class Engine:
+    """One world behind one ABI library."""
+
+    def __init__(self, lib, prefix: str, world: WorldSoA, interaction: Interaction, disease: DiseaseConfig,
+                 outcome_prob: np.ndarray, device: int = 0, n_variants: int = 1, slot_capacity: int = 0):
+        self._lib = lib
+        self._p = prefix
+        self.world = world
+        self.interaction = interaction
+        self.disease = disease
+        self.n_variants = n_variants
+        world.validate()
+        self._keep: List[object] = []
+        # contact matrices, one block per supergroup spec
+        cm_blocks, sgs = [], (JbSupergroup * len(world.supergroups))()
+        off = 0
+        for k, sg in enumerate(world.supergroups):
+            m = np.ascontiguousarray(interaction.contact_matrices[sg.spec], dtype=np.float64)
+            if sg.kind == KIND_SCHOOL:
+                assert m.shape == (SCHOOL_DIM, SCHOOL_DIM)
+            dim = m.shape[0]
+            sgs[k].first_group, sgs[k].n_groups = sg.first_group, sg.n_groups
+            sgs[k].kind, sgs[k].dim, sgs[k].cm_offset = sg.kind, dim, off
+            sgs[k].activity, sgs[k].launch_mode, sgs[k].has_dynamic = sg.activity, sg.launch_mode, sg.has_dynamic
+            cm_blocks.append(m.ravel())
+            off += dim * dim
+        cm = np.concatenate(cm_blocks) if cm_blocks else np.zeros(1)
+        self._hi = np.ascontiguousarray(health_index_cum(outcome_prob))
+        d = JbWorldDesc()
+        d.abi_version = _lib.ABI_VERSION
+        d.n_people, d.n_halo, d.n_groups, d.n_members = world.n_people, world.n_halo, world.n_groups, world.n_members
+        d.n_supergroups, d.n_regions, d.n_super_areas = len(world.supergroups), world.n_regions, world.n_super_areas
+        d.n_variants, d.n_beta, d.n_scale = n_variants, len(world.beta_rules), len(world.beta_scale)
+        d.n_cm_doubles, d.n_school_years = cm.size, world.school_years.size
+        d.slot_capacity, d.newinf_capacity = slot_capacity, 0
+        d.person_id_base = world.person_id_base
+        arrays = dict(
+            age=world.age, sex=world.sex, care_home_resident=world.care_home_resident,
+            has_activity=world.has_activity, super_area=world.super_area, sa_hospital=world.sa_hospital,
+            sa_region=world.sa_region, grp_offset=world.grp_offset, grp_info=world.grp_info, grp_aux=world.grp_aux,
+            reg_member=world.reg_member, reg_info=world.reg_info, school_years=world.school_years,
+            cm=cm, beta_scale=world.beta_scale)
+        for name, arr in arrays.items():
+            arr = np.ascontiguousarray(arr)
+            self._keep.append(arr)
+            setattr(d, name, arr.ctypes.data)
+        d.supergroups = C.addressof(sgs)
+        d.disease = fill_disease(disease, self._hi)
+        self._keep += [sgs, cm]
+        handle = C.c_void_p()
+        self._check(self._f("world_create")(C.byref(d), device, C.byref(handle)))
+        self._h = handle
+        if world.n_halo:
+            hg = np.ascontiguousarray(world.halo_gid, dtype=np.uint32)
+            self._check(self._f("set_halo_gids")(self._h, ptr(hg), hg.size))
+        if world.out_person.size:
+            op = np.ascontiguousarray(world.out_person, dtype=np.uint32)
+            self._check(self._f("set_halo")(self._h, ptr(op), op.size))
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _f(self, name):
+        return getattr(self._lib, self._p + name)
+
+    def _check(self, rc: int):
+        if rc == 0:
+            return
+        msg = self._f("last_error")().decode()
+        if rc in (_lib.JB_ENOACT, _lib.JB_ECAP):
+            raise SimulatorError(msg)
+        if rc == _lib.JB_ENOGPU:
+            raise RuntimeError(msg)
+        raise RuntimeError(f"{self._p}* call failed (code {rc}): {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._f("world_destroy")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ---- state -----------------------------------------------------------------------------------
+    def set_person_state(self, pstate: Optional[np.ndarray] = None, susceptibility: Optional[np.ndarray] = None):
+        if pstate is not None:
+            pstate = np.ascontiguousarray(pstate, dtype=np.uint8)
+            assert pstate.shape == (self.world.n_people,)
+        if susceptibility is not None:
+            susceptibility = np.ascontiguousarray(susceptibility, dtype=np.float64).reshape(self.n_variants, self.world.n_people)
+        self._check(self._f("set_person_state")(self._h, ptr(pstate), ptr(susceptibility)))
+
+    def inject_uniforms(self, u: np.ndarray):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        self._check(self._f("inject_uniforms")(self._h, ptr(u), u.size))
+
+    def infect(self, persons: Sequence[int], time: float, seed: int, step: int, variants: Optional[Sequence[int]] = None):
+        p = np.ascontiguousarray(persons, dtype=np.uint32)
+        v = None if variants is None else np.ascontiguousarray(variants, dtype=np.uint32)
+        self._check(self._f("infect")(self._h, ptr(p), ptr(v), p.size, float(time), int(seed), int(step)))
+
+    def upload_infections(self, rows: List[dict]):
+        arr = (JbInfectionRow * len(rows))()
+        for i, r in enumerate(rows):
+            a = arr[i]
+            a.person, a.variant, a.start_time = int(r["person"]), int(r.get("variant", 0)), float(r["start_time"])
+            for q in range(N_TPAR):
+                a.tpar[q] = float(r["tpar"][q]) if q < len(r["tpar"]) else 0.0
+            a.probability = float(r.get("probability", 0.0))
+            tt, tg = list(r["traj_time"]), list(r["traj_tag"])
+            a.n_stages, a.stage = len(tt), int(r.get("stage", 0))
+            a.max_tag, a.tag = int(r.get("max_tag", max(tg))), int(r.get("tag", tg[a.stage]))
+            for q in range(len(tt)):
+                a.traj_time[q], a.traj_tag[q] = float(tt[q]), int(tg[q])
+        self._check(self._f("upload_infections")(self._h, arr, len(rows)))
+
+    # ---- stepping --------------------------------------------------------------------------------
+    def make_params(self, now: float, delta_time: float, step: int, activity_mask: int, seed: int, flags: int,
+                    beta: np.ndarray) -> JbStepParams:
+        beta = np.ascontiguousarray(beta, dtype=np.float64)
+        assert beta.shape == (len(self.world.beta_rules), self.world.n_regions), beta.shape
+        p = JbStepParams()
+        p.now, p.delta_time, p.step, p.activity_mask = float(now), float(delta_time), int(step), int(activity_mask)
+        p.seed, p.flags = int(seed), int(flags)
+        p.beta = beta.ctypes.data
+        p._beta_keep = beta
+        return p
+
+    def step(self, params: JbStepParams, want_stats: bool = True) -> Optional[Dict[str, int]]:
+        stats = JbStepStats()
+        self._check(self._f("step")(self._h, C.byref(params), C.byref(stats) if want_stats else None))
+        return stats.as_dict() if want_stats else None
+
+    def step_begin(self, params: JbStepParams, d_send: int = 0):
+        self._check(self._f("step_begin")(self._h, C.byref(params), C.c_void_p(d_send or None)))
+
+    def step_interact(self, d_recv: int = 0, d_ret_send: int = 0):
+        self._check(self._f("step_interact")(self._h, C.c_void_p(d_recv or None), C.c_void_p(d_ret_send or None)))
+
+    def step_finish(self, d_ret_recv: int = 0, want_stats: bool = True) -> Optional[Dict[str, int]]:
+        stats = JbStepStats()
+        self._check(self._f("step_finish")(self._h, C.c_void_p(d_ret_recv or None), C.byref(stats) if want_stats else None))
+        return stats.as_dict() if want_stats else None
+
+    def sync(self):
+        self._check(self._f("sync")(self._h))
+
+    def halo_record_size(self) -> int:
+        return int(self._f("halo_record_size_w")(self._h))
+
+    # ---- readback --------------------------------------------------------------------------------
+    def fetch_new_infections(self) -> Tuple[np.ndarray, np.ndarray]:
+        cap = self.world.n_people + self.world.n_halo
+        m, v = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        n = C.c_size_t()
+        self._check(self._f("fetch_new_infections")(self._h, ptr(m), ptr(v), cap, C.byref(n)))
+        return m[: n.value].copy(), v[: n.value].copy()
+
+    def fetch_person_state(self) -> Dict[str, np.ndarray]:
+        n = self.world.n_people
+        out = dict(pstate=np.zeros(n, np.uint8), tag=np.zeros(n, np.int8), trans_prob=np.zeros(n, np.float64),
+                   susceptibility=np.zeros((self.n_variants, n), np.float64), medical=np.zeros(n, np.int32))
+        self._check(self._f("fetch_person_state")(self._h, ptr(out["pstate"]), ptr(out["tag"]), ptr(out["trans_prob"]),
+                                                  ptr(out["susceptibility"]), ptr(out["medical"])))
+        return out
+
+    def fetch_lambda(self) -> np.ndarray:
+        out = np.zeros(self.world.n_people + self.world.n_halo, np.float64)
+        self._check(self._f("fetch_lambda")(self._h, ptr(out)))
+        return out
+
+    def fetch_infections(self) -> List[dict]:
+        n = C.c_size_t()
+        self._check(self._f("fetch_infections")(self._h, None, 0, C.byref(n)))
+        arr = (JbInfectionRow * max(1, n.value))()
+        self._check(self._f("fetch_infections")(self._h, arr, n.value, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            a = arr[i]
+            ns = a.n_stages
+            out.append(dict(person=a.person, variant=a.variant, start_time=a.start_time, tpar=list(a.tpar),
+                            probability=a.probability, stage=a.stage, max_tag=a.max_tag, tag=a.tag,
+                            traj_time=list(a.traj_time)[:ns], traj_tag=list(a.traj_tag)[:ns]))
+        return out
+
+    def timing_enable(self, on: bool = True):
+        self._check(self._f("timing_enable")(self._h, 1 if on else 0))
+
+    def timing_read(self, reset: bool = False) -> Dict[str, float]:
+        a, b = C.c_double(), C.c_double()
+        n, l = C.c_uint64(), C.c_uint64()
+        self._check(self._f("timing_read")(self._h, C.byref(a), C.byref(b), C.byref(n), C.byref(l), 1 if reset else 0))
+        return dict(interaction_ms=a.value, step_ms=b.value, n_steps=n.value, n_launches=l.value)
+
+
+class DeviceWorld(Engine):
+    """World resident on one CUDA device (the product path; raises without the CUDA library/GPU)."""
+
+    def __init__(self, world: WorldSoA, interaction: Interaction, disease: DiseaseConfig, outcome_prob: np.ndarray,
+                 device: int = 0, n_variants: int = 1, slot_capacity: int = 0):
+        super().__init__(_lib.load(), "jb_", world, interaction, disease, outcome_prob, device=device,
+                         n_variants=n_variants, slot_capacity=slot_capacity)

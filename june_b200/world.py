@@ -1,0 +1,223 @@
+"""Device-facing struct-of-arrays description of a JUNE world (or of one domain of it).
+
+This is the host-side (numpy) form of ``JbWorldDesc`` in ``include/june_b200.h``: people,
+groups, and the registered membership CSR group -> (subgroup, member).  It replaces the object
+graph the reference hot path walks (``june/world.py:63-98``, ``june/groups/group/group.py:25``,
+``june/demography/person.py:35-81``).
+
+Index spaces
+------------
+* persons ``[0, n_people)`` live in this domain; ``[n_people, n_people + n_halo)`` are halo
+  persons (residents of another domain that are registered members of groups here; the device
+  form of the visitors in ``june/mpi_wrapper.py:169-190``).
+* groups are laid out supergroup after supergroup, in the order the reference iterates them in
+  ``Simulator.do_timestep`` (``june/simulator.py:399-455``): activity-hierarchy order
+  (``june/activity/activity_manager.py:24-33``), then the order of ``activity_to_super_groups``.
+* inside a group, registered members are sorted by (local subgroup index, person index), which
+  is the reference's traversal order of ``InteractiveGroup`` (``interactive.py:65-99``) when
+  people were appended in ``world.people`` order.
+"""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+# activity codes, hierarchy order (activity_manager.py:24-33)
+ACT_MEDICAL, ACT_COMMUTE, ACT_PRIMARY, ACT_LEISURE, ACT_RESIDENCE, ACT_NONE = 0, 1, 2, 3, 4, 7
+ACTIVITY_CODES = {
+    "medical_facility": ACT_MEDICAL,
+    "commute": ACT_COMMUTE,
+    "primary_activity": ACT_PRIMARY,
+    "leisure": ACT_LEISURE,
+    "residence": ACT_RESIDENCE,
+}
+ACTIVITY_NAMES = {v: k for k, v in ACTIVITY_CODES.items()}
+
+PS_ACT_MASK, PS_INFECTED, PS_DEAD, PS_SEVERE, PS_MEDICAL = 0x07, 0x08, 0x10, 0x20, 0x40
+
+KIND_MATRIX, KIND_SCHOOL = 0, 1
+SCHOOL_DIM = 32
+MAX_STAGES = 8
+N_TPAR = 5
+
+
+def make_info(lsg, act):
+    return (np.asarray(act, dtype=np.uint16) << 8) | np.asarray(lsg, dtype=np.uint16)
+
+
+def make_ginfo(beta_idx, scale_idx, region):
+    return (
+        np.asarray(beta_idx, dtype=np.uint32)
+        | (np.asarray(scale_idx, dtype=np.uint32) << 8)
+        | (np.asarray(region, dtype=np.uint32) << 16)
+    )
+
+
+@dataclass
+class Supergroup:
+    """One contiguous range of groups of the same spec (one reference ``Supergroup``)."""
+
+    name: str            # attribute name on the reference World ("households", "companies", ...)
+    spec: str            # group spec: key into Interaction.contact_matrices / betas
+    activity: int        # activity whose presence in timer.activities activates it
+    first_group: int
+    n_groups: int
+    kind: int = KIND_MATRIX
+    launch_mode: int = 1  # 0 thread per group, 1 warp per group
+    has_dynamic: int = 0
+
+    def to_json(self):
+        return dict(self.__dict__)
+
+
+@dataclass
+class BetaRule:
+    """How one row of the per-step beta table is computed (``get_processed_beta``)."""
+
+    key: str                       # e.g. "company", "secondary_school", "household"
+    fallback: Optional[str] = None  # school.py:495-502: fall back to "school"
+    uses_tier: bool = True          # household.py:305-307 has no lockdown-tier term
+
+    def to_json(self):
+        return dict(self.__dict__)
+
+
+@dataclass
+class WorldSoA:
+    # persons
+    age: np.ndarray
+    sex: np.ndarray
+    care_home_resident: np.ndarray
+    has_activity: np.ndarray
+    super_area: np.ndarray
+    # super areas
+    sa_hospital: np.ndarray
+    sa_region: np.ndarray
+    region_names: List[str]
+    # groups
+    grp_offset: np.ndarray
+    grp_info: np.ndarray
+    grp_aux: np.ndarray
+    reg_member: np.ndarray
+    reg_info: np.ndarray
+    school_years: np.ndarray
+    supergroups: List[Supergroup]
+    beta_rules: List[BetaRule]
+    beta_scale: np.ndarray
+    # domain decomposition
+    n_halo: int = 0
+    person_id_base: int = 0
+    halo_gid: np.ndarray = field(default_factory=lambda: np.zeros(0, np.uint32))
+    out_person: np.ndarray = field(default_factory=lambda: np.zeros(0, np.uint32))
+    out_counts: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # per destination rank
+    in_counts: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))   # per source rank
+    # bookkeeping for adapters (not used on the device)
+    person_ids: Optional[np.ndarray] = None  # reference Person.id per person index
+    group_ids: Optional[np.ndarray] = None   # reference Group.id per group index
+
+    _ARRAYS = ("age", "sex", "care_home_resident", "has_activity", "super_area", "sa_hospital", "sa_region",
+               "grp_offset", "grp_info", "grp_aux", "reg_member", "reg_info", "school_years", "beta_scale",
+               "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids")
+
+    @property
+    def n_people(self) -> int:
+        return int(self.age.shape[0])
+
+    @property
+    def n_groups(self) -> int:
+        return int(self.grp_info.shape[0])
+
+    @property
+    def n_members(self) -> int:
+        return int(self.reg_member.shape[0])
+
+    @property
+    def n_regions(self) -> int:
+        return max(1, len(self.region_names))
+
+    @property
+    def n_super_areas(self) -> int:
+        return int(self.sa_region.shape[0])
+
+    def supergroup(self, name: str) -> Supergroup:
+        for sg in self.supergroups:
+            if sg.name == name:
+                return sg
+        raise KeyError(name)
+
+    def group_supergroup(self) -> np.ndarray:
+        out = np.zeros(self.n_groups, np.int32)
+        for k, sg in enumerate(self.supergroups):
+            out[sg.first_group: sg.first_group + sg.n_groups] = k
+        return out
+
+    def validate(self) -> None:
+        n, g, m = self.n_people, self.n_groups, self.n_members
+        assert self.age.dtype == np.uint8 and self.sex.dtype == np.uint8
+        assert self.care_home_resident.shape == (n,) and self.has_activity.shape == (n,)
+        assert self.super_area.dtype == np.uint32 and self.super_area.shape == (n,)
+        assert self.grp_offset.dtype == np.uint32 and self.grp_offset.shape == (g + 1,)
+        assert self.grp_offset[0] == 0 and self.grp_offset[-1] == m
+        assert np.all(np.diff(self.grp_offset.astype(np.int64)) >= 0)
+        assert self.grp_info.dtype == np.uint32 and self.grp_aux.dtype == np.uint32 and self.grp_aux.shape == (g,)
+        assert self.reg_member.dtype == np.uint32 and self.reg_info.dtype == np.uint16 and self.reg_info.shape == (m,)
+        if m:
+            assert int(self.reg_member.max()) < n + self.n_halo
+        if n:
+            assert int(self.super_area.max()) < self.n_super_areas
+        exp = 0
+        for sg in self.supergroups:
+            assert sg.first_group == exp, "supergroups must tile the group range"
+            exp += sg.n_groups
+        assert exp == g
+        if g:
+            assert int((self.grp_info & 0xFF).max()) < len(self.beta_rules)
+            assert int(((self.grp_info >> 8) & 0xFF).max()) < len(self.beta_scale)
+            assert int((self.grp_info >> 16).max()) < self.n_regions
+        assert self.halo_gid.shape == (self.n_halo,)
+        # members sorted by (lsg, person) inside each group
+        if m:
+            grp_of = np.repeat(np.arange(g, dtype=np.int64), np.diff(self.grp_offset.astype(np.int64)))
+            key = (grp_of << 40) | ((self.reg_info & 0xFF).astype(np.int64) << 32) | self.reg_member.astype(np.int64)
+            assert np.all(np.diff(key) > 0), "registered members must be sorted by (group, subgroup, person)"
+
+    # ---- persistence (small fixtures under tests/golden/) ------------------------------------
+    def save(self, path: str) -> None:
+        meta = {
+            "region_names": self.region_names,
+            "supergroups": [sg.to_json() for sg in self.supergroups],
+            "beta_rules": [b.to_json() for b in self.beta_rules],
+            "n_halo": int(self.n_halo),
+            "person_id_base": int(self.person_id_base),
+        }
+        arrays = {k: getattr(self, k) for k in self._ARRAYS if getattr(self, k) is not None}
+        np.savez_compressed(path, _meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
+
+    @classmethod
+    def load(cls, path: str) -> "WorldSoA":
+        z = np.load(path)
+        return cls.from_npz(z)
+
+    @classmethod
+    def from_npz(cls, z, prefix: str = "") -> "WorldSoA":
+        meta = json.loads(bytes(z[prefix + "_meta"]).decode())
+        kw: Dict[str, object] = {}
+        for k in cls._ARRAYS:
+            kw[k] = z[prefix + k] if (prefix + k) in z else None
+        for k in ("halo_gid", "out_person"):
+            if kw[k] is None:
+                kw[k] = np.zeros(0, np.uint32)
+        for k in ("out_counts", "in_counts"):
+            if kw[k] is None:
+                kw[k] = np.zeros(0, np.int64)
+        return cls(
+            region_names=list(meta["region_names"]),
+            supergroups=[Supergroup(**d) for d in meta["supergroups"]],
+            beta_rules=[BetaRule(**d) for d in meta["beta_rules"]],
+            n_halo=int(meta["n_halo"]),
+            person_id_base=int(meta["person_id_base"]),
+            **kw,
+        )

@@ -1,0 +1,254 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(IDAS-Durham/JUNE, /root/reference) on a small programmatic world and tracing its hot path.
+
+Run by hand in the build container (the reference cannot travel to the GPU box):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+What is traced, per ``Simulator.do_timestep`` call (june/simulator.py:346-626):
+  * the step inputs: ``timer.now``, ``timer.duration``, ``timer.activities``, processed betas;
+  * infections created *before* the step (seeding, infection_seed.py:209-278) as parameter rows;
+  * the placement the reference's ActivityManager produced (which subgroup holds whom);
+  * every Bernoulli draw of ``Interaction._gets_infected`` (interaction.py:634-641): the person,
+    the exponent ``Lambda`` and the uniform consumed (the module-level ``random`` is replaced by an
+    iterator over a fixed stream -- SURVEY.md section 4.4);
+  * the infections created in the step (parameter rows sampled by the reference's scipy path);
+  * the person state after ``Epidemiology.update_health_status``.
+Also dumped: processed contact matrices / betas, the health-index table, gamma-pdf spot values.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import random as pyrandom
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_world  # noqa: E402
+
+from june_b200.adapter import compile_world  # noqa: E402
+from june_b200.world import ACTIVITY_CODES, MAX_STAGES  # noqa: E402
+
+
+def infection_row(pidx, person, time):
+    inf = person.infection
+    tr = inf.transmission
+    name = type(tr).__name__
+    if name == "TransmissionGamma":
+        tpar = [tr.shape, tr.shift, tr.scale, tr.norm, 0.0]
+    elif name == "TransmissionXNExp":
+        tpar = [tr.n, tr.alpha, tr.time_first_infectious, tr.norm, tr.norm_time]
+    else:
+        tpar = [tr.probability, 0.0, 0.0, 0.0, 0.0]
+    traj = inf.symptoms.trajectory
+    tt = [float(t) for t, _ in traj] + [0.0] * (MAX_STAGES - len(traj))
+    tg = [int(g) for _, g in traj] + [0] * (MAX_STAGES - len(traj))
+    return [pidx[person.id], float(time), len(traj), int(inf.symptoms.max_tag), float(tr.probability)] + tpar + tt + tg
+
+
+ROW_LEN = 5 + 5 + 2 * MAX_STAGES
+
+
+def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000):
+    pyrandom.seed(seed)
+    np.random.seed(seed)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        world, dc = ref_world.build_world(n_people, seed=seed)
+        sim = ref_world.make_simulator(world, dc, total_days=total_days, cases_per_capita=cases_per_capita,
+                                       schedule=schedule)
+    import june.interaction.interaction as inter_mod
+    import june.policy.individual_policies as indiv_mod
+    from june.epidemiology.infection import InfectionSelector
+    from june.groups.company import InteractiveCompany
+    from june.interaction import Interaction
+    from june.simulator import Simulator
+
+    # The "child cannot stay home alone -> fetch a guardian" rule is order dependent, draws from
+    # Python's global `random.choice`, and is switched off by the reference itself whenever it runs
+    # domain-decomposed (`if mpi_size == 1`, individual_policies.py:57-77).  The device path
+    # replaces the domain-decomposed mode, so the traces are taken in that branch.
+    indiv_mod.mpi_size = 2
+
+    a2sg = {"medical_facility": ["hospitals"], "primary_activity": ["schools", "companies"],
+            "residence": ["households", "care_homes"]}
+    soa = compile_world(world, a2sg, InteractiveCompany.sector_betas)
+    people = list(world.people)
+    pidx = {p.id: i for i, p in enumerate(people)}
+    gidx = {}
+    for sg in soa.supergroups:
+        for k, g in enumerate(getattr(world, sg.name).members):
+            gidx[id(g)] = sg.first_group + k
+
+    # ---- instrumentation ---------------------------------------------------------------------
+    rng = np.random.default_rng(1234 + seed)
+    uniforms = rng.random(n_uniform)
+    state = {"upos": 0, "draw_person": [], "draw_lambda": [], "draw_u": [], "rows": [], "pending": []}
+
+    def fake_random():
+        u = uniforms[state["upos"]]
+        state["upos"] += 1
+        state["draw_u"].append(u)
+        return float(u)
+
+    inter_mod.random = fake_random
+    orig_gets = Interaction._gets_infected
+    orig_sub = Interaction._time_step_for_subgroup
+    orig_infect = InfectionSelector.infect_person_at_time
+
+    def gets(self, params, infection_ids):
+        state["draw_lambda"].append(float(params.sum()))
+        return orig_gets(self, params, infection_ids)
+
+    def sub(self, infector_tensor, susceptible_subgroup_id, subgroup_susceptibles):
+        state["draw_person"].extend(pidx[i] for i in subgroup_susceptibles.keys())
+        return orig_sub(self, infector_tensor=infector_tensor, susceptible_subgroup_id=susceptible_subgroup_id,
+                        subgroup_susceptibles=subgroup_susceptibles)
+
+    def infect(self, person, time):
+        orig_infect(self, person, time)
+        state["rows"].append(infection_row(pidx, person, time))
+
+    Interaction._gets_infected = gets
+    Interaction._time_step_for_subgroup = sub
+    InfectionSelector.infect_person_at_time = infect
+
+    steps = []
+    orig_step = Simulator.do_timestep
+    orig_am = type(sim.activity_manager).do_timestep
+    placement = {}
+
+    def am_do_timestep(self, record=None):
+        ret = orig_am(self, record=record)
+        pg = np.full(len(people), -1, np.int32)
+        pl = np.zeros(len(people), np.uint8)
+        for sg in soa.supergroups:
+            for g in getattr(world, sg.name).members:
+                for li, s in enumerate(g.subgroups):
+                    for person in s.people:
+                        pg[pidx[person.id]] = gidx[id(g)]
+                        pl[pidx[person.id]] = li
+        placement["group"], placement["lsg"] = pg, pl
+        return ret
+
+    type(sim.activity_manager).do_timestep = am_do_timestep
+
+    def snapshot():
+        n = len(people)
+        inf = np.zeros(n, np.uint8); dead = np.zeros(n, np.uint8); tag = np.full(n, -1, np.int8)
+        trans = np.zeros(n); susc = np.zeros(n); med = np.full(n, -1, np.int32); stage = np.zeros(n, np.uint8)
+        iid = sim.epidemiology.infection_selectors[0].infection_class.infection_id()
+        for i, p in enumerate(people):
+            dead[i] = p.dead
+            susc[i] = p.immunity.get_susceptibility(iid)
+            if p.infection is not None:
+                inf[i] = 1
+                tag[i] = int(p.infection.tag)
+                trans[i] = p.infection.transmission.probability
+                stage[i] = p.infection.symptoms.stage
+            mf = p.subgroups.medical_facility if p.subgroups is not None else None
+            if mf is not None:
+                med[i] = (gidx[id(mf.group)] << 8) | mf.group.subgroups.index(mf)
+        return dict(infected=inf, dead=dead, tag=tag, trans=trans, susc=susc, med=med, stage=stage)
+
+    def do_timestep(self):
+        rec = {}
+        rec["pre_rows"] = np.array(state["rows"], np.float64).reshape(-1, ROW_LEN)
+        state["rows"] = []
+        state["draw_person"], state["draw_lambda"], state["draw_u"] = [], [], []
+        timer = self.timer
+        rec["now"], rec["dt"] = float(timer.now), float(timer.duration)
+        mask = 0
+        for a in timer.activities:
+            mask |= 1 << ACTIVITY_CODES[a]
+        rec["activity_mask"] = mask
+        orig_step(self)
+        rec["place_group"], rec["place_lsg"] = placement["group"], placement["lsg"]
+        rec["draw_person"] = np.array(state["draw_person"], np.int64)
+        rec["draw_lambda"] = np.array(state["draw_lambda"], np.float64)
+        rec["draw_u"] = np.array(state["draw_u"], np.float64)
+        rec["new_rows"] = np.array(state["rows"], np.float64).reshape(-1, ROW_LEN)
+        state["rows"] = []
+        rec["post"] = snapshot()
+        steps.append(rec)
+
+    Simulator.do_timestep = do_timestep
+    try:
+        with contextlib.redirect_stdout(sink):
+            sim.run()
+    finally:
+        Simulator.do_timestep = orig_step
+        type(sim.activity_manager).do_timestep = orig_am
+        Interaction._gets_infected = orig_gets
+        Interaction._time_step_for_subgroup = orig_sub
+        InfectionSelector.infect_person_at_time = orig_infect
+        from random import random as real_random
+        inter_mod.random = real_random
+
+    # ---- reference constants -------------------------------------------------------------------
+    interaction = sim.interaction
+    hig = sim.epidemiology.infection_selectors[0].health_index_generator
+    prob = np.zeros((2, 2, 100, 9))
+    for pi, pop in enumerate(("gp", "ch")):
+        for si, sx in enumerate(("f", "m")):
+            prob[pi, si] = hig.probabilities[pop][sx][:100]
+    out = {}
+    soa.save(os.path.join(HERE, out_name + "_world.npz"))
+    out["n_steps"] = np.array(len(steps))
+    out["health_index_prob"] = prob
+    for k, m in interaction.contact_matrices.items():
+        out["cm_" + k] = np.asarray(m, np.float64)
+    out["beta_keys"] = np.array(list(interaction.betas.keys()))
+    out["beta_vals"] = np.array(list(interaction.betas.values()), np.float64)
+    for i, rec in enumerate(steps):
+        for k, v in rec.items():
+            if k == "post":
+                for kk, vv in v.items():
+                    out[f"s{i}_post_{kk}"] = vv
+            else:
+                out[f"s{i}_{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, out_name + "_trace.npz"), **out)
+    n_draws = sum(len(r["draw_u"]) for r in steps)
+    n_inf = sum(len(r["new_rows"]) for r in steps)
+    print(f"{out_name}: {len(people)} people, {soa.n_groups} groups, {len(steps)} steps, {n_draws} draws, "
+          f"{n_inf} infections in steps, {int(steps[-1]['post']['dead'].sum())} dead")
+    return world, sim, soa
+
+
+def spot_values(out_name="spot"):
+    """Known-answer values of the scalar functions on the path."""
+    ref_world.ref_harness.setup()
+    from june.epidemiology.infection.transmission import TransmissionGamma, gamma_pdf
+    from june.epidemiology.infection.transmission_xnexp import TransmissionXNExp
+    from june.groups.school import InteractiveSchool
+
+    rng = np.random.default_rng(7)
+    xs = rng.uniform(-1, 25, 200); a = rng.normal(1.56, 0.08, 200); loc = rng.normal(-2.12, 0.1, 200) + rng.uniform(1, 8, 200)
+    sc = 1.0 / rng.normal(0.53, 0.03, 200)
+    g = np.array([gamma_pdf(float(x), float(aa), float(ll), float(ss)) for x, aa, ll, ss in zip(xs, a, loc, sc)])
+    xn_in, xn_out = [], []
+    for _ in range(100):
+        mp, tfi, nt, n, al = rng.uniform(0.2, 2), rng.uniform(0.5, 4), rng.uniform(0.5, 2), rng.uniform(0.5, 3), rng.uniform(1, 6)
+        t = TransmissionXNExp(max_probability=mp, time_first_infectious=tfi, norm_time=nt, n=n, alpha=al)
+        tt = rng.uniform(0, 15)
+        t.update_infection_probability(tt)
+        xn_in.append([n, al, tfi, t.norm, nt, tt, mp]); xn_out.append(t.probability)
+    tg = TransmissionGamma(max_infectiousness=1.3, shape=1.56, rate=0.53, shift=2.88)
+    tg.update_infection_probability(5.5)
+    np.savez_compressed(os.path.join(HERE, out_name + ".npz"), gamma_x=xs, gamma_a=a, gamma_loc=loc, gamma_scale=sc,
+                        gamma_pdf=g, xnexp_in=np.array(xn_in), xnexp_out=np.array(xn_out),
+                        tg_55=np.array(tg.probability))
+    print("spot values written")
+
+
+if __name__ == "__main__":
+    run_trace(3000, 12, 0, "w3k")
+    run_trace(1200, 40, 1, "w1k_long", cases_per_capita=0.05, schedule="simple")
+    spot_values()

@@ -1,0 +1,113 @@
+"""Parity against golden traces of the UNMODIFIED reference (tests/golden/make_golden.py).
+
+The same checks run against
+  * the CPU oracle (``oracle/june_oracle.c``)            -- here, without a GPU;
+  * the CUDA path through the C ABI (``libjune_b200.so``) -- ``-m gpu`` on the B200 box.
+
+Per reference ``do_timestep`` we check, with the reference's own uniform stream injected:
+  placement (activity chosen per person), the infection exponent Lambda of every Bernoulli draw
+  (<= 1e-9 relative, BASELINE.json), the set of newly infected people (bit-exact), and the person
+  state after the health update (infected/dead flags, symptom tag and hospital ward exact;
+  transmission probability <= 1e-9 relative).
+"""
+import numpy as np
+import pytest
+
+from june_b200 import _lib
+from june_b200.interaction import Interaction
+from june_b200.world import PS_ACT_MASK, PS_DEAD, PS_INFECTED
+
+from helpers import Golden, default_beta_table, have_gpu, make_engine, rows_to_dicts
+
+REL = 1e-9  # tolerance stated in BASELINE.json:north_star
+FLAGS = (_lib.STEP_SEVERE_STAY_HOME | _lib.STEP_HOSPITALISATION | _lib.STEP_INJECT_UNIFORMS
+         | _lib.STEP_NO_NEW_INFECTIONS | _lib.STEP_RECORD_LAMBDA)
+
+
+def run_trace(kind: str, name: str, max_steps=None):
+    g = Golden(name)
+    inter = Interaction.from_file()
+    eng = make_engine(kind, g.world, g.outcome_prob, interaction=inter)
+    beta = default_beta_table(g.world, inter)
+    n = g.world.n_people
+    grp_sg = g.world.group_supergroup()
+    sg_act = np.array([sg.activity for sg in g.world.supergroups])
+    total_draws = total_inf = 0
+    worst = 0.0
+    for i in range(g.n_steps if max_steps is None else min(max_steps, g.n_steps)):
+        s = g.step(i)
+        if len(s["pre_rows"]):
+            eng.upload_infections(rows_to_dicts(s["pre_rows"]))
+        eng.inject_uniforms(s["draw_u"])
+        p = eng.make_params(now=float(s["now"]), delta_time=float(s["dt"]), step=i,
+                            activity_mask=int(s["activity_mask"]), seed=0, flags=FLAGS, beta=beta)
+        eng.step_begin(p)
+        eng.step_interact()
+        # -- infection exponents, in draw order ------------------------------------------------
+        lam = eng.fetch_lambda()[:n]
+        dp = s["draw_person"]
+        assert len(dp) == len(s["draw_u"]) == len(s["draw_lambda"])
+        drawn = np.zeros(n, bool)
+        drawn[dp] = True
+        assert np.array_equal(~np.isnan(lam), drawn), f"step {i}: set of people who consumed a draw differs"
+        if len(dp):
+            ref = s["draw_lambda"]
+            got = lam[dp]
+            err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+            err[ref == 0] = np.abs(got[ref == 0])
+            worst = max(worst, float(err.max()))
+            assert err.max() <= REL, f"step {i}: Lambda differs by {err.max():.3e}"
+        # -- infection events: bit-exact -----------------------------------------------------------
+        member, variant = eng.fetch_new_infections()
+        ref_new = np.sort(s["new_rows"][:, 0].astype(np.int64)) if len(s["new_rows"]) else np.zeros(0, np.int64)
+        assert np.array_equal(member.astype(np.int64), ref_new), f"step {i}: infected set differs"
+        if len(s["new_rows"]):
+            eng.upload_infections(rows_to_dicts(s["new_rows"]))
+        stats = eng.step_finish()
+        assert stats["n_draws"] == len(dp)
+        # -- placement -------------------------------------------------------------------------------
+        st = eng.fetch_person_state()
+        act = st["pstate"] & PS_ACT_MASK
+        pg = s["place_group"]
+        exp_act = np.where(pg >= 0, sg_act[grp_sg[np.maximum(pg, 0)]], 7)
+        # hospital workers sit in a hospital group through their primary activity
+        mism = (act != exp_act) & (pg >= 0)
+        for q in np.nonzero(mism)[0]:
+            lo, hi = g.world.grp_offset[pg[q]], g.world.grp_offset[pg[q] + 1]
+            slot = lo + np.nonzero(g.world.reg_member[lo:hi] == q)[0]
+            assert len(slot) and (g.world.reg_info[slot[0]] >> 8) == act[q], f"step {i}: person {q} misplaced"
+        assert np.array_equal(act == 7, pg < 0), f"step {i}: set of placed people differs"
+        # -- health update ---------------------------------------------------------------------------
+        assert np.array_equal((st["pstate"] & PS_INFECTED) != 0, s["post_infected"] != 0), f"step {i}: infected flags"
+        assert np.array_equal((st["pstate"] & PS_DEAD) != 0, s["post_dead"] != 0), f"step {i}: dead flags"
+        assert np.array_equal(st["tag"], s["post_tag"]), f"step {i}: symptom tags"
+        assert np.array_equal(st["medical"], s["post_med"]), f"step {i}: hospital wards"
+        inf = s["post_infected"] != 0
+        ref_t, got_t = s["post_trans"][inf], st["trans_prob"][inf]
+        terr = np.abs(got_t - ref_t) / np.maximum(np.abs(ref_t), 1e-300)
+        terr[ref_t == 0] = np.abs(got_t[ref_t == 0])
+        if inf.any():
+            worst = max(worst, float(terr.max()))
+            assert terr.max() <= REL, f"step {i}: transmission probability differs by {terr.max():.3e}"
+        assert np.array_equal(st["susceptibility"][0], s["post_susc"]), f"step {i}: susceptibilities"
+        assert stats["n_infected"] == int(inf.sum())
+        total_draws += len(dp)
+        total_inf += len(ref_new)
+    eng.close()
+    return total_draws, total_inf, worst
+
+
+@pytest.mark.parametrize("name", ["w3k", "w1k_long"])
+def test_oracle_matches_reference_trace(name):
+    draws, infections, worst = run_trace("oracle", name)
+    assert draws > 10000 and infections > 100
+    assert worst <= REL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["w3k", "w1k_long"])
+def test_cuda_matches_reference_trace(name):
+    assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
+    draws, infections, worst = run_trace("cuda", name)
+    assert draws > 10000 and infections > 100
+    assert worst <= REL
