@@ -619,7 +619,8 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
       ++c_inf;
       if (st & JB_PS_MEDICAL) { ++c_hosp; if (bit & D.icu_mask) ++c_icu; }
     }
-    a.ptag[p] = (int8_t)tag;
+    // ptag mirrors person.infection.tag; -1 ("healthy") once the infection object is gone
+    a.ptag[p] = (bit & (D.rec_mask | D.dead_mask)) ? (int8_t)-1 : (int8_t)tag;
     a.pstate[p] = (uint8_t)st;
   }
   // block-level reduction of the "current" counters
