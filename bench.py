@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the JUNE per-timestep hot path (``Simulator.do_timestep``) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--people P]
+
+Metric (BASELINE.json): person-timesteps / second.  A "step" is one ``do_timestep`` of the
+default schedule (config_simulation.yaml: 5 weekday / 4 weekend steps) over a synthetic world
+built by ``june_b200.synth`` (SURVEY.md section 8d recipe).  N=1 runs BASELINE.json configs[1]
+(2.7 M people on one B200); N>1 is weak scaling: one 2.7 M-person domain per GPU, 5 % of the
+workers commuting to a neighbouring domain, two NCCL all-to-all exchanges per step.
+
+Prints ONE JSON line on rank 0 (contract in the task statement):
+  value     device-resident throughput: K steps timed with CUDA events on the library stream,
+            L2 flushed (256 MiB memset) between steps, max over ranks;
+  e2e       the same K steps through the public API ``Simulator.do_timestep()``: per-step host
+            parameters copied h2d from pinned memory, per-step statistics copied d2h, wall clock;
+  roofline  interaction kernel of the busiest supergroup: algorithmic bytes / CUDA-event time
+            against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+  cpu_baseline  the CPU oracle (oracle/june_oracle.c, a port of the reference algorithm) on the
+            host cores, on a bounded sample of the same workload.
+``--impl reference`` times that CPU port alone with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from june_b200.disease import DiseaseConfig, outcome_probabilities, synthetic_rates  # noqa: E402
+from june_b200.interaction import Interaction, load_defaults  # noqa: E402
+from june_b200.policy import Policies  # noqa: E402
+from june_b200.simulator import Simulator  # noqa: E402
+from june_b200.synth import generate_domain, generate_world, wire_halos_distributed  # noqa: E402
+from june_b200.timer import Timer  # noqa: E402
+from june_b200.world import ACT_RESIDENCE  # noqa: E402
+
+METRIC = "person-timesteps/sec"
+PEOPLE_PER_GPU = 2_700_000
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_setup(n_people: int, rank: int, world_size: int, dist=None):
+    defaults = load_defaults()
+    sb = defaults["company_sector_betas"]
+    if world_size == 1:
+        world = generate_world(n_people, seed=0, sector_betas=sb)
+    else:
+        draft = generate_domain(n_people, rank, world_size, seed=0, sector_betas=sb)
+        world = wire_halos_distributed(draft, dist)
+    inter = Interaction.from_file()
+    dc = DiseaseConfig("covid19")
+    rates, bins = synthetic_rates()
+    prob = outcome_probabilities(dc, rates, bins)
+    cfg = defaults["simulation"]
+    cfg["time"]["total_days"] = 10_000
+    cfg["time"]["initial_day"] = "2020-03-02 8:00"  # a Monday
+    policies = Policies.from_file(disease_config=dc)
+    return world, inter, dc, prob, cfg, policies
+
+
+def seed_epidemic(sim: Simulator, rank: int):
+    """~3 % of the residents infected over the 12 days before the start, so that the timed steps
+    see infections in every stage (exposed ... hospitalised) instead of a fresh seed."""
+    n = sim.world.n_people
+    rng = np.random.default_rng([17, rank])
+    chosen = rng.choice(n, size=int(0.03 * n), replace=False).astype(np.uint32)
+    for k, part in enumerate(np.array_split(chosen, 12)):
+        sim.device.infect(np.sort(part), time=-(12.0 - k), seed=1234, step=0xFFFF0000 + k)
+
+
+def interaction_bytes(world, sg, n_present: int) -> int:
+    """Algorithmic bytes of one launch of the interaction kernel over supergroup ``sg``
+    (DESIGN.md section 4): every registered slot read once (member u32 + info u16 + person state
+    byte = 7 B), 8 B (transmission probability or susceptibility) per person present, one CSR
+    offset (4 B) per group.  New-infection output is O(#infections) and ignored."""
+    lo, hi = int(world.grp_offset[sg.first_group]), int(world.grp_offset[sg.first_group + sg.n_groups])
+    return 7 * (hi - lo) + 4 * (sg.n_groups + 1) + 8 * n_present
+
+
+def run_gpu(args):
+    import torch
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_people = args.people or PEOPLE_PER_GPU
+    world, inter, dc, prob, cfg, policies = build_setup(n_people, rank, world_size, dist)
+    sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, device=local_rank,
+                              seed=2020, distributed=world_size > 1)
+    sim.timer = Timer.from_config(cfg)
+    sim.activity_manager.timer = sim.timer
+    seed_epidemic(sim, rank)
+    dev = sim.device
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        dev.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        sim.do_timestep()
+        next(sim.timer)
+    barrier()
+
+    # ---- leg 1: device-resident (CUDA events on the library stream, L2 flushed between steps) --
+    dev.timing_enable(True)
+    dev.timing_read(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    person_steps = 0
+    act_res, n_alive_last = [], n_people
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        sim.do_timestep(want_stats=True)
+        st = sim.last_stats
+        n_alive_last = n_people - st["n_dead_total"]
+        person_steps += n_alive_last
+        act_res.append(st["n_by_activity"][ACT_RESIDENCE])
+        next(sim.timer)
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop()
+    tim = dev.timing_read()
+    per_sg = dev.timing_read_supergroups()
+    dev.timing_enable(False)
+    step_ms = tim["step_ms"] / max(1, tim["n_steps"])
+    launches = int(tim["n_launches"])
+
+    # ---- leg 2: end to end through the public API (host params h2d, stats d2h, wall clock) -----
+    barrier()
+    e2e_steps_s = 0.0
+    e2e_person_steps = 0
+    for _ in range(args.steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        sim.do_timestep(want_stats=True)
+        e2e_steps_s += time.perf_counter() - t0
+        e2e_person_steps += n_people - sim.last_stats["n_dead_total"]
+        next(sim.timer)
+    barrier()
+
+    # ---- reduce over ranks -----------------------------------------------------------------------
+    vals = torch.tensor([step_ms * args.steps, e2e_steps_s * 1e3, float(person_steps), float(e2e_person_steps)],
+                        dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if dist is not None:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms, ps, e2e_ps = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
+    else:
+        total_ms, e2e_ms, ps, e2e_ps = (float(x) for x in vals)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    # dominant interaction kernel = the supergroup with the largest accumulated kernel time
+    k_top = int(np.argmax([s["ms"] for s in per_sg]))
+    sg = world.supergroups[k_top]
+    n_launch = max(1, per_sg[k_top]["launches"])
+    if sg.name == "households":
+        care = int((world.care_home_resident != 0).sum())
+        present = max(0, int(np.mean(act_res)) - care)
+    else:
+        present = int(world.grp_offset[sg.first_group + sg.n_groups] - world.grp_offset[sg.first_group])
+    a_bytes = interaction_bytes(world, sg, present)
+    t_launch_s = per_sg[k_top]["ms"] / n_launch * 1e-3
+    achieved = a_bytes / t_launch_s / 1e9 if t_launch_s > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_groups_thread<1>" if sg.launch_mode == 0 else "k_groups_warp<1>",
+                "supergroup": sg.name, "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "bytes_per_launch": a_bytes, "us_per_launch": round(t_launch_s * 1e6, 2),
+                "interaction_ms_per_step": round(tim["interaction_ms"] / max(1, tim["n_steps"]), 4)}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(roofline["kernel"])
+        except Exception:
+            pass
+
+    cpu = cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s=args.cpu_seconds) if world_size == 1 else None
+    h2d = int(world.n_regions * len(world.beta_rules) * 8 + 48)
+    d2h = int(16 * 4)
+    out = {
+        "metric": METRIC, "value": ps / (total_ms * 1e-3), "unit": "person-timesteps/s", "n_gpus": world_size,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {n_people / 1e6:.1f}M-person region per GPU (households, schools, companies, "
+                               "care homes, hospitals), default 5/4-step day schedule, ~3% seeded prevalence",
+                   "people_per_gpu": n_people, "people_total": n_people * world_size,
+                   "l2": "flushed between steps (256 MiB memset, outside the event brackets)",
+                   "parallelism": "1 domain per GPU" + (", halo all-to-all over NCCL" if world_size > 1 else "")},
+        "e2e": {"value": e2e_ps / (e2e_ms * 1e-3), "unit": "person-timesteps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "wall_s_leg1": round(t_wall1 - t_wall0, 3),
+        "kernel_ms_by_supergroup": {s["name"]: round(s["ms"] / max(1, s["launches"]), 4) for s in per_sg},
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def oracle_engine(world, inter, dc, prob):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_engine  # the oracle is loaded here only as the timed CPU baseline
+    return make_engine("oracle", world, prob, interaction=inter, disease=dc)
+
+
+def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int):
+    eng = oracle_engine(world, inter, dc, prob)
+    sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, engine=eng, seed=2020)
+    sim.timer = Timer.from_config(cfg)
+    sim.activity_manager.timer = sim.timer
+    seed_epidemic(sim, 0)
+    for _ in range(warmup):
+        sim.do_timestep()
+        next(sim.timer)
+    ps, t0 = 0, time.perf_counter()
+    for _ in range(steps):
+        sim.do_timestep()
+        ps += world.n_people - sim.last_stats["n_dead_total"]
+        next(sim.timer)
+    dt = time.perf_counter() - t0
+    threads = int(eng._lib.jo_num_threads())
+    eng.close()
+    return ps, dt, threads
+
+
+def cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s: float = 15.0):
+    """Oracle port on the host cores, bounded sample: as many steps of the same world as fit in
+    ~budget_s seconds (at least 3)."""
+    ps, dt, threads = cpu_run(world, inter, dc, prob, cfg, policies, steps=2, warmup=1)
+    per_step = dt / 2
+    steps = int(max(3, min(40, budget_s / max(per_step, 1e-6))))
+    ps, dt, threads = cpu_run(world, inter, dc, prob, cfg, policies, steps=steps, warmup=1)
+    return {"value": ps / dt, "unit": "person-timesteps/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} steps of the same {world.n_people}-person world (oracle/june_oracle.c, OpenMP)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    n_people = args.people or PEOPLE_PER_GPU
+    world, inter, dc, prob, cfg, policies = build_setup(n_people, 0, 1)
+    # bounded: the CPU port needs ~0.1-1 s per step of a 2.7 M world
+    steps = min(args.steps, 40)
+    ps, dt, threads = cpu_run(world, inter, dc, prob, cfg, policies, steps=steps, warmup=min(args.warmup, 3))
+    v = ps / dt
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "person-timesteps/s", "n_gpus": world_size,
+           "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"synthetic {n_people / 1e6:.1f}M-person region (same generator and schedule as the GPU arm)",
+                      "people_per_gpu": n_people},
+           "cpu_baseline": {"value": v, "unit": "person-timesteps/s", "cores": threads, "kind": "port",
+                            "sample": f"{steps} steps of the {n_people}-person world on rank 0"},
+           "e2e": {"value": v, "unit": "person-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=45)
+    ap.add_argument("--warmup", type=int, default=9)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--people", type=int, default=0, help="people per GPU (default 2.7 M = BASELINE.json configs[1])")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

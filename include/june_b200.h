@@ -202,7 +202,7 @@ typedef struct {
   uint32_t n_no_activity;     /* >0 -> JB_ENOACT                                            */
   uint32_t n_slots_used;
   uint32_t n_halo_infected;   /* new infections of halo persons (to be sent home)           */
-  uint32_t _pad;
+  uint32_t n_by_activity[JB_N_ACT]; /* residents placed per activity this step               */
 } JbStepStats;
 
 /* One host-created infection (jb_upload_infections), mirroring the fields the reference's

@@ -76,10 +76,12 @@ class JbStepParams(C.Structure):
 class JbStepStats(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "n_new_infections", "n_infected", "n_dead_total", "n_recovered_step", "n_deaths_step", "n_hospitalised",
-        "n_icu", "n_draws", "n_no_activity", "n_slots_used", "n_halo_infected", "_pad")]
+        "n_icu", "n_draws", "n_no_activity", "n_slots_used", "n_halo_infected")] + [("n_by_activity", C.c_uint32 * 5)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if not n.startswith("_")}
+        d = {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "n_by_activity"}
+        d["n_by_activity"] = [int(x) for x in self.n_by_activity]
+        return d
 
 
 class JbInfectionRow(C.Structure):
@@ -147,7 +149,8 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("timing_enable").argtypes = [vp, C.c_int]
     f("timing_read").argtypes = [vp, dp, dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
     f("last_step_bytes").argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-    for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp])):
+    for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp]),
+                        ("timing_read_supergroups", [vp, dp, C.POINTER(C.c_uint64), C.c_int])):
         if hasattr(lib, prefix + extra):
             getattr(lib, prefix + extra).argtypes = args
     if hasattr(lib, prefix + "halo_record_size_w"):

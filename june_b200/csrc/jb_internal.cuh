@@ -17,6 +17,8 @@ enum {
   CNT_DEATHS_STEP,
   CNT_HALO_INF,
   CNT_OVERFLOW,        // a capacity was exceeded
+  CNT_ACT0,            // persons placed per activity (5 words: JB_ACT_MEDICAL..JB_ACT_RESIDENCE)
+  CNT_ACT4 = CNT_ACT0 + 4,
   CNT_STEP_END,        // ---- everything above is zeroed at the start of every step ----
   CNT_SLOTS_HW = CNT_STEP_END,  // infection slot high-water mark
   CNT_DEAD_TOTAL,
@@ -128,6 +130,10 @@ struct JbWorld {
   // timing
   bool timing = false;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr, ev_int0 = nullptr, ev_int1 = nullptr;
+  cudaEvent_t ev_sg0[JB_MAX_SUPERGROUPS] = {}, ev_sg1[JB_MAX_SUPERGROUPS] = {};
+  bool sg_pending[JB_MAX_SUPERGROUPS] = {};
+  double acc_sg_ms[JB_MAX_SUPERGROUPS] = {};
+  uint64_t acc_sg_launches[JB_MAX_SUPERGROUPS] = {};
   double acc_int_ms = 0, acc_step_ms = 0;
   uint64_t acc_steps = 0, acc_launches = 0;
   bool ev_pending = false;

@@ -30,10 +30,10 @@ k_place(uint8_t* __restrict__ pstate, const uint8_t* __restrict__ phas, const in
         uint64_t* __restrict__ dyn_key, uint32_t dyn_cap, uint32_t* __restrict__ counters, uint32_t N,
         uint32_t activity_mask, uint32_t flags) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= N) return;
-  uint32_t st = pstate[p];
   uint32_t act = JB_ACT_NONE;
-  if (!(st & JB_PS_DEAD)) {
+  uint32_t st = 0;
+  if (p < N) st = pstate[p];
+  if (p < N && !(st & JB_PS_DEAD)) {
     uint32_t allowed = activity_mask;
     if ((flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE))
       allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
@@ -54,7 +54,13 @@ k_place(uint8_t* __restrict__ pstate, const uint8_t* __restrict__ phas, const in
       atomicAdd(&counters[CNT_NOACT], 1u);
     }
   }
-  pstate[p] = (uint8_t)((st & ~JB_PS_ACT_MASK) | act);
+  if (p < N) pstate[p] = (uint8_t)((st & ~JB_PS_ACT_MASK) | act);
+  // persons per activity (feeds the algorithmic-byte accounting and the conservation check)
+#pragma unroll
+  for (uint32_t a = 0; a < JB_N_ACT; ++a) {
+    uint32_t m = __ballot_sync(JB_FULL, act == a);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(&counters[CNT_ACT0 + a], (uint32_t)__popc(m));
+  }
 }
 
 // Per-group offsets into the sorted dynamic-member list (lower bound of group g).

@@ -216,6 +216,7 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   CK(cudaEventCreate(&w->ev_step1));
   CK(cudaEventCreate(&w->ev_int0));
   CK(cudaEventCreate(&w->ev_int1));
+  for (size_t k = 0; k < w->sgs.size(); ++k) { CK(cudaEventCreate(&w->ev_sg0[k])); CK(cudaEventCreate(&w->ev_sg1[k])); }
   // the warp kernel may need > 48 KB of dynamic shared memory for very large schools
   CK(cudaFuncSetAttribute(k_groups_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_groups_warp<JB_MAX_VARIANTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -243,6 +244,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   if (w->ev_step1) cudaEventDestroy(w->ev_step1);
   if (w->ev_int0) cudaEventDestroy(w->ev_int0);
   if (w->ev_int1) cudaEventDestroy(w->ev_int1);
+  for (int k = 0; k < JB_MAX_SUPERGROUPS; ++k) { if (w->ev_sg0[k]) cudaEventDestroy(w->ev_sg0[k]); if (w->ev_sg1[k]) cudaEventDestroy(w->ev_sg1[k]); }
   cudaStreamDestroy(w->stream);
   delete w;
 }
@@ -431,6 +433,8 @@ static int launch_groups(JbWorld* w, int mode) {
     if (!(w->cur.activity_mask & (1u << sg.activity))) continue;
     GroupArgs a = make_group_args(w, sg, w->sg_L[k]);
     a.mode = mode;
+    const bool tme = w->timing && mode == 0;
+    if (tme) CK(cudaEventRecord(w->ev_sg0[k], w->stream));
     if (sg.launch_mode == 0) {
       unsigned blocks = (sg.n_groups + 255) / 256;
       if (w->V == 1) k_groups_thread<1><<<blocks, 256, 0, w->stream>>>(a);
@@ -444,7 +448,27 @@ static int launch_groups(JbWorld* w, int mode) {
     }
     CK(cudaGetLastError());
     w->launches++;
+    if (tme) { CK(cudaEventRecord(w->ev_sg1[k], w->stream)); w->sg_pending[k] = true; }
   }
+  return JB_OK;
+}
+
+// Fold finished event pairs into the accumulators (called with the stream idle or synchronised).
+static int harvest_timing(JbWorld* w) {
+  if (!w->ev_pending) return JB_OK;
+  CK(cudaEventSynchronize(w->ev_step1));
+  float a = 0, b = 0;
+  CK(cudaEventElapsedTime(&a, w->ev_int0, w->ev_int1));
+  CK(cudaEventElapsedTime(&b, w->ev_step0, w->ev_step1));
+  w->acc_int_ms += a; w->acc_step_ms += b; w->acc_steps++;
+  for (size_t k = 0; k < w->sgs.size(); ++k)
+    if (w->sg_pending[k]) {
+      float c = 0;
+      CK(cudaEventElapsedTime(&c, w->ev_sg0[k], w->ev_sg1[k]));
+      w->acc_sg_ms[k] += c; w->acc_sg_launches[k]++;
+      w->sg_pending[k] = false;
+    }
+  w->ev_pending = false;
   return JB_OK;
 }
 
@@ -457,14 +481,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   cudaStream_t s = w->stream;
   w->cur = *p;
   if (w->timing) {
-    if (w->ev_pending) {
-      CK(cudaEventSynchronize(w->ev_step1));
-      float a = 0, b = 0;
-      CK(cudaEventElapsedTime(&a, w->ev_int0, w->ev_int1));
-      CK(cudaEventElapsedTime(&b, w->ev_step0, w->ev_step1));
-      w->acc_int_ms += a; w->acc_step_ms += b; w->acc_steps++;
-      w->ev_pending = false;
-    }
+    TRY(harvest_timing(w));
     CK(cudaEventRecord(w->ev_step0, s));
   }
   memcpy(w->h_beta, p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
@@ -593,6 +610,7 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
     out->n_no_activity = c[CNT_NOACT];
     out->n_slots_used = c[CNT_SLOTS_HW];
     out->n_halo_infected = c[CNT_HALO_INF];
+    for (int a = 0; a < JB_N_ACT; ++a) out->n_by_activity[a] = c[CNT_ACT0 + a];
     if (c[CNT_NOACT]) {
       jb_set_error("Attention! Some people do not have an activity in this timestep.");
       return JB_ENOACT;
@@ -735,19 +753,24 @@ extern "C" int jb_timing_read(JbWorld* w, double* interaction_ms, double* step_m
                               uint64_t* n_launches, int reset) {
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
-  if (w->ev_pending) {
-    CK(cudaEventSynchronize(w->ev_step1));
-    float a = 0, b = 0;
-    CK(cudaEventElapsedTime(&a, w->ev_int0, w->ev_int1));
-    CK(cudaEventElapsedTime(&b, w->ev_step0, w->ev_step1));
-    w->acc_int_ms += a; w->acc_step_ms += b; w->acc_steps++;
-    w->ev_pending = false;
-  }
+  TRY(harvest_timing(w));
   if (interaction_ms) *interaction_ms = w->acc_int_ms;
   if (step_ms) *step_ms = w->acc_step_ms;
   if (n_steps) *n_steps = w->acc_steps;
   if (n_launches) *n_launches = w->launches;
-  if (reset) { w->acc_int_ms = w->acc_step_ms = 0; w->acc_steps = 0; w->launches = 0; }
+  if (reset) {
+    w->acc_int_ms = w->acc_step_ms = 0; w->acc_steps = 0; w->launches = 0;
+    for (int k = 0; k < JB_MAX_SUPERGROUPS; ++k) { w->acc_sg_ms[k] = 0; w->acc_sg_launches[k] = 0; }
+  }
+  return JB_OK;
+}
+
+// Per-supergroup interaction kernel time (ms, launches) accumulated since the last reset.
+extern "C" int jb_timing_read_supergroups(JbWorld* w, double* ms, uint64_t* launches, int cap) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  TRY(harvest_timing(w));
+  for (int k = 0; k < cap && k < (int)w->sgs.size(); ++k) { ms[k] = w->acc_sg_ms[k]; launches[k] = w->acc_sg_launches[k]; }
   return JB_OK;
 }
 

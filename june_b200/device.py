@@ -244,6 +244,12 @@ class Engine:
     def timing_enable(self, on: bool = True):
         self._check(self._f("timing_enable")(self._h, 1 if on else 0))
 
+    def timing_read_supergroups(self) -> List[Dict[str, float]]:
+        k = len(self.world.supergroups)
+        ms, ln = (C.c_double * k)(), (C.c_uint64 * k)()
+        self._check(self._f("timing_read_supergroups")(self._h, ms, ln, k))
+        return [dict(name=sg.name, ms=ms[i], launches=int(ln[i])) for i, sg in enumerate(self.world.supergroups)]
+
     def timing_read(self, reset: bool = False) -> Dict[str, float]:
         a, b = C.c_double(), C.c_double()
         n, l = C.c_uint64(), C.c_uint64()

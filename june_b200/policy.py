@@ -1,0 +1,201 @@
+"""The policies ``Simulator.do_timestep`` evaluates on every step, with the reference's class
+names, constructor arguments and YAML schema (``june/policy/*.py``,
+``configs/defaults/policy/policy_<disease>.yaml``):
+
+* interaction policies -> ``interaction.beta_reductions`` (``interaction_policies.py:15-96``),
+* regional compliance / tiered lockdown -> per-region scalars (``regional_compliance.py:21-66``),
+* ``SevereSymptomsStayHome`` (``individual_policies.py:121-149``) and ``Hospitalisation``
+  (``medical_care_policies.py:413-526``) -> step flags evaluated per person on the device.
+
+Per-person work never happens here: a policy contributes either a few host scalars per step or a
+flag bit that switches a branch inside the placement / health kernels.
+"""
+from __future__ import annotations
+
+import datetime
+import re
+from collections import defaultdict
+from typing import Dict, List, Optional, Sequence, Union
+
+import yaml
+
+from . import _lib
+from .interaction import load_defaults
+
+DateLike = Union[str, datetime.date, datetime.datetime]
+
+
+def read_date(date: DateLike) -> datetime.datetime:
+    if isinstance(date, datetime.datetime):
+        return date
+    if isinstance(date, datetime.date):
+        return datetime.datetime(date.year, date.month, date.day)
+    if isinstance(date, str):
+        return datetime.datetime.strptime(date.split(" ")[0], "%Y-%m-%d")
+    raise TypeError("date must be a string or a datetime.date object")
+
+
+class Policy:
+    policy_type = "policy"
+
+    def __init__(self, start_time: DateLike = "1900-01-01", end_time: DateLike = "2100-01-01"):
+        self.spec = re.sub(r"(?<!^)(?=[A-Z])", "_", self.__class__.__name__).lower()
+        self.start_time = read_date(start_time)
+        self.end_time = read_date(end_time)
+
+    def is_active(self, date: datetime.datetime) -> bool:
+        return self.start_time <= date < self.end_time
+
+
+# ---- interaction policies -----------------------------------------------------------------------
+class SocialDistancing(Policy):
+    policy_type = "interaction"
+
+    def __init__(self, start_time: DateLike, end_time: DateLike, beta_factors: Optional[dict] = None):
+        super().__init__(start_time, end_time)
+        self.beta_factors = beta_factors or {}
+
+    def apply(self) -> Dict[str, float]:
+        return self.beta_factors
+
+
+class MaskWearing(Policy):
+    policy_type = "interaction"
+
+    def __init__(self, start_time: DateLike, end_time: DateLike, compliance: float, beta_factor: float,
+                 mask_probabilities: Optional[dict] = None):
+        super().__init__(start_time, end_time)
+        self.compliance, self.beta_factor, self.mask_probabilities = compliance, beta_factor, mask_probabilities or {}
+
+    def apply(self) -> Dict[str, float]:
+        # interaction_policies.py:93-96
+        return {k: 1 - (v * self.compliance * (1 - self.beta_factor)) for k, v in self.mask_probabilities.items()}
+
+
+# ---- region-level policies ------------------------------------------------------------------------
+class RegionalCompliance(Policy):
+    policy_type = "regional_compliance"
+
+    def __init__(self, start_time: DateLike, end_time: DateLike, compliances_per_region: dict):
+        super().__init__(start_time, end_time)
+        self.compliances_per_region = compliances_per_region
+
+
+class TieredLockdown(Policy):
+    policy_type = "tiered_lockdown"
+
+    def __init__(self, start_time: DateLike, end_time: DateLike, tiers_per_region: dict):
+        super().__init__(start_time, end_time)
+        self.tiers_per_region = tiers_per_region
+
+
+# ---- per-person policies evaluated on the device ---------------------------------------------------
+class SevereSymptomsStayHome(Policy):
+    policy_type = "individual"
+    step_flag = _lib.STEP_SEVERE_STAY_HOME
+
+
+class Hospitalisation(Policy):
+    policy_type = "medical_care"
+    step_flag = _lib.STEP_HOSPITALISATION
+
+    def __init__(self, disease_config=None, start_time: DateLike = "1900-01-01", end_time: DateLike = "2100-01-01"):
+        super().__init__(start_time, end_time)
+        self.disease_config = disease_config
+
+
+_CLASSES = {c.__name__: c for c in (SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
+                                    SevereSymptomsStayHome, Hospitalisation)}
+
+
+def _camel(key: str) -> str:
+    return "".join(x.capitalize() for x in key.split("_"))
+
+
+class Policies:
+    """Collection with the reference's category views (``policy/policy.py:56-99``)."""
+
+    def __init__(self, policies: Optional[Sequence[Policy]] = None):
+        self.policies: List[Policy] = list(policies or [])
+
+    def _of(self, ptype: str) -> List[Policy]:
+        return [p for p in self.policies if p.policy_type == ptype]
+
+    @property
+    def interaction_policies(self):
+        return self._of("interaction")
+
+    @property
+    def individual_policies(self):
+        return self._of("individual")
+
+    @property
+    def medical_care_policies(self):
+        return self._of("medical_care")
+
+    @classmethod
+    def from_file(cls, config_file: Optional[str] = None, disease: str = "covid19", disease_config=None) -> "Policies":
+        """YAML key -> CamelCase class; numbered sub-entries expand to several instances
+        (``policy/policy.py:137-229``).  Keys of policies this package does not evaluate are
+        skipped (they are out of the hot-path scope)."""
+        if config_file is None:
+            cfg = load_defaults()["policy"][disease]
+        else:
+            with open(config_file) as f:
+                cfg = yaml.safe_load(f)
+        out: List[Policy] = []
+        for key, data in (cfg or {}).items():
+            klass = _CLASSES.get(_camel(key))
+            if klass is None:
+                continue
+            entries = [data]
+            if isinstance(data, dict) and data and all(str(k).isdigit() for k in data):
+                entries = [data[k] for k in sorted(data, key=lambda x: int(x))]
+            for e in entries:
+                kw = dict(e or {})
+                if klass is Hospitalisation:
+                    kw["disease_config"] = disease_config
+                out.append(klass(**kw))
+        return cls(out)
+
+    # ---- what do_timestep needs every step -------------------------------------------------------
+    def beta_reductions(self, date: datetime.datetime) -> Dict[str, float]:
+        """``InteractionPolicies.apply`` (``interaction_policies.py:15-35``)."""
+        red: Dict[str, float] = defaultdict(lambda: 1.0)
+        for p in self.interaction_policies:
+            if p.is_active(date):
+                for group, f in p.apply().items():
+                    red[group] *= f
+        return red
+
+    def regional_scalars(self, date: datetime.datetime, region_names: Sequence[str], state: Optional[dict] = None):
+        """``RegionalCompliances.apply`` + ``TieredLockdowns.apply`` (``regional_compliance.py:21-66``):
+        returns ``(compliances, lockdown_tiers)`` per region.  ``state`` keeps values between steps
+        exactly like the attributes on the reference's ``Region`` objects do."""
+        state = state if state is not None else {}
+        comp = state.setdefault("compliance", {r: 1.0 for r in region_names})
+        tiers = state.setdefault("tier", {r: None for r in region_names})
+        rc = self._of("regional_compliance")
+        if rc:
+            for r in region_names:
+                comp[r] = 1.0
+        for p in rc:
+            if p.is_active(date):
+                for r in region_names:
+                    comp[r] = p.compliances_per_region[r]
+        tl = self._of("tiered_lockdown")
+        if tl:
+            for r in region_names:
+                tiers[r] = None
+        for p in tl:
+            if p.is_active(date):
+                for r in region_names:
+                    tiers[r] = int(p.tiers_per_region[r])
+        return [comp[r] for r in region_names], [tiers[r] for r in region_names]
+
+    def step_flags(self, date: datetime.datetime) -> int:
+        flags = 0
+        for p in self.policies:
+            if hasattr(p, "step_flag") and p.is_active(date):
+                flags |= p.step_flag
+        return flags

@@ -1,0 +1,258 @@
+"""Drop-in for the reference's time loop: ``Simulator.run`` / ``Simulator.do_timestep``
+(``june/simulator.py:346-707``) with the same collaborators -- ``Interaction``, ``Timer``,
+``ActivityManager``, ``Epidemiology``, ``Policies`` -- but the world lives in HBM and each
+``do_timestep`` is one enqueue of the CUDA kernels behind the C ABI.
+
+Host work per step is O(#regions + #specs): policy scalars, the beta table and one parameter
+struct.  Nothing here loops over people or groups.
+"""
+from __future__ import annotations
+
+import datetime
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import SimulatorError
+from .adapter import ACTIVITY_HIERARCHY
+from .device import DeviceWorld, Engine
+from .disease import DiseaseConfig
+from .interaction import Interaction, load_defaults
+from .policy import Policies
+from .timer import Timer
+from .world import ACTIVITY_CODES, WorldSoA
+
+
+class ActivityManager:
+    """Configuration half of the reference ``ActivityManager``
+    (``june/activity/activity_manager.py:37-140,172-188``); the per-person loop
+    (``move_people_to_active_subgroups``, ``:255-402``) is the placement kernel."""
+
+    def __init__(self, world, policies: Optional[Policies], timer: Timer, all_activities: Sequence[str],
+                 activity_to_super_groups: Dict[str, Sequence[str]], record=None, leisure=None, travel=None):
+        self.world, self.policies, self.timer = world, policies if policies is not None else Policies([]), timer
+        self.all_activities = list(all_activities)
+        self.activity_to_super_group_dict = {a: list(activity_to_super_groups.get(a, [])) for a in ACTIVITY_HIERARCHY}
+        self.leisure, self.travel = leisure, travel
+        for a in self.all_activities:
+            if a not in ACTIVITY_CODES:
+                raise SimulatorError("Config file contains unsupported activity name.")
+
+    @classmethod
+    def from_file(cls, config_filename, world, policies, timer, record=None, leisure=None, travel=None):
+        import yaml
+        with open(config_filename) as f:
+            config = yaml.safe_load(f)
+        return cls.from_config(config, world, policies, timer)
+
+    @classmethod
+    def from_config(cls, config: dict, world, policies, timer):
+        a2sg = config.get("activity_to_super_groups") or config.get("activity_to_groups")  # legacy key, :80-87
+        acts = set()
+        for day in ("weekday", "weekend"):
+            sched = config["time"]["step_activities"][day]
+            for a in (sched.values() if isinstance(sched, dict) else sched):
+                acts.update(a)
+        return cls(world=world, policies=policies, timer=timer, all_activities=sorted(acts, key=ACTIVITY_HIERARCHY.index),
+                   activity_to_super_groups=a2sg)
+
+    @staticmethod
+    def apply_activity_hierarchy(activities: List[str]) -> List[str]:
+        activities.sort(key=ACTIVITY_HIERARCHY.index)
+        return activities
+
+    def activities_to_super_groups(self, activities: Sequence[str]) -> List[str]:
+        return [sg for a in activities for sg in self.activity_to_super_group_dict.get(a, [])]
+
+    @property
+    def active_super_groups(self) -> List[str]:
+        return self.activities_to_super_groups(self.timer.activities)
+
+    def activity_mask(self) -> int:
+        mask = 0
+        for a in self.timer.activities:
+            code = ACTIVITY_CODES.get(a)
+            if code is not None:
+                mask |= 1 << code
+        return mask
+
+
+class InfectionSeed:
+    """Uniform seeding (``InfectionSeed.from_uniform_cases`` + ``unleash_virus_per_day``,
+    ``infection_seed.py:146-192,401-475``): on ``date`` a fraction ``cases_per_capita`` of the
+    not-yet-infected residents is infected through the device sampler."""
+
+    def __init__(self, cases_per_capita: float, date: str, seed: int = 0):
+        self.cases_per_capita = cases_per_capita
+        self.date = datetime.datetime.strptime(date.split(" ")[0], "%Y-%m-%d").date()
+        self.seed = seed
+        self.done = False
+
+    @classmethod
+    def from_uniform_cases(cls, world=None, infection_selector=None, cases_per_capita: float = 0.01,
+                           date: str = "2020-03-01", seed_past_infections=False, seed: int = 0):
+        return cls(cases_per_capita, date, seed)
+
+    def unleash_virus_per_day(self, sim: "Simulator", date: datetime.datetime, time: float) -> int:
+        if self.done or date.date() != self.date:
+            return 0
+        n = sim.world.n_people
+        rng = np.random.default_rng([self.seed, sim.rank, 99])
+        k = int(round(self.cases_per_capita * n))
+        chosen = np.sort(rng.choice(n, size=k, replace=False)).astype(np.uint32)
+        sim.device.infect(chosen, time=time, seed=sim.seed ^ 0x5EED, step=0xFFFF0000)
+        self.done = True
+        return k
+
+
+class Epidemiology:
+    def __init__(self, infection_selectors=None, infection_seeds: Optional[Sequence[InfectionSeed]] = None,
+                 immunity_setter=None, medical_care_policies=None, vaccination_campaigns=None):
+        self.infection_selectors = infection_selectors
+        self.infection_seeds = list(infection_seeds or [])
+
+    def infection_seeds_timestep(self, sim: "Simulator", timer: Timer) -> None:
+        for s in self.infection_seeds:
+            s.unleash_virus_per_day(sim, timer.date, timer.now)
+
+
+class HaloExchange:
+    """The two per-step exchanges of the reference's domain-decomposed mode
+    (``activity_manager.py:404-447`` people, ``epidemiology.py:359-401`` infections) as two
+    fixed-size ``all_to_all_single`` calls on device buffers (NCCL over NVLink; gloo in CPU tests)."""
+
+    def __init__(self, world: WorldSoA, record_size: int, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.out_counts = [int(x) for x in world.out_counts]
+        self.in_counts = [int(x) for x in world.in_counts]
+        n_out, n_in = sum(self.out_counts), sum(self.in_counts)
+        self.rec = record_size
+        dev = device if device is not None else "cpu"
+        self.send = torch.zeros(max(1, n_out) * record_size, dtype=torch.uint8, device=dev)
+        self.recv = torch.zeros(max(1, n_in) * record_size, dtype=torch.uint8, device=dev)
+        self.ret_send = torch.zeros(max(1, n_in), dtype=torch.uint8, device=dev)
+        self.ret_recv = torch.zeros(max(1, n_out), dtype=torch.uint8, device=dev)
+        self.n_out, self.n_in = n_out, n_in
+
+    def exchange_people(self):
+        r = self.rec
+        self.dist.all_to_all_single(self.recv[: self.n_in * r], self.send[: self.n_out * r],
+                                    output_split_sizes=[c * r for c in self.in_counts],
+                                    input_split_sizes=[c * r for c in self.out_counts])
+
+    def exchange_infections(self):
+        self.dist.all_to_all_single(self.ret_recv[: self.n_out], self.ret_send[: self.n_in],
+                                    output_split_sizes=self.out_counts, input_split_sizes=self.in_counts)
+
+
+class Simulator:
+    ActivityManager = ActivityManager
+
+    def __init__(self, world: WorldSoA, interaction: Interaction, timer: Timer, activity_manager: ActivityManager,
+                 epidemiology: Optional[Epidemiology] = None, tracker=None, events=None, record=None,
+                 disease_config: Optional[DiseaseConfig] = None, outcome_prob: Optional[np.ndarray] = None,
+                 device: int = 0, seed: int = 0, engine: Optional[Engine] = None, distributed: bool = False):
+        self.world, self.interaction, self.timer = world, interaction, timer
+        self.activity_manager, self.epidemiology, self.record = activity_manager, epidemiology, record
+        self.disease_config = disease_config or DiseaseConfig("covid19")
+        self.seed = int(seed)
+        self.step_ordinal = 0
+        self.rank = 0
+        self._region_state: dict = {}
+        if outcome_prob is None:
+            from .disease import outcome_probabilities, synthetic_rates
+            rates, bins = synthetic_rates()
+            outcome_prob = outcome_probabilities(self.disease_config, rates, bins)
+        self.device = engine or DeviceWorld(world, interaction, self.disease_config, outcome_prob, device=device)
+        self.halo: Optional[HaloExchange] = None
+        if distributed:
+            import torch
+            import torch.distributed as dist
+            self.rank = dist.get_rank()
+            on_gpu = isinstance(self.device, DeviceWorld)
+            self.halo = HaloExchange(world, self.device.halo_record_size(),
+                                     device=torch.device("cuda", device) if on_gpu else None)
+        self.last_stats: Dict[str, int] = {}
+        self.history: List[Dict[str, object]] = []
+
+    @classmethod
+    def from_file(cls, world: WorldSoA, interaction: Interaction, policies: Optional[Policies] = None,
+                  epidemiology: Optional[Epidemiology] = None, config_filename: Optional[str] = None, **kw):
+        if config_filename is None:
+            config = load_defaults()["simulation"]
+        else:
+            import yaml
+            with open(config_filename) as f:
+                config = yaml.safe_load(f)
+        timer = Timer.from_config(config)
+        am = cls.ActivityManager.from_config(config, world, policies, timer)
+        return cls(world=world, interaction=interaction, timer=timer, activity_manager=am, epidemiology=epidemiology, **kw)
+
+    def clear_world(self) -> None:
+        """``simulator.py:305-343`` empties every subgroup list; here membership is a per-step
+        byte per person that the next placement overwrites, so there is nothing to clear."""
+
+    # ---- one step -----------------------------------------------------------------------------------
+    def step_params(self, extra_flags: int = 0):
+        date = self.timer.date
+        policies = self.activity_manager.policies
+        self.interaction.beta_reductions = policies.beta_reductions(date)
+        comp, tiers = policies.regional_scalars(date, self.world.region_names, self._region_state)
+        beta = self.interaction.beta_table(self.world.beta_rules, comp, tiers)
+        flags = policies.step_flags(date) | extra_flags
+        return self.device.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self.step_ordinal,
+                                       activity_mask=self.activity_manager.activity_mask(), seed=self.seed,
+                                       flags=flags, beta=beta)
+
+    def do_timestep(self, want_stats: bool = True) -> None:
+        activities = self.timer.activities
+        if not activities:
+            return  # simulator.py:377-379
+        params = self.step_params()
+        dev = self.device
+        if self.halo is None:
+            stats = dev.step(params, want_stats=want_stats)
+        else:
+            h = self.halo
+            dev.step_begin(params, h.send.data_ptr())
+            dev.sync()  # the exchange runs on torch's stream
+            h.exchange_people()
+            self._torch_sync()
+            dev.step_interact(h.recv.data_ptr(), h.ret_send.data_ptr())
+            dev.sync()
+            h.exchange_infections()
+            self._torch_sync()
+            stats = dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
+        self.step_ordinal += 1
+        if stats is not None:
+            self.last_stats = stats
+            self.history.append(dict(date=self.timer.date, now=self.timer.now, **stats))
+
+    def _torch_sync(self):
+        if self.halo is not None and self.halo.send.is_cuda:
+            self.halo.torch.cuda.current_stream().synchronize()
+
+    def run(self) -> None:
+        """``Simulator.run`` (``simulator.py:628-707``)."""
+        while self.timer.date < self.timer.final_date:
+            if self.epidemiology is not None:
+                self.epidemiology.infection_seeds_timestep(self, self.timer)
+            self.do_timestep()
+            next(self.timer)
+
+    def daily_summary(self) -> List[Dict[str, object]]:
+        """Daily curves in the spirit of ``summary.csv`` (``records_writer.py:151-164``), whole domain."""
+        days: Dict[datetime.date, Dict[str, object]] = {}
+        for h in self.history:
+            d = h["date"].date()
+            row = days.setdefault(d, dict(time_stamp=d, daily_infected=0, daily_deaths=0, daily_recovered=0))
+            row["daily_infected"] += h["n_new_infections"]
+            row["daily_deaths"] += h["n_deaths_step"]
+            row["daily_recovered"] += h["n_recovered_step"]
+            row["current_infected"] = h["n_infected"]
+            row["current_hospitalised"] = h["n_hospitalised"]
+            row["current_intensive_care"] = h["n_icu"]
+        return [days[k] for k in sorted(days)]
