@@ -80,6 +80,7 @@ extern "C" {
 #define JB_MAX_SUPERGROUPS 32
 #define JB_MAX_VARIANTS 4
 #define JB_N_TPAR 5         /* transmission parameters per infection                       */
+#define JB_DYN_BIN_CAP 4096 /* dynamic members (patients) per group and step                */
 
 /* transmission profile types (infection_selector.py:130-143) */
 #define JB_TRANS_CONSTANT 0 /* par0 = probability                                          */

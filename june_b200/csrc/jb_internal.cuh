@@ -46,8 +46,9 @@ struct GroupArgs {
   const double* cm;
   const double* beta;
   const double* beta_scale;
-  const uint64_t* dyn_key;   // sorted dynamic members (or null)
-  const uint32_t* dyn_off;   // per group offsets into dyn_key (or null)
+  const uint32_t* dyn_cnt;   // per dynamic group: members scattered this step (or null)
+  const uint32_t* dyn_bin;   // [bins][bin_cap] entries (lsg << 28) | person
+  uint32_t bin_cap, dyn_bin_base;
   uint32_t g0, g1;
   int dim, kind, L;
   uint32_t N, NP;
@@ -115,9 +116,9 @@ struct JbWorld {
   double* inject = nullptr;
   size_t inject_cap = 0, n_inject = 0;
   uint32_t *draw_cnt = nullptr, *draw_base = nullptr;
-  uint64_t *dyn_key = nullptr, *dyn_key_alt = nullptr;
-  uint32_t* dyn_off = nullptr;
-  uint32_t dyn_cap = 0;
+  uint32_t *dyn_cnt = nullptr, *dyn_bin = nullptr;
+  uint32_t n_bins = 0, bin_cap = 0;
+  uint32_t sg_bin_base[JB_MAX_SUPERGROUPS] = {};
   bool any_dynamic = false;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;

@@ -18,64 +18,101 @@
 #define JB_FULL 0xFFFFFFFFu
 
 // ------------------------------------------------------------------------------------------
-// Stage A: placement.  One thread per resident.  The reference walks the activity hierarchy
-// and takes the first activity with a non-None subgroup (activity_manager.py:380-398); stay-home
-// policies reduce the activity list to (medical_facility, residence)
-// (individual_policies.py:87-119).  Here the chosen activity is written into the low bits of the
-// person's state byte; fixed-membership subgroups test that byte instead of being scattered
-// into.  People whose subgroup is dynamic (hospital patients) are appended to the dynamic list.
+// Stage A: placement.  The reference walks the activity hierarchy per person and takes the first
+// activity with a non-None subgroup (activity_manager.py:380-398); stay-home policies reduce the
+// activity list to (medical_facility, residence) (individual_policies.py:87-119).  Here the
+// chosen activity is written into the low bits of the person's state byte; fixed-membership
+// subgroups test that byte instead of being scattered into.  People whose subgroup is dynamic
+// (hospital patients) are scattered into the per-group bin of their ward.
+// 16 persons per thread (one 128-bit load of each byte array), grid-stride, counters reduced in
+// registers -> shared memory -> one global atomic per block and counter.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_place(uint8_t* __restrict__ pstate, const uint8_t* __restrict__ phas, const int32_t* __restrict__ pmed,
-        uint64_t* __restrict__ dyn_key, uint32_t dyn_cap, uint32_t* __restrict__ counters, uint32_t N,
-        uint32_t activity_mask, uint32_t flags) {
-  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+struct DynRanges {
+  uint32_t n;
+  uint32_t first[4], count[4], bin_base[4];
+};
+
+struct PlaceArgs {
+  uint8_t* pstate;
+  const uint8_t* phas;
+  const int32_t* pmed;
+  uint32_t* dyn_cnt;   // per dynamic group: members appended this step
+  uint32_t* dyn_bin;   // [n_bins][bin_cap] entries (lsg << 28) | person
+  uint32_t bin_cap;
+  DynRanges dr;
+  uint32_t* counters;
+  uint32_t N, activity_mask, flags;
+};
+
+__device__ __forceinline__ uint32_t jb_place_one(const PlaceArgs& a, uint32_t p, uint32_t st, uint32_t has,
+                                                 uint32_t* cnt) {
   uint32_t act = JB_ACT_NONE;
-  uint32_t st = 0;
-  if (p < N) st = pstate[p];
-  if (p < N && !(st & JB_PS_DEAD)) {
-    uint32_t allowed = activity_mask;
-    if ((flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE))
+  if (!(st & JB_PS_DEAD)) {
+    uint32_t allowed = a.activity_mask;
+    if ((a.flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE))
       allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
-    uint32_t has = phas[p];
     if (st & JB_PS_MEDICAL) has |= 1u << JB_ACT_MEDICAL;
-    uint32_t cand = allowed & has;
+    const uint32_t cand = allowed & has;
     if (cand) {
       act = __ffs(cand) - 1;  // hierarchy order == bit order
       if (act == JB_ACT_MEDICAL) {
-        uint32_t med = (uint32_t)pmed[p];  // (hospital group << 8) | local subgroup
-        uint32_t i = atomicAdd(&counters[CNT_DYN], 1u);
-        if (i < dyn_cap)
-          dyn_key[i] = ((uint64_t)(med >> 8) << 36) | ((uint64_t)(med & 0xFFu) << 28) | (uint64_t)p;
-        else
-          atomicAdd(&counters[CNT_OVERFLOW], 1u);
+        const uint32_t med = (uint32_t)a.pmed[p];  // (hospital group << 8) | local subgroup
+        const uint32_t g = med >> 8;
+        bool ok = false;
+        for (uint32_t r = 0; r < a.dr.n; ++r) {
+          if (g - a.dr.first[r] < a.dr.count[r]) {
+            const uint32_t bin = a.dr.bin_base[r] + (g - a.dr.first[r]);
+            const uint32_t i = atomicAdd(&a.dyn_cnt[bin], 1u);
+            if (i < a.bin_cap) { a.dyn_bin[(size_t)bin * a.bin_cap + i] = ((med & 0xFu) << 28) | p; ok = true; }
+            break;
+          }
+        }
+        if (!ok) atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
       }
+      cnt[act]++;
     } else {
-      atomicAdd(&counters[CNT_NOACT], 1u);
+      cnt[JB_N_ACT]++;
     }
   }
-  if (p < N) pstate[p] = (uint8_t)((st & ~JB_PS_ACT_MASK) | act);
-  // persons per activity (feeds the algorithmic-byte accounting and the conservation check)
-#pragma unroll
-  for (uint32_t a = 0; a < JB_N_ACT; ++a) {
-    uint32_t m = __ballot_sync(JB_FULL, act == a);
-    if (m && (threadIdx.x & 31) == 0) atomicAdd(&counters[CNT_ACT0 + a], (uint32_t)__popc(m));
-  }
+  return (st & ~JB_PS_ACT_MASK) | act;
 }
 
-// Per-group offsets into the sorted dynamic-member list (lower bound of group g).
-__global__ void k_dyn_offsets(const uint64_t* __restrict__ key, uint32_t n_cap, const uint32_t* __restrict__ counters,
-                              uint32_t* __restrict__ dyn_off, uint32_t g0, uint32_t g1) {
-  uint32_t g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (g > g1) return;
-  uint32_t n = min(counters[CNT_DYN], n_cap);
-  uint64_t target = (uint64_t)g << 36;
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (key[mid] < target) lo = mid + 1; else hi = mid;
+__global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
+  __shared__ uint32_t s_cnt[JB_N_ACT + 1];
+  if (threadIdx.x <= JB_N_ACT) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t cnt[JB_N_ACT + 1] = {0, 0, 0, 0, 0, 0};
+  const uint32_t n_chunks = (a.N + 15) / 16;
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
+    const uint32_t p0 = c * 16;
+    if (p0 + 16 <= a.N) {
+      uint4 sv = *reinterpret_cast<const uint4*>(a.pstate + p0);
+      const uint4 hv = *reinterpret_cast<const uint4*>(a.phas + p0);
+      uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t st = (sw[q] >> (8 * b)) & 0xFFu, has = (hw[q] >> (8 * b)) & 0xFFu;
+          o |= jb_place_one(a, p0 + q * 4 + b, st, has, cnt) << (8 * b);
+        }
+        sw[q] = o;
+      }
+      *reinterpret_cast<uint4*>(a.pstate + p0) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+    } else {
+      for (uint32_t p = p0; p < a.N; ++p) a.pstate[p] = (uint8_t)jb_place_one(a, p, a.pstate[p], a.phas[p], cnt);
+    }
   }
-  dyn_off[g] = lo;
+#pragma unroll
+  for (int k = 0; k <= JB_N_ACT; ++k) {
+    const uint32_t v = __reduce_add_sync(JB_FULL, cnt[k]);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < JB_N_ACT && s_cnt[threadIdx.x]) atomicAdd(&a.counters[CNT_ACT0 + threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x == JB_N_ACT && s_cnt[JB_N_ACT]) atomicAdd(&a.counters[CNT_NOACT], s_cnt[JB_N_ACT]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -242,9 +279,10 @@ struct JbMember {
   bool present, infected;
 };
 
-// Member `idx` of group (static registered slots first, then the sorted dynamic members).
+// Member `idx` of group (static registered slots first, then the sorted dynamic members, which
+// the warp has staged in shared memory as (lsg << 28) | person).
 __device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t idx, uint32_t b, uint32_t ns,
-                                                   uint32_t db, uint32_t ntot) {
+                                                   const uint32_t* dyn_s, uint32_t ntot) {
   JbMember mbr;
   mbr.p = 0; mbr.lsg = 0xFFFFu; mbr.present = false; mbr.infected = false;
   if (idx >= ntot) return mbr;
@@ -257,9 +295,9 @@ __device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t 
     mbr.lsg = JB_INFO_LSG(info);
     mbr.present = (st & JB_PS_ACT_MASK) == JB_INFO_ACT(info);
   } else {
-    uint64_t k = a.dyn_key[db + (idx - ns)];
-    mbr.p = (uint32_t)(k & 0x0FFFFFFFull);
-    mbr.lsg = (uint32_t)((k >> 28) & 0xFFull);
+    uint32_t k = dyn_s[idx - ns];
+    mbr.p = k & 0x0FFFFFFFu;
+    mbr.lsg = k >> 28;
     st = a.pstate[mbr.p];
     mbr.present = true;
   }
@@ -268,9 +306,10 @@ __device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t 
 }
 
 // Shared memory per warp: n[L] u32 | sus_static[L] u32 | sus_dyn[L] u32 | pad | T[V*L] f64 | row[V*L] f64
-__host__ __device__ inline size_t jb_warp_smem_bytes(int L, int V) {
+// | dynamic member staging (bin_cap u32, only for supergroups with dynamic members)
+__host__ __device__ inline size_t jb_warp_smem_bytes(int L, int V, uint32_t bin_cap) {
   size_t ints = ((size_t)3 * L + 1) & ~(size_t)1;
-  return ints * 4 + (size_t)2 * V * L * 8;
+  return ints * 4 + (size_t)2 * V * L * 8 + (size_t)bin_cap * 4;
 }
 
 template <int VM>
@@ -280,16 +319,42 @@ __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ Gro
   const uint32_t g = a.g0 + blockIdx.x * (blockDim.x >> 5) + wib;
   if (g >= a.g1) return;
   const int L = a.L, V = (VM > 1) ? a.V : 1;
-  unsigned char* base = smem_raw + (size_t)wib * jb_warp_smem_bytes(L, V);
+  const uint32_t bin_cap = a.dyn_cnt ? a.bin_cap : 0u;
+  unsigned char* base = smem_raw + (size_t)wib * jb_warp_smem_bytes(L, V, bin_cap);
   uint32_t* n_l = (uint32_t*)base;
   uint32_t* ss_l = n_l + L;   // susceptibles among static members, per subgroup
   uint32_t* sd_l = ss_l + L;  // susceptibles among dynamic members
   double* T_l = (double*)(base + ((((size_t)3 * L + 1) & ~(size_t)1) * 4));
   double* row_l = T_l + (size_t)V * L;
+  uint32_t* dyn_s = (uint32_t*)(row_l + (size_t)V * L);
 
   const uint32_t b = a.grp_off[g], ns = a.grp_off[g + 1] - b;
-  uint32_t db = 0, nd = 0;
-  if (a.dyn_off) { db = a.dyn_off[g]; nd = a.dyn_off[g + 1] - db; }
+  uint32_t nd = 0;
+  if (a.dyn_cnt) {
+    // stage this group's bin and sort it: members arrive in arbitrary (atomic) order, the
+    // reference order is (subgroup, person) -- bitonic sort by the warp in shared memory
+    const uint32_t bin = a.dyn_bin_base + (g - a.g0);
+    nd = min(a.dyn_cnt[bin], bin_cap);
+    if (nd) {
+      uint32_t npad = 32;
+      while (npad < nd) npad <<= 1;
+      const uint32_t* src = a.dyn_bin + (size_t)bin * bin_cap;
+      for (uint32_t i = lane; i < npad; i += 32) dyn_s[i] = i < nd ? src[i] : 0xFFFFFFFFu;
+      __syncwarp();
+      for (uint32_t k = 2; k <= npad; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t i = lane; i < npad; i += 32) {
+            const uint32_t ixj = i ^ j;
+            if (ixj > i) {
+              const uint32_t x = dyn_s[i], y = dyn_s[ixj];
+              const bool asc = (i & k) == 0;
+              if ((x > y) == asc) { dyn_s[i] = y; dyn_s[ixj] = x; }
+            }
+          }
+          __syncwarp();
+        }
+    }
+  }
   const uint32_t ntot = ns + nd;
   if (ntot == 0) {
     if (a.mode == 1 && lane == 0) a.draw_cnt[g] = 0;
@@ -319,7 +384,7 @@ __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ Gro
     const uint32_t lo = phase ? ns : 0u, hi = phase ? ntot : ns;
     for (uint32_t it = lo; it < hi; it += 32) {
       const uint32_t idx = it + lane;
-      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, db, ntot);
+      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
       const uint32_t key = mb.lsg;
       const uint32_t sus = (mb.present && !mb.infected) ? 1u : 0u;
       uint32_t packed = (mb.present ? 1u : 0u) | (sus << 16);
@@ -393,7 +458,7 @@ __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ Gro
     uint32_t* run = phase ? sd_l : ss_l;
     for (uint32_t it = lo; it < hi; it += 32) {
       const uint32_t idx = it + lane;
-      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, db, ntot);
+      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
       const bool sus = mb.present && !mb.infected && mb.lsg < (uint32_t)Lg;
       uint32_t ordinal = 0;
       if (a.inject) {
@@ -449,8 +514,17 @@ struct NewInfArgs {
 };
 
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a) {
+  // the disease tables are walked with data-dependent indices: stage them in shared memory once
+  // per block instead of chasing them through L2 for every sample
+  __shared__ __align__(8) unsigned char s_dis[sizeof(DiseaseDev)];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.dis);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_dis);
+    for (uint32_t i = threadIdx.x; i < sizeof(DiseaseDev) / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
   const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap) : a.count_host;
-  const DiseaseDev& D = *a.dis;
+  const DiseaseDev& D = *reinterpret_cast<const DiseaseDev*>(s_dis);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = a.member[i];
     const uint32_t var = a.variant ? a.variant[i] : 0u;
@@ -534,7 +608,12 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
 // ------------------------------------------------------------------------------------------
 // Stage C2: health update for every active infection slot (epidemiology.py:217-303).
 // ------------------------------------------------------------------------------------------
+struct DiseaseMasks {
+  int trans_type, rec_mask, dead_mask, hosp_mask, icu_mask, severe_mask;
+};
+
 struct HealthArgs {
+  DiseaseMasks masks;
   uint32_t C;
   double t_now;       // timer.now + timer.duration
   uint32_t flags;
@@ -555,7 +634,7 @@ __device__ __forceinline__ double jb_gamma_pdf(double x, double a, double loc, d
 
 __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthArgs a) {
   const uint32_t hw = min(a.counters[CNT_SLOTS_HW], a.C);
-  const DiseaseDev& D = *a.dis;
+  const DiseaseMasks D = a.masks;
   uint32_t c_inf = 0, c_hosp = 0, c_icu = 0;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < hw; s += gridDim.x * blockDim.x) {
     const int32_t p = a.inf_person[s];

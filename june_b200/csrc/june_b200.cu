@@ -198,16 +198,20 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_alloc(&w->draw_cnt, (size_t)w->G + 1));
   TRY(dev_alloc(&w->draw_base, (size_t)w->G + 1));
   if (w->any_dynamic) {
-    w->dyn_cap = std::max<uint32_t>(4096u, w->N / 32);
-    TRY(dev_alloc(&w->dyn_key, w->dyn_cap));
-    TRY(dev_alloc(&w->dyn_key_alt, w->dyn_cap));
-    TRY(dev_alloc(&w->dyn_off, (size_t)w->G + 2));
+    // one bin of JB_DYN_BIN_CAP entries per group of a dynamic supergroup (hospital wards)
+    w->bin_cap = JB_DYN_BIN_CAP;
+    int n_ranges = 0;
+    for (size_t k = 0; k < w->sgs.size(); ++k)
+      if (w->sgs[k].has_dynamic) { w->sg_bin_base[k] = w->n_bins; w->n_bins += w->sgs[k].n_groups; ++n_ranges; }
+    REQUIRE(n_ranges <= 4, "at most 4 supergroups may have dynamic members");
+    REQUIRE(w->n_bins <= 65536, "too many groups with dynamic members (bins are per group)");
+    TRY(dev_alloc(&w->dyn_cnt, w->n_bins));
+    TRY(dev_alloc(&w->dyn_bin, (size_t)w->n_bins * w->bin_cap));
   }
   {
-    size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, b1, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)std::max(1u, w->dyn_cap), 0, 64, s);
+    size_t b2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, b2, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(w->G + 1), s);
-    w->cub_tmp_bytes = std::max(b1, b2) + 256;
+    w->cub_tmp_bytes = b2 + 256;
     CK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
   }
   CK(cudaMallocHost((void**)&w->h_beta, sizeof(double) * std::max<size_t>(1, (size_t)w->n_beta * w->R)));
@@ -234,7 +238,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->pstate, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->counters, w->newinf_member, w->newinf_var,
-                  w->beta, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_key, w->dyn_key_alt, w->dyn_off,
+                  w->beta, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_cnt, w->dyn_bin,
                   w->cub_tmp};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -409,8 +413,10 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   a.reg_member = w->reg_member; a.reg_info = w->reg_info;
   a.pstate = w->pstate; a.pvar = w->pvar; a.susc = w->susc; a.trans = w->trans; a.halo_gid = w->halo_gid;
   a.school_years = w->school_years; a.cm = w->cm + sg.cm_offset; a.beta = w->beta; a.beta_scale = w->beta_scale;
-  a.dyn_key = sg.has_dynamic ? w->dyn_key : nullptr;
-  a.dyn_off = sg.has_dynamic ? w->dyn_off : nullptr;
+  a.dyn_cnt = sg.has_dynamic ? w->dyn_cnt : nullptr;
+  a.dyn_bin = sg.has_dynamic ? w->dyn_bin : nullptr;
+  a.bin_cap = w->bin_cap;
+  a.dyn_bin_base = w->sg_bin_base[&sg - w->sgs.data()];
   a.g0 = sg.first_group; a.g1 = sg.first_group + sg.n_groups;
   a.dim = sg.dim; a.kind = sg.kind; a.L = L;
   a.N = w->N; a.NP = w->NP; a.V = (int)w->V; a.R = (int)w->R;
@@ -441,7 +447,7 @@ static int launch_groups(JbWorld* w, int mode) {
       else k_groups_thread<JB_MAX_VARIANTS><<<blocks, 256, 0, w->stream>>>(a);
     } else {
       const int wpb = 4;
-      size_t smem = jb_warp_smem_bytes(a.L, (int)w->V) * wpb;
+      size_t smem = jb_warp_smem_bytes(a.L, (int)w->V, sg.has_dynamic ? w->bin_cap : 0u) * wpb;
       unsigned blocks = (sg.n_groups + wpb - 1) / wpb;
       if (w->V == 1) k_groups_warp<1><<<blocks, wpb * 32, smem, w->stream>>>(a);
       else k_groups_warp<JB_MAX_VARIANTS><<<blocks, wpb * 32, smem, w->stream>>>(a);
@@ -487,15 +493,24 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   memcpy(w->h_beta, p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
   CK(cudaMemcpyAsync(w->beta, w->h_beta, sizeof(double) * (size_t)w->n_beta * w->R, cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(w->counters, 0, CNT_STEP_END * 4, s));
-  if (w->any_dynamic) CK(cudaMemsetAsync(w->dyn_key, 0xFF, (size_t)w->dyn_cap * 8, s));
+  if (w->any_dynamic) CK(cudaMemsetAsync(w->dyn_cnt, 0, (size_t)w->n_bins * 4, s));
   if (p->flags & JB_STEP_RECORD_LAMBDA) {
     if (!w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
     k_fill_f64<<<(w->NP + 255) / 256, 256, 0, s>>>(w->lambda, w->NP, std::numeric_limits<double>::quiet_NaN());
     w->launches++;
   }
   if (w->N) {
-    k_place<<<(w->N + 255) / 256, 256, 0, s>>>(w->pstate, w->phas, w->pmed, w->dyn_key, w->dyn_cap, w->counters,
-                                               w->N, p->activity_mask, p->flags);
+    PlaceArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.pstate = w->pstate; pa.phas = w->phas; pa.pmed = w->pmed; pa.dyn_cnt = w->dyn_cnt; pa.dyn_bin = w->dyn_bin;
+    pa.bin_cap = w->bin_cap; pa.counters = w->counters; pa.N = w->N; pa.activity_mask = p->activity_mask; pa.flags = p->flags;
+    for (size_t k = 0; k < w->sgs.size(); ++k)
+      if (w->sgs[k].has_dynamic) {
+        uint32_t r = pa.dr.n++;
+        pa.dr.first[r] = w->sgs[k].first_group; pa.dr.count[r] = w->sgs[k].n_groups; pa.dr.bin_base[r] = w->sg_bin_base[k];
+      }
+    const uint32_t chunks = (w->N + 15) / 16;
+    k_place<<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     CK(cudaGetLastError());
     w->launches++;
   }
@@ -520,19 +535,6 @@ extern "C" int jb_step_interact(JbWorld* w, const void* d_recv, void* d_ret_send
                                                      w->pstate, w->pvar, w->susc, w->trans, (uint8_t*)d_ret_send);
     CK(cudaGetLastError());
     w->launches++;
-  }
-  if (w->any_dynamic) {
-    size_t tmp = w->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortKeys(w->cub_tmp, tmp, w->dyn_key, w->dyn_key_alt, (int)w->dyn_cap, 0, 64, s));
-    std::swap(w->dyn_key, w->dyn_key_alt);
-    w->launches += 4;
-    for (const JbSupergroup& sg : w->sgs) {
-      if (!sg.has_dynamic || !sg.n_groups) continue;
-      k_dyn_offsets<<<(sg.n_groups + 1 + 127) / 128, 128, 0, s>>>(w->dyn_key, w->dyn_cap, w->counters, w->dyn_off,
-                                                                 sg.first_group, sg.first_group + sg.n_groups);
-      CK(cudaGetLastError());
-      w->launches++;
-    }
   }
   if (w->timing) CK(cudaEventRecord(w->ev_int0, s));
   if (p.flags & JB_STEP_INJECT_UNIFORMS) {
@@ -584,6 +586,9 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
     HealthArgs a;
     memset(&a, 0, sizeof(a));
     a.C = w->C; a.t_now = p.now + p.delta_time; a.flags = p.flags; a.dis = w->dis;
+    a.masks.trans_type = w->dis_host.trans_type; a.masks.rec_mask = w->dis_host.rec_mask;
+    a.masks.dead_mask = w->dis_host.dead_mask; a.masks.hosp_mask = w->dis_host.hosp_mask;
+    a.masks.icu_mask = w->dis_host.icu_mask; a.masks.severe_mask = w->dis_host.severe_mask;
     a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
     a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
     a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
