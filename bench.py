@@ -182,7 +182,7 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     person_steps = 0
-    act_res, n_alive_last = [], n_people
+    n_alive_last = n_people
     barrier()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -191,16 +191,31 @@ def run_gpu(args):
         st = sim.last_stats
         n_alive_last = n_people - st["n_dead_total"]
         person_steps += n_alive_last
-        act_res.append(st["n_by_activity"][ACT_RESIDENCE])
         next(sim.timer)
     barrier()
     t_wall1 = time.perf_counter()
     clocks = sampler.stop()
     tim = dev.timing_read()
-    per_sg = dev.timing_read_supergroups()
-    dev.timing_enable(False)
     step_ms = tim["step_ms"] / max(1, tim["n_steps"])
     launches = int(tim["n_launches"])
+
+    # ---- leg 1b: roofline of the interaction kernels.  In the normal step the supergroups'
+    # kernels overlap on side streams; here they run one after the other on the main stream so
+    # that the CUDA-event bracket around each supergroup's launches measures that kernel alone.
+    dev.set_concurrency(False)
+    dev.timing_read(reset=True)
+    n_roof = min(args.steps, 27)
+    act_res = []
+    for _ in range(n_roof):
+        flush_l2()
+        sim.do_timestep(want_stats=True)
+        act_res.append(sim.last_stats["n_by_activity"][ACT_RESIDENCE])
+        next(sim.timer)
+    barrier()
+    tim_serial = dev.timing_read()
+    per_sg = dev.timing_read_supergroups()
+    dev.set_concurrency(True)
+    dev.timing_enable(False)
 
     # ---- leg 2: end to end through the public API (host params h2d, stats d2h, wall clock) -----
     barrier()
@@ -244,11 +259,13 @@ def run_gpu(args):
     a_bytes = interaction_bytes(world, sg, present)
     t_launch_s = per_sg[k_top]["ms"] / n_launch * 1e-3
     achieved = a_bytes / t_launch_s / 1e9 if t_launch_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_groups_thread<1>" if sg.launch_mode == 0 else "k_groups_warp<1>",
+    roofline = {"bound": "hbm", "kernel": ("k_detect+k_process" if sg.launch_mode == 0 else "k_groups_warp"),
                 "supergroup": sg.name, "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                 "bytes_per_launch": a_bytes, "us_per_launch": round(t_launch_s * 1e6, 2),
-                "interaction_ms_per_step": round(tim["interaction_ms"] / max(1, tim["n_steps"]), 4)}
+                "interaction_ms_per_step": round(tim["interaction_ms"] / max(1, tim["n_steps"]), 4),
+                "interaction_ms_per_step_serial": round(tim_serial["interaction_ms"] / max(1, tim_serial["n_steps"]), 4),
+                "timing": "CUDA events on the launch stream, supergroup kernels serialised, L2 flushed between steps"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -345,7 +362,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=45)
+    ap.add_argument("--steps", type=int, default=180)
     ap.add_argument("--warmup", type=int, default=9)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--people", type=int, default=0, help="people per GPU (default 2.7 M = BASELINE.json configs[1])")

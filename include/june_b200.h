@@ -284,6 +284,9 @@ int jb_fetch_summary(JbWorld* w, uint32_t* counts);
 /* Kernel timing hooks for bench.py: CUDA-event time (ms) of the interaction kernels and of
  * the whole step, measured on the library's stream, accumulated since the last reset. */
 int jb_timing_enable(JbWorld* w, int on);
+/* on = 1 (default): the interaction kernels of different supergroups run concurrently on side
+ * streams; on = 0: serially on the main stream (isolated per-kernel timings). */
+int jb_set_concurrency(JbWorld* w, int on);
 int jb_timing_read(JbWorld* w, double* interaction_ms, double* step_ms, uint64_t* n_steps,
                    uint64_t* n_launches, int reset);
 /* Algorithmic bytes of the interaction kernels for the last step. */

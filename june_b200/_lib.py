@@ -97,6 +97,7 @@ ABI_SYMBOLS = [
     "inject_uniforms", "infect", "upload_infections", "step", "step_begin", "step_interact", "step_finish",
     "set_halo", "halo_record_size", "halo_return_size", "sync", "fetch_new_infections", "fetch_person_state",
     "fetch_lambda", "fetch_infections", "fetch_summary", "timing_enable", "timing_read", "last_step_bytes",
+    "set_concurrency",
 ]
 
 
@@ -150,7 +151,8 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("timing_read").argtypes = [vp, dp, dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
     f("last_step_bytes").argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp]),
-                        ("timing_read_supergroups", [vp, dp, C.POINTER(C.c_uint64), C.c_int])):
+                        ("timing_read_supergroups", [vp, dp, C.POINTER(C.c_uint64), C.c_int]),
+                        ("set_concurrency", [vp, C.c_int])):
         if hasattr(lib, prefix + extra):
             getattr(lib, prefix + extra).argtypes = args
     if hasattr(lib, prefix + "halo_record_size_w"):

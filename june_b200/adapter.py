@@ -58,8 +58,13 @@ def school_beta_key(sector) -> str:
     return "primary_school"
 
 
+# specs whose groups go through the warp-per-group kernel: per-school matrices, dynamic members
+# (hospital wards), contact matrices larger than 4x4.  Everything else is tiled.
+WARP_MODE_SPECS = ("school", "hospital", "university")
+
+
 def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sector_betas: Dict[str, float],
-                  thread_mode_specs=("household",)) -> WorldSoA:
+                  warp_mode_specs=WARP_MODE_SPECS) -> WorldSoA:
     people = list(world.people)
     n = len(people)
     pidx = {id(p): i for i, p in enumerate(people)}
@@ -144,7 +149,7 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
         has_dyn = 1 if spec == "hospital" else 0
         supergroups.append(Supergroup(name=name, spec=spec, activity=ACTIVITY_CODES[act], first_group=first,
                                       n_groups=len(members), kind=kind,
-                                      launch_mode=0 if spec in thread_mode_specs else 1, has_dynamic=has_dyn))
+                                      launch_mode=1 if spec in warp_mode_specs else 0, has_dynamic=has_dyn))
 
     # ---- registered members -----------------------------------------------------------------
     lsg_of: Dict[int, Tuple[int, int]] = {}

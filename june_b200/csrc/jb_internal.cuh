@@ -19,6 +19,8 @@ enum {
   CNT_OVERFLOW,        // a capacity was exceeded
   CNT_ACT0,            // persons placed per activity (5 words: JB_ACT_MEDICAL..JB_ACT_RESIDENCE)
   CNT_ACT4 = CNT_ACT0 + 4,
+  CNT_WORK0,           // per-supergroup work-list lengths (JB_MAX_SUPERGROUPS words)
+  CNT_WORK_LAST = CNT_WORK0 + JB_MAX_SUPERGROUPS - 1,
   CNT_STEP_END,        // ---- everything above is zeroed at the start of every step ----
   CNT_SLOTS_HW = CNT_STEP_END,  // infection slot high-water mark
   CNT_DEAD_TOTAL,
@@ -50,6 +52,15 @@ struct GroupArgs {
   const uint32_t* dyn_bin;   // [bins][bin_cap] entries (lsg << 28) | person
   uint32_t bin_cap, dyn_bin_base;
   uint32_t g0, g1;
+  const uint32_t* group_list; // explicit groups for the warp kernel (big groups), or null = [g0, g1)
+  uint32_t n_list;
+  const uint32_t* int2ext;    // internal -> caller person index
+  const uint32_t* tile_group0;
+  const uint32_t* tp_member;
+  const uint16_t* tp_info;
+  uint32_t n_tiles, stream_base;
+  uint2* work_items;          // groups that must timestep, found by k_detect
+  uint32_t* work_cnt;
   int dim, kind, L;
   uint32_t N, NP;
   int V, R;
@@ -79,10 +90,31 @@ struct DiseaseDev {
   JbDist trans_par[6];
 };
 
+// Tile decomposition of one supergroup (built once at world create).
+struct SgTiles {
+  int mode = 0;               // 0 = warp per group only, 1 = gather tiles, 2 = stream tiles
+  uint32_t n_tiles = 0, stream_base = 0, n_big = 0;
+  uint32_t* tile_group0 = nullptr;
+  uint32_t* tp_member = nullptr;
+  uint16_t* tp_info = nullptr;
+  uint32_t* big_list = nullptr;  // groups too large for a tile -> warp kernel
+  uint2* work_items = nullptr;   // capacity = number of groups of the supergroup
+};
+
 struct JbWorld {
   int device = 0;
   cudaStream_t stream = nullptr;
-  uint32_t N = 0, H = 0, NP = 0, G = 0, M = 0, V = 1, R = 1, SA = 0, C = 0, newinf_cap = 0;
+  // the interaction kernels of the active supergroups are independent: they run concurrently on
+  // side streams forked from / joined into `stream`
+  cudaStream_t side[JB_MAX_SUPERGROUPS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[JB_MAX_SUPERGROUPS] = {};
+  bool serial = false;
+  // N = residents in the INTERNAL numbering (includes padding slots of the streamed supergroup),
+  // N_ext = residents as the caller numbers them
+  uint32_t N = 0, N_ext = 0, H = 0, NP = 0, G = 0, M = 0, V = 1, R = 1, SA = 0, C = 0, newinf_cap = 0;
+  std::vector<uint32_t> h_ext2int, h_int2ext;  // int2ext == 0xFFFFFFFF for padding
+  uint32_t* int2ext = nullptr;
+  std::vector<SgTiles> tiles;
   uint32_t n_beta = 0, n_scale = 0, n_out = 0;
   uint64_t id_base = 0;
   std::vector<JbSupergroup> sgs;

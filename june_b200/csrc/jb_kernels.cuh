@@ -118,8 +118,10 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
 // ------------------------------------------------------------------------------------------
 // Stage B: interaction.
 // ------------------------------------------------------------------------------------------
+// Global person id (the Philox counter word): residents are renumbered internally
+// (int2ext maps back to the caller's index), halo persons carry their home domain's id.
 __device__ __forceinline__ uint32_t jb_gid(const GroupArgs& a, uint32_t p) {
-  return p < a.N ? a.gid_base + p : a.halo_gid[p - a.N];
+  return p < a.N ? a.gid_base + a.int2ext[p] : a.halo_gid[p - a.N];
 }
 
 // Append one new infection.
@@ -135,15 +137,14 @@ __device__ __forceinline__ void jb_emit(const GroupArgs& a, uint32_t p, uint32_t
 
 // Bernoulli draw + variant choice for one susceptible (interaction.py:610-641).
 template <int VM>
-__device__ __forceinline__ void jb_draw(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
-                                        uint32_t ordinal) {
+__device__ __forceinline__ void jb_draw_core(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
+                                             uint32_t ordinal) {
   double u;
   if (a.inject) {
     u = ordinal < a.n_inject ? a.inject[ordinal] : 2.0;
   } else {
     u = jb_bernoulli_uniform(a.seed, a.step, jb_gid(a, p));
   }
-  if (a.lambda) a.lambda[p] = lam;
   if (u < 1.0 - exp(-lam)) {
     uint32_t v = 0;
     if (VM > 1 && a.V > 1) {
@@ -160,92 +161,11 @@ __device__ __forceinline__ void jb_draw(const GroupArgs& a, uint32_t p, const do
   }
 }
 
-// One thread per group: fixed contact matrix with dim <= 4, static members only (households).
-// Sums run left to right in member order, exactly like the reference's Python `sum`
-// (interaction.py:463-467).
 template <int VM>
-__global__ void __launch_bounds__(256) k_groups_thread(const __grid_constant__ GroupArgs a) {
-  uint32_t g = a.g0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.g1) return;
-  const uint32_t b = a.grp_off[g], e = a.grp_off[g + 1];
-  int n[4] = {0, 0, 0, 0};
-  double T[VM][4];
-#pragma unroll
-  for (int v = 0; v < VM; ++v)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) T[v][k] = 0.0;
-  int nsus = 0, ninf = 0;
-  for (uint32_t m = b; m < e; ++m) {
-    uint32_t p = a.reg_member[m];
-    uint32_t info = a.reg_info[m];
-    uint32_t st = a.pstate[p];
-    if ((st & JB_PS_ACT_MASK) != JB_INFO_ACT(info)) continue;
-    int l = JB_INFO_LSG(info);
-    if (st & JB_PS_INFECTED) {
-      double t = a.trans[p];
-      int v = (VM > 1) ? a.pvar[p] : 0;
-      ++ninf;
-#pragma unroll
-      for (int vv = 0; vv < VM; ++vv)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (vv == v && k == l) T[vv][k] += t;
-    } else {
-      ++nsus;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) n[k] += (k == l);
-  }
-  const bool must = nsus > 0 && ninf > 0;  // interactive.py:136
-  if (a.mode == 1) {
-    a.draw_cnt[g] = must ? nsus : 0;
-    return;
-  }
-  if (!must) return;
-  const uint32_t gi = a.grp_info[g];
-  const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
-  double row[VM][4];
-#pragma unroll
-  for (int v = 0; v < VM; ++v) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double s = 0.0;
-      if (i < a.dim) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < a.dim && T[v][j] != 0.0) {
-            int nn = (i == j) ? max(1, n[j] - 1) : n[j];  // interaction.py:469-471
-            s += a.cm[i * a.dim + j] * T[v][j] / (double)nn * beta * a.dt;
-          }
-        }
-      }
-      row[v][i] = s;
-    }
-  }
-  uint32_t ord = a.inject ? a.draw_base[g] : 0u;
-  for (uint32_t m = b; m < e; ++m) {
-    uint32_t p = a.reg_member[m];
-    uint32_t info = a.reg_info[m];
-    uint32_t st = a.pstate[p];
-    if ((st & JB_PS_ACT_MASK) != JB_INFO_ACT(info)) continue;
-    if (st & JB_PS_INFECTED) continue;
-    int l = JB_INFO_LSG(info);
-    double lam_v[VM];
-    double lam = 0.0;
-#pragma unroll
-    for (int v = 0; v < VM; ++v) {
-      double r = 0.0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k == l) r = row[v][k];
-      double s = (v < a.V) ? a.susc[(size_t)v * a.NP + p] : 0.0;
-      lam_v[v] = r * s;
-      lam += lam_v[v];
-    }
-    jb_draw<VM>(a, p, lam_v, lam, ord);
-    ++ord;
-  }
-  atomicAdd(&a.counters[CNT_DRAWS], (uint32_t)nsus);
+__device__ __forceinline__ void jb_draw(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
+                                        uint32_t ordinal) {
+  if (a.lambda) a.lambda[p] = lam;
+  jb_draw_core<VM>(a, p, lam_v, lam, ordinal);
 }
 
 // ---- warp-per-group kernel ---------------------------------------------------------------
@@ -316,8 +236,9 @@ template <int VM>
 __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ GroupArgs a) {
   extern __shared__ __align__(8) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t g = a.g0 + blockIdx.x * (blockDim.x >> 5) + wib;
-  if (g >= a.g1) return;
+  const uint32_t gi_ = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (gi_ >= a.n_list) return;
+  const uint32_t g = a.group_list ? a.group_list[gi_] : a.g0 + gi_;
   const int L = a.L, V = (VM > 1) ? a.V : 1;
   const uint32_t bin_cap = a.dyn_cnt ? a.bin_cap : 0u;
   unsigned char* base = smem_raw + (size_t)wib * jb_warp_smem_bytes(L, V, bin_cap);
@@ -380,35 +301,47 @@ __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ Gro
   // Static and dynamic members are walked in separate batches so that the subgroup keys stay
   // sorted inside every 32-wide batch (needed by the segmented scan).
   uint32_t nsus = 0, ninf = 0;
+  constexpr int UB = 4;  // batches in flight: the member -> state -> value chain is latency bound
   for (int phase = 0; phase < 2; ++phase) {
     const uint32_t lo = phase ? ns : 0u, hi = phase ? ntot : ns;
-    for (uint32_t it = lo; it < hi; it += 32) {
-      const uint32_t idx = it + lane;
-      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
-      const uint32_t key = mb.lsg;
-      const uint32_t sus = (mb.present && !mb.infected) ? 1u : 0u;
-      uint32_t packed = (mb.present ? 1u : 0u) | (sus << 16);
-      packed = jb_seg_scan<uint32_t>(packed, key, lane);
-      const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
-      const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
-      if (tail) {
-        n_l[key] += packed & 0xFFFFu;
-        if (phase == 0) ss_l[key] += packed >> 16; else sd_l[key] += packed >> 16;
+    for (uint32_t it0 = lo; it0 < hi; it0 += 32 * UB) {
+      JbMember mbs[UB];
+      double tvs[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const uint32_t idx = it0 + 32 * u + lane;
+        mbs[u] = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
       }
-      nsus += __popc(__ballot_sync(JB_FULL, sus));
-      const bool inf = mb.present && mb.infected;
-      const uint32_t infm = __ballot_sync(JB_FULL, inf);
-      ninf += __popc(infm);
-      if (infm) {
-        const double t = inf ? a.trans[mb.p] : 0.0;
-        const int pv = (VM > 1 && inf) ? a.pvar[mb.p] : 0;
-        for (int v = 0; v < V; ++v) {
-          double tv = (pv == v) ? t : 0.0;
-          tv = jb_seg_scan<double>(tv, key, lane);
-          if (tail) T_l[v * L + key] += tv;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) tvs[u] = (mbs[u].present && mbs[u].infected) ? a.trans[mbs[u].p] : 0.0;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (it0 + 32 * u >= hi) break;
+        const JbMember mb = mbs[u];
+        const uint32_t key = mb.lsg;
+        const uint32_t sus = (mb.present && !mb.infected) ? 1u : 0u;
+        uint32_t packed = (mb.present ? 1u : 0u) | (sus << 16);
+        packed = jb_seg_scan<uint32_t>(packed, key, lane);
+        const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
+        const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
+        if (tail) {
+          n_l[key] += packed & 0xFFFFu;
+          if (phase == 0) ss_l[key] += packed >> 16; else sd_l[key] += packed >> 16;
         }
+        nsus += __popc(__ballot_sync(JB_FULL, sus));
+        const bool inf = mb.present && mb.infected;
+        const uint32_t infm = __ballot_sync(JB_FULL, inf);
+        ninf += __popc(infm);
+        if (infm) {
+          const int pv = (VM > 1 && inf) ? a.pvar[mb.p] : 0;
+          for (int v = 0; v < V; ++v) {
+            double tv = (pv == v) ? tvs[u] : 0.0;
+            tv = jb_seg_scan<double>(tv, key, lane);
+            if (tail) T_l[v * L + key] += tv;
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   const bool must = nsus > 0 && ninf > 0;
@@ -456,36 +389,279 @@ __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ Gro
   for (int phase = 0; phase < 2; ++phase) {
     const uint32_t lo = phase ? ns : 0u, hi = phase ? ntot : ns;
     uint32_t* run = phase ? sd_l : ss_l;
-    for (uint32_t it = lo; it < hi; it += 32) {
-      const uint32_t idx = it + lane;
-      JbMember mb = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
-      const bool sus = mb.present && !mb.infected && mb.lsg < (uint32_t)Lg;
-      uint32_t ordinal = 0;
-      if (a.inject) {
-        const uint32_t key = mb.lsg;
-        const uint32_t incl = jb_seg_scan<uint32_t>(sus ? 1u : 0u, key, lane);
-        const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
-        const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
-        if (sus) ordinal = ord_base + run[key] + incl - 1;
-        __syncwarp();
-        if (tail) run[key] += incl;
-        __syncwarp();
-      }
-      if (sus) {
-        double lam_v[VM];
-        double lam = 0.0;
+    for (uint32_t it0 = lo; it0 < hi; it0 += 32 * UB) {
+      JbMember mbs[UB];
+      double s0[UB];
 #pragma unroll
-        for (int v = 0; v < VM; ++v) {
-          double r = 0.0, s = 0.0;
-          if (v < V) { r = row_l[v * L + mb.lsg]; s = a.susc[(size_t)v * a.NP + mb.p]; }
-          lam_v[v] = r * s;
-          lam += lam_v[v];
+      for (int u = 0; u < UB; ++u) {
+        const uint32_t idx = it0 + 32 * u + lane;
+        mbs[u] = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u)
+        s0[u] = (mbs[u].present && !mbs[u].infected && mbs[u].lsg < (uint32_t)Lg) ? a.susc[mbs[u].p] : 0.0;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (it0 + 32 * u >= hi) break;
+        const JbMember mb = mbs[u];
+        const bool sus = mb.present && !mb.infected && mb.lsg < (uint32_t)Lg;
+        uint32_t ordinal = 0;
+        if (a.inject) {
+          const uint32_t key = mb.lsg;
+          const uint32_t incl = jb_seg_scan<uint32_t>(sus ? 1u : 0u, key, lane);
+          const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
+          const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
+          if (sus) ordinal = ord_base + run[key] + incl - 1;
+          __syncwarp();
+          if (tail) run[key] += incl;
+          __syncwarp();
         }
-        jb_draw<VM>(a, mb.p, lam_v, lam, ordinal);
+        if (sus) {
+          double lam_v[VM];
+          double lam = 0.0;
+#pragma unroll
+          for (int v = 0; v < VM; ++v) {
+            double r = 0.0, sv = 0.0;
+            if (v < V) { r = row_l[v * L + mb.lsg]; sv = (v == 0) ? s0[u] : a.susc[(size_t)v * a.NP + mb.p]; }
+            lam_v[v] = r * sv;
+            lam += lam_v[v];
+          }
+          if (a.lambda) a.lambda[mb.p] = lam;
+          if (lam != 0.0) jb_draw_core<VM>(a, mb.p, lam_v, lam, ordinal);  // lambda == 0 can never infect
+        }
       }
     }
   }
   if (lane == 0) atomicAdd(&a.counters[CNT_DRAWS], nsus);
+}
+
+// ---- tile kernel ----------------------------------------------------------------------------
+// Small groups (<= 32 registered slots, contact matrix dim <= 4, static members) are packed at
+// world-create time into 32-slot tiles that never split a group; one warp processes one tile
+// entirely in registers.  STREAM: the tile's slots ARE the (renumbered) person indices, so the
+// person state is read as a coalesced stream with no index indirection (households).  Otherwise
+// the slot holds the person index and the state is gathered (companies, care homes, ...).
+// Tiles without a present infector are dismissed after reading one state byte per slot.
+#define JB_TI_VALID 0x0800u  // slot holds a person
+#define JB_TI_FIRST 0x1000u  // first slot of its group
+
+// Kernel A: streaming detection.  One thread owns 16 consecutive slots (a lane pair owns a
+// tile): 128-bit loads of the slot descriptors and state bytes, per-tile bit masks exchanged with
+// one shuffle, and for the (few) groups that hold both a present infector and a present
+// susceptible one work item {first slot, length, group} is appended to the supergroup's work list
+// (one atomic per warp iteration).  Everything else in the tile costs a handful of bit operations.
+__device__ __forceinline__ uint32_t jb_byte(const uint4& v, int i) {
+  const uint32_t w = i < 4 ? v.x : i < 8 ? v.y : i < 12 ? v.z : v.w;
+  return (w >> (8 * (i & 3))) & 0xFFu;
+}
+__device__ __forceinline__ uint32_t jb_half(const uint4& v, int i) {
+  const uint32_t w = i < 2 ? v.x : i < 4 ? v.y : i < 6 ? v.z : v.w;
+  return (w >> (16 * (i & 1))) & 0xFFFFu;
+}
+
+template <bool STREAM>
+__global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_chunks = a.n_tiles * 2;
+  const uint32_t n_threads = gridDim.x * blockDim.x;
+  const uint32_t n_iter = (n_chunks + n_threads - 1) / n_threads;
+  uint32_t draws = 0;
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t it = 0; it < n_iter; ++it, c += n_threads) {
+    const bool ok = c < n_chunks;
+    const uint32_t slot0 = c * 16;
+    uint32_t valid = 0, first = 0, pres = 0, inf = 0;
+    if (ok) {
+      const uint4 i0 = *reinterpret_cast<const uint4*>(a.tp_info + slot0);
+      const uint4 i1 = *reinterpret_cast<const uint4*>(a.tp_info + slot0 + 8);
+      uint4 sv = make_uint4(0, 0, 0, 0);
+      uint32_t stg[16];
+      if (STREAM) {
+        sv = *reinterpret_cast<const uint4*>(a.pstate + a.stream_base + slot0);
+      } else {
+        uint32_t mem[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 mv = *reinterpret_cast<const uint4*>(a.tp_member + slot0 + 4 * q);
+          mem[4 * q] = mv.x; mem[4 * q + 1] = mv.y; mem[4 * q + 2] = mv.z; mem[4 * q + 3] = mv.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) stg[i] = mem[i] != 0xFFFFFFFFu ? a.pstate[mem[i]] : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t inf_ = i < 8 ? jb_half(i0, i) : jb_half(i1, i - 8);
+        const uint32_t st = STREAM ? jb_byte(sv, i) : stg[i];
+        const bool v = (inf_ & JB_TI_VALID) != 0;
+        const bool pr = v && (st & JB_PS_ACT_MASK) == JB_INFO_ACT(inf_);
+        valid |= (v ? 1u : 0u) << i;
+        first |= ((v && (inf_ & JB_TI_FIRST)) ? 1u : 0u) << i;
+        pres |= (pr ? 1u : 0u) << i;
+        inf |= ((pr && (st & JB_PS_INFECTED)) ? 1u : 0u) << i;
+      }
+    }
+    // a tile = two neighbouring chunks: exchange the 16-bit masks inside the lane pair
+    const uint32_t mine = first | (pres << 16);
+    const uint32_t other = __shfl_xor_sync(JB_FULL, mine, 1);
+    const uint32_t iv_o = __shfl_xor_sync(JB_FULL, inf | (valid << 16), 1);
+    uint32_t items[4], item_g[4], n_items = 0, n_extra = 0;
+    const uint32_t t = c >> 1;
+    if (ok && !(lane & 1)) {  // the even lane of the pair owns the tile
+      const uint32_t first32 = (first & 0xFFFFu) | (other << 16);
+      const uint32_t pres32 = pres | (other & 0xFFFF0000u);
+      const uint32_t inf32 = inf | (iv_o << 16);
+      const uint32_t n_valid = 32 - __clz((valid & 0xFFFFu) | (iv_o & 0xFFFF0000u));  // valid slots are a prefix
+      const uint32_t sus32 = pres32 & ~inf32;
+      uint32_t rem = inf32;
+      const uint32_t tg0 = rem ? a.tile_group0[t] : 0u;
+      while (rem) {
+        const uint32_t src = __ffs(rem) - 1;
+        const uint32_t le = 0xFFFFFFFFu >> (31 - src);
+        const uint32_t below = first32 & le, above = first32 & ~le;
+        const uint32_t start = 31 - __clz(below | 1u);
+        const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : n_valid;
+        const uint32_t gmask = (end == 32u ? 0xFFFFFFFFu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
+        rem &= ~gmask;
+        const uint32_t nsus = __popc(gmask & sus32);
+        if (!nsus) continue;  // must_timestep needs a susceptible too (interactive.py:136)
+        const uint32_t g = tg0 + __popc(below) - 1u;
+        if (a.mode == 1) { a.draw_cnt[g] = nsus; continue; }
+        draws += nsus;
+        const uint32_t len = end - start;
+        const uint32_t item = ((t * 32 + start) << 5) | (len - 1);
+        if (n_items < 4) { items[n_items] = item; item_g[n_items] = g; ++n_items; }
+        else {  // rare: more than 4 groups with infectors in one tile
+          const uint32_t pos = atomicAdd(a.work_cnt, 1u);
+          a.work_items[pos] = make_uint2(item, g);
+          ++n_extra;
+        }
+      }
+    }
+    (void)n_extra;
+    // one atomic per warp iteration for all buffered items
+    uint32_t incl = n_items;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t up = __shfl_up_sync(JB_FULL, incl, off);
+      if (lane >= off) incl += up;
+    }
+    const uint32_t total = __shfl_sync(JB_FULL, incl, 31);
+    if (total) {
+      uint32_t base = 0;
+      if (lane == 31) base = atomicAdd(a.work_cnt, total);
+      base = __shfl_sync(JB_FULL, base, 31) + incl - n_items;
+      for (uint32_t q = 0; q < n_items; ++q) a.work_items[base + q] = make_uint2(items[q], item_g[q]);
+    }
+  }
+  draws = __reduce_add_sync(JB_FULL, draws);
+  if (lane == 0 && draws) atomicAdd(&a.counters[CNT_DRAWS], draws);
+}
+
+// Kernel B: 8 lanes per group that must timestep (4 groups per warp).  The lanes load the
+// members' state in parallel (one dependent round per 8 members instead of one per member), then
+// every lane accumulates the subgroup sizes and transmission sums from shuffle broadcasts in slot
+// order -- the reference's own left-to-right order (Python `sum`, interaction.py:463-467) -- and
+// finally each lane draws for its own member.
+#define JB_LG 8
+template <bool STREAM, int VM>
+__global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupArgs a) {
+  const uint32_t n_work = *a.work_cnt;
+  const int V = (VM > 1) ? a.V : 1;
+  const int lane = threadIdx.x & 31;
+  const int sl = lane & (JB_LG - 1);
+  const uint32_t submask = 0xFFu << (lane & ~(JB_LG - 1));
+  const uint32_t n_sub = gridDim.x * blockDim.x / JB_LG;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / JB_LG; w < n_work; w += n_sub) {
+    const uint2 item = a.work_items[w];
+    const uint32_t slot0 = item.x >> 5, len = (item.x & 31u) + 1u, g = item.y;
+    int n[4] = {0, 0, 0, 0};
+    double T[VM][4];
+#pragma unroll
+    for (int v = 0; v < VM; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) T[v][k] = 0.0;
+    // my own member of the first chunk stays in registers for the draw pass
+    uint32_t p0 = 0, pk0 = 0;
+    for (uint32_t base = 0; base < len; base += JB_LG) {
+      const uint32_t m = base + sl;
+      uint32_t pk = 0, p = 0;  // lsg | present << 2 | infected << 3 | variant << 4
+      double tv = 0.0;
+      if (m < len) {
+        const uint32_t info = a.tp_info[slot0 + m];
+        p = STREAM ? a.stream_base + slot0 + m : a.tp_member[slot0 + m];
+        const uint32_t st = a.pstate[p];
+        if ((st & JB_PS_ACT_MASK) == JB_INFO_ACT(info)) {
+          pk = (JB_INFO_LSG(info) & 3u) | 4u;
+          if (st & JB_PS_INFECTED) {
+            pk |= 8u;
+            tv = a.trans[p];
+            if (VM > 1) pk |= (uint32_t)a.pvar[p] << 4;
+          }
+        }
+      }
+      if (base == 0) { p0 = p; pk0 = pk; }
+      const uint32_t cnt = min((uint32_t)JB_LG, len - base);
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t q = __shfl_sync(submask, pk, k, JB_LG);
+        const double t = __shfl_sync(submask, tv, k, JB_LG);
+        if (q & 4u) {
+          const int l = q & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) n[j] += (j == l);
+          if (q & 8u) {
+            const int pv = (VM > 1) ? (int)(q >> 4) : 0;
+#pragma unroll
+            for (int v = 0; v < VM; ++v)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (v == pv && j == l) T[v][j] += t;
+          }
+        }
+      }
+    }
+    const uint32_t gi = a.grp_info[g];
+    const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+    uint32_t ord = a.inject ? a.draw_base[g] : 0u;
+    for (uint32_t base = 0; base < len; base += JB_LG) {
+      const uint32_t m = base + sl;
+      uint32_t pk = pk0, p = p0;
+      if (base != 0) {
+        pk = 0;
+        if (m < len) {
+          const uint32_t info = a.tp_info[slot0 + m];
+          p = STREAM ? a.stream_base + slot0 + m : a.tp_member[slot0 + m];
+          const uint32_t st = a.pstate[p];
+          if ((st & JB_PS_ACT_MASK) == JB_INFO_ACT(info)) pk = (JB_INFO_LSG(info) & 3u) | 4u | ((st & JB_PS_INFECTED) ? 8u : 0u);
+        }
+      }
+      const bool sus = (pk & 12u) == 4u;
+      const uint32_t susm = __ballot_sync(submask, sus) >> (lane & ~(JB_LG - 1));
+      if (sus) {
+        const int i = pk & 3;
+        double lam_v[VM];
+        double lam = 0.0;
+#pragma unroll
+        for (int v = 0; v < VM; ++v) {
+          double r = 0.0;
+          if (v < V) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < a.dim && T[v][j] != 0.0) {
+                const int nn = (i == j) ? max(1, n[j] - 1) : n[j];  // interaction.py:469-471
+                r += a.cm[i * a.dim + j] * T[v][j] / (double)nn * beta * a.dt;
+              }
+            r *= a.susc[(size_t)v * a.NP + p];
+          }
+          lam_v[v] = r;
+          lam += r;
+        }
+        if (a.lambda) a.lambda[p] = lam;
+        if (lam != 0.0)  // lambda == 0 can never infect
+          jb_draw_core<VM>(a, p, lam_v, lam, ord + __popc(susm & ((1u << sl) - 1u)));
+      }
+      ord += __popc(susm & 0xFFu);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -500,6 +676,7 @@ struct NewInfArgs {
   uint32_t N, NP, C;
   int V;
   uint32_t gid_base;
+  const uint32_t* int2ext;
   double now;
   uint64_t seed;
   uint32_t step;
@@ -511,6 +688,7 @@ struct NewInfArgs {
   uint8_t* inf_stage; uint8_t* inf_nst; uint8_t* inf_var; int8_t* inf_tag; int8_t* inf_maxtag; int8_t* traj_tag;
   uint32_t* counters;
   uint8_t* halo_ret;        // per halo person: variant+1 if infected here (or null)
+  int skip_local;           // only route halo infections (the host creates the local ones)
 };
 
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a) {
@@ -533,12 +711,13 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
       atomicAdd(&a.counters[CNT_HALO_INF], 1u);
       continue;
     }
+    if (a.skip_local) continue;
     uint32_t st = a.pstate[p];
     if (st & (JB_PS_INFECTED | JB_PS_DEAD)) continue;  // cannot happen within a step; guards seeding
     const uint32_t slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);
     if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
     JbStream rs;
-    jb_stream_init(rs, a.seed, a.step, a.gid_base + p, JB_STREAM_NEWINF);
+    jb_stream_init(rs, a.seed, a.step, a.gid_base + a.int2ext[p], JB_STREAM_NEWINF);
     // symptoms: max_severity -> outcome slot (symptoms.py:47,110-120; health_index.py:151-182)
     const double max_sev = jb_stream_next(rs);
     const int age = a.age[p] > 99 ? 99 : a.age[p];

@@ -1,0 +1,118 @@
+// World-create-time layout: internal person numbering and the 32-slot tile decomposition.
+//
+// The reference keeps people in Python lists per subgroup; the device wants the dominant access
+// (every resident's household, every step) to be a coalesced stream.  So residents are renumbered
+// by the padded slot order of the streamed residence supergroup: person index == slot index, no
+// member indirection for households.  Padding slots are permanently "dead" pseudo-persons.
+// Everything crossing the C ABI is translated back to the caller's numbering.
+#pragma once
+#include <algorithm>
+#include <vector>
+
+#include "jb_internal.cuh"
+
+#define JB_TI_VALID_H 0x0800u
+#define JB_TI_FIRST_H 0x1000u
+
+struct HostTiles {
+  int mode = 0;  // 0 warp only, 1 gather tiles, 2 stream tiles
+  std::vector<uint32_t> tile_group0, tp_member, big;
+  std::vector<uint16_t> tp_info;
+};
+
+struct HostLayout {
+  uint32_t N_int = 0;
+  std::vector<uint32_t> ext2int, int2ext;
+  std::vector<uint8_t> age, sex, ch, phas;
+  std::vector<uint32_t> psa, reg_member;
+  std::vector<HostTiles> tiles;
+};
+
+static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool stream, HostTiles& T) {
+  auto pad = [&]() {
+    while (T.tp_member.size() % 32) { T.tp_member.push_back(0xFFFFFFFFu); T.tp_info.push_back(0); }
+  };
+  uint32_t fill = 32;  // 32 = no open tile
+  for (uint32_t g = sg.first_group; g < sg.first_group + sg.n_groups; ++g) {
+    const uint32_t b = d->grp_offset[g], e = d->grp_offset[g + 1], sz = e - b;
+    if (sz == 0) { pad(); fill = 32; continue; }  // keeps group indices consecutive inside a tile
+    if (sz > 32) {
+      T.big.push_back(g);
+      pad();
+      fill = 32;
+      if (stream) {  // big groups still own a contiguous block of person indices (not tile-valid)
+        for (uint32_t m = b; m < e; ++m) {
+          if ((m - b) % 32 == 0) T.tile_group0.push_back(g);
+          T.tp_member.push_back(d->reg_member[m]);
+          T.tp_info.push_back((uint16_t)(d->reg_info[m] & 0x07FFu));
+        }
+        pad();
+      }
+      continue;
+    }
+    if (fill + sz > 32) { pad(); T.tile_group0.push_back(g); fill = 0; }
+    for (uint32_t m = b; m < e; ++m) {
+      T.tp_member.push_back(d->reg_member[m]);
+      T.tp_info.push_back((uint16_t)((d->reg_info[m] & 0x07FFu) | JB_TI_VALID_H | (m == b ? JB_TI_FIRST_H : 0u)));
+    }
+    fill += sz;
+  }
+  pad();
+}
+
+// Returns an error string or nullptr.
+static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSupergroup>& sgs, HostLayout& L) {
+  const uint32_t N = d->n_people;
+  L.tiles.assign(sgs.size(), HostTiles());
+  // the streamed supergroup: first tile-mode residence supergroup whose slots are distinct residents
+  int ks = -1;
+  for (size_t k = 0; k < sgs.size() && ks < 0; ++k) {
+    const JbSupergroup& sg = sgs[k];
+    if (sg.launch_mode != 0 || sg.activity != JB_ACT_RESIDENCE || sg.n_groups == 0) continue;
+    std::vector<uint8_t> seen(N, 0);
+    bool ok = true;
+    for (uint32_t m = d->grp_offset[sg.first_group]; ok && m < d->grp_offset[sg.first_group + sg.n_groups]; ++m) {
+      const uint32_t p = d->reg_member[m];
+      if (p >= N || seen[p] || JB_INFO_ACT(d->reg_info[m]) != JB_ACT_RESIDENCE) ok = false; else seen[p] = 1;
+    }
+    if (ok) ks = (int)k;
+  }
+  for (size_t k = 0; k < sgs.size(); ++k) {
+    const JbSupergroup& sg = sgs[k];
+    if (sg.launch_mode != 0) continue;
+    for (uint32_t m = d->grp_offset[sg.first_group]; m < d->grp_offset[sg.first_group + sg.n_groups]; ++m)
+      if ((int)JB_INFO_LSG(d->reg_info[m]) >= sg.dim) return "registered member has a subgroup index >= contact matrix dimension";
+    L.tiles[k].mode = ((int)k == ks) ? 2 : 1;
+    jb_pack_tiles(d, sg, (int)k == ks, L.tiles[k]);
+  }
+  // internal numbering
+  L.ext2int.assign(N, 0xFFFFFFFFu);
+  uint32_t next = 0;
+  if (ks >= 0) {
+    const HostTiles& T = L.tiles[ks];
+    for (uint32_t s = 0; s < T.tp_member.size(); ++s)
+      if (T.tp_member[s] != 0xFFFFFFFFu) L.ext2int[T.tp_member[s]] = s;
+    next = (uint32_t)T.tp_member.size();
+  }
+  for (uint32_t p = 0; p < N; ++p)
+    if (L.ext2int[p] == 0xFFFFFFFFu) L.ext2int[p] = next++;
+  L.N_int = next;
+  L.int2ext.assign(L.N_int, 0xFFFFFFFFu);
+  for (uint32_t p = 0; p < N; ++p) L.int2ext[L.ext2int[p]] = p;
+  // remapped person attributes (padding: dead pseudo-persons without activities)
+  L.age.assign(L.N_int, 0); L.sex.assign(L.N_int, 0); L.ch.assign(L.N_int, 0); L.phas.assign(L.N_int, 0);
+  L.psa.assign(L.N_int, 0);
+  for (uint32_t p = 0; p < N; ++p) {
+    const uint32_t i = L.ext2int[p];
+    L.age[i] = d->age[p]; L.sex[i] = d->sex[p]; L.ch[i] = d->care_home_resident[p];
+    L.phas[i] = d->has_activity[p]; L.psa[i] = d->super_area[p];
+  }
+  auto remap = [&](uint32_t p) { return p < N ? L.ext2int[p] : L.N_int + (p - N); };
+  L.reg_member.resize(d->n_members);
+  for (uint32_t m = 0; m < d->n_members; ++m) L.reg_member[m] = remap(d->reg_member[m]);
+  for (size_t k = 0; k < sgs.size(); ++k)
+    if (L.tiles[k].mode == 1)
+      for (uint32_t& x : L.tiles[k].tp_member)
+        if (x != 0xFFFFFFFFu) x = remap(x);
+  return nullptr;
+}

@@ -9,6 +9,7 @@
 #include <limits>
 
 #include "jb_kernels.cuh"
+#include "jb_layout.cuh"
 
 static thread_local std::string g_err;
 void jb_set_error(const std::string& msg) { g_err = msg; }
@@ -27,6 +28,24 @@ void jb_set_error(const std::string& msg) { g_err = msg; }
     if (!(cond)) {                                                                            \
       jb_set_error(msg);                                                                      \
       return JB_EINVAL;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+// JB_DEBUG_SYNC=1: synchronise after every kernel launch and name the kernel that faulted.
+static bool jb_debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JB_DEBUG_SYNC"); v = (e && *e && *e != '0') ? 1 : 0; }
+  return v == 1;
+}
+#define KCHECK(name, st)                                                                      \
+  do {                                                                                        \
+    CK(cudaGetLastError());                                                                   \
+    if (jb_debug_sync()) {                                                                    \
+      cudaError_t e_ = cudaStreamSynchronize(st);                                             \
+      if (e_ != cudaSuccess) {                                                                \
+        jb_set_error(std::string("kernel ") + (name) + ": " + cudaGetErrorString(e_));          \
+        return JB_ECUDA;                                                                      \
+      }                                                                                       \
     }                                                                                         \
   } while (0)
 
@@ -104,11 +123,9 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   w->device = device;
   CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
   cudaStream_t s = w->stream;
-  w->N = d->n_people; w->H = d->n_halo; w->NP = w->N + w->H; w->G = d->n_groups; w->M = d->n_members;
+  w->N_ext = d->n_people; w->H = d->n_halo; w->G = d->n_groups; w->M = d->n_members;
   w->V = d->n_variants; w->R = std::max(1u, d->n_regions); w->SA = d->n_super_areas;
   w->n_beta = d->n_beta; w->n_scale = d->n_scale; w->id_base = d->person_id_base;
-  w->C = d->slot_capacity ? d->slot_capacity : std::max(1u, w->N);
-  w->newinf_cap = d->newinf_capacity ? d->newinf_capacity : std::max(1u, w->NP);
   w->sgs.assign(d->supergroups, d->supergroups + d->n_supergroups);
   copy_disease(d->disease, w->dis_host);
 
@@ -130,7 +147,7 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
       }
     } else {
       REQUIRE(sg.dim >= 1 && sg.dim <= JB_MAX_DIM, "contact matrix dimension out of range");
-      if (sg.launch_mode == 0) REQUIRE(sg.dim <= 4 && !sg.has_dynamic, "thread-per-group mode needs dim<=4, static members");
+      if (sg.launch_mode == 0) REQUIRE(sg.dim <= 4 && !sg.has_dynamic, "tile mode needs dim<=4 and static members");
     }
     REQUIRE(sg.cm_offset >= 0 && (uint32_t)(sg.cm_offset + sg.dim * sg.dim) <= d->n_cm_doubles, "cm offset out of range");
     REQUIRE(sg.activity >= 0 && sg.activity < JB_N_ACT, "bad supergroup activity");
@@ -139,17 +156,44 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   }
   REQUIRE(expect == w->G, "supergroups do not cover all groups");
 
-  TRY(dev_upload(&w->age, d->age, w->N, s));
-  TRY(dev_upload(&w->sex, d->sex, w->N, s));
-  TRY(dev_upload(&w->ch, d->care_home_resident, w->N, s));
-  TRY(dev_upload(&w->phas, d->has_activity, w->N, s));
-  TRY(dev_upload(&w->psa, d->super_area, w->N, s));
+  // internal numbering + tiles (jb_layout.cuh)
+  HostLayout lay;
+  {
+    const char* err = jb_build_layout(d, w->sgs, lay);
+    REQUIRE(err == nullptr, err ? err : "");
+  }
+  w->N = lay.N_int; w->NP = w->N + w->H;
+  REQUIRE((uint64_t)w->NP < (1ull << 28), "internal person count must be < 2^28");
+  w->C = d->slot_capacity ? d->slot_capacity : std::max(1u, w->N_ext);
+  w->newinf_cap = d->newinf_capacity ? d->newinf_capacity : std::max(1u, w->N_ext + w->H);
+  w->h_ext2int = lay.ext2int; w->h_int2ext = lay.int2ext;
+  TRY(dev_upload(&w->int2ext, lay.int2ext.data(), w->N, s));
+  w->tiles.resize(w->sgs.size());
+  for (size_t k = 0; k < w->sgs.size(); ++k) {
+    const HostTiles& T = lay.tiles[k];
+    SgTiles& D = w->tiles[k];
+    D.mode = T.mode;
+    if (T.mode == 0) continue;
+    D.n_tiles = (uint32_t)(T.tp_info.size() / 32);
+    D.n_big = (uint32_t)T.big.size();
+    REQUIRE(T.tile_group0.size() == D.n_tiles, "internal: tile table size mismatch");
+    TRY(dev_upload(&D.tile_group0, T.tile_group0.data(), T.tile_group0.size(), s));
+    TRY(dev_upload(&D.tp_info, T.tp_info.data(), T.tp_info.size(), s));
+    if (T.mode == 1) TRY(dev_upload(&D.tp_member, T.tp_member.data(), T.tp_member.size(), s));
+    if (D.n_big) TRY(dev_upload(&D.big_list, T.big.data(), T.big.size(), s));
+    TRY(dev_alloc(&D.work_items, (size_t)w->sgs[k].n_groups + 1));
+  }
+  TRY(dev_upload(&w->age, lay.age.data(), w->N, s));
+  TRY(dev_upload(&w->sex, lay.sex.data(), w->N, s));
+  TRY(dev_upload(&w->ch, lay.ch.data(), w->N, s));
+  TRY(dev_upload(&w->phas, lay.phas.data(), w->N, s));
+  TRY(dev_upload(&w->psa, lay.psa.data(), w->N, s));
   TRY(dev_upload(&w->sa_hospital, d->sa_hospital, w->SA, s));
   TRY(dev_upload(&w->sa_region, d->sa_region, w->SA, s));
   TRY(dev_upload(&w->grp_off, d->grp_offset, (size_t)w->G + 1, s));
   TRY(dev_upload(&w->grp_info, d->grp_info, w->G, s));
   TRY(dev_upload(&w->grp_aux, d->grp_aux, w->G, s));
-  TRY(dev_upload(&w->reg_member, d->reg_member, w->M, s));
+  TRY(dev_upload(&w->reg_member, lay.reg_member.data(), w->M, s));
   TRY(dev_upload(&w->reg_info, d->reg_info, w->M, s));
   TRY(dev_upload(&w->school_years, d->school_years, d->n_school_years, s));
   TRY(dev_upload(&w->cm, d->cm, d->n_cm_doubles, s));
@@ -165,7 +209,14 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_alloc(&w->pmed, w->N));
   TRY(dev_alloc(&w->pslot, w->N));
   TRY(dev_alloc(&w->halo_gid, w->H));
-  CK(cudaMemsetAsync(w->pstate, JB_ACT_NONE, w->NP, s));
+  {
+    // residents start alive and nowhere; padding slots are permanently dead
+    std::vector<uint8_t> st(w->NP, JB_ACT_NONE);
+    for (uint32_t i = 0; i < w->N; ++i)
+      if (lay.int2ext[i] == 0xFFFFFFFFu) st[i] = JB_ACT_NONE | JB_PS_DEAD;
+    CK(cudaMemcpyAsync(w->pstate, st.data(), w->NP, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
   CK(cudaMemsetAsync(w->pvar, 0, w->NP, s));
   CK(cudaMemsetAsync(w->ptag, 0xFF, w->N, s));  // -1 = healthy
   CK(cudaMemsetAsync(w->trans, 0, (size_t)w->NP * 8, s));
@@ -220,10 +271,17 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   CK(cudaEventCreate(&w->ev_step1));
   CK(cudaEventCreate(&w->ev_int0));
   CK(cudaEventCreate(&w->ev_int1));
-  for (size_t k = 0; k < w->sgs.size(); ++k) { CK(cudaEventCreate(&w->ev_sg0[k])); CK(cudaEventCreate(&w->ev_sg1[k])); }
+  for (size_t k = 0; k < w->sgs.size(); ++k) {
+    CK(cudaEventCreate(&w->ev_sg0[k]));
+    CK(cudaEventCreate(&w->ev_sg1[k]));
+    CK(cudaStreamCreateWithFlags(&w->side[k], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&w->ev_join[k], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
   // the warp kernel may need > 48 KB of dynamic shared memory for very large schools
   CK(cudaFuncSetAttribute(k_groups_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_groups_warp<JB_MAX_VARIANTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   *out = w;
   return JB_OK;
@@ -239,9 +297,16 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->counters, w->newinf_member, w->newinf_var,
                   w->beta, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_cnt, w->dyn_bin,
-                  w->cub_tmp};
+                  w->cub_tmp, w->int2ext};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (SgTiles& t : w->tiles) {
+    if (t.tile_group0) cudaFree(t.tile_group0);
+    if (t.tp_member) cudaFree(t.tp_member);
+    if (t.tp_info) cudaFree(t.tp_info);
+    if (t.big_list) cudaFree(t.big_list);
+    if (t.work_items) cudaFree(t.work_items);
+  }
   if (w->h_beta) cudaFreeHost(w->h_beta);
   if (w->h_counters) cudaFreeHost(w->h_counters);
   if (w->ev_step0) cudaEventDestroy(w->ev_step0);
@@ -249,6 +314,11 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   if (w->ev_int0) cudaEventDestroy(w->ev_int0);
   if (w->ev_int1) cudaEventDestroy(w->ev_int1);
   for (int k = 0; k < JB_MAX_SUPERGROUPS; ++k) { if (w->ev_sg0[k]) cudaEventDestroy(w->ev_sg0[k]); if (w->ev_sg1[k]) cudaEventDestroy(w->ev_sg1[k]); }
+  for (int k = 0; k < JB_MAX_SUPERGROUPS; ++k) {
+    if (w->side[k]) cudaStreamDestroy(w->side[k]);
+    if (w->ev_join[k]) cudaEventDestroy(w->ev_join[k]);
+  }
+  if (w->ev_fork) cudaEventDestroy(w->ev_fork);
   cudaStreamDestroy(w->stream);
   delete w;
 }
@@ -256,12 +326,19 @@ extern "C" void jb_world_destroy(JbWorld* w) {
 extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const double* susceptibility) {
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
-  if (pstate) CK(cudaMemcpyAsync(w->pstate, pstate, w->N, cudaMemcpyHostToDevice, w->stream));
-  if (susceptibility)
-    for (uint32_t v = 0; v < w->V; ++v)
-      CK(cudaMemcpyAsync(w->susc + (size_t)v * w->NP, susceptibility + (size_t)v * w->N, (size_t)w->N * 8,
-                         cudaMemcpyHostToDevice, w->stream));
   CK(cudaStreamSynchronize(w->stream));
+  if (pstate) {
+    std::vector<uint8_t> st(w->N, JB_ACT_NONE | JB_PS_DEAD);
+    for (uint32_t p = 0; p < w->N_ext; ++p) st[w->h_ext2int[p]] = pstate[p];
+    CK(cudaMemcpy(w->pstate, st.data(), w->N, cudaMemcpyHostToDevice));
+  }
+  if (susceptibility) {
+    std::vector<double> su(w->N, 1.0);
+    for (uint32_t v = 0; v < w->V; ++v) {
+      for (uint32_t p = 0; p < w->N_ext; ++p) su[w->h_ext2int[p]] = susceptibility[(size_t)v * w->N_ext + p];
+      CK(cudaMemcpy(w->susc + (size_t)v * w->NP, su.data(), (size_t)w->N * 8, cudaMemcpyHostToDevice));
+    }
+  }
   return JB_OK;
 }
 
@@ -283,7 +360,7 @@ extern "C" int jb_inject_uniforms(JbWorld* w, const double* u, size_t n) {
 static NewInfArgs make_newinf_args(JbWorld* w) {
   NewInfArgs a;
   memset(&a, 0, sizeof(a));
-  a.N = w->N; a.NP = w->NP; a.C = w->C; a.V = (int)w->V; a.gid_base = (uint32_t)w->id_base;
+  a.N = w->N; a.NP = w->NP; a.C = w->C; a.V = (int)w->V; a.gid_base = (uint32_t)w->id_base; a.int2ext = w->int2ext;
   a.age = w->age; a.sex = w->sex; a.ch = w->ch; a.hi_cum = w->hi_cum; a.dis = w->dis;
   a.pstate = w->pstate; a.pvar = w->pvar; a.ptag = w->ptag; a.susc = w->susc; a.trans = w->trans; a.pslot = w->pslot;
   a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
@@ -300,11 +377,13 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   uint32_t* d_p = nullptr;
   uint8_t* d_v = nullptr;
   std::vector<uint8_t> v8(n, 0);
+  std::vector<uint32_t> pint(n);
   for (size_t i = 0; i < n; ++i) {
-    REQUIRE(persons[i] < w->N, "jb_infect: person index out of range");
+    REQUIRE(persons[i] < w->N_ext, "jb_infect: person index out of range");
+    pint[i] = w->h_ext2int[persons[i]];
     if (variants) { REQUIRE(variants[i] < w->V, "jb_infect: variant out of range"); v8[i] = (uint8_t)variants[i]; }
   }
-  TRY(dev_upload(&d_p, persons, n, w->stream));
+  TRY(dev_upload(&d_p, pint.data(), n, w->stream));
   TRY(dev_upload(&d_v, v8.data(), n, w->stream));
   NewInfArgs a = make_newinf_args(w);
   a.member = d_p; a.variant = d_v; a.count_dev = nullptr; a.count_host = (uint32_t)n; a.cap = (uint32_t)n;
@@ -334,10 +413,10 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
   std::vector<int8_t> tag(n), maxtag(n), ttag(n * JB_MAX_STAGES);
   for (size_t i = 0; i < n; ++i) {
     const JbInfectionRow& r = rows[i];
-    REQUIRE(r.person < w->N, "jb_upload_infections: person out of range");
+    REQUIRE(r.person < w->N_ext, "jb_upload_infections: person out of range");
     REQUIRE(r.n_stages >= 1 && r.n_stages <= JB_MAX_STAGES && r.stage >= 0 && r.stage < r.n_stages, "bad stages");
     REQUIRE(r.variant < w->V, "bad variant");
-    person[i] = (int32_t)r.person; start[i] = r.start_time;
+    person[i] = (int32_t)w->h_ext2int[r.person]; start[i] = r.start_time;
     stage[i] = (uint8_t)r.stage; nst[i] = (uint8_t)r.n_stages; var[i] = (uint8_t)r.variant;
     tag[i] = (int8_t)r.tag; maxtag[i] = (int8_t)r.max_tag;
     next[i] = (r.stage + 1 < r.n_stages) ? r.traj_time[r.stage + 1] : 1e300;
@@ -363,7 +442,8 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
   }
   // per-person side: element-wise copies (cold path)
   for (size_t i = 0; i < n; ++i) {
-    const JbInfectionRow& r = rows[i];
+    JbInfectionRow r = rows[i];
+    r.person = w->h_ext2int[r.person];
     uint8_t st = 0;
     CK(cudaMemcpy(&st, w->pstate + r.person, 1, cudaMemcpyDeviceToHost));
     st |= JB_PS_INFECTED;
@@ -388,9 +468,13 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
 extern "C" int jb_set_halo(JbWorld* w, const uint32_t* out_person, size_t n_out) {
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
-  for (size_t i = 0; i < n_out; ++i) REQUIRE(out_person[i] < w->N, "jb_set_halo: person out of range");
+  std::vector<uint32_t> op(n_out);
+  for (size_t i = 0; i < n_out; ++i) {
+    REQUIRE(out_person[i] < w->N_ext, "jb_set_halo: person out of range");
+    op[i] = w->h_ext2int[out_person[i]];
+  }
   if (w->out_person) cudaFree(w->out_person);
-  TRY(dev_upload(&w->out_person, out_person, n_out, w->stream));
+  TRY(dev_upload(&w->out_person, op.data(), n_out, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   w->n_out = (uint32_t)n_out;
   return JB_OK;
@@ -418,6 +502,7 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   a.bin_cap = w->bin_cap;
   a.dyn_bin_base = w->sg_bin_base[&sg - w->sgs.data()];
   a.g0 = sg.first_group; a.g1 = sg.first_group + sg.n_groups;
+  a.group_list = nullptr; a.n_list = sg.n_groups; a.int2ext = w->int2ext;
   a.dim = sg.dim; a.kind = sg.kind; a.L = L;
   a.N = w->N; a.NP = w->NP; a.V = (int)w->V; a.R = (int)w->R;
   a.dt = p.delta_time; a.seed = p.seed; a.step = p.step; a.gid_base = (uint32_t)w->id_base;
@@ -432,29 +517,68 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   return a;
 }
 
+template <int VM>
+static int launch_warp(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_t st) {
+  const int wpb = 4;
+  size_t smem = jb_warp_smem_bytes(a.L, (int)w->V, dynamic ? w->bin_cap : 0u) * wpb;
+  unsigned blocks = (a.n_list + wpb - 1) / wpb;
+  k_groups_warp<VM><<<blocks, wpb * 32, smem, st>>>(a);
+  KCHECK("k_groups_warp", st);
+  return JB_OK;
+}
+
+template <bool STREAM, int VM>
+static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
+  const unsigned chunks = a.n_tiles * 2;
+  unsigned blocks = std::min<unsigned>((chunks + 255) / 256, 148 * 8);
+  k_detect<STREAM><<<blocks, 256, 0, st>>>(a);
+  KCHECK(STREAM ? "k_detect<stream>" : "k_detect<gather>", st);
+  if (a.mode == 0) {
+    k_process<STREAM, VM><<<148 * 8, 128, 0, st>>>(a);
+    KCHECK(STREAM ? "k_process<stream>" : "k_process<gather>", st);
+  }
+  return JB_OK;
+}
+
 static int launch_groups(JbWorld* w, int mode) {
+  // fork: every active supergroup gets its own stream (its groups are disjoint from all others,
+  // person state is read-only here, outputs are appended with atomics)
+  CK(cudaEventRecord(w->ev_fork, w->stream));
   for (size_t k = 0; k < w->sgs.size(); ++k) {
     const JbSupergroup& sg = w->sgs[k];
     if (sg.n_groups == 0) continue;
     if (!(w->cur.activity_mask & (1u << sg.activity))) continue;
+    cudaStream_t st = w->serial ? w->stream : w->side[k];
+    if (!w->serial) CK(cudaStreamWaitEvent(st, w->ev_fork, 0));
     GroupArgs a = make_group_args(w, sg, w->sg_L[k]);
     a.mode = mode;
     const bool tme = w->timing && mode == 0;
-    if (tme) CK(cudaEventRecord(w->ev_sg0[k], w->stream));
-    if (sg.launch_mode == 0) {
-      unsigned blocks = (sg.n_groups + 255) / 256;
-      if (w->V == 1) k_groups_thread<1><<<blocks, 256, 0, w->stream>>>(a);
-      else k_groups_thread<JB_MAX_VARIANTS><<<blocks, 256, 0, w->stream>>>(a);
+    if (tme) CK(cudaEventRecord(w->ev_sg0[k], st));
+    const SgTiles& T = w->tiles[k];
+    if (T.mode == 0) {
+      if (w->V == 1) TRY(launch_warp<1>(w, a, sg.has_dynamic != 0, st)); else TRY(launch_warp<JB_MAX_VARIANTS>(w, a, sg.has_dynamic != 0, st));
+      w->launches++;
     } else {
-      const int wpb = 4;
-      size_t smem = jb_warp_smem_bytes(a.L, (int)w->V, sg.has_dynamic ? w->bin_cap : 0u) * wpb;
-      unsigned blocks = (sg.n_groups + wpb - 1) / wpb;
-      if (w->V == 1) k_groups_warp<1><<<blocks, wpb * 32, smem, w->stream>>>(a);
-      else k_groups_warp<JB_MAX_VARIANTS><<<blocks, wpb * 32, smem, w->stream>>>(a);
+      a.tile_group0 = T.tile_group0; a.tp_member = T.tp_member; a.tp_info = T.tp_info;
+      a.n_tiles = T.n_tiles; a.stream_base = T.stream_base;
+      a.work_items = T.work_items; a.work_cnt = w->counters + CNT_WORK0 + k;
+      if (T.n_tiles) {
+        if (T.mode == 2) { if (w->V == 1) TRY((launch_tiles<true, 1>(w, a, st))); else TRY((launch_tiles<true, JB_MAX_VARIANTS>(w, a, st))); }
+        else { if (w->V == 1) TRY((launch_tiles<false, 1>(w, a, st))); else TRY((launch_tiles<false, JB_MAX_VARIANTS>(w, a, st))); }
+        w->launches += (mode == 0) ? 2 : 1;
+      }
+      if (T.n_big) {  // groups with more than 32 registered slots
+        a.group_list = T.big_list; a.n_list = T.n_big;
+        if (w->V == 1) TRY(launch_warp<1>(w, a, false, st)); else TRY(launch_warp<JB_MAX_VARIANTS>(w, a, false, st));
+        w->launches++;
+      }
     }
     CK(cudaGetLastError());
-    w->launches++;
-    if (tme) { CK(cudaEventRecord(w->ev_sg1[k], w->stream)); w->sg_pending[k] = true; }
+    if (tme) { CK(cudaEventRecord(w->ev_sg1[k], st)); w->sg_pending[k] = true; }
+    if (!w->serial) {
+      CK(cudaEventRecord(w->ev_join[k], st));
+      CK(cudaStreamWaitEvent(w->stream, w->ev_join[k], 0));
+    }
   }
   return JB_OK;
 }
@@ -511,7 +635,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
       }
     const uint32_t chunks = (w->N + 15) / 16;
     k_place<<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
-    CK(cudaGetLastError());
+    KCHECK("k_place", s);
     w->launches++;
   }
   if (w->n_out && d_send) {
@@ -552,9 +676,9 @@ extern "C" int jb_step_interact(JbWorld* w, const void* d_recv, void* d_ret_send
     a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_NEWINF;
     a.cap = w->newinf_cap; a.now = p.now; a.seed = p.seed; a.step = p.step;
     a.halo_ret = (uint8_t*)d_ret_send;
-    if (p.flags & JB_STEP_NO_NEW_INFECTIONS) a.N = 0;  // only route halo infections
+    a.skip_local = (p.flags & JB_STEP_NO_NEW_INFECTIONS) ? 1 : 0;
     k_newinf<<<148 * 2, 128, 0, s>>>(a);
-    CK(cudaGetLastError());
+    KCHECK("k_newinf", s);
     w->launches++;
   }
   return JB_OK;
@@ -594,7 +718,7 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
     a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
     a.pslot = w->pslot; a.phas = w->phas; a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.counters = w->counters;
     k_health<<<148 * 4, 256, 0, s>>>(a);
-    CK(cudaGetLastError());
+    KCHECK("k_health", s);
     w->launches++;
   }
   CK(cudaMemcpyAsync(w->h_counters, w->counters, CNT_N * 4, cudaMemcpyDeviceToHost, s));
@@ -658,6 +782,8 @@ extern "C" int jb_fetch_new_infections(JbWorld* w, uint32_t* member, uint32_t* v
   std::vector<uint8_t> v(cnt);
   CK(cudaMemcpy(m.data(), w->newinf_member, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(v.data(), w->newinf_var, cnt, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < cnt; ++i)  // back to the caller's numbering (halo persons follow the residents)
+    m[i] = m[i] < w->N ? w->h_int2ext[m[i]] : w->N_ext + (m[i] - w->N);
   // the device appends in arbitrary order: return sorted by member index
   std::vector<uint32_t> order(cnt);
   for (uint32_t i = 0; i < cnt; ++i) order[i] = i;
@@ -669,19 +795,25 @@ extern "C" int jb_fetch_new_infections(JbWorld* w, uint32_t* member, uint32_t* v
   return JB_OK;
 }
 
+template <typename T>
+static int fetch_permuted(JbWorld* w, const T* dev, T* out) {
+  std::vector<T> tmp(w->N);
+  CK(cudaMemcpy(tmp.data(), dev, (size_t)w->N * sizeof(T), cudaMemcpyDeviceToHost));
+  for (uint32_t p = 0; p < w->N_ext; ++p) out[p] = tmp[w->h_ext2int[p]];
+  return JB_OK;
+}
+
 extern "C" int jb_fetch_person_state(JbWorld* w, uint8_t* pstate, int8_t* tag, double* trans_prob,
                                      double* susceptibility, int32_t* medical) {
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
   CK(cudaStreamSynchronize(w->stream));
-  if (pstate) CK(cudaMemcpy(pstate, w->pstate, w->N, cudaMemcpyDeviceToHost));
-  if (tag) CK(cudaMemcpy(tag, w->ptag, w->N, cudaMemcpyDeviceToHost));
-  if (trans_prob) CK(cudaMemcpy(trans_prob, w->trans, (size_t)w->N * 8, cudaMemcpyDeviceToHost));
+  if (pstate) TRY(fetch_permuted(w, w->pstate, pstate));
+  if (tag) TRY(fetch_permuted(w, w->ptag, tag));
+  if (trans_prob) TRY(fetch_permuted(w, w->trans, trans_prob));
   if (susceptibility)
-    for (uint32_t v = 0; v < w->V; ++v)
-      CK(cudaMemcpy(susceptibility + (size_t)v * w->N, w->susc + (size_t)v * w->NP, (size_t)w->N * 8,
-                    cudaMemcpyDeviceToHost));
-  if (medical) CK(cudaMemcpy(medical, w->pmed, (size_t)w->N * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t v = 0; v < w->V; ++v) TRY(fetch_permuted(w, w->susc + (size_t)v * w->NP, susceptibility + (size_t)v * w->N_ext));
+  if (medical) TRY(fetch_permuted(w, w->pmed, medical));
   return JB_OK;
 }
 
@@ -690,7 +822,10 @@ extern "C" int jb_fetch_lambda(JbWorld* w, double* out) {
   REQUIRE(w->lambda != nullptr, "no step ran with JB_STEP_RECORD_LAMBDA");
   CK(cudaSetDevice(w->device));
   CK(cudaStreamSynchronize(w->stream));
-  CK(cudaMemcpy(out, w->lambda, (size_t)w->NP * 8, cudaMemcpyDeviceToHost));
+  std::vector<double> tmp(w->NP);
+  CK(cudaMemcpy(tmp.data(), w->lambda, (size_t)w->NP * 8, cudaMemcpyDeviceToHost));
+  for (uint32_t p = 0; p < w->N_ext; ++p) out[p] = tmp[w->h_ext2int[p]];
+  for (uint32_t j = 0; j < w->H; ++j) out[w->N_ext + j] = tmp[w->N + j];
   return JB_OK;
 }
 
@@ -728,7 +863,7 @@ extern "C" int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap,
     if (k < cap && rows) {
       JbInfectionRow& r = rows[k];
       memset(&r, 0, sizeof(r));
-      r.person = (uint32_t)person[s]; r.variant = var[s]; r.start_time = start[s];
+      r.person = w->h_int2ext[person[s]]; r.variant = var[s]; r.start_time = start[s];
       for (int q = 0; q < JB_N_TPAR; ++q) r.tpar[q] = par[(size_t)q * hw + s];
       r.probability = trans[person[s]];
       r.n_stages = nst[s]; r.stage = stage[s]; r.max_tag = maxtag[s]; r.tag = tag[s];
@@ -746,6 +881,16 @@ extern "C" int jb_fetch_summary(JbWorld* w, uint32_t* counts) {
   if (!w || !counts) { jb_set_error("null argument"); return JB_EINVAL; }
   jb_set_error("jb_fetch_summary: not implemented in this round");
   return JB_EINVAL;
+}
+
+// on = 0: run the supergroup kernels one after the other on the main stream (isolated per-kernel
+// timings for the roofline); on = 1 (default): concurrently on side streams.
+extern "C" int jb_set_concurrency(JbWorld* w, int on) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  w->serial = on == 0;
+  return JB_OK;
 }
 
 extern "C" int jb_timing_enable(JbWorld* w, int on) {

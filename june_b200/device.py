@@ -241,6 +241,9 @@ class Engine:
                             traj_time=list(a.traj_time)[:ns], traj_tag=list(a.traj_tag)[:ns]))
         return out
 
+    def set_concurrency(self, on: bool = True):
+        self._check(self._f("set_concurrency")(self._h, 1 if on else 0))
+
     def timing_enable(self, on: bool = True):
         self._check(self._f("timing_enable")(self._h, 1 if on else 0))
 

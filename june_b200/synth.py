@@ -293,9 +293,9 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     supergroups = [
         Supergroup("hospitals", "hospital", ACT_MEDICAL, g_hosp0, n_hosp, KIND_MATRIX, 1, 1),
         Supergroup("schools", "school", ACT_PRIMARY, g_school0, n_schools, KIND_SCHOOL, 1, 0),
-        Supergroup("companies", "company", ACT_PRIMARY, g_comp0, n_comp, KIND_MATRIX, 1, 0),
+        Supergroup("companies", "company", ACT_PRIMARY, g_comp0, n_comp, KIND_MATRIX, 0, 0),
         Supergroup("households", "household", ACT_RESIDENCE, g_hh0, n_hh, KIND_MATRIX, 0, 0),
-        Supergroup("care_homes", "care_home", ACT_RESIDENCE, g_ch0, n_ch, KIND_MATRIX, 1, 0),
+        Supergroup("care_homes", "care_home", ACT_RESIDENCE, g_ch0, n_ch, KIND_MATRIX, 0, 0),
     ]
     w = WorldSoA(
         age=age, sex=sex, care_home_resident=ch_res, has_activity=has_activity, super_area=psa,

@@ -24,8 +24,12 @@ FLAGS = (_lib.STEP_SEVERE_STAY_HOME | _lib.STEP_HOSPITALISATION | _lib.STEP_INJE
          | _lib.STEP_NO_NEW_INFECTIONS | _lib.STEP_RECORD_LAMBDA)
 
 
-def run_trace(kind: str, name: str, max_steps=None):
+def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     g = Golden(name)
+    if launch_modes is not None:  # exercise the other kernel flavour on the same trace
+        for sg in g.world.supergroups:
+            if sg.spec in launch_modes:
+                sg.launch_mode = launch_modes[sg.spec]
     inter = Interaction.from_file()
     eng = make_engine(kind, g.world, g.outcome_prob, interaction=inter)
     beta = default_beta_table(g.world, inter)
@@ -104,10 +108,20 @@ def test_oracle_matches_reference_trace(name):
     assert worst <= REL
 
 
+# kernel flavours per spec: 0 = 32-slot tiles (stream for the residence supergroup, gather
+# otherwise), 1 = one warp per group
+LAUNCH_MODES = {
+    "tiles": {"household": 0, "company": 0, "care_home": 0},
+    "warps": {"household": 1, "company": 1, "care_home": 1},
+    "mixed": {"household": 1, "company": 0, "care_home": 0},
+}
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("modes", ["tiles", "warps", "mixed"])
 @pytest.mark.parametrize("name", ["w3k", "w1k_long"])
-def test_cuda_matches_reference_trace(name):
+def test_cuda_matches_reference_trace(name, modes):
     assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
-    draws, infections, worst = run_trace("cuda", name)
+    draws, infections, worst = run_trace("cuda", name, launch_modes=LAUNCH_MODES[modes])
     assert draws > 10000 and infections > 100
     assert worst <= REL
