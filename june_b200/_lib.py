@@ -2,8 +2,8 @@
 
 The product path has NO CPU fallback: if the shared library is missing, or no CUDA device is
 usable, creating a device world raises.  The same structures are reused by the tests to drive
-the CPU oracle (``oracle/libjune_oracle.so``, prefix ``jo_``) -- the oracle is never loaded from
-inside this package.
+the CPU checker library under ``oracle/`` (same ABI, prefix ``jo_``) -- that library is never
+loaded from inside this package.
 """
 from __future__ import annotations
 

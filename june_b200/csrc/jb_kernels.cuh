@@ -435,6 +435,109 @@ __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ Gro
   if (lane == 0) atomicAdd(&a.counters[CNT_DRAWS], nsus);
 }
 
+// ---- warp-per-group kernel, 1x1 contact matrix, static members (big companies, venues) ------
+// One subgroup: the group needs only its size and the summed transmission probability, so the
+// segmented scans / shared memory of the general kernel are replaced by ballots and one
+// butterfly reduction.
+template <int VM>
+__global__ void __launch_bounds__(128) k_groups_warp_d1(const __grid_constant__ GroupArgs a) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t gi_ = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (gi_ >= a.n_list) return;
+  const uint32_t g = a.group_list ? a.group_list[gi_] : a.g0 + gi_;
+  const int V = (VM > 1) ? a.V : 1;
+  const uint32_t b = a.grp_off[g], ns = a.grp_off[g + 1] - b;
+  constexpr int UB = 4;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint32_t n = 0, nsus = 0, ninf = 0;
+  double T[VM];
+#pragma unroll
+  for (int v = 0; v < VM; ++v) T[v] = 0.0;
+  for (uint32_t it0 = 0; it0 < ns; it0 += 32 * UB) {
+    uint32_t p[UB], st[UB];
+    bool pres[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const uint32_t idx = it0 + 32 * u + lane;
+      p[u] = idx < ns ? a.reg_member[b + idx] : 0xFFFFFFFFu;
+      st[u] = idx < ns ? a.reg_info[b + idx] : 0u;  // info for now
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const uint32_t info = st[u];
+      st[u] = p[u] != 0xFFFFFFFFu ? a.pstate[p[u]] : 0u;
+      pres[u] = p[u] != 0xFFFFFFFFu && (st[u] & JB_PS_ACT_MASK) == JB_INFO_ACT(info);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const bool inf = pres[u] && (st[u] & JB_PS_INFECTED);
+      n += __popc(__ballot_sync(JB_FULL, pres[u]));
+      nsus += __popc(__ballot_sync(JB_FULL, pres[u] && !inf));
+      ninf += __popc(__ballot_sync(JB_FULL, inf));
+      if (inf) {
+        const double t = a.trans[p[u]];
+        const int pv = (VM > 1) ? a.pvar[p[u]] : 0;
+#pragma unroll
+        for (int v = 0; v < VM; ++v)
+          if (v == pv) T[v] += t;
+      }
+    }
+  }
+  const bool must = nsus > 0 && ninf > 0;  // interactive.py:136
+  if (a.mode == 1) {
+    if (lane == 0) a.draw_cnt[g] = must ? nsus : 0;
+    return;
+  }
+  if (!must) return;
+#pragma unroll
+  for (int v = 0; v < VM; ++v)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) T[v] += __shfl_xor_sync(JB_FULL, T[v], off);
+  const uint32_t gi = a.grp_info[g];
+  const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+  double row[VM];
+#pragma unroll
+  for (int v = 0; v < VM; ++v)
+    row[v] = (v < V && T[v] != 0.0) ? a.cm[0] * T[v] / (double)max(1, (int)n - 1) * beta * a.dt : 0.0;  // interaction.py:469-471
+  uint32_t ord = a.inject ? a.draw_base[g] : 0u;
+  for (uint32_t it0 = 0; it0 < ns; it0 += 32 * UB) {
+    uint32_t p[UB], st[UB];
+    bool sus[UB];
+    double s0[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const uint32_t idx = it0 + 32 * u + lane;
+      p[u] = idx < ns ? a.reg_member[b + idx] : 0xFFFFFFFFu;
+      st[u] = idx < ns ? a.reg_info[b + idx] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const uint32_t info = st[u];
+      st[u] = p[u] != 0xFFFFFFFFu ? a.pstate[p[u]] : 0u;
+      sus[u] = p[u] != 0xFFFFFFFFu && (st[u] & JB_PS_ACT_MASK) == JB_INFO_ACT(info) && !(st[u] & JB_PS_INFECTED);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) s0[u] = sus[u] ? a.susc[p[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const uint32_t sm = __ballot_sync(JB_FULL, sus[u]);
+      if (sus[u]) {
+        double lam_v[VM];
+        double lam = 0.0;
+#pragma unroll
+        for (int v = 0; v < VM; ++v) {
+          lam_v[v] = (v < V) ? row[v] * ((v == 0) ? s0[u] : a.susc[(size_t)v * a.NP + p[u]]) : 0.0;
+          lam += lam_v[v];
+        }
+        if (a.lambda) a.lambda[p[u]] = lam;
+        if (lam != 0.0) jb_draw_core<VM>(a, p[u], lam_v, lam, ord + __popc(sm & lane_lt));  // lambda == 0 never infects
+      }
+      ord += __popc(sm);
+    }
+  }
+  if (lane == 0) atomicAdd(&a.counters[CNT_DRAWS], nsus);
+}
+
 // ---- tile kernel ----------------------------------------------------------------------------
 // Small groups (<= 32 registered slots, contact matrix dim <= 4, static members) are packed at
 // world-create time into 32-slot tiles that never split a group; one warp processes one tile
@@ -562,14 +665,13 @@ __global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArg
 // every lane accumulates the subgroup sizes and transmission sums from shuffle broadcasts in slot
 // order -- the reference's own left-to-right order (Python `sum`, interaction.py:463-467) -- and
 // finally each lane draws for its own member.
-#define JB_LG 8
-template <bool STREAM, int VM>
+template <bool STREAM, int VM, int JB_LG>
 __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupArgs a) {
   const uint32_t n_work = *a.work_cnt;
   const int V = (VM > 1) ? a.V : 1;
   const int lane = threadIdx.x & 31;
   const int sl = lane & (JB_LG - 1);
-  const uint32_t submask = 0xFFu << (lane & ~(JB_LG - 1));
+  const uint32_t submask = ((1u << JB_LG) - 1u) << (lane & ~(JB_LG - 1));
   const uint32_t n_sub = gridDim.x * blockDim.x / JB_LG;
   for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / JB_LG; w < n_work; w += n_sub) {
     const uint2 item = a.work_items[w];
@@ -659,7 +761,7 @@ __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupAr
         if (lam != 0.0)  // lambda == 0 can never infect
           jb_draw_core<VM>(a, p, lam_v, lam, ord + __popc(susm & ((1u << sl) - 1u)));
       }
-      ord += __popc(susm & 0xFFu);
+      ord += __popc(susm & ((1u << JB_LG) - 1u));
     }
   }
 }
@@ -691,6 +793,10 @@ struct NewInfArgs {
   int skip_local;           // only route halo infections (the host creates the local ones)
 };
 
+// 16 lanes per new infection: every completion time / transmission parameter is an independent
+// sample with its own Philox stream (JB_STREAM_SAMPLE0 + slot), so the lanes draw them in
+// parallel and lane 0 assembles the infection.  Slots: 0 max_severity; 1..8 stage s = slot-1;
+// 9..14 transmission parameter k = slot-9; 15 the second `alpha()` call of the xnexp profile.
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a) {
   // the disease tables are walked with data-dependent indices: stage them in shared memory once
   // per block instead of chasing them through L2 for every sample
@@ -703,23 +809,27 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
   __syncthreads();
   const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap) : a.count_host;
   const DiseaseDev& D = *reinterpret_cast<const DiseaseDev*>(s_dis);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, j = lane & 15;
+  const uint32_t segmask = 0xFFFFu << (lane & 16);
+  const uint32_t n_seg = gridDim.x * blockDim.x / 16;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / 16; i < n; i += n_seg) {
     const uint32_t p = a.member[i];
     const uint32_t var = a.variant ? a.variant[i] : 0u;
     if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
-      if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
-      atomicAdd(&a.counters[CNT_HALO_INF], 1u);
+      if (j == 0) {
+        if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
+        atomicAdd(&a.counters[CNT_HALO_INF], 1u);
+      }
       continue;
     }
     if (a.skip_local) continue;
-    uint32_t st = a.pstate[p];
+    const uint32_t st = a.pstate[p];
     if (st & (JB_PS_INFECTED | JB_PS_DEAD)) continue;  // cannot happen within a step; guards seeding
-    const uint32_t slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);
-    if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
-    JbStream rs;
-    jb_stream_init(rs, a.seed, a.step, a.gid_base + a.int2ext[p], JB_STREAM_NEWINF);
+    const uint32_t gid = a.gid_base + a.int2ext[p];
     // symptoms: max_severity -> outcome slot (symptoms.py:47,110-120; health_index.py:151-182)
-    const double max_sev = jb_stream_next(rs);
+    JbStream r0;
+    jb_stream_init(r0, a.seed, a.step, gid, JB_STREAM_SAMPLE0);
+    const double max_sev = jb_stream_next(r0);
     const int age = a.age[p] > 99 ? 99 : a.age[p];
     const int pop = (a.ch[p] && age >= 50) ? 1 : 0;
     const double* cum = a.hi_cum + ((size_t)(pop * 2 + a.sex[p]) * 100 + age) * D.n_tags;
@@ -729,16 +839,40 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
     int k = 0;
     for (int t = 0; t < D.n_traj; ++t)
       if (D.traj_max_tag[t] == idx) k = t;
-    // trajectory: cumulative stage start times (trajectory_maker.py:215-227)
     const int nst = D.traj_n_stages[k];
+    // my sample
+    double x = 0.0;
+    {
+      JbStream rs;
+      jb_stream_init(rs, a.seed, a.step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
+      if (j >= 1 && j <= 8) {
+        const int s = j - 1;
+        if (s < nst) x = jb_sample_dist(rs, D.traj_stage_time[k][s].type, D.traj_stage_time[k][s].p);
+      } else if (j >= 9) {
+        const int q = (j == 15) ? 3 : j - 9;
+        const int need = D.trans_type == JB_TRANS_GAMMA ? 4 : D.trans_type == JB_TRANS_XNEXP ? 5 : 1;
+        if (q < need && (j != 15 || D.trans_type == JB_TRANS_XNEXP)) x = jb_sample_dist(rs, D.trans_par[q].type, D.trans_par[q].p);
+      }
+    }
+    // lane 0 of the segment assembles the infection
+    double tstage[JB_MAX_STAGES], tp[7];
+#pragma unroll
+    for (int s = 0; s < JB_MAX_STAGES; ++s) tstage[s] = __shfl_sync(segmask, x, 1 + s, 16);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) tp[q] = __shfl_sync(segmask, x, 9 + q, 16);
+    if (j != 0) continue;
+    const uint32_t slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);
+    if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
+    // trajectory: cumulative stage start times (trajectory_maker.py:215-227)
     double cumt = 0.0, t_exposed = 0.0;
+#pragma unroll
     for (int s = 0; s < JB_MAX_STAGES; ++s) {
       double tt = 1e300;
       int tg = 0;
       if (s < nst) {
         tt = cumt;
         tg = D.traj_stage_tag[k][s];
-        cumt += jb_sample_dist(rs, D.traj_stage_time[k][s].type, D.traj_stage_time[k][s].p);
+        cumt += tstage[s];
       }
       if (s == 1) t_exposed = tt;
       a.traj_time[(size_t)s * a.C + slot] = tt;
@@ -747,28 +881,23 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
     // transmission (infection_selector.py:280-332)
     double par[JB_N_TPAR] = {0, 0, 0, 0, 0};
     if (D.trans_type == JB_TRANS_GAMMA) {
-      double max_inf = jb_sample_dist(rs, D.trans_par[0].type, D.trans_par[0].p);
-      double shape = jb_sample_dist(rs, D.trans_par[1].type, D.trans_par[1].p);
-      double rate = jb_sample_dist(rs, D.trans_par[2].type, D.trans_par[2].p);
-      double shift = jb_sample_dist(rs, D.trans_par[3].type, D.trans_par[3].p) + t_exposed;
-      par[0] = shape; par[1] = shift; par[2] = 1.0 / rate; par[3] = max_inf;
+      par[0] = tp[1]; par[1] = tp[3] + t_exposed; par[2] = 1.0 / tp[2]; par[3] = tp[0];
     } else if (D.trans_type == JB_TRANS_XNEXP) {
-      double tfi = jb_sample_dist(rs, D.trans_par[1].type, D.trans_par[1].p) + t_exposed;
-      double peak = t_exposed - tfi + jb_sample_dist(rs, D.trans_par[2].type, D.trans_par[2].p);
-      double maxp = jb_sample_dist(rs, D.trans_par[0].type, D.trans_par[0].p);
-      double norm_time = jb_sample_dist(rs, D.trans_par[4].type, D.trans_par[4].p);
-      double nn = peak / jb_sample_dist(rs, D.trans_par[3].type, D.trans_par[3].p);
-      double alpha = jb_sample_dist(rs, D.trans_par[3].type, D.trans_par[3].p);
-      double max_tau = nn * alpha * norm_time / norm_time;  // transmission_xnexp.py:119-121
+      const double tfi = tp[1] + t_exposed;
+      const double peak = t_exposed - tfi + tp[2];
+      const double norm_time = tp[4];
+      const double nn = peak / tp[3];
+      const double alpha = tp[6];
+      const double max_tau = nn * alpha * norm_time / norm_time;  // transmission_xnexp.py:119-121
       par[0] = nn; par[1] = alpha; par[2] = tfi; par[4] = norm_time;
-      par[3] = maxp / (pow(max_tau, nn) * exp(-max_tau / alpha));
+      par[3] = tp[0] / (pow(max_tau, nn) * exp(-max_tau / alpha));
     } else {
-      par[0] = jb_sample_dist(rs, D.trans_par[0].type, D.trans_par[0].p);
+      par[0] = tp[0];
     }
     for (int q = 0; q < JB_N_TPAR; ++q) a.inf_par[(size_t)q * a.C + slot] = par[q];
     a.inf_person[slot] = (int32_t)p;
     a.inf_start[slot] = a.now;
-    a.inf_next[slot] = a.traj_time[(size_t)1 * a.C + slot];
+    a.inf_next[slot] = nst > 1 ? tstage[0] : 1e300;  // == traj_time[1]
     a.inf_stage[slot] = 0;
     a.inf_nst[slot] = (uint8_t)nst;
     a.inf_var[slot] = (uint8_t)var;

@@ -12,8 +12,8 @@
 #include <stdint.h>
 
 #define JB_STREAM_BERNOULLI 0u
-#define JB_STREAM_NEWINF 1u
 #define JB_STREAM_VARIANT 2u
+#define JB_STREAM_SAMPLE0 16u  // + sample slot (0..15) of a new infection, see k_newinf
 
 struct JbPhilox4 {
   uint32_t x[4];
@@ -122,8 +122,8 @@ __host__ __device__ inline double jb_sample_dist(JbStream& s, int type, const do
     case 4: return p[0] + p[1] * jb_normal(s);                      // norm(loc, scale)
     case 5: {                                                       // exponweib(a, c, loc, scale)
       double u = jb_stream_next(s);                                 // F(x) = (1 - exp(-x^c))^a
-      double w = -expm1(log(u) / p[0]);                             // 1 - u^(1/a)
-      return p[2] + p[3] * pow(-log(w), 1.0 / p[1]);
+      double q = exp(log(u) / p[0]);                                // u^(1/a), may be << 1e-16
+      return p[2] + p[3] * pow(-log1p(-q), 1.0 / p[1]);
     }
     default: return 0.0;
   }

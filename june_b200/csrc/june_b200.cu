@@ -388,7 +388,7 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   NewInfArgs a = make_newinf_args(w);
   a.member = d_p; a.variant = d_v; a.count_dev = nullptr; a.count_host = (uint32_t)n; a.cap = (uint32_t)n;
   a.now = time; a.seed = seed; a.step = step;
-  unsigned blocks = (unsigned)std::min<size_t>((n + 127) / 128, 148 * 8);
+  unsigned blocks = (unsigned)std::min<size_t>((n * 16 + 127) / 128, 148 * 8);
   k_newinf<<<blocks, 128, 0, w->stream>>>(a);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(w->stream));
@@ -522,6 +522,11 @@ static int launch_warp(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_
   const int wpb = 4;
   size_t smem = jb_warp_smem_bytes(a.L, (int)w->V, dynamic ? w->bin_cap : 0u) * wpb;
   unsigned blocks = (a.n_list + wpb - 1) / wpb;
+  if (a.kind == JB_KIND_MATRIX && a.dim == 1 && !dynamic) {
+    k_groups_warp_d1<VM><<<blocks, wpb * 32, 0, st>>>(a);
+    KCHECK("k_groups_warp_d1", st);
+    return JB_OK;
+  }
   k_groups_warp<VM><<<blocks, wpb * 32, smem, st>>>(a);
   KCHECK("k_groups_warp", st);
   return JB_OK;
@@ -534,7 +539,9 @@ static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
   k_detect<STREAM><<<blocks, 256, 0, st>>>(a);
   KCHECK(STREAM ? "k_detect<stream>" : "k_detect<gather>", st);
   if (a.mode == 0) {
-    k_process<STREAM, VM><<<148 * 8, 128, 0, st>>>(a);
+    // households are small: 4 lanes per group; gathered groups (companies, care homes): 8
+    if (STREAM) k_process<STREAM, VM, 4><<<148 * 8, 128, 0, st>>>(a);
+    else k_process<STREAM, VM, 8><<<148 * 8, 128, 0, st>>>(a);
     KCHECK(STREAM ? "k_process<stream>" : "k_process<gather>", st);
   }
   return JB_OK;
@@ -677,7 +684,7 @@ extern "C" int jb_step_interact(JbWorld* w, const void* d_recv, void* d_ret_send
     a.cap = w->newinf_cap; a.now = p.now; a.seed = p.seed; a.step = p.step;
     a.halo_ret = (uint8_t*)d_ret_send;
     a.skip_local = (p.flags & JB_STEP_NO_NEW_INFECTIONS) ? 1 : 0;
-    k_newinf<<<148 * 2, 128, 0, s>>>(a);
+    k_newinf<<<148 * 8, 128, 0, s>>>(a);
     KCHECK("k_newinf", s);
     w->launches++;
   }
@@ -701,7 +708,7 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
     NewInfArgs a = make_newinf_args(w);
     a.member = member; a.variant = variant; a.count_dev = w->counters + CNT_HALO_INF;
     a.cap = w->newinf_cap; a.now = p.now; a.seed = p.seed; a.step = p.step;
-    if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS)) k_newinf<<<148, 128, 0, s>>>(a);
+    if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS)) k_newinf<<<148 * 2, 128, 0, s>>>(a);
     CK(cudaGetLastError());
     w->launches += 2;
   }

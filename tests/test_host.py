@@ -1,0 +1,86 @@
+"""Host-side mirrors against values dumped from the running reference (tests/golden/*.npz,
+SURVEY.md Appendix B)."""
+import datetime
+
+import numpy as np
+import pytest
+
+from june_b200.disease import DiseaseConfig, outcome_probabilities, synthetic_rates
+from june_b200.interaction import Interaction, processed_school_matrix
+from june_b200.policy import Policies, SocialDistancing, MaskWearing
+from june_b200.timer import Timer
+from june_b200.world import BetaRule
+
+from helpers import Golden
+
+
+def test_raw_contact_matrices_match_reference():
+    g = Golden("w3k")
+    inter = Interaction.from_file()
+    for k in g.z.files:
+        if k.startswith("cm_"):
+            spec = k[3:]
+            np.testing.assert_array_equal(inter.contact_matrices[spec], g.z[k], err_msg=spec)
+    ref = {str(k): float(v) for k, v in zip(g.z["beta_keys"], g.z["beta_vals"])}
+    assert ref == {k: float(v) for k, v in inter.betas.items()}
+
+
+def test_survey_appendix_b_spot_values():
+    inter = Interaction.from_file()
+    assert inter.contact_matrices["company"][0, 0] == 15.408000000000001
+    np.testing.assert_allclose(inter.contact_matrices["household"][2], [4.4268, 2.5984, 3.86208, 3.86208], rtol=1e-15)
+    s = inter.contact_matrices["school"]
+    assert s.shape == (32, 32) and s[0, 0] == 15.75 and s[1, 1] == 8.625
+    assert s[0, 1] == pytest.approx(48.60000000000001, rel=1e-15) and s[5, 9] == pytest.approx(0.06986249999999998, rel=1e-14)
+    m = processed_school_matrix(s, (4, 5, 6))
+    exp = [[15.75, 16.2, 16.2, 16.2], [0.81, 8.625, 2.5875, 0.77625], [0.81, 2.5875, 8.625, 2.5875], [0.81, 0.77625, 2.5875, 8.625]]
+    np.testing.assert_allclose(m, exp, rtol=1e-14)
+
+
+def test_outcome_table_matches_reference_health_index():
+    g = Golden("w3k")
+    dc = DiseaseConfig("covid19")
+    rates, bins = synthetic_rates()
+    prob = outcome_probabilities(dc, rates, bins)
+    np.testing.assert_allclose(prob, g.outcome_prob, rtol=1e-14, atol=0)
+
+
+def test_processed_beta_rules():
+    inter = Interaction.from_file()
+    inter.beta_reductions = {"company": 0.5, "school": 0.8, "household": 0.9}
+    # interactive.py:154-177
+    assert inter.processed_beta(BetaRule("company"), 0.95, None) == 0.371 * (1 + 0.95 * 1.0 * (0.5 - 1))
+    assert inter.processed_beta(BetaRule("company"), 0.95, 4) == 0.371 * (1 + 0.95 * 0.5 * (0.5 - 1))
+    # school.py:487-522: key falls back to "school" for beta and reduction
+    assert inter.processed_beta(BetaRule("primary_school", "school"), 1.0, None) == 0.07 * (1 + 1.0 * 1.0 * (0.8 - 1))
+    # household.py:305-307: no tier term
+    assert inter.processed_beta(BetaRule("household", None, False), 1.1, 4) == 0.208 * (1 + 1.1 * (0.9 - 1))
+
+
+def test_interaction_policies_multiply():
+    p = Policies([SocialDistancing("2020-03-16", "2020-03-24", beta_factors={"pub": 0.5, "company": 0.8}),
+                  MaskWearing("2020-03-20", "2020-04-01", compliance=0.5, beta_factor=0.5, mask_probabilities={"company": 0.4})])
+    assert dict(p.beta_reductions(datetime.datetime(2020, 3, 15))) == {}
+    assert dict(p.beta_reductions(datetime.datetime(2020, 3, 17))) == {"pub": 0.5, "company": 0.8}
+    r = p.beta_reductions(datetime.datetime(2020, 3, 21))
+    assert r["company"] == 0.8 * (1 - 0.4 * 0.5 * 0.5)
+
+
+def test_default_policy_file_parses():
+    p = Policies.from_file()
+    names = {type(x).__name__ for x in p.policies}
+    assert {"Hospitalisation", "SevereSymptomsStayHome", "RegionalCompliance", "SocialDistancing", "MaskWearing"} <= names
+    assert p.step_flags(datetime.datetime(2020, 3, 1)) == 0x3
+
+
+def test_timer_schedule_like_reference():
+    # june/time.py:110-161 semantics: shift resets when the calendar day changes
+    t = Timer(initial_day="2020-03-06 0:00", total_days=3, weekday_step_duration=[8, 16], weekend_step_duration=[24],
+              weekday_activities=[["primary_activity", "residence"], ["residence"]], weekend_activities=[["residence"]])
+    seen = []
+    while t.date < t.final_date:
+        seen.append((t.date.day, t.shift, t.duration, tuple(t.activities), t.day_type))
+        next(t)
+    assert seen == [(6, 0, 8 / 24, ("primary_activity", "residence"), "weekday"), (6, 1, 16 / 24, ("residence",), "weekday"),
+                    (7, 0, 1.0, ("residence",), "weekend"), (8, 0, 1.0, ("residence",), "weekend")]
+    assert t.now == 3.0
