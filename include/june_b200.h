@@ -283,6 +283,8 @@ int jb_fetch_summary(JbWorld* w, uint32_t* counts);
 
 /* Kernel timing hooks for bench.py: CUDA-event time (ms) of the interaction kernels and of
  * the whole step, measured on the library's stream, accumulated since the last reset. */
+/* on: 0 off; 1 whole-step events only (CUDA-graph replay stays on); 2 additionally per-kernel
+ * events around the interaction kernels (plain launches, no graph). */
 int jb_timing_enable(JbWorld* w, int on);
 /* on = 1 (default): the interaction kernels of different supergroups run concurrently on side
  * streams; on = 0: serially on the main stream (isolated per-kernel timings). */

@@ -104,6 +104,7 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
     beta_i: List[int] = []
     scale_i: List[int] = []
     region_i: List[int] = []
+    gsa_i: List[int] = []
     aux: List[int] = []
     years_flat: List[int] = []
     for name, act in supergroup_order(activity_to_super_groups):
@@ -126,6 +127,7 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
             groups.append(g)
             sa = getattr(g, "super_area", None)
             region_i.append(int(sa_region[sa_idx[id(sa)]]) if sa is not None and id(sa) in sa_idx else 0)
+            gsa_i.append(sa_idx[id(sa)] if sa is not None and id(sa) in sa_idx else 0)
             sc = 0
             a = 0
             if spec == "household":
@@ -206,6 +208,7 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
         school_years=np.array(years_flat, np.uint8), supergroups=supergroups, beta_rules=beta_rules,
         beta_scale=np.array(scales, np.float64), person_ids=person_ids,
         group_ids=np.array([int(g.id) for g in groups], np.int64),
+        grp_super_area=np.array(gsa_i, np.uint32),
     )
     w.validate()
     return w

@@ -32,6 +32,15 @@ enum {
 
 #define JB_TAG_BIT(tag) (1 << ((tag) + 2))
 
+// Per-step scalars, resident on the device so that a captured CUDA graph of the step can be
+// replayed: one h2d copy from a pinned ring buffer precedes every step.  The processed beta
+// table [n_beta][n_regions] follows the struct in the same allocation.
+struct StepDev {
+  double now, dt, t_now;
+  uint64_t seed;
+  uint32_t step, activity_mask, flags, n_inject;
+};
+
 // Arguments of the interaction (group) kernels; passed by value as a __grid_constant__.
 struct GroupArgs {
   const uint32_t* grp_off;
@@ -64,9 +73,7 @@ struct GroupArgs {
   int dim, kind, L;
   uint32_t N, NP;
   int V, R;
-  double dt;
-  uint64_t seed;
-  uint32_t step;
+  const StepDev* sp;         // dt, seed, step, n_inject
   uint32_t gid_base;
   uint32_t* counters;
   uint32_t* newinf_member;
@@ -74,7 +81,6 @@ struct GroupArgs {
   uint32_t newinf_cap;
   double* lambda;            // null unless JB_STEP_RECORD_LAMBDA
   const double* inject;      // null unless JB_STEP_INJECT_UNIFORMS
-  uint32_t n_inject;
   const uint32_t* draw_base; // exclusive scan of draw_cnt (inject mode)
   uint32_t* draw_cnt;
   int mode;                  // 0 = interact, 1 = only count draws per group
@@ -154,14 +160,24 @@ struct JbWorld {
   bool any_dynamic = false;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  // pinned host staging
-  double* h_beta = nullptr;
+  // per-step parameter block: device copy + pinned ring (written by the host, copied h2d per step)
+  unsigned char* d_step = nullptr;   // StepDev + beta table
+  unsigned char* d_step_aux = nullptr;  // StepDev for jb_infect (seeding outside a step)
+  unsigned char* h_step[4] = {};
+  cudaEvent_t ev_step_buf[4] = {};
+  size_t step_bytes = 0;
+  uint64_t step_seq = 0;
   uint32_t* h_counters = nullptr;
+  // captured step graphs, keyed by (phase, activity mask, flags, buffers)
+  struct GraphEntry { uint64_t k0, k1, k2; cudaGraphExec_t exec; uint64_t launches; };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;
   // step in flight
   JbStepParams cur;
   bool in_step = false;
   // timing
-  bool timing = false;
+  int timing = 0;
+  bool ev_detail = false;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr, ev_int0 = nullptr, ev_int1 = nullptr;
   cudaEvent_t ev_sg0[JB_MAX_SUPERGROUPS] = {}, ev_sg1[JB_MAX_SUPERGROUPS] = {};
   bool sg_pending[JB_MAX_SUPERGROUPS] = {};

@@ -41,15 +41,16 @@ struct PlaceArgs {
   uint32_t bin_cap;
   DynRanges dr;
   uint32_t* counters;
-  uint32_t N, activity_mask, flags;
+  uint32_t N;
+  const StepDev* sp;
 };
 
 __device__ __forceinline__ uint32_t jb_place_one(const PlaceArgs& a, uint32_t p, uint32_t st, uint32_t has,
                                                  uint32_t* cnt) {
   uint32_t act = JB_ACT_NONE;
   if (!(st & JB_PS_DEAD)) {
-    uint32_t allowed = a.activity_mask;
-    if ((a.flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE))
+    uint32_t allowed = a.sp->activity_mask;
+    if ((a.sp->flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE))
       allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
     if (st & JB_PS_MEDICAL) has |= 1u << JB_ACT_MEDICAL;
     const uint32_t cand = allowed & has;
@@ -141,15 +142,15 @@ __device__ __forceinline__ void jb_draw_core(const GroupArgs& a, uint32_t p, con
                                              uint32_t ordinal) {
   double u;
   if (a.inject) {
-    u = ordinal < a.n_inject ? a.inject[ordinal] : 2.0;
+    u = ordinal < a.sp->n_inject ? a.inject[ordinal] : 2.0;
   } else {
-    u = jb_bernoulli_uniform(a.seed, a.step, jb_gid(a, p));
+    u = jb_bernoulli_uniform(a.sp->seed, a.sp->step, jb_gid(a, p));
   }
   if (u < 1.0 - exp(-lam)) {
     uint32_t v = 0;
     if (VM > 1 && a.V > 1) {
       // np.random.choice(ids, p=lam_v/lam): inverse CDF on a second, independent uniform
-      double u2 = jb_variant_uniform(a.seed, a.step, jb_gid(a, p)) * lam;
+      double u2 = jb_variant_uniform(a.sp->seed, a.sp->step, jb_gid(a, p)) * lam;
       double c = 0.0;
       v = a.V - 1;
       for (int k = 0; k < a.V; ++k) {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(128) k_groups_warp(const __grid_constant__ Gro
         if (t != 0.0) {
           int nj = (int)n_l[j];
           int nn = (i == j) ? max(1, nj - 1) : nj;
-          s += jb_cm_elem(a, i, j, years, n_years) * t / (double)nn * beta * a.dt;
+          s += jb_cm_elem(a, i, j, years, n_years) * t / (double)nn * beta * a.sp->dt;
         }
       }
       row_l[v * L + i] = s;
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(128) k_groups_warp_d1(const __grid_constant__ 
   double row[VM];
 #pragma unroll
   for (int v = 0; v < VM; ++v)
-    row[v] = (v < V && T[v] != 0.0) ? a.cm[0] * T[v] / (double)max(1, (int)n - 1) * beta * a.dt : 0.0;  // interaction.py:469-471
+    row[v] = (v < V && T[v] != 0.0) ? a.cm[0] * T[v] / (double)max(1, (int)n - 1) * beta * a.sp->dt : 0.0;  // interaction.py:469-471
   uint32_t ord = a.inject ? a.draw_base[g] : 0u;
   for (uint32_t it0 = 0; it0 < ns; it0 += 32 * UB) {
     uint32_t p[UB], st[UB];
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupAr
             for (int j = 0; j < 4; ++j)
               if (j < a.dim && T[v][j] != 0.0) {
                 const int nn = (i == j) ? max(1, n[j] - 1) : n[j];  // interaction.py:469-471
-                r += a.cm[i * a.dim + j] * T[v][j] / (double)nn * beta * a.dt;
+                r += a.cm[i * a.dim + j] * T[v][j] / (double)nn * beta * a.sp->dt;
               }
             r *= a.susc[(size_t)v * a.NP + p];
           }
@@ -779,9 +780,7 @@ struct NewInfArgs {
   int V;
   uint32_t gid_base;
   const uint32_t* int2ext;
-  double now;
-  uint64_t seed;
-  uint32_t step;
+  const StepDev* sp;        // now, seed, step, flags
   const uint8_t* age; const uint8_t* sex; const uint8_t* ch;
   const double* hi_cum;
   const DiseaseDev* dis;
@@ -790,7 +789,6 @@ struct NewInfArgs {
   uint8_t* inf_stage; uint8_t* inf_nst; uint8_t* inf_var; int8_t* inf_tag; int8_t* inf_maxtag; int8_t* traj_tag;
   uint32_t* counters;
   uint8_t* halo_ret;        // per halo person: variant+1 if infected here (or null)
-  int skip_local;           // only route halo infections (the host creates the local ones)
 };
 
 // 16 lanes per new infection: every completion time / transmission parameter is an independent
@@ -822,13 +820,13 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
       }
       continue;
     }
-    if (a.skip_local) continue;
+    if (a.sp->flags & JB_STEP_NO_NEW_INFECTIONS) continue;  // only route halo infections (the host creates the local ones)
     const uint32_t st = a.pstate[p];
     if (st & (JB_PS_INFECTED | JB_PS_DEAD)) continue;  // cannot happen within a step; guards seeding
     const uint32_t gid = a.gid_base + a.int2ext[p];
     // symptoms: max_severity -> outcome slot (symptoms.py:47,110-120; health_index.py:151-182)
     JbStream r0;
-    jb_stream_init(r0, a.seed, a.step, gid, JB_STREAM_SAMPLE0);
+    jb_stream_init(r0, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0);
     const double max_sev = jb_stream_next(r0);
     const int age = a.age[p] > 99 ? 99 : a.age[p];
     const int pop = (a.ch[p] && age >= 50) ? 1 : 0;
@@ -844,7 +842,7 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
     double x = 0.0;
     {
       JbStream rs;
-      jb_stream_init(rs, a.seed, a.step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
+      jb_stream_init(rs, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
       if (j >= 1 && j <= 8) {
         const int s = j - 1;
         if (s < nst) x = jb_sample_dist(rs, D.traj_stage_time[k][s].type, D.traj_stage_time[k][s].p);
@@ -896,7 +894,7 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
     }
     for (int q = 0; q < JB_N_TPAR; ++q) a.inf_par[(size_t)q * a.C + slot] = par[q];
     a.inf_person[slot] = (int32_t)p;
-    a.inf_start[slot] = a.now;
+    a.inf_start[slot] = a.sp->now;
     a.inf_next[slot] = nst > 1 ? tstage[0] : 1e300;  // == traj_time[1]
     a.inf_stage[slot] = 0;
     a.inf_nst[slot] = (uint8_t)nst;
@@ -923,8 +921,7 @@ struct DiseaseMasks {
 struct HealthArgs {
   DiseaseMasks masks;
   uint32_t C;
-  double t_now;       // timer.now + timer.duration
-  uint32_t flags;
+  const StepDev* sp;  // t_now = timer.now + timer.duration, flags
   const DiseaseDev* dis;
   int32_t* inf_person; const double* inf_start; const double* inf_par; double* inf_next; const double* traj_time;
   uint8_t* inf_stage; const uint8_t* inf_nst; int8_t* inf_tag; const int8_t* traj_tag;
@@ -947,7 +944,7 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < hw; s += gridDim.x * blockDim.x) {
     const int32_t p = a.inf_person[s];
     if (p < 0) continue;
-    const double t = a.t_now - a.inf_start[s];
+    const double t = a.sp->t_now - a.inf_start[s];
     // transmission.update_infection_probability (infection.py:91)
     double prob;
     if (D.trans_type == JB_TRANS_GAMMA) {
@@ -977,7 +974,7 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
     const int bit = JB_TAG_BIT(tag);
     uint32_t st = a.pstate[p];
     // Hospitalisation.apply (medical_care_policies.py:413-526; hospital.py:62-122)
-    if (a.flags & JB_STEP_HOSPITALISATION) {
+    if (a.sp->flags & JB_STEP_HOSPITALISATION) {
       if (bit & D.hosp_mask) {
         int32_t hg;
         if (st & JB_PS_MEDICAL) hg = a.pmed[p] >> 8; else hg = a.sa_hospital[a.psa[p]];

@@ -245,7 +245,10 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   CK(cudaMemsetAsync(w->counters, 0, CNT_N * 4, s));
   TRY(dev_alloc(&w->newinf_member, w->newinf_cap));
   TRY(dev_alloc(&w->newinf_var, w->newinf_cap));
-  TRY(dev_alloc(&w->beta, (size_t)w->n_beta * w->R));
+  w->step_bytes = sizeof(StepDev) + sizeof(double) * (size_t)w->n_beta * w->R;
+  TRY(dev_alloc(&w->d_step, w->step_bytes));
+  TRY(dev_alloc(&w->d_step_aux, sizeof(StepDev)));
+  w->beta = reinterpret_cast<double*>(w->d_step + sizeof(StepDev));
   TRY(dev_alloc(&w->draw_cnt, (size_t)w->G + 1));
   TRY(dev_alloc(&w->draw_base, (size_t)w->G + 1));
   if (w->any_dynamic) {
@@ -265,7 +268,10 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     w->cub_tmp_bytes = b2 + 256;
     CK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
   }
-  CK(cudaMallocHost((void**)&w->h_beta, sizeof(double) * std::max<size_t>(1, (size_t)w->n_beta * w->R)));
+  for (int i = 0; i < 4; ++i) {
+    CK(cudaMallocHost((void**)&w->h_step[i], w->step_bytes));
+    CK(cudaEventCreateWithFlags(&w->ev_step_buf[i], cudaEventDisableTiming));
+  }
   CK(cudaMallocHost((void**)&w->h_counters, sizeof(uint32_t) * CNT_N));
   CK(cudaEventCreate(&w->ev_step0));
   CK(cudaEventCreate(&w->ev_step1));
@@ -296,7 +302,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->pstate, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->counters, w->newinf_member, w->newinf_var,
-                  w->beta, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_cnt, w->dyn_bin,
+                  w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_cnt, w->dyn_bin,
                   w->cub_tmp, w->int2ext};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -307,7 +313,11 @@ extern "C" void jb_world_destroy(JbWorld* w) {
     if (t.big_list) cudaFree(t.big_list);
     if (t.work_items) cudaFree(t.work_items);
   }
-  if (w->h_beta) cudaFreeHost(w->h_beta);
+  for (int i = 0; i < 4; ++i) {
+    if (w->h_step[i]) cudaFreeHost(w->h_step[i]);
+    if (w->ev_step_buf[i]) cudaEventDestroy(w->ev_step_buf[i]);
+  }
+  for (JbWorld::GraphEntry& e : w->graphs) cudaGraphExecDestroy(e.exec);
   if (w->h_counters) cudaFreeHost(w->h_counters);
   if (w->ev_step0) cudaEventDestroy(w->ev_step0);
   if (w->ev_step1) cudaEventDestroy(w->ev_step1);
@@ -357,6 +367,8 @@ extern "C" int jb_inject_uniforms(JbWorld* w, const double* u, size_t n) {
   return JB_OK;
 }
 
+static inline const StepDev* step_dev(JbWorld* w) { return reinterpret_cast<const StepDev*>(w->d_step); }
+
 static NewInfArgs make_newinf_args(JbWorld* w) {
   NewInfArgs a;
   memset(&a, 0, sizeof(a));
@@ -387,7 +399,12 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   TRY(dev_upload(&d_v, v8.data(), n, w->stream));
   NewInfArgs a = make_newinf_args(w);
   a.member = d_p; a.variant = d_v; a.count_dev = nullptr; a.count_host = (uint32_t)n; a.cap = (uint32_t)n;
-  a.now = time; a.seed = seed; a.step = step;
+  StepDev sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.now = time; sd.seed = seed; sd.step = step;
+  CK(cudaMemcpyAsync(w->d_step_aux, &sd, sizeof(sd), cudaMemcpyHostToDevice, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  a.sp = reinterpret_cast<const StepDev*>(w->d_step_aux);
   unsigned blocks = (unsigned)std::min<size_t>((n * 16 + 127) / 128, 148 * 8);
   k_newinf<<<blocks, 128, 0, w->stream>>>(a);
   CK(cudaGetLastError());
@@ -505,12 +522,12 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   a.group_list = nullptr; a.n_list = sg.n_groups; a.int2ext = w->int2ext;
   a.dim = sg.dim; a.kind = sg.kind; a.L = L;
   a.N = w->N; a.NP = w->NP; a.V = (int)w->V; a.R = (int)w->R;
-  a.dt = p.delta_time; a.seed = p.seed; a.step = p.step; a.gid_base = (uint32_t)w->id_base;
+  a.sp = step_dev(w); a.gid_base = (uint32_t)w->id_base;
   a.counters = w->counters; a.newinf_member = w->newinf_member; a.newinf_var = w->newinf_var;
   a.newinf_cap = w->newinf_cap;
   a.lambda = (p.flags & JB_STEP_RECORD_LAMBDA) ? w->lambda : nullptr;
   if (p.flags & JB_STEP_INJECT_UNIFORMS) {
-    a.inject = w->inject; a.n_inject = (uint32_t)w->n_inject; a.draw_base = w->draw_base;
+    a.inject = w->inject; a.draw_base = w->draw_base;
   }
   a.draw_cnt = w->draw_cnt;
   a.mode = 0;
@@ -559,7 +576,7 @@ static int launch_groups(JbWorld* w, int mode) {
     if (!w->serial) CK(cudaStreamWaitEvent(st, w->ev_fork, 0));
     GroupArgs a = make_group_args(w, sg, w->sg_L[k]);
     a.mode = mode;
-    const bool tme = w->timing && mode == 0;
+    const bool tme = w->timing >= 2 && mode == 0;
     if (tme) CK(cudaEventRecord(w->ev_sg0[k], st));
     const SgTiles& T = w->tiles[k];
     if (T.mode == 0) {
@@ -595,7 +612,7 @@ static int harvest_timing(JbWorld* w) {
   if (!w->ev_pending) return JB_OK;
   CK(cudaEventSynchronize(w->ev_step1));
   float a = 0, b = 0;
-  CK(cudaEventElapsedTime(&a, w->ev_int0, w->ev_int1));
+  if (w->ev_detail) CK(cudaEventElapsedTime(&a, w->ev_int0, w->ev_int1));
   CK(cudaEventElapsedTime(&b, w->ev_step0, w->ev_step1));
   w->acc_int_ms += a; w->acc_step_ms += b; w->acc_steps++;
   for (size_t k = 0; k < w->sgs.size(); ++k)
@@ -606,6 +623,147 @@ static int harvest_timing(JbWorld* w) {
       w->sg_pending[k] = false;
     }
   w->ev_pending = false;
+  return JB_OK;
+}
+
+// ---- device work of the three step phases (no host synchronisation: capturable) ----------
+
+static int enqueue_begin(JbWorld* w, void* d_send) {
+  cudaStream_t s = w->stream;
+  const JbStepParams& p = w->cur;
+  CK(cudaMemsetAsync(w->counters, 0, CNT_STEP_END * 4, s));
+  if (w->any_dynamic) CK(cudaMemsetAsync(w->dyn_cnt, 0, (size_t)w->n_bins * 4, s));
+  if (p.flags & JB_STEP_RECORD_LAMBDA) {
+    k_fill_f64<<<(w->NP + 255) / 256, 256, 0, s>>>(w->lambda, w->NP, std::numeric_limits<double>::quiet_NaN());
+    w->launches++;
+  }
+  if (w->N) {
+    PlaceArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.pstate = w->pstate; pa.phas = w->phas; pa.pmed = w->pmed; pa.dyn_cnt = w->dyn_cnt; pa.dyn_bin = w->dyn_bin;
+    pa.bin_cap = w->bin_cap; pa.counters = w->counters; pa.N = w->N; pa.sp = step_dev(w);
+    for (size_t k = 0; k < w->sgs.size(); ++k)
+      if (w->sgs[k].has_dynamic) {
+        uint32_t r = pa.dr.n++;
+        pa.dr.first[r] = w->sgs[k].first_group; pa.dr.count[r] = w->sgs[k].n_groups; pa.dr.bin_base[r] = w->sg_bin_base[k];
+      }
+    const uint32_t chunks = (w->N + 15) / 16;
+    k_place<<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
+    KCHECK("k_place", s);
+    w->launches++;
+  }
+  if (w->n_out && d_send) {
+    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->pstate, w->pvar, w->susc, w->trans,
+                                                       w->NP, (int)w->V, (unsigned char*)d_send);
+    KCHECK("k_halo_pack", s);
+    w->launches++;
+  }
+  return JB_OK;
+}
+
+static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
+  cudaStream_t s = w->stream;
+  const JbStepParams& p = w->cur;
+  if (w->H && d_recv) {
+    k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
+                                                     w->pstate, w->pvar, w->susc, w->trans, (uint8_t*)d_ret_send);
+    KCHECK("k_halo_unpack", s);
+    w->launches++;
+  }
+  if (w->timing >= 2) CK(cudaEventRecord(w->ev_int0, s));
+  if (p.flags & JB_STEP_INJECT_UNIFORMS) {
+    CK(cudaMemsetAsync(w->draw_cnt, 0, ((size_t)w->G + 1) * 4, s));
+    TRY(launch_groups(w, 1));
+    size_t tmp = w->cub_tmp_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->draw_cnt, w->draw_base, (int)(w->G + 1), s));
+    w->launches += 2;
+  }
+  TRY(launch_groups(w, 0));
+  if (w->timing >= 2) CK(cudaEventRecord(w->ev_int1, s));
+  // create infections for residents infected here; flag halo persons for their home domain
+  if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS) || w->H) {
+    NewInfArgs a = make_newinf_args(w);
+    a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_NEWINF;
+    a.cap = w->newinf_cap; a.sp = step_dev(w);
+    a.halo_ret = (uint8_t*)d_ret_send;
+    k_newinf<<<148 * 8, 128, 0, s>>>(a);
+    KCHECK("k_newinf", s);
+    w->launches++;
+  }
+  return JB_OK;
+}
+
+static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
+  cudaStream_t s = w->stream;
+  const JbStepParams& p = w->cur;
+  if (w->n_out && d_ret_recv) {
+    // residents infected abroad: reuse the new-infection list
+    // (tell_domains_to_infect, epidemiology.py:359-401)
+    CK(cudaMemsetAsync(w->counters + CNT_HALO_INF, 0, 4, s));
+    k_halo_return<<<(w->n_out + 255) / 256, 256, 0, s>>>((const uint8_t*)d_ret_recv, w->out_person, w->n_out,
+                                                         w->newinf_member, w->newinf_var, w->newinf_cap,
+                                                         w->counters + CNT_HALO_INF);
+    KCHECK("k_halo_return", s);
+    w->launches++;
+    if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS)) {
+      NewInfArgs a = make_newinf_args(w);
+      a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_HALO_INF;
+      a.cap = w->newinf_cap; a.sp = step_dev(w);
+      k_newinf<<<148 * 2, 128, 0, s>>>(a);
+      KCHECK("k_newinf(halo)", s);
+      w->launches++;
+    }
+  }
+  CK(cudaMemsetAsync(w->counters + CNT_INFECTED, 0, 3 * 4, s));
+  {
+    HealthArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C = w->C; a.sp = step_dev(w); a.dis = w->dis;
+    a.masks.trans_type = w->dis_host.trans_type; a.masks.rec_mask = w->dis_host.rec_mask;
+    a.masks.dead_mask = w->dis_host.dead_mask; a.masks.hosp_mask = w->dis_host.hosp_mask;
+    a.masks.icu_mask = w->dis_host.icu_mask; a.masks.severe_mask = w->dis_host.severe_mask;
+    a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
+    a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
+    a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
+    a.pslot = w->pslot; a.phas = w->phas; a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.counters = w->counters;
+    k_health<<<148 * 4, 256, 0, s>>>(a);
+    KCHECK("k_health", s);
+    w->launches++;
+  }
+  CK(cudaMemcpyAsync(w->h_counters, w->counters, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+  return JB_OK;
+}
+
+// Run one phase: replay its captured CUDA graph, capturing it on first use.  Graphs are keyed by
+// everything that shapes the launch sequence (phase, activity mask, flags, exchange buffers);
+// the per-step scalars live in the device parameter block, so a replay needs no patching.
+template <typename F>
+static int run_phase(JbWorld* w, int phase, const void* p0, const void* p1, F&& enqueue) {
+  const JbStepParams& p = w->cur;
+  const bool plain = !w->use_graphs || w->timing >= 2 || jb_debug_sync() ||
+                     (p.flags & (JB_STEP_INJECT_UNIFORMS | JB_STEP_RECORD_LAMBDA));
+  if (plain) return enqueue();
+  const uint64_t k0 = ((uint64_t)phase << 56) | ((uint64_t)(w->serial ? 1 : 0) << 48) | ((uint64_t)p.activity_mask << 32) | p.flags;
+  const uint64_t k1 = (uint64_t)(uintptr_t)p0, k2 = (uint64_t)(uintptr_t)p1;
+  for (const JbWorld::GraphEntry& e : w->graphs)
+    if (e.k0 == k0 && e.k1 == k1 && e.k2 == k2) {
+      CK(cudaGraphLaunch(e.exec, w->stream));
+      w->launches += e.launches;
+      return JB_OK;
+    }
+  const uint64_t before = w->launches;
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue();
+  cudaError_t ce = cudaStreamEndCapture(w->stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) { jb_set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return JB_ECUDA; }
+  JbWorld::GraphEntry e;
+  e.k0 = k0; e.k1 = k1; e.k2 = k2; e.exec = nullptr; e.launches = w->launches - before;
+  CK(cudaGraphInstantiate(&e.exec, graph, 0));
+  CK(cudaGraphDestroy(graph));
+  w->graphs.push_back(e);
+  CK(cudaGraphLaunch(e.exec, w->stream));
   return JB_OK;
 }
 
@@ -621,36 +779,17 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
     TRY(harvest_timing(w));
     CK(cudaEventRecord(w->ev_step0, s));
   }
-  memcpy(w->h_beta, p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
-  CK(cudaMemcpyAsync(w->beta, w->h_beta, sizeof(double) * (size_t)w->n_beta * w->R, cudaMemcpyHostToDevice, s));
-  CK(cudaMemsetAsync(w->counters, 0, CNT_STEP_END * 4, s));
-  if (w->any_dynamic) CK(cudaMemsetAsync(w->dyn_cnt, 0, (size_t)w->n_bins * 4, s));
-  if (p->flags & JB_STEP_RECORD_LAMBDA) {
-    if (!w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
-    k_fill_f64<<<(w->NP + 255) / 256, 256, 0, s>>>(w->lambda, w->NP, std::numeric_limits<double>::quiet_NaN());
-    w->launches++;
-  }
-  if (w->N) {
-    PlaceArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    pa.pstate = w->pstate; pa.phas = w->phas; pa.pmed = w->pmed; pa.dyn_cnt = w->dyn_cnt; pa.dyn_bin = w->dyn_bin;
-    pa.bin_cap = w->bin_cap; pa.counters = w->counters; pa.N = w->N; pa.activity_mask = p->activity_mask; pa.flags = p->flags;
-    for (size_t k = 0; k < w->sgs.size(); ++k)
-      if (w->sgs[k].has_dynamic) {
-        uint32_t r = pa.dr.n++;
-        pa.dr.first[r] = w->sgs[k].first_group; pa.dr.count[r] = w->sgs[k].n_groups; pa.dr.bin_base[r] = w->sg_bin_base[k];
-      }
-    const uint32_t chunks = (w->N + 15) / 16;
-    k_place<<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
-    KCHECK("k_place", s);
-    w->launches++;
-  }
-  if (w->n_out && d_send) {
-    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->pstate, w->pvar, w->susc, w->trans,
-                                                       w->NP, (int)w->V, (unsigned char*)d_send);
-    CK(cudaGetLastError());
-    w->launches++;
-  }
+  if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
+  // per-step parameter block: pinned ring slot -> device (the h2d payload of every step)
+  const int slot = (int)(w->step_seq++ & 3);
+  CK(cudaEventSynchronize(w->ev_step_buf[slot]));  // the copy that last used this slot has finished
+  StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
+  h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject;
+  memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
+  CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(w->ev_step_buf[slot], s));
+  TRY(run_phase(w, 0, d_send, nullptr, [&]() { return enqueue_begin(w, d_send); }));
   w->in_step = true;
   return JB_OK;
 }
@@ -659,36 +798,7 @@ extern "C" int jb_step_interact(JbWorld* w, const void* d_recv, void* d_ret_send
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   REQUIRE(w->in_step, "jb_step_interact without jb_step_begin");
   CK(cudaSetDevice(w->device));
-  cudaStream_t s = w->stream;
-  const JbStepParams& p = w->cur;
-  if (w->H && d_recv) {
-    k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
-                                                     w->pstate, w->pvar, w->susc, w->trans, (uint8_t*)d_ret_send);
-    CK(cudaGetLastError());
-    w->launches++;
-  }
-  if (w->timing) CK(cudaEventRecord(w->ev_int0, s));
-  if (p.flags & JB_STEP_INJECT_UNIFORMS) {
-    CK(cudaMemsetAsync(w->draw_cnt, 0, ((size_t)w->G + 1) * 4, s));
-    TRY(launch_groups(w, 1));
-    size_t tmp = w->cub_tmp_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->draw_cnt, w->draw_base, (int)(w->G + 1), s));
-    w->launches += 2;
-  }
-  TRY(launch_groups(w, 0));
-  if (w->timing) CK(cudaEventRecord(w->ev_int1, s));
-  // create infections for residents infected here; flag halo persons for their home domain
-  if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS) || w->H) {
-    NewInfArgs a = make_newinf_args(w);
-    a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_NEWINF;
-    a.cap = w->newinf_cap; a.now = p.now; a.seed = p.seed; a.step = p.step;
-    a.halo_ret = (uint8_t*)d_ret_send;
-    a.skip_local = (p.flags & JB_STEP_NO_NEW_INFECTIONS) ? 1 : 0;
-    k_newinf<<<148 * 8, 128, 0, s>>>(a);
-    KCHECK("k_newinf", s);
-    w->launches++;
-  }
-  return JB_OK;
+  return run_phase(w, 1, d_recv, d_ret_send, [&]() { return enqueue_interact(w, d_recv, d_ret_send); });
 }
 
 extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* out) {
@@ -696,40 +806,8 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
   REQUIRE(w->in_step, "jb_step_finish without jb_step_begin");
   CK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
-  const JbStepParams& p = w->cur;
-  if (w->n_out && d_ret_recv) {
-    // residents infected abroad: reuse the tail of the new-infection list
-    // (tell_domains_to_infect, epidemiology.py:359-401)
-    uint32_t* member = w->newinf_member;
-    uint8_t* variant = w->newinf_var;
-    CK(cudaMemsetAsync(w->counters + CNT_HALO_INF, 0, 4, s));
-    k_halo_return<<<(w->n_out + 255) / 256, 256, 0, s>>>((const uint8_t*)d_ret_recv, w->out_person, w->n_out, member,
-                                                         variant, w->newinf_cap, w->counters + CNT_HALO_INF);
-    NewInfArgs a = make_newinf_args(w);
-    a.member = member; a.variant = variant; a.count_dev = w->counters + CNT_HALO_INF;
-    a.cap = w->newinf_cap; a.now = p.now; a.seed = p.seed; a.step = p.step;
-    if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS)) k_newinf<<<148 * 2, 128, 0, s>>>(a);
-    CK(cudaGetLastError());
-    w->launches += 2;
-  }
-  CK(cudaMemsetAsync(w->counters + CNT_INFECTED, 0, 3 * 4, s));
-  {
-    HealthArgs a;
-    memset(&a, 0, sizeof(a));
-    a.C = w->C; a.t_now = p.now + p.delta_time; a.flags = p.flags; a.dis = w->dis;
-    a.masks.trans_type = w->dis_host.trans_type; a.masks.rec_mask = w->dis_host.rec_mask;
-    a.masks.dead_mask = w->dis_host.dead_mask; a.masks.hosp_mask = w->dis_host.hosp_mask;
-    a.masks.icu_mask = w->dis_host.icu_mask; a.masks.severe_mask = w->dis_host.severe_mask;
-    a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
-    a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
-    a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
-    a.pslot = w->pslot; a.phas = w->phas; a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.counters = w->counters;
-    k_health<<<148 * 4, 256, 0, s>>>(a);
-    KCHECK("k_health", s);
-    w->launches++;
-  }
-  CK(cudaMemcpyAsync(w->h_counters, w->counters, CNT_N * 4, cudaMemcpyDeviceToHost, s));
-  if (w->timing) { CK(cudaEventRecord(w->ev_step1, s)); w->ev_pending = true; }
+  TRY(run_phase(w, 2, d_ret_recv, nullptr, [&]() { return enqueue_finish(w, d_ret_recv); }));
+  if (w->timing) { CK(cudaEventRecord(w->ev_step1, s)); w->ev_pending = true; w->ev_detail = w->timing >= 2; }
   w->in_step = false;
   if (out) {
     CK(cudaStreamSynchronize(s));
@@ -759,10 +837,69 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
   return JB_OK;
 }
 
+// Single-GPU step: the three phases are captured as ONE graph.
 extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
-  TRY(jb_step_begin(w, p, nullptr));
-  TRY(jb_step_interact(w, nullptr, nullptr));
-  return jb_step_finish(w, nullptr, out);
+  if (w && (w->H || w->n_out)) {  // halo worlds need the exchange between the phases
+    TRY(jb_step_begin(w, p, nullptr));
+    TRY(jb_step_interact(w, nullptr, nullptr));
+    return jb_step_finish(w, nullptr, out);
+  }
+  // same prologue as jb_step_begin, then one graph for begin + interact + finish
+  if (!w || !p) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(!w->in_step, "jb_step: previous step not finished");
+  REQUIRE(p->beta != nullptr, "JbStepParams.beta is null");
+  REQUIRE(p->delta_time > 0.0, "delta_time must be positive");
+  CK(cudaSetDevice(w->device));
+  cudaStream_t s = w->stream;
+  w->cur = *p;
+  if (w->timing) {
+    TRY(harvest_timing(w));
+    CK(cudaEventRecord(w->ev_step0, s));
+  }
+  if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
+  const int slot = (int)(w->step_seq++ & 3);
+  CK(cudaEventSynchronize(w->ev_step_buf[slot]));
+  StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
+  h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject;
+  memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
+  CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(w->ev_step_buf[slot], s));
+  TRY(run_phase(w, 3, nullptr, nullptr, [&]() {
+    TRY(enqueue_begin(w, nullptr));
+    TRY(enqueue_interact(w, nullptr, nullptr));
+    return enqueue_finish(w, nullptr);
+  }));
+  w->in_step = true;  // jb_step_finish_tail expects it
+  if (w->timing) { CK(cudaEventRecord(w->ev_step1, s)); w->ev_pending = true; w->ev_detail = w->timing >= 2; }
+  w->in_step = false;
+  if (!out) return JB_OK;
+  CK(cudaStreamSynchronize(s));
+  {
+    const uint32_t* c = w->h_counters;
+    memset(out, 0, sizeof(*out));
+    out->n_new_infections = c[CNT_NEWINF];
+    out->n_infected = c[CNT_INFECTED];
+    out->n_dead_total = c[CNT_DEAD_TOTAL];
+    out->n_recovered_step = c[CNT_RECOVERED_STEP];
+    out->n_deaths_step = c[CNT_DEATHS_STEP];
+    out->n_hospitalised = c[CNT_HOSP];
+    out->n_icu = c[CNT_ICU];
+    out->n_draws = c[CNT_DRAWS];
+    out->n_no_activity = c[CNT_NOACT];
+    out->n_slots_used = c[CNT_SLOTS_HW];
+    out->n_halo_infected = c[CNT_HALO_INF];
+    for (int a = 0; a < JB_N_ACT; ++a) out->n_by_activity[a] = c[CNT_ACT0 + a];
+    if (c[CNT_NOACT]) {
+      jb_set_error("Attention! Some people do not have an activity in this timestep.");
+      return JB_ENOACT;
+    }
+    if (c[CNT_OVERFLOW]) {
+      jb_set_error("a device buffer capacity was exceeded (dynamic members / new infections / slots)");
+      return JB_ECAP;
+    }
+  }
+  return JB_OK;
 }
 
 extern "C" int jb_sync(JbWorld* w) {
@@ -902,7 +1039,9 @@ extern "C" int jb_set_concurrency(JbWorld* w, int on) {
 
 extern "C" int jb_timing_enable(JbWorld* w, int on) {
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
-  w->timing = on != 0;
+  TRY(harvest_timing(w));
+  w->timing = on;  // 1: whole-step events only (graphs stay on); 2: + per-kernel events (plain launches)
+  w->ev_detail = on >= 2;
   return JB_OK;
 }
 

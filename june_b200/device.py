@@ -244,8 +244,9 @@ class Engine:
     def set_concurrency(self, on: bool = True):
         self._check(self._f("set_concurrency")(self._h, 1 if on else 0))
 
-    def timing_enable(self, on: bool = True):
-        self._check(self._f("timing_enable")(self._h, 1 if on else 0))
+    def timing_enable(self, level: int = 1):
+        """0 off; 1 whole-step CUDA events (graph replay stays on); 2 + per-kernel events (plain launches)."""
+        self._check(self._f("timing_enable")(self._h, int(level)))
 
     def timing_read_supergroups(self) -> List[Dict[str, float]]:
         k = len(self.world.supergroups)

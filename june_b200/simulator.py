@@ -162,6 +162,7 @@ class Simulator:
         self.step_ordinal = 0
         self.rank = 0
         self._region_state: dict = {}
+        self._policy_cache: dict = {}
         if outcome_prob is None:
             from .disease import outcome_probabilities, synthetic_rates
             rates, bins = synthetic_rates()
@@ -197,15 +198,23 @@ class Simulator:
 
     # ---- one step -----------------------------------------------------------------------------------
     def step_params(self, extra_flags: int = 0):
+        """Per-step host scalars (``simulator.py:360-366`` + ``get_processed_beta``).  Everything
+        but the clock depends only on WHICH policies are active, so the beta table and flags are
+        cached per active-policy set."""
         date = self.timer.date
         policies = self.activity_manager.policies
-        self.interaction.beta_reductions = policies.beta_reductions(date)
-        comp, tiers = policies.regional_scalars(date, self.world.region_names, self._region_state)
-        beta = self.interaction.beta_table(self.world.beta_rules, comp, tiers)
-        flags = policies.step_flags(date) | extra_flags
+        key = tuple(p.is_active(date) for p in policies.policies)
+        hit = self._policy_cache.get(key)
+        if hit is None:
+            self.interaction.beta_reductions = policies.beta_reductions(date)
+            comp, tiers = policies.regional_scalars(date, self.world.region_names, self._region_state)
+            beta = np.ascontiguousarray(self.interaction.beta_table(self.world.beta_rules, comp, tiers))
+            hit = (beta, policies.step_flags(date), dict(self.interaction.beta_reductions))
+            self._policy_cache[key] = hit
+        beta, flags, self.interaction.beta_reductions = hit
         return self.device.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self.step_ordinal,
                                        activity_mask=self.activity_manager.activity_mask(), seed=self.seed,
-                                       flags=flags, beta=beta)
+                                       flags=flags | extra_flags, beta=beta)
 
     def do_timestep(self, want_stats: bool = True) -> None:
         activities = self.timer.activities

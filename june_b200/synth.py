@@ -274,6 +274,12 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     ch_sa = (np.arange(n_ch) * n_sa // n_ch).astype(np.int64)
     beta_idx[g_ch0:] = 7
     region[g_ch0:] = sa_region[ch_sa]
+    grp_sa = np.zeros(G, np.uint32)
+    grp_sa[g_hosp0:g_school0] = hosp_sa
+    grp_sa[g_school0:g_comp0] = school_sa
+    grp_sa[g_comp0:g_hh0] = comp_sa
+    grp_sa[g_hh0:g_ch0] = sa_of_hh
+    grp_sa[g_ch0:] = ch_sa
 
     # ---- registrations ----------------------------------------------------------------------------
     add_rows(g_hosp0 + hosp_of_worker, np.zeros(len(hosp_workers)), hosp_workers, ACT_PRIMARY)
@@ -304,6 +310,7 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
         reg_member=reg_member, reg_info=reg_info, school_years=years_age, supergroups=supergroups,
         beta_rules=rules, beta_scale=np.array(scales, np.float64),
         person_id_base=(rank * n_people if person_id_base is None else person_id_base),
+        grp_super_area=grp_sa,
     )
     w.validate()
     return DomainDraft(world=w, out_person=out_person, company_first=g_comp0, company_count=n_comp,

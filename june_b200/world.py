@@ -117,10 +117,11 @@ class WorldSoA:
     # bookkeeping for adapters (not used on the device)
     person_ids: Optional[np.ndarray] = None  # reference Person.id per person index
     group_ids: Optional[np.ndarray] = None   # reference Group.id per group index
+    grp_super_area: Optional[np.ndarray] = None  # super area of every group (domain decomposition)
 
     _ARRAYS = ("age", "sex", "care_home_resident", "has_activity", "super_area", "sa_hospital", "sa_region",
                "grp_offset", "grp_info", "grp_aux", "reg_member", "reg_info", "school_years", "beta_scale",
-               "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids")
+               "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids", "grp_super_area")
 
     @property
     def n_people(self) -> int:

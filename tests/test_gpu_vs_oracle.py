@@ -46,6 +46,30 @@ def compare_state(a, b, tag=""):
     np.testing.assert_allclose(sa["trans_prob"], sb["trans_prob"], rtol=REL, atol=0, err_msg=f"{tag}: trans")
 
 
+def test_graph_replay_matches_plain_launches_and_oracle():
+    """Without the record/inject test flags the step runs as a replayed CUDA graph: state must
+    still equal the oracle's, step after step."""
+    assert have_gpu()
+    w = generate_world(40_000, seed=8, sector_betas=load_defaults()["company_sector_betas"])
+    a, b, beta = setup(w)
+    seeds = np.sort(np.random.default_rng(1).choice(w.n_people, 1200, replace=False)).astype(np.uint32)
+    for e in (a, b):
+        e.infect(seeds, time=-5.0, seed=11, step=1000)
+    flags = _lib.STEP_SEVERE_STAY_HOME | _lib.STEP_HOSPITALISATION
+    now = 0.0
+    for i in range(30):
+        m, dt = MASKS[i % 5], DTS[i % 5]
+        sa = a.step(a.make_params(now, dt, i, m, seed=5, flags=flags, beta=beta))
+        sb = b.step(b.make_params(now, dt, i, m, seed=5, flags=flags, beta=beta))
+        for key in ("n_new_infections", "n_infected", "n_dead_total", "n_recovered_step", "n_hospitalised", "n_draws"):
+            assert sa[key] == sb[key], (i, key, sa[key], sb[key])
+        assert np.array_equal(a.fetch_new_infections()[0], b.fetch_new_infections()[0]), f"step {i}"
+        if i % 5 == 4:
+            compare_state(a, b, f"step {i}")
+        now += dt
+    compare_state(a, b, "end")
+
+
 def test_philox_mode_full_steps_match_oracle():
     assert have_gpu()
     w = generate_world(60_000, seed=3, sector_betas=load_defaults()["company_sector_betas"])
