@@ -58,6 +58,7 @@ class Engine:
                  outcome_prob: np.ndarray, device: int = 0, n_variants: int = 1, slot_capacity: int = 0):
         self._lib = lib
         self._p = prefix
+        self.device_index = device
         self.world = world
         self.interaction = interaction
         self.disease = disease

@@ -175,7 +175,12 @@ class Simulator:
             self.rank = dist.get_rank()
             on_gpu = isinstance(self.device, DeviceWorld)
             self.halo = HaloExchange(world, self.device.halo_record_size(),
-                                     device=torch.device("cuda", device) if on_gpu else None)
+                                     device=torch.device("cuda", self.device.device_index) if on_gpu else None)
+        self._ext_stream = None
+        if self.halo is not None and isinstance(self.device, DeviceWorld):
+            import torch
+            ptr = self.device._f("stream_handle")(self.device.handle)
+            self._ext_stream = torch.cuda.ExternalStream(int(ptr), device=torch.device("cuda", self.device.device_index))
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
 
@@ -224,25 +229,27 @@ class Simulator:
         dev = self.device
         if self.halo is None:
             stats = dev.step(params, want_stats=want_stats)
-        else:
+        elif self._ext_stream is not None:
+            # GPU ranks: the NCCL all-to-alls are issued with the library's stream current, so
+            # kernels and collectives are ordered on the device -- no host synchronisation
             h = self.halo
+            with self.halo.torch.cuda.stream(self._ext_stream):
+                dev.step_begin(params, h.send.data_ptr())
+                h.exchange_people()
+                dev.step_interact(h.recv.data_ptr(), h.ret_send.data_ptr())
+                h.exchange_infections()
+                stats = dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
+        else:
+            h = self.halo  # CPU engine (tests): host buffers, gloo
             dev.step_begin(params, h.send.data_ptr())
-            dev.sync()  # the exchange runs on torch's stream
             h.exchange_people()
-            self._torch_sync()
             dev.step_interact(h.recv.data_ptr(), h.ret_send.data_ptr())
-            dev.sync()
             h.exchange_infections()
-            self._torch_sync()
             stats = dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
         self.step_ordinal += 1
         if stats is not None:
             self.last_stats = stats
             self.history.append(dict(date=self.timer.date, now=self.timer.now, **stats))
-
-    def _torch_sync(self):
-        if self.halo is not None and self.halo.send.is_cuda:
-            self.halo.torch.cuda.current_stream().synchronize()
 
     def run(self) -> None:
         """``Simulator.run`` (``simulator.py:628-707``)."""
