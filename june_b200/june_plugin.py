@@ -1,0 +1,221 @@
+"""Drop-in for a real JUNE installation: ``make_b200_simulator_class(june.simulator.Simulator)``
+returns a subclass whose ``do_timestep`` runs on the B200 path.
+
+This is the binding a JUNE maintainer adds.  It imports nothing from JUNE
+itself -- the reference class is passed in -- so this package stays importable without JUNE.
+
+What it does
+------------
+* ``__init__`` / ``from_file`` are the reference's own (``june/simulator.py:82-303``): same
+  arguments, same YAML.  On the first step the world object graph is compiled ONCE into the SoA
+  form (``june_b200.adapter.compile_world``) and uploaded.
+* ``do_timestep`` (``simulator.py:346-626``): applies the reference's own interaction / regional
+  policies to get ``beta_reductions`` and compliances (host scalars), builds the per-step beta
+  table with the reference ``Interaction.betas``, and calls ``jb_step``.
+* Infections present on ``Person`` objects (seeding through the reference's ``InfectionSeed``,
+  ``infection_seed.py:209-278``) are uploaded before the step; after the step the people whose
+  state changed get light-weight views written back (``person.infection``, ``person.dead``,
+  immunity), so that seeding, records and checkpoints keep working on the reference's objects.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .adapter import compile_world
+from .device import DeviceWorld, Engine
+from .disease import DiseaseConfig, outcome_probabilities, rates_from_dataframe
+from .interaction import Interaction
+from .world import ACTIVITY_CODES, PS_DEAD, PS_INFECTED
+
+
+class _TransmissionView:
+    __slots__ = ("probability",)
+
+    def __init__(self, probability):
+        self.probability = probability
+
+
+class _SymptomsView:
+    __slots__ = ("tag", "max_tag", "stage", "trajectory", "time_of_symptoms_onset")
+
+    def __init__(self, tag, max_tag, stage, trajectory):
+        self.tag, self.max_tag, self.stage, self.trajectory = tag, max_tag, stage, trajectory
+        self.time_of_symptoms_onset = None
+
+
+def make_b200_simulator_class(reference_simulator_cls):
+    class B200Simulator(reference_simulator_cls):
+        """``Simulator`` with ``do_timestep`` on the B200 path."""
+
+        b200_engine: Optional[Engine] = None
+        b200_device: int = 0
+        b200_seed: int = 0
+
+        # ---- one-off compilation ---------------------------------------------------------------
+        def _b200_setup(self):
+            am = self.activity_manager
+            a2sg = {k: v for k, v in am.activity_to_super_group_dict.items()}
+            sector_betas = {}
+            for g in getattr(getattr(self.world, "companies", None), "members", []) or []:
+                ig = g.get_interactive_group(None)
+                sector_betas = dict(type(ig).sector_betas)
+                break
+            self._soa = compile_world(self.world, a2sg, sector_betas)
+            ref_inter = self.interaction
+            self._inter = Interaction.__new__(Interaction)
+            self._inter.alpha_physical = ref_inter.alpha_physical
+            self._inter.betas = dict(ref_inter.betas)
+            self._inter.contact_matrices = {k: np.asarray(v, np.float64) for k, v in ref_inter.contact_matrices.items()}
+            self._inter.beta_reductions = {}
+            selector = self.epidemiology.infection_selectors[0]
+            self._selector = selector
+            dc_ref = selector.disease_config
+            # the reference pops keys out of its parsed YAML while building CompletionTime objects
+            # (trajectory_maker.py:59-60), so re-read the file it came from
+            self._dc = None
+            paths = sys.modules.get("june.paths")
+            if paths is not None:
+                f = os.path.join(str(paths.configs_path), "defaults", "epidemiology", "infection", "disease",
+                                 f"{dc_ref.disease_name.lower()}.yaml")
+                if os.path.exists(f):
+                    self._dc = DiseaseConfig.from_file(f)
+            if self._dc is None:
+                self._dc = DiseaseConfig(dc_ref.disease_name)
+            hig = selector.health_index_generator
+            rates, bins = rates_from_dataframe(hig.rates_df)
+            prob = outcome_probabilities(self._dc, rates, bins)
+            if self.b200_engine is None:
+                type(self).b200_engine = None
+                self._eng = DeviceWorld(self._soa, self._inter, self._dc, prob, device=self.b200_device)
+            else:
+                self._eng = self.b200_engine(self._soa, self._inter, self._dc, prob)
+            self._people = list(self.world.people)
+            self._known_infected = np.zeros(len(self._people), bool)
+            self._step = 0
+
+        # ---- host -> device: infections created by the reference (seeding) -----------------------
+        def _b200_upload_new_reference_infections(self):
+            rows = []
+            for i, p in enumerate(self._people):
+                inf = p.infection
+                if inf is None or self._known_infected[i] or isinstance(inf, _InfectionView):
+                    continue
+                tr = inf.transmission
+                name = type(tr).__name__
+                if name == "TransmissionGamma":
+                    tpar = [tr.shape, tr.shift, tr.scale, tr.norm, 0.0]
+                elif name == "TransmissionXNExp":
+                    tpar = [tr.n, tr.alpha, tr.time_first_infectious, tr.norm, tr.norm_time]
+                else:
+                    tpar = [tr.probability, 0, 0, 0, 0]
+                traj = inf.symptoms.trajectory
+                rows.append(dict(person=i, start_time=inf.start_time, tpar=tpar, probability=tr.probability,
+                                 traj_time=[t for t, _ in traj], traj_tag=[int(g) for _, g in traj],
+                                 stage=inf.symptoms.stage, max_tag=int(inf.symptoms.max_tag), tag=int(inf.symptoms.tag)))
+                self._known_infected[i] = True
+            if rows:
+                self._eng.upload_infections(rows)
+
+        # ---- device -> host: views on the reference objects ---------------------------------------
+        def _b200_write_back(self):
+            st = self._eng.fetch_person_state()
+            infected = (st["pstate"] & PS_INFECTED) != 0
+            dead = (st["pstate"] & PS_DEAD) != 0
+            changed = np.nonzero((infected != self._known_infected) | dead)[0]
+            iid = self._selector.infection_class.infection_id()
+            for i in changed:
+                p = self._people[i]
+                if dead[i]:
+                    if not p.dead:
+                        p.dead, p.infection = True, None
+                elif infected[i]:
+                    p.infection = _InfectionView(self._selector.infection_class, st["trans_prob"][i], int(st["tag"][i]))
+                    p.immunity.add_immunity(p.infection.immunity_ids())
+                else:
+                    p.infection = None
+                    p.immunity.susceptibility_dict[iid] = float(st["susceptibility"][0][i])
+            self._known_infected = infected & ~dead
+            for i in np.nonzero(self._known_infected)[0]:
+                inf = self._people[i].infection
+                if isinstance(inf, _InfectionView):
+                    inf.transmission.probability = float(st["trans_prob"][i])
+                    inf.symptoms.tag = int(st["tag"][i])
+
+        # ---- the replaced method --------------------------------------------------------------------
+        def do_timestep(self):
+            if not hasattr(self, "_eng"):
+                self._b200_setup()
+            pol = self.activity_manager.policies
+            if pol is not None:
+                pol.interaction_policies.apply(date=self.timer.date, interaction=self.interaction)
+                pol.regional_compliance.apply(date=self.timer.date, regions=self.world.regions)
+            activities = self.timer.activities
+            if not activities:
+                return
+            self._b200_upload_new_reference_infections()
+            self._inter.beta_reductions = dict(self.interaction.beta_reductions)
+            regions = {r.name: r for r in self.world.regions}
+            comp = [regions[n].regional_compliance if n in regions else 1.0 for n in self._soa.region_names]
+            tiers = [regions[n].policy.get("lockdown_tier") if n in regions else None for n in self._soa.region_names]
+            beta = self._inter.beta_table(self._soa.beta_rules, comp, tiers)
+            mask = 0
+            for a in activities:
+                if a in ACTIVITY_CODES:
+                    mask |= 1 << ACTIVITY_CODES[a]
+            flags = 0
+            if pol is not None:
+                date = self.timer.date
+                if any(type(p).__name__ == "SevereSymptomsStayHome" and p.is_active(date) for p in pol.individual_policies.policies):
+                    flags |= _lib.STEP_SEVERE_STAY_HOME
+                if any(type(p).__name__ == "Hospitalisation" and p.is_active(date) for p in pol.medical_care_policies.policies):
+                    flags |= _lib.STEP_HOSPITALISATION
+            params = self._eng.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self._step,
+                                           activity_mask=mask, seed=self.b200_seed, flags=flags, beta=beta)
+            self.b200_last_stats = self._eng.step(params)
+            self._step += 1
+            self._b200_write_back()
+
+        def clear_world(self):
+            """The reference empties every subgroup list after each step (``simulator.py:305-343``).
+            Here membership is a per-step byte on the device, so the lists are emptied once (world
+            builders leave people in them) and never filled again."""
+            if not getattr(self, "_b200_cleared", False):
+                super().clear_world()
+                self._b200_cleared = True
+
+    return B200Simulator
+
+
+class _InfectionView:
+    """What the rest of JUNE reads from ``person.infection`` (``infection.py:13-135``)."""
+
+    __slots__ = ("transmission", "symptoms", "start_time", "_cls")
+
+    def __init__(self, infection_class, probability, tag):
+        self._cls = infection_class
+        self.transmission = _TransmissionView(probability)
+        self.symptoms = _SymptomsView(tag, tag, 0, [])
+        self.start_time = -1
+
+    def infection_id(self):
+        return self._cls.infection_id()
+
+    def immunity_ids(self):
+        return self._cls.immunity_ids()
+
+    @property
+    def tag(self):
+        return self.symptoms.tag
+
+    @property
+    def max_tag(self):
+        return self.symptoms.max_tag
+
+    @property
+    def infection_probability(self):
+        return self.transmission.probability

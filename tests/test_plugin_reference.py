@@ -1,0 +1,50 @@
+"""The drop-in binding on the REAL reference objects (only where /root/reference exists, i.e. in
+the build container; skipped on the GPU box).  The reference's own ``Simulator`` subclass runs its
+``run()`` loop, seeding through the reference ``InfectionSeed``; ``do_timestep`` goes through the C
+ABI (CPU oracle engine here, the CUDA library on a GPU)."""
+import contextlib
+import io
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_harness  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree not present")
+
+
+def test_reference_simulator_subclass_runs_on_the_abi():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_world
+    from june_b200.june_plugin import make_b200_simulator_class
+    from helpers import make_engine
+
+    random.seed(3)
+    np.random.seed(3)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        world, dc = ref_world.build_world(2500, seed=3)
+        ref_sim = ref_world.make_simulator(world, dc, total_days=12, cases_per_capita=0.03)
+    from june.simulator import Simulator
+    B200Simulator = make_b200_simulator_class(Simulator)
+    B200Simulator.b200_engine = staticmethod(lambda soa, inter, dcfg, prob: make_engine("oracle", soa, prob, interaction=inter, disease=dcfg))
+    sim = B200Simulator(world=world, interaction=ref_sim.interaction, timer=ref_sim.timer,
+                        activity_manager=ref_sim.activity_manager, epidemiology=ref_sim.epidemiology,
+                        tracker=None, record=None)
+    with contextlib.redirect_stdout(sink):
+        sim.run()
+    people = list(world.people)
+    n_inf = sum(p.infection is not None for p in people)
+    n_imm = sum(p.immunity.get_susceptibility(sim._selector.infection_class.infection_id()) == 0.0 for p in people)
+    assert sim._step == 54
+    assert n_imm > 75 + 30, "the epidemic must have spread beyond the 3 % seed"
+    assert n_inf > 0
+    st = sim._eng.fetch_person_state()
+    assert n_inf == int(((st["pstate"] & 0x08) != 0).sum())
+    # subgroup lists of the reference objects stay untouched (placement lives on the device)
+    assert all(len(sg.people) == 0 for g in world.companies.members for sg in g.subgroups)
