@@ -276,7 +276,8 @@ def run_gpu(args):
         except Exception:
             pass
 
-    cpu = cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s=args.cpu_seconds) if world_size == 1 else None
+    cpu = (cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s=args.cpu_seconds)
+           if world_size == 1 and args.cpu_seconds > 0 else None)
     h2d = int(world.n_regions * len(world.beta_rules) * 8 + 48)
     d2h = int(16 * 4)
     out = {

@@ -8,27 +8,32 @@
 #include "../../include/june_b200.h"
 
 // ---- device counters (uint32 array `counters`) -------------------------------------------
+// The counter block is laid out as [persistent | per-step | per-region summary | dynamic-bin
+// counts]; everything from CNT_STEP_BEGIN to the end is zeroed by ONE memset at step start.
 enum {
-  CNT_NEWINF = 0,      // new infections appended this step (local + halo)
+  CNT_SLOTS_HW = 0,    // infection slot high-water mark (persistent)
+  CNT_DEAD_TOTAL,      // persistent
+  CNT_STEP_BEGIN,
+  CNT_NEWINF = CNT_STEP_BEGIN,  // new infections appended this step (local + halo)
   CNT_NOACT,           // persons without any activity this step
   CNT_DRAWS,           // Bernoulli draws consumed this step
-  CNT_DYN,             // dynamic members appended this step
+  CNT_DYN,             // (unused)
   CNT_RECOVERED_STEP,
   CNT_DEATHS_STEP,
   CNT_HALO_INF,
   CNT_OVERFLOW,        // a capacity was exceeded
+  CNT_INFECTED,        // currently infected / in hospital / in icu (recomputed by k_health)
+  CNT_HOSP,
+  CNT_ICU,
   CNT_ACT0,            // persons placed per activity (5 words: JB_ACT_MEDICAL..JB_ACT_RESIDENCE)
   CNT_ACT4 = CNT_ACT0 + 4,
   CNT_WORK0,           // per-supergroup work-list lengths (JB_MAX_SUPERGROUPS words)
   CNT_WORK_LAST = CNT_WORK0 + JB_MAX_SUPERGROUPS - 1,
-  CNT_STEP_END,        // ---- everything above is zeroed at the start of every step ----
-  CNT_SLOTS_HW = CNT_STEP_END,  // infection slot high-water mark
-  CNT_DEAD_TOTAL,
-  CNT_INFECTED,        // currently infected / in hospital / in icu: recomputed by k_health,
-  CNT_HOSP,            // zeroed (3 consecutive words) right before it
-  CNT_ICU,
-  CNT_N
+  CNT_N                // followed by summary[R][JB_N_SUMMARY], then dyn_cnt[n_bins]
 };
+
+// per-region summary columns (records_writer.py:151-164)
+enum { SUM_NEW_INFECTED = 0, SUM_CUR_INFECTED, SUM_CUR_HOSP, SUM_CUR_ICU, SUM_DEATHS, SUM_HOSP_DEATHS, SUM_RECOVERED, SUM_ADMISSIONS };
 
 #define JB_TAG_BIT(tag) (1 << ((tag) + 2))
 
@@ -146,7 +151,10 @@ struct JbWorld {
   uint8_t *inf_stage = nullptr, *inf_nst = nullptr, *inf_var = nullptr;
   int8_t *inf_tag = nullptr, *inf_maxtag = nullptr, *traj_tag = nullptr;
   // per step
-  uint32_t* counters = nullptr;
+  uint32_t* counters = nullptr;   // CNT_N words + summary + dyn_cnt (one allocation)
+  uint32_t* summary = nullptr;    // [R][JB_N_SUMMARY], inside the counter block
+  uint8_t* pregion = nullptr;     // region of every resident
+  size_t counter_words = 0;
   uint32_t* newinf_member = nullptr;
   uint8_t* newinf_var = nullptr;
   double* beta = nullptr;

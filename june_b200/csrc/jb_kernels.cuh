@@ -788,6 +788,8 @@ struct NewInfArgs {
   int32_t* inf_person; double* inf_start; double* inf_par; double* inf_next; double* traj_time;
   uint8_t* inf_stage; uint8_t* inf_nst; uint8_t* inf_var; int8_t* inf_tag; int8_t* inf_maxtag; int8_t* traj_tag;
   uint32_t* counters;
+  uint32_t* summary;        // [R][JB_N_SUMMARY]
+  const uint8_t* pregion;
   uint8_t* halo_ret;        // per halo person: variant+1 if infected here (or null)
 };
 
@@ -908,6 +910,7 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
     // immunity.add_immunity(infection.immunity_ids()) (infection_selector.py:160-162)
     for (int v = 0; v < a.V; ++v) a.susc[(size_t)v * a.NP + p] = 0.0;
     a.pstate[p] = (uint8_t)(st | JB_PS_INFECTED);
+    atomicAdd(&a.summary[a.pregion[p] * JB_N_SUMMARY + SUM_NEW_INFECTED], 1u);
   }
 }
 
@@ -928,7 +931,12 @@ struct HealthArgs {
   uint8_t* pstate; int8_t* ptag; double* trans; int32_t* pmed; int32_t* pslot; uint8_t* phas;
   const uint32_t* psa; const int32_t* sa_hospital;
   uint32_t* counters;
+  uint32_t* summary;        // [R][JB_N_SUMMARY]
+  const uint8_t* pregion;
+  int R;
 };
+
+#define JB_SUM_SMEM_REGIONS 64
 
 __device__ __forceinline__ double jb_gamma_pdf(double x, double a, double loc, double scale) {
   // transmission.py:47-75
@@ -938,6 +946,14 @@ __device__ __forceinline__ double jb_gamma_pdf(double x, double a, double loc, d
 }
 
 __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthArgs a) {
+  // per-region counters are accumulated in shared memory and flushed once per block: a global
+  // atomic per infected person on nine addresses serialises in L2
+  __shared__ uint32_t s_sum[JB_SUM_SMEM_REGIONS * JB_N_SUMMARY];
+  const bool sum_smem = a.R <= JB_SUM_SMEM_REGIONS;
+  if (sum_smem) {
+    for (int i = threadIdx.x; i < a.R * JB_N_SUMMARY; i += blockDim.x) s_sum[i] = 0;
+    __syncthreads();
+  }
   const uint32_t hw = min(a.counters[CNT_SLOTS_HW], a.C);
   const DiseaseMasks D = a.masks;
   uint32_t c_inf = 0, c_hosp = 0, c_icu = 0;
@@ -973,6 +989,8 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
     }
     const int bit = JB_TAG_BIT(tag);
     uint32_t st = a.pstate[p];
+    uint32_t* sum = (sum_smem ? s_sum : a.summary) + (size_t)a.pregion[p] * JB_N_SUMMARY;
+    const bool was_med = (st & JB_PS_MEDICAL) != 0;
     // Hospitalisation.apply (medical_care_policies.py:413-526; hospital.py:62-122)
     if (a.sp->flags & JB_STEP_HOSPITALISATION) {
       if (bit & D.hosp_mask) {
@@ -995,6 +1013,7 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
       a.pslot[p] = -1;
       a.trans[p] = 0.0;
       atomicAdd(&a.counters[CNT_RECOVERED_STEP], 1u);
+      atomicAdd(&sum[SUM_RECOVERED], 1u);
     } else if (bit & D.dead_mask) {  // bury_the_dead (epidemiology.py:168-195)
       st &= ~(JB_PS_INFECTED | JB_PS_SEVERE | JB_PS_MEDICAL);
       st |= JB_PS_DEAD;
@@ -1005,9 +1024,17 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
       a.trans[p] = 0.0;
       atomicAdd(&a.counters[CNT_DEATHS_STEP], 1u);
       atomicAdd(&a.counters[CNT_DEAD_TOTAL], 1u);
+      atomicAdd(&sum[SUM_DEATHS], 1u);
+      if (was_med) atomicAdd(&sum[SUM_HOSP_DEATHS], 1u);
     } else {
       ++c_inf;
-      if (st & JB_PS_MEDICAL) { ++c_hosp; if (bit & D.icu_mask) ++c_icu; }
+      atomicAdd(&sum[SUM_CUR_INFECTED], 1u);
+      if (st & JB_PS_MEDICAL) {
+        ++c_hosp;
+        atomicAdd(&sum[SUM_CUR_HOSP], 1u);
+        if (bit & D.icu_mask) { ++c_icu; atomicAdd(&sum[SUM_CUR_ICU], 1u); }
+        if (!was_med) atomicAdd(&sum[SUM_ADMISSIONS], 1u);
+      }
     }
     // ptag mirrors person.infection.tag; -1 ("healthy") once the infection object is gone
     a.ptag[p] = (bit & (D.rec_mask | D.dead_mask)) ? (int8_t)-1 : (int8_t)tag;
@@ -1021,6 +1048,11 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
     if (c_inf) atomicAdd(&a.counters[CNT_INFECTED], c_inf);
     if (c_hosp) atomicAdd(&a.counters[CNT_HOSP], c_hosp);
     if (c_icu) atomicAdd(&a.counters[CNT_ICU], c_icu);
+  }
+  if (sum_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.R * JB_N_SUMMARY; i += blockDim.x)
+      if (s_sum[i]) atomicAdd(&a.summary[i], s_sum[i]);
   }
 }
 

@@ -241,8 +241,19 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_alloc(&w->traj_tag, C * JB_MAX_STAGES));
   CK(cudaMemsetAsync(w->inf_person, 0xFF, C * 4, s));
 
-  TRY(dev_alloc(&w->counters, CNT_N));
-  CK(cudaMemsetAsync(w->counters, 0, CNT_N * 4, s));
+  // counters | per-region summary | dynamic-bin counts: one block, one memset per step
+  for (size_t k = 0; k < w->sgs.size(); ++k)
+    if (w->sgs[k].has_dynamic) { w->sg_bin_base[k] = w->n_bins; w->n_bins += w->sgs[k].n_groups; }
+  w->counter_words = (size_t)CNT_N + (size_t)w->R * JB_N_SUMMARY + w->n_bins;
+  TRY(dev_alloc(&w->counters, w->counter_words));
+  CK(cudaMemsetAsync(w->counters, 0, w->counter_words * 4, s));
+  w->summary = w->counters + CNT_N;
+  w->dyn_cnt = w->summary + (size_t)w->R * JB_N_SUMMARY;
+  {
+    std::vector<uint8_t> reg(std::max(1u, w->N), 0);
+    for (uint32_t p = 0; p < w->N_ext; ++p) reg[lay.ext2int[p]] = (uint8_t)d->sa_region[d->super_area[p]];
+    TRY(dev_upload(&w->pregion, reg.data(), reg.size(), s));
+  }
   TRY(dev_alloc(&w->newinf_member, w->newinf_cap));
   TRY(dev_alloc(&w->newinf_var, w->newinf_cap));
   w->step_bytes = sizeof(StepDev) + sizeof(double) * (size_t)w->n_beta * w->R;
@@ -256,10 +267,9 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     w->bin_cap = JB_DYN_BIN_CAP;
     int n_ranges = 0;
     for (size_t k = 0; k < w->sgs.size(); ++k)
-      if (w->sgs[k].has_dynamic) { w->sg_bin_base[k] = w->n_bins; w->n_bins += w->sgs[k].n_groups; ++n_ranges; }
+      if (w->sgs[k].has_dynamic) ++n_ranges;
     REQUIRE(n_ranges <= 4, "at most 4 supergroups may have dynamic members");
     REQUIRE(w->n_bins <= 65536, "too many groups with dynamic members (bins are per group)");
-    TRY(dev_alloc(&w->dyn_cnt, w->n_bins));
     TRY(dev_alloc(&w->dyn_bin, (size_t)w->n_bins * w->bin_cap));
   }
   {
@@ -272,7 +282,8 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     CK(cudaMallocHost((void**)&w->h_step[i], w->step_bytes));
     CK(cudaEventCreateWithFlags(&w->ev_step_buf[i], cudaEventDisableTiming));
   }
-  CK(cudaMallocHost((void**)&w->h_counters, sizeof(uint32_t) * CNT_N));
+  CK(cudaMallocHost((void**)&w->h_counters, sizeof(uint32_t) * (CNT_N + (size_t)w->R * JB_N_SUMMARY)));
+  memset(w->h_counters, 0, sizeof(uint32_t) * (CNT_N + (size_t)w->R * JB_N_SUMMARY));
   CK(cudaEventCreate(&w->ev_step0));
   CK(cudaEventCreate(&w->ev_step1));
   CK(cudaEventCreate(&w->ev_int0));
@@ -302,7 +313,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->pstate, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->counters, w->newinf_member, w->newinf_var,
-                  w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_cnt, w->dyn_bin,
+                  w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
                   w->cub_tmp, w->int2ext};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -378,6 +389,7 @@ static NewInfArgs make_newinf_args(JbWorld* w) {
   a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
   a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_var = w->inf_var;
   a.inf_tag = w->inf_tag; a.inf_maxtag = w->inf_maxtag; a.traj_tag = w->traj_tag; a.counters = w->counters;
+  a.summary = w->summary; a.pregion = w->pregion;
   return a;
 }
 
@@ -631,8 +643,7 @@ static int harvest_timing(JbWorld* w) {
 static int enqueue_begin(JbWorld* w, void* d_send) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
-  CK(cudaMemsetAsync(w->counters, 0, CNT_STEP_END * 4, s));
-  if (w->any_dynamic) CK(cudaMemsetAsync(w->dyn_cnt, 0, (size_t)w->n_bins * 4, s));
+  CK(cudaMemsetAsync(w->counters + CNT_STEP_BEGIN, 0, (w->counter_words - CNT_STEP_BEGIN) * 4, s));
   if (p.flags & JB_STEP_RECORD_LAMBDA) {
     k_fill_f64<<<(w->NP + 255) / 256, 256, 0, s>>>(w->lambda, w->NP, std::numeric_limits<double>::quiet_NaN());
     w->launches++;
@@ -714,7 +725,6 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
       w->launches++;
     }
   }
-  CK(cudaMemsetAsync(w->counters + CNT_INFECTED, 0, 3 * 4, s));
   {
     HealthArgs a;
     memset(&a, 0, sizeof(a));
@@ -726,11 +736,12 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
     a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
     a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
     a.pslot = w->pslot; a.phas = w->phas; a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.counters = w->counters;
+    a.summary = w->summary; a.pregion = w->pregion; a.R = (int)w->R;
     k_health<<<148 * 4, 256, 0, s>>>(a);
     KCHECK("k_health", s);
     w->launches++;
   }
-  CK(cudaMemcpyAsync(w->h_counters, w->counters, CNT_N * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(w->h_counters, w->counters, (CNT_N + (size_t)w->R * JB_N_SUMMARY) * 4, cudaMemcpyDeviceToHost, s));
   return JB_OK;
 }
 
@@ -1023,8 +1034,10 @@ extern "C" int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap,
 
 extern "C" int jb_fetch_summary(JbWorld* w, uint32_t* counts) {
   if (!w || !counts) { jb_set_error("null argument"); return JB_EINVAL; }
-  jb_set_error("jb_fetch_summary: not implemented in this round");
-  return JB_EINVAL;
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));  // the d2h copy of the last step has landed in h_counters
+  memcpy(counts, w->h_counters + CNT_N, sizeof(uint32_t) * (size_t)w->R * JB_N_SUMMARY);
+  return JB_OK;
 }
 
 // on = 0: run the supergroup kernels one after the other on the main stream (isolated per-kernel

@@ -242,6 +242,16 @@ class Engine:
                             traj_time=list(a.traj_time)[:ns], traj_tag=list(a.traj_tag)[:ns]))
         return out
 
+    SUMMARY_COLUMNS = ("daily_infected", "current_infected", "current_hospitalised", "current_intensive_care",
+                       "daily_deaths", "daily_hospital_deaths", "daily_recovered", "daily_hospitalised")
+
+    def fetch_summary(self) -> np.ndarray:
+        """Per-region counts of the last step, columns ``SUMMARY_COLUMNS`` (the quantities of the
+        reference's ``summary.csv``, ``records_writer.py:151-164``)."""
+        out = np.zeros((self.world.n_regions, 8), np.uint32)
+        self._check(self._f("fetch_summary")(self._h, ptr(out)))
+        return out
+
     def set_concurrency(self, on: bool = True):
         self._check(self._f("set_concurrency")(self._h, 1 if on else 0))
 

@@ -181,6 +181,7 @@ class Simulator:
             import torch
             ptr = self.device._f("stream_handle")(self.device.handle)
             self._ext_stream = torch.cuda.ExternalStream(int(ptr), device=torch.device("cuda", self.device.device_index))
+        self.region_history: List[tuple] = []
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
 
@@ -250,6 +251,8 @@ class Simulator:
         if stats is not None:
             self.last_stats = stats
             self.history.append(dict(date=self.timer.date, now=self.timer.now, **stats))
+            if self.record is not None:
+                self.region_history.append((self.timer.date, dev.fetch_summary()))
 
     def run(self) -> None:
         """``Simulator.run`` (``simulator.py:628-707``)."""
@@ -258,6 +261,30 @@ class Simulator:
                 self.epidemiology.infection_seeds_timestep(self, self.timer)
             self.do_timestep()
             next(self.timer)
+
+    def summary_rows(self) -> List[Dict[str, object]]:
+        """Rows of the reference's ``summary.csv`` (``records_writer.py:151-164,693-790``): one per
+        (day, region); ``daily_*`` columns are summed over the day's steps, ``current_*`` are taken
+        at the day's last step.  Needs ``record`` to be set (any truthy object or a file path)."""
+        cols = self.device.SUMMARY_COLUMNS
+        rows: Dict[tuple, Dict[str, object]] = {}
+        for date, summ in self.region_history:
+            for r, name in enumerate(self.world.region_names):
+                row = rows.setdefault((date.date(), name), dict(time_stamp=date.date(), region=name, **{c: 0 for c in cols}))
+                for k, c in enumerate(cols):
+                    row[c] = int(summ[r, k]) if c.startswith("current") else row[c] + int(summ[r, k])
+        return [rows[k] for k in sorted(rows, key=lambda x: (x[0], self.world.region_names.index(x[1])))]
+
+    def write_summary_csv(self, path: str) -> None:
+        import csv
+        rows = self.summary_rows()
+        header = ["time_stamp", "region", "current_infected", "daily_infected", "current_hospitalised",
+                  "daily_hospitalised", "current_intensive_care", "daily_hospital_deaths", "daily_deaths", "daily_recovered"]
+        with open(path, "w", newline="") as f:
+            wr = csv.DictWriter(f, fieldnames=header)
+            wr.writeheader()
+            for r in rows:
+                wr.writerow({k: r[k] for k in header})
 
     def daily_summary(self) -> List[Dict[str, object]]:
         """Daily curves in the spirit of ``summary.csv`` (``records_writer.py:151-164``), whole domain."""

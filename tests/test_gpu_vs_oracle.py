@@ -97,6 +97,12 @@ def test_philox_mode_full_steps_match_oracle():
                     "n_draws", "n_by_activity"):
             assert sa[key] == sb[key], (i, key, sa[key], sb[key])
         compare_state(a, b, f"step {i}")
+        # per-region summary (records_writer.py:151-164): identical, and consistent with the totals
+        ra, rb = a.fetch_summary(), b.fetch_summary()
+        assert np.array_equal(ra, rb), f"step {i}: per-region summary"
+        assert ra[:, 1].sum() == sa["n_infected"] and ra[:, 2].sum() == sa["n_hospitalised"]
+        assert ra[:, 4].sum() == sa["n_deaths_step"] and ra[:, 6].sum() == sa["n_recovered_step"]
+        assert ra[:, 0].sum() == sa["n_new_infections"] - sa["n_halo_infected"]
         total_new += len(ma)
         now += dt
     assert total_new > 300

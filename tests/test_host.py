@@ -84,3 +84,35 @@ def test_timer_schedule_like_reference():
     assert seen == [(6, 0, 8 / 24, ("primary_activity", "residence"), "weekday"), (6, 1, 16 / 24, ("residence",), "weekday"),
                     (7, 0, 1.0, ("residence",), "weekend"), (8, 0, 1.0, ("residence",), "weekend")]
     assert t.now == 3.0
+
+
+def test_summary_csv_rows(tmp_path):
+    """Per-region daily rows (summary.csv schema) from the per-step device summaries."""
+    from june_b200.interaction import load_defaults
+    from june_b200.simulator import Epidemiology, InfectionSeed, Simulator
+    from june_b200.synth import generate_world
+    from helpers import make_engine
+    w = generate_world(12_000, seed=2)
+    inter = Interaction.from_file()
+    dc = DiseaseConfig("covid19")
+    rates, bins = synthetic_rates()
+    prob = outcome_probabilities(dc, rates, bins)
+    cfg = load_defaults()["simulation"]
+    cfg["time"]["total_days"] = 8
+    eng = make_engine("oracle", w, prob, interaction=inter, disease=dc)
+    epi = Epidemiology(infection_seeds=[InfectionSeed(0.02, cfg["time"]["initial_day"])])
+    sim = Simulator.from_file(w, inter, policies=Policies.from_file(disease_config=dc), epidemiology=epi, engine=eng,
+                              disease_config=dc, outcome_prob=prob, record=True)
+    sim.timer = Timer.from_config(cfg)
+    sim.activity_manager.timer = sim.timer
+    sim.run()
+    rows = sim.summary_rows()
+    assert len(rows) == 8 * len(w.region_names)
+    per_day = {}
+    for r in rows:
+        per_day.setdefault(r["time_stamp"], 0)
+        per_day[r["time_stamp"]] += r["daily_infected"]
+    tot = sum(h["n_new_infections"] for h in sim.history)
+    assert sum(per_day.values()) == tot > 0
+    sim.write_summary_csv(str(tmp_path / "summary.csv"))
+    assert (tmp_path / "summary.csv").read_text().startswith("time_stamp,region,current_infected,daily_infected")
