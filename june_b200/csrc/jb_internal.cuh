@@ -150,6 +150,10 @@ struct JbWorld {
   double *inf_start = nullptr, *inf_par = nullptr, *inf_next = nullptr, *traj_time = nullptr;
   uint8_t *inf_stage = nullptr, *inf_nst = nullptr, *inf_var = nullptr;
   int8_t *inf_tag = nullptr, *inf_maxtag = nullptr, *traj_tag = nullptr;
+  uint8_t *inf_region = nullptr, *inf_sev = nullptr;   // slot-resident mirrors of person facts
+  int32_t *inf_hosp = nullptr, *inf_med = nullptr;
+  std::vector<uint8_t> h_pregion;                       // host copies for jb_upload_infections
+  std::vector<int32_t> h_phosp;
   // per step
   uint32_t* counters = nullptr;   // CNT_N words + summary + dyn_cnt (one allocation)
   uint32_t* summary = nullptr;    // [R][JB_N_SUMMARY], inside the counter block

@@ -45,45 +45,55 @@ struct PlaceArgs {
   const StepDev* sp;
 };
 
-__device__ __forceinline__ uint32_t jb_place_one(const PlaceArgs& a, uint32_t p, uint32_t st, uint32_t has,
-                                                 uint32_t* cnt) {
-  uint32_t act = JB_ACT_NONE;
-  if (!(st & JB_PS_DEAD)) {
-    uint32_t allowed = a.sp->activity_mask;
-    if ((a.sp->flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE))
-      allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
-    if (st & JB_PS_MEDICAL) has |= 1u << JB_ACT_MEDICAL;
-    const uint32_t cand = allowed & has;
-    if (cand) {
-      act = __ffs(cand) - 1;  // hierarchy order == bit order
-      if (act == JB_ACT_MEDICAL) {
-        const uint32_t med = (uint32_t)a.pmed[p];  // (hospital group << 8) | local subgroup
-        const uint32_t g = med >> 8;
-        bool ok = false;
-        for (uint32_t r = 0; r < a.dr.n; ++r) {
-          if (g - a.dr.first[r] < a.dr.count[r]) {
-            const uint32_t bin = a.dr.bin_base[r] + (g - a.dr.first[r]);
-            const uint32_t i = atomicAdd(&a.dyn_cnt[bin], 1u);
-            if (i < a.bin_cap) { a.dyn_bin[(size_t)bin * a.bin_cap + i] = ((med & 0xFu) << 28) | p; ok = true; }
-            break;
-          }
-        }
-        if (!ok) atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
-      }
-      cnt[act]++;
-    } else {
-      cnt[JB_N_ACT]++;
-    }
-  }
-  return (st & ~JB_PS_ACT_MASK) | act;
+// activity chosen for a person byte: pure function of (dead, severe, has-medical, fixed
+// activities) and of the step's activity mask / policy flags -> 512-entry table per block
+__device__ __forceinline__ uint32_t jb_place_key(uint32_t st, uint32_t has) {
+  return (((st >> 3) & 0xFu) << 5) | (has & 0x1Fu);  // bits: INF DEAD SEVERE MED | has[5]
 }
 
 __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
-  __shared__ uint32_t s_cnt[JB_N_ACT + 1];
-  if (threadIdx.x <= JB_N_ACT) s_cnt[threadIdx.x] = 0;
+  __shared__ uint8_t s_act[512];      // 0..4 activity, 7 none (dead), 15 alive without any activity
+  __shared__ uint32_t s_cnt[8];
+  const uint32_t mask = a.sp->activity_mask, flags = a.sp->flags;
+  for (uint32_t k = threadIdx.x; k < 512; k += blockDim.x) {
+    const uint32_t bits = k >> 5, has0 = k & 0x1Fu;
+    const bool dead = bits & 2u, severe = bits & 4u, med = bits & 8u;
+    uint32_t act = JB_ACT_NONE;
+    if (!dead) {
+      uint32_t allowed = mask;
+      if ((flags & JB_STEP_SEVERE_STAY_HOME) && severe) allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
+      const uint32_t cand = allowed & (has0 | (med ? 1u << JB_ACT_MEDICAL : 0u));
+      act = cand ? (uint32_t)__ffs(cand) - 1u : 15u;  // hierarchy order == bit order
+    }
+    s_act[k] = (uint8_t)act;
+  }
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  uint32_t cnt[JB_N_ACT + 1] = {0, 0, 0, 0, 0, 0};
+  // eight 8-bit counters (one per activity code) packed in a 64-bit register
+  unsigned long long cnt = 0ull;
+  uint32_t noact = 0;
   const uint32_t n_chunks = (a.N + 15) / 16;
+  auto one = [&](uint32_t p, uint32_t st, uint32_t has) -> uint32_t {
+    uint32_t act = s_act[jb_place_key(st, has)];
+    if (act == 15u) { ++noact; act = JB_ACT_NONE; }
+    cnt += 1ull << (8 * act);
+    if (act == JB_ACT_MEDICAL) {  // rare: scatter the patient into its ward's bin
+      const uint32_t med = (uint32_t)a.pmed[p];  // (hospital group << 8) | local subgroup
+      const uint32_t g = med >> 8;
+      bool okb = false;
+      for (uint32_t r = 0; r < a.dr.n; ++r) {
+        if (g - a.dr.first[r] < a.dr.count[r]) {
+          const uint32_t bin = a.dr.bin_base[r] + (g - a.dr.first[r]);
+          const uint32_t i = atomicAdd(&a.dyn_cnt[bin], 1u);
+          if (i < a.bin_cap) { a.dyn_bin[(size_t)bin * a.bin_cap + i] = ((med & 0xFu) << 28) | p; okb = true; }
+          break;
+        }
+      }
+      if (!okb) atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+    }
+    return (st & ~JB_PS_ACT_MASK) | act;
+  };
+  uint32_t iters = 0;
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
     const uint32_t p0 = c * 16;
     if (p0 + 16 <= a.N) {
@@ -95,25 +105,29 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
       for (int q = 0; q < 4; ++q) {
         uint32_t o = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t st = (sw[q] >> (8 * b)) & 0xFFu, has = (hw[q] >> (8 * b)) & 0xFFu;
-          o |= jb_place_one(a, p0 + q * 4 + b, st, has, cnt) << (8 * b);
-        }
+        for (int b = 0; b < 4; ++b)
+          o |= one(p0 + q * 4 + b, (sw[q] >> (8 * b)) & 0xFFu, (hw[q] >> (8 * b)) & 0xFFu) << (8 * b);
         sw[q] = o;
       }
       *reinterpret_cast<uint4*>(a.pstate + p0) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
     } else {
-      for (uint32_t p = p0; p < a.N; ++p) a.pstate[p] = (uint8_t)jb_place_one(a, p, a.pstate[p], a.phas[p], cnt);
+      for (uint32_t p = p0; p < a.N; ++p) a.pstate[p] = (uint8_t)one(p, a.pstate[p], a.phas[p]);
+    }
+    if (++iters == 15) {  // 15 * 16 = 240 < 256: flush the packed 8-bit counters
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&s_cnt[k], (uint32_t)((cnt >> (8 * k)) & 0xFFull));
+      cnt = 0ull; iters = 0;
     }
   }
 #pragma unroll
-  for (int k = 0; k <= JB_N_ACT; ++k) {
-    const uint32_t v = __reduce_add_sync(JB_FULL, cnt[k]);
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t v = __reduce_add_sync(JB_FULL, (uint32_t)((cnt >> (8 * k)) & 0xFFull));
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
   }
+  noact = __reduce_add_sync(JB_FULL, noact);
+  if ((threadIdx.x & 31) == 0 && noact) atomicAdd(&a.counters[CNT_NOACT], noact);
   __syncthreads();
   if (threadIdx.x < JB_N_ACT && s_cnt[threadIdx.x]) atomicAdd(&a.counters[CNT_ACT0 + threadIdx.x], s_cnt[threadIdx.x]);
-  if (threadIdx.x == JB_N_ACT && s_cnt[JB_N_ACT]) atomicAdd(&a.counters[CNT_NOACT], s_cnt[JB_N_ACT]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -454,6 +468,9 @@ __global__ void __launch_bounds__(128) k_groups_warp_d1(const __grid_constant__ 
   double T[VM];
 #pragma unroll
   for (int v = 0; v < VM; ++v) T[v] = 0.0;
+  // the first 128 members stay in registers for the draw pass (most groups are that small)
+  uint32_t p0[UB], st0[UB];
+  bool pres0[UB];
   for (uint32_t it0 = 0; it0 < ns; it0 += 32 * UB) {
     uint32_t p[UB], st[UB];
     bool pres[UB];
@@ -468,6 +485,10 @@ __global__ void __launch_bounds__(128) k_groups_warp_d1(const __grid_constant__ 
       const uint32_t info = st[u];
       st[u] = p[u] != 0xFFFFFFFFu ? a.pstate[p[u]] : 0u;
       pres[u] = p[u] != 0xFFFFFFFFu && (st[u] & JB_PS_ACT_MASK) == JB_INFO_ACT(info);
+    }
+    if (it0 == 0) {
+#pragma unroll
+      for (int u = 0; u < UB; ++u) { p0[u] = p[u]; st0[u] = st[u]; pres0[u] = pres[u]; }
     }
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
@@ -502,20 +523,26 @@ __global__ void __launch_bounds__(128) k_groups_warp_d1(const __grid_constant__ 
     row[v] = (v < V && T[v] != 0.0) ? a.cm[0] * T[v] / (double)max(1, (int)n - 1) * beta * a.sp->dt : 0.0;  // interaction.py:469-471
   uint32_t ord = a.inject ? a.draw_base[g] : 0u;
   for (uint32_t it0 = 0; it0 < ns; it0 += 32 * UB) {
-    uint32_t p[UB], st[UB];
+    uint32_t p[UB];
     bool sus[UB];
     double s0[UB];
+    if (it0 == 0) {
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const uint32_t idx = it0 + 32 * u + lane;
-      p[u] = idx < ns ? a.reg_member[b + idx] : 0xFFFFFFFFu;
-      st[u] = idx < ns ? a.reg_info[b + idx] : 0u;
-    }
+      for (int u = 0; u < UB; ++u) { p[u] = p0[u]; sus[u] = pres0[u] && !(st0[u] & JB_PS_INFECTED); }
+    } else {
+      uint32_t st[UB];
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const uint32_t info = st[u];
-      st[u] = p[u] != 0xFFFFFFFFu ? a.pstate[p[u]] : 0u;
-      sus[u] = p[u] != 0xFFFFFFFFu && (st[u] & JB_PS_ACT_MASK) == JB_INFO_ACT(info) && !(st[u] & JB_PS_INFECTED);
+      for (int u = 0; u < UB; ++u) {
+        const uint32_t idx = it0 + 32 * u + lane;
+        p[u] = idx < ns ? a.reg_member[b + idx] : 0xFFFFFFFFu;
+        st[u] = idx < ns ? a.reg_info[b + idx] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const uint32_t info = st[u];
+        st[u] = p[u] != 0xFFFFFFFFu ? a.pstate[p[u]] : 0u;
+        sus[u] = p[u] != 0xFFFFFFFFu && (st[u] & JB_PS_ACT_MASK) == JB_INFO_ACT(info) && !(st[u] & JB_PS_INFECTED);
+      }
     }
 #pragma unroll
     for (int u = 0; u < UB; ++u) s0[u] = sus[u] ? a.susc[p[u]] : 0.0;
@@ -578,10 +605,10 @@ __global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArg
     if (ok) {
       const uint4 i0 = *reinterpret_cast<const uint4*>(a.tp_info + slot0);
       const uint4 i1 = *reinterpret_cast<const uint4*>(a.tp_info + slot0 + 8);
-      uint4 sv = make_uint4(0, 0, 0, 0);
-      uint32_t stg[16];
+      uint32_t sw[4];
       if (STREAM) {
-        sv = *reinterpret_cast<const uint4*>(a.pstate + a.stream_base + slot0);
+        const uint4 sv = *reinterpret_cast<const uint4*>(a.pstate + a.stream_base + slot0);
+        sw[0] = sv.x; sw[1] = sv.y; sw[2] = sv.z; sw[3] = sv.w;
       } else {
         uint32_t mem[16];
 #pragma unroll
@@ -589,19 +616,28 @@ __global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArg
           const uint4 mv = *reinterpret_cast<const uint4*>(a.tp_member + slot0 + 4 * q);
           mem[4 * q] = mv.x; mem[4 * q + 1] = mv.y; mem[4 * q + 2] = mv.z; mem[4 * q + 3] = mv.w;
         }
+        uint32_t stg[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) stg[i] = mem[i] != 0xFFFFFFFFu ? a.pstate[mem[i]] : 0u;
-      }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const uint32_t inf_ = i < 8 ? jb_half(i0, i) : jb_half(i1, i - 8);
-        const uint32_t st = STREAM ? jb_byte(sv, i) : stg[i];
-        const bool v = (inf_ & JB_TI_VALID) != 0;
-        const bool pr = v && (st & JB_PS_ACT_MASK) == JB_INFO_ACT(inf_);
-        valid |= (v ? 1u : 0u) << i;
-        first |= ((v && (inf_ & JB_TI_FIRST)) ? 1u : 0u) << i;
-        pres |= (pr ? 1u : 0u) << i;
-        inf |= ((pr && (st & JB_PS_INFECTED)) ? 1u : 0u) << i;
+        for (int q = 0; q < 4; ++q) sw[q] = stg[4 * q] | (stg[4 * q + 1] << 8) | (stg[4 * q + 2] << 16) | (stg[4 * q + 3] << 24);
+      }
+      // four slots at a time: the high byte of each descriptor holds activity (bits 0-2), VALID
+      // (bit 3) and FIRST (bit 4); one byte-wise compare against the four state bytes
+      const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t hi4 = __byte_perm(iw[2 * q], iw[2 * q + 1], 0x7531);
+        const uint32_t st4 = sw[q];
+        const uint32_t valid4 = (hi4 >> 3) & 0x01010101u;
+        const uint32_t first4 = (hi4 >> 4) & valid4;
+        const uint32_t pres4 = __vcmpeq4(hi4 & 0x07070707u, st4 & 0x07070707u) & valid4;
+        const uint32_t inf4 = (st4 >> 3) & pres4;
+        // bit 0 of every byte -> 4-bit mask
+        valid |= (((valid4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        first |= (((first4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        pres |= (((pres4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        inf |= (((inf4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
       }
     }
     // a tile = two neighbouring chunks: exchange the 16-bit masks inside the lane pair
@@ -666,17 +702,43 @@ __global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArg
 // every lane accumulates the subgroup sizes and transmission sums from shuffle broadcasts in slot
 // order -- the reference's own left-to-right order (Python `sum`, interaction.py:463-467) -- and
 // finally each lane draws for its own member.
+#define JB_DRAW_QUEUE 64  // per-warp queue of pending Bernoulli draws (shared memory)
+
 template <bool STREAM, int VM, int JB_LG>
 __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupArgs a) {
+  // Philox + exp are the expensive part and only ~1 lane in 3 holds a susceptible: the draws are
+  // queued per warp and executed 32 at a time on fully populated warps
+  __shared__ double q_lam[4][VM][JB_DRAW_QUEUE];
+  __shared__ uint32_t q_p[4][JB_DRAW_QUEUE], q_ord[4][JB_DRAW_QUEUE];
   const uint32_t n_work = *a.work_cnt;
   const int V = (VM > 1) ? a.V : 1;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sl = lane & (JB_LG - 1);
   const uint32_t submask = ((1u << JB_LG) - 1u) << (lane & ~(JB_LG - 1));
-  const uint32_t n_sub = gridDim.x * blockDim.x / JB_LG;
-  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / JB_LG; w < n_work; w += n_sub) {
-    const uint2 item = a.work_items[w];
-    const uint32_t slot0 = item.x >> 5, len = (item.x & 31u) + 1u, g = item.y;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  constexpr uint32_t per_warp = 32 / JB_LG;
+  const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+  uint32_t qn = 0;  // warp-uniform queue length
+
+  auto drain = [&](uint32_t n) {
+    if ((uint32_t)lane < n) {
+      double lam_v[VM];
+      double lam = 0.0;
+#pragma unroll
+      for (int v = 0; v < VM; ++v) { lam_v[v] = q_lam[wib][v][lane]; lam += lam_v[v]; }
+      jb_draw_core<VM>(a, q_p[wib][lane], lam_v, lam, q_ord[wib][lane]);
+    }
+    __syncwarp();
+  };
+
+  // all lanes of a warp iterate together (the queue is warp-wide); sub-groups beyond the work
+  // list idle through the iteration
+  const uint32_t warp0 = blockIdx.x * (blockDim.x >> 5) + wib;
+  for (uint32_t wbase = warp0 * per_warp; wbase < n_work; wbase += n_warps * per_warp) {
+    const uint32_t w = wbase + (lane / JB_LG);
+    const bool have_item = w < n_work;
+    const uint2 item = have_item ? a.work_items[w] : make_uint2(0u, 0u);
+    const uint32_t slot0 = item.x >> 5, len = have_item ? (item.x & 31u) + 1u : 0u, g = item.y;
     int n[4] = {0, 0, 0, 0};
     double T[VM][4];
 #pragma unroll
@@ -722,10 +784,15 @@ __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupAr
         }
       }
     }
-    const uint32_t gi = a.grp_info[g];
-    const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
-    uint32_t ord = a.inject ? a.draw_base[g] : 0u;
-    for (uint32_t base = 0; base < len; base += JB_LG) {
+    double beta = 0.0;
+    uint32_t ord = 0;
+    if (have_item) {
+      const uint32_t gi = a.grp_info[g];
+      beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+      ord = a.inject ? a.draw_base[g] : 0u;
+    }
+    const uint32_t max_len = __reduce_max_sync(JB_FULL, len);
+    for (uint32_t base = 0; base < max_len; base += JB_LG) {
       const uint32_t m = base + sl;
       uint32_t pk = pk0, p = p0;
       if (base != 0) {
@@ -737,12 +804,13 @@ __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupAr
           if ((st & JB_PS_ACT_MASK) == JB_INFO_ACT(info)) pk = (JB_INFO_LSG(info) & 3u) | 4u | ((st & JB_PS_INFECTED) ? 8u : 0u);
         }
       }
-      const bool sus = (pk & 12u) == 4u;
-      const uint32_t susm = __ballot_sync(submask, sus) >> (lane & ~(JB_LG - 1));
+      const bool sus = m < len && (pk & 12u) == 4u;
+      const uint32_t susm = __ballot_sync(JB_FULL, sus);
+      const uint32_t sub_sus = (susm >> (lane & ~(JB_LG - 1))) & ((1u << JB_LG) - 1u);
+      double lam_v[VM];
+      double lam = 0.0;
       if (sus) {
         const int i = pk & 3;
-        double lam_v[VM];
-        double lam = 0.0;
 #pragma unroll
         for (int v = 0; v < VM; ++v) {
           double r = 0.0;
@@ -759,12 +827,44 @@ __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupAr
           lam += r;
         }
         if (a.lambda) a.lambda[p] = lam;
-        if (lam != 0.0)  // lambda == 0 can never infect
-          jb_draw_core<VM>(a, p, lam_v, lam, ord + __popc(susm & ((1u << sl) - 1u)));
       }
-      ord += __popc(susm & ((1u << JB_LG) - 1u));
+      // queue the draws that can succeed (lambda == 0 never infects)
+      const bool want = sus && lam != 0.0;
+      const uint32_t wm = __ballot_sync(JB_FULL, want);
+      if (wm) {
+        if (want) {
+          const uint32_t pos = qn + __popc(wm & lane_lt);
+          q_p[wib][pos] = p;
+          q_ord[wib][pos] = ord + __popc(sub_sus & ((1u << sl) - 1u));
+#pragma unroll
+          for (int v = 0; v < VM; ++v) q_lam[wib][v][pos] = lam_v[v];
+        }
+        qn += __popc(wm);
+        __syncwarp();
+        if (qn >= 32) {
+          drain(32);
+          const uint32_t rest = qn - 32;
+          uint32_t mp = 0, mo = 0;
+          double ml[VM];
+          if ((uint32_t)lane < rest) {
+            mp = q_p[wib][32 + lane]; mo = q_ord[wib][32 + lane];
+#pragma unroll
+            for (int v = 0; v < VM; ++v) ml[v] = q_lam[wib][v][32 + lane];
+          }
+          __syncwarp();
+          if ((uint32_t)lane < rest) {
+            q_p[wib][lane] = mp; q_ord[wib][lane] = mo;
+#pragma unroll
+            for (int v = 0; v < VM; ++v) q_lam[wib][v][lane] = ml[v];
+          }
+          __syncwarp();
+          qn = rest;
+        }
+      }
+      ord += __popc(sub_sus);
     }
   }
+  if (qn) drain(qn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -787,6 +887,8 @@ struct NewInfArgs {
   uint8_t* pstate; uint8_t* pvar; int8_t* ptag; double* susc; double* trans; int32_t* pslot;
   int32_t* inf_person; double* inf_start; double* inf_par; double* inf_next; double* traj_time;
   uint8_t* inf_stage; uint8_t* inf_nst; uint8_t* inf_var; int8_t* inf_tag; int8_t* inf_maxtag; int8_t* traj_tag;
+  uint8_t* inf_region; int32_t* inf_hosp; int32_t* inf_med; uint8_t* inf_sev;  // slot-resident person facts
+  const uint32_t* psa; const int32_t* sa_hospital; const int32_t* pmed;
   uint32_t* counters;
   uint32_t* summary;        // [R][JB_N_SUMMARY]
   const uint8_t* pregion;
@@ -903,6 +1005,10 @@ __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfAr
     a.inf_var[slot] = (uint8_t)var;
     a.inf_tag[slot] = (int8_t)D.tag_exposed;
     a.inf_maxtag[slot] = (int8_t)idx;
+    a.inf_region[slot] = a.pregion[p];
+    a.inf_hosp[slot] = a.sa_hospital[a.psa[p]];
+    a.inf_med[slot] = a.pmed[p];
+    a.inf_sev[slot] = 0;
     a.pslot[p] = (int32_t)slot;
     a.pvar[p] = (uint8_t)var;
     a.ptag[p] = (int8_t)D.tag_exposed;
@@ -928,11 +1034,10 @@ struct HealthArgs {
   const DiseaseDev* dis;
   int32_t* inf_person; const double* inf_start; const double* inf_par; double* inf_next; const double* traj_time;
   uint8_t* inf_stage; const uint8_t* inf_nst; int8_t* inf_tag; const int8_t* traj_tag;
+  const uint8_t* inf_region; const int32_t* inf_hosp; int32_t* inf_med; uint8_t* inf_sev;
   uint8_t* pstate; int8_t* ptag; double* trans; int32_t* pmed; int32_t* pslot; uint8_t* phas;
-  const uint32_t* psa; const int32_t* sa_hospital;
   uint32_t* counters;
   uint32_t* summary;        // [R][JB_N_SUMMARY]
-  const uint8_t* pregion;
   int R;
 };
 
@@ -945,6 +1050,10 @@ __device__ __forceinline__ double jb_gamma_pdf(double x, double a, double loc, d
   return 1.0 / tgamma(a) * pow(z, a - 1.0) * exp(-z) / scale;
 }
 
+// One thread per infection slot.  Everything the update needs about the PERSON (region, closest
+// hospital, ward, severe flag) is mirrored in the slot, so the only per-step access indexed by
+// person is the write of the new transmission probability; the person's state byte, ward and
+// tag are touched only when they change.
 __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthArgs a) {
   // per-region counters are accumulated in shared memory and flushed once per block: a global
   // atomic per infected person on nine addresses serialises in L2
@@ -956,22 +1065,22 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
   }
   const uint32_t hw = min(a.counters[CNT_SLOTS_HW], a.C);
   const DiseaseMasks D = a.masks;
+  const double t_now = a.sp->t_now;
+  const uint32_t flags = a.sp->flags;
   uint32_t c_inf = 0, c_hosp = 0, c_icu = 0;
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < hw; s += gridDim.x * blockDim.x) {
     const int32_t p = a.inf_person[s];
     if (p < 0) continue;
-    const double t = a.sp->t_now - a.inf_start[s];
+    const double t = t_now - a.inf_start[s];
     // transmission.update_infection_probability (infection.py:91)
-    double prob;
     if (D.trans_type == JB_TRANS_GAMMA) {
-      prob = a.inf_par[(size_t)3 * a.C + s] *
-             jb_gamma_pdf(t, a.inf_par[s], a.inf_par[(size_t)1 * a.C + s], a.inf_par[(size_t)2 * a.C + s]);
-      a.trans[p] = prob;
+      a.trans[p] = a.inf_par[(size_t)3 * a.C + s] *
+                   jb_gamma_pdf(t, a.inf_par[s], a.inf_par[(size_t)1 * a.C + s], a.inf_par[(size_t)2 * a.C + s]);
     } else if (D.trans_type == JB_TRANS_XNEXP) {
-      double tfi = a.inf_par[(size_t)2 * a.C + s];
-      prob = 0.0;
+      const double tfi = a.inf_par[(size_t)2 * a.C + s];
+      double prob = 0.0;
       if (t > tfi) {
-        double tau = (t - tfi) / a.inf_par[(size_t)4 * a.C + s];
+        const double tau = (t - tfi) / a.inf_par[(size_t)4 * a.C + s];
         prob = a.inf_par[(size_t)3 * a.C + s] * (pow(tau, a.inf_par[s]) * exp(-tau / a.inf_par[(size_t)1 * a.C + s]));
       }
       a.trans[p] = prob;
@@ -980,48 +1089,59 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
     int stage = a.inf_stage[s];
     int tag = a.inf_tag[s];
     const int nst = a.inf_nst[s];
+    bool changed = false;
     if (stage + 1 < nst && t > a.inf_next[s]) {
       ++stage;
       tag = a.traj_tag[(size_t)stage * a.C + s];
       a.inf_stage[s] = (uint8_t)stage;
       a.inf_tag[s] = (int8_t)tag;
       a.inf_next[s] = (stage + 1 < JB_MAX_STAGES) ? a.traj_time[(size_t)(stage + 1) * a.C + s] : 1e300;
+      changed = true;
     }
     const int bit = JB_TAG_BIT(tag);
-    uint32_t st = a.pstate[p];
-    uint32_t* sum = (sum_smem ? s_sum : a.summary) + (size_t)a.pregion[p] * JB_N_SUMMARY;
-    const bool was_med = (st & JB_PS_MEDICAL) != 0;
+    uint32_t* sum = (sum_smem ? s_sum : a.summary) + (size_t)a.inf_region[s] * JB_N_SUMMARY;
     // Hospitalisation.apply (medical_care_policies.py:413-526; hospital.py:62-122)
-    if (a.sp->flags & JB_STEP_HOSPITALISATION) {
+    const int32_t med_old = a.inf_med[s];
+    const bool was_med = med_old >= 0;
+    int32_t med_new = med_old;
+    if (flags & JB_STEP_HOSPITALISATION) {
       if (bit & D.hosp_mask) {
-        int32_t hg;
-        if (st & JB_PS_MEDICAL) hg = a.pmed[p] >> 8; else hg = a.sa_hospital[a.psa[p]];
-        if (hg >= 0) {
-          int lsg = (bit & D.icu_mask) ? 2 : 1;
-          a.pmed[p] = (hg << 8) | lsg;
-          st |= JB_PS_MEDICAL;
-        }
-      } else if ((st & JB_PS_MEDICAL) && !(bit & D.dead_mask)) {
-        a.pmed[p] = -1;
-        st &= ~JB_PS_MEDICAL;
+        const int32_t hg = was_med ? (med_old >> 8) : a.inf_hosp[s];
+        if (hg >= 0) med_new = (hg << 8) | ((bit & D.icu_mask) ? 2 : 1);
+      } else if (was_med && !(bit & D.dead_mask)) {
+        med_new = -1;
       }
     }
-    if (bit & D.severe_mask) st |= JB_PS_SEVERE; else st &= ~JB_PS_SEVERE;
-    if (bit & D.rec_mask) {  // Epidemiology.recover (epidemiology.py:197-215)
-      st &= ~(JB_PS_INFECTED | JB_PS_SEVERE);
-      a.inf_person[s] = -1;
-      a.pslot[p] = -1;
-      a.trans[p] = 0.0;
+    const uint32_t sev_new = (bit & D.severe_mask) ? 1u : 0u;
+    const bool rec = (bit & D.rec_mask) != 0, dead = !rec && (bit & D.dead_mask) != 0;
+    if (rec || dead || changed || med_new != med_old || sev_new != a.inf_sev[s]) {
+      uint32_t st = a.pstate[p];
+      st = (med_new >= 0) ? (st | JB_PS_MEDICAL) : (st & ~JB_PS_MEDICAL);
+      st = sev_new ? (st | JB_PS_SEVERE) : (st & ~JB_PS_SEVERE);
+      if (med_new != med_old) { a.pmed[p] = med_new; a.inf_med[s] = med_new; }
+      a.inf_sev[s] = (uint8_t)sev_new;
+      if (rec) {  // Epidemiology.recover (epidemiology.py:197-215)
+        st &= ~(JB_PS_INFECTED | JB_PS_SEVERE);
+        a.inf_person[s] = -1;
+        a.pslot[p] = -1;
+        a.trans[p] = 0.0;
+      } else if (dead) {  // bury_the_dead (epidemiology.py:168-195)
+        st &= ~(JB_PS_INFECTED | JB_PS_SEVERE | JB_PS_MEDICAL);
+        st |= JB_PS_DEAD;
+        a.inf_person[s] = -1;
+        a.pslot[p] = -1;
+        a.pmed[p] = -1;
+        a.phas[p] = 0;
+        a.trans[p] = 0.0;
+      }
+      // ptag mirrors person.infection.tag; -1 ("healthy") once the infection object is gone
+      a.ptag[p] = (rec || dead) ? (int8_t)-1 : (int8_t)tag;
+      a.pstate[p] = (uint8_t)st;
+    }
+    if (rec) {
       atomicAdd(&a.counters[CNT_RECOVERED_STEP], 1u);
       atomicAdd(&sum[SUM_RECOVERED], 1u);
-    } else if (bit & D.dead_mask) {  // bury_the_dead (epidemiology.py:168-195)
-      st &= ~(JB_PS_INFECTED | JB_PS_SEVERE | JB_PS_MEDICAL);
-      st |= JB_PS_DEAD;
-      a.inf_person[s] = -1;
-      a.pslot[p] = -1;
-      a.pmed[p] = -1;
-      a.phas[p] = 0;
-      a.trans[p] = 0.0;
+    } else if (dead) {
       atomicAdd(&a.counters[CNT_DEATHS_STEP], 1u);
       atomicAdd(&a.counters[CNT_DEAD_TOTAL], 1u);
       atomicAdd(&sum[SUM_DEATHS], 1u);
@@ -1029,16 +1149,13 @@ __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthAr
     } else {
       ++c_inf;
       atomicAdd(&sum[SUM_CUR_INFECTED], 1u);
-      if (st & JB_PS_MEDICAL) {
+      if (med_new >= 0) {
         ++c_hosp;
         atomicAdd(&sum[SUM_CUR_HOSP], 1u);
         if (bit & D.icu_mask) { ++c_icu; atomicAdd(&sum[SUM_CUR_ICU], 1u); }
         if (!was_med) atomicAdd(&sum[SUM_ADMISSIONS], 1u);
       }
     }
-    // ptag mirrors person.infection.tag; -1 ("healthy") once the infection object is gone
-    a.ptag[p] = (bit & (D.rec_mask | D.dead_mask)) ? (int8_t)-1 : (int8_t)tag;
-    a.pstate[p] = (uint8_t)st;
   }
   // block-level reduction of the "current" counters
   c_inf = __reduce_add_sync(JB_FULL, c_inf);

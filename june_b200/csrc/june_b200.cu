@@ -115,7 +115,7 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   REQUIRE(d->n_variants >= 1 && d->n_variants <= JB_MAX_VARIANTS, "n_variants out of range");
   REQUIRE(d->n_supergroups >= 1 && d->n_supergroups <= JB_MAX_SUPERGROUPS, "n_supergroups out of range");
   REQUIRE(d->n_people + (uint64_t)d->n_halo < (1ull << 28), "n_people + n_halo must be < 2^28");
-  REQUIRE(d->n_groups < (1u << 23), "n_groups must be < 2^23 per domain");
+  REQUIRE(d->n_groups < (1u << 27), "n_groups must be < 2^27 per domain");
   REQUIRE(d->disease.n_tags >= 1 && d->disease.n_tags <= 16 && d->disease.n_traj >= 1 && d->disease.n_traj <= 16,
           "disease table sizes out of range");
   CK(cudaSetDevice(device));
@@ -239,6 +239,10 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_alloc(&w->inf_tag, C));
   TRY(dev_alloc(&w->inf_maxtag, C));
   TRY(dev_alloc(&w->traj_tag, C * JB_MAX_STAGES));
+  TRY(dev_alloc(&w->inf_region, C));
+  TRY(dev_alloc(&w->inf_sev, C));
+  TRY(dev_alloc(&w->inf_hosp, C));
+  TRY(dev_alloc(&w->inf_med, C));
   CK(cudaMemsetAsync(w->inf_person, 0xFF, C * 4, s));
 
   // counters | per-region summary | dynamic-bin counts: one block, one memset per step
@@ -253,6 +257,9 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     std::vector<uint8_t> reg(std::max(1u, w->N), 0);
     for (uint32_t p = 0; p < w->N_ext; ++p) reg[lay.ext2int[p]] = (uint8_t)d->sa_region[d->super_area[p]];
     TRY(dev_upload(&w->pregion, reg.data(), reg.size(), s));
+    w->h_pregion = reg;
+    w->h_phosp.assign(std::max(1u, w->N), -1);
+    for (uint32_t p = 0; p < w->N_ext; ++p) w->h_phosp[lay.ext2int[p]] = d->sa_hospital[d->super_area[p]];
   }
   TRY(dev_alloc(&w->newinf_member, w->newinf_cap));
   TRY(dev_alloc(&w->newinf_var, w->newinf_cap));
@@ -312,7 +319,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->reg_member, w->reg_info, w->sa_region, w->sa_hospital, w->cm, w->beta_scale, w->hi_cum, w->dis,
                   w->pstate, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
-                  w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->counters, w->newinf_member, w->newinf_var,
+                  w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
                   w->cub_tmp, w->int2ext};
   for (void* p : ptrs)
@@ -390,6 +397,8 @@ static NewInfArgs make_newinf_args(JbWorld* w) {
   a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_var = w->inf_var;
   a.inf_tag = w->inf_tag; a.inf_maxtag = w->inf_maxtag; a.traj_tag = w->traj_tag; a.counters = w->counters;
   a.summary = w->summary; a.pregion = w->pregion;
+  a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
+  a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.pmed = w->pmed;
   return a;
 }
 
@@ -463,6 +472,20 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
   CK(cudaMemcpy(w->inf_var + hw, var.data(), n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(w->inf_tag + hw, tag.data(), n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(w->inf_maxtag + hw, maxtag.data(), n, cudaMemcpyHostToDevice));
+  {
+    std::vector<uint8_t> reg(n), sev(n);
+    std::vector<int32_t> hosp(n), med(n);
+    for (size_t i = 0; i < n; ++i) {
+      const uint32_t pi = (uint32_t)person[i];
+      reg[i] = w->h_pregion[pi]; hosp[i] = w->h_phosp[pi];
+      sev[i] = (JB_TAG_BIT(rows[i].tag) & w->dis_host.severe_mask) ? 1 : 0;
+      CK(cudaMemcpy(&med[i], w->pmed + pi, 4, cudaMemcpyDeviceToHost));
+    }
+    CK(cudaMemcpy(w->inf_region + hw, reg.data(), n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->inf_sev + hw, sev.data(), n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->inf_hosp + hw, hosp.data(), n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->inf_med + hw, med.data(), n * 4, cudaMemcpyHostToDevice));
+  }
   for (int q = 0; q < JB_N_TPAR; ++q)
     CK(cudaMemcpy(w->inf_par + (size_t)q * C + hw, par.data() + (size_t)q * n, n * 8, cudaMemcpyHostToDevice));
   for (int q = 0; q < JB_MAX_STAGES; ++q) {
@@ -569,8 +592,8 @@ static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
   KCHECK(STREAM ? "k_detect<stream>" : "k_detect<gather>", st);
   if (a.mode == 0) {
     // households are small: 4 lanes per group; gathered groups (companies, care homes): 8
-    if (STREAM) k_process<STREAM, VM, 4><<<148 * 8, 128, 0, st>>>(a);
-    else k_process<STREAM, VM, 8><<<148 * 8, 128, 0, st>>>(a);
+    if (STREAM) k_process<STREAM, VM, 4><<<148 * 12, 128, 0, st>>>(a);
+    else k_process<STREAM, VM, 8><<<148 * 12, 128, 0, st>>>(a);
     KCHECK(STREAM ? "k_process<stream>" : "k_process<gather>", st);
   }
   return JB_OK;
@@ -735,8 +758,9 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
     a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
     a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
     a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
-    a.pslot = w->pslot; a.phas = w->phas; a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.counters = w->counters;
-    a.summary = w->summary; a.pregion = w->pregion; a.R = (int)w->R;
+    a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
+    a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
+    a.summary = w->summary; a.R = (int)w->R;
     k_health<<<148 * 4, 256, 0, s>>>(a);
     KCHECK("k_health", s);
     w->launches++;

@@ -81,7 +81,7 @@ def partition(world: WorldSoA, n_domains: int) -> List[WorldSoA]:
         if (~local).any():
             new_member[~local] = np.array([halo_idx[int(p)] for p in mp[~local]], np.int64)
         info = world.reg_info[sel]
-        key = (g_new[mg] << 40) | ((info & 0xFF).astype(np.int64) << 32) | new_member
+        key = (g_new[mg] << 36) | ((info & 0xFF).astype(np.int64) << 28) | new_member
         order = np.argsort(key, kind="stable")
         counts = np.bincount(g_new[mg], minlength=len(groups))
         off = np.zeros(len(groups) + 1, np.uint32)

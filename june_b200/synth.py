@@ -56,7 +56,7 @@ class DomainDraft:
 
 
 def _csr_from_rows(group: np.ndarray, lsg: np.ndarray, member: np.ndarray, act: np.ndarray, n_groups: int):
-    key = (group.astype(np.int64) << 40) | (lsg.astype(np.int64) << 32) | member.astype(np.int64)
+    key = (group.astype(np.int64) << 36) | (lsg.astype(np.int64) << 28) | member.astype(np.int64)
     order = np.argsort(key, kind="stable")
     group, lsg, member, act = group[order], lsg[order], member[order], act[order]
     counts = np.bincount(group, minlength=n_groups)

@@ -182,7 +182,7 @@ class WorldSoA:
         # members sorted by (lsg, person) inside each group
         if m:
             grp_of = np.repeat(np.arange(g, dtype=np.int64), np.diff(self.grp_offset.astype(np.int64)))
-            key = (grp_of << 40) | ((self.reg_info & 0xFF).astype(np.int64) << 32) | self.reg_member.astype(np.int64)
+            key = (grp_of << 36) | ((self.reg_info & 0xFF).astype(np.int64) << 28) | self.reg_member.astype(np.int64)
             assert np.all(np.diff(key) > 0), "registered members must be sorted by (group, subgroup, person)"
 
     # ---- persistence (small fixtures under tests/golden/) ------------------------------------
