@@ -27,8 +27,8 @@ enum {
   CNT_ICU,
   CNT_ACT0,            // persons placed per activity (5 words: JB_ACT_MEDICAL..JB_ACT_RESIDENCE)
   CNT_ACT4 = CNT_ACT0 + 4,
-  CNT_WORK0,           // per-supergroup work-list lengths (JB_MAX_SUPERGROUPS words)
-  CNT_WORK_LAST = CNT_WORK0 + JB_MAX_SUPERGROUPS - 1,
+  CNT_WORK0,           // per-supergroup work-list lengths: JB_MAX_SUPERGROUPS x JB_WORK_SUBLISTS words
+  CNT_WORK_LAST = CNT_WORK0 + JB_MAX_SUPERGROUPS * 32 - 1,
   CNT_N                // followed by summary[R][JB_N_SUMMARY], then dyn_cnt[n_bins]
 };
 
@@ -36,6 +36,7 @@ enum {
 enum { SUM_NEW_INFECTED = 0, SUM_CUR_INFECTED, SUM_CUR_HOSP, SUM_CUR_ICU, SUM_DEATHS, SUM_HOSP_DEATHS, SUM_RECOVERED, SUM_ADMISSIONS };
 
 #define JB_TAG_BIT(tag) (1 << ((tag) + 2))
+#define JB_WORK_SUBLISTS 32
 
 // Per-step scalars, resident on the device so that a captured CUDA graph of the step can be
 // replayed: one h2d copy from a pinned ring buffer precedes every step.  The processed beta
@@ -73,8 +74,10 @@ struct GroupArgs {
   const uint32_t* tp_member;
   const uint16_t* tp_info;
   uint32_t n_tiles, stream_base;
-  uint2* work_items;          // groups that must timestep, found by k_detect
-  uint32_t* work_cnt;
+  uint2* work_items;          // groups that must timestep, found by k_detect: JB_WORK_SUBLISTS
+  uint32_t* work_cnt;         // sub-lists (one per blockIdx & 31) so that the append counters do
+  uint32_t sub_off[JB_WORK_SUBLISTS + 1];  // not serialise on one L2 address; exact capacities
+  uint32_t detect_blocks;
   int dim, kind, L;
   uint32_t N, NP;
   int V, R;
@@ -110,6 +113,8 @@ struct SgTiles {
   uint16_t* tp_info = nullptr;
   uint32_t* big_list = nullptr;  // groups too large for a tile -> warp kernel
   uint2* work_items = nullptr;   // capacity = number of groups of the supergroup
+  uint32_t sub_off[JB_WORK_SUBLISTS + 1] = {};  // region of every sub-list inside work_items
+  uint32_t detect_blocks = 0;    // grid of k_detect (fixes which block sees which tile)
 };
 
 struct JbWorld {

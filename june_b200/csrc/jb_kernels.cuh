@@ -593,6 +593,8 @@ __device__ __forceinline__ uint32_t jb_half(const uint4& v, int i) {
 template <bool STREAM>
 __global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArgs a) {
   const int lane = threadIdx.x & 31;
+  uint32_t* const my_cnt = a.work_cnt + (blockIdx.x & (JB_WORK_SUBLISTS - 1));
+  uint2* const my_items = a.work_items + a.sub_off[blockIdx.x & (JB_WORK_SUBLISTS - 1)];
   const uint32_t n_chunks = a.n_tiles * 2;
   const uint32_t n_threads = gridDim.x * blockDim.x;
   const uint32_t n_iter = (n_chunks + n_threads - 1) / n_threads;
@@ -671,8 +673,8 @@ __global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArg
         const uint32_t item = ((t * 32 + start) << 5) | (len - 1);
         if (n_items < 4) { items[n_items] = item; item_g[n_items] = g; ++n_items; }
         else {  // rare: more than 4 groups with infectors in one tile
-          const uint32_t pos = atomicAdd(a.work_cnt, 1u);
-          a.work_items[pos] = make_uint2(item, g);
+          const uint32_t pos = atomicAdd(my_cnt, 1u);
+          my_items[pos] = make_uint2(item, g);
           ++n_extra;
         }
       }
@@ -688,9 +690,9 @@ __global__ void __launch_bounds__(256) k_detect(const __grid_constant__ GroupArg
     const uint32_t total = __shfl_sync(JB_FULL, incl, 31);
     if (total) {
       uint32_t base = 0;
-      if (lane == 31) base = atomicAdd(a.work_cnt, total);
+      if (lane == 31) base = atomicAdd(my_cnt, total);
       base = __shfl_sync(JB_FULL, base, 31) + incl - n_items;
-      for (uint32_t q = 0; q < n_items; ++q) a.work_items[base + q] = make_uint2(items[q], item_g[q]);
+      for (uint32_t q = 0; q < n_items; ++q) my_items[base + q] = make_uint2(items[q], item_g[q]);
     }
   }
   draws = __reduce_add_sync(JB_FULL, draws);
@@ -710,9 +712,19 @@ __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupAr
   // queued per warp and executed 32 at a time on fully populated warps
   __shared__ double q_lam[4][VM][JB_DRAW_QUEUE];
   __shared__ uint32_t q_p[4][JB_DRAW_QUEUE], q_ord[4][JB_DRAW_QUEUE];
-  const uint32_t n_work = *a.work_cnt;
-  const int V = (VM > 1) ? a.V : 1;
+  // lane j holds the length of sub-list j; exclusive prefix -> flat work index space
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t my_len = a.work_cnt[lane];
+  uint32_t my_pre = my_len;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t up = __shfl_up_sync(JB_FULL, my_pre, off);
+    if (lane >= off) my_pre += up;
+  }
+  const uint32_t n_work = __shfl_sync(JB_FULL, my_pre, 31);
+  my_pre -= my_len;  // exclusive
+  const uint32_t my_region = a.sub_off[lane];
+  const int V = (VM > 1) ? a.V : 1;
   const int sl = lane & (JB_LG - 1);
   const uint32_t submask = ((1u << JB_LG) - 1u) << (lane & ~(JB_LG - 1));
   const uint32_t lane_lt = (1u << lane) - 1u;
@@ -737,7 +749,20 @@ __global__ void __launch_bounds__(128) k_process(const __grid_constant__ GroupAr
   for (uint32_t wbase = warp0 * per_warp; wbase < n_work; wbase += n_warps * per_warp) {
     const uint32_t w = wbase + (lane / JB_LG);
     const bool have_item = w < n_work;
-    const uint2 item = have_item ? a.work_items[w] : make_uint2(0u, 0u);
+    // sub-list of flat index w: the largest j whose exclusive prefix is <= w (binary search over
+    // the prefix held one entry per lane)
+    uint2 item = make_uint2(0u, 0u);
+    {
+      uint32_t j = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t cand = j + step;
+        const uint32_t pre_c = __shfl_sync(JB_FULL, my_pre, cand & 31);
+        if (cand < JB_WORK_SUBLISTS && pre_c <= w) j = cand;
+      }
+      const uint32_t pre_j = __shfl_sync(JB_FULL, my_pre, j), reg_j = __shfl_sync(JB_FULL, my_region, j);
+      if (have_item) item = a.work_items[reg_j + (w - pre_j)];
+    }
     const uint32_t slot0 = item.x >> 5, len = have_item ? (item.x & 31u) + 1u : 0u, g = item.y;
     int n[4] = {0, 0, 0, 0};
     double T[VM][4];

@@ -182,6 +182,23 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     if (T.mode == 1) TRY(dev_upload(&D.tp_member, T.tp_member.data(), T.tp_member.size(), s));
     if (D.n_big) TRY(dev_upload(&D.big_list, T.big.data(), T.big.size(), s));
     TRY(dev_alloc(&D.work_items, (size_t)w->sgs[k].n_groups + 1));
+    {
+      // k_detect runs a fixed grid-stride schedule, so the set of tiles (hence groups) a block
+      // can ever report is known: exact capacity of each of the JB_WORK_SUBLISTS sub-lists
+      const uint32_t chunks = D.n_tiles * 2;
+      D.detect_blocks = std::max<uint32_t>(1u, std::min<uint32_t>((chunks + 255) / 256, 148 * 8));
+      const uint64_t n_threads = (uint64_t)D.detect_blocks * 256;
+      std::vector<uint32_t> cap(JB_WORK_SUBLISTS, 0);
+      for (uint32_t t = 0; t < D.n_tiles; ++t) {
+        uint32_t groups = 0;
+        for (int i = 0; i < 32; ++i) groups += (T.tp_info[(size_t)t * 32 + i] & JB_TI_FIRST_H) ? 1u : 0u;
+        const uint32_t block = (uint32_t)(((uint64_t)(2 * t) % n_threads) / 256);
+        cap[block & (JB_WORK_SUBLISTS - 1)] += groups;
+      }
+      D.sub_off[0] = 0;
+      for (int j = 0; j < JB_WORK_SUBLISTS; ++j) D.sub_off[j + 1] = D.sub_off[j] + cap[j];
+      REQUIRE(D.sub_off[JB_WORK_SUBLISTS] <= w->sgs[k].n_groups, "internal: work-list capacity");
+    }
   }
   TRY(dev_upload(&w->age, lay.age.data(), w->N, s));
   TRY(dev_upload(&w->sex, lay.sex.data(), w->N, s));
@@ -586,9 +603,7 @@ static int launch_warp(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_
 
 template <bool STREAM, int VM>
 static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
-  const unsigned chunks = a.n_tiles * 2;
-  unsigned blocks = std::min<unsigned>((chunks + 255) / 256, 148 * 8);
-  k_detect<STREAM><<<blocks, 256, 0, st>>>(a);
+  k_detect<STREAM><<<a.detect_blocks, 256, 0, st>>>(a);
   KCHECK(STREAM ? "k_detect<stream>" : "k_detect<gather>", st);
   if (a.mode == 0) {
     // households are small: 4 lanes per group; gathered groups (companies, care homes): 8
@@ -620,7 +635,8 @@ static int launch_groups(JbWorld* w, int mode) {
     } else {
       a.tile_group0 = T.tile_group0; a.tp_member = T.tp_member; a.tp_info = T.tp_info;
       a.n_tiles = T.n_tiles; a.stream_base = T.stream_base;
-      a.work_items = T.work_items; a.work_cnt = w->counters + CNT_WORK0 + k;
+      a.work_items = T.work_items; a.work_cnt = w->counters + CNT_WORK0 + k * JB_WORK_SUBLISTS;
+      memcpy(a.sub_off, T.sub_off, sizeof(a.sub_off)); a.detect_blocks = T.detect_blocks;
       if (T.n_tiles) {
         if (T.mode == 2) { if (w->V == 1) TRY((launch_tiles<true, 1>(w, a, st))); else TRY((launch_tiles<true, JB_MAX_VARIANTS>(w, a, st))); }
         else { if (w->V == 1) TRY((launch_tiles<false, 1>(w, a, st))); else TRY((launch_tiles<false, JB_MAX_VARIANTS>(w, a, st))); }
