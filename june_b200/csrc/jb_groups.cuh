@@ -1,0 +1,624 @@
+// Interaction kernels (Interaction.time_step_for_group, interaction.py:516-641, with
+// InteractiveGroup.__init__, interactive.py:37-137).  Included by jb_kernels.cuh.
+//
+//   k_groups       one warp or one CTA per group: schools, hospitals (dynamic members), any group
+//                  with more than 32 registered slots or a contact matrix larger than 4x4
+//   k_tiles        groups of <= 32 slots packed into 32-slot tiles: streaming detection of the
+//                  groups that must timestep + their processing, fused in one kernel through a
+//                  shared-memory work list
+//
+// Per present member the kernels read ONE byte (`phot`: activity, infected flag, susceptibility
+// code, variant); 8 more bytes only for infectors (transmission probability) and for
+// susceptibles whose susceptibility is neither 0 nor 1.
+#pragma once
+
+// Contact matrix element for (susceptible subgroup i, infector subgroup j).
+__device__ __forceinline__ double jb_cm_elem(const GroupArgs& a, int i, int j, const uint8_t* years, int n_years) {
+  if (a.kind == JB_KIND_MATRIX) return a.cm[i * a.dim + j];
+  // school.py:462-485 on the 32x32 table built by school.py:424-460
+  const double* c = a.cm;
+  if (i == j) return i != 0 ? c[1 * JB_SCHOOL_DIM + 1] : c[0];
+  if (i == 0) return c[0 * JB_SCHOOL_DIM + 1] / (double)n_years;
+  if (j == 0) return c[1 * JB_SCHOOL_DIM + 0] / (double)n_years;
+  int yi = years[i - 1] + 1, yj = years[j - 1] + 1;
+  double x = c[yi * JB_SCHOOL_DIM + yj];
+  return yi == yj ? x / 4.0 : x;
+}
+
+// Susceptibility of person p to variant v given its hot byte.
+template <int VM>
+__device__ __forceinline__ double jb_susc(const GroupArgs& a, uint32_t p, uint32_t hot, int v) {
+  if (VM == 1) {
+    const uint32_t code = JB_HOT_CODE(hot);
+    return code == JB_SC_ONE ? 1.0 : code == JB_SC_ZERO ? 0.0 : a.susc[p];
+  }
+  return a.susc[(size_t)v * a.NP + p];
+}
+
+// Inclusive segmented scan over a warp for keys that are contiguous (sorted) in lane order.
+template <typename Tv>
+__device__ __forceinline__ Tv jb_seg_scan(Tv val, uint32_t key, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    Tv up = __shfl_up_sync(JB_FULL, val, off);
+    uint32_t kup = __shfl_up_sync(JB_FULL, key, off);
+    if (lane >= off && kup == key) val += up;
+  }
+  return val;
+}
+
+// A member as two registers: person index and {lsg (16 bits) | hot byte << 16 | present << 30 |
+// infected << 31}.
+struct JbMember {
+  uint32_t p, k;
+  __device__ __forceinline__ uint32_t lsg() const { return k & 0xFFFFu; }
+  __device__ __forceinline__ uint32_t hot() const { return (k >> 16) & 0xFFu; }
+  __device__ __forceinline__ bool present() const { return (k >> 30) & 1u; }
+  __device__ __forceinline__ bool infector() const { return (k >> 30) == 3u; }   // present and infected
+  __device__ __forceinline__ bool susceptible() const { return (k >> 30) == 1u; }  // present, not infected
+};
+
+// Member `idx` of group (static registered slots first, then the sorted dynamic members, which
+// the CTA has staged in shared memory as (lsg << 28) | person).
+__device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t idx, uint32_t b, uint32_t ns,
+                                                   const uint32_t* dyn_s, uint32_t ntot) {
+  JbMember mbr;
+  mbr.p = 0; mbr.k = 0xFFFFu;
+  if (idx >= ntot) return mbr;
+  if (idx < ns) {
+    const uint32_t m = b + idx;
+    mbr.p = a.reg_member[m];
+    const uint32_t info = a.reg_info[m];
+    const uint32_t hot = a.phot[mbr.p];
+    const uint32_t pres = (hot & JB_PS_ACT_MASK) == JB_INFO_ACT(info) ? 1u : 0u;
+    mbr.k = JB_INFO_LSG(info) | (hot << 16) | (pres << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
+  } else {
+    const uint32_t k = dyn_s[idx - ns];
+    mbr.p = k & 0x0FFFFFFFu;
+    const uint32_t hot = a.phot[mbr.p];
+    mbr.k = (k >> 28) | (hot << 16) | (1u << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
+  }
+  return mbr;
+}
+
+// ---- group kernel: WPG warps per group --------------------------------------------------------
+// WPG = 1: one warp per group, JB_CTA_WARPS groups per CTA (groups of <= 128 members: the whole
+// group sits in the warp's registers between the two passes).  WPG = JB_CTA_WARPS: one CTA per
+// group (large groups, and groups with dynamic members whose bin the CTA sorts).
+#define JB_CTA 128
+#define JB_CTA_WARPS (JB_CTA / 32)
+#define JB_UB 4  // 32-member batches in flight per warp: the member -> byte -> value chain is latency bound
+
+// Shared memory per group: n[L] u32 | sus_static[L] | sus_dyn[L] | totals[2] | pad | T[WPG][V][L]
+// f64 (one copy per warp: fixed summation order) | row[V][L] f64 | dynamic member staging
+__host__ __device__ inline size_t jb_grp_smem_bytes(int L, int V, uint32_t bin_cap, int wpg) {
+  size_t ints = ((size_t)3 * L + 2 + 1) & ~(size_t)1;
+  size_t b = ints * 4 + (size_t)(wpg + 1) * V * L * 8 + (size_t)bin_cap * 4;
+  return (b + 7) & ~(size_t)7;
+}
+
+template <int WPG>
+__device__ __forceinline__ void jb_grp_sync() {
+  if (WPG == 1) __syncwarp(); else __syncthreads();
+}
+
+template <int VM, int WPG>
+__global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ GroupArgs a) {
+  extern __shared__ __align__(8) unsigned char smem_raw[];
+  constexpr int GT = 32 * WPG;                 // threads per group
+  constexpr int GPC = JB_CTA_WARPS / WPG;      // groups per CTA
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wl = wib % WPG, gs = wib / WPG, tg = threadIdx.x - gs * GT;
+  const uint32_t gi_ = blockIdx.x * GPC + gs;
+  if (gi_ >= a.n_list) return;  // uniform over the group's threads
+  const uint32_t g = a.group_list ? a.group_list[gi_] : a.g0 + gi_;
+  const int L = a.L, V = (VM > 1) ? a.V : 1;
+  const uint32_t bin_cap = a.dyn_cnt ? a.bin_cap : 0u;
+  unsigned char* base = smem_raw + (size_t)gs * jb_grp_smem_bytes(L, V, bin_cap, WPG);
+  uint32_t* n_l = (uint32_t*)base;
+  uint32_t* ss_l = n_l + L;   // susceptibles among static members, per subgroup
+  uint32_t* sd_l = ss_l + L;  // susceptibles among dynamic members
+  uint32_t* tot = sd_l + L;   // [0] susceptibles, [1] infectors
+  double* T_w = (double*)(base + ((((size_t)3 * L + 2 + 1) & ~(size_t)1) * 4));
+  double* row_l = T_w + (size_t)WPG * V * L;
+  uint32_t* dyn_s = (uint32_t*)(row_l + (size_t)V * L);
+
+  const uint32_t b = a.grp_off[g], ns = a.grp_off[g + 1] - b;
+  uint32_t nd = 0;
+  if (a.dyn_cnt) {
+    // stage this group's bin and sort it: members arrive in arbitrary (atomic) order, the
+    // reference order is (subgroup, person) -- bitonic sort in shared memory
+    const uint32_t bin = a.dyn_bin_base + (g - a.g0);
+    nd = min(a.dyn_cnt[bin], bin_cap);
+    if (nd) {
+      uint32_t npad = 32;
+      while (npad < nd) npad <<= 1;
+      const uint32_t* src = a.dyn_bin + (size_t)bin * bin_cap;
+      for (uint32_t i = tg; i < npad; i += GT) dyn_s[i] = i < nd ? src[i] : 0xFFFFFFFFu;
+      jb_grp_sync<WPG>();
+      for (uint32_t k = 2; k <= npad; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t i = tg; i < npad; i += GT) {
+            const uint32_t ixj = i ^ j;
+            if (ixj > i) {
+              const uint32_t x = dyn_s[i], y = dyn_s[ixj];
+              const bool asc = (i & k) == 0;
+              if ((x > y) == asc) { dyn_s[i] = y; dyn_s[ixj] = x; }
+            }
+          }
+          jb_grp_sync<WPG>();
+        }
+    }
+  }
+  const uint32_t ntot = ns + nd;
+  if (ntot == 0) {
+    if (a.mode == 1 && tg == 0) a.draw_cnt[g] = 0;
+    return;
+  }
+  // number of local subgroups of this group
+  int Lg = a.dim;
+  const uint8_t* years = nullptr;
+  int n_years = 0;
+  if (a.kind == JB_KIND_SCHOOL) {
+    const uint32_t aux = a.grp_aux[g];
+    n_years = aux & 0xFFu;
+    years = a.school_years + (aux >> 8);
+    Lg = n_years + 1;
+  }
+  for (int i = tg; i < Lg; i += GT) {
+    n_l[i] = 0; ss_l[i] = 0; sd_l[i] = 0;
+    for (int w = 0; w < WPG; ++w)
+      for (int v = 0; v < V; ++v) T_w[((size_t)w * V + v) * L + i] = 0.0;
+  }
+  if (tg < 2) tot[tg] = 0;
+  jb_grp_sync<WPG>();
+
+  // ---- pass 1: subgroup sizes and summed transmission probabilities ----------------------
+  // Static and dynamic members are walked in separate batches so that the subgroup keys stay
+  // sorted inside every 32-wide batch (needed by the segmented scan).  Warp w takes the batches
+  // w, w + WPG, ... and accumulates into its own copy of T, so the summation order is fixed.
+  // A group without dynamic members that fits in one round of batches stays in registers.
+  const bool resident = nd == 0 && ns <= (uint32_t)(GT * JB_UB);
+  JbMember keep[JB_UB];
+  double* T_mine = T_w + (size_t)wl * V * L;
+  uint32_t nsus = 0, ninf = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    const uint32_t lo = phase ? ns : 0u, hi = phase ? ntot : ns;
+    for (uint32_t it0 = lo + wl * 32 * JB_UB; it0 < hi; it0 += GT * JB_UB) {
+      JbMember mbs[JB_UB];
+      double tvs[JB_UB];
+#pragma unroll
+      for (int u = 0; u < JB_UB; ++u) {
+        const uint32_t idx = it0 + 32 * u + lane;
+        mbs[u] = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
+      }
+#pragma unroll
+      for (int u = 0; u < JB_UB; ++u) tvs[u] = mbs[u].infector() ? a.trans[mbs[u].p] : 0.0;
+      if (resident) {
+#pragma unroll
+        for (int u = 0; u < JB_UB; ++u) keep[u] = mbs[u];
+      }
+#pragma unroll
+      for (int u = 0; u < JB_UB; ++u) {
+        if (it0 + 32 * u >= hi) break;
+        const JbMember mb = mbs[u];
+        const uint32_t key = mb.lsg();
+        const uint32_t sus = mb.susceptible() ? 1u : 0u;
+        uint32_t packed = (mb.present() ? 1u : 0u) | (sus << 16);
+        packed = jb_seg_scan<uint32_t>(packed, key, lane);
+        const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
+        const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
+        if (tail && packed) {
+          atomicAdd(&n_l[key], packed & 0xFFFFu);
+          if (packed >> 16) atomicAdd(phase == 0 ? &ss_l[key] : &sd_l[key], packed >> 16);
+        }
+        nsus += __popc(__ballot_sync(JB_FULL, sus));
+        const bool inf = mb.infector();
+        const uint32_t infm = __ballot_sync(JB_FULL, inf);
+        ninf += __popc(infm);
+        if (infm) {
+          const int pv = (VM > 1 && inf) ? (int)JB_HOT_VAR(mb.hot()) : 0;
+          for (int v = 0; v < V; ++v) {
+            double tv = (pv == v) ? tvs[u] : 0.0;
+            tv = jb_seg_scan<double>(tv, key, lane);
+            if (tail) T_mine[v * L + key] += tv;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (WPG > 1) {
+    if (lane == 0) {
+      if (nsus) atomicAdd(&tot[0], nsus);
+      if (ninf) atomicAdd(&tot[1], ninf);
+    }
+    __syncthreads();
+    nsus = tot[0]; ninf = tot[1];
+  } else {
+    __syncwarp();
+  }
+  const bool must = nsus > 0 && ninf > 0;  // interactive.py:136
+  if (a.mode == 1) {
+    if (tg == 0) a.draw_cnt[g] = must ? nsus : 0;
+    return;
+  }
+  if (!must) return;
+
+  // ---- infector tensor row sums (interaction.py:451-478, :619) ---------------------------
+  if (WPG > 1) {
+    for (int i = tg; i < Lg * V; i += GT) {  // fold the per-warp copies, warp order
+      const int v = i / Lg, j = i - v * Lg;
+      double s = 0.0;
+      for (int w = 0; w < WPG; ++w) s += T_w[((size_t)w * V + v) * L + j];
+      T_w[(size_t)v * L + j] = s;
+    }
+    __syncthreads();
+  }
+  const uint32_t gi = a.grp_info[g];
+  const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+  const double dt = a.sp->dt;
+  for (int i = tg; i < Lg; i += GT) {
+    for (int v = 0; v < V; ++v) {
+      double s = 0.0;
+      for (int j = 0; j < Lg; ++j) {
+        const double t = T_w[(size_t)v * L + j];
+        if (t != 0.0) {
+          const int nj = (int)n_l[j];
+          const int nn = (i == j) ? max(1, nj - 1) : nj;
+          s += jb_cm_elem(a, i, j, years, n_years) * t / (double)nn * beta * dt;
+        }
+      }
+      row_l[v * L + i] = s;
+    }
+  }
+  // injected-uniform ordinals: susceptibles are numbered subgroup by subgroup, static members
+  // before dynamic ones (interactive.py:86-131 dict insertion order)
+  uint32_t ord_base = 0;
+  if (a.inject) {
+    ord_base = a.draw_base[g];
+    if (tg == 0) {
+      uint32_t run = 0;
+      for (int i = 0; i < Lg; ++i) {
+        const uint32_t s_ = ss_l[i], d_ = sd_l[i];
+        ss_l[i] = run; run += s_;
+        sd_l[i] = run; run += d_;
+      }
+    }
+  }
+  jb_grp_sync<WPG>();
+
+  // ---- pass 2: one Bernoulli draw per susceptible ----------------------------------------
+  // With injected uniforms the ordinal of a draw depends on all earlier members: warp 0 walks the
+  // group alone, in order (test mode).  Otherwise the warps share the batches.
+  const int n_walk = a.inject ? 1 : WPG;
+  if (wl < n_walk) {
+    for (int phase = 0; phase < 2; ++phase) {
+      const uint32_t lo = phase ? ns : 0u, hi = phase ? ntot : ns;
+      uint32_t* run = phase ? sd_l : ss_l;
+      for (uint32_t it0 = lo + wl * 32 * JB_UB; it0 < hi; it0 += n_walk * 32 * JB_UB) {
+        JbMember mbs[JB_UB];
+        double s0[JB_UB];
+        if (resident && n_walk == WPG) {
+#pragma unroll
+          for (int u = 0; u < JB_UB; ++u) mbs[u] = keep[u];
+        } else {
+#pragma unroll
+          for (int u = 0; u < JB_UB; ++u) {
+            const uint32_t idx = it0 + 32 * u + lane;
+            mbs[u] = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < JB_UB; ++u)
+          s0[u] = (mbs[u].susceptible() && mbs[u].lsg() < (uint32_t)Lg) ? jb_susc<VM>(a, mbs[u].p, mbs[u].hot(), 0) : 0.0;
+#pragma unroll
+        for (int u = 0; u < JB_UB; ++u) {
+          if (it0 + 32 * u >= hi) break;
+          const JbMember mb = mbs[u];
+          const bool sus = mb.susceptible() && mb.lsg() < (uint32_t)Lg;
+          uint32_t ordinal = 0;
+          if (a.inject) {
+            const uint32_t key = mb.lsg();
+            const uint32_t incl = jb_seg_scan<uint32_t>(sus ? 1u : 0u, key, lane);
+            const uint32_t knext = __shfl_down_sync(JB_FULL, key, 1);
+            const bool tail = (lane == 31 || knext != key) && key < (uint32_t)Lg;
+            if (sus) ordinal = ord_base + run[key] + incl - 1;
+            __syncwarp();
+            if (tail) run[key] += incl;
+            __syncwarp();
+          }
+          if (sus) {
+            double lam_v[VM];
+            double lam = 0.0;
+#pragma unroll
+            for (int v = 0; v < VM; ++v) {
+              double r = 0.0, sv = 0.0;
+              if (v < V) { r = row_l[v * L + mb.lsg()]; sv = (v == 0) ? s0[u] : a.susc[(size_t)v * a.NP + mb.p]; }
+              lam_v[v] = r * sv;
+              lam += lam_v[v];
+            }
+            if (a.lambda) a.lambda[mb.p] = lam;
+            if (lam != 0.0) jb_draw_core<VM>(a, mb.p, lam_v, lam, ordinal);  // lambda == 0 can never infect
+          }
+        }
+      }
+    }
+  }
+  if (tg == 0) atomicAdd(&a.counters[CNT_DRAWS], nsus);
+}
+
+// ---- tile kernel ----------------------------------------------------------------------------
+// Small groups (static members, contact matrix dim <= 4) are packed at world-create time into
+// 32-slot tiles that never split a group.  STREAM: the tile's slots ARE the (renumbered) person
+// indices, so the person bytes are read as a coalesced stream with no index indirection
+// (households).  Otherwise the slot holds the person index and the byte is gathered (companies).
+//
+// Phase A (detection): one thread owns 16 consecutive slots (a lane pair owns a tile): 128-bit
+// loads of the slot descriptors and person bytes, which are also parked in shared memory; per-tile
+// bit masks are exchanged with one shuffle; the (few) groups that hold both a present infector and
+// a present susceptible are appended to the block's work list in shared memory.  Everything else
+// costs a handful of bit operations.
+// Phase B (processing): one LANE per listed group.  The lane walks its group's slots in shared
+// memory in slot order -- the reference's own left-to-right order (Python `sum`,
+// interaction.py:463-467) -- gathers the infectors' transmission probabilities, and computes
+// Lambda for its susceptibles.  Philox + exp are the expensive part: draws are queued per warp
+// and executed 32 at a time on fully populated warps.
+#define JB_TILE_THREADS 128
+#define JB_TILE_WARPS (JB_TILE_THREADS / 32)
+#define JB_TILE_SLOTS (JB_TILE_THREADS * 16)
+#define JB_TILE_ITEMS (JB_TILE_SLOTS / 2)  // a listed group has >= 2 slots
+#define JB_DRAW_QUEUE 64
+
+__device__ __forceinline__ void jb_prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
+template <bool STREAM, int VM>
+// (stream tiles are occupancy hungry: 48 registers measured 20 % faster than 70; the gather
+// flavour keeps its registers for the 16 gathers in flight per thread)
+__global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(const __grid_constant__ GroupArgs a) {
+  __shared__ uint2 s_items[JB_TILE_ITEMS];  // {(block-local first slot << 5) | (len - 1), group}
+  __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
+  __shared__ uint32_t s_mem[STREAM ? 1 : JB_TILE_SLOTS];
+  __shared__ double s_cm[16];
+  __shared__ uint32_t s_n;
+  __shared__ double q_lam[JB_TILE_WARPS][VM][JB_DRAW_QUEUE];
+  __shared__ uint32_t q_p[JB_TILE_WARPS][JB_DRAW_QUEUE], q_ord[JB_TILE_WARPS][JB_DRAW_QUEUE];
+  const uint8_t* s_hot = reinterpret_cast<const uint8_t*>(s_hot4);
+  const uint8_t* s_info = reinterpret_cast<const uint8_t*>(s_info4);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_n = 0;
+  if (threadIdx.x < a.dim * a.dim) s_cm[threadIdx.x] = a.cm[threadIdx.x];
+  __syncthreads();
+
+  // ---- phase A ---------------------------------------------------------------------------
+  const uint32_t slot_base = blockIdx.x * JB_TILE_SLOTS;  // first slot of this block
+  {
+    const uint32_t n_chunks = a.n_tiles * 2;
+    const uint32_t c = blockIdx.x * JB_TILE_THREADS + threadIdx.x;
+    const bool ok = c < n_chunks;
+    const uint32_t slot0 = c * 16;
+    uint32_t valid = 0, first = 0, pres = 0, inf = 0;
+    uint4 iv = make_uint4(0u, 0u, 0u, 0u), sv = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t tg0 = 0;
+    if (ok) {
+      if (!(lane & 1)) tg0 = a.tile_group0[c >> 1];  // with the other loads, not behind the bit logic
+      iv = *reinterpret_cast<const uint4*>(a.tp_info + slot0);
+      if (STREAM) {
+        sv = *reinterpret_cast<const uint4*>(a.phot + a.stream_base + slot0);
+      } else {
+        uint32_t mem[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 mv = *reinterpret_cast<const uint4*>(a.tp_member + slot0 + 4 * q);
+          mem[4 * q] = mv.x; mem[4 * q + 1] = mv.y; mem[4 * q + 2] = mv.z; mem[4 * q + 3] = mv.w;
+          *reinterpret_cast<uint4*>(&s_mem[threadIdx.x * 16 + 4 * q]) = mv;
+        }
+        uint32_t stg[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) stg[i] = mem[i] != 0xFFFFFFFFu ? a.phot[mem[i]] : 0u;
+        sv.x = stg[0] | (stg[1] << 8) | (stg[2] << 16) | (stg[3] << 24);
+        sv.y = stg[4] | (stg[5] << 8) | (stg[6] << 16) | (stg[7] << 24);
+        sv.z = stg[8] | (stg[9] << 8) | (stg[10] << 16) | (stg[11] << 24);
+        sv.w = stg[12] | (stg[13] << 8) | (stg[14] << 16) | (stg[15] << 24);
+      }
+      // four slots at a time: one byte-wise compare of the descriptors' activity against the
+      // persons' activity
+      const uint32_t iw[4] = {iv.x, iv.y, iv.z, iv.w}, sw[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t hi4 = iw[q], st4 = sw[q];
+        const uint32_t valid4 = (hi4 >> 3) & 0x01010101u;
+        const uint32_t first4 = (hi4 >> 4) & valid4;
+        const uint32_t pres4 = __vcmpeq4(hi4 & 0x07070707u, st4 & 0x07070707u) & valid4;
+        const uint32_t inf4 = (st4 >> 3) & pres4;
+        // bit 0 of every byte -> 4-bit mask
+        valid |= (((valid4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        first |= (((first4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        pres |= (((pres4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        inf |= (((inf4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+      }
+    }
+    s_hot4[threadIdx.x] = sv;
+    s_info4[threadIdx.x] = iv;
+    // a tile = two neighbouring chunks: exchange the 16-bit masks inside the lane pair
+    const uint32_t mine = first | (pres << 16);
+    const uint32_t other = __shfl_xor_sync(JB_FULL, mine, 1);
+    const uint32_t iv_o = __shfl_xor_sync(JB_FULL, inf | (valid << 16), 1);
+    uint32_t draws = 0;
+    const uint32_t t = c >> 1;
+    if (ok && !(lane & 1)) {  // the even lane of the pair owns the tile
+      const uint32_t first32 = (first & 0xFFFFu) | (other << 16);
+      const uint32_t pres32 = pres | (other & 0xFFFF0000u);
+      const uint32_t inf32 = inf | (iv_o << 16);
+      const uint32_t n_valid = 32 - __clz((valid & 0xFFFFu) | (iv_o & 0xFFFF0000u));  // valid slots are a prefix
+      const uint32_t sus32 = pres32 & ~inf32;
+      uint32_t rem = inf32;
+      while (rem) {
+        const uint32_t src = __ffs(rem) - 1;
+        const uint32_t le = 0xFFFFFFFFu >> (31 - src);
+        const uint32_t below = first32 & le, above = first32 & ~le;
+        const uint32_t start = 31 - __clz(below | 1u);
+        const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : n_valid;
+        const uint32_t gmask = (end == 32u ? 0xFFFFFFFFu : ((1u << end) - 1u)) & ~((1u << start) - 1u);
+        rem &= ~gmask;
+        const uint32_t nsus = __popc(gmask & sus32);
+        if (!nsus) continue;  // must_timestep needs a susceptible too (interactive.py:136)
+        const uint32_t g = tg0 + __popc(below) - 1u;
+        if (a.mode == 1) { a.draw_cnt[g] = nsus; continue; }
+        draws += nsus;
+        const uint32_t pos = atomicAdd(&s_n, 1u);
+        s_items[pos] = make_uint2(((t * 32 + start - slot_base) << 5) | (end - start - 1), g);
+      }
+    }
+    draws = __reduce_add_sync(JB_FULL, draws);
+    if (lane == 0 && draws) atomicAdd(&a.counters[CNT_DRAWS], draws);
+  }
+  __syncthreads();
+  const uint32_t n_work = s_n;
+  if (n_work == 0 || a.mode == 2) return;  // mode 2: detection only (profiling aid)
+
+  // ---- phase B ---------------------------------------------------------------------------
+  const int V = (VM > 1) ? a.V : 1;
+  const int dim = a.dim;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  const double dt = a.sp->dt;
+  uint32_t qn = 0;  // warp-uniform queue length
+
+  auto drain = [&](uint32_t n) {
+    if ((uint32_t)lane < n) {
+      double lam_v[VM];
+      double lam = 0.0;
+#pragma unroll
+      for (int v = 0; v < VM; ++v) { lam_v[v] = q_lam[wib][v][lane]; lam += lam_v[v]; }
+      jb_draw_core<VM>(a, q_p[wib][lane], lam_v, lam, q_ord[wib][lane]);
+    }
+    __syncwarp();
+  };
+
+  for (uint32_t wbase = wib * 32; wbase < n_work; wbase += JB_TILE_WARPS * 32) {
+    const uint32_t w = wbase + lane;
+    const bool have_item = w < n_work;
+    const uint2 item = have_item ? s_items[w] : make_uint2(0u, 0u);
+    const uint32_t loc = item.x >> 5, len = have_item ? (item.x & 31u) + 1u : 0u, g = item.y;
+    const uint32_t max_len = __reduce_max_sync(JB_FULL, len);
+    // Everything phase B gathers per group (the infectors' transmission probabilities, the group
+    // word, the members' global ids for the Philox counter) is independent: prefetch it all into
+    // L2 first so that the DRAM latencies overlap instead of chaining.
+    if (have_item) {
+      jb_prefetch_l2(a.grp_info + g);
+      const uint32_t pf = STREAM ? a.stream_base + slot_base + loc : s_mem[loc];
+      if (pf < a.N) jb_prefetch_l2(a.int2ext + pf);
+    }
+    for (uint32_t m = 0; m < max_len; ++m) {
+      if (m < len) {
+        const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
+        if (((hot ^ info) & JB_PS_ACT_MASK) == 0u && (hot & JB_PS_INFECTED))
+          jb_prefetch_l2(a.trans + (STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m]));
+      }
+    }
+    double beta = 0.0;
+    uint32_t ord = 0;
+    if (have_item) {
+      const uint32_t gi = a.grp_info[g];
+      beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+      ord = a.inject ? a.draw_base[g] : 0u;
+    }
+    // pass 1: subgroup sizes (four 8-bit counters) and summed transmission probabilities
+    uint32_t npk = 0;
+    double T[VM][4];
+#pragma unroll
+    for (int v = 0; v < VM; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) T[v][k] = 0.0;
+    for (uint32_t m = 0; m < max_len; ++m) {
+      if (m < len) {
+        const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
+        if (((hot ^ info) & JB_PS_ACT_MASK) == 0u) {  // present
+          const int l = (int)JB_TI_LSG(info);
+          npk += 1u << (8 * l);
+          if (hot & JB_PS_INFECTED) {
+            const uint32_t p = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+            const double t = a.trans[p];
+            const int pv = (VM > 1) ? (int)JB_HOT_VAR(hot) : 0;
+#pragma unroll
+            for (int v = 0; v < VM; ++v)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (v == pv && j == l) T[v][j] += t;
+          }
+        }
+      }
+    }
+    // pass 2: Lambda of every susceptible (interaction.py:594-631), draws queued
+    for (uint32_t m = 0; m < max_len; ++m) {
+      bool sus = false;
+      uint32_t p = 0;
+      double lam_v[VM];
+      double lam = 0.0;
+#pragma unroll
+      for (int v = 0; v < VM; ++v) lam_v[v] = 0.0;
+      if (m < len) {
+        const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
+        if (((hot ^ info) & JB_PS_ACT_MASK) == 0u && !(hot & JB_PS_INFECTED)) {
+          sus = true;
+          p = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+          const int i = (int)JB_TI_LSG(info);
+#pragma unroll
+          for (int v = 0; v < VM; ++v) {
+            double r = 0.0;
+            if (v < V) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < dim && T[v][j] != 0.0) {
+                  const int nj = (int)((npk >> (8 * j)) & 0xFFu);
+                  const int nn = (i == j) ? max(1, nj - 1) : nj;  // interaction.py:469-471
+                  r += s_cm[i * dim + j] * T[v][j] / (double)nn * beta * dt;
+                }
+              r *= jb_susc<VM>(a, p, hot, v);
+            }
+            lam_v[v] = r;
+            lam += r;
+          }
+          if (a.lambda) a.lambda[p] = lam;
+        }
+      }
+      // queue the draws that can succeed (lambda == 0 never infects)
+      const bool want = sus && lam != 0.0;
+      const uint32_t wm = __ballot_sync(JB_FULL, want);
+      if (wm) {
+        if (want) {
+          const uint32_t pos = qn + __popc(wm & lane_lt);
+          q_p[wib][pos] = p;
+          q_ord[wib][pos] = ord;
+#pragma unroll
+          for (int v = 0; v < VM; ++v) q_lam[wib][v][pos] = lam_v[v];
+        }
+        qn += __popc(wm);
+        __syncwarp();
+        if (qn >= 32) {
+          drain(32);
+          const uint32_t rest = qn - 32;
+          uint32_t mp = 0, mo = 0;
+          double ml[VM];
+          if ((uint32_t)lane < rest) {
+            mp = q_p[wib][32 + lane]; mo = q_ord[wib][32 + lane];
+#pragma unroll
+            for (int v = 0; v < VM; ++v) ml[v] = q_lam[wib][v][32 + lane];
+          }
+          __syncwarp();
+          if ((uint32_t)lane < rest) {
+            q_p[wib][lane] = mp; q_ord[wib][lane] = mo;
+#pragma unroll
+            for (int v = 0; v < VM; ++v) q_lam[wib][v][lane] = ml[v];
+          }
+          __syncwarp();
+          qn = rest;
+        }
+      }
+      if (sus) ++ord;
+    }
+  }
+  if (qn) drain(qn);
+}

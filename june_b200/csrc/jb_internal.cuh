@@ -13,6 +13,7 @@
 enum {
   CNT_SLOTS_HW = 0,    // infection slot high-water mark (persistent)
   CNT_DEAD_TOTAL,      // persistent
+  CNT_SLOTS_PREV,      // high-water mark at the start of the step (snapshot by k_place)
   CNT_STEP_BEGIN,
   CNT_NEWINF = CNT_STEP_BEGIN,  // new infections appended this step (local + halo)
   CNT_NOACT,           // persons without any activity this step
@@ -27,8 +28,6 @@ enum {
   CNT_ICU,
   CNT_ACT0,            // persons placed per activity (5 words: JB_ACT_MEDICAL..JB_ACT_RESIDENCE)
   CNT_ACT4 = CNT_ACT0 + 4,
-  CNT_WORK0,           // per-supergroup work-list lengths: JB_MAX_SUPERGROUPS x JB_WORK_SUBLISTS words
-  CNT_WORK_LAST = CNT_WORK0 + JB_MAX_SUPERGROUPS * 32 - 1,
   CNT_N                // followed by summary[R][JB_N_SUMMARY], then dyn_cnt[n_bins]
 };
 
@@ -36,7 +35,27 @@ enum {
 enum { SUM_NEW_INFECTED = 0, SUM_CUR_INFECTED, SUM_CUR_HOSP, SUM_CUR_ICU, SUM_DEATHS, SUM_HOSP_DEATHS, SUM_RECOVERED, SUM_ADMISSIONS };
 
 #define JB_TAG_BIT(tag) (1 << ((tag) + 2))
-#define JB_WORK_SUBLISTS 32
+
+// ---- internal person bytes -----------------------------------------------------------------
+// `pstate` (persistent): bits 0-1 susceptibility code of variant 0, bit 3 INFECTED, 4 DEAD,
+// 5 SEVERE, 6 MEDICAL (the JB_PS_* positions of the ABI byte; the activity bits are NOT kept
+// here).  `phot` (rebuilt by k_place every step, the only per-person byte the interaction
+// kernels read): bits 0-2 activity of the step, bit 3 INFECTED, bits 4-5 susceptibility code,
+// bits 6-7 variant of the infection.  The code spares the 8-byte susceptibility gather for the
+// common values: 0 -> 0.0 (immune), 1 -> 1.0, 2 -> read `susc`.
+#define JB_SC_ZERO 0u
+#define JB_SC_ONE 1u
+#define JB_SC_READ 2u
+#define JB_PST_CODE_MASK 0x03u
+#define JB_HOT_CODE(x) (((x) >> 4) & 3u)
+#define JB_HOT_VAR(x) ((x) >> 6)
+
+// tile slot descriptor (uint8): bits 0-2 feeding activity, 3 VALID, 4 FIRST slot of its group,
+// 5-6 local subgroup (tile mode needs dim <= 4)
+#define JB_TI_VALID 0x08u
+#define JB_TI_FIRST 0x10u
+#define JB_TI_LSG(x) (((x) >> 5) & 3u)
+#define JB_TI_ACT(x) ((x) & 7u)
 
 // Per-step scalars, resident on the device so that a captured CUDA graph of the step can be
 // replayed: one h2d copy from a pinned ring buffer precedes every step.  The processed beta
@@ -54,8 +73,7 @@ struct GroupArgs {
   const uint32_t* grp_aux;
   const uint32_t* reg_member;
   const uint16_t* reg_info;
-  const uint8_t* pstate;
-  const uint8_t* pvar;
+  const uint8_t* phot;       // per-step person byte (see above)
   const double* susc;
   const double* trans;
   const uint32_t* halo_gid;
@@ -72,12 +90,8 @@ struct GroupArgs {
   const uint32_t* int2ext;    // internal -> caller person index
   const uint32_t* tile_group0;
   const uint32_t* tp_member;
-  const uint16_t* tp_info;
+  const uint8_t* tp_info;
   uint32_t n_tiles, stream_base;
-  uint2* work_items;          // groups that must timestep, found by k_detect: JB_WORK_SUBLISTS
-  uint32_t* work_cnt;         // sub-lists (one per blockIdx & 31) so that the append counters do
-  uint32_t sub_off[JB_WORK_SUBLISTS + 1];  // not serialise on one L2 address; exact capacities
-  uint32_t detect_blocks;
   int dim, kind, L;
   uint32_t N, NP;
   int V, R;
@@ -107,14 +121,15 @@ struct DiseaseDev {
 // Tile decomposition of one supergroup (built once at world create).
 struct SgTiles {
   int mode = 0;               // 0 = warp per group only, 1 = gather tiles, 2 = stream tiles
-  uint32_t n_tiles = 0, stream_base = 0, n_big = 0;
+  uint32_t n_tiles = 0, stream_base = 0;
   uint32_t* tile_group0 = nullptr;
   uint32_t* tp_member = nullptr;
-  uint16_t* tp_info = nullptr;
-  uint32_t* big_list = nullptr;  // groups too large for a tile -> warp kernel
-  uint2* work_items = nullptr;   // capacity = number of groups of the supergroup
-  uint32_t sub_off[JB_WORK_SUBLISTS + 1] = {};  // region of every sub-list inside work_items
-  uint32_t detect_blocks = 0;    // grid of k_detect (fixes which block sees which tile)
+  uint8_t* tp_info = nullptr;
+  // groups not handled by tiles, longest first: <= 128 members and static -> one warp each,
+  // the others -> one CTA each
+  uint32_t *list_w = nullptr, *list_c = nullptr;
+  uint32_t n_w = 0, n_c = 0;
+  double mean_len = 0;          // mean slots per tiled group (picks the lanes-per-group flavour)
 };
 
 struct JbWorld {
@@ -122,8 +137,11 @@ struct JbWorld {
   cudaStream_t stream = nullptr;
   // the interaction kernels of the active supergroups are independent: they run concurrently on
   // side streams forked from / joined into `stream`
-  cudaStream_t side[JB_MAX_SUPERGROUPS] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[JB_MAX_SUPERGROUPS] = {};
+  // (up to three independent launches per supergroup: tiles, warp list, CTA list)
+  cudaStream_t side[JB_MAX_SUPERGROUPS][3] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[JB_MAX_SUPERGROUPS][3] = {};
+  cudaStream_t side_health = nullptr;
+  cudaEvent_t ev_fork_health = nullptr, ev_join_health = nullptr;
   bool serial = false;
   // N = residents in the INTERNAL numbering (includes padding slots of the streamed supergroup),
   // N_ext = residents as the caller numbers them
@@ -144,7 +162,7 @@ struct JbWorld {
   double *cm = nullptr, *beta_scale = nullptr, *hi_cum = nullptr;
   DiseaseDev* dis = nullptr;
   // person state
-  uint8_t *pstate = nullptr, *pvar = nullptr;
+  uint8_t *pstate = nullptr, *phot = nullptr, *pvar = nullptr;
   int8_t* ptag = nullptr;
   double *susc = nullptr, *trans = nullptr;
   int32_t *pmed = nullptr, *pslot = nullptr;

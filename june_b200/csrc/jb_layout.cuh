@@ -11,13 +11,11 @@
 
 #include "jb_internal.cuh"
 
-#define JB_TI_VALID_H 0x0800u
-#define JB_TI_FIRST_H 0x1000u
 
 struct HostTiles {
   int mode = 0;  // 0 warp only, 1 gather tiles, 2 stream tiles
   std::vector<uint32_t> tile_group0, tp_member, big;
-  std::vector<uint16_t> tp_info;
+  std::vector<uint8_t> tp_info;
 };
 
 struct HostLayout {
@@ -28,7 +26,9 @@ struct HostLayout {
   std::vector<HostTiles> tiles;
 };
 
-static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool stream, HostTiles& T) {
+// Groups of more than `tile_max` slots are left to the per-group kernels (a tile lane group walks
+// its group in rounds, which only pays for short groups).
+static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool stream, uint32_t tile_max, HostTiles& T) {
   auto pad = [&]() {
     while (T.tp_member.size() % 32) { T.tp_member.push_back(0xFFFFFFFFu); T.tp_info.push_back(0); }
   };
@@ -36,7 +36,7 @@ static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool str
   for (uint32_t g = sg.first_group; g < sg.first_group + sg.n_groups; ++g) {
     const uint32_t b = d->grp_offset[g], e = d->grp_offset[g + 1], sz = e - b;
     if (sz == 0) { pad(); fill = 32; continue; }  // keeps group indices consecutive inside a tile
-    if (sz > 32) {
+    if (sz > tile_max) {
       T.big.push_back(g);
       pad();
       fill = 32;
@@ -44,7 +44,7 @@ static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool str
         for (uint32_t m = b; m < e; ++m) {
           if ((m - b) % 32 == 0) T.tile_group0.push_back(g);
           T.tp_member.push_back(d->reg_member[m]);
-          T.tp_info.push_back((uint16_t)(d->reg_info[m] & 0x07FFu));
+          T.tp_info.push_back((uint8_t)JB_INFO_ACT(d->reg_info[m]));  // not VALID: handled by the CTA kernel
         }
         pad();
       }
@@ -53,7 +53,8 @@ static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool str
     if (fill + sz > 32) { pad(); T.tile_group0.push_back(g); fill = 0; }
     for (uint32_t m = b; m < e; ++m) {
       T.tp_member.push_back(d->reg_member[m]);
-      T.tp_info.push_back((uint16_t)((d->reg_info[m] & 0x07FFu) | JB_TI_VALID_H | (m == b ? JB_TI_FIRST_H : 0u)));
+      T.tp_info.push_back((uint8_t)(JB_INFO_ACT(d->reg_info[m]) | JB_TI_VALID | (m == b ? JB_TI_FIRST : 0u) |
+                                    ((JB_INFO_LSG(d->reg_info[m]) & 3u) << 5)));
     }
     fill += sz;
   }
@@ -61,7 +62,8 @@ static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool str
 }
 
 // Returns an error string or nullptr.
-static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSupergroup>& sgs, HostLayout& L) {
+static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSupergroup>& sgs, uint32_t tile_max_gather,
+                                   HostLayout& L) {
   const uint32_t N = d->n_people;
   L.tiles.assign(sgs.size(), HostTiles());
   // the streamed supergroup: first tile-mode residence supergroup whose slots are distinct residents
@@ -83,7 +85,7 @@ static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSup
     for (uint32_t m = d->grp_offset[sg.first_group]; m < d->grp_offset[sg.first_group + sg.n_groups]; ++m)
       if ((int)JB_INFO_LSG(d->reg_info[m]) >= sg.dim) return "registered member has a subgroup index >= contact matrix dimension";
     L.tiles[k].mode = ((int)k == ks) ? 2 : 1;
-    jb_pack_tiles(d, sg, (int)k == ks, L.tiles[k]);
+    jb_pack_tiles(d, sg, (int)k == ks, (int)k == ks ? 32u : tile_max_gather, L.tiles[k]);
   }
   // internal numbering
   L.ext2int.assign(N, 0xFFFFFFFFu);

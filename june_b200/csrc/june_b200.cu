@@ -49,6 +49,11 @@ static bool jb_debug_sync() {
     }                                                                                         \
   } while (0)
 
+static int jb_env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 template <typename T>
 static int dev_alloc(T** p, size_t n) {
   *p = nullptr;
@@ -159,7 +164,7 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   // internal numbering + tiles (jb_layout.cuh)
   HostLayout lay;
   {
-    const char* err = jb_build_layout(d, w->sgs, lay);
+    const char* err = jb_build_layout(d, w->sgs, (uint32_t)std::min(32, std::max(1, jb_env_flag("JB_TILE_MAX_GATHER", 16))), lay);
     REQUIRE(err == nullptr, err ? err : "");
   }
   w->N = lay.N_int; w->NP = w->N + w->H;
@@ -173,32 +178,28 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     const HostTiles& T = lay.tiles[k];
     SgTiles& D = w->tiles[k];
     D.mode = T.mode;
+    // groups the tiles do not cover, longest first (the long ones set the tail of the launch)
+    const JbSupergroup& sg = w->sgs[k];
+    std::vector<uint32_t> rest;
+    if (T.mode == 0) { rest.resize(sg.n_groups); for (uint32_t i = 0; i < sg.n_groups; ++i) rest[i] = sg.first_group + i; }
+    else rest = T.big;
+    auto gsize = [&](uint32_t g) { return d->grp_offset[g + 1] - d->grp_offset[g]; };
+    std::stable_sort(rest.begin(), rest.end(), [&](uint32_t x, uint32_t y) { return gsize(x) > gsize(y); });
+    std::vector<uint32_t> lw, lc;
+    for (uint32_t g : rest) ((sg.has_dynamic || gsize(g) > 32 * JB_UB) ? lc : lw).push_back(g);
+    D.n_w = (uint32_t)lw.size(); D.n_c = (uint32_t)lc.size();
+    if (D.n_w) TRY(dev_upload(&D.list_w, lw.data(), lw.size(), s));
+    if (D.n_c) TRY(dev_upload(&D.list_c, lc.data(), lc.size(), s));
+    CK(cudaStreamSynchronize(s));  // lw / lc are locals
     if (T.mode == 0) continue;
     D.n_tiles = (uint32_t)(T.tp_info.size() / 32);
-    D.n_big = (uint32_t)T.big.size();
     REQUIRE(T.tile_group0.size() == D.n_tiles, "internal: tile table size mismatch");
     TRY(dev_upload(&D.tile_group0, T.tile_group0.data(), T.tile_group0.size(), s));
     TRY(dev_upload(&D.tp_info, T.tp_info.data(), T.tp_info.size(), s));
     if (T.mode == 1) TRY(dev_upload(&D.tp_member, T.tp_member.data(), T.tp_member.size(), s));
-    if (D.n_big) TRY(dev_upload(&D.big_list, T.big.data(), T.big.size(), s));
-    TRY(dev_alloc(&D.work_items, (size_t)w->sgs[k].n_groups + 1));
-    {
-      // k_detect runs a fixed grid-stride schedule, so the set of tiles (hence groups) a block
-      // can ever report is known: exact capacity of each of the JB_WORK_SUBLISTS sub-lists
-      const uint32_t chunks = D.n_tiles * 2;
-      D.detect_blocks = std::max<uint32_t>(1u, std::min<uint32_t>((chunks + 255) / 256, 148 * 8));
-      const uint64_t n_threads = (uint64_t)D.detect_blocks * 256;
-      std::vector<uint32_t> cap(JB_WORK_SUBLISTS, 0);
-      for (uint32_t t = 0; t < D.n_tiles; ++t) {
-        uint32_t groups = 0;
-        for (int i = 0; i < 32; ++i) groups += (T.tp_info[(size_t)t * 32 + i] & JB_TI_FIRST_H) ? 1u : 0u;
-        const uint32_t block = (uint32_t)(((uint64_t)(2 * t) % n_threads) / 256);
-        cap[block & (JB_WORK_SUBLISTS - 1)] += groups;
-      }
-      D.sub_off[0] = 0;
-      for (int j = 0; j < JB_WORK_SUBLISTS; ++j) D.sub_off[j + 1] = D.sub_off[j] + cap[j];
-      REQUIRE(D.sub_off[JB_WORK_SUBLISTS] <= w->sgs[k].n_groups, "internal: work-list capacity");
-    }
+    size_t n_first = 0, n_valid = 0;
+    for (uint8_t x : T.tp_info) { n_first += (x & JB_TI_FIRST) ? 1 : 0; n_valid += (x & JB_TI_VALID) ? 1 : 0; }
+    D.mean_len = n_first ? (double)n_valid / (double)n_first : 0.0;
   }
   TRY(dev_upload(&w->age, lay.age.data(), w->N, s));
   TRY(dev_upload(&w->sex, lay.sex.data(), w->N, s));
@@ -219,6 +220,7 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_upload(&w->dis, &w->dis_host, 1, s));
 
   TRY(dev_alloc(&w->pstate, w->NP));
+  TRY(dev_alloc(&w->phot, w->NP + 16));
   TRY(dev_alloc(&w->pvar, w->NP));
   TRY(dev_alloc(&w->ptag, w->N));
   TRY(dev_alloc(&w->susc, (size_t)w->V * w->NP));
@@ -227,11 +229,12 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_alloc(&w->pslot, w->N));
   TRY(dev_alloc(&w->halo_gid, w->H));
   {
-    // residents start alive and nowhere; padding slots are permanently dead
-    std::vector<uint8_t> st(w->NP, JB_ACT_NONE);
+    // residents start alive, fully susceptible and nowhere; padding slots are permanently dead
+    std::vector<uint8_t> st(w->NP, JB_SC_ONE);
     for (uint32_t i = 0; i < w->N; ++i)
-      if (lay.int2ext[i] == 0xFFFFFFFFu) st[i] = JB_ACT_NONE | JB_PS_DEAD;
+      if (lay.int2ext[i] == 0xFFFFFFFFu) st[i] = JB_PS_DEAD;
     CK(cudaMemcpyAsync(w->pstate, st.data(), w->NP, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(w->phot, JB_ACT_NONE, w->NP + 16, s));
     CK(cudaStreamSynchronize(s));
   }
   CK(cudaMemsetAsync(w->pvar, 0, w->NP, s));
@@ -315,13 +318,20 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   for (size_t k = 0; k < w->sgs.size(); ++k) {
     CK(cudaEventCreate(&w->ev_sg0[k]));
     CK(cudaEventCreate(&w->ev_sg1[k]));
-    CK(cudaStreamCreateWithFlags(&w->side[k], cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&w->ev_join[k], cudaEventDisableTiming));
+    for (int u = 0; u < 3; ++u) {
+      CK(cudaStreamCreateWithFlags(&w->side[k][u], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&w->ev_join[k][u], cudaEventDisableTiming));
+    }
   }
   CK(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
-  // the warp kernel may need > 48 KB of dynamic shared memory for very large schools
-  CK(cudaFuncSetAttribute(k_groups_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_groups_warp<JB_MAX_VARIANTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaStreamCreateWithFlags(&w->side_health, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&w->ev_fork_health, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&w->ev_join_health, cudaEventDisableTiming));
+  // the CTA kernel may need > 48 KB of dynamic shared memory for very large schools
+  CK(cudaFuncSetAttribute(k_groups<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<1, JB_CTA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, JB_CTA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   *out = w;
@@ -334,7 +344,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   cudaStreamSynchronize(w->stream);
   void* ptrs[] = {w->age, w->sex, w->ch, w->phas, w->school_years, w->psa, w->grp_off, w->grp_info, w->grp_aux,
                   w->reg_member, w->reg_info, w->sa_region, w->sa_hospital, w->cm, w->beta_scale, w->hi_cum, w->dis,
-                  w->pstate, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
+                  w->pstate, w->phot, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
@@ -345,8 +355,8 @@ extern "C" void jb_world_destroy(JbWorld* w) {
     if (t.tile_group0) cudaFree(t.tile_group0);
     if (t.tp_member) cudaFree(t.tp_member);
     if (t.tp_info) cudaFree(t.tp_info);
-    if (t.big_list) cudaFree(t.big_list);
-    if (t.work_items) cudaFree(t.work_items);
+    if (t.list_w) cudaFree(t.list_w);
+    if (t.list_c) cudaFree(t.list_c);
   }
   for (int i = 0; i < 4; ++i) {
     if (w->h_step[i]) cudaFreeHost(w->h_step[i]);
@@ -359,11 +369,15 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   if (w->ev_int0) cudaEventDestroy(w->ev_int0);
   if (w->ev_int1) cudaEventDestroy(w->ev_int1);
   for (int k = 0; k < JB_MAX_SUPERGROUPS; ++k) { if (w->ev_sg0[k]) cudaEventDestroy(w->ev_sg0[k]); if (w->ev_sg1[k]) cudaEventDestroy(w->ev_sg1[k]); }
-  for (int k = 0; k < JB_MAX_SUPERGROUPS; ++k) {
-    if (w->side[k]) cudaStreamDestroy(w->side[k]);
-    if (w->ev_join[k]) cudaEventDestroy(w->ev_join[k]);
-  }
+  for (int k = 0; k < JB_MAX_SUPERGROUPS; ++k)
+    for (int u = 0; u < 3; ++u) {
+      if (w->side[k][u]) cudaStreamDestroy(w->side[k][u]);
+      if (w->ev_join[k][u]) cudaEventDestroy(w->ev_join[k][u]);
+    }
   if (w->ev_fork) cudaEventDestroy(w->ev_fork);
+  if (w->side_health) cudaStreamDestroy(w->side_health);
+  if (w->ev_fork_health) cudaEventDestroy(w->ev_fork_health);
+  if (w->ev_join_health) cudaEventDestroy(w->ev_join_health);
   cudaStreamDestroy(w->stream);
   delete w;
 }
@@ -373,9 +387,14 @@ extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const doub
   CK(cudaSetDevice(w->device));
   CK(cudaStreamSynchronize(w->stream));
   if (pstate) {
-    std::vector<uint8_t> st(w->N, JB_ACT_NONE | JB_PS_DEAD);
-    for (uint32_t p = 0; p < w->N_ext; ++p) st[w->h_ext2int[p]] = pstate[p];
+    // ABI byte -> persistent flags (bits 3-6) and the activity of the (last) step
+    std::vector<uint8_t> st(w->N, JB_PS_DEAD), hot(w->N, JB_ACT_NONE);
+    for (uint32_t p = 0; p < w->N_ext; ++p) {
+      st[w->h_ext2int[p]] = pstate[p] & 0x78u;
+      hot[w->h_ext2int[p]] = (pstate[p] & (JB_PS_ACT_MASK | JB_PS_INFECTED));
+    }
     CK(cudaMemcpy(w->pstate, st.data(), w->N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->phot, hot.data(), w->N, cudaMemcpyHostToDevice));
   }
   if (susceptibility) {
     std::vector<double> su(w->N, 1.0);
@@ -383,6 +402,11 @@ extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const doub
       for (uint32_t p = 0; p < w->N_ext; ++p) su[w->h_ext2int[p]] = susceptibility[(size_t)v * w->N_ext + p];
       CK(cudaMemcpy(w->susc + (size_t)v * w->NP, su.data(), (size_t)w->N * 8, cudaMemcpyHostToDevice));
     }
+  }
+  if (w->N) {
+    k_refresh_codes<<<(w->N + 255) / 256, 256, 0, w->stream>>>(w->pstate, w->susc, w->N);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(w->stream));
   }
   return JB_OK;
 }
@@ -515,7 +539,7 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
     r.person = w->h_ext2int[r.person];
     uint8_t st = 0;
     CK(cudaMemcpy(&st, w->pstate + r.person, 1, cudaMemcpyDeviceToHost));
-    st |= JB_PS_INFECTED;
+    st = (uint8_t)((st & ~JB_PST_CODE_MASK) | JB_PS_INFECTED);  // susceptibility 0.0 from now on
     if (JB_TAG_BIT(r.tag) & w->dis_host.severe_mask) st |= JB_PS_SEVERE;
     CK(cudaMemcpy(w->pstate + r.person, &st, 1, cudaMemcpyHostToDevice));
     int32_t slot = (int32_t)(hw + i);
@@ -564,7 +588,7 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   const JbStepParams& p = w->cur;
   a.grp_off = w->grp_off; a.grp_info = w->grp_info; a.grp_aux = w->grp_aux;
   a.reg_member = w->reg_member; a.reg_info = w->reg_info;
-  a.pstate = w->pstate; a.pvar = w->pvar; a.susc = w->susc; a.trans = w->trans; a.halo_gid = w->halo_gid;
+  a.phot = w->phot; a.susc = w->susc; a.trans = w->trans; a.halo_gid = w->halo_gid;
   a.school_years = w->school_years; a.cm = w->cm + sg.cm_offset; a.beta = w->beta; a.beta_scale = w->beta_scale;
   a.dyn_cnt = sg.has_dynamic ? w->dyn_cnt : nullptr;
   a.dyn_bin = sg.has_dynamic ? w->dyn_bin : nullptr;
@@ -586,74 +610,67 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   return a;
 }
 
-template <int VM>
-static int launch_warp(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_t st) {
-  const int wpb = 4;
-  size_t smem = jb_warp_smem_bytes(a.L, (int)w->V, dynamic ? w->bin_cap : 0u) * wpb;
-  unsigned blocks = (a.n_list + wpb - 1) / wpb;
-  if (a.kind == JB_KIND_MATRIX && a.dim == 1 && !dynamic) {
-    k_groups_warp_d1<VM><<<blocks, wpb * 32, 0, st>>>(a);
-    KCHECK("k_groups_warp_d1", st);
-    return JB_OK;
-  }
-  k_groups_warp<VM><<<blocks, wpb * 32, smem, st>>>(a);
-  KCHECK("k_groups_warp", st);
+template <int VM, int WPG>
+static int launch_list(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_t st) {
+  if (a.n_list == 0) return JB_OK;
+  constexpr int gpc = JB_CTA_WARPS / WPG;
+  const size_t smem = jb_grp_smem_bytes(a.L, (int)w->V, dynamic ? w->bin_cap : 0u, WPG) * gpc;
+  k_groups<VM, WPG><<<(a.n_list + gpc - 1) / gpc, JB_CTA, smem, st>>>(a);
+  KCHECK(WPG == 1 ? "k_groups<warp>" : "k_groups<cta>", st);
   return JB_OK;
 }
 
 template <bool STREAM, int VM>
 static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
-  k_detect<STREAM><<<a.detect_blocks, 256, 0, st>>>(a);
-  KCHECK(STREAM ? "k_detect<stream>" : "k_detect<gather>", st);
-  if (a.mode == 0) {
-    // households are small: 4 lanes per group; gathered groups (companies, care homes): 8
-    if (STREAM) k_process<STREAM, VM, 4><<<148 * 12, 128, 0, st>>>(a);
-    else k_process<STREAM, VM, 8><<<148 * 12, 128, 0, st>>>(a);
-    KCHECK(STREAM ? "k_process<stream>" : "k_process<gather>", st);
-  }
+  const unsigned blocks = (a.n_tiles * 2 + JB_TILE_THREADS - 1) / JB_TILE_THREADS;
+  k_tiles<STREAM, VM><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
+  KCHECK(STREAM ? "k_tiles<stream>" : "k_tiles<gather>", st);
   return JB_OK;
 }
 
 static int launch_groups(JbWorld* w, int mode) {
-  // fork: every active supergroup gets its own stream (its groups are disjoint from all others,
-  // person state is read-only here, outputs are appended with atomics)
+  // fork: every active supergroup gets its own streams (its groups are disjoint from all others,
+  // person state is read-only here, outputs are appended with atomics); inside a supergroup the
+  // tiles, the warp list and the CTA list are independent launches as well
   CK(cudaEventRecord(w->ev_fork, w->stream));
   for (size_t k = 0; k < w->sgs.size(); ++k) {
     const JbSupergroup& sg = w->sgs[k];
     if (sg.n_groups == 0) continue;
     if (!(w->cur.activity_mask & (1u << sg.activity))) continue;
-    cudaStream_t st = w->serial ? w->stream : w->side[k];
-    if (!w->serial) CK(cudaStreamWaitEvent(st, w->ev_fork, 0));
     GroupArgs a = make_group_args(w, sg, w->sg_L[k]);
     a.mode = mode;
     const bool tme = w->timing >= 2 && mode == 0;
-    if (tme) CK(cudaEventRecord(w->ev_sg0[k], st));
+    if (tme) CK(cudaEventRecord(w->ev_sg0[k], w->stream));
     const SgTiles& T = w->tiles[k];
-    if (T.mode == 0) {
-      if (w->V == 1) TRY(launch_warp<1>(w, a, sg.has_dynamic != 0, st)); else TRY(launch_warp<JB_MAX_VARIANTS>(w, a, sg.has_dynamic != 0, st));
-      w->launches++;
-    } else {
-      a.tile_group0 = T.tile_group0; a.tp_member = T.tp_member; a.tp_info = T.tp_info;
-      a.n_tiles = T.n_tiles; a.stream_base = T.stream_base;
-      a.work_items = T.work_items; a.work_cnt = w->counters + CNT_WORK0 + k * JB_WORK_SUBLISTS;
-      memcpy(a.sub_off, T.sub_off, sizeof(a.sub_off)); a.detect_blocks = T.detect_blocks;
-      if (T.n_tiles) {
-        if (T.mode == 2) { if (w->V == 1) TRY((launch_tiles<true, 1>(w, a, st))); else TRY((launch_tiles<true, JB_MAX_VARIANTS>(w, a, st))); }
-        else { if (w->V == 1) TRY((launch_tiles<false, 1>(w, a, st))); else TRY((launch_tiles<false, JB_MAX_VARIANTS>(w, a, st))); }
-        w->launches += (mode == 0) ? 2 : 1;
+    const bool multi = w->V > 1;
+    for (int u = 0; u < 3; ++u) {
+      if ((u == 0 && (T.mode == 0 || T.n_tiles == 0)) || (u == 1 && T.n_w == 0) || (u == 2 && T.n_c == 0)) continue;
+      static const int unit_streams = jb_env_flag("JB_UNIT_STREAMS", 1);
+      cudaStream_t st = w->serial ? w->stream : w->side[k][unit_streams ? u : 0];
+      if (!w->serial) CK(cudaStreamWaitEvent(st, w->ev_fork, 0));
+      if (u == 0) {
+        static const int skip_b = jb_env_flag("JB_TILES_SKIP_B", 0);
+        if (skip_b && mode == 0) a.mode = 2;
+        a.tile_group0 = T.tile_group0; a.tp_member = T.tp_member; a.tp_info = T.tp_info;
+        a.n_tiles = T.n_tiles; a.stream_base = T.stream_base;
+        if (T.mode == 2) { if (!multi) TRY((launch_tiles<true, 1>(w, a, st))); else TRY((launch_tiles<true, JB_MAX_VARIANTS>(w, a, st))); }
+        else { if (!multi) TRY((launch_tiles<false, 1>(w, a, st))); else TRY((launch_tiles<false, JB_MAX_VARIANTS>(w, a, st))); }
+      } else if (u == 1) {
+        a.group_list = T.list_w; a.n_list = T.n_w;
+        if (!multi) TRY((launch_list<1, 1>(w, a, false, st))); else TRY((launch_list<JB_MAX_VARIANTS, 1>(w, a, false, st)));
+      } else {
+        a.group_list = T.list_c; a.n_list = T.n_c;
+        if (!multi) TRY((launch_list<1, JB_CTA_WARPS>(w, a, sg.has_dynamic != 0, st)));
+        else TRY((launch_list<JB_MAX_VARIANTS, JB_CTA_WARPS>(w, a, sg.has_dynamic != 0, st)));
       }
-      if (T.n_big) {  // groups with more than 32 registered slots
-        a.group_list = T.big_list; a.n_list = T.n_big;
-        if (w->V == 1) TRY(launch_warp<1>(w, a, false, st)); else TRY(launch_warp<JB_MAX_VARIANTS>(w, a, false, st));
-        w->launches++;
+      w->launches++;
+      if (!w->serial) {
+        CK(cudaEventRecord(w->ev_join[k][u], st));
+        CK(cudaStreamWaitEvent(w->stream, w->ev_join[k][u], 0));
       }
     }
     CK(cudaGetLastError());
-    if (tme) { CK(cudaEventRecord(w->ev_sg1[k], st)); w->sg_pending[k] = true; }
-    if (!w->serial) {
-      CK(cudaEventRecord(w->ev_join[k], st));
-      CK(cudaStreamWaitEvent(w->stream, w->ev_join[k], 0));
-    }
+    if (tme) { CK(cudaEventRecord(w->ev_sg1[k], w->stream)); w->sg_pending[k] = true; }
   }
   return JB_OK;
 }
@@ -690,7 +707,7 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
   if (w->N) {
     PlaceArgs pa;
     memset(&pa, 0, sizeof(pa));
-    pa.pstate = w->pstate; pa.phas = w->phas; pa.pmed = w->pmed; pa.dyn_cnt = w->dyn_cnt; pa.dyn_bin = w->dyn_bin;
+    pa.pstate = w->pstate; pa.phot = w->phot; pa.pvar = w->V > 1 ? w->pvar : nullptr; pa.phas = w->phas; pa.pmed = w->pmed; pa.dyn_cnt = w->dyn_cnt; pa.dyn_bin = w->dyn_bin;
     pa.bin_cap = w->bin_cap; pa.counters = w->counters; pa.N = w->N; pa.sp = step_dev(w);
     for (size_t k = 0; k < w->sgs.size(); ++k)
       if (w->sgs[k].has_dynamic) {
@@ -703,11 +720,43 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     w->launches++;
   }
   if (w->n_out && d_send) {
-    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->pstate, w->pvar, w->susc, w->trans,
+    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->phot, w->susc, w->trans,
                                                        w->NP, (int)w->V, (unsigned char*)d_send);
     KCHECK("k_halo_pack", s);
     w->launches++;
   }
+  return JB_OK;
+}
+
+// The infections created in a step get their first health update from k_newinf itself, so
+// k_health only walks the slots that existed at step start.  Single-domain steps run both as one
+// launch (k_finish).  (With halos the step is three separately captured phases; when the host
+// creates the infections, JB_STEP_NO_NEW_INFECTIONS, k_health walks every slot.)
+static inline bool fused_finish(const JbWorld* w) {
+  return !(w->H || w->n_out) && !(w->cur.flags & JB_STEP_NO_NEW_INFECTIONS);
+}
+
+static HealthArgs make_health_args(JbWorld* w, int old_only) {
+  HealthArgs a;
+  memset(&a, 0, sizeof(a));
+  a.C = w->C; a.sp = step_dev(w); a.dis = w->dis; a.old_only = old_only;
+  a.masks.trans_type = w->dis_host.trans_type; a.masks.rec_mask = w->dis_host.rec_mask;
+  a.masks.dead_mask = w->dis_host.dead_mask; a.masks.hosp_mask = w->dis_host.hosp_mask;
+  a.masks.icu_mask = w->dis_host.icu_mask; a.masks.severe_mask = w->dis_host.severe_mask;
+  a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
+  a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
+  a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
+  a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
+  a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
+  a.summary = w->summary; a.R = (int)w->R;
+  return a;
+}
+
+static int launch_health(JbWorld* w, cudaStream_t s) {
+  const HealthArgs a = make_health_args(w, (w->cur.flags & JB_STEP_NO_NEW_INFECTIONS) ? 0 : 1);
+  k_health<<<148 * 4, 256, 0, s>>>(a);
+  KCHECK("k_health", s);
+  w->launches++;
   return JB_OK;
 }
 
@@ -716,7 +765,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   const JbStepParams& p = w->cur;
   if (w->H && d_recv) {
     k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
-                                                     w->pstate, w->pvar, w->susc, w->trans, (uint8_t*)d_ret_send);
+                                                     w->phot, w->susc, w->trans, (uint8_t*)d_ret_send);
     KCHECK("k_halo_unpack", s);
     w->launches++;
   }
@@ -736,8 +785,15 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_NEWINF;
     a.cap = w->newinf_cap; a.sp = step_dev(w);
     a.halo_ret = (uint8_t*)d_ret_send;
-    k_newinf<<<148 * 8, 128, 0, s>>>(a);
-    KCHECK("k_newinf", s);
+    a.fuse_health = 1; a.h = make_health_args(w, 0);
+    if (fused_finish(w)) {
+      a.h.old_only = 1;
+      k_finish<<<148 * 8 + 148 * 8, 128, 0, s>>>(a, 148 * 8);
+      KCHECK("k_finish", s);
+    } else {
+      k_newinf<<<148 * 8, 128, 0, s>>>(a);
+      KCHECK("k_newinf", s);
+    }
     w->launches++;
   }
   return JB_OK;
@@ -759,28 +815,13 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
       NewInfArgs a = make_newinf_args(w);
       a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_HALO_INF;
       a.cap = w->newinf_cap; a.sp = step_dev(w);
+      a.fuse_health = 1; a.h = make_health_args(w, 0);
       k_newinf<<<148 * 2, 128, 0, s>>>(a);
       KCHECK("k_newinf(halo)", s);
       w->launches++;
     }
   }
-  {
-    HealthArgs a;
-    memset(&a, 0, sizeof(a));
-    a.C = w->C; a.sp = step_dev(w); a.dis = w->dis;
-    a.masks.trans_type = w->dis_host.trans_type; a.masks.rec_mask = w->dis_host.rec_mask;
-    a.masks.dead_mask = w->dis_host.dead_mask; a.masks.hosp_mask = w->dis_host.hosp_mask;
-    a.masks.icu_mask = w->dis_host.icu_mask; a.masks.severe_mask = w->dis_host.severe_mask;
-    a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
-    a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
-    a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
-    a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
-    a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
-    a.summary = w->summary; a.R = (int)w->R;
-    k_health<<<148 * 4, 256, 0, s>>>(a);
-    KCHECK("k_health", s);
-    w->launches++;
-  }
+  if (!fused_finish(w)) TRY(launch_health(w, s));
   CK(cudaMemcpyAsync(w->h_counters, w->counters, (CNT_N + (size_t)w->R * JB_N_SUMMARY) * 4, cudaMemcpyDeviceToHost, s));
   return JB_OK;
 }
@@ -1003,7 +1044,12 @@ extern "C" int jb_fetch_person_state(JbWorld* w, uint8_t* pstate, int8_t* tag, d
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
   CK(cudaStreamSynchronize(w->stream));
-  if (pstate) TRY(fetch_permuted(w, w->pstate, pstate));
+  if (pstate) {  // ABI byte = activity of the last step (phot) | persistent flags (bits 3-6)
+    std::vector<uint8_t> hot(w->N_ext);
+    TRY(fetch_permuted(w, w->pstate, pstate));
+    TRY(fetch_permuted(w, w->phot, hot.data()));
+    for (uint32_t p = 0; p < w->N_ext; ++p) pstate[p] = (uint8_t)((pstate[p] & 0x78u) | (hot[p] & JB_PS_ACT_MASK));
+  }
   if (tag) TRY(fetch_permuted(w, w->ptag, tag));
   if (trans_prob) TRY(fetch_permuted(w, w->trans, trans_prob));
   if (susceptibility)
