@@ -14,8 +14,10 @@ Prints ONE JSON line on rank 0 (contract in the task statement):
             L2 flushed (256 MiB memset) between steps, max over ranks;
   e2e       the same K steps through the public API ``Simulator.do_timestep()``: per-step host
             parameters copied h2d from pinned memory, per-step statistics copied d2h, wall clock;
-  roofline  interaction kernel of the busiest supergroup: algorithmic bytes / CUDA-event time
-            against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+  roofline  interaction kernel of the busiest supergroup (households, k_tiles): SURVEY.md 8(d)
+            algorithmic bytes / CUDA-event time against the measured HBM copy bandwidth
+            (MEASURED_PEAKS.json); `traffic` = DRAM bytes per launch from the committed ncu capture
+            (profiles/traffic.json);
   cpu_baseline  the CPU oracle (oracle/june_oracle.c, a port of the reference algorithm) on the
             host cores, on a bounded sample of the same workload.
 ``--impl reference`` times that CPU port alone with all host threads.
@@ -131,12 +133,22 @@ def seed_epidemic(sim: Simulator, rank: int):
 
 
 def interaction_bytes(world, sg, n_present: int) -> int:
-    """Algorithmic bytes of one launch of the interaction kernel over supergroup ``sg``
-    (DESIGN.md section 4): every registered slot read once (member u32 + info u16 + person state
-    byte = 7 B), 8 B (transmission probability or susceptibility) per person present, one CSR
-    offset (4 B) per group.  New-infection output is O(#infections) and ignored."""
+    """Algorithmic bytes of one launch of the interaction kernel over supergroup ``sg``: SURVEY.md
+    section 8(d), ``A_inf = 14 N_present + 8 S_active + 8 G_active`` -- per present person the member
+    index (4), flags (1), susceptibility or transmission probability (8) and the result flag (1);
+    per non-empty subgroup its CSR offset and group id (8); per group its beta/spec/region word (8).
+    The figure is a property of the problem, not of this library's encoding (which reads fewer
+    bytes: DESIGN.md section 4).  Subgroups and groups are counted from the registrations and scaled
+    by the fraction of registered members present in the step."""
     lo, hi = int(world.grp_offset[sg.first_group]), int(world.grp_offset[sg.first_group + sg.n_groups])
-    return 7 * (hi - lo) + 4 * (sg.n_groups + 1) + 8 * n_present
+    n_reg = max(1, hi - lo)
+    grp_of = np.repeat(np.arange(sg.n_groups, dtype=np.int64),
+                       np.diff(world.grp_offset[sg.first_group: sg.first_group + sg.n_groups + 1].astype(np.int64)))
+    lsg = (world.reg_info[lo:hi] & 0xFF).astype(np.int64)
+    n_sub = int(np.unique(grp_of * 256 + lsg).size)
+    n_grp = int(np.unique(grp_of).size)
+    f = min(1.0, n_present / n_reg)
+    return int(14 * n_present + 8 * n_sub * f + 8 * n_grp * f)
 
 
 def run_gpu(args):
@@ -263,7 +275,7 @@ def run_gpu(args):
     a_bytes = interaction_bytes(world, sg, present)
     t_launch_s = per_sg[k_top]["ms"] / n_launch * 1e-3
     achieved = a_bytes / t_launch_s / 1e9 if t_launch_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": ("k_detect+k_process" if sg.launch_mode == 0 else "k_groups_warp"),
+    roofline = {"bound": "hbm", "kernel": ("k_tiles" if sg.launch_mode == 0 else "k_groups"),
                 "supergroup": sg.name, "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                 "bytes_per_launch": a_bytes, "us_per_launch": round(t_launch_s * 1e6, 2),
@@ -272,7 +284,7 @@ def run_gpu(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(roofline["kernel"])
+            roofline["traffic"] = json.load(open(traffic_file)).get(f"{roofline['kernel']}@{n_people}")
         except Exception:
             pass
 

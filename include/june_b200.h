@@ -109,7 +109,9 @@ typedef struct {
   int32_t cm_offset;     /* offset (in doubles) of the dim*dim row-major matrix in `cm`    */
   int32_t activity;      /* activity whose presence in the step activates this supergroup  */
   int32_t launch_mode;   /* 0 = one thread per group, 1 = one warp per group               */
-  int32_t has_dynamic;   /* groups of this supergroup may receive dynamic members          */
+  int32_t has_dynamic;   /* groups of this supergroup may receive dynamic members: 0 no,
+                          * 1 yes with JB_DYN_BIN_CAP entries per group and step, > 1 = that
+                          * capacity (rounded up to a power of two)                         */
 } JbSupergroup;
 
 /* Disease description: symptom trajectories + transmission sampler + outcome table.
@@ -178,7 +180,8 @@ typedef struct {
   uint32_t activity_mask;     /* bit a set if activity a is in timer.activities             */
   uint64_t seed;              /* Philox key                                                 */
   uint32_t flags;             /* JB_STEP_*                                                  */
-  uint32_t _pad;
+  uint32_t leisure_table;     /* 0 = no leisure probabilities this step, t + 1 = table t of
+                               * jb_set_leisure_tables                                      */
   /* processed beta per (beta index, region): get_processed_beta, interactive.py:154-177,
    * household.py:256-309, school.py:487-522.  Row-major [n_beta][n_regions]. */
   const double* beta;
@@ -189,6 +192,7 @@ typedef struct {
 #define JB_STEP_INJECT_UNIFORMS 0x4u  /* Bernoulli draws come from jb_inject_uniforms               */
 #define JB_STEP_NO_NEW_INFECTIONS 0x8u /* do not create infections on device (host uploads rows)    */
 #define JB_STEP_RECORD_LAMBDA 0x10u   /* keep per-person Lambda of this step for jb_fetch_lambda   */
+#define JB_STEP_INJECT_LEISURE 0x20u  /* leisure venues come from jb_inject_leisure (test mode)    */
 
 /* Per-step outputs (the d2h payload of every step). */
 typedef struct {
@@ -268,6 +272,32 @@ int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* stats_out);
 int jb_set_halo(JbWorld* w, const uint32_t* out_person, size_t n_out);
 size_t jb_halo_record_size(void);   /* bytes per person in d_send / d_recv       */
 size_t jb_halo_return_size(void);   /* bytes per person in d_ret_send / d_ret_recv */
+
+/* ---- leisure (groups/leisure/leisure.py:205-275, social_venue_distributor.py:257-278) ----
+ * K leisure activities in the reference's distributor order.  Activity k sends a person to one
+ * of the venues its AREA lists for k (`area.social_venues[spec]`), as a dynamic member of local
+ * subgroup `subgroup[k]` of a group of supergroup `supergroup[k]` (which must have has_dynamic
+ * set).  `area_off` is a CSR over (area, activity), index area * K + k, into `area_venue` (group
+ * indices).  Care-home residents never do leisure (leisure.py:246-248). */
+#define JB_MAX_LEISURE 8
+typedef struct {
+  uint32_t n_activities;       /* K <= JB_MAX_LEISURE                                        */
+  uint32_t n_areas;
+  const int32_t* supergroup;   /* [K]                                                        */
+  const int32_t* subgroup;     /* [K] leisure_subgroup_type                                  */
+  const uint32_t* person_area; /* [n_people]                                                 */
+  const uint32_t* area_off;    /* [n_areas * K + 1]                                          */
+  const uint32_t* area_venue;  /* [area_off[n_areas * K]] group indices                      */
+} JbLeisureDesc;
+int jb_set_leisure(JbWorld* w, const JbLeisureDesc* desc);
+/* Probability tables (Leisure.generate_leisure_probabilities_for_timestep, leisure.py:205-228,
+ * 297-372): table t holds does[n_regions][2 (f, m)][100] = P(does any activity) and
+ * cum[n_regions][2][100][K] = cumulative P(activity | does).  JbStepParams.leisure_table picks
+ * one per step. */
+int jb_set_leisure_tables(JbWorld* w, uint32_t n_tables, const double* does, const double* cum);
+/* Test mode (JB_STEP_INJECT_LEISURE): the venue of every person for the next step, -1 = none;
+ * replaces the three random choices of leisure.py:253-263 / social_venue_distributor.py:257-266. */
+int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person);
 
 int jb_sync(JbWorld* w);
 

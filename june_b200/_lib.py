@@ -23,7 +23,7 @@ ABI_VERSION = 1
 
 JB_OK, JB_EINVAL, JB_ECUDA, JB_ENOACT, JB_ECAP, JB_ENOGPU = 0, 1, 2, 3, 4, 5
 STEP_SEVERE_STAY_HOME, STEP_HOSPITALISATION, STEP_INJECT_UNIFORMS = 0x1, 0x2, 0x4
-STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA = 0x8, 0x10
+STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE = 0x8, 0x10, 0x20
 
 
 class SimulatorError(BaseException):
@@ -70,7 +70,13 @@ class JbWorldDesc(C.Structure):
 
 class JbStepParams(C.Structure):
     _fields_ = [("now", C.c_double), ("delta_time", C.c_double), ("step", C.c_uint32), ("activity_mask", C.c_uint32),
-                ("seed", C.c_uint64), ("flags", C.c_uint32), ("_pad", C.c_uint32), ("beta", C.c_void_p)]
+                ("seed", C.c_uint64), ("flags", C.c_uint32), ("leisure_table", C.c_uint32), ("beta", C.c_void_p)]
+
+
+class JbLeisureDesc(C.Structure):
+    _fields_ = [("n_activities", C.c_uint32), ("n_areas", C.c_uint32), ("supergroup", C.c_void_p),
+                ("subgroup", C.c_void_p), ("person_area", C.c_void_p), ("area_off", C.c_void_p),
+                ("area_venue", C.c_void_p)]
 
 
 class JbStepStats(C.Structure):
@@ -97,7 +103,7 @@ ABI_SYMBOLS = [
     "inject_uniforms", "infect", "upload_infections", "step", "step_begin", "step_interact", "step_finish",
     "set_halo", "halo_record_size", "halo_return_size", "sync", "fetch_new_infections", "fetch_person_state",
     "fetch_lambda", "fetch_infections", "fetch_summary", "timing_enable", "timing_read", "last_step_bytes",
-    "set_concurrency",
+    "set_concurrency", "set_leisure", "set_leisure_tables", "inject_leisure",
 ]
 
 
@@ -150,6 +156,9 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("timing_enable").argtypes = [vp, C.c_int]
     f("timing_read").argtypes = [vp, dp, dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
     f("last_step_bytes").argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    f("set_leisure").argtypes = [vp, C.POINTER(JbLeisureDesc)]
+    f("set_leisure_tables").argtypes = [vp, C.c_uint32, vp, vp]
+    f("inject_leisure").argtypes = [vp, vp]
     for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp]),
                         ("timing_read_supergroups", [vp, dp, C.POINTER(C.c_uint64), C.c_int]),
                         ("set_concurrency", [vp, C.c_int])):

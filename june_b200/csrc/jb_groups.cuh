@@ -128,12 +128,11 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
   if (a.dyn_cnt) {
     // stage this group's bin and sort it: members arrive in arbitrary (atomic) order, the
     // reference order is (subgroup, person) -- bitonic sort in shared memory
-    const uint32_t bin = a.dyn_bin_base + (g - a.g0);
-    nd = min(a.dyn_cnt[bin], bin_cap);
+    nd = min(a.dyn_cnt[a.dyn_bin_base + (g - a.g0)], bin_cap);
     if (nd) {
       uint32_t npad = 32;
       while (npad < nd) npad <<= 1;
-      const uint32_t* src = a.dyn_bin + (size_t)bin * bin_cap;
+      const uint32_t* src = a.dyn_bin + (size_t)(g - a.g0) * bin_cap;  // dyn_bin = the supergroup's first bin
       for (uint32_t i = tg; i < npad; i += GT) dyn_s[i] = i < nd ? src[i] : 0xFFFFFFFFu;
       jb_grp_sync<WPG>();
       for (uint32_t k = 2; k <= npad; k <<= 1)

@@ -57,6 +57,29 @@ enum { SUM_NEW_INFECTED = 0, SUM_CUR_INFECTED, SUM_CUR_HOSP, SUM_CUR_ICU, SUM_DE
 #define JB_TI_LSG(x) (((x) >> 5) & 3u)
 #define JB_TI_ACT(x) ((x) & 7u)
 
+// Dynamic-member bins: one bin of `cap` entries per group of every supergroup with has_dynamic.
+#define JB_MAX_DYN_RANGES 12
+struct DynRanges {
+  uint32_t n;
+  uint32_t first[JB_MAX_DYN_RANGES], count[JB_MAX_DYN_RANGES];  // group range of the supergroup
+  uint32_t cnt_base[JB_MAX_DYN_RANGES];   // index of the range's first counter in dyn_cnt
+  uint32_t slot_base[JB_MAX_DYN_RANGES];  // offset of the range's first bin in dyn_bin (entries)
+  uint32_t cap[JB_MAX_DYN_RANGES];        // entries per bin (power of two)
+};
+
+// Leisure tables on the device (jb_set_leisure / jb_set_leisure_tables).
+struct LeisureDev {
+  uint32_t K, n_tables;
+  const uint32_t* parea;   // [N] internal numbering
+  const uint32_t* off;     // [(areas * K) + 1]
+  const uint32_t* venue;
+  const double* does;      // [tables][R][2][100]
+  const double* cum;       // [tables][R][2][100][K]
+  const int32_t* inject;   // [N] venue per person (test mode) or null
+  uint32_t sg_first[JB_MAX_LEISURE], sg_count[JB_MAX_LEISURE];
+  int32_t lsg[JB_MAX_LEISURE];
+};
+
 // Per-step scalars, resident on the device so that a captured CUDA graph of the step can be
 // replayed: one h2d copy from a pinned ring buffer precedes every step.  The processed beta
 // table [n_beta][n_regions] follows the struct in the same allocation.
@@ -64,6 +87,7 @@ struct StepDev {
   double now, dt, t_now;
   uint64_t seed;
   uint32_t step, activity_mask, flags, n_inject;
+  uint32_t leisure_table, pad_[3];
 };
 
 // Arguments of the interaction (group) kernels; passed by value as a __grid_constant__.
@@ -190,8 +214,16 @@ struct JbWorld {
   size_t inject_cap = 0, n_inject = 0;
   uint32_t *draw_cnt = nullptr, *draw_base = nullptr;
   uint32_t *dyn_cnt = nullptr, *dyn_bin = nullptr;
-  uint32_t n_bins = 0, bin_cap = 0;
-  uint32_t sg_bin_base[JB_MAX_SUPERGROUPS] = {};
+  uint32_t n_bins = 0;
+  uint32_t sg_bin_base[JB_MAX_SUPERGROUPS] = {};   // first counter of the supergroup in dyn_cnt
+  uint32_t sg_bin_slot[JB_MAX_SUPERGROUPS] = {};   // first entry of the supergroup in dyn_bin
+  uint32_t sg_bin_cap[JB_MAX_SUPERGROUPS] = {};    // entries per bin
+  DynRanges dyn_ranges = {};
+  // leisure
+  LeisureDev lz = {};
+  uint32_t *lz_parea = nullptr, *lz_off = nullptr, *lz_venue = nullptr;
+  double *lz_does = nullptr, *lz_cum = nullptr;
+  int32_t* lz_inject = nullptr;
   bool any_dynamic = false;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;

@@ -28,11 +28,6 @@
 // 16 persons per thread (one 128-bit load of each byte array), grid-stride, counters reduced in
 // registers -> shared memory -> one global atomic per block and counter.
 // ------------------------------------------------------------------------------------------
-struct DynRanges {
-  uint32_t n;
-  uint32_t first[4], count[4], bin_base[4];
-};
-
 struct PlaceArgs {
   const uint8_t* pstate;
   uint8_t* phot;
@@ -40,13 +35,64 @@ struct PlaceArgs {
   const uint8_t* phas;
   const int32_t* pmed;
   uint32_t* dyn_cnt;   // per dynamic group: members appended this step
-  uint32_t* dyn_bin;   // [n_bins][bin_cap] entries (lsg << 28) | person
-  uint32_t bin_cap;
+  uint32_t* dyn_bin;   // bins of (lsg << 28) | person entries
   DynRanges dr;
   uint32_t* counters;
   uint32_t N;
   const StepDev* sp;
+  // leisure
+  LeisureDev lz;
+  const uint8_t* age; const uint8_t* sex; const uint8_t* ch; const uint8_t* pregion;
+  const uint32_t* int2ext;
+  uint32_t gid_base;
+  int R;
 };
+
+// Append person p to the bin of dynamic group g (hospital ward, leisure venue).
+__device__ __forceinline__ void jb_dyn_scatter(const PlaceArgs& a, uint32_t g, uint32_t lsg, uint32_t p) {
+  for (uint32_t r = 0; r < a.dr.n; ++r) {
+    const uint32_t k = g - a.dr.first[r];
+    if (k < a.dr.count[r]) {
+      const uint32_t i = atomicAdd(&a.dyn_cnt[a.dr.cnt_base[r] + k], 1u);
+      if (i < a.dr.cap[r]) { a.dyn_bin[(size_t)a.dr.slot_base[r] + (size_t)k * a.dr.cap[r] + i] = (lsg << 28) | p; return; }
+      break;
+    }
+  }
+  atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+}
+
+// Leisure.get_subgroup_for_person_and_housemates (leisure.py:230-275) for social venues: does the
+// person go out, which activity, which of its area's candidate venues
+// (social_venue_distributor.py:257-266).  Returns the venue group (and its subgroup) or -1.
+__device__ __forceinline__ int32_t jb_leisure_venue(const PlaceArgs& a, uint32_t p, uint32_t& lsg) {
+  const LeisureDev& z = a.lz;
+  if (a.ch[p]) return -1;  // care-home residents stay (leisure.py:246-248)
+  if (z.inject) {
+    const int32_t g = z.inject[p];
+    if (g < 0) return -1;
+    for (uint32_t k = 0; k < z.K; ++k)
+      if ((uint32_t)g - z.sg_first[k] < z.sg_count[k]) { lsg = (uint32_t)z.lsg[k]; return g; }
+    return -1;
+  }
+  const uint32_t K = z.K, tab = a.sp->leisure_table;
+  if (!tab || tab > z.n_tables) return -1;
+  const uint32_t age = min((uint32_t)a.age[p], 99u);
+  const size_t row = ((size_t)(tab - 1) * a.R + a.pregion[p]) * 200 + (size_t)a.sex[p] * 100 + age;
+  const uint32_t gid = a.gid_base + a.int2ext[p];
+  const JbPhilox4 r0 = jb_philox4x32_10(gid, a.sp->step, JB_STREAM_LEISURE, 0u, (uint32_t)a.sp->seed, (uint32_t)(a.sp->seed >> 32));
+  if (!(jb_u52(r0.x[0], r0.x[1]) < z.does[row])) return -1;
+  const double u_act = jb_u52(r0.x[2], r0.x[3]);
+  const double* cum = z.cum + row * K;
+  uint32_t k = 0;
+  while (k + 1 < K && !(u_act < cum[k])) ++k;
+  const uint32_t o = z.off[(size_t)z.parea[p] * K + k], n = z.off[(size_t)z.parea[p] * K + k + 1] - o;
+  if (n == 0) return -1;  // get_leisure_group returns None: the person falls through to residence
+  const JbPhilox4 r1 = jb_philox4x32_10(gid, a.sp->step, JB_STREAM_LEISURE, 1u, (uint32_t)a.sp->seed, (uint32_t)(a.sp->seed >> 32));
+  uint32_t j = (uint32_t)(jb_u52(r1.x[0], r1.x[1]) * (double)n);
+  if (j >= n) j = n - 1;
+  lsg = (uint32_t)z.lsg[k];
+  return (int32_t)z.venue[o + j];
+}
 
 // activity chosen for a person byte: pure function of (dead, severe, has-medical, fixed
 // activities) and of the step's activity mask / policy flags -> 512-entry table per block
@@ -58,6 +104,7 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
   __shared__ uint8_t s_act[512];      // 0..4 activity, 7 none (dead), 15 alive without any activity
   __shared__ uint32_t s_cnt[8];
   const uint32_t mask = a.sp->activity_mask, flags = a.sp->flags;
+  const bool leisure_on = a.lz.K != 0 && (a.lz.inject != nullptr || a.sp->leisure_table != 0);
   for (uint32_t k = threadIdx.x; k < 512; k += blockDim.x) {
     const uint32_t bits = k >> 5, has0 = k & 0x1Fu;
     const bool dead = bits & 2u, severe = bits & 4u, med = bits & 8u;
@@ -67,6 +114,9 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
       if ((flags & JB_STEP_SEVERE_STAY_HOME) && severe) allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
       const uint32_t cand = allowed & (has0 | (med ? 1u << JB_ACT_MEDICAL : 0u));
       act = cand ? (uint32_t)__ffs(cand) - 1u : 15u;  // hierarchy order == bit order
+      // leisure has no fixed subgroup: it is drawn per person when nothing above it in the
+      // hierarchy applies (activity_manager.py:380-398) -> flag bit 7, resolved below
+      if (leisure_on && (allowed & (1u << JB_ACT_LEISURE)) && !(cand & ((1u << JB_ACT_LEISURE) - 1u))) act |= 0x80u;
     }
     s_act[k] = (uint8_t)act;
   }
@@ -80,21 +130,17 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
   const uint32_t n_chunks = (a.N + 15) / 16;
   auto one = [&](uint32_t p, uint32_t st, uint32_t has) -> uint32_t {
     uint32_t act = s_act[jb_place_key(st, has)];
+    if (act & 0x80u) {  // leisure draw
+      act &= 0x7Fu;
+      uint32_t lsg = 0;
+      const int32_t g = jb_leisure_venue(a, p, lsg);
+      if (g >= 0) { act = JB_ACT_LEISURE; jb_dyn_scatter(a, (uint32_t)g, lsg, p); }
+    }
     if (act == 15u) { ++noact; act = JB_ACT_NONE; }
     cnt += 1ull << (8 * act);
     if (act == JB_ACT_MEDICAL) {  // rare: scatter the patient into its ward's bin
       const uint32_t med = (uint32_t)a.pmed[p];  // (hospital group << 8) | local subgroup
-      const uint32_t g = med >> 8;
-      bool okb = false;
-      for (uint32_t r = 0; r < a.dr.n; ++r) {
-        if (g - a.dr.first[r] < a.dr.count[r]) {
-          const uint32_t bin = a.dr.bin_base[r] + (g - a.dr.first[r]);
-          const uint32_t i = atomicAdd(&a.dyn_cnt[bin], 1u);
-          if (i < a.bin_cap) { a.dyn_bin[(size_t)bin * a.bin_cap + i] = ((med & 0xFu) << 28) | p; okb = true; }
-          break;
-        }
-      }
-      if (!okb) atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+      jb_dyn_scatter(a, med >> 8, med & 0xFu, p);
     }
     // the step's hot byte: activity | INFECTED | susceptibility code | variant
     return act | (st & JB_PS_INFECTED) | ((st & JB_PST_CODE_MASK) << 4) | (a.pvar ? (uint32_t)a.pvar[p] << 6 : 0u);

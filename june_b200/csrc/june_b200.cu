@@ -266,8 +266,26 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   CK(cudaMemsetAsync(w->inf_person, 0xFF, C * 4, s));
 
   // counters | per-region summary | dynamic-bin counts: one block, one memset per step
-  for (size_t k = 0; k < w->sgs.size(); ++k)
-    if (w->sgs[k].has_dynamic) { w->sg_bin_base[k] = w->n_bins; w->n_bins += w->sgs[k].n_groups; }
+  {
+    size_t slots = 0;
+    for (size_t k = 0; k < w->sgs.size(); ++k) {
+      if (!w->sgs[k].has_dynamic) continue;
+      uint32_t cap = w->sgs[k].has_dynamic == 1 ? JB_DYN_BIN_CAP : (uint32_t)w->sgs[k].has_dynamic;
+      uint32_t c2 = 32;
+      while (c2 < cap) c2 <<= 1;  // the bin is sorted with a bitonic network
+      REQUIRE(c2 <= 8192, "dynamic bin capacity above 8192 (shared-memory sort)");
+      REQUIRE(w->dyn_ranges.n < JB_MAX_DYN_RANGES, "too many supergroups with dynamic members");
+      REQUIRE(slots + (size_t)w->sgs[k].n_groups * c2 < (1ull << 32), "dynamic bins exceed 2^32 entries");
+      w->sg_bin_base[k] = w->n_bins; w->sg_bin_slot[k] = (uint32_t)slots; w->sg_bin_cap[k] = c2;
+      DynRanges& dr = w->dyn_ranges;
+      const uint32_t r = dr.n++;
+      dr.first[r] = w->sgs[k].first_group; dr.count[r] = w->sgs[k].n_groups;
+      dr.cnt_base[r] = w->n_bins; dr.slot_base[r] = (uint32_t)slots; dr.cap[r] = c2;
+      w->n_bins += w->sgs[k].n_groups;
+      slots += (size_t)w->sgs[k].n_groups * c2;
+    }
+    if (slots) TRY(dev_alloc(&w->dyn_bin, slots));
+  }
   w->counter_words = (size_t)CNT_N + (size_t)w->R * JB_N_SUMMARY + w->n_bins;
   TRY(dev_alloc(&w->counters, w->counter_words));
   CK(cudaMemsetAsync(w->counters, 0, w->counter_words * 4, s));
@@ -289,16 +307,6 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   w->beta = reinterpret_cast<double*>(w->d_step + sizeof(StepDev));
   TRY(dev_alloc(&w->draw_cnt, (size_t)w->G + 1));
   TRY(dev_alloc(&w->draw_base, (size_t)w->G + 1));
-  if (w->any_dynamic) {
-    // one bin of JB_DYN_BIN_CAP entries per group of a dynamic supergroup (hospital wards)
-    w->bin_cap = JB_DYN_BIN_CAP;
-    int n_ranges = 0;
-    for (size_t k = 0; k < w->sgs.size(); ++k)
-      if (w->sgs[k].has_dynamic) ++n_ranges;
-    REQUIRE(n_ranges <= 4, "at most 4 supergroups may have dynamic members");
-    REQUIRE(w->n_bins <= 65536, "too many groups with dynamic members (bins are per group)");
-    TRY(dev_alloc(&w->dyn_bin, (size_t)w->n_bins * w->bin_cap));
-  }
   {
     size_t b2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, b2, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(w->G + 1), s);
@@ -348,7 +356,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
-                  w->cub_tmp, w->int2ext};
+                  w->cub_tmp, w->int2ext, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (SgTiles& t : w->tiles) {
@@ -423,6 +431,70 @@ extern "C" int jb_inject_uniforms(JbWorld* w, const double* u, size_t n) {
   if (n) CK(cudaMemcpyAsync(w->inject, u, n * 8, cudaMemcpyHostToDevice, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   w->n_inject = n;
+  return JB_OK;
+}
+
+// ---- leisure set-up -------------------------------------------------------------------------
+static void drop_graphs(JbWorld* w) {  // captured launches hold kernel arguments by value
+  for (JbWorld::GraphEntry& e : w->graphs) cudaGraphExecDestroy(e.exec);
+  w->graphs.clear();
+}
+
+extern "C" int jb_set_leisure(JbWorld* w, const JbLeisureDesc* d) {
+  if (!w || !d) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(d->n_activities >= 1 && d->n_activities <= JB_MAX_LEISURE, "n_activities out of range");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);
+  LeisureDev& z = w->lz;
+  const uint32_t K = d->n_activities;
+  for (uint32_t k = 0; k < K; ++k) {
+    REQUIRE(d->supergroup[k] >= 0 && (size_t)d->supergroup[k] < w->sgs.size() && w->sgs[d->supergroup[k]].has_dynamic,
+            "leisure supergroup must exist and have dynamic members");
+    REQUIRE(d->subgroup[k] >= 0 && d->subgroup[k] < 16, "leisure subgroup out of range");
+    z.sg_first[k] = w->sgs[d->supergroup[k]].first_group; z.sg_count[k] = w->sgs[d->supergroup[k]].n_groups;
+    z.lsg[k] = d->subgroup[k];
+  }
+  const size_t n_off = (size_t)d->n_areas * K + 1;
+  std::vector<uint32_t> pa(std::max(1u, w->N), 0);
+  for (uint32_t p = 0; p < w->N_ext; ++p) {
+    REQUIRE(d->person_area[p] < d->n_areas, "person_area out of range");
+    pa[w->h_ext2int[p]] = d->person_area[p];
+  }
+  for (size_t i = 0; i < d->area_off[n_off - 1]; ++i) REQUIRE(d->area_venue[i] < w->G, "area_venue out of range");
+  for (uint32_t* q : {w->lz_parea, w->lz_off, w->lz_venue}) if (q) cudaFree(q);
+  TRY(dev_upload(&w->lz_parea, pa.data(), pa.size(), w->stream));
+  TRY(dev_upload(&w->lz_off, d->area_off, n_off, w->stream));
+  TRY(dev_upload(&w->lz_venue, d->area_venue, (size_t)d->area_off[n_off - 1], w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  z.K = K; z.parea = w->lz_parea; z.off = w->lz_off; z.venue = w->lz_venue;
+  return JB_OK;
+}
+
+extern "C" int jb_set_leisure_tables(JbWorld* w, uint32_t n_tables, const double* does, const double* cum) {
+  if (!w || !does || !cum) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(w->lz.K != 0, "jb_set_leisure_tables before jb_set_leisure");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);
+  if (w->lz_does) cudaFree(w->lz_does);
+  if (w->lz_cum) cudaFree(w->lz_cum);
+  const size_t per = (size_t)w->R * 200;
+  TRY(dev_upload(&w->lz_does, does, per * n_tables, w->stream));
+  TRY(dev_upload(&w->lz_cum, cum, per * w->lz.K * n_tables, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  w->lz.does = w->lz_does; w->lz.cum = w->lz_cum; w->lz.n_tables = n_tables;
+  return JB_OK;
+}
+
+extern "C" int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person) {
+  if (!w || !group_per_person) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  std::vector<int32_t> v(std::max(1u, w->N), -1);
+  for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = group_per_person[p];
+  if (!w->lz_inject) { TRY(dev_alloc(&w->lz_inject, v.size())); drop_graphs(w); }
+  CK(cudaMemcpy(w->lz_inject, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
   return JB_OK;
 }
 
@@ -591,9 +663,10 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   a.phot = w->phot; a.susc = w->susc; a.trans = w->trans; a.halo_gid = w->halo_gid;
   a.school_years = w->school_years; a.cm = w->cm + sg.cm_offset; a.beta = w->beta; a.beta_scale = w->beta_scale;
   a.dyn_cnt = sg.has_dynamic ? w->dyn_cnt : nullptr;
-  a.dyn_bin = sg.has_dynamic ? w->dyn_bin : nullptr;
-  a.bin_cap = w->bin_cap;
-  a.dyn_bin_base = w->sg_bin_base[&sg - w->sgs.data()];
+  const size_t ksg = &sg - w->sgs.data();
+  a.dyn_bin = sg.has_dynamic ? w->dyn_bin + w->sg_bin_slot[ksg] : nullptr;  // the supergroup's first bin
+  a.bin_cap = w->sg_bin_cap[ksg];
+  a.dyn_bin_base = w->sg_bin_base[ksg];
   a.g0 = sg.first_group; a.g1 = sg.first_group + sg.n_groups;
   a.group_list = nullptr; a.n_list = sg.n_groups; a.int2ext = w->int2ext;
   a.dim = sg.dim; a.kind = sg.kind; a.L = L;
@@ -614,7 +687,7 @@ template <int VM, int WPG>
 static int launch_list(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_t st) {
   if (a.n_list == 0) return JB_OK;
   constexpr int gpc = JB_CTA_WARPS / WPG;
-  const size_t smem = jb_grp_smem_bytes(a.L, (int)w->V, dynamic ? w->bin_cap : 0u, WPG) * gpc;
+  const size_t smem = jb_grp_smem_bytes(a.L, (int)w->V, dynamic ? a.bin_cap : 0u, WPG) * gpc;
   k_groups<VM, WPG><<<(a.n_list + gpc - 1) / gpc, JB_CTA, smem, st>>>(a);
   KCHECK(WPG == 1 ? "k_groups<warp>" : "k_groups<cta>", st);
   return JB_OK;
@@ -708,12 +781,13 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     PlaceArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.pstate = w->pstate; pa.phot = w->phot; pa.pvar = w->V > 1 ? w->pvar : nullptr; pa.phas = w->phas; pa.pmed = w->pmed; pa.dyn_cnt = w->dyn_cnt; pa.dyn_bin = w->dyn_bin;
-    pa.bin_cap = w->bin_cap; pa.counters = w->counters; pa.N = w->N; pa.sp = step_dev(w);
-    for (size_t k = 0; k < w->sgs.size(); ++k)
-      if (w->sgs[k].has_dynamic) {
-        uint32_t r = pa.dr.n++;
-        pa.dr.first[r] = w->sgs[k].first_group; pa.dr.count[r] = w->sgs[k].n_groups; pa.dr.bin_base[r] = w->sg_bin_base[k];
-      }
+    pa.counters = w->counters; pa.N = w->N; pa.sp = step_dev(w);
+    pa.dr = w->dyn_ranges;
+    pa.lz = w->lz;
+    pa.lz.inject = (p.flags & JB_STEP_INJECT_LEISURE) ? w->lz_inject : nullptr;
+    if ((p.flags & JB_STEP_INJECT_LEISURE) && !w->lz_inject) { jb_set_error("JB_STEP_INJECT_LEISURE without jb_inject_leisure"); return JB_EINVAL; }
+    pa.age = w->age; pa.sex = w->sex; pa.ch = w->ch; pa.pregion = w->pregion; pa.int2ext = w->int2ext;
+    pa.gid_base = (uint32_t)w->id_base; pa.R = (int)w->R;
     const uint32_t chunks = (w->N + 15) / 16;
     k_place<<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     KCHECK("k_place", s);
@@ -877,7 +951,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));  // the copy that last used this slot has finished
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
-  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
   CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(w->ev_step_buf[slot], s));
@@ -953,7 +1027,7 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
-  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
   CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(w->ev_step_buf[slot], s));

@@ -12,8 +12,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (JbDisease, JbDist, JbInfectionRow, JbStepParams, JbStepStats, JbSupergroup, JbWorldDesc,
-                   SimulatorError, ptr)
+from ._lib import (JbDisease, JbDist, JbInfectionRow, JbLeisureDesc, JbStepParams, JbStepStats, JbSupergroup,
+                   JbWorldDesc, SimulatorError, ptr)
 from .disease import DiseaseConfig, health_index_cum
 from .interaction import Interaction
 from .world import KIND_SCHOOL, MAX_STAGES, N_TPAR, SCHOOL_DIM, WorldSoA
@@ -104,12 +104,43 @@ class Engine:
         handle = C.c_void_p()
         self._check(self._f("world_create")(C.byref(d), device, C.byref(handle)))
         self._h = handle
+        if world.has_leisure:
+            self._set_leisure(world)
         if world.n_halo:
             hg = np.ascontiguousarray(world.halo_gid, dtype=np.uint32)
             self._check(self._f("set_halo_gids")(self._h, ptr(hg), hg.size))
         if world.out_person.size:
             op = np.ascontiguousarray(world.out_person, dtype=np.uint32)
             self._check(self._f("set_halo")(self._h, ptr(op), op.size))
+
+    # ---- leisure --------------------------------------------------------------------------------
+    def _set_leisure(self, world: WorldSoA):
+        names = [sg.name for sg in world.supergroups]
+        K = len(world.leisure_activities)
+        sgi = np.array([names.index(n) for n in world.leisure_supergroups], np.int32)
+        lsg = np.array(world.leisure_subgroups, np.int32)
+        pa = np.ascontiguousarray(world.person_area, dtype=np.uint32)
+        off = np.ascontiguousarray(world.area_venue_off, dtype=np.uint32)
+        ven = np.ascontiguousarray(world.area_venue, dtype=np.uint32)
+        assert off.size == world.n_areas * K + 1 and int(off[-1]) == ven.size
+        d = JbLeisureDesc()
+        d.n_activities, d.n_areas = K, world.n_areas
+        d.supergroup, d.subgroup = sgi.ctypes.data, lsg.ctypes.data
+        d.person_area, d.area_off, d.area_venue = pa.ctypes.data, off.ctypes.data, (ven if ven.size else np.zeros(1, np.uint32)).ctypes.data
+        self._check(self._f("set_leisure")(self._h, C.byref(d)))
+
+    def set_leisure_tables(self, does: np.ndarray, cum: np.ndarray):
+        """``does[T][R][2][100]``, ``cum[T][R][2][100][K]`` (see ``june_b200.leisure``)."""
+        does = np.ascontiguousarray(does, dtype=np.float64)
+        cum = np.ascontiguousarray(cum, dtype=np.float64)
+        K = len(self.world.leisure_activities)
+        assert does.shape[1:] == (self.world.n_regions, 2, 100) and cum.shape == does.shape + (K,)
+        self._check(self._f("set_leisure_tables")(self._h, does.shape[0], ptr(does), ptr(cum)))
+
+    def inject_leisure(self, group_per_person: np.ndarray):
+        g = np.ascontiguousarray(group_per_person, dtype=np.int32)
+        assert g.shape == (self.world.n_people,)
+        self._check(self._f("inject_leisure")(self._h, ptr(g)))
 
     # ---- plumbing ------------------------------------------------------------------------------
     def _f(self, name):
@@ -175,12 +206,12 @@ class Engine:
 
     # ---- stepping --------------------------------------------------------------------------------
     def make_params(self, now: float, delta_time: float, step: int, activity_mask: int, seed: int, flags: int,
-                    beta: np.ndarray) -> JbStepParams:
+                    beta: np.ndarray, leisure_table: int = 0) -> JbStepParams:
         beta = np.ascontiguousarray(beta, dtype=np.float64)
         assert beta.shape == (len(self.world.beta_rules), self.world.n_regions), beta.shape
         p = JbStepParams()
         p.now, p.delta_time, p.step, p.activity_mask = float(now), float(delta_time), int(step), int(activity_mask)
-        p.seed, p.flags = int(seed), int(flags)
+        p.seed, p.flags, p.leisure_table = int(seed), int(flags), int(leisure_table)
         p.beta = beta.ctypes.data
         p._beta_keep = beta
         return p

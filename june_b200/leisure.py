@@ -1,0 +1,196 @@
+"""Host half of the reference's leisure model (``june/groups/leisure/leisure.py:125-372``,
+``social_venue_distributor.py:24-215``): configuration and the per-time-slot probability tables.
+
+The per-person part -- does the person go out, which activity, which of the venues its area
+lists (``leisure.py:230-275``, ``social_venue_distributor.py:257-278``) -- runs inside the placement
+kernel; this module only produces, per time slot, the two tables the kernel looks up::
+
+    does[region][sex][age]          = 1 - exp(-delta_t * sum_k lambda_k)          (leisure.py:338)
+    cum[region][sex][age][k]        = cumulative lambda_k / sum lambda             (leisure.py:342-349)
+
+with the reference's Poisson parameters ``lambda_k = times_per_week / n_days * 24 / hours_per_day``
+(``social_venue_distributor.py:143-149``), opening hours (``leisure.py:402-408``), regional
+compliance / closed venues (``:183-205``) and leisure-policy reductions (``:410-413``).
+
+Covered: social venues (pubs, cinemas, groceries, gyms: one leisure subgroup per venue).
+Not covered yet: residence visits (``residence_visits.py``; their placement has order-dependent side
+effects on the visited household) and friend invitations.
+"""
+from __future__ import annotations
+
+import datetime
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import yaml
+
+from .interaction import load_defaults
+
+DEFAULT_DAYTYPES = {"weekday": ["Monday", "Tuesday", "Wednesday", "Thursday", "Friday"],
+                    "weekend": ["Saturday", "Sunday"]}
+_DAY_NAMES = ["Monday", "Tuesday", "Wednesday", "Thursday", "Friday", "Saturday", "Sunday"]
+SEXES = ("f", "m")  # device sex byte: 0 = f, 1 = m
+
+
+def parse_age_probabilities(age_dict: Optional[dict], fill_value: float = 0.0) -> List[float]:
+    """``{"a-b": v}`` -> 100 per-age values, ``a <= age < b`` (``utils/parse_probabilities.py:6-34``)."""
+    out = [fill_value] * 100
+    if not age_dict:
+        return out
+    for key, v in age_dict.items():
+        lo, hi = (int(x) for x in str(key).split("-"))
+        for age in range(max(0, lo), min(100, hi)):
+            out[age] = v
+    return out
+
+
+def parse_opens(opens: Dict[str, str]) -> Dict[str, List[int]]:
+    return {k: [int(x) for x in v.split("-")] for k, v in opens.items()}
+
+
+class SocialVenueDistributor:
+    """Configuration of one leisure activity (``social_venue_distributor.py:24-215``)."""
+
+    spec = "social_venue"
+    config_key: Optional[str] = None
+
+    def __init__(self, social_venues=None, times_per_week: Optional[dict] = None, daytypes: dict = DEFAULT_DAYTYPES,
+                 hours_per_day: Optional[dict] = None, drags_household_probability: float = 0.0,
+                 invites_friends_probability: float = 0.0, neighbours_to_consider: int = 5, maximum_distance: float = 5,
+                 leisure_subgroup_type: int = 0, nearest_venues_to_visit: int = 0, open: Optional[dict] = None):
+        self.social_venues = social_venues
+        self.daytypes = daytypes
+        self.drags_household_probability = drags_household_probability
+        self.invites_friends_probability = invites_friends_probability
+        self.neighbours_to_consider = neighbours_to_consider
+        self.maximum_distance = maximum_distance
+        self.leisure_subgroup_type = leisure_subgroup_type
+        self.nearest_venues_to_visit = nearest_venues_to_visit
+        self.open = open or {"weekday": "0-24", "weekend": "0-24"}
+        if hours_per_day is None:
+            hours_per_day = {d: {"male": {"0-65": 3, "65-100": 11}, "female": {"0-65": 3, "65-100": 11}} if d == "weekday"
+                             else {"male": {"0-100": 12}, "female": {"0-100": 12}} for d in ("weekday", "weekend")}
+        self.poisson_parameters = self._parse_poisson_parameters(times_per_week or {}, hours_per_day)
+
+    @classmethod
+    def from_config(cls, social_venues=None, daytypes: dict = DEFAULT_DAYTYPES, config_filename: Optional[str] = None,
+                    config_override: Optional[dict] = None):
+        if config_filename is None:
+            config = dict(load_defaults()["leisure"][cls.config_key])
+        else:
+            with open(config_filename) as f:
+                config = yaml.safe_load(f)
+        for k, v in (config_override or {}).items():
+            if v is not None:
+                config[k] = v
+        return cls(social_venues, daytypes=daytypes, **config)
+
+    def _parse_poisson_parameters(self, times_per_week: dict, hours_per_day: dict):
+        ret: Dict[str, Dict[str, List[float]]] = {}
+        for day_type in ("weekday", "weekend"):
+            ret[day_type] = {}
+            ndays = len(self.daytypes[day_type])
+            for sex_long, sex in (("male", "m"), ("female", "f")):
+                tpw = parse_age_probabilities((times_per_week.get(day_type) or {}).get(sex_long))
+                hpd = parse_age_probabilities((hours_per_day.get(day_type) or {}).get(sex_long))
+                # social_venue_distributor.py:143-149
+                ret[day_type][sex] = [0.0 if t == 0 else (t / ndays) * (24 / h) for t, h in zip(tpw, hpd)]
+        return ret
+
+    def get_poisson_parameter(self, sex: str, age: int, day_type: str, working_hours: bool,
+                              regional_compliance: Optional[float] = None, closed: bool = False,
+                              policy_reduction: Optional[float] = None) -> float:
+        """``social_venue_distributor.py:176-205`` (``regional_compliance`` None = no region)."""
+        if closed:
+            return 0.0
+        original = self.poisson_parameters[day_type][sex][age]
+        if policy_reduction is None:
+            return original
+        rc = 1.0 if regional_compliance is None else regional_compliance
+        return original * (1 + rc * (policy_reduction - 1))
+
+
+class PubDistributor(SocialVenueDistributor):
+    spec, config_key = "pub", "pubs"
+
+
+class CinemaDistributor(SocialVenueDistributor):
+    spec, config_key = "cinema", "cinemas"
+
+
+class GroceryDistributor(SocialVenueDistributor):
+    spec, config_key = "grocery", "groceries"
+
+
+class GymDistributor(SocialVenueDistributor):
+    spec, config_key = "gym", "gyms"
+
+
+DISTRIBUTORS = {"pubs": PubDistributor, "cinemas": CinemaDistributor, "groceries": GroceryDistributor,
+                "gyms": GymDistributor}
+
+
+class Leisure:
+    """``Leisure`` (``leisure.py:125-372``): ``leisure_distributors`` keeps the reference's insertion
+    order (pub, gym, cinema, grocery -- ``generate_leisure_for_world``, ``:33-91``), which is the order
+    of the activity axis of the tables and of ``WorldSoA.leisure_activities``."""
+
+    def __init__(self, leisure_distributors: Dict[str, SocialVenueDistributor], region_names: Optional[Sequence[str]] = None):
+        self.leisure_distributors = dict(leisure_distributors)
+        self.n_activities = len(self.leisure_distributors)
+        self.policy_reductions: Dict[str, dict] = {}
+        self.region_names = list(region_names or [])
+        self.regional_compliance: Dict[str, float] = {}
+        self.closed_venues: Dict[str, set] = {}
+        self.probabilities_by_region_sex_age = None
+
+    @property
+    def activities(self) -> List[str]:
+        return list(self.leisure_distributors)
+
+    def generate_leisure_probabilities_for_timestep(self, delta_time: float, working_hours: bool,
+                                                    date: datetime.datetime):
+        """Returns ``(does[R][2][100], cum[R][2][100][K])`` and keeps the reference's nested-dict view
+        in ``probabilities_by_region_sex_age`` (``leisure.py:205-228``)."""
+        regions = self.region_names or [None]
+        K = self.n_activities
+        does = np.zeros((len(regions), 2, 100))
+        cum = np.zeros((len(regions), 2, 100, max(1, K)))
+        day = _DAY_NAMES[date.weekday()]
+        view = {}
+        for r, region in enumerate(regions):
+            view[region] = {}
+            for si, sex in enumerate(SEXES):
+                rows = []
+                for age in range(100):
+                    lam = []
+                    for activity, dist in self.leisure_distributors.items():
+                        day_type = "weekday" if day in dist.daytypes["weekday"] else "weekend"
+                        ot = parse_opens(dist.open)[day_type]
+                        is_open = 0 if (ot[1] - ot[0] == 0 or date.hour < ot[0] or date.hour >= ot[1]) else 1
+                        red = self.policy_reductions[activity][day_type][sex][age] if activity in self.policy_reductions else 1
+                        lam.append(dist.get_poisson_parameter(
+                            sex=sex, age=age, day_type=day_type, working_hours=working_hours,
+                            regional_compliance=None if region is None else self.regional_compliance.get(region, 1.0),
+                            closed=region is not None and dist.spec in self.closed_venues.get(region, ()),
+                            policy_reduction=red) * is_open)
+                    total = sum(lam)
+                    does[r, si, age] = 1.0 - np.exp(-delta_time * total)
+                    probs = [0.0 if x == 0 else x / total for x in lam]
+                    cum[r, si, age, :K] = np.cumsum(probs) if K else 0.0
+                    rows.append({"does_activity": does[r, si, age], "activities": dict(zip(self.leisure_distributors, probs))})
+                view[region][sex] = rows
+        self.probabilities_by_region_sex_age = view if self.region_names else view[None]
+        return does, cum
+
+
+def generate_leisure_for_world(list_of_leisure_groups: Sequence[str], world, daytypes: dict = DEFAULT_DAYTYPES) -> Leisure:
+    """``generate_leisure_for_world`` (``leisure.py:33-91``) for a ``WorldSoA``: one distributor per
+    listed venue supergroup the world has, in the reference's fixed order."""
+    dists: Dict[str, SocialVenueDistributor] = {}
+    have = {sg.name for sg in world.supergroups}
+    for name in ("pubs", "gyms", "cinemas", "groceries"):
+        if name in list_of_leisure_groups and name in have:
+            d = DISTRIBUTORS[name].from_config(daytypes=daytypes)
+            dists[d.spec] = d
+    return Leisure(dists, region_names=world.region_names)

@@ -54,8 +54,15 @@ class ActivityManager:
             sched = config["time"]["step_activities"][day]
             for a in (sched.values() if isinstance(sched, dict) else sched):
                 acts.update(a)
+        leisure = None
+        if getattr(world, "has_leisure", False):
+            from .leisure import generate_leisure_for_world
+            leisure = generate_leisure_for_world(a2sg.get("leisure", []), world)
+            if leisure.activities != list(world.leisure_activities):
+                raise SimulatorError(f"leisure activities of the config {leisure.activities} do not match the "
+                                     f"world's {world.leisure_activities}")
         return cls(world=world, policies=policies, timer=timer, all_activities=sorted(acts, key=ACTIVITY_HIERARCHY.index),
-                   activity_to_super_groups=a2sg)
+                   activity_to_super_groups=a2sg, leisure=leisure)
 
     @staticmethod
     def apply_activity_hierarchy(activities: List[str]) -> List[str]:
@@ -181,6 +188,8 @@ class Simulator:
             import torch
             ptr = self.device._f("stream_handle")(self.device.handle)
             self._ext_stream = torch.cuda.ExternalStream(int(ptr), device=torch.device("cuda", self.device.device_index))
+        self._leisure_tables: dict = {}   # time-slot key -> table index on the device
+        self._leisure_stack: List[tuple] = []
         self.region_history: List[tuple] = []
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
@@ -220,7 +229,29 @@ class Simulator:
         beta, flags, self.interaction.beta_reductions = hit
         return self.device.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self.step_ordinal,
                                        activity_mask=self.activity_manager.activity_mask(), seed=self.seed,
-                                       flags=flags | extra_flags, beta=beta)
+                                       flags=flags | extra_flags, beta=beta, leisure_table=self.leisure_table(key))
+
+    def leisure_table(self, policy_key: tuple = ()) -> int:
+        """``ActivityManager.do_timestep`` regenerates the leisure probabilities on every step
+        (``activity_manager.py:200-209``); they only depend on the time slot (duration, working
+        hours, day type, hour) and on the active policies, so each distinct slot is computed once,
+        appended to the device-resident stack and selected per step by index."""
+        leisure = self.activity_manager.leisure
+        acts = self.timer.activities
+        if leisure is None or not self.world.has_leisure or "leisure" not in acts:
+            return 0
+        date = self.timer.date
+        key = (round(self.timer.duration, 9), "primary_activity" in acts, date.weekday(), date.hour, policy_key)
+        idx = self._leisure_tables.get(key)
+        if idx is None:
+            comp, _ = self.activity_manager.policies.regional_scalars(date, self.world.region_names, self._region_state)
+            leisure.regional_compliance = dict(zip(self.world.region_names, comp))
+            self._leisure_stack.append(leisure.generate_leisure_probabilities_for_timestep(
+                delta_time=self.timer.duration, working_hours="primary_activity" in acts, date=date))
+            idx = self._leisure_tables[key] = len(self._leisure_stack) - 1
+            self.device.set_leisure_tables(np.stack([t[0] for t in self._leisure_stack]),
+                                           np.stack([t[1] for t in self._leisure_stack]))
+        return idx + 1
 
     def do_timestep(self, want_stats: bool = True) -> None:
         activities = self.timer.activities

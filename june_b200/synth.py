@@ -18,8 +18,8 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from .world import (ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, KIND_MATRIX, KIND_SCHOOL, BetaRule, Supergroup, WorldSoA,
-                    make_ginfo, make_info)
+from .world import (ACT_LEISURE, ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, KIND_MATRIX, KIND_SCHOOL, BetaRule, Supergroup,
+                    WorldSoA, make_ginfo, make_info)
 
 REGIONS = ["North East", "North West", "Yorkshire and The Humber", "East Midlands", "West Midlands",
            "East of England", "London", "South East", "South West"]
@@ -27,6 +27,14 @@ SECTORS = list("ABCDEFGHIJKLMNOPQRSTU")
 HH_SIZES = np.array([1, 2, 3, 4, 5, 6])
 HH_P = np.array([0.30, 0.34, 0.16, 0.13, 0.05, 0.02])
 MAX_CLASSROOM = 40  # school_distributor.yaml: max_classroom_size
+# leisure venues (config 4): supergroup name, spec, people per venue, candidates per area
+# (pubs.yaml / cinemas.yaml / groceries.yaml / gyms.yaml: neighbours_to_consider), in the order of
+# activity_to_super_groups["leisure"]; LEISURE_ORDER is the reference's distributor order
+# (generate_leisure_for_world, leisure.py:33-91)
+LEISURE_VENUES = [("pubs", "pub", 1000, 7), ("cinemas", "cinema", 20000, 5), ("groceries", "grocery", 2000, 15),
+                  ("gyms", "gym", 5000, 7)]
+LEISURE_ORDER = ["pubs", "gyms", "cinemas", "groceries"]
+LEISURE_BIN_CAP = 2048  # visitors per venue and step
 
 
 def age_pmf() -> np.ndarray:
@@ -66,7 +74,8 @@ def _csr_from_rows(group: np.ndarray, lsg: np.ndarray, member: np.ndarray, act: 
 
 
 def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int = 0, commute_fraction: float = 0.05,
-                    person_id_base: Optional[int] = None, sector_betas: Optional[Dict[str, float]] = None) -> DomainDraft:
+                    person_id_base: Optional[int] = None, sector_betas: Optional[Dict[str, float]] = None,
+                    leisure: bool = False) -> DomainDraft:
     rng = np.random.default_rng([seed, rank, 20200301])
     pmf = age_pmf()
     adult_pmf = pmf.copy()
@@ -243,12 +252,17 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     g_hosp0 = 0
     g_school0 = g_hosp0 + n_hosp
     g_comp0 = g_school0 + n_schools
-    g_hh0 = g_comp0 + n_comp
+    # leisure venues sit between the primary-activity and the residence supergroups (hierarchy order)
+    n_venues = [max(1, n // per) for _, _, per, _ in LEISURE_VENUES] if leisure else []
+    g_ven0 = [g_comp0 + n_comp + int(sum(n_venues[:i])) for i in range(len(n_venues))]
+    g_hh0 = g_comp0 + n_comp + int(sum(n_venues))
     g_ch0 = g_hh0 + n_hh
     G = g_ch0 + n_ch
     rules = [BetaRule("hospital"), BetaRule("primary_school", "school"), BetaRule("secondary_school", "school"),
              BetaRule("company"), BetaRule("household", None, False), BetaRule("household_visits", None, False),
              BetaRule("care_visits", None, False), BetaRule("care_home")]
+    if leisure:
+        rules += [BetaRule(spec) for _, spec, _, _ in LEISURE_VENUES]
     scales = [1.0]
     sec_scale = np.zeros(len(SECTORS), np.int64)
     for i, s in enumerate(SECTORS):
@@ -266,9 +280,9 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     beta_idx[g_school0:g_comp0] = 1 + school_sector
     region[g_school0:g_comp0] = sa_region[school_sa]
     aux[g_school0:g_comp0] = (years_off[:-1].astype(np.uint32) << 8) | n_years_per_school.astype(np.uint32)
-    beta_idx[g_comp0:g_hh0] = 3
-    scale_idx[g_comp0:g_hh0] = sec_scale[comp_sector]
-    region[g_comp0:g_hh0] = sa_region[comp_sa]
+    beta_idx[g_comp0:g_comp0 + n_comp] = 3
+    scale_idx[g_comp0:g_comp0 + n_comp] = sec_scale[comp_sector]
+    region[g_comp0:g_comp0 + n_comp] = sa_region[comp_sa]
     beta_idx[g_hh0:g_ch0] = 4
     region[g_hh0:g_ch0] = sa_region[sa_of_hh]
     ch_sa = (np.arange(n_ch) * n_sa // n_ch).astype(np.int64)
@@ -277,9 +291,28 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     grp_sa = np.zeros(G, np.uint32)
     grp_sa[g_hosp0:g_school0] = hosp_sa
     grp_sa[g_school0:g_comp0] = school_sa
-    grp_sa[g_comp0:g_hh0] = comp_sa
+    grp_sa[g_comp0:g_comp0 + n_comp] = comp_sa
     grp_sa[g_hh0:g_ch0] = sa_of_hh
     grp_sa[g_ch0:] = ch_sa
+    # venues are spread evenly over the areas; an area's candidates are the nearest ones by index
+    area_venue_off = area_venue = None
+    if leisure:
+        K = len(LEISURE_VENUES)
+        cand = []  # [activity in LEISURE_ORDER][area] -> group indices
+        for name in LEISURE_ORDER:
+            i = [v[0] for v in LEISURE_VENUES].index(name)
+            nv, ncand = n_venues[i], min(n_venues[i], LEISURE_VENUES[i][3])
+            ven_area = (np.arange(nv) * n_areas // nv).astype(np.int64)
+            ven_sa = sa_of_area[ven_area]
+            beta_idx[g_ven0[i]: g_ven0[i] + nv] = 8 + i
+            region[g_ven0[i]: g_ven0[i] + nv] = sa_region[ven_sa]
+            grp_sa[g_ven0[i]: g_ven0[i] + nv] = ven_sa
+            centre = np.clip((np.arange(n_areas) * nv) // n_areas - ncand // 2, 0, nv - ncand)
+            cand.append(g_ven0[i] + centre[:, None] + np.arange(ncand)[None, :])
+        counts = np.stack([np.full(n_areas, c.shape[1]) for c in cand], axis=1).ravel()  # (area, activity) order
+        area_venue_off = np.zeros(n_areas * K + 1, np.uint32)
+        area_venue_off[1:] = np.cumsum(counts)
+        area_venue = np.concatenate([np.concatenate([cand[k][a] for k in range(K)]) for a in range(n_areas)]).astype(np.uint32)
 
     # ---- registrations ----------------------------------------------------------------------------
     add_rows(g_hosp0 + hosp_of_worker, np.zeros(len(hosp_workers)), hosp_workers, ACT_PRIMARY)
@@ -300,6 +333,8 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
         Supergroup("hospitals", "hospital", ACT_MEDICAL, g_hosp0, n_hosp, KIND_MATRIX, 1, 1),
         Supergroup("schools", "school", ACT_PRIMARY, g_school0, n_schools, KIND_SCHOOL, 1, 0),
         Supergroup("companies", "company", ACT_PRIMARY, g_comp0, n_comp, KIND_MATRIX, 0, 0),
+    ] + [Supergroup(name, spec, ACT_LEISURE, g_ven0[i], n_venues[i], KIND_MATRIX, 1, LEISURE_BIN_CAP)
+         for i, (name, spec, _, _) in enumerate(LEISURE_VENUES if leisure else [])] + [
         Supergroup("households", "household", ACT_RESIDENCE, g_hh0, n_hh, KIND_MATRIX, 0, 0),
         Supergroup("care_homes", "care_home", ACT_RESIDENCE, g_ch0, n_ch, KIND_MATRIX, 0, 0),
     ]
@@ -312,6 +347,12 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
         person_id_base=(rank * n_people if person_id_base is None else person_id_base),
         grp_super_area=grp_sa,
     )
+    if leisure:
+        w.person_area = area_of_hh[hh_of].astype(np.uint32)
+        w.leisure_supergroups = list(LEISURE_ORDER)
+        w.leisure_activities = [dict((v[0], v[1]) for v in LEISURE_VENUES)[n_] for n_ in LEISURE_ORDER]
+        w.leisure_subgroups = [0] * len(LEISURE_ORDER)
+        w.area_venue_off, w.area_venue = area_venue_off, area_venue
     w.validate()
     return DomainDraft(world=w, out_person=out_person, company_first=g_comp0, company_count=n_comp,
                        company_size=csize, rank=rank, world_size=world_size, seed=seed)
@@ -378,8 +419,9 @@ def wire_halos_distributed(draft: DomainDraft, dist) -> WorldSoA:
     return draft.world
 
 
-def generate_world(n_people: int, seed: int = 0, sector_betas: Optional[Dict[str, float]] = None) -> WorldSoA:
-    """Single-domain world (configs 0/1 of BASELINE.json)."""
-    d = generate_domain(n_people, 0, 1, seed, sector_betas=sector_betas)
+def generate_world(n_people: int, seed: int = 0, sector_betas: Optional[Dict[str, float]] = None,
+                   leisure: bool = False) -> WorldSoA:
+    """Single-domain world (configs 0/1 of BASELINE.json; ``leisure=True`` adds the venues of config 3)."""
+    d = generate_domain(n_people, 0, 1, seed, sector_betas=sector_betas, leisure=leisure)
     _attach_halo(d, [np.zeros(0, np.uint32)])
     return d.world

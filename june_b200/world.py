@@ -118,10 +118,19 @@ class WorldSoA:
     person_ids: Optional[np.ndarray] = None  # reference Person.id per person index
     group_ids: Optional[np.ndarray] = None   # reference Group.id per group index
     grp_super_area: Optional[np.ndarray] = None  # super area of every group (domain decomposition)
+    # leisure (leisure.py:230-275): activity k (reference distributor order) sends people to groups
+    # of supergroup `leisure_supergroups[k]`; candidates per (area, activity) as a CSR
+    person_area: Optional[np.ndarray] = None      # uint32 [n_people]
+    leisure_activities: List[str] = field(default_factory=list)     # distributor specs: "pub", "gym", ...
+    leisure_supergroups: List[str] = field(default_factory=list)    # supergroup names: "pubs", "gyms", ...
+    leisure_subgroups: List[int] = field(default_factory=list)      # leisure_subgroup_type per activity
+    area_venue_off: Optional[np.ndarray] = None   # uint32 [n_areas * K + 1]
+    area_venue: Optional[np.ndarray] = None       # uint32 group indices
 
     _ARRAYS = ("age", "sex", "care_home_resident", "has_activity", "super_area", "sa_hospital", "sa_region",
                "grp_offset", "grp_info", "grp_aux", "reg_member", "reg_info", "school_years", "beta_scale",
-               "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids", "grp_super_area")
+               "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids", "grp_super_area",
+               "person_area", "area_venue_off", "area_venue")
 
     @property
     def n_people(self) -> int:
@@ -138,6 +147,14 @@ class WorldSoA:
     @property
     def n_regions(self) -> int:
         return max(1, len(self.region_names))
+
+    @property
+    def n_areas(self) -> int:
+        return 0 if self.person_area is None or not len(self.person_area) else int(self.person_area.max()) + 1
+
+    @property
+    def has_leisure(self) -> bool:
+        return bool(self.leisure_activities) and self.person_area is not None and self.area_venue_off is not None
 
     @property
     def n_super_areas(self) -> int:
@@ -193,6 +210,9 @@ class WorldSoA:
             "beta_rules": [b.to_json() for b in self.beta_rules],
             "n_halo": int(self.n_halo),
             "person_id_base": int(self.person_id_base),
+            "leisure_activities": list(self.leisure_activities),
+            "leisure_supergroups": list(self.leisure_supergroups),
+            "leisure_subgroups": [int(x) for x in self.leisure_subgroups],
         }
         arrays = {k: getattr(self, k) for k in self._ARRAYS if getattr(self, k) is not None}
         np.savez_compressed(path, _meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
@@ -220,5 +240,8 @@ class WorldSoA:
             beta_rules=[BetaRule(**d) for d in meta["beta_rules"]],
             n_halo=int(meta["n_halo"]),
             person_id_base=int(meta["person_id_base"]),
+            leisure_activities=list(meta.get("leisure_activities", [])),
+            leisure_supergroups=list(meta.get("leisure_supergroups", [])),
+            leisure_subgroups=list(meta.get("leisure_subgroups", [])),
             **kw,
         )
