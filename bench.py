@@ -103,13 +103,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_setup(n_people: int, rank: int, world_size: int, dist=None):
+def build_setup(n_people: int, rank: int, world_size: int, dist=None, leisure: bool = False):
     defaults = load_defaults()
     sb = defaults["company_sector_betas"]
     if world_size == 1:
-        world = generate_world(n_people, seed=0, sector_betas=sb)
+        world = generate_world(n_people, seed=0, sector_betas=sb, leisure=leisure)
     else:
-        draft = generate_domain(n_people, rank, world_size, seed=0, sector_betas=sb)
+        draft = generate_domain(n_people, rank, world_size, seed=0, sector_betas=sb, leisure=leisure)
         world = wire_halos_distributed(draft, dist)
     inter = Interaction.from_file()
     dc = DiseaseConfig("covid19")
@@ -162,12 +162,13 @@ def run_gpu(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_people = args.people or PEOPLE_PER_GPU
-    world, inter, dc, prob, cfg, policies = build_setup(n_people, rank, world_size, dist)
+    world, inter, dc, prob, cfg, policies = build_setup(n_people, rank, world_size, dist, leisure=args.leisure)
     sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, device=local_rank,
                               seed=2020, distributed=world_size > 1)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
     seed_epidemic(sim, rank)
+    sim.prepare_leisure_tables(days=14)
     dev = sim.device
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))
 
@@ -297,7 +298,8 @@ def run_gpu(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"synthetic {n_people / 1e6:.1f}M-person region per GPU (households, schools, companies, "
-                               "care homes, hospitals), default 5/4-step day schedule, ~3% seeded prevalence",
+                               "care homes, hospitals" + (", pubs, cinemas, groceries, gyms with leisure" if args.leisure else "")
+                               + "), default 5/4-step day schedule, ~3% seeded prevalence",
                    "people_per_gpu": n_people, "people_total": n_people * world_size,
                    "l2": "flushed between steps (256 MiB memset, outside the event brackets)",
                    "parallelism": "1 domain per GPU" + (", halo all-to-all over NCCL" if world_size > 1 else "")},
@@ -359,7 +361,7 @@ def run_reference(args):
     if rank != 0:
         return
     n_people = args.people or PEOPLE_PER_GPU
-    world, inter, dc, prob, cfg, policies = build_setup(n_people, 0, 1)
+    world, inter, dc, prob, cfg, policies = build_setup(n_people, 0, 1, leisure=args.leisure)
     # bounded: the CPU port needs ~0.1-1 s per step of a 2.7 M world
     steps = min(args.steps, 40)
     ps, dt, threads = cpu_run(world, inter, dc, prob, cfg, policies, steps=steps, warmup=min(args.warmup, 3))
@@ -383,6 +385,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--people", type=int, default=0, help="people per GPU (default 2.7 M = BASELINE.json configs[1])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--leisure", action="store_true",
+                    help="add pubs / cinemas / groceries / gyms and the leisure placement (BASELINE.json configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -63,8 +63,14 @@ def school_beta_key(sector) -> str:
 WARP_MODE_SPECS = ("school", "hospital", "university")
 
 
+LEISURE_BIN_CAP = 2048  # visitors per social venue and step
+
+
 def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sector_betas: Dict[str, float],
-                  warp_mode_specs=WARP_MODE_SPECS) -> WorldSoA:
+                  warp_mode_specs=WARP_MODE_SPECS, leisure=None) -> WorldSoA:
+    """``leisure``: the reference's ``Leisure`` object (or None).  Its social-venue distributors
+    (``leisure.leisure_distributors``, in order) become the leisure activities of the device world;
+    ``area.social_venues[spec]`` (``social_venue_distributor.py:258``) the per-area candidates."""
     people = list(world.people)
     n = len(people)
     pidx = {id(p): i for i, p in enumerate(people)}
@@ -148,10 +154,11 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
             beta_i.append(b)
             scale_i.append(sc)
             aux.append(a)
-        has_dyn = 1 if spec == "hospital" else 0
+        is_venue = act == "leisure"
+        has_dyn = 1 if spec == "hospital" else LEISURE_BIN_CAP if is_venue else 0
         supergroups.append(Supergroup(name=name, spec=spec, activity=ACTIVITY_CODES[act], first_group=first,
                                       n_groups=len(members), kind=kind,
-                                      launch_mode=1 if spec in warp_mode_specs else 0, has_dynamic=has_dyn))
+                                      launch_mode=1 if (spec in warp_mode_specs or is_venue) else 0, has_dynamic=has_dyn))
 
     # ---- registered members -----------------------------------------------------------------
     lsg_of: Dict[int, Tuple[int, int]] = {}
@@ -210,6 +217,24 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
         group_ids=np.array([int(g.id) for g in groups], np.int64),
         grp_super_area=np.array(gsa_i, np.uint32),
     )
+    if leisure is not None:
+        areas = list(world.areas.members) if hasattr(world.areas, "members") else list(world.areas)
+        aidx = {id(a): i for i, a in enumerate(areas)}
+        specs = [s_ for s_ in leisure.leisure_distributors if "visits" not in s_]
+        by_spec = {sg.spec: sg for sg in supergroups}
+        specs = [s_ for s_ in specs if s_ in by_spec]
+        off, ven = [0], []
+        for a in areas:
+            for s_ in specs:
+                for v in (getattr(a, "social_venues", {}) or {}).get(s_, ()) or ():
+                    if id(v) in gidx:
+                        ven.append(gidx[id(v)])
+                off.append(len(ven))
+        w.person_area = np.array([aidx[id(p.area)] for p in people], np.uint32)
+        w.leisure_activities = specs
+        w.leisure_supergroups = [by_spec[s_].name for s_ in specs]
+        w.leisure_subgroups = [int(leisure.leisure_distributors[s_].leisure_subgroup_type) for s_ in specs]
+        w.area_venue_off, w.area_venue = np.array(off, np.uint32), np.array(ven, np.uint32)
     w.validate()
     return w
 

@@ -231,6 +231,30 @@ class Simulator:
                                        activity_mask=self.activity_manager.activity_mask(), seed=self.seed,
                                        flags=flags | extra_flags, beta=beta, leisure_table=self.leisure_table(key))
 
+    def prepare_leisure_tables(self, days: int = 7) -> int:
+        """Compute and upload the leisure tables of every time slot of the next ``days`` days in one
+        go (otherwise each new slot is appended -- and the captured step graphs dropped -- the first
+        time the clock reaches it).  Returns the number of distinct slots."""
+        if self.activity_manager.leisure is None or not self.world.has_leisure:
+            return 0
+        import copy
+        saved = self.timer
+        policies = self.activity_manager.policies
+        try:
+            self.timer = copy.deepcopy(saved)
+            end = self.timer.date + datetime.timedelta(days=days)
+            upload, self.device.set_leisure_tables = self.device.set_leisure_tables, lambda *a: None
+            while self.timer.date < end and self.timer.date < self.timer.final_date:
+                self.leisure_table(tuple(p.is_active(self.timer.date) for p in policies.policies))
+                next(self.timer)
+        finally:
+            self.timer = saved
+            del self.device.set_leisure_tables
+        if self._leisure_stack:
+            self.device.set_leisure_tables(np.stack([t[0] for t in self._leisure_stack]),
+                                           np.stack([t[1] for t in self._leisure_stack]))
+        return len(self._leisure_stack)
+
     def leisure_table(self, policy_key: tuple = ()) -> int:
         """``ActivityManager.do_timestep`` regenerates the leisure probabilities on every step
         (``activity_manager.py:200-209``); they only depend on the time slot (duration, working

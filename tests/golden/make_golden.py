@@ -56,14 +56,15 @@ def infection_row(pidx, person, time):
 ROW_LEN = 5 + 5 + 2 * MAX_STAGES
 
 
-def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000):
+def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000,
+              with_leisure=False):
     pyrandom.seed(seed)
     np.random.seed(seed)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink):
-        world, dc = ref_world.build_world(n_people, seed=seed)
+        world, dc = ref_world.build_world(n_people, seed=seed, with_leisure=with_leisure)
         sim = ref_world.make_simulator(world, dc, total_days=total_days, cases_per_capita=cases_per_capita,
-                                       schedule=schedule)
+                                       schedule=schedule, with_leisure=with_leisure)
     import june.interaction.interaction as inter_mod
     import june.policy.individual_policies as indiv_mod
     from june.epidemiology.infection import InfectionSelector
@@ -79,7 +80,9 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
 
     a2sg = {"medical_facility": ["hospitals"], "primary_activity": ["schools", "companies"],
             "residence": ["households", "care_homes"]}
-    soa = compile_world(world, a2sg, InteractiveCompany.sector_betas)
+    if with_leisure:
+        a2sg["leisure"] = ["pubs", "cinemas", "groceries"]
+    soa = compile_world(world, a2sg, InteractiveCompany.sector_betas, leisure=sim.activity_manager.leisure)
     people = list(world.people)
     pidx = {p.id: i for i, p in enumerate(people)}
     gidx = {}
@@ -249,6 +252,9 @@ def spot_values(out_name="spot"):
 
 
 if __name__ == "__main__":
+    if "leisure" in sys.argv[1:]:  # leisure placement (pubs, cinemas, groceries) on top of the w3k recipe
+        run_trace(2500, 9, 2, "w2k_leisure", cases_per_capita=0.04, with_leisure=True)
+        sys.exit(0)
     run_trace(3000, 12, 0, "w3k")
     run_trace(1200, 40, 1, "w1k_long", cases_per_capita=0.05, schedule="simple")
     spot_values()

@@ -50,7 +50,7 @@ def synthetic_rates_df():
 
 
 def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
-                people_per_company=40, people_per_school=1000, n_super_areas=4):
+                people_per_company=40, people_per_school=1000, n_super_areas=4, with_leisure=False):
     """Returns ``(world, disease_config)``.  People are created household by household so
     that person index order == household order."""
     ref_harness.setup()
@@ -200,11 +200,27 @@ def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
     if care_homes:
         world.care_homes = CareHomes(care_homes)
     world.cemeteries = Cemeteries()
+    if with_leisure:
+        # social venues: one pub per area, one grocery per two areas, one cinema per super area;
+        # an area's candidates are hand-wired (the reference's distributor needs coordinates + a tree)
+        from june.groups.leisure import Cinema, Cinemas, Groceries, Grocery, Pub, Pubs
+        pubs = [Pub(area=a) for a in areas]
+        groceries = [Grocery(area=a) for a in areas[::2]]
+        cinemas = [Cinema(area=sa.areas[0]) for sa in super_areas]
+        for i, a in enumerate(areas):
+            a.social_venues = {
+                "pub": tuple(pubs[j % len(pubs)] for j in (i, i + 1, i + 2)),
+                "grocery": tuple(groceries[j % len(groceries)] for j in (i // 2, i // 2 + 1)),
+                "cinema": (cinemas[(i // 4) % len(cinemas)],),
+            }
+        world.pubs = Pubs(pubs, make_tree=False)
+        world.groceries = Groceries(groceries, make_tree=False)
+        world.cinemas = Cinemas(cinemas, make_tree=False)
     return world, dc
 
 
 def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policies=True,
-                   initial_day="2020-03-02 0:00", schedule="default"):
+                   initial_day="2020-03-02 0:00", schedule="default", with_leisure=False):
     """Reference Simulator wired as ``example_scripts/run_simulation.py:332-512`` does, minus
     leisure / travel / records."""
     ref_harness.setup()
@@ -243,6 +259,18 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
     timer = Timer(initial_day=initial_day, total_days=total_days,
                   weekday_step_duration=wd_dur, weekend_step_duration=we_dur,
                   weekday_activities=wd_act, weekend_activities=we_act)
+    if with_leisure:
+        # config_simulation.yaml:15-41 with leisure (no commute)
+        wd_dur, we_dur = [1, 8, 1, 3, 11], [4, 4, 4, 12]
+        wd_act = [["medical_facility", "residence"],
+                  ["medical_facility", "primary_activity", "leisure", "residence"],
+                  ["medical_facility", "residence"],
+                  ["medical_facility", "leisure", "residence"],
+                  ["medical_facility", "residence"]]
+        we_act = [["medical_facility", "leisure", "residence"]] * 3 + [["medical_facility", "residence"]]
+        timer = Timer(initial_day=initial_day, total_days=total_days,
+                      weekday_step_duration=wd_dur, weekend_step_duration=we_dur,
+                      weekday_activities=wd_act, weekend_activities=we_act)
     pol = [Hospitalisation(disease_config=dc), SevereSymptomsStayHome(start_time="1900-01-01", end_time="2100-01-01")] if with_policies else []
     policies = Policies(pol)
     a2sg = {
@@ -251,8 +279,16 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
         "residence": ["households"] + (["care_homes"] if world.care_homes is not None else []),
     }
     all_activities = ["medical_facility", "primary_activity", "residence"]
+    leisure = None
+    if with_leisure:
+        from june.groups.leisure import generate_leisure_for_world
+        a2sg["leisure"] = ["pubs", "cinemas", "groceries"]
+        all_activities = ["medical_facility", "primary_activity", "leisure", "residence"]
+        leisure = generate_leisure_for_world(
+            a2sg["leisure"], world,
+            daytypes={"weekday": ["Monday", "Tuesday", "Wednesday", "Thursday", "Friday"], "weekend": ["Saturday", "Sunday"]})
     am = ActivityManager(world=world, policies=policies, timer=timer,
-                         all_activities=all_activities, activity_to_super_groups=a2sg)
+                         all_activities=all_activities, activity_to_super_groups=a2sg, leisure=leisure)
     sim = Simulator(world=world, interaction=interaction, timer=timer, activity_manager=am,
                     epidemiology=epidemiology, tracker=None, record=None)
     return sim

@@ -5,7 +5,8 @@ The same checks run against
   * the CUDA path through the C ABI (``libjune_b200.so``) -- ``-m gpu`` on the B200 box.
 
 Per reference ``do_timestep`` we check, with the reference's own uniform stream injected:
-  placement (activity chosen per person), the infection exponent Lambda of every Bernoulli draw
+  placement (activity chosen per person; in the leisure trace the reference's own venue choices
+  are replayed and the visitors' draws checked), the infection exponent Lambda of every Bernoulli draw
   (<= 1e-9 relative, BASELINE.json), the set of newly infected people (bit-exact), and the person
   state after the health update (infected/dead flags, symptom tag and hospital ward exact;
   transmission probability <= 1e-9 relative).
@@ -15,7 +16,7 @@ import pytest
 
 from june_b200 import _lib
 from june_b200.interaction import Interaction
-from june_b200.world import PS_ACT_MASK, PS_DEAD, PS_INFECTED
+from june_b200.world import ACT_LEISURE, PS_ACT_MASK, PS_DEAD, PS_INFECTED
 
 from helpers import Golden, default_beta_table, have_gpu, make_engine, rows_to_dicts
 
@@ -43,8 +44,16 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
         if len(s["pre_rows"]):
             eng.upload_infections(rows_to_dicts(s["pre_rows"]))
         eng.inject_uniforms(s["draw_u"])
+        flags = FLAGS
+        if g.world.has_leisure:
+            # the reference's own leisure choices (leisure.py:253-263 draws from Python's / numba's
+            # global generators) are replayed: venue per person, -1 = did not go out
+            pg = s["place_group"]
+            at_venue = (pg >= 0) & (sg_act[grp_sg[np.maximum(pg, 0)]] == ACT_LEISURE)
+            eng.inject_leisure(np.where(at_venue, pg, -1).astype(np.int32))
+            flags |= _lib.STEP_INJECT_LEISURE
         p = eng.make_params(now=float(s["now"]), delta_time=float(s["dt"]), step=i,
-                            activity_mask=int(s["activity_mask"]), seed=0, flags=FLAGS, beta=beta)
+                            activity_mask=int(s["activity_mask"]), seed=0, flags=flags, beta=beta)
         eng.step_begin(p)
         eng.step_interact()
         # -- infection exponents, in draw order ------------------------------------------------
@@ -101,7 +110,7 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     return total_draws, total_inf, worst
 
 
-@pytest.mark.parametrize("name", ["w3k", "w1k_long"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure"])
 def test_oracle_matches_reference_trace(name):
     draws, infections, worst = run_trace("oracle", name)
     assert draws > 10000 and infections > 100
@@ -119,7 +128,7 @@ LAUNCH_MODES = {
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("modes", ["tiles", "warps", "mixed"])
-@pytest.mark.parametrize("name", ["w3k", "w1k_long"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure"])
 def test_cuda_matches_reference_trace(name, modes):
     assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
     draws, infections, worst = run_trace("cuda", name, launch_modes=LAUNCH_MODES[modes])
