@@ -193,6 +193,7 @@ typedef struct {
 #define JB_STEP_NO_NEW_INFECTIONS 0x8u /* do not create infections on device (host uploads rows)    */
 #define JB_STEP_RECORD_LAMBDA 0x10u   /* keep per-person Lambda of this step for jb_fetch_lambda   */
 #define JB_STEP_INJECT_LEISURE 0x20u  /* leisure venues come from jb_inject_leisure (test mode)    */
+#define JB_STEP_INJECT_POLICY 0x40u   /* policy uniforms come from jb_inject_policy_uniforms        */
 
 /* Per-step outputs (the d2h payload of every step). */
 typedef struct {
@@ -298,6 +299,45 @@ int jb_set_leisure_tables(JbWorld* w, uint32_t n_tables, const double* does, con
 /* Test mode (JB_STEP_INJECT_LEISURE): the venue of every person for the next step, -1 = none;
  * replaces the three random choices of leisure.py:253-263 / social_venue_distributor.py:257-266. */
 int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person);
+
+/* ---- individual policies (policy/individual_policies.py:36-84) ---------------------------
+ * The active individual policies, in the reference's list order, evaluated per person by the
+ * placement stage.  A stay-home policy that fires reduces the person's activities to
+ * (medical_facility, residence) and ends the evaluation (:52-77); a skip-activity policy removes
+ * activities (:78-80).  Probabilities that are None in the reference are passed as NaN. */
+#define JB_MAX_POLICIES 8
+#define JB_POLICY_DRAWS 3          /* uniforms a policy may consume per person and step      */
+#define JB_POL_SEVERE_STAY_HOME 1  /* SevereSymptomsStayHome (:121-149)                      */
+#define JB_POL_QUARANTINE 2        /* Quarantine (:152-237): p0 n_days, p1 compliance,
+                                    * mask = stay_at_home tags (bit tag+2)                    */
+#define JB_POL_SHIELDING 3         /* Shielding (:416-439): p0 min_age, p1 compliance | NaN   */
+#define JB_POL_CLOSE_SCHOOLS 4     /* CloseSchools (:480-530): flags bit0 full_closure,
+                                    * mask = ages (0..31) of years_to_close, p0 attending_compliance */
+#define JB_POL_CLOSE_UNIVERSITIES 5 /* CloseUniversities (:533-548)                          */
+#define JB_POL_CLOSE_COMPANIES 6   /* CloseCompanies (:604-770): flags bit0 full_closure, p0
+                                    * avoid_work_probability, p1 furlough_probability, p2
+                                    * key_probability, p3..p5 furlough / key / random ratios    */
+typedef struct {
+  int32_t type;
+  uint32_t flags;
+  uint32_t mask;
+  uint32_t _pad;
+  double p[6];
+} JbIndividualPolicy;
+/* regional_compliance: [n_regions] (region.regional_compliance, regional_compliance.py:21-30) */
+int jb_set_individual_policies(JbWorld* w, const JbIndividualPolicy* policies, uint32_t n,
+                               const double* regional_compliance);
+/* Static per-person facts the policies read: bits 0-1 lockdown_status (0 none, 1 key_worker,
+ * 2 random, 3 furlough; person.py), bits 2-4 spec of the primary-activity group (0 none, 1 school,
+ * 2 company, 3 university, 4 other), bit 5 = at least two key workers among the household's
+ * residents (CloseSchools._check_kid_goes_to_school, :497-510). */
+#define JB_PA_LOCKDOWN(x) ((x) & 3u)
+#define JB_PA_KIND(x) (((x) >> 2) & 7u)
+#define JB_PA_TWO_KEY_WORKERS 0x20u
+int jb_set_person_attributes(JbWorld* w, const uint8_t* attr);
+/* Test mode (JB_STEP_INJECT_POLICY): the uniforms the policies consume, [JB_MAX_POLICIES]
+ * [JB_POLICY_DRAWS][n_people]; replaces Python's random() in individual_policies.py. */
+int jb_inject_policy_uniforms(JbWorld* w, const double* u);
 
 int jb_sync(JbWorld* w);
 

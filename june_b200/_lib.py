@@ -23,7 +23,9 @@ ABI_VERSION = 1
 
 JB_OK, JB_EINVAL, JB_ECUDA, JB_ENOACT, JB_ECAP, JB_ENOGPU = 0, 1, 2, 3, 4, 5
 STEP_SEVERE_STAY_HOME, STEP_HOSPITALISATION, STEP_INJECT_UNIFORMS = 0x1, 0x2, 0x4
-STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE = 0x8, 0x10, 0x20
+STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE, STEP_INJECT_POLICY = 0x8, 0x10, 0x20, 0x40
+MAX_POLICIES, POLICY_DRAWS = 8, 3
+POL_SEVERE_STAY_HOME, POL_QUARANTINE, POL_SHIELDING, POL_CLOSE_SCHOOLS, POL_CLOSE_UNIVERSITIES, POL_CLOSE_COMPANIES = 1, 2, 3, 4, 5, 6
 
 
 class SimulatorError(BaseException):
@@ -73,6 +75,11 @@ class JbStepParams(C.Structure):
                 ("seed", C.c_uint64), ("flags", C.c_uint32), ("leisure_table", C.c_uint32), ("beta", C.c_void_p)]
 
 
+class JbIndividualPolicy(C.Structure):
+    _fields_ = [("type", C.c_int32), ("flags", C.c_uint32), ("mask", C.c_uint32), ("_pad", C.c_uint32),
+                ("p", C.c_double * 6)]
+
+
 class JbLeisureDesc(C.Structure):
     _fields_ = [("n_activities", C.c_uint32), ("n_areas", C.c_uint32), ("supergroup", C.c_void_p),
                 ("subgroup", C.c_void_p), ("person_area", C.c_void_p), ("area_off", C.c_void_p),
@@ -104,6 +111,7 @@ ABI_SYMBOLS = [
     "set_halo", "halo_record_size", "halo_return_size", "sync", "fetch_new_infections", "fetch_person_state",
     "fetch_lambda", "fetch_infections", "fetch_summary", "timing_enable", "timing_read", "last_step_bytes",
     "set_concurrency", "set_leisure", "set_leisure_tables", "inject_leisure",
+    "set_individual_policies", "set_person_attributes", "inject_policy_uniforms",
 ]
 
 
@@ -159,6 +167,9 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("set_leisure").argtypes = [vp, C.POINTER(JbLeisureDesc)]
     f("set_leisure_tables").argtypes = [vp, C.c_uint32, vp, vp]
     f("inject_leisure").argtypes = [vp, vp]
+    f("set_individual_policies").argtypes = [vp, C.POINTER(JbIndividualPolicy), C.c_uint32, vp]
+    f("set_person_attributes").argtypes = [vp, vp]
+    f("inject_policy_uniforms").argtypes = [vp, vp]
     for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp]),
                         ("timing_read_supergroups", [vp, dp, C.POINTER(C.c_uint64), C.c_int]),
                         ("set_concurrency", [vp, C.c_int])):

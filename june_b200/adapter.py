@@ -20,8 +20,8 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
-from .world import (ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, ACTIVITY_CODES, KIND_MATRIX, KIND_SCHOOL, BetaRule,
-                    Supergroup, WorldSoA, make_ginfo, make_info)
+from .world import (ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, ACTIVITY_CODES, KIND_MATRIX, KIND_SCHOOL, LOCKDOWN_CODES,
+                    PRIMARY_KIND_CODES, BetaRule, Supergroup, WorldSoA, make_ginfo, make_info, make_person_attr)
 
 # activity hierarchy, june/activity/activity_manager.py:24-33 (activities without device support
 # in this round are listed so that the supergroup order stays the reference's)
@@ -217,6 +217,18 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
         group_ids=np.array([int(g.id) for g in groups], np.int64),
         grp_super_area=np.array(gsa_i, np.uint32),
     )
+    # what the individual policies read per person (individual_policies.py:497-510,651-770)
+    lock = np.array([LOCKDOWN_CODES.get(getattr(p, "lockdown_status", None), 0) for p in people], np.uint8)
+    kind = np.zeros(n, np.uint8)
+    kw2 = np.zeros(n, bool)
+    for i, p in enumerate(people):
+        sub = getattr(p.subgroups, "primary_activity", None) if p.subgroups is not None else None
+        if sub is not None:
+            kind[i] = PRIMARY_KIND_CODES.get(sub.group.spec, 4)
+        res = getattr(p.subgroups, "residence", None) if p.subgroups is not None else None
+        if res is not None and hasattr(res.group, "residents"):
+            kw2[i] = sum(1 for m in res.group.residents if getattr(m, "lockdown_status", None) == "key_worker") > 1
+    w.person_attr = make_person_attr(lock, kind, kw2)
     if leisure is not None:
         areas = list(world.areas.members) if hasattr(world.areas, "members") else list(world.areas)
         aidx = {id(a): i for i, a in enumerate(areas)}

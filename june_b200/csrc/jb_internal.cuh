@@ -80,6 +80,14 @@ struct LeisureDev {
   int32_t lsg[JB_MAX_LEISURE];
 };
 
+// Active individual policies + regional compliance (jb_set_individual_policies), device resident.
+#define JB_MAX_REGIONS_POLICY 64
+struct PolicyDev {
+  uint32_t n, pad_;
+  JbIndividualPolicy pol[JB_MAX_POLICIES];
+  double rc[JB_MAX_REGIONS_POLICY];
+};
+
 // Per-step scalars, resident on the device so that a captured CUDA graph of the step can be
 // replayed: one h2d copy from a pinned ring buffer precedes every step.  The processed beta
 // table [n_beta][n_regions] follows the struct in the same allocation.
@@ -224,6 +232,11 @@ struct JbWorld {
   uint32_t *lz_parea = nullptr, *lz_off = nullptr, *lz_venue = nullptr;
   double *lz_does = nullptr, *lz_cum = nullptr;
   int32_t* lz_inject = nullptr;
+  // individual policies
+  PolicyDev* d_pol = nullptr;
+  uint32_t n_pol = 0;
+  uint8_t* pattr = nullptr;
+  double* pol_inject = nullptr;
   bool any_dynamic = false;
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;

@@ -46,7 +46,107 @@ struct PlaceArgs {
   const uint32_t* int2ext;
   uint32_t gid_base;
   int R;
+  // individual policies (null / 0 = none)
+  const PolicyDev* pol;
+  uint32_t n_pol;
+  const int8_t* ptag;
+  const uint8_t* pattr;
+  const double* pol_inject;  // [JB_MAX_POLICIES][JB_POLICY_DRAWS][N] or null
+  int severe_mask;
 };
+
+// Uniform number j of policy k for person p in this step (or the injected one, test mode).
+__device__ __forceinline__ double jb_policy_uniform(const PlaceArgs& a, uint32_t p, uint32_t k, uint32_t j) {
+  if (a.pol_inject) return a.pol_inject[((size_t)k * JB_POLICY_DRAWS + j) * a.N + p];
+  const JbPhilox4 r = jb_philox4x32_10(a.gid_base + a.int2ext[p], a.sp->step, JB_STREAM_POLICY0 + k, j >> 1,
+                                       (uint32_t)a.sp->seed, (uint32_t)(a.sp->seed >> 32));
+  return (j & 1u) ? jb_u52(r.x[2], r.x[3]) : jb_u52(r.x[0], r.x[1]);
+}
+
+// CloseCompanies.check_skips_activity (individual_policies.py:651-770).  NaN = None.
+__device__ bool jb_close_companies_skips(const PlaceArgs& a, uint32_t p, uint32_t k, const JbIndividualPolicy& q, int status) {
+  const double awp = q.p[0], fp = q.p[1], kp = q.p[2], fr = q.p[3], kr = q.p[4], rr = q.p[5];
+  const bool have_f = !isnan(fr) && !isnan(fp), have_k = !isnan(kr) && !isnan(kp), have_r = !isnan(rr);
+  uint32_t j = 0;
+  if (q.flags & 1u) return true;  // full_closure
+  if (status == 3) {  // furlough
+    if (!have_f) return true;
+    if (fr < fp) return true;
+    if (jb_policy_uniform(a, p, k, j++) < fp / fr) return true;
+    return !isnan(awp) && jb_policy_uniform(a, p, k, j++) < awp;
+  }
+  if (status == 1 && have_k)  // key worker
+    return kr > kp && jb_policy_uniform(a, p, k, j++) > kp / kr;
+  if (status == 2 && !isnan(awp)) {  // random
+    if (have_f && have_k && have_r) {
+      if (fr < fp && kr < kp) {
+        if (jb_policy_uniform(a, p, k, j++) < (fp - fr) / rr) return true;
+        else if (jb_policy_uniform(a, p, k, j++) < (kp - kr) / (rr - (fp - fr))) return false;
+      } else if (fr < fp) {
+        if (jb_policy_uniform(a, p, k, j++) < (fp - fr) / rr) return true;
+      } else if (kr < kp) {
+        if (jb_policy_uniform(a, p, k, j++) < (kp - kr) / rr) return false;
+      }
+    } else if (have_f && have_r) {
+      if (fr < fp && jb_policy_uniform(a, p, k, j++) < (fp - fr) / rr) return true;
+    } else if (have_k && have_r) {
+      if (kr < kp && jb_policy_uniform(a, p, k, j++) < (kp - kr) / rr) return false;
+    }
+    return jb_policy_uniform(a, p, k, j++) < awp;
+  }
+  return false;
+}
+
+// IndividualPolicies.apply (individual_policies.py:36-84): the person's allowed-activity mask.
+__device__ __noinline__ uint32_t jb_apply_policies(const PlaceArgs& a, uint32_t p, uint32_t st, uint32_t allowed) {
+  const uint32_t stay = (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
+  const PolicyDev& P = *a.pol;
+  const double rc = P.rc[a.pregion[p]];
+  const uint32_t attr = a.pattr ? a.pattr[p] : 0u, kind = JB_PA_KIND(attr);
+  const uint32_t age = a.age[p];
+  const bool infected = (st & JB_PS_INFECTED) != 0;
+  const int tagbit = infected ? JB_TAG_BIT(a.ptag[p]) : 0;
+  for (uint32_t k = 0; k < a.n_pol; ++k) {
+    const JbIndividualPolicy& q = P.pol[k];
+    switch (q.type) {
+      case JB_POL_SEVERE_STAY_HOME:
+        if (tagbit & a.severe_mask) return allowed & stay;
+        break;
+      case JB_POL_QUARANTINE: {
+        // time_of_symptoms_onset is 0 for every infection (symptoms.py:77-88 stops at the first
+        // trajectory entry), so release_day = n_days; the household branch never fires because a
+        // quarantine_starting_date of 0 is falsy (household.py:175-185)
+        const double release = 0.0 + q.p[0];
+        if ((tagbit & (int)q.mask) && 0 < release - a.sp->now && release - a.sp->now < q.p[0])
+          if (jb_policy_uniform(a, p, k, 0) < q.p[1] * rc) return allowed & stay;
+        break;
+      }
+      case JB_POL_SHIELDING:
+        if ((double)age >= q.p[0] && (isnan(q.p[1]) || jb_policy_uniform(a, p, k, 0) < q.p[1] * rc)) return allowed & stay;
+        break;
+      case JB_POL_CLOSE_SCHOOLS:
+        if (kind == 1u) {
+          bool skip = false;
+          if (q.flags & 1u) skip = true;
+          else if (!(age < 14u && (attr & JB_PA_TWO_KEY_WORKERS))) {
+            if (age < 32u && ((q.mask >> age) & 1u)) skip = true;
+            else if (jb_policy_uniform(a, p, k, 0) > q.p[0]) skip = true;
+          }
+          if (skip) allowed &= ~(1u << JB_ACT_PRIMARY);
+        }
+        break;
+      case JB_POL_CLOSE_UNIVERSITIES:
+        if (kind == 3u) allowed &= ~(1u << JB_ACT_PRIMARY);
+        break;
+      case JB_POL_CLOSE_COMPANIES:
+        if (kind == 2u && jb_close_companies_skips(a, p, k, q, (int)JB_PA_LOCKDOWN(attr)))
+          allowed &= ~((1u << JB_ACT_PRIMARY) | (1u << JB_ACT_COMMUTE));
+        break;
+      default: break;
+    }
+  }
+  return allowed;
+}
 
 // Append person p to the bin of dynamic group g (hospital ward, leisure venue).
 __device__ __forceinline__ void jb_dyn_scatter(const PlaceArgs& a, uint32_t g, uint32_t lsg, uint32_t p) {
@@ -64,7 +164,7 @@ __device__ __forceinline__ void jb_dyn_scatter(const PlaceArgs& a, uint32_t g, u
 // Leisure.get_subgroup_for_person_and_housemates (leisure.py:230-275) for social venues: does the
 // person go out, which activity, which of its area's candidate venues
 // (social_venue_distributor.py:257-266).  Returns the venue group (and its subgroup) or -1.
-__device__ __forceinline__ int32_t jb_leisure_venue(const PlaceArgs& a, uint32_t p, uint32_t& lsg) {
+__device__ __noinline__ int32_t jb_leisure_venue(const PlaceArgs& a, uint32_t p, uint32_t& lsg) {
   const LeisureDev& z = a.lz;
   if (a.ch[p]) return -1;  // care-home residents stay (leisure.py:246-248)
   if (z.inject) {
@@ -100,11 +200,14 @@ __device__ __forceinline__ uint32_t jb_place_key(uint32_t st, uint32_t has) {
   return (((st >> 3) & 0xFu) << 5) | (has & 0x1Fu);  // bits: INF DEAD SEVERE MED | has[5]
 }
 
+// FULL = false: neither leisure nor individual policies in this step -- the activity is a pure
+// table lookup per byte (the common weekday-night / no-lockdown step keeps its 48 registers).
+template <bool FULL>
 __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
   __shared__ uint8_t s_act[512];      // 0..4 activity, 7 none (dead), 15 alive without any activity
   __shared__ uint32_t s_cnt[8];
   const uint32_t mask = a.sp->activity_mask, flags = a.sp->flags;
-  const bool leisure_on = a.lz.K != 0 && (a.lz.inject != nullptr || a.sp->leisure_table != 0);
+  const bool leisure_on = FULL && a.lz.K != 0 && (a.lz.inject != nullptr || a.sp->leisure_table != 0);
   for (uint32_t k = threadIdx.x; k < 512; k += blockDim.x) {
     const uint32_t bits = k >> 5, has0 = k & 0x1Fu;
     const bool dead = bits & 2u, severe = bits & 4u, med = bits & 8u;
@@ -129,8 +232,19 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
   uint32_t noact = 0;
   const uint32_t n_chunks = (a.N + 15) / 16;
   auto one = [&](uint32_t p, uint32_t st, uint32_t has) -> uint32_t {
-    uint32_t act = s_act[jb_place_key(st, has)];
-    if (act & 0x80u) {  // leisure draw
+    uint32_t act;
+    if (FULL && a.n_pol && !(st & JB_PS_DEAD)) {
+      // individual policies decide per person (ages, tags, uniforms): the table's logic, inline
+      uint32_t allowed = mask;
+      if ((flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE)) allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
+      else allowed = jb_apply_policies(a, p, st, allowed);
+      const uint32_t cand = allowed & ((has & 0x1Fu) | ((st & JB_PS_MEDICAL) ? 1u << JB_ACT_MEDICAL : 0u));
+      act = cand ? (uint32_t)__ffs(cand) - 1u : 15u;
+      if (leisure_on && (allowed & (1u << JB_ACT_LEISURE)) && !(cand & ((1u << JB_ACT_LEISURE) - 1u))) act |= 0x80u;
+    } else {
+      act = s_act[jb_place_key(st, has)];
+    }
+    if (FULL && (act & 0x80u)) {  // leisure draw
       act &= 0x7Fu;
       uint32_t lsg = 0;
       const int32_t g = jb_leisure_venue(a, p, lsg);

@@ -356,7 +356,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
-                  w->cub_tmp, w->int2ext, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
+                  w->cub_tmp, w->int2ext, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (SgTiles& t : w->tiles) {
@@ -495,6 +495,50 @@ extern "C" int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person) {
   for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = group_per_person[p];
   if (!w->lz_inject) { TRY(dev_alloc(&w->lz_inject, v.size())); drop_graphs(w); }
   CK(cudaMemcpy(w->lz_inject, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
+// ---- individual policies ---------------------------------------------------------------------
+extern "C" int jb_set_individual_policies(JbWorld* w, const JbIndividualPolicy* pol, uint32_t n, const double* rc) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(n <= JB_MAX_POLICIES, "too many individual policies");
+  REQUIRE(n == 0 || w->R <= JB_MAX_REGIONS_POLICY, "too many regions for the policy table");
+  REQUIRE(n == 0 || pol != nullptr, "null policies");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  PolicyDev h;
+  memset(&h, 0, sizeof(h));
+  h.n = n;
+  for (uint32_t k = 0; k < n; ++k) h.pol[k] = pol[k];
+  for (uint32_t r = 0; r < w->R && r < JB_MAX_REGIONS_POLICY; ++r) h.rc[r] = rc ? rc[r] : 1.0;
+  if (!w->d_pol) TRY(dev_alloc(&w->d_pol, 1));
+  CK(cudaMemcpy(w->d_pol, &h, sizeof(h), cudaMemcpyHostToDevice));
+  if (w->n_pol != n) drop_graphs(w);  // the count is a launch argument
+  w->n_pol = n;
+  return JB_OK;
+}
+
+extern "C" int jb_set_person_attributes(JbWorld* w, const uint8_t* attr) {
+  if (!w || !attr) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  std::vector<uint8_t> v(std::max(1u, w->N), 0);
+  for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = attr[p];
+  if (!w->pattr) { TRY(dev_alloc(&w->pattr, v.size())); drop_graphs(w); }
+  CK(cudaMemcpy(w->pattr, v.data(), v.size(), cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
+extern "C" int jb_inject_policy_uniforms(JbWorld* w, const double* u) {
+  if (!w || !u) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  const size_t rows = (size_t)JB_MAX_POLICIES * JB_POLICY_DRAWS;
+  std::vector<double> v(rows * std::max(1u, w->N), 2.0);
+  for (size_t r = 0; r < rows; ++r)
+    for (uint32_t p = 0; p < w->N_ext; ++p) v[r * w->N + w->h_ext2int[p]] = u[r * w->N_ext + p];
+  if (!w->pol_inject) { TRY(dev_alloc(&w->pol_inject, v.size())); drop_graphs(w); }
+  CK(cudaMemcpy(w->pol_inject, v.data(), v.size() * 8, cudaMemcpyHostToDevice));
   return JB_OK;
 }
 
@@ -788,8 +832,13 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     if ((p.flags & JB_STEP_INJECT_LEISURE) && !w->lz_inject) { jb_set_error("JB_STEP_INJECT_LEISURE without jb_inject_leisure"); return JB_EINVAL; }
     pa.age = w->age; pa.sex = w->sex; pa.ch = w->ch; pa.pregion = w->pregion; pa.int2ext = w->int2ext;
     pa.gid_base = (uint32_t)w->id_base; pa.R = (int)w->R;
+    pa.pol = w->d_pol; pa.n_pol = w->n_pol; pa.ptag = w->ptag; pa.pattr = w->pattr;
+    pa.pol_inject = (p.flags & JB_STEP_INJECT_POLICY) ? w->pol_inject : nullptr;
+    pa.severe_mask = w->dis_host.severe_mask;
     const uint32_t chunks = (w->N + 15) / 16;
-    k_place<<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
+    const bool full = w->n_pol != 0 || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE)));
+    if (full) k_place<true><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
+    else k_place<false><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     KCHECK("k_place", s);
     w->launches++;
   }
@@ -909,7 +958,8 @@ static int run_phase(JbWorld* w, int phase, const void* p0, const void* p1, F&& 
   const bool plain = !w->use_graphs || w->timing >= 2 || jb_debug_sync() ||
                      (p.flags & (JB_STEP_INJECT_UNIFORMS | JB_STEP_RECORD_LAMBDA));
   if (plain) return enqueue();
-  const uint64_t k0 = ((uint64_t)phase << 56) | ((uint64_t)(w->serial ? 1 : 0) << 48) | ((uint64_t)p.activity_mask << 32) | p.flags;
+  const uint64_t k0 = ((uint64_t)phase << 56) | ((uint64_t)(w->serial ? 1 : 0) << 48) | ((uint64_t)(p.leisure_table ? 1 : 0) << 49) |
+                      ((uint64_t)p.activity_mask << 32) | p.flags;
   const uint64_t k1 = (uint64_t)(uintptr_t)p0, k2 = (uint64_t)(uintptr_t)p1;
   for (const JbWorld::GraphEntry& e : w->graphs)
     if (e.k0 == k0 && e.k1 == k1 && e.k2 == k2) {

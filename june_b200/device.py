@@ -12,8 +12,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (JbDisease, JbDist, JbInfectionRow, JbLeisureDesc, JbStepParams, JbStepStats, JbSupergroup,
-                   JbWorldDesc, SimulatorError, ptr)
+from ._lib import (JbDisease, JbDist, JbIndividualPolicy, JbInfectionRow, JbLeisureDesc, JbStepParams, JbStepStats,
+                   JbSupergroup, JbWorldDesc, SimulatorError, ptr)
 from .disease import DiseaseConfig, health_index_cum
 from .interaction import Interaction
 from .world import KIND_SCHOOL, MAX_STAGES, N_TPAR, SCHOOL_DIM, WorldSoA
@@ -106,6 +106,9 @@ class Engine:
         self._h = handle
         if world.has_leisure:
             self._set_leisure(world)
+        if world.person_attr is not None:
+            pa = np.ascontiguousarray(world.person_attr, dtype=np.uint8)
+            self._check(self._f("set_person_attributes")(self._h, ptr(pa)))
         if world.n_halo:
             hg = np.ascontiguousarray(world.halo_gid, dtype=np.uint32)
             self._check(self._f("set_halo_gids")(self._h, ptr(hg), hg.size))
@@ -141,6 +144,26 @@ class Engine:
         g = np.ascontiguousarray(group_per_person, dtype=np.int32)
         assert g.shape == (self.world.n_people,)
         self._check(self._f("inject_leisure")(self._h, ptr(g)))
+
+    # ---- individual policies ---------------------------------------------------------------------
+    def set_individual_policies(self, records: Sequence[dict], regional_compliance: Optional[Sequence[float]] = None):
+        """``records``: dicts with ``type`` (``_lib.POL_*``), optional ``flags``, ``mask`` and up to six
+        doubles ``p`` (None -> NaN), in the reference's policy-list order."""
+        n = len(records)
+        arr = (JbIndividualPolicy * max(1, n))()
+        for k, r in enumerate(records):
+            arr[k].type, arr[k].flags, arr[k].mask = int(r["type"]), int(r.get("flags", 0)), int(r.get("mask", 0))
+            for q, v in enumerate(list(r.get("p", []))[:6]):
+                arr[k].p[q] = float("nan") if v is None else float(v)
+        rc = np.ascontiguousarray(regional_compliance if regional_compliance is not None else np.ones(self.world.n_regions),
+                                  dtype=np.float64)
+        assert rc.shape == (self.world.n_regions,)
+        self._check(self._f("set_individual_policies")(self._h, arr, n, ptr(rc)))
+
+    def inject_policy_uniforms(self, u: np.ndarray):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.shape == (_lib.MAX_POLICIES, _lib.POLICY_DRAWS, self.world.n_people)
+        self._check(self._f("inject_policy_uniforms")(self._h, ptr(u)))
 
     # ---- plumbing ------------------------------------------------------------------------------
     def _f(self, name):

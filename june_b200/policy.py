@@ -5,7 +5,10 @@ names, constructor arguments and YAML schema (``june/policy/*.py``,
 * interaction policies -> ``interaction.beta_reductions`` (``interaction_policies.py:15-96``),
 * regional compliance / tiered lockdown -> per-region scalars (``regional_compliance.py:21-66``),
 * ``SevereSymptomsStayHome`` (``individual_policies.py:121-149``) and ``Hospitalisation``
-  (``medical_care_policies.py:413-526``) -> step flags evaluated per person on the device.
+  (``medical_care_policies.py:413-526``) -> step flags evaluated per person on the device,
+* ``Quarantine``, ``Shielding``, ``CloseSchools``, ``CloseUniversities``, ``CloseCompanies``
+  (``individual_policies.py:152-237,416-548,604-770``) -> one small record each; the placement
+  kernel evaluates the active records per person, in the reference's list order.
 
 Per-person work never happens here: a policy contributes either a few host scalars per step or a
 flag bit that switches a branch inside the placement / health kernels.
@@ -104,8 +107,100 @@ class Hospitalisation(Policy):
         self.disease_config = disease_config
 
 
+class Quarantine(Policy):
+    """``individual_policies.py:152-237``.  What reaches the device is what the reference actually
+    evaluates: ``infection.time_of_symptoms_onset`` is 0 for every infection (``symptoms.py:77-88``
+    stops at the first trajectory entry), hence ``release_day == n_days`` and the household branch
+    (``household.py:175-185``) never fires -- ``n_days_household`` and the household compliances are
+    accepted and unused, exactly as in the reference."""
+    policy_type = "individual"
+
+    def __init__(self, start_time: DateLike = "1900-01-01", end_time: DateLike = "2100-01-01", n_days: int = 7,
+                 n_days_household: int = 14, compliance: float = 1.0, household_compliance: float = 1.0,
+                 vaccinated_household_compliance: float = 1.0):
+        super().__init__(start_time, end_time)
+        self.n_days, self.n_days_household, self.compliance = n_days, n_days_household, compliance
+        self.household_compliance = household_compliance
+        self.vaccinated_household_compliance = vaccinated_household_compliance
+
+    def device_record(self, ctx) -> dict:
+        return dict(type=_lib.POL_QUARANTINE, mask=ctx["stay_at_home_mask"], p=[self.n_days, self.compliance])
+
+
+class Shielding(Policy):
+    """``individual_policies.py:416-439``."""
+    policy_type = "individual"
+
+    def __init__(self, start_time: DateLike, end_time: DateLike, min_age: int, compliance: Optional[float] = None):
+        super().__init__(start_time, end_time)
+        self.min_age, self.compliance = min_age, compliance
+
+    def device_record(self, ctx) -> dict:
+        return dict(type=_lib.POL_SHIELDING, p=[self.min_age, self.compliance])
+
+
+class CloseSchools(Policy):
+    """``individual_policies.py:480-530``."""
+    policy_type = "individual"
+
+    def __init__(self, start_time: DateLike, end_time: DateLike, years_to_close=None, attending_compliance: float = 1.0,
+                 full_closure=None):
+        super().__init__(start_time, end_time)
+        self.full_closure, self.attending_compliance = full_closure, attending_compliance
+        self.years_to_close = list(range(20)) if years_to_close == "all" else years_to_close
+
+    def device_record(self, ctx) -> dict:
+        mask = 0
+        for y in self.years_to_close or []:
+            if 0 <= int(y) < 32:
+                mask |= 1 << int(y)
+        return dict(type=_lib.POL_CLOSE_SCHOOLS, flags=1 if self.full_closure else 0, mask=mask,
+                    p=[self.attending_compliance])
+
+
+class CloseUniversities(Policy):
+    """``individual_policies.py:533-548``."""
+    policy_type = "individual"
+
+    def device_record(self, ctx) -> dict:
+        return dict(type=_lib.POL_CLOSE_UNIVERSITIES)
+
+
+class CloseCompanies(Policy):
+    """``individual_policies.py:604-770``.  ``initialize`` reproduces the reference's ratio
+    arithmetic literally, including the running normalisation of ``:641-643``."""
+    policy_type = "individual"
+    furlough_ratio = key_ratio = random_ratio = None
+
+    def __init__(self, start_time: DateLike, end_time: DateLike, full_closure: bool = False, avoid_work_probability=None,
+                 furlough_probability=None, key_probability=None):
+        super().__init__(start_time, end_time)
+        self.full_closure, self.avoid_work_probability = full_closure, avoid_work_probability
+        self.furlough_probability, self.key_probability = furlough_probability, key_probability
+
+    @classmethod
+    def initialize(cls, world, date=None, record=None):
+        """``world``: a ``WorldSoA`` with ``person_attr`` (lockdown status in bits 0-1)."""
+        import numpy as np
+        status = (world.person_attr & 3) if getattr(world, "person_attr", None) is not None else np.zeros(0, np.uint8)
+        f, k, r = (float(np.count_nonzero(status == c)) for c in (3, 1, 2))
+        if f != 0 and k != 0 and r != 0:
+            f /= f + k + r
+            k /= f + k + r
+            r /= f + k + r
+        else:
+            f = k = r = None
+        cls.furlough_ratio, cls.key_ratio, cls.random_ratio = f, k, r
+
+    def device_record(self, ctx) -> dict:
+        return dict(type=_lib.POL_CLOSE_COMPANIES, flags=1 if self.full_closure else 0,
+                    p=[self.avoid_work_probability, self.furlough_probability, self.key_probability,
+                       self.furlough_ratio, self.key_ratio, self.random_ratio])
+
+
 _CLASSES = {c.__name__: c for c in (SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
-                                    SevereSymptomsStayHome, Hospitalisation)}
+                                    SevereSymptomsStayHome, Hospitalisation, Quarantine, Shielding, CloseSchools,
+                                    CloseUniversities, CloseCompanies)}
 
 
 def _camel(key: str) -> str:
@@ -192,6 +287,20 @@ class Policies:
                 for r in region_names:
                     tiers[r] = int(p.tiers_per_region[r])
         return [comp[r] for r in region_names], [tiers[r] for r in region_names]
+
+    def device_policies(self, date: datetime.datetime, ctx: dict) -> List[dict]:
+        """Records of the active individual policies the placement kernel evaluates per person, in
+        list order (``IndividualPolicies.get_active``/``apply``, ``individual_policies.py:30-84``).
+        ``SevereSymptomsStayHome`` stays a step flag: it draws nothing, so its position is immaterial."""
+        return [p.device_record(ctx) for p in self.individual_policies
+                if hasattr(p, "device_record") and p.is_active(date)]
+
+    def init_policies(self, world, date=None, record=None) -> None:
+        """``Policies.init_policies`` (``policy/policy.py``): class-level set-up such as the
+        lockdown-status ratios of ``CloseCompanies``."""
+        for p in self.policies:
+            if hasattr(type(p), "initialize"):
+                type(p).initialize(world, date, record)
 
     def step_flags(self, date: datetime.datetime) -> int:
         flags = 0

@@ -188,6 +188,8 @@ class Simulator:
             import torch
             ptr = self.device._f("stream_handle")(self.device.handle)
             self._ext_stream = torch.cuda.ExternalStream(int(ptr), device=torch.device("cuda", self.device.device_index))
+        self._policy_key_on_device = None
+        self.activity_manager.policies.init_policies(world)
         self._leisure_tables: dict = {}   # time-slot key -> table index on the device
         self._leisure_stack: List[tuple] = []
         self.region_history: List[tuple] = []
@@ -224,9 +226,16 @@ class Simulator:
             self.interaction.beta_reductions = policies.beta_reductions(date)
             comp, tiers = policies.regional_scalars(date, self.world.region_names, self._region_state)
             beta = np.ascontiguousarray(self.interaction.beta_table(self.world.beta_rules, comp, tiers))
-            hit = (beta, policies.step_flags(date), dict(self.interaction.beta_reductions))
+            ctx = dict(stay_at_home_mask=self.disease_config.tag_mask("stay_at_home_stage"))
+            hit = (beta, policies.step_flags(date), dict(self.interaction.beta_reductions),
+                   policies.device_policies(date, ctx), list(comp))
             self._policy_cache[key] = hit
-        beta, flags, self.interaction.beta_reductions = hit
+        beta, flags, self.interaction.beta_reductions, records, comp = hit
+        if key != self._policy_key_on_device:
+            # the active set changed (a handful of times per run): refresh the device-resident table
+            if records or self._policy_key_on_device is not None:
+                self.device.set_individual_policies(records, comp)
+            self._policy_key_on_device = key
         return self.device.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self.step_ordinal,
                                        activity_mask=self.activity_manager.activity_mask(), seed=self.seed,
                                        flags=flags | extra_flags, beta=beta, leisure_table=self.leisure_table(key))

@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from .world import (ACT_LEISURE, ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, KIND_MATRIX, KIND_SCHOOL, BetaRule, Supergroup,
-                    WorldSoA, make_ginfo, make_info)
+                    WorldSoA, make_ginfo, make_info, make_person_attr)
 
 REGIONS = ["North East", "North West", "Yorkshire and The Humber", "East Midlands", "West Midlands",
            "East of England", "London", "South East", "South West"]
@@ -347,6 +347,23 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
         person_id_base=(rank * n_people if person_id_base is None else person_id_base),
         grp_super_area=grp_sa,
     )
+    # lockdown status of the workers (key 19 %, furlough 4 %, else "random": policy_covid19.yaml
+    # close_companies), spec of the primary activity, and the two-key-worker-household flag
+    lock = np.zeros(n, np.uint8)
+    wk = np.concatenate([teachers, hosp_workers, ch_workers, rest] + list(out_person.values())).astype(np.int64)
+    draw = np.random.default_rng([seed, rank, 4242]).random(len(wk))
+    lock[wk] = np.where(draw < 0.19, 1, np.where(draw < 0.23, 3, 2))
+    lock[hosp_workers] = 1
+    kind = np.zeros(n, np.uint8)
+    kind[kid] = 1
+    kind[teachers] = 1
+    kind[rest] = 2
+    kind[hosp_workers] = 4
+    kind[ch_workers] = 4
+    for sel in out_person.values():
+        kind[sel] = 2
+    n_key = np.bincount(hh_of, weights=(lock == 1), minlength=n_hh)
+    w.person_attr = make_person_attr(lock, kind, (n_key[hh_of] > 1) & ~in_care)
     if leisure:
         w.person_area = area_of_hh[hh_of].astype(np.uint32)
         w.leisure_supergroups = list(LEISURE_ORDER)

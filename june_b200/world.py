@@ -39,6 +39,15 @@ ACTIVITY_NAMES = {v: k for k, v in ACTIVITY_CODES.items()}
 PS_ACT_MASK, PS_INFECTED, PS_DEAD, PS_SEVERE, PS_MEDICAL = 0x07, 0x08, 0x10, 0x20, 0x40
 
 KIND_MATRIX, KIND_SCHOOL = 0, 1
+# person_attr fields
+LOCKDOWN_CODES = {None: 0, "key_worker": 1, "random": 2, "furlough": 3}
+PRIMARY_KIND_CODES = {"school": 1, "company": 2, "university": 3}
+PA_TWO_KEY_WORKERS = 0x20
+
+
+def make_person_attr(lockdown, kind, two_key_workers):
+    return (np.asarray(lockdown, np.uint8) | (np.asarray(kind, np.uint8) << 2)
+            | np.where(np.asarray(two_key_workers, bool), PA_TWO_KEY_WORKERS, 0).astype(np.uint8)).astype(np.uint8)
 SCHOOL_DIM = 32
 MAX_STAGES = 8
 N_TPAR = 5
@@ -126,11 +135,14 @@ class WorldSoA:
     leisure_subgroups: List[int] = field(default_factory=list)      # leisure_subgroup_type per activity
     area_venue_off: Optional[np.ndarray] = None   # uint32 [n_areas * K + 1]
     area_venue: Optional[np.ndarray] = None       # uint32 group indices
+    # static facts the individual policies read (include/june_b200.h: JB_PA_*): lockdown status,
+    # spec of the primary-activity group, ">= 2 key workers among the household's residents"
+    person_attr: Optional[np.ndarray] = None      # uint8 [n_people]
 
     _ARRAYS = ("age", "sex", "care_home_resident", "has_activity", "super_area", "sa_hospital", "sa_region",
                "grp_offset", "grp_info", "grp_aux", "reg_member", "reg_info", "school_years", "beta_scale",
                "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids", "grp_super_area",
-               "person_area", "area_venue_off", "area_venue")
+               "person_area", "area_venue_off", "area_venue", "person_attr")
 
     @property
     def n_people(self) -> int:

@@ -57,14 +57,14 @@ ROW_LEN = 5 + 5 + 2 * MAX_STAGES
 
 
 def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000,
-              with_leisure=False):
+              with_leisure=False, lockdown=False):
     pyrandom.seed(seed)
     np.random.seed(seed)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink):
         world, dc = ref_world.build_world(n_people, seed=seed, with_leisure=with_leisure)
         sim = ref_world.make_simulator(world, dc, total_days=total_days, cases_per_capita=cases_per_capita,
-                                       schedule=schedule, with_leisure=with_leisure)
+                                       schedule=schedule, with_leisure=with_leisure, lockdown=lockdown)
     import june.interaction.interaction as inter_mod
     import june.policy.individual_policies as indiv_mod
     from june.epidemiology.infection import InfectionSelector
@@ -123,6 +123,26 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
     Interaction._time_step_for_subgroup = sub
     InfectionSelector.infect_person_at_time = infect
 
+    # ---- individual policies: every random() they consume, tagged (policy class, draw, person) -----
+    pol_state = {"name": None, "person": None, "j": 0, "draws": []}
+    prng = np.random.default_rng(4321 + seed)
+
+    def policy_random():
+        u = float(prng.random())
+        pol_state["draws"].append((pol_state["name"], pol_state["j"], pidx[pol_state["person"].id], u))
+        pol_state["j"] += 1
+        return u
+
+    if lockdown:
+        indiv_mod.random = policy_random
+        for pol in sim.activity_manager.policies.individual_policies.policies:
+            for meth in ("check_stay_home_condition", "check_skips_activity"):
+                if hasattr(pol, meth):
+                    def wrapped(person, *a, _f=getattr(pol, meth), _n=type(pol).__name__, **kw):
+                        pol_state["name"], pol_state["person"], pol_state["j"] = _n, person, 0
+                        return _f(person, *a, **kw)
+                    setattr(pol, meth, wrapped)
+
     steps = []
     orig_step = Simulator.do_timestep
     orig_am = type(sim.activity_manager).do_timestep
@@ -166,6 +186,7 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         rec["pre_rows"] = np.array(state["rows"], np.float64).reshape(-1, ROW_LEN)
         state["rows"] = []
         state["draw_person"], state["draw_lambda"], state["draw_u"] = [], [], []
+        pol_state["draws"] = []
         timer = self.timer
         rec["now"], rec["dt"] = float(timer.now), float(timer.duration)
         mask = 0
@@ -179,6 +200,13 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         rec["draw_u"] = np.array(state["draw_u"], np.float64)
         rec["new_rows"] = np.array(state["rows"], np.float64).reshape(-1, ROW_LEN)
         state["rows"] = []
+        if lockdown:
+            names = sorted({d[0] for d in pol_state["draws"]})
+            rec["pol_names"] = np.array(names if names else ["-"])
+            rec["pol_draws"] = np.array([[names.index(d[0]), d[1], d[2], d[3]] for d in pol_state["draws"]],
+                                        np.float64).reshape(-1, 4)
+            rec["pol_active"] = np.array([type(p).__name__ for p in
+                                          self.activity_manager.policies.individual_policies.get_active(date=timer.date).policies] or ["-"])
         rec["post"] = snapshot()
         steps.append(rec)
 
@@ -208,6 +236,10 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
     out["health_index_prob"] = prob
     for k, m in interaction.contact_matrices.items():
         out["cm_" + k] = np.asarray(m, np.float64)
+    if lockdown:
+        from june.policy import CloseCompanies
+        out["close_companies_ratios"] = np.array([CloseCompanies.furlough_ratio, CloseCompanies.key_ratio,
+                                                  CloseCompanies.random_ratio], np.float64)
     out["beta_keys"] = np.array(list(interaction.betas.keys()))
     out["beta_vals"] = np.array(list(interaction.betas.values()), np.float64)
     for i, rec in enumerate(steps):
@@ -254,6 +286,9 @@ def spot_values(out_name="spot"):
 if __name__ == "__main__":
     if "leisure" in sys.argv[1:]:  # leisure placement (pubs, cinemas, groceries) on top of the w3k recipe
         run_trace(2500, 9, 2, "w2k_leisure", cases_per_capita=0.04, with_leisure=True)
+        sys.exit(0)
+    if "policies" in sys.argv[1:]:  # Quarantine, Shielding, CloseSchools, CloseCompanies switching on day by day
+        run_trace(2500, 9, 3, "w2k_policies", cases_per_capita=0.05, lockdown=True)
         sys.exit(0)
     run_trace(3000, 12, 0, "w3k")
     run_trace(1200, 40, 1, "w1k_long", cases_per_capita=0.05, schedule="simple")

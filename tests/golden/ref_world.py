@@ -186,6 +186,13 @@ def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
             c.add(w)
             w.busy = False
             w.sector = c.sector
+    # lockdown status of everybody with a primary activity that is not a school pupil
+    # (CloseCompanies / CloseSchools read it, individual_policies.py:497-510,651-770)
+    lrng = np.random.default_rng(seed + 77)
+    for p in people:
+        if p.primary_activity is not None and p.age > 18:
+            u = lrng.random()
+            p.lockdown_status = "key_worker" if u < 0.25 else "furlough" if u < 0.35 else "random"
 
     world = World()
     world.areas = Areas(areas, ball_tree=False)
@@ -220,7 +227,7 @@ def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
 
 
 def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policies=True,
-                   initial_day="2020-03-02 0:00", schedule="default", with_leisure=False):
+                   initial_day="2020-03-02 0:00", schedule="default", with_leisure=False, lockdown=False):
     """Reference Simulator wired as ``example_scripts/run_simulation.py:332-512`` does, minus
     leisure / travel / records."""
     ref_harness.setup()
@@ -272,6 +279,18 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
                       weekday_step_duration=wd_dur, weekend_step_duration=we_dur,
                       weekday_activities=wd_act, weekend_activities=we_act)
     pol = [Hospitalisation(disease_config=dc), SevereSymptomsStayHome(start_time="1900-01-01", end_time="2100-01-01")] if with_policies else []
+    if lockdown:
+        from june.policy import CloseCompanies, CloseSchools, Quarantine, Shielding
+        pol += [
+            Quarantine(start_time="2020-03-03", end_time="2100-01-01", n_days=7, n_days_household=14, compliance=0.8,
+                       household_compliance=0.9),
+            Shielding(start_time="2020-03-04", end_time="2100-01-01", min_age=70, compliance=0.6),
+            CloseSchools(start_time="2020-03-05", end_time="2100-01-01", years_to_close=[5, 6, 7, 12, 13, 17],
+                         attending_compliance=0.7),
+            CloseCompanies(start_time="2020-03-06", end_time="2100-01-01", avoid_work_probability=0.3,
+                           furlough_probability=0.2, key_probability=0.2),
+        ]
+        CloseCompanies.initialize(world, None, None)
     policies = Policies(pol)
     a2sg = {
         "medical_facility": ["hospitals"] if world.hospitals is not None else [],

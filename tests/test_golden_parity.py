@@ -25,6 +25,18 @@ FLAGS = (_lib.STEP_SEVERE_STAY_HOME | _lib.STEP_HOSPITALISATION | _lib.STEP_INJE
          | _lib.STEP_NO_NEW_INFECTIONS | _lib.STEP_RECORD_LAMBDA)
 
 
+# parameters of the lockdown policies of the w2k_policies trace (tests/golden/ref_world.py:make_simulator)
+def policy_records(names, ratios):
+    f, k, r = (None if np.isnan(x) else float(x) for x in ratios)
+    table = {
+        "Quarantine": dict(type=_lib.POL_QUARANTINE, mask=(1 << (2 + 2)) | (1 << (3 + 2)), p=[7, 0.8]),  # mild, severe
+        "Shielding": dict(type=_lib.POL_SHIELDING, p=[70, 0.6]),
+        "CloseSchools": dict(type=_lib.POL_CLOSE_SCHOOLS, mask=sum(1 << y for y in (5, 6, 7, 12, 13, 17)), p=[0.7]),
+        "CloseCompanies": dict(type=_lib.POL_CLOSE_COMPANIES, p=[0.3, 0.2, 0.2, f, k, r]),
+    }
+    return [(n, table[n]) for n in names if n in table]
+
+
 def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     g = Golden(name)
     if launch_modes is not None:  # exercise the other kernel flavour on the same trace
@@ -52,6 +64,19 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
             at_venue = (pg >= 0) & (sg_act[grp_sg[np.maximum(pg, 0)]] == ACT_LEISURE)
             eng.inject_leisure(np.where(at_venue, pg, -1).astype(np.int32))
             flags |= _lib.STEP_INJECT_LEISURE
+        if "pol_active" in s:
+            # individual policies: the reference's active list (in order) and every random() it drew
+            recs = policy_records([str(x) for x in s["pol_active"]], g.z["close_companies_ratios"])
+            eng.set_individual_policies([r for _, r in recs], np.ones(g.world.n_regions))
+            u = np.full((_lib.MAX_POLICIES, _lib.POLICY_DRAWS, n), np.nan)
+            index = {nm: k for k, (nm, _) in enumerate(recs)}
+            names = [str(x) for x in s["pol_names"]]
+            for row in s["pol_draws"]:
+                u[index[names[int(row[0])]], int(row[1]), int(row[2])] = row[3]
+            eng.inject_policy_uniforms(u)
+            flags |= _lib.STEP_INJECT_POLICY
+            n_policy_draws = getattr(run_trace, "policy_draws", 0) + len(s["pol_draws"])
+            run_trace.policy_draws = n_policy_draws
         p = eng.make_params(now=float(s["now"]), delta_time=float(s["dt"]), step=i,
                             activity_mask=int(s["activity_mask"]), seed=0, flags=flags, beta=beta)
         eng.step_begin(p)
@@ -110,9 +135,12 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     return total_draws, total_inf, worst
 
 
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies"])
 def test_oracle_matches_reference_trace(name):
+    run_trace.policy_draws = 0
     draws, infections, worst = run_trace("oracle", name)
+    if name == "w2k_policies":
+        assert run_trace.policy_draws > 5000, "the lockdown policies must have drawn"
     assert draws > 10000 and infections > 100
     assert worst <= REL
 
@@ -128,7 +156,7 @@ LAUNCH_MODES = {
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("modes", ["tiles", "warps", "mixed"])
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies"])
 def test_cuda_matches_reference_trace(name, modes):
     assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
     draws, infections, worst = run_trace("cuda", name, launch_modes=LAUNCH_MODES[modes])
