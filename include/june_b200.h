@@ -194,6 +194,7 @@ typedef struct {
 #define JB_STEP_RECORD_LAMBDA 0x10u   /* keep per-person Lambda of this step for jb_fetch_lambda   */
 #define JB_STEP_INJECT_LEISURE 0x20u  /* leisure venues come from jb_inject_leisure (test mode)    */
 #define JB_STEP_INJECT_POLICY 0x40u   /* policy uniforms come from jb_inject_policy_uniforms        */
+#define JB_STEP_RECORD_EVENTS 0x80u   /* keep {where, infector} of every new infection (records)    */
 
 /* Per-step outputs (the d2h payload of every step). */
 typedef struct {
@@ -347,6 +348,13 @@ int jb_fetch_person_state(JbWorld* w, uint8_t* pstate, int8_t* tag, double* tran
                           double* susceptibility, int32_t* medical);
 int jb_fetch_lambda(JbWorld* w, double* lambda_out); /* n_people + n_halo, NaN where no draw */
 int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap, size_t* n);
+/* Infection events of the last step run with JB_STEP_RECORD_EVENTS: the rows of the reference's
+ * "infections" record table (interaction.py:664-683, records/event_records_writer.py:60-84) --
+ * who was infected, in which group, with which variant, and the infector chosen by
+ * _blame_subgroup / _blame_individuals (interaction.py:643-662).  Person indices are local
+ * (halo persons: n_people + halo index); sorted by infected person. */
+int jb_fetch_infection_events(JbWorld* w, uint32_t* infected, uint32_t* infector, uint32_t* group,
+                              uint32_t* variant, size_t cap, size_t* n);
 /* per-region summary: counts[n_regions][JB_N_SUMMARY] (records_writer.py:151-164) */
 #define JB_N_SUMMARY 8
 int jb_fetch_summary(JbWorld* w, uint32_t* counts);

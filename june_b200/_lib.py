@@ -24,6 +24,7 @@ ABI_VERSION = 1
 JB_OK, JB_EINVAL, JB_ECUDA, JB_ENOACT, JB_ECAP, JB_ENOGPU = 0, 1, 2, 3, 4, 5
 STEP_SEVERE_STAY_HOME, STEP_HOSPITALISATION, STEP_INJECT_UNIFORMS = 0x1, 0x2, 0x4
 STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE, STEP_INJECT_POLICY = 0x8, 0x10, 0x20, 0x40
+STEP_RECORD_EVENTS = 0x80
 MAX_POLICIES, POLICY_DRAWS = 8, 3
 POL_SEVERE_STAY_HOME, POL_QUARANTINE, POL_SHIELDING, POL_CLOSE_SCHOOLS, POL_CLOSE_UNIVERSITIES, POL_CLOSE_COMPANIES = 1, 2, 3, 4, 5, 6
 
@@ -111,7 +112,7 @@ ABI_SYMBOLS = [
     "set_halo", "halo_record_size", "halo_return_size", "sync", "fetch_new_infections", "fetch_person_state",
     "fetch_lambda", "fetch_infections", "fetch_summary", "timing_enable", "timing_read", "last_step_bytes",
     "set_concurrency", "set_leisure", "set_leisure_tables", "inject_leisure",
-    "set_individual_policies", "set_person_attributes", "inject_policy_uniforms",
+    "set_individual_policies", "set_person_attributes", "inject_policy_uniforms", "fetch_infection_events",
 ]
 
 
@@ -170,6 +171,7 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("set_individual_policies").argtypes = [vp, C.POINTER(JbIndividualPolicy), C.c_uint32, vp]
     f("set_person_attributes").argtypes = [vp, vp]
     f("inject_policy_uniforms").argtypes = [vp, vp]
+    f("fetch_infection_events").argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp]),
                         ("timing_read_supergroups", [vp, dp, C.POINTER(C.c_uint64), C.c_int]),
                         ("set_concurrency", [vp, C.c_int])):

@@ -59,7 +59,7 @@ struct JbMember {
 };
 
 // Member `idx` of group (static registered slots first, then the sorted dynamic members, which
-// the CTA has staged in shared memory as (lsg << 28) | person).
+// the CTA has staged in shared memory as (lsg << 28) | person, sorted).
 __device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t idx, uint32_t b, uint32_t ns,
                                                    const uint32_t* dyn_s, uint32_t ntot) {
   JbMember mbr;
@@ -73,8 +73,8 @@ __device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t 
     const uint32_t pres = (hot & JB_PS_ACT_MASK) == JB_INFO_ACT(info) ? 1u : 0u;
     mbr.k = JB_INFO_LSG(info) | (hot << 16) | (pres << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
   } else {
-    const uint32_t k = dyn_s[idx - ns];
-    mbr.p = k & 0x0FFFFFFFu;
+    const uint32_t k = dyn_s[idx - ns];  // (lsg << 28) | caller's person index
+    mbr.p = a.ext2int[k & 0x0FFFFFFFu];
     const uint32_t hot = a.phot[mbr.p];
     mbr.k = (k >> 28) | (hot << 16) | (1u << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
   }
@@ -102,7 +102,46 @@ __device__ __forceinline__ void jb_grp_sync() {
   if (WPG == 1) __syncwarp(); else __syncthreads();
 }
 
-template <int VM, int WPG>
+// Rare path (a draw succeeded and events are recorded), kept out of line so that it does not
+// cost the hot loop registers.  _blame_subgroup (interaction.py:643-645): infector subgroup j with
+// probability ~ its term of the susceptible's row; _blame_individuals (:647-662): infector with
+// probability ~ transmission probability inside that subgroup, in member order.
+template <int VM>
+__device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, uint32_t p, int i, int v, uint32_t b, uint32_t ns,
+                                                uint32_t ntot, const uint32_t* dyn_s, int Lg, const uint8_t* years,
+                                                int n_years, const uint32_t* n_l, const double* T, double row,
+                                                double beta, double dt) {
+  double u_sub, u_ind;
+  jb_blame_uniforms(a, p, u_sub, u_ind);
+  const double target = u_sub * row;
+  double c = 0.0;
+  int jb = -1, jlast = 0;
+  for (int j = 0; j < Lg && jb < 0; ++j) {
+    const double t = T[j];
+    if (t == 0.0) continue;
+    const int nj = (int)n_l[j];
+    const int nn = (i == j) ? max(1, nj - 1) : nj;
+    c += jb_cm_elem(a, i, j, years, n_years) * t / (double)nn * beta * dt;
+    jlast = j;
+    if (c > target) jb = j;
+  }
+  if (jb < 0) jb = jlast;
+  const double target2 = u_ind * T[jb];
+  double c2 = 0.0;
+  uint32_t infector = 0xFFFFFFFFu;
+  for (uint32_t idx = 0; idx < ntot; ++idx) {
+    const JbMember o = jb_load_member(a, idx, b, ns, dyn_s, ntot);
+    if (!o.infector() || (int)o.lsg() != jb || (VM > 1 && (int)JB_HOT_VAR(o.hot()) != v)) continue;
+    c2 += a.trans[o.p];
+    infector = o.p;
+    if (c2 > target2) break;
+  }
+  return infector;
+}
+
+// EV: record infection events (who infected whom, JB_STEP_RECORD_EVENTS).  A separate
+// instantiation, so that the rare blame path costs the common launch neither registers nor stack.
+template <int VM, int WPG, bool EV>
 __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ GroupArgs a) {
   extern __shared__ __align__(8) unsigned char smem_raw[];
   constexpr int GT = 32 * WPG;                 // threads per group
@@ -338,7 +377,16 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
               lam += lam_v[v];
             }
             if (a.lambda) a.lambda[mb.p] = lam;
-            if (lam != 0.0) jb_draw_core<VM>(a, mb.p, lam_v, lam, ordinal);  // lambda == 0 can never infect
+            if (lam != 0.0) {  // lambda == 0 can never infect
+              const int v = jb_draw_core<VM>(a, mb.p, lam_v, lam, ordinal);
+              if (v >= 0) {
+                uint32_t infector = 0xFFFFFFFFu;
+                if (EV)
+                  infector = jb_blame_group<VM>(a, mb.p, (int)mb.lsg(), v, b, ns, ntot, dyn_s, Lg, years, n_years, n_l,
+                                                T_w + (size_t)v * L, row_l[v * L + mb.lsg()], beta, dt);
+                jb_emit(a, mb.p, (uint32_t)v, g, infector);
+              }
+            }
           }
         }
       }
@@ -373,7 +421,7 @@ __device__ __forceinline__ void jb_prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
-template <bool STREAM, int VM>
+template <bool STREAM, int VM, bool EV>
 // (stream tiles are occupancy hungry: 48 registers measured 20 % faster than 70; the gather
 // flavour keeps its registers for the 16 gathers in flight per thread)
 __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(const __grid_constant__ GroupArgs a) {
@@ -384,6 +432,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
   __shared__ uint32_t s_n;
   __shared__ double q_lam[JB_TILE_WARPS][VM][JB_DRAW_QUEUE];
   __shared__ uint32_t q_p[JB_TILE_WARPS][JB_DRAW_QUEUE], q_ord[JB_TILE_WARPS][JB_DRAW_QUEUE];
+  __shared__ uint16_t q_item[JB_TILE_WARPS][JB_DRAW_QUEUE];  // work item of the queued draw (blame)
   const uint8_t* s_hot = reinterpret_cast<const uint8_t*>(s_hot4);
   const uint8_t* s_info = reinterpret_cast<const uint8_t*>(s_info4);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -491,7 +540,71 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
       double lam = 0.0;
 #pragma unroll
       for (int v = 0; v < VM; ++v) { lam_v[v] = q_lam[wib][v][lane]; lam += lam_v[v]; }
-      jb_draw_core<VM>(a, q_p[wib][lane], lam_v, lam, q_ord[wib][lane]);
+      const uint32_t p = q_p[wib][lane];
+      const int v = jb_draw_core<VM>(a, p, lam_v, lam, q_ord[wib][lane]);
+      if (v >= 0) {
+        const uint2 it = s_items[q_item[wib][lane]];
+        uint32_t infector = 0xFFFFFFFFu;
+        if (EV) {
+          // rare path: rebuild the group's sums from the block's shared-memory copy of the slots,
+          // then _blame_subgroup / _blame_individuals (interaction.py:643-662)
+          const uint32_t loc = it.x >> 5, len = (it.x & 31u) + 1u;
+          uint32_t npk = 0, my_i = 0;
+          double Tj[4] = {0.0, 0.0, 0.0, 0.0};
+          for (uint32_t m = 0; m < len; ++m) {
+            const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
+            if (((hot ^ info) & JB_PS_ACT_MASK) != 0u) continue;
+            const uint32_t q = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+            const int l = (int)JB_TI_LSG(info);
+            npk += 1u << (8 * l);
+            if (q == p) my_i = (uint32_t)l;
+            if ((hot & JB_PS_INFECTED) && (VM == 1 || (int)JB_HOT_VAR(hot) == v)) {
+              const double t = a.trans[q];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j == l) Tj[j] += t;
+            }
+          }
+          const uint32_t gi = a.grp_info[it.y];
+          const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+          double term[4], total = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            term[j] = 0.0;
+            if (j < dim && Tj[j] != 0.0) {
+              const int nj = (int)((npk >> (8 * j)) & 0xFFu);
+              const int nn = ((int)my_i == j) ? max(1, nj - 1) : nj;
+              term[j] = s_cm[my_i * dim + j] * Tj[j] / (double)nn * beta * dt;
+              total += term[j];
+            }
+          }
+          double u_sub, u_ind;
+          jb_blame_uniforms(a, p, u_sub, u_ind);
+          const double target = u_sub * total;
+          double c = 0.0;
+          int jb = -1, jlast = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (term[j] != 0.0 && jb < 0) { c += term[j]; jlast = j; if (c > target) jb = j; }
+          if (jb < 0) jb = jlast;
+          double tsel = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j == jb) tsel = Tj[j];
+          const double target2 = u_ind * tsel;
+          double c2 = 0.0;
+          for (uint32_t m = 0; m < len; ++m) {
+            const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
+            if (((hot ^ info) & JB_PS_ACT_MASK) != 0u || !(hot & JB_PS_INFECTED) || (int)JB_TI_LSG(info) != jb) continue;
+            if (VM > 1 && (int)JB_HOT_VAR(hot) != v) continue;
+            const uint32_t q = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+            c2 += a.trans[q];
+            infector = q;
+            if (c2 > target2) break;
+          }
+        }
+        jb_emit(a, p, (uint32_t)v, it.y, infector);
+      }
     }
     __syncwarp();
   };
@@ -591,6 +704,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
           const uint32_t pos = qn + __popc(wm & lane_lt);
           q_p[wib][pos] = p;
           q_ord[wib][pos] = ord;
+          if (EV) q_item[wib][pos] = (uint16_t)w;
 #pragma unroll
           for (int v = 0; v < VM; ++v) q_lam[wib][v][pos] = lam_v[v];
         }
@@ -599,16 +713,16 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
         if (qn >= 32) {
           drain(32);
           const uint32_t rest = qn - 32;
-          uint32_t mp = 0, mo = 0;
+          uint32_t mp = 0, mo = 0, mi = 0;
           double ml[VM];
           if ((uint32_t)lane < rest) {
-            mp = q_p[wib][32 + lane]; mo = q_ord[wib][32 + lane];
+            mp = q_p[wib][32 + lane]; mo = q_ord[wib][32 + lane]; mi = q_item[wib][32 + lane];
 #pragma unroll
             for (int v = 0; v < VM; ++v) ml[v] = q_lam[wib][v][32 + lane];
           }
           __syncwarp();
           if ((uint32_t)lane < rest) {
-            q_p[wib][lane] = mp; q_ord[wib][lane] = mo;
+            q_p[wib][lane] = mp; q_ord[wib][lane] = mo; q_item[wib][lane] = (uint16_t)mi;
 #pragma unroll
             for (int v = 0; v < VM; ++v) q_lam[wib][v][lane] = ml[v];
           }

@@ -120,6 +120,7 @@ struct GroupArgs {
   const uint32_t* group_list; // explicit groups for the warp kernel (big groups), or null = [g0, g1)
   uint32_t n_list;
   const uint32_t* int2ext;    // internal -> caller person index
+  const uint32_t* ext2int;    // caller -> internal person index
   const uint32_t* tile_group0;
   const uint32_t* tp_member;
   const uint8_t* tp_info;
@@ -133,6 +134,11 @@ struct GroupArgs {
   uint32_t* newinf_member;
   uint8_t* newinf_var;
   uint32_t newinf_cap;
+  // infection events (JB_STEP_RECORD_EVENTS): same index as newinf_member; null otherwise
+  uint32_t* ev_infected;
+  uint32_t* ev_infector;
+  uint32_t* ev_group;
+  uint8_t* ev_var;
   double* lambda;            // null unless JB_STEP_RECORD_LAMBDA
   const double* inject;      // null unless JB_STEP_INJECT_UNIFORMS
   const uint32_t* draw_base; // exclusive scan of draw_cnt (inject mode)
@@ -179,7 +185,7 @@ struct JbWorld {
   // N_ext = residents as the caller numbers them
   uint32_t N = 0, N_ext = 0, H = 0, NP = 0, G = 0, M = 0, V = 1, R = 1, SA = 0, C = 0, newinf_cap = 0;
   std::vector<uint32_t> h_ext2int, h_int2ext;  // int2ext == 0xFFFFFFFF for padding
-  uint32_t* int2ext = nullptr;
+  uint32_t *int2ext = nullptr, *ext2int = nullptr;
   std::vector<SgTiles> tiles;
   uint32_t n_beta = 0, n_scale = 0, n_out = 0;
   uint64_t id_base = 0;
@@ -216,6 +222,9 @@ struct JbWorld {
   size_t counter_words = 0;
   uint32_t* newinf_member = nullptr;
   uint8_t* newinf_var = nullptr;
+  uint32_t *ev_infected = nullptr, *ev_infector = nullptr, *ev_group = nullptr;  // allocated on first use
+  uint8_t* ev_var = nullptr;
+  uint32_t ev_count = 0;  // events of the last step that recorded them
   double* beta = nullptr;
   double* lambda = nullptr;
   double* inject = nullptr;

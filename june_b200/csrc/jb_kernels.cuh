@@ -154,7 +154,8 @@ __device__ __forceinline__ void jb_dyn_scatter(const PlaceArgs& a, uint32_t g, u
     const uint32_t k = g - a.dr.first[r];
     if (k < a.dr.count[r]) {
       const uint32_t i = atomicAdd(&a.dyn_cnt[a.dr.cnt_base[r] + k], 1u);
-      if (i < a.dr.cap[r]) { a.dyn_bin[(size_t)a.dr.slot_base[r] + (size_t)k * a.dr.cap[r] + i] = (lsg << 28) | p; return; }
+      // the bin is sorted later: key on the CALLER's person index, the order the reference appends in
+      if (i < a.dr.cap[r]) { a.dyn_bin[(size_t)a.dr.slot_base[r] + (size_t)k * a.dr.cap[r] + i] = (lsg << 28) | a.int2ext[p]; return; }
       break;
     }
   }
@@ -305,48 +306,52 @@ __device__ __forceinline__ uint32_t jb_gid(const GroupArgs& a, uint32_t p) {
   return p < a.N ? a.gid_base + a.int2ext[p] : a.halo_gid[p - a.N];
 }
 
-// Append one new infection.
-__device__ __forceinline__ void jb_emit(const GroupArgs& a, uint32_t p, uint32_t v) {
+// Append one new infection (and, when events are recorded, where and by whom).
+__device__ __forceinline__ void jb_emit(const GroupArgs& a, uint32_t p, uint32_t v, uint32_t g, uint32_t infector) {
   uint32_t i = atomicAdd(&a.counters[CNT_NEWINF], 1u);
   if (i < a.newinf_cap) {
     a.newinf_member[i] = p;
     a.newinf_var[i] = (uint8_t)v;
+    if (a.ev_group) { a.ev_infected[i] = p; a.ev_var[i] = (uint8_t)v; a.ev_group[i] = g; a.ev_infector[i] = infector; }
   } else {
     atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
   }
 }
 
-// Bernoulli draw + variant choice for one susceptible (interaction.py:610-641).
+// Bernoulli draw + variant choice for one susceptible (interaction.py:610-641).  Returns the
+// variant the person caught, or -1.
 template <int VM>
-__device__ __forceinline__ void jb_draw_core(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
-                                             uint32_t ordinal) {
+__device__ __forceinline__ int jb_draw_core(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
+                                            uint32_t ordinal) {
   double u;
   if (a.inject) {
     u = ordinal < a.sp->n_inject ? a.inject[ordinal] : 2.0;
   } else {
     u = jb_bernoulli_uniform(a.sp->seed, a.sp->step, jb_gid(a, p));
   }
-  if (u < 1.0 - exp(-lam)) {
-    uint32_t v = 0;
-    if (VM > 1 && a.V > 1) {
-      // np.random.choice(ids, p=lam_v/lam): inverse CDF on a second, independent uniform
-      double u2 = jb_variant_uniform(a.sp->seed, a.sp->step, jb_gid(a, p)) * lam;
-      double c = 0.0;
-      v = a.V - 1;
-      for (int k = 0; k < a.V; ++k) {
-        c += lam_v[k];
-        if (u2 < c) { v = k; break; }
-      }
+  if (!(u < 1.0 - exp(-lam))) return -1;
+  uint32_t v = 0;
+  if (VM > 1 && a.V > 1) {
+    // np.random.choice(ids, p=lam_v/lam): inverse CDF on a second, independent uniform
+    double u2 = jb_variant_uniform(a.sp->seed, a.sp->step, jb_gid(a, p)) * lam;
+    double c = 0.0;
+    v = a.V - 1;
+    for (int k = 0; k < a.V; ++k) {
+      c += lam_v[k];
+      if (u2 < c) { v = k; break; }
     }
-    jb_emit(a, p, v);
   }
+  return (int)v;
 }
 
-template <int VM>
-__device__ __forceinline__ void jb_draw(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
-                                        uint32_t ordinal) {
-  if (a.lambda) a.lambda[p] = lam;
-  jb_draw_core<VM>(a, p, lam_v, lam, ordinal);
+// The two uniforms of an infection's blame (_blame_subgroup / _blame_individuals,
+// interaction.py:643-662): np.random.choice(p=...) picks the first index whose cumulative
+// probability exceeds the uniform.
+__device__ __forceinline__ void jb_blame_uniforms(const GroupArgs& a, uint32_t p, double& u_sub, double& u_ind) {
+  const JbPhilox4 r = jb_philox4x32_10(jb_gid(a, p), a.sp->step, JB_STREAM_BLAME, 0u, (uint32_t)a.sp->seed,
+                                       (uint32_t)(a.sp->seed >> 32));
+  u_sub = jb_u52(r.x[0], r.x[1]);
+  u_ind = jb_u52(r.x[2], r.x[3]);
 }
 
 #include "jb_groups.cuh"

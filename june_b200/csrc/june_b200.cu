@@ -173,6 +173,7 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   w->newinf_cap = d->newinf_capacity ? d->newinf_capacity : std::max(1u, w->N_ext + w->H);
   w->h_ext2int = lay.ext2int; w->h_int2ext = lay.int2ext;
   TRY(dev_upload(&w->int2ext, lay.int2ext.data(), w->N, s));
+  TRY(dev_upload(&w->ext2int, lay.ext2int.data(), w->N_ext, s));
   w->tiles.resize(w->sgs.size());
   for (size_t k = 0; k < w->sgs.size(); ++k) {
     const HostTiles& T = lay.tiles[k];
@@ -336,10 +337,14 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   CK(cudaEventCreateWithFlags(&w->ev_fork_health, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&w->ev_join_health, cudaEventDisableTiming));
   // the CTA kernel may need > 48 KB of dynamic shared memory for very large schools
-  CK(cudaFuncSetAttribute(k_groups<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_groups<1, JB_CTA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, JB_CTA_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<1, JB_CTA_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, JB_CTA_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<1, JB_CTA_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_groups<JB_MAX_VARIANTS, JB_CTA_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   *out = w;
@@ -356,7 +361,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
-                  w->cub_tmp, w->int2ext, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
+                  w->cub_tmp, w->int2ext, w->ext2int, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (SgTiles& t : w->tiles) {
@@ -712,12 +717,15 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   a.bin_cap = w->sg_bin_cap[ksg];
   a.dyn_bin_base = w->sg_bin_base[ksg];
   a.g0 = sg.first_group; a.g1 = sg.first_group + sg.n_groups;
-  a.group_list = nullptr; a.n_list = sg.n_groups; a.int2ext = w->int2ext;
+  a.group_list = nullptr; a.n_list = sg.n_groups; a.int2ext = w->int2ext; a.ext2int = w->ext2int;
   a.dim = sg.dim; a.kind = sg.kind; a.L = L;
   a.N = w->N; a.NP = w->NP; a.V = (int)w->V; a.R = (int)w->R;
   a.sp = step_dev(w); a.gid_base = (uint32_t)w->id_base;
   a.counters = w->counters; a.newinf_member = w->newinf_member; a.newinf_var = w->newinf_var;
   a.newinf_cap = w->newinf_cap;
+  if (p.flags & JB_STEP_RECORD_EVENTS) {
+    a.ev_infected = w->ev_infected; a.ev_infector = w->ev_infector; a.ev_group = w->ev_group; a.ev_var = w->ev_var;
+  }
   a.lambda = (p.flags & JB_STEP_RECORD_LAMBDA) ? w->lambda : nullptr;
   if (p.flags & JB_STEP_INJECT_UNIFORMS) {
     a.inject = w->inject; a.draw_base = w->draw_base;
@@ -732,7 +740,8 @@ static int launch_list(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_
   if (a.n_list == 0) return JB_OK;
   constexpr int gpc = JB_CTA_WARPS / WPG;
   const size_t smem = jb_grp_smem_bytes(a.L, (int)w->V, dynamic ? a.bin_cap : 0u, WPG) * gpc;
-  k_groups<VM, WPG><<<(a.n_list + gpc - 1) / gpc, JB_CTA, smem, st>>>(a);
+  if (a.ev_group) k_groups<VM, WPG, true><<<(a.n_list + gpc - 1) / gpc, JB_CTA, smem, st>>>(a);
+  else k_groups<VM, WPG, false><<<(a.n_list + gpc - 1) / gpc, JB_CTA, smem, st>>>(a);
   KCHECK(WPG == 1 ? "k_groups<warp>" : "k_groups<cta>", st);
   return JB_OK;
 }
@@ -740,7 +749,8 @@ static int launch_list(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_
 template <bool STREAM, int VM>
 static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
   const unsigned blocks = (a.n_tiles * 2 + JB_TILE_THREADS - 1) / JB_TILE_THREADS;
-  k_tiles<STREAM, VM><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
+  if (a.ev_group) k_tiles<STREAM, VM, true><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
+  else k_tiles<STREAM, VM, false><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
   KCHECK(STREAM ? "k_tiles<stream>" : "k_tiles<gather>", st);
   return JB_OK;
 }
@@ -983,6 +993,15 @@ static int run_phase(JbWorld* w, int phase, const void* p0, const void* p1, F&& 
   return JB_OK;
 }
 
+static int ensure_event_buffers(JbWorld* w, uint32_t flags) {
+  if (!(flags & JB_STEP_RECORD_EVENTS) || w->ev_group) return JB_OK;
+  TRY(dev_alloc(&w->ev_infected, w->newinf_cap));
+  TRY(dev_alloc(&w->ev_infector, w->newinf_cap));
+  TRY(dev_alloc(&w->ev_group, w->newinf_cap));
+  TRY(dev_alloc(&w->ev_var, w->newinf_cap));
+  return JB_OK;
+}
+
 extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   if (!w || !p) { jb_set_error("null argument"); return JB_EINVAL; }
   REQUIRE(!w->in_step, "jb_step_begin: previous step not finished");
@@ -996,6 +1015,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
     CK(cudaEventRecord(w->ev_step0, s));
   }
   if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
+  TRY(ensure_event_buffers(w, p->flags));
   // per-step parameter block: pinned ring slot -> device (the h2d payload of every step)
   const int slot = (int)(w->step_seq++ & 3);
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));  // the copy that last used this slot has finished
@@ -1073,6 +1093,7 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
     CK(cudaEventRecord(w->ev_step0, s));
   }
   if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
+  TRY(ensure_event_buffers(w, p->flags));
   const int slot = (int)(w->step_seq++ & 3);
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
@@ -1151,6 +1172,39 @@ extern "C" int jb_fetch_new_infections(JbWorld* w, uint32_t* member, uint32_t* v
   for (uint32_t i = 0; i < cnt; ++i) {
     member[i] = m[order[i]];
     if (variant) variant[i] = v[order[i]];
+  }
+  return JB_OK;
+}
+
+extern "C" int jb_fetch_infection_events(JbWorld* w, uint32_t* infected, uint32_t* infector, uint32_t* group,
+                                         uint32_t* variant, size_t cap, size_t* n) {
+  if (!w || !n) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  *n = 0;
+  if (!w->ev_group || !(w->cur.flags & JB_STEP_RECORD_EVENTS)) return JB_OK;  // the last step did not record events
+  uint32_t cnt = 0;
+  CK(cudaMemcpy(&cnt, w->counters + CNT_NEWINF, 4, cudaMemcpyDeviceToHost));
+  cnt = std::min(cnt, w->newinf_cap);
+  REQUIRE(cnt <= cap, "jb_fetch_infection_events: caller buffers too small");
+  *n = cnt;
+  if (!cnt) return JB_OK;
+  std::vector<uint32_t> a(cnt), b(cnt), g(cnt);
+  std::vector<uint8_t> v(cnt);
+  CK(cudaMemcpy(a.data(), w->ev_infected, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.data(), w->ev_infector, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(g.data(), w->ev_group, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(v.data(), w->ev_var, cnt, cudaMemcpyDeviceToHost));
+  auto ext = [&](uint32_t p) { return p == 0xFFFFFFFFu ? p : p < w->N ? w->h_int2ext[p] : w->N_ext + (p - w->N); };
+  std::vector<uint32_t> order(cnt);
+  for (uint32_t i = 0; i < cnt; ++i) { order[i] = i; a[i] = ext(a[i]); b[i] = ext(b[i]); }
+  std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return a[x] < a[y]; });
+  for (uint32_t i = 0; i < cnt; ++i) {
+    const uint32_t k = order[i];
+    if (infected) infected[i] = a[k];
+    if (infector) infector[i] = b[k];
+    if (group) group[i] = g[k];
+    if (variant) variant[i] = v[k];
   }
   return JB_OK;
 }

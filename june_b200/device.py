@@ -269,6 +269,16 @@ class Engine:
         self._check(self._f("fetch_new_infections")(self._h, ptr(m), ptr(v), cap, C.byref(n)))
         return m[: n.value].copy(), v[: n.value].copy()
 
+    def fetch_infection_events(self) -> Dict[str, np.ndarray]:
+        """Rows of the reference's ``infections`` record table for the last step that ran with
+        ``STEP_RECORD_EVENTS``: ``infected``, ``infector`` (person indices), ``group``, ``variant``."""
+        cap = self.world.n_people + self.world.n_halo
+        a = [np.zeros(cap, np.uint32) for _ in range(4)]
+        n = C.c_size_t()
+        self._check(self._f("fetch_infection_events")(self._h, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), cap, C.byref(n)))
+        return dict(infected=a[0][: n.value].copy(), infector=a[1][: n.value].copy(), group=a[2][: n.value].copy(),
+                    variant=a[3][: n.value].copy())
+
     def fetch_person_state(self) -> Dict[str, np.ndarray]:
         n = self.world.n_people
         out = dict(pstate=np.zeros(n, np.uint8), tag=np.zeros(n, np.int8), trans_prob=np.zeros(n, np.float64),

@@ -192,6 +192,7 @@ class Simulator:
         self.activity_manager.policies.init_policies(world)
         self._leisure_tables: dict = {}   # time-slot key -> table index on the device
         self._leisure_stack: List[tuple] = []
+        self.infection_events: List[tuple] = []
         self.region_history: List[tuple] = []
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
@@ -290,7 +291,7 @@ class Simulator:
         activities = self.timer.activities
         if not activities:
             return  # simulator.py:377-379
-        params = self.step_params()
+        params = self.step_params(_lib.STEP_RECORD_EVENTS if self.record is not None else 0)
         dev = self.device
         if self.halo is None:
             stats = dev.step(params, want_stats=want_stats)
@@ -317,6 +318,9 @@ class Simulator:
             self.history.append(dict(date=self.timer.date, now=self.timer.now, **stats))
             if self.record is not None:
                 self.region_history.append((self.timer.date, dev.fetch_summary()))
+                ev = dev.fetch_infection_events()
+                if len(ev["infected"]):
+                    self.infection_events.append((self.timer.date, ev))
 
     def run(self) -> None:
         """``Simulator.run`` (``simulator.py:628-707``)."""
@@ -338,6 +342,27 @@ class Simulator:
                 for k, c in enumerate(cols):
                     row[c] = int(summ[r, k]) if c.startswith("current") else row[c] + int(summ[r, k])
         return [rows[k] for k in sorted(rows, key=lambda x: (x[0], self.world.region_names.index(x[1])))]
+
+    def infection_rows(self) -> List[Dict[str, object]]:
+        """Rows of the reference's ``infections`` record table (``Record.accumulate(table_name=
+        "infections", ...)``, ``interaction.py:664-683``; ``records/event_records_writer.py:60-84``):
+        ``time_stamp, location_specs, location_ids, region_names, infector_ids, infected_ids,
+        infection_ids``.  Ids are the caller's (``world.person_ids`` / ``world.group_ids`` when the
+        world was compiled from reference objects, else indices + ``person_id_base``)."""
+        w = self.world
+        grp_sg = w.group_supergroup()
+        pid = w.person_ids if w.person_ids is not None else np.arange(w.n_people, dtype=np.int64) + w.person_id_base
+        if w.n_halo:
+            pid = np.concatenate([pid, w.halo_gid.astype(np.int64)])
+        gid = w.group_ids if w.group_ids is not None else np.arange(w.n_groups, dtype=np.int64)
+        rows = []
+        for date, ev in self.infection_events:
+            for a, b, g, v in zip(ev["infected"], ev["infector"], ev["group"], ev["variant"]):
+                rows.append(dict(time_stamp=date, location_specs=w.supergroups[grp_sg[g]].spec, location_ids=int(gid[g]),
+                                 region_names=w.region_names[int(w.grp_info[g] >> 16)] if w.region_names else "",
+                                 infector_ids=int(pid[b]) if b != 0xFFFFFFFF else -1, infected_ids=int(pid[a]),
+                                 infection_ids=int(v)))
+        return rows
 
     def write_summary_csv(self, path: str) -> None:
         import csv
