@@ -195,6 +195,7 @@ typedef struct {
 #define JB_STEP_INJECT_LEISURE 0x20u  /* leisure venues come from jb_inject_leisure (test mode)    */
 #define JB_STEP_INJECT_POLICY 0x40u   /* policy uniforms come from jb_inject_policy_uniforms        */
 #define JB_STEP_RECORD_EVENTS 0x80u   /* keep {where, infector} of every new infection (records)    */
+#define JB_STEP_INJECT_COMMUTE 0x100u /* transports come from jb_inject_commute (test mode)         */
 
 /* Per-step outputs (the d2h payload of every step). */
 typedef struct {
@@ -300,6 +301,26 @@ int jb_set_leisure_tables(JbWorld* w, uint32_t n_tables, const double* does, con
 /* Test mode (JB_STEP_INJECT_LEISURE): the venue of every person for the next step, -1 = none;
  * replaces the three random choices of leisure.py:253-263 / social_venue_distributor.py:257-266. */
 int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person);
+
+/* ---- commute (groups/travel/travel.py:125-131, geography/city.py:83-102, station.py:52-76) ----
+ * A public-transport commuter either commutes inside its work city (a random station of the city,
+ * then a random transport of that station) or through the inter-city station of its home super
+ * area (a random transport of that station); always subgroup 0 of the transport.  Transports are
+ * groups of supergroups with has_dynamic set and activity JB_ACT_COMMUTE.
+ * person_commute[p]: -1 = does not commute by public transport; (city << 1) = internal commuter
+ * of that city; (station << 1) | 1 = commuter of that inter-city station. */
+typedef struct {
+  uint32_t n_cities, n_stations;
+  const int32_t* person_commute;           /* [n_people]                                     */
+  const uint32_t* city_station_off;        /* [n_cities + 1] CSR into city_station           */
+  const uint32_t* city_station;            /* station indices (city.city_stations)           */
+  const uint32_t* station_transport_off;   /* [n_stations + 1] CSR into station_transport    */
+  const uint32_t* station_transport;       /* group indices (station.*_transports)           */
+} JbCommuteDesc;
+int jb_set_commute(JbWorld* w, const JbCommuteDesc* desc);
+/* Test mode (JB_STEP_INJECT_COMMUTE): the transport of every person for the next step, -1 = none;
+ * replaces the randint calls of city.py:95-97 and station.py:52-53,73-76. */
+int jb_inject_commute(JbWorld* w, const int32_t* group_per_person);
 
 /* ---- individual policies (policy/individual_policies.py:36-84) ---------------------------
  * The active individual policies, in the reference's list order, evaluated per person by the

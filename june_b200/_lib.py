@@ -24,7 +24,7 @@ ABI_VERSION = 1
 JB_OK, JB_EINVAL, JB_ECUDA, JB_ENOACT, JB_ECAP, JB_ENOGPU = 0, 1, 2, 3, 4, 5
 STEP_SEVERE_STAY_HOME, STEP_HOSPITALISATION, STEP_INJECT_UNIFORMS = 0x1, 0x2, 0x4
 STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE, STEP_INJECT_POLICY = 0x8, 0x10, 0x20, 0x40
-STEP_RECORD_EVENTS = 0x80
+STEP_RECORD_EVENTS, STEP_INJECT_COMMUTE = 0x80, 0x100
 MAX_POLICIES, POLICY_DRAWS = 8, 3
 POL_SEVERE_STAY_HOME, POL_QUARANTINE, POL_SHIELDING, POL_CLOSE_SCHOOLS, POL_CLOSE_UNIVERSITIES, POL_CLOSE_COMPANIES = 1, 2, 3, 4, 5, 6
 
@@ -81,6 +81,12 @@ class JbIndividualPolicy(C.Structure):
                 ("p", C.c_double * 6)]
 
 
+class JbCommuteDesc(C.Structure):
+    _fields_ = [("n_cities", C.c_uint32), ("n_stations", C.c_uint32), ("person_commute", C.c_void_p),
+                ("city_station_off", C.c_void_p), ("city_station", C.c_void_p),
+                ("station_transport_off", C.c_void_p), ("station_transport", C.c_void_p)]
+
+
 class JbLeisureDesc(C.Structure):
     _fields_ = [("n_activities", C.c_uint32), ("n_areas", C.c_uint32), ("supergroup", C.c_void_p),
                 ("subgroup", C.c_void_p), ("person_area", C.c_void_p), ("area_off", C.c_void_p),
@@ -113,6 +119,7 @@ ABI_SYMBOLS = [
     "fetch_lambda", "fetch_infections", "fetch_summary", "timing_enable", "timing_read", "last_step_bytes",
     "set_concurrency", "set_leisure", "set_leisure_tables", "inject_leisure",
     "set_individual_policies", "set_person_attributes", "inject_policy_uniforms", "fetch_infection_events",
+    "set_commute", "inject_commute",
 ]
 
 
@@ -171,6 +178,8 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("set_individual_policies").argtypes = [vp, C.POINTER(JbIndividualPolicy), C.c_uint32, vp]
     f("set_person_attributes").argtypes = [vp, vp]
     f("inject_policy_uniforms").argtypes = [vp, vp]
+    f("set_commute").argtypes = [vp, C.POINTER(JbCommuteDesc)]
+    f("inject_commute").argtypes = [vp, vp]
     f("fetch_infection_events").argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     for extra, args in (("set_halo_gids", [vp, vp, C.c_size_t]), ("halo_record_size_w", [vp]), ("stream_handle", [vp]),
                         ("timing_read_supergroups", [vp, dp, C.POINTER(C.c_uint64), C.c_int]),

@@ -67,7 +67,7 @@ LEISURE_BIN_CAP = 2048  # visitors per social venue and step
 
 
 def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sector_betas: Dict[str, float],
-                  warp_mode_specs=WARP_MODE_SPECS, leisure=None) -> WorldSoA:
+                  warp_mode_specs=WARP_MODE_SPECS, leisure=None, travel=None) -> WorldSoA:
     """``leisure``: the reference's ``Leisure`` object (or None).  Its social-venue distributors
     (``leisure.leisure_distributors``, in order) become the leisure activities of the device world;
     ``area.social_venues[spec]`` (``social_venue_distributor.py:258``) the per-area candidates."""
@@ -154,7 +154,7 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
             beta_i.append(b)
             scale_i.append(sc)
             aux.append(a)
-        is_venue = act == "leisure"
+        is_venue = act in ("leisure", "commute")
         has_dyn = 1 if spec == "hospital" else LEISURE_BIN_CAP if is_venue else 0
         supergroups.append(Supergroup(name=name, spec=spec, activity=ACTIVITY_CODES[act], first_group=first,
                                       n_groups=len(members), kind=kind,
@@ -229,6 +229,39 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
         if res is not None and hasattr(res.group, "residents"):
             kw2[i] = sum(1 for m in res.group.residents if getattr(m, "lockdown_status", None) == "key_worker") > 1
     w.person_attr = make_person_attr(lock, kind, kw2)
+    if travel is not None and getattr(world, "cities", None) is not None:
+        # Travel.get_commute_subgroup (travel.py:125-131): work city, public transport, internal commuter
+        # of the city or commuter of the home super area's inter-city station (city.py:83-102)
+        cities = list(world.cities.members) if hasattr(world.cities, "members") else list(world.cities)
+        stations, st_idx = [], {}
+        cs_off, cs = [0], []
+        for c in cities:
+            for st in list(c.city_stations) + list(c.inter_city_stations):
+                st_idx[id(st)] = len(stations)
+                stations.append(st)
+            cs += [st_idx[id(st)] for st in c.city_stations]
+            cs_off.append(len(cs))
+        st_off, st_tr = [0], []
+        for st in stations:
+            trs = getattr(st, "city_transports", None) or getattr(st, "inter_city_transports", None) or []
+            st_tr += [gidx[id(t)] for t in trs if id(t) in gidx]
+            st_off.append(len(st_tr))
+        cidx = {id(c): i for i, c in enumerate(cities)}
+        pc = np.full(n, -1, np.int32)
+        for i, p in enumerate(people):
+            city = p.work_city
+            mode = getattr(p, "mode_of_transport", None)
+            if city is None or mode is None or not mode.is_public or not city.has_stations:
+                continue
+            if p.id in city.internal_commuter_ids:
+                pc[i] = cidx[id(city)] << 1
+            else:
+                st = p.super_area.closest_inter_city_station_for_city.get(city.name)
+                if st is not None and p.id in st.commuter_ids:
+                    pc[i] = (st_idx[id(st)] << 1) | 1
+        w.person_commute = pc
+        w.city_station_off, w.city_station = np.array(cs_off, np.uint32), np.array(cs, np.uint32)
+        w.station_transport_off, w.station_transport = np.array(st_off, np.uint32), np.array(st_tr, np.uint32)
     if leisure is not None:
         areas = list(world.areas.members) if hasattr(world.areas, "members") else list(world.areas)
         aidx = {id(a): i for i, a in enumerate(areas)}

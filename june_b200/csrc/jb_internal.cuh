@@ -88,6 +88,16 @@ struct PolicyDev {
   double rc[JB_MAX_REGIONS_POLICY];
 };
 
+// Commute tables on the device (jb_set_commute).
+struct CommuteDev {
+  const int32_t* person;     // [N] internal numbering: -1 | city << 1 | (station << 1) | 1
+  const uint32_t* cs_off;    // city -> stations
+  const uint32_t* cs;
+  const uint32_t* st_off;    // station -> transports (groups)
+  const uint32_t* st;
+  const int32_t* inject;     // [N] transport per person (test mode) or null
+};
+
 // Per-step scalars, resident on the device so that a captured CUDA graph of the step can be
 // replayed: one h2d copy from a pinned ring buffer precedes every step.  The processed beta
 // table [n_beta][n_regions] follows the struct in the same allocation.
@@ -241,6 +251,10 @@ struct JbWorld {
   uint32_t *lz_parea = nullptr, *lz_off = nullptr, *lz_venue = nullptr;
   double *lz_does = nullptr, *lz_cum = nullptr;
   int32_t* lz_inject = nullptr;
+  // commute
+  CommuteDev cmt = {};
+  int32_t *cm_person = nullptr, *cm_inject = nullptr;
+  uint32_t *cm_cs_off = nullptr, *cm_cs = nullptr, *cm_st_off = nullptr, *cm_st = nullptr;
   // individual policies
   PolicyDev* d_pol = nullptr;
   uint32_t n_pol = 0;

@@ -46,6 +46,7 @@ struct PlaceArgs {
   const uint32_t* int2ext;
   uint32_t gid_base;
   int R;
+  CommuteDev cmt;
   // individual policies (null / 0 = none)
   const PolicyDev* pol;
   uint32_t n_pol;
@@ -162,6 +163,30 @@ __device__ __forceinline__ void jb_dyn_scatter(const PlaceArgs& a, uint32_t g, u
   atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
 }
 
+// Travel.get_commute_subgroup (travel.py:125-131) -> City.get_commute_subgroup (city.py:83-102) ->
+// Station.get_commute_subgroup (station.py:52-53,73-76): the transport group, or -1.
+__device__ __noinline__ int32_t jb_commute_transport(const PlaceArgs& a, uint32_t p) {
+  const CommuteDev& c = a.cmt;
+  if (c.inject) return c.inject[p];
+  const int32_t code = c.person[p];
+  if (code < 0) return -1;
+  const JbPhilox4 r = jb_philox4x32_10(a.gid_base + a.int2ext[p], a.sp->step, JB_STREAM_COMMUTE, 0u, (uint32_t)a.sp->seed,
+                                       (uint32_t)(a.sp->seed >> 32));
+  uint32_t station;
+  if (code & 1) {
+    station = (uint32_t)code >> 1;
+  } else {
+    const uint32_t o = c.cs_off[code >> 1], n = c.cs_off[(code >> 1) + 1] - o;
+    if (!n) return -1;
+    const uint32_t j = (uint32_t)(jb_u52(r.x[0], r.x[1]) * (double)n);
+    station = c.cs[o + (j < n ? j : n - 1)];
+  }
+  const uint32_t o = c.st_off[station], n = c.st_off[station + 1] - o;
+  if (!n) return -1;
+  const uint32_t j = (uint32_t)(jb_u52(r.x[2], r.x[3]) * (double)n);
+  return (int32_t)c.st[o + (j < n ? j : n - 1)];
+}
+
 // Leisure.get_subgroup_for_person_and_housemates (leisure.py:230-275) for social venues: does the
 // person go out, which activity, which of its area's candidate venues
 // (social_venue_distributor.py:257-266).  Returns the venue group (and its subgroup) or -1.
@@ -209,6 +234,7 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
   __shared__ uint32_t s_cnt[8];
   const uint32_t mask = a.sp->activity_mask, flags = a.sp->flags;
   const bool leisure_on = FULL && a.lz.K != 0 && (a.lz.inject != nullptr || a.sp->leisure_table != 0);
+  const bool commute_on = FULL && (a.cmt.person != nullptr || a.cmt.inject != nullptr);
   for (uint32_t k = threadIdx.x; k < 512; k += blockDim.x) {
     const uint32_t bits = k >> 5, has0 = k & 0x1Fu;
     const bool dead = bits & 2u, severe = bits & 4u, med = bits & 8u;
@@ -218,6 +244,8 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
       if ((flags & JB_STEP_SEVERE_STAY_HOME) && severe) allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
       const uint32_t cand = allowed & (has0 | (med ? 1u << JB_ACT_MEDICAL : 0u));
       act = cand ? (uint32_t)__ffs(cand) - 1u : 15u;  // hierarchy order == bit order
+      // commute has no fixed subgroup either: drawn per commuter unless a medical facility comes first
+      if (commute_on && (allowed & (1u << JB_ACT_COMMUTE)) && !(cand & (1u << JB_ACT_MEDICAL))) act |= 0x40u;
       // leisure has no fixed subgroup: it is drawn per person when nothing above it in the
       // hierarchy applies (activity_manager.py:380-398) -> flag bit 7, resolved below
       if (leisure_on && (allowed & (1u << JB_ACT_LEISURE)) && !(cand & ((1u << JB_ACT_LEISURE) - 1u))) act |= 0x80u;
@@ -242,8 +270,14 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
       const uint32_t cand = allowed & ((has & 0x1Fu) | ((st & JB_PS_MEDICAL) ? 1u << JB_ACT_MEDICAL : 0u));
       act = cand ? (uint32_t)__ffs(cand) - 1u : 15u;
       if (leisure_on && (allowed & (1u << JB_ACT_LEISURE)) && !(cand & ((1u << JB_ACT_LEISURE) - 1u))) act |= 0x80u;
+      if (commute_on && (allowed & (1u << JB_ACT_COMMUTE)) && !(cand & (1u << JB_ACT_MEDICAL))) act |= 0x40u;
     } else {
       act = s_act[jb_place_key(st, has)];
+    }
+    if (FULL && (act & 0x40u)) {  // commute draw (above primary activity, leisure and residence)
+      const int32_t g = jb_commute_transport(a, p);
+      if (g >= 0) { act = JB_ACT_COMMUTE; jb_dyn_scatter(a, (uint32_t)g, 0u, p); }
+      else act &= ~0x40u;
     }
     if (FULL && (act & 0x80u)) {  // leisure draw
       act &= 0x7Fu;

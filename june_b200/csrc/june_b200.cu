@@ -361,7 +361,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
-                  w->cub_tmp, w->int2ext, w->ext2int, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
+                  w->cub_tmp, w->int2ext, w->ext2int, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (SgTiles& t : w->tiles) {
@@ -500,6 +500,42 @@ extern "C" int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person) {
   for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = group_per_person[p];
   if (!w->lz_inject) { TRY(dev_alloc(&w->lz_inject, v.size())); drop_graphs(w); }
   CK(cudaMemcpy(w->lz_inject, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
+// ---- commute ---------------------------------------------------------------------------------
+extern "C" int jb_set_commute(JbWorld* w, const JbCommuteDesc* d) {
+  if (!w || !d) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);
+  std::vector<int32_t> pc(std::max(1u, w->N), -1);
+  for (uint32_t p = 0; p < w->N_ext; ++p) {
+    const int32_t c = d->person_commute[p];
+    REQUIRE(c < 0 || ((c & 1) ? (uint32_t)(c >> 1) < d->n_stations : (uint32_t)(c >> 1) < d->n_cities), "person_commute out of range");
+    pc[w->h_ext2int[p]] = c;
+  }
+  for (uint32_t i = 0; i < d->city_station_off[d->n_cities]; ++i) REQUIRE(d->city_station[i] < d->n_stations, "city_station out of range");
+  for (uint32_t i = 0; i < d->station_transport_off[d->n_stations]; ++i) REQUIRE(d->station_transport[i] < w->G, "station_transport out of range");
+  for (void* q : {(void*)w->cm_person, (void*)w->cm_cs_off, (void*)w->cm_cs, (void*)w->cm_st_off, (void*)w->cm_st}) if (q) cudaFree(q);
+  TRY(dev_upload(&w->cm_person, pc.data(), pc.size(), w->stream));
+  TRY(dev_upload(&w->cm_cs_off, d->city_station_off, (size_t)d->n_cities + 1, w->stream));
+  TRY(dev_upload(&w->cm_cs, d->city_station, (size_t)d->city_station_off[d->n_cities], w->stream));
+  TRY(dev_upload(&w->cm_st_off, d->station_transport_off, (size_t)d->n_stations + 1, w->stream));
+  TRY(dev_upload(&w->cm_st, d->station_transport, (size_t)d->station_transport_off[d->n_stations], w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  w->cmt.person = w->cm_person; w->cmt.cs_off = w->cm_cs_off; w->cmt.cs = w->cm_cs; w->cmt.st_off = w->cm_st_off; w->cmt.st = w->cm_st;
+  return JB_OK;
+}
+
+extern "C" int jb_inject_commute(JbWorld* w, const int32_t* g) {
+  if (!w || !g) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  std::vector<int32_t> v(std::max(1u, w->N), -1);
+  for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = g[p];
+  if (!w->cm_inject) { TRY(dev_alloc(&w->cm_inject, v.size())); drop_graphs(w); }
+  CK(cudaMemcpy(w->cm_inject, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
   return JB_OK;
 }
 
@@ -842,11 +878,15 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     if ((p.flags & JB_STEP_INJECT_LEISURE) && !w->lz_inject) { jb_set_error("JB_STEP_INJECT_LEISURE without jb_inject_leisure"); return JB_EINVAL; }
     pa.age = w->age; pa.sex = w->sex; pa.ch = w->ch; pa.pregion = w->pregion; pa.int2ext = w->int2ext;
     pa.gid_base = (uint32_t)w->id_base; pa.R = (int)w->R;
+    pa.cmt = w->cmt;
+    pa.cmt.inject = (p.flags & JB_STEP_INJECT_COMMUTE) ? w->cm_inject : nullptr;
+    if (!(p.activity_mask & (1u << JB_ACT_COMMUTE))) { pa.cmt.person = nullptr; pa.cmt.inject = nullptr; }
     pa.pol = w->d_pol; pa.n_pol = w->n_pol; pa.ptag = w->ptag; pa.pattr = w->pattr;
     pa.pol_inject = (p.flags & JB_STEP_INJECT_POLICY) ? w->pol_inject : nullptr;
     pa.severe_mask = w->dis_host.severe_mask;
     const uint32_t chunks = (w->N + 15) / 16;
-    const bool full = w->n_pol != 0 || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE)));
+    const bool full = w->n_pol != 0 || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
+                      pa.cmt.person != nullptr || pa.cmt.inject != nullptr;
     if (full) k_place<true><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     else k_place<false><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     KCHECK("k_place", s);

@@ -12,7 +12,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (JbDisease, JbDist, JbIndividualPolicy, JbInfectionRow, JbLeisureDesc, JbStepParams, JbStepStats,
+from ._lib import (JbCommuteDesc, JbDisease, JbDist, JbIndividualPolicy, JbInfectionRow, JbLeisureDesc, JbStepParams, JbStepStats,
                    JbSupergroup, JbWorldDesc, SimulatorError, ptr)
 from .disease import DiseaseConfig, health_index_cum
 from .interaction import Interaction
@@ -106,6 +106,8 @@ class Engine:
         self._h = handle
         if world.has_leisure:
             self._set_leisure(world)
+        if world.has_commute:
+            self._set_commute(world)
         if world.person_attr is not None:
             pa = np.ascontiguousarray(world.person_attr, dtype=np.uint8)
             self._check(self._f("set_person_attributes")(self._h, ptr(pa)))
@@ -144,6 +146,23 @@ class Engine:
         g = np.ascontiguousarray(group_per_person, dtype=np.int32)
         assert g.shape == (self.world.n_people,)
         self._check(self._f("inject_leisure")(self._h, ptr(g)))
+
+    # ---- commute --------------------------------------------------------------------------------
+    def _set_commute(self, world: WorldSoA):
+        arrs = [np.ascontiguousarray(world.person_commute, dtype=np.int32)] + [
+            np.ascontiguousarray(x, dtype=np.uint32) for x in (world.city_station_off, world.city_station,
+                                                               world.station_transport_off, world.station_transport)]
+        arrs = [a if a.size else np.zeros(1, a.dtype) for a in arrs]
+        d = JbCommuteDesc()
+        d.n_cities, d.n_stations = len(world.city_station_off) - 1, len(world.station_transport_off) - 1
+        (d.person_commute, d.city_station_off, d.city_station, d.station_transport_off,
+         d.station_transport) = (a.ctypes.data for a in arrs)
+        self._check(self._f("set_commute")(self._h, C.byref(d)))
+
+    def inject_commute(self, group_per_person: np.ndarray):
+        g = np.ascontiguousarray(group_per_person, dtype=np.int32)
+        assert g.shape == (self.world.n_people,)
+        self._check(self._f("inject_commute")(self._h, ptr(g)))
 
     # ---- individual policies ---------------------------------------------------------------------
     def set_individual_policies(self, records: Sequence[dict], regional_compliance: Optional[Sequence[float]] = None):

@@ -18,7 +18,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from .world import (ACT_LEISURE, ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, KIND_MATRIX, KIND_SCHOOL, BetaRule, Supergroup,
+from .world import (ACT_COMMUTE, ACT_LEISURE, ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, KIND_MATRIX, KIND_SCHOOL, BetaRule, Supergroup,
                     WorldSoA, make_ginfo, make_info, make_person_attr)
 
 REGIONS = ["North East", "North West", "Yorkshire and The Humber", "East Midlands", "West Midlands",
@@ -35,6 +35,11 @@ LEISURE_VENUES = [("pubs", "pub", 1000, 7), ("cinemas", "cinema", 20000, 5), ("g
                   ("gyms", "gym", 5000, 7)]
 LEISURE_ORDER = ["pubs", "gyms", "cinemas", "groceries"]
 LEISURE_BIN_CAP = 2048  # visitors per venue and step
+# commute (config 2 of BASELINE.json): one city per CITY_SUPER_AREAS super areas with CITY_STATIONS
+# stations; 30 % of the company workers use public transport, 60 % of them inside their city, the
+# others through the inter-city station of their home super area; ~50 commuters per transport
+CITY_SUPER_AREAS, CITY_STATIONS, SEATS = 20, 4, 50
+TRANSPORT_BIN_CAP = 512
 
 
 def age_pmf() -> np.ndarray:
@@ -75,7 +80,7 @@ def _csr_from_rows(group: np.ndarray, lsg: np.ndarray, member: np.ndarray, act: 
 
 def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int = 0, commute_fraction: float = 0.05,
                     person_id_base: Optional[int] = None, sector_betas: Optional[Dict[str, float]] = None,
-                    leisure: bool = False) -> DomainDraft:
+                    leisure: bool = False, commute: bool = False) -> DomainDraft:
     rng = np.random.default_rng([seed, rank, 20200301])
     pmf = age_pmf()
     adult_pmf = pmf.copy()
@@ -250,7 +255,26 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     # ---- group table, in the reference's supergroup order ----------------------------------------
     sector_betas = sector_betas or {}
     g_hosp0 = 0
-    g_school0 = g_hosp0 + n_hosp
+    # commuters and their transports (commute precedes the primary activity in the hierarchy)
+    n_city = max(1, -(-n_sa // CITY_SUPER_AREAS)) if commute else 0
+    person_commute = np.full(n, -1, np.int32)
+    n_ct = n_it = 0
+    if commute:
+        crng = np.random.default_rng([seed, rank, 5150])
+        pub = rest[crng.random(len(rest)) < 0.30]
+        internal = crng.random(len(pub)) < 0.60
+        city_of = (psa[pub] // CITY_SUPER_AREAS).astype(np.int64)
+        person_commute[pub[internal]] = (city_of[internal] << 1).astype(np.int32)
+        # inter-city stations: one per super area (closest_inter_city_station_for_city), index after the city stations
+        n_cstation = n_city * CITY_STATIONS
+        person_commute[pub[~internal]] = (((n_cstation + psa[pub[~internal]].astype(np.int64)) << 1) | 1).astype(np.int32)
+        per_cstation = np.bincount(city_of[internal], minlength=n_city) / CITY_STATIONS
+        ct_per_station = np.maximum(1, np.ceil(np.repeat(per_cstation, CITY_STATIONS) / SEATS)).astype(np.int64)
+        it_per_station = np.maximum(1, np.ceil(np.bincount(psa[pub[~internal]], minlength=n_sa) / SEATS)).astype(np.int64)
+        n_ct, n_it = int(ct_per_station.sum()), int(it_per_station.sum())
+    g_ct0 = g_hosp0 + n_hosp
+    g_it0 = g_ct0 + n_ct
+    g_school0 = g_it0 + n_it
     g_comp0 = g_school0 + n_schools
     # leisure venues sit between the primary-activity and the residence supergroups (hierarchy order)
     n_venues = [max(1, n // per) for _, _, per, _ in LEISURE_VENUES] if leisure else []
@@ -263,6 +287,8 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
              BetaRule("care_visits", None, False), BetaRule("care_home")]
     if leisure:
         rules += [BetaRule(spec) for _, spec, _, _ in LEISURE_VENUES]
+    if commute:
+        rules += [BetaRule("city_transport"), BetaRule("inter_city_transport")]
     scales = [1.0]
     sec_scale = np.zeros(len(SECTORS), np.int64)
     for i, s in enumerate(SECTORS):
@@ -275,8 +301,8 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     region = np.zeros(G, np.uint32)
     aux = np.zeros(G, np.uint32)
     hosp_sa = (np.arange(n_hosp) * n_sa // n_hosp).astype(np.int64)
-    beta_idx[g_hosp0:g_school0] = 0
-    region[g_hosp0:g_school0] = sa_region[hosp_sa]
+    beta_idx[g_hosp0:g_hosp0 + n_hosp] = 0
+    region[g_hosp0:g_hosp0 + n_hosp] = sa_region[hosp_sa]
     beta_idx[g_school0:g_comp0] = 1 + school_sector
     region[g_school0:g_comp0] = sa_region[school_sa]
     aux[g_school0:g_comp0] = (years_off[:-1].astype(np.uint32) << 8) | n_years_per_school.astype(np.uint32)
@@ -289,11 +315,26 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     beta_idx[g_ch0:] = 7
     region[g_ch0:] = sa_region[ch_sa]
     grp_sa = np.zeros(G, np.uint32)
-    grp_sa[g_hosp0:g_school0] = hosp_sa
+    grp_sa[g_hosp0:g_hosp0 + n_hosp] = hosp_sa
     grp_sa[g_school0:g_comp0] = school_sa
     grp_sa[g_comp0:g_comp0 + n_comp] = comp_sa
     grp_sa[g_hh0:g_ch0] = sa_of_hh
     grp_sa[g_ch0:] = ch_sa
+    commute_tables = None
+    if commute:
+        bi = len(rules) - 2
+        st_sa = np.concatenate([np.repeat(np.arange(n_city) * CITY_SUPER_AREAS, CITY_STATIONS), np.arange(n_sa)]).clip(0, n_sa - 1)
+        per = np.concatenate([ct_per_station, it_per_station])
+        st_off = np.zeros(len(per) + 1, np.uint32)
+        st_off[1:] = np.cumsum(per)
+        tr_station = np.repeat(np.arange(len(per)), per)
+        tr_group = (g_ct0 + np.arange(n_ct + n_it)).astype(np.uint32)
+        beta_idx[g_ct0:g_it0] = bi
+        beta_idx[g_it0:g_school0] = bi + 1
+        region[g_ct0:g_school0] = sa_region[st_sa[tr_station]]
+        grp_sa[g_ct0:g_school0] = st_sa[tr_station]
+        cs_off = (np.arange(n_city + 1) * CITY_STATIONS).astype(np.uint32)
+        commute_tables = (cs_off, np.arange(n_city * CITY_STATIONS, dtype=np.uint32), st_off, tr_group)
     # venues are spread evenly over the areas; an area's candidates are the nearest ones by index
     area_venue_off = area_venue = None
     if leisure:
@@ -331,6 +372,9 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     sa_hospital = (g_hosp0 + (np.arange(n_sa) * n_hosp // n_sa)).astype(np.int32)
     supergroups = [
         Supergroup("hospitals", "hospital", ACT_MEDICAL, g_hosp0, n_hosp, KIND_MATRIX, 1, 1),
+    ] + ([Supergroup("city_transports", "city_transport", ACT_COMMUTE, g_ct0, n_ct, KIND_MATRIX, 1, TRANSPORT_BIN_CAP),
+          Supergroup("inter_city_transports", "inter_city_transport", ACT_COMMUTE, g_it0, n_it, KIND_MATRIX, 1, TRANSPORT_BIN_CAP)]
+         if commute else []) + [
         Supergroup("schools", "school", ACT_PRIMARY, g_school0, n_schools, KIND_SCHOOL, 1, 0),
         Supergroup("companies", "company", ACT_PRIMARY, g_comp0, n_comp, KIND_MATRIX, 0, 0),
     ] + [Supergroup(name, spec, ACT_LEISURE, g_ven0[i], n_venues[i], KIND_MATRIX, 1, LEISURE_BIN_CAP)
@@ -364,6 +408,9 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
         kind[sel] = 2
     n_key = np.bincount(hh_of, weights=(lock == 1), minlength=n_hh)
     w.person_attr = make_person_attr(lock, kind, (n_key[hh_of] > 1) & ~in_care)
+    if commute:
+        w.person_commute = person_commute
+        w.city_station_off, w.city_station, w.station_transport_off, w.station_transport = commute_tables
     if leisure:
         w.person_area = area_of_hh[hh_of].astype(np.uint32)
         w.leisure_supergroups = list(LEISURE_ORDER)
@@ -437,8 +484,8 @@ def wire_halos_distributed(draft: DomainDraft, dist) -> WorldSoA:
 
 
 def generate_world(n_people: int, seed: int = 0, sector_betas: Optional[Dict[str, float]] = None,
-                   leisure: bool = False) -> WorldSoA:
+                   leisure: bool = False, commute: bool = False) -> WorldSoA:
     """Single-domain world (configs 0/1 of BASELINE.json; ``leisure=True`` adds the venues of config 3)."""
-    d = generate_domain(n_people, 0, 1, seed, sector_betas=sector_betas, leisure=leisure)
+    d = generate_domain(n_people, 0, 1, seed, sector_betas=sector_betas, leisure=leisure, commute=commute)
     _attach_halo(d, [np.zeros(0, np.uint32)])
     return d.world

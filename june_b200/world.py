@@ -135,6 +135,13 @@ class WorldSoA:
     leisure_subgroups: List[int] = field(default_factory=list)      # leisure_subgroup_type per activity
     area_venue_off: Optional[np.ndarray] = None   # uint32 [n_areas * K + 1]
     area_venue: Optional[np.ndarray] = None       # uint32 group indices
+    # commute (travel.py:125-131): -1 | city << 1 | (station << 1) | 1 per person; city -> stations and
+    # station -> transports (groups) as CSRs
+    person_commute: Optional[np.ndarray] = None          # int32 [n_people]
+    city_station_off: Optional[np.ndarray] = None
+    city_station: Optional[np.ndarray] = None
+    station_transport_off: Optional[np.ndarray] = None
+    station_transport: Optional[np.ndarray] = None
     # static facts the individual policies read (include/june_b200.h: JB_PA_*): lockdown status,
     # spec of the primary-activity group, ">= 2 key workers among the household's residents"
     person_attr: Optional[np.ndarray] = None      # uint8 [n_people]
@@ -142,7 +149,8 @@ class WorldSoA:
     _ARRAYS = ("age", "sex", "care_home_resident", "has_activity", "super_area", "sa_hospital", "sa_region",
                "grp_offset", "grp_info", "grp_aux", "reg_member", "reg_info", "school_years", "beta_scale",
                "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids", "grp_super_area",
-               "person_area", "area_venue_off", "area_venue", "person_attr")
+               "person_area", "area_venue_off", "area_venue", "person_attr",
+               "person_commute", "city_station_off", "city_station", "station_transport_off", "station_transport")
 
     @property
     def n_people(self) -> int:
@@ -167,6 +175,10 @@ class WorldSoA:
     @property
     def has_leisure(self) -> bool:
         return bool(self.leisure_activities) and self.person_area is not None and self.area_venue_off is not None
+
+    @property
+    def has_commute(self) -> bool:
+        return self.person_commute is not None and self.station_transport_off is not None
 
     @property
     def n_super_areas(self) -> int:

@@ -57,14 +57,15 @@ ROW_LEN = 5 + 5 + 2 * MAX_STAGES
 
 
 def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000,
-              with_leisure=False, lockdown=False):
+              with_leisure=False, lockdown=False, with_commute=False):
     pyrandom.seed(seed)
     np.random.seed(seed)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink):
-        world, dc = ref_world.build_world(n_people, seed=seed, with_leisure=with_leisure)
+        world, dc = ref_world.build_world(n_people, seed=seed, with_leisure=with_leisure, with_commute=with_commute)
         sim = ref_world.make_simulator(world, dc, total_days=total_days, cases_per_capita=cases_per_capita,
-                                       schedule=schedule, with_leisure=with_leisure, lockdown=lockdown)
+                                       schedule=schedule, with_leisure=with_leisure, lockdown=lockdown,
+                                       with_commute=with_commute)
     import june.interaction.interaction as inter_mod
     import june.policy.individual_policies as indiv_mod
     from june.epidemiology.infection import InfectionSelector
@@ -82,7 +83,10 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
             "residence": ["households", "care_homes"]}
     if with_leisure:
         a2sg["leisure"] = ["pubs", "cinemas", "groceries"]
-    soa = compile_world(world, a2sg, InteractiveCompany.sector_betas, leisure=sim.activity_manager.leisure)
+    if with_commute:
+        a2sg["commute"] = ["city_transports", "inter_city_transports"]
+    soa = compile_world(world, a2sg, InteractiveCompany.sector_betas, leisure=sim.activity_manager.leisure,
+                        travel=sim.activity_manager.travel)
     people = list(world.people)
     pidx = {p.id: i for i, p in enumerate(people)}
     gidx = {}
@@ -286,6 +290,9 @@ def spot_values(out_name="spot"):
 if __name__ == "__main__":
     if "leisure" in sys.argv[1:]:  # leisure placement (pubs, cinemas, groceries) on top of the w3k recipe
         run_trace(2500, 9, 2, "w2k_leisure", cases_per_capita=0.04, with_leisure=True)
+        sys.exit(0)
+    if "commute" in sys.argv[1:]:  # city / inter-city transports on the two commute steps of a weekday
+        run_trace(2500, 9, 4, "w2k_commute", cases_per_capita=0.05, with_commute=True)
         sys.exit(0)
     if "policies" in sys.argv[1:]:  # Quarantine, Shielding, CloseSchools, CloseCompanies switching on day by day
         run_trace(2500, 9, 3, "w2k_policies", cases_per_capita=0.05, lockdown=True)

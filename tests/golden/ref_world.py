@@ -50,7 +50,8 @@ def synthetic_rates_df():
 
 
 def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
-                people_per_company=40, people_per_school=1000, n_super_areas=4, with_leisure=False):
+                people_per_company=40, people_per_school=1000, n_super_areas=4, with_leisure=False,
+                with_commute=False):
     """Returns ``(world, disease_config)``.  People are created household by household so
     that person index order == household order."""
     ref_harness.setup()
@@ -207,6 +208,51 @@ def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
     if care_homes:
         world.care_homes = CareHomes(care_homes)
     world.cemeteries = Cemeteries()
+    if with_commute:
+        # two cities of two super areas each; per city 2 city stations x 2 transports and one inter-city
+        # station x 2 transports per super area (travel.py:125-131, city.py:83-102, station.py:52-76)
+        from june.geography.city import Cities, City
+        from june.geography.station import CityStation, InterCityStation
+        from june.groups.travel import CityTransport, CityTransports, InterCityTransport, InterCityTransports
+        from june.groups.travel.mode_of_transport import ModeOfTransport
+        public, private = ModeOfTransport("Bus, minibus or coach", is_public=True), ModeOfTransport("Driving a car or van", is_public=False)
+        cities, ctrans, itrans = [], [], []
+        for c in range(max(1, n_super_areas // 2)):
+            sas = super_areas[2 * c: 2 * c + 2]
+            city = City(super_areas=[sa.name for sa in sas], super_area=sas[0], name=f"City{c}", coordinates=sas[0].coordinates)
+            for sa in sas:
+                sa.city = city
+            for k in range(2):
+                st = CityStation(city=city.name, super_area=sas[k % len(sas)])
+                st.city_transports = [CityTransport(station=st) for _ in range(2)]
+                ctrans += st.city_transports
+                city.city_stations.append(st)
+            for sa in sas:
+                ist = InterCityStation(city=city.name, super_area=sa)
+                ist.inter_city_transports = [InterCityTransport(station=ist) for _ in range(2)]
+                itrans += ist.inter_city_transports
+                city.inter_city_stations.append(ist)
+            cities.append(city)
+        for sa in super_areas:
+            for city in cities:  # the station a commuter from this super area uses to reach `city`
+                same = [st for st in city.inter_city_stations if st.super_area is sa]
+                sa.closest_inter_city_station_for_city[city.name] = same[0] if same else city.inter_city_stations[0]
+        crng = np.random.default_rng(seed + 99)
+        for p in people:
+            if p.primary_activity is not None and p.primary_activity.group.spec == "company":
+                p.work_super_area = p.primary_activity.group.super_area
+                p.mode_of_transport = public if crng.random() < 0.5 else private
+                if p.mode_of_transport.is_public:
+                    city = p.work_super_area.city
+                    if p.area.super_area.city is city and crng.random() < 0.6:
+                        city.internal_commuter_ids.add(p.id)
+                    elif crng.random() < 0.8:
+                        p.area.super_area.closest_inter_city_station_for_city[city.name].commuter_ids.add(p.id)
+            else:
+                p.mode_of_transport = private
+        world.cities = Cities(cities, ball_tree=False)
+        world.city_transports = CityTransports(ctrans)
+        world.inter_city_transports = InterCityTransports(itrans)
     if with_leisure:
         # social venues: one pub per area, one grocery per two areas, one cinema per super area;
         # an area's candidates are hand-wired (the reference's distributor needs coordinates + a tree)
@@ -227,7 +273,8 @@ def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
 
 
 def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policies=True,
-                   initial_day="2020-03-02 0:00", schedule="default", with_leisure=False, lockdown=False):
+                   initial_day="2020-03-02 0:00", schedule="default", with_leisure=False, lockdown=False,
+                   with_commute=False):
     """Reference Simulator wired as ``example_scripts/run_simulation.py:332-512`` does, minus
     leisure / travel / records."""
     ref_harness.setup()
@@ -266,6 +313,18 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
     timer = Timer(initial_day=initial_day, total_days=total_days,
                   weekday_step_duration=wd_dur, weekend_step_duration=we_dur,
                   weekday_activities=wd_act, weekend_activities=we_act)
+    if with_commute:
+        # config_simulation.yaml:15-41 with commute (no leisure)
+        wd_dur, we_dur = [1, 8, 1, 3, 11], [12, 12]
+        wd_act = [["medical_facility", "residence", "commute"],
+                  ["medical_facility", "primary_activity", "residence"],
+                  ["medical_facility", "residence", "commute"],
+                  ["medical_facility", "residence"],
+                  ["medical_facility", "residence"]]
+        we_act = [["medical_facility", "residence"], ["medical_facility", "residence"]]
+        timer = Timer(initial_day=initial_day, total_days=total_days,
+                      weekday_step_duration=wd_dur, weekend_step_duration=we_dur,
+                      weekday_activities=wd_act, weekend_activities=we_act)
     if with_leisure:
         # config_simulation.yaml:15-41 with leisure (no commute)
         wd_dur, we_dur = [1, 8, 1, 3, 11], [4, 4, 4, 12]
@@ -306,8 +365,14 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
         leisure = generate_leisure_for_world(
             a2sg["leisure"], world,
             daytypes={"weekday": ["Monday", "Tuesday", "Wednesday", "Thursday", "Friday"], "weekend": ["Saturday", "Sunday"]})
+    travel = None
+    if with_commute:
+        from june.groups.travel import Travel
+        travel = Travel.__new__(Travel)  # only get_commute_subgroup is used (activity_manager.py:389)
+        a2sg["commute"] = ["city_transports", "inter_city_transports"]
+        all_activities = ["medical_facility", "commute", "primary_activity", "residence"]
     am = ActivityManager(world=world, policies=policies, timer=timer,
-                         all_activities=all_activities, activity_to_super_groups=a2sg, leisure=leisure)
+                         all_activities=all_activities, activity_to_super_groups=a2sg, leisure=leisure, travel=travel)
     sim = Simulator(world=world, interaction=interaction, timer=timer, activity_manager=am,
                     epidemiology=epidemiology, tracker=None, record=None)
     return sim

@@ -16,7 +16,7 @@ import pytest
 
 from june_b200 import _lib
 from june_b200.interaction import Interaction
-from june_b200.world import ACT_LEISURE, PS_ACT_MASK, PS_DEAD, PS_INFECTED
+from june_b200.world import ACT_COMMUTE, ACT_LEISURE, PS_ACT_MASK, PS_DEAD, PS_INFECTED
 
 from helpers import Golden, default_beta_table, have_gpu, make_engine, rows_to_dicts
 
@@ -64,6 +64,30 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
             at_venue = (pg >= 0) & (sg_act[grp_sg[np.maximum(pg, 0)]] == ACT_LEISURE)
             eng.inject_leisure(np.where(at_venue, pg, -1).astype(np.int32))
             flags |= _lib.STEP_INJECT_LEISURE
+        if g.world.has_commute:
+            # the reference's own station / transport choices (randint in city.py:95-97, station.py:52-76)
+            pg = s["place_group"]
+            on_transport = (pg >= 0) & (sg_act[grp_sg[np.maximum(pg, 0)]] == ACT_COMMUTE)
+            eng.inject_commute(np.where(on_transport, pg, -1).astype(np.int32))
+            flags |= _lib.STEP_INJECT_COMMUTE
+            run_trace.commuters = getattr(run_trace, "commuters", 0) + int(on_transport.sum())
+            if int(s["activity_mask"]) & (1 << ACT_COMMUTE):
+                # the compiled commute tables describe exactly what the reference did: every traveller is a
+                # commuter of the tables and sits on a transport of one of "its" stations; commuters who
+                # do not travel are in hospital / at home with severe symptoms / dead
+                w_ = g.world
+                assert (w_.person_commute[on_transport] >= 0).all()
+                tr_station = np.repeat(np.arange(len(w_.station_transport_off) - 1), np.diff(w_.station_transport_off.astype(np.int64)))
+                station_of = dict(zip(w_.station_transport.tolist(), tr_station.tolist()))
+                for q in np.nonzero(on_transport)[0]:
+                    code, st_ = int(w_.person_commute[q]), station_of[int(pg[q])]
+                    if code & 1:
+                        assert code >> 1 == st_
+                    else:
+                        c_ = code >> 1
+                        assert st_ in w_.city_station[w_.city_station_off[c_]: w_.city_station_off[c_ + 1]]
+                stayed = (w_.person_commute >= 0) & ~on_transport
+                assert stayed.sum() <= 0.1 * max(1, on_transport.sum())
         if "pol_active" in s:
             # individual policies: the reference's active list (in order) and every random() it drew
             recs = policy_records([str(x) for x in s["pol_active"]], g.z["close_companies_ratios"])
@@ -135,12 +159,14 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     return total_draws, total_inf, worst
 
 
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute"])
 def test_oracle_matches_reference_trace(name):
-    run_trace.policy_draws = 0
+    run_trace.policy_draws = run_trace.commuters = 0
     draws, infections, worst = run_trace("oracle", name)
     if name == "w2k_policies":
         assert run_trace.policy_draws > 5000, "the lockdown policies must have drawn"
+    if name == "w2k_commute":
+        assert run_trace.commuters > 2000, "commuters must have travelled"
     assert draws > 10000 and infections > 100
     assert worst <= REL
 
@@ -156,7 +182,7 @@ LAUNCH_MODES = {
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("modes", ["tiles", "warps", "mixed"])
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute"])
 def test_cuda_matches_reference_trace(name, modes):
     assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
     draws, infections, worst = run_trace("cuda", name, launch_modes=LAUNCH_MODES[modes])
