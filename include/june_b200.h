@@ -322,6 +322,48 @@ int jb_set_commute(JbWorld* w, const JbCommuteDesc* desc);
  * replaces the randint calls of city.py:95-97 and station.py:52-53,73-76. */
 int jb_inject_commute(JbWorld* w, const int32_t* group_per_person);
 
+/* ---- vaccination (epidemiology/vaccines/vaccination_campaign.py:36-385, vaccines.py:58-617;
+ * called once per simulated day per living person from update_health_status,
+ * epidemiology.py:295-303).  All dates are whole days (every day starts at the same hour), counted
+ * from the simulation's first day. */
+#define JB_MAX_VACCINES 8
+#define JB_MAX_CAMPAIGNS 16
+#define JB_MAX_DOSES 4
+typedef struct {
+  int32_t n_doses;                                   /* doses the vaccine defines (<= JB_MAX_DOSES) */
+  int32_t days_administered_to_effective[JB_MAX_DOSES];
+  int32_t days_effective_to_waning[JB_MAX_DOSES];
+  int32_t days_waning[JB_MAX_DOSES];
+  double waning_factor;
+  const double* sterilisation; /* [n_doses][n_variants][100 ages] efficacy against infection   */
+  const double* symptomatic;   /* [n_doses][n_variants][100 ages] efficacy against symptoms    */
+} JbVaccine;
+#define JB_VG_AGE 0        /* lo <= age < hi                         (vaccination_campaign.py:173-179) */
+#define JB_VG_RESIDENCE 1  /* lo: 1 = care_home, 0 = household        (residence.group.spec)           */
+#define JB_VG_PRIMARY 2    /* lo = JB_PA_KIND code of primary_activity.group.spec                      */
+#define JB_VG_SEX 3        /* lo: 0 = f, 1 = m                                                         */
+typedef struct {
+  int32_t vaccine;                       /* index into the vaccine table                              */
+  int32_t group_by, lo, hi;              /* JB_VG_*                                                   */
+  int32_t n_doses;                       /* len(dose_numbers)                                         */
+  int32_t dose_numbers[JB_MAX_DOSES];
+  int32_t days_to_next_dose[JB_MAX_DOSES];
+  int32_t start_day, end_day;            /* campaign active while start_day <= today < end_day        */
+  uint32_t last_dose_vaccines;           /* bit v: previous vaccine v accepted; 0 = any (:197-199)    */
+  double coverage;                       /* group_coverage                                            */
+} JbVaccinationCampaign;
+int jb_set_vaccination(JbWorld* w, const JbVaccine* vaccines, uint32_t n_vaccines,
+                       const JbVaccinationCampaign* campaigns, uint32_t n_campaigns);
+/* VaccinationCampaigns.apply + VaccineTrajectory.update_vaccine_effect for every living person,
+ * for the simulated day `today` (enqueued on the world's stream, after the last step). */
+int jb_vaccinate(JbWorld* w, int32_t today, uint64_t seed);
+/* Test mode: the uniform each person consumes in VaccinationCampaigns.apply (:373) on the next
+ * jb_vaccinate call; NULL switches back to Philox. */
+int jb_inject_vaccination_uniforms(JbWorld* w, const double* u);
+/* dose: person.vaccinated (-1 = None); vaccine: index of person.vaccine_type (-1 = None);
+ * effective_multiplier: [n_variants][n_people] (immunity.effective_multiplier_dict). */
+int jb_fetch_vaccination(JbWorld* w, int8_t* dose, int8_t* vaccine, double* effective_multiplier);
+
 /* ---- individual policies (policy/individual_policies.py:36-84) ---------------------------
  * The active individual policies, in the reference's list order, evaluated per person by the
  * placement stage.  A stay-home policy that fires reduces the person's activities to

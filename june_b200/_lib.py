@@ -81,6 +81,22 @@ class JbIndividualPolicy(C.Structure):
                 ("p", C.c_double * 6)]
 
 
+MAX_DOSES = 4
+
+
+class JbVaccine(C.Structure):
+    _fields_ = [("n_doses", C.c_int32), ("days_administered_to_effective", C.c_int32 * MAX_DOSES),
+                ("days_effective_to_waning", C.c_int32 * MAX_DOSES), ("days_waning", C.c_int32 * MAX_DOSES),
+                ("waning_factor", C.c_double), ("sterilisation", C.c_void_p), ("symptomatic", C.c_void_p)]
+
+
+class JbVaccinationCampaign(C.Structure):
+    _fields_ = [("vaccine", C.c_int32), ("group_by", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32),
+                ("n_doses", C.c_int32), ("dose_numbers", C.c_int32 * MAX_DOSES),
+                ("days_to_next_dose", C.c_int32 * MAX_DOSES), ("start_day", C.c_int32), ("end_day", C.c_int32),
+                ("last_dose_vaccines", C.c_uint32), ("coverage", C.c_double)]
+
+
 class JbCommuteDesc(C.Structure):
     _fields_ = [("n_cities", C.c_uint32), ("n_stations", C.c_uint32), ("person_commute", C.c_void_p),
                 ("city_station_off", C.c_void_p), ("city_station", C.c_void_p),
@@ -120,6 +136,7 @@ ABI_SYMBOLS = [
     "set_concurrency", "set_leisure", "set_leisure_tables", "inject_leisure",
     "set_individual_policies", "set_person_attributes", "inject_policy_uniforms", "fetch_infection_events",
     "set_commute", "inject_commute",
+    "set_vaccination", "vaccinate", "inject_vaccination_uniforms", "fetch_vaccination",
 ]
 
 
@@ -178,6 +195,10 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("set_individual_policies").argtypes = [vp, C.POINTER(JbIndividualPolicy), C.c_uint32, vp]
     f("set_person_attributes").argtypes = [vp, vp]
     f("inject_policy_uniforms").argtypes = [vp, vp]
+    f("set_vaccination").argtypes = [vp, C.POINTER(JbVaccine), C.c_uint32, C.POINTER(JbVaccinationCampaign), C.c_uint32]
+    f("vaccinate").argtypes = [vp, C.c_int32, C.c_uint64]
+    f("inject_vaccination_uniforms").argtypes = [vp, vp]
+    f("fetch_vaccination").argtypes = [vp, vp, vp, vp]
     f("set_commute").argtypes = [vp, C.POINTER(JbCommuteDesc)]
     f("inject_commute").argtypes = [vp, vp]
     f("fetch_infection_events").argtypes = [vp, vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]

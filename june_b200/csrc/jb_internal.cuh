@@ -88,6 +88,13 @@ struct PolicyDev {
   double rc[JB_MAX_REGIONS_POLICY];
 };
 
+// Vaccines and campaigns on the device (jb_set_vaccination); efficacy tables as device pointers.
+struct VaccDev {
+  uint32_t n_vaccines, n_campaigns;
+  JbVaccine vaccines[JB_MAX_VACCINES];
+  JbVaccinationCampaign campaigns[JB_MAX_CAMPAIGNS];
+};
+
 // Commute tables on the device (jb_set_commute).
 struct CommuteDev {
   const int32_t* person;     // [N] internal numbering: -1 | city << 1 | (station << 1) | 1
@@ -251,6 +258,15 @@ struct JbWorld {
   uint32_t *lz_parea = nullptr, *lz_off = nullptr, *lz_venue = nullptr;
   double *lz_does = nullptr, *lz_cum = nullptr;
   int32_t* lz_inject = nullptr;
+  // vaccination
+  VaccDev* d_vacc = nullptr;
+  std::vector<double*> vacc_tables;
+  int8_t *vac_dose = nullptr, *vac_type = nullptr, *traj_camp = nullptr;
+  int32_t* traj_day0 = nullptr;
+  uint8_t* traj_stage = nullptr;
+  double *prior_eff_inf = nullptr, *prior_eff_sym = nullptr, *effmult = nullptr, *vac_inject = nullptr;
+  bool vac_inject_on = false;
+  uint32_t n_campaigns = 0;
   // commute
   CommuteDev cmt = {};
   int32_t *cm_person = nullptr, *cm_inject = nullptr;

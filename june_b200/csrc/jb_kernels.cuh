@@ -587,6 +587,7 @@ struct NewInfArgs {
   uint32_t* summary;        // [R][JB_N_SUMMARY]
   const uint8_t* pregion;
   uint8_t* halo_ret;        // per halo person: variant+1 if infected here (or null)
+  const double* effmult;    // [V][N] immunity.effective_multiplier_dict, or null (no vaccination)
   int fuse_health;          // 1 inside a step: the creating lane also runs the slot's first health update
   HealthArgs h;
 };
@@ -633,7 +634,31 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, uint32_t bid
     const int pop = (a.ch[p] && age >= 50) ? 1 : 0;
     const double* cum = a.hi_cum + ((size_t)(pop * 2 + a.sex[p]) * 100 + age) * D.n_tags;
     // np.searchsorted(side="left"): the 16 lanes of the segment test one table entry each
-    const bool below = j < D.n_tags && cum[j] < max_sev;
+    double my_cum = j < D.n_tags ? cum[j] : 2.0;
+    const double mult = a.effmult ? a.effmult[(size_t)var * a.N + p] : 1.0;
+    if (mult != 1.0) {
+      // HealthIndexGenerator.apply_effective_multiplier (health_index.py:183-204): the mass of the
+      // outcomes from "severe" upwards (+ the residual) is scaled, the milder ones renormalised.
+      // Lane j holds outcome j; the sums run in index order, like the sequential reference.
+      const int max_mild = __ffs(D.severe_mask) - 1 - 2;
+      const double prev = __shfl_up_sync(segmask, my_cum, 1, 16);
+      const double pr = j < D.n_tags ? my_cum - (j ? prev : 0.0) : 0.0;
+      double total = 0.0, mild = 0.0, severe = 0.0;
+      for (int k = 0; k < D.n_tags; ++k) {
+        const double x = __shfl_sync(segmask, pr, k, 16);
+        total += x;
+        if (k < max_mild) mild += x; else severe += x;
+      }
+      severe += 1 - total;
+      const double mod_severe = severe * mult, mod_mild = 1.0 - mod_severe;
+      const double mine = j < max_mild ? pr * mod_mild / mild : pr * mod_severe / severe;
+      double run = 0.0;
+      for (int k = 0; k < D.n_tags; ++k) {
+        run += __shfl_sync(segmask, mine, k, 16);
+        if (k == j) my_cum = run;
+      }
+    }
+    const bool below = j < D.n_tags && my_cum < max_sev;
     int idx = __popc(__ballot_sync(segmask, below) & segmask);
     if (idx >= D.n_tags) idx = D.n_tags - 1;  // residual mass of a cumsum ending at 1-eps
     int k = 0;
@@ -794,6 +819,141 @@ __global__ void k_halo_return(const uint8_t* __restrict__ ret, const uint32_t* _
   if (!v) return;
   uint32_t k = atomicAdd(counter, 1u);
   if (k < cap) { member[k] = out_person[i]; variant[k] = (uint8_t)(v - 1); }
+}
+
+// ------------------------------------------------------------------------------------------
+// Vaccination: VaccinationCampaigns.apply + VaccineTrajectory.update_vaccine_effect for every living
+// person, once per simulated day (vaccination_campaign.py:340-385, vaccines.py:109-150,319-376;
+// called from epidemiology.py:295-303).  One thread per person; all state is per-person SoA.
+// ------------------------------------------------------------------------------------------
+struct VaccArgs {
+  const VaccDev* tab;
+  uint32_t N, NP;
+  int V;
+  int32_t today;
+  uint64_t seed;
+  uint32_t gid_base;
+  const uint32_t* int2ext;
+  uint8_t* pstate;
+  const uint8_t* age; const uint8_t* sex; const uint8_t* ch; const uint8_t* pattr;
+  double* susc;
+  int8_t* vac_dose; int8_t* vac_type; int8_t* traj_camp; int32_t* traj_day0; uint8_t* traj_stage;
+  double* prior_eff_inf; double* prior_eff_sym; double* effmult;
+  const double* inject;  // per-person uniform (test mode) or null
+};
+
+// Dose.get_efficacy (vaccines.py:109-150), t = whole days since the dose was administered.
+__device__ __forceinline__ double jb_dose_efficacy(double eff, double prior, double wf, int t, int A, int W, int Z) {
+  double pr, fin;
+  int n_days, duration;
+  if (t > A + W + Z) return wf * eff;
+  else if (t > A + W) { pr = eff; fin = wf * eff; n_days = t - (A + W); duration = Z; }
+  else if (t > A) return eff;
+  else { pr = prior; fin = eff; n_days = t; duration = A; }
+  const double m = (fin - pr) / (double)duration;
+  return m * (double)n_days + pr;
+}
+
+__global__ void __launch_bounds__(256) k_vaccinate(const __grid_constant__ VaccArgs a) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.N) return;
+  const uint32_t st = a.pstate[p];
+  if (st & JB_PS_DEAD) return;  // also the padding pseudo-persons
+  const VaccDev& T = *a.tab;
+  const int V = a.V;
+  const uint32_t N = a.N;
+  const int age_raw = a.age[p], age = min(age_raw, 99);
+  const uint32_t attr = a.pattr ? a.pattr[p] : 0u;
+  // ---- VaccinationCampaigns.apply ---------------------------------------------------------------
+  double prob[JB_MAX_CAMPAIGNS], norm = 0.0;
+  int cand[JB_MAX_CAMPAIGNS], n = 0;
+  const int dose_now = a.vac_dose[p], type_now = a.vac_type[p];
+  for (uint32_t k = 0; k < T.n_campaigns; ++k) {
+    const JbVaccinationCampaign& c = T.campaigns[k];
+    if (!(c.start_day <= a.today && a.today < c.end_day)) continue;
+    const int sd = c.dose_numbers[0];
+    bool ok = true;  // has_right_dosage (:182-202)
+    if (dose_now >= 0 && sd == 0) ok = false;
+    if (sd > 0) {
+      if (dose_now < 0 || dose_now != sd - 1) ok = false;
+      else if (c.last_dose_vaccines && !((c.last_dose_vaccines >> type_now) & 1u)) ok = false;
+    }
+    if (!ok) continue;
+    bool target;  // is_target_group (:151-180)
+    switch (c.group_by) {
+      case JB_VG_AGE: target = c.lo <= age_raw && age_raw < c.hi; break;
+      case JB_VG_RESIDENCE: target = (a.ch[p] != 0) == (c.lo != 0); break;
+      case JB_VG_PRIMARY: target = (int)JB_PA_KIND(attr) == c.lo; break;
+      default: target = (int)a.sex[p] == c.lo; break;
+    }
+    if (!target) continue;
+    const int total_days = c.end_day - c.start_day, days_passed = a.today - c.start_day;
+    prob[n] = c.coverage * (1 / ((double)total_days - (double)days_passed * c.coverage));  // :248-262
+    norm += prob[n];
+    cand[n++] = (int)k;
+  }
+  if (n) {
+    const JbPhilox4 r = jb_philox4x32_10(a.gid_base + a.int2ext[p], (uint32_t)a.today, JB_STREAM_VACCINE, 0u,
+                                         (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    const double u = a.inject ? a.inject[p] : jb_u52(r.x[0], r.x[1]);
+    if (u < norm) {
+      const double u2 = jb_u52(r.x[2], r.x[3]);
+      int pick = cand[n - 1];
+      double c = 0.0;
+      for (int i = 0; i < n; ++i) { c += prob[i] / norm; if (c > u2) { pick = cand[i]; break; } }
+      // VaccinationCampaign.vaccinate -> Vaccine.generate_trajectory (vaccines.py:515-617)
+      for (int v = 0; v < V; ++v) {
+        a.prior_eff_inf[(size_t)v * N + p] = 1.0 - a.susc[(size_t)v * a.NP + p];
+        a.prior_eff_sym[(size_t)v * N + p] = 1.0 - a.effmult[(size_t)v * N + p];
+      }
+      a.traj_camp[p] = (int8_t)pick; a.traj_day0[p] = a.today; a.traj_stage[p] = 0;
+      a.vac_dose[p] = (int8_t)T.campaigns[pick].dose_numbers[0];
+      a.vac_type[p] = (int8_t)T.campaigns[pick].vaccine;
+    }
+  }
+  // ---- VaccineTrajectory.update_vaccine_effect --------------------------------------------------
+  const int tc = a.traj_camp[p];
+  if (tc < 0) return;
+  const JbVaccinationCampaign& c = T.campaigns[tc];
+  const JbVaccine& vac = T.vaccines[c.vaccine];
+  int admin[JB_MAX_DOSES], day = a.traj_day0[p];
+#pragma unroll
+  for (int i = 0; i < JB_MAX_DOSES; ++i) { if (i < c.n_doses) day += c.days_to_next_dose[i]; admin[i] = day; }
+  const int last = c.n_doses - 1, nl = c.dose_numbers[last];
+  if (a.today > admin[last] + vac.days_administered_to_effective[nl] + vac.days_effective_to_waning[nl] + vac.days_waning[nl]) {
+    a.traj_camp[p] = -1;  // is_finished: person.vaccine_trajectory = None
+    return;
+  }
+  int stage = a.traj_stage[p];
+  const int number_before = c.dose_numbers[stage];
+  if (stage < last && a.today >= admin[stage + 1]) ++stage;  // update_trajectory_stage
+  a.traj_stage[p] = (uint8_t)stage;
+  const int num = c.dose_numbers[stage];
+  const int t = a.today - admin[stage];
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int kind = 0; kind < 2; ++kind) {
+      const double* tab = kind == 0 ? vac.sterilisation : vac.symptomatic;
+      const double eff = tab[((size_t)num * V + v) * 100 + age];
+      double* prior_arr = kind == 0 ? a.prior_eff_inf : a.prior_eff_sym;
+      const double prior0 = prior_arr[(size_t)v * N + p];
+      const double prior = stage == 0 ? prior0 : tab[((size_t)c.dose_numbers[stage - 1] * V + v) * 100 + age] * vac.waning_factor;
+      const double e = jb_dose_efficacy(eff, prior, vac.waning_factor, t, vac.days_administered_to_effective[num],
+                                        vac.days_effective_to_waning[num], vac.days_waning[num]);
+      const double updated = 1.0 - e, prior_v = 1.0 - prior0;
+      const double out = prior_v < updated ? prior_v : updated;
+      if (kind == 0) {
+        a.susc[(size_t)v * a.NP + p] = out;
+        if (v == 0) {  // the 2-bit code the interaction kernels read instead of the f64
+          const uint32_t code = out == 0.0 ? JB_SC_ZERO : out == 1.0 ? JB_SC_ONE : JB_SC_READ;
+          a.pstate[p] = (uint8_t)((st & ~JB_PST_CODE_MASK) | code);
+        }
+      } else {
+        a.effmult[(size_t)v * N + p] = out;
+      }
+    }
+  }
+  if (num != number_before) a.vac_dose[p] = (int8_t)num;
 }
 
 // Recompute the susceptibility codes kept in `pstate` after the host replaced susceptibilities.

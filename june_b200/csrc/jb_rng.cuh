@@ -16,6 +16,7 @@
 #define JB_STREAM_LEISURE 3u   // block 0: (does any activity, which activity), block 1: which venue
 #define JB_STREAM_BLAME 4u     // block 0: (which infector subgroup, which infector) of a new infection
 #define JB_STREAM_COMMUTE 5u   // block 0: (which station of the city, which transport of the station)
+#define JB_STREAM_VACCINE 6u   // counter word "step" = day; block 0: (gets vaccinated today, which campaign)
 #define JB_STREAM_POLICY0 8u   // + index of the individual policy (two uniforms per block)
 #define JB_STREAM_SAMPLE0 16u  // + sample slot (0..15) of a new infection, see k_newinf
 

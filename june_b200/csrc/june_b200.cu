@@ -361,9 +361,11 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
-                  w->cub_tmp, w->int2ext, w->ext2int, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
+                  w->cub_tmp, w->int2ext, w->ext2int, w->d_vacc, w->vac_dose, w->vac_type, w->traj_camp, w->traj_day0, w->traj_stage,
+                  w->prior_eff_inf, w->prior_eff_sym, w->effmult, w->vac_inject, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (double* q : w->vacc_tables) cudaFree(q);
   for (SgTiles& t : w->tiles) {
     if (t.tile_group0) cudaFree(t.tile_group0);
     if (t.tp_member) cudaFree(t.tp_member);
@@ -503,6 +505,105 @@ extern "C" int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person) {
   return JB_OK;
 }
 
+template <typename T>
+static int fetch_permuted(JbWorld* w, const T* dev, T* out);
+
+// ---- vaccination -------------------------------------------------------------------------------
+extern "C" int jb_set_vaccination(JbWorld* w, const JbVaccine* vac, uint32_t nv, const JbVaccinationCampaign* cam, uint32_t nc) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(nv <= JB_MAX_VACCINES && nc <= JB_MAX_CAMPAIGNS, "too many vaccines / campaigns");
+  REQUIRE((nv == 0 || vac) && (nc == 0 || cam), "null argument");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);  // k_newinf starts reading the effective multipliers
+  for (double* q : w->vacc_tables) cudaFree(q);
+  w->vacc_tables.clear();
+  VaccDev h;
+  memset(&h, 0, sizeof(h));
+  h.n_vaccines = nv; h.n_campaigns = nc;
+  for (uint32_t k = 0; k < nv; ++k) {
+    REQUIRE(vac[k].n_doses >= 1 && vac[k].n_doses <= JB_MAX_DOSES, "vaccine doses out of range");
+    h.vaccines[k] = vac[k];
+    const size_t n = (size_t)vac[k].n_doses * w->V * 100;
+    double *d0 = nullptr, *d1 = nullptr;
+    TRY(dev_upload(&d0, vac[k].sterilisation, n, w->stream));
+    TRY(dev_upload(&d1, vac[k].symptomatic, n, w->stream));
+    w->vacc_tables.push_back(d0); w->vacc_tables.push_back(d1);
+    h.vaccines[k].sterilisation = d0; h.vaccines[k].symptomatic = d1;
+  }
+  for (uint32_t k = 0; k < nc; ++k) {
+    const JbVaccinationCampaign& c = cam[k];
+    REQUIRE(c.vaccine >= 0 && (uint32_t)c.vaccine < nv && c.n_doses >= 1 && c.n_doses <= JB_MAX_DOSES, "bad campaign");
+    for (int i = 0; i < c.n_doses; ++i)
+      REQUIRE(c.dose_numbers[i] >= 0 && c.dose_numbers[i] < vac[c.vaccine].n_doses, "campaign dose number not defined by its vaccine");
+    h.campaigns[k] = c;
+  }
+  if (!w->d_vacc) TRY(dev_alloc(&w->d_vacc, 1));
+  CK(cudaMemcpyAsync(w->d_vacc, &h, sizeof(h), cudaMemcpyHostToDevice, w->stream));
+  if (!w->vac_dose) {
+    const size_t N = std::max(1u, w->N);
+    TRY(dev_alloc(&w->vac_dose, N)); TRY(dev_alloc(&w->vac_type, N)); TRY(dev_alloc(&w->traj_camp, N));
+    TRY(dev_alloc(&w->traj_day0, N)); TRY(dev_alloc(&w->traj_stage, N));
+    TRY(dev_alloc(&w->prior_eff_inf, N * w->V)); TRY(dev_alloc(&w->prior_eff_sym, N * w->V)); TRY(dev_alloc(&w->effmult, N * w->V));
+    CK(cudaMemsetAsync(w->vac_dose, 0xFF, N, w->stream)); CK(cudaMemsetAsync(w->vac_type, 0xFF, N, w->stream));
+    CK(cudaMemsetAsync(w->traj_camp, 0xFF, N, w->stream)); CK(cudaMemsetAsync(w->traj_day0, 0, N * 4, w->stream));
+    CK(cudaMemsetAsync(w->traj_stage, 0, N, w->stream));
+    CK(cudaMemsetAsync(w->prior_eff_inf, 0, N * w->V * 8, w->stream)); CK(cudaMemsetAsync(w->prior_eff_sym, 0, N * w->V * 8, w->stream));
+    k_fill_f64<<<(unsigned)((N * w->V + 255) / 256), 256, 0, w->stream>>>(w->effmult, N * w->V, 1.0);
+  }
+  CK(cudaStreamSynchronize(w->stream));
+  w->n_campaigns = nc;
+  return JB_OK;
+}
+
+extern "C" int jb_vaccinate(JbWorld* w, int32_t today, uint64_t seed) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(!w->in_step, "jb_vaccinate inside a step");
+  if (!w->n_campaigns || !w->N) return JB_OK;
+  CK(cudaSetDevice(w->device));
+  VaccArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tab = w->d_vacc; a.N = w->N; a.NP = w->NP; a.V = (int)w->V; a.today = today; a.seed = seed;
+  a.gid_base = (uint32_t)w->id_base; a.int2ext = w->int2ext; a.pstate = w->pstate;
+  a.age = w->age; a.sex = w->sex; a.ch = w->ch; a.pattr = w->pattr; a.susc = w->susc;
+  a.vac_dose = w->vac_dose; a.vac_type = w->vac_type; a.traj_camp = w->traj_camp; a.traj_day0 = w->traj_day0;
+  a.traj_stage = w->traj_stage; a.prior_eff_inf = w->prior_eff_inf; a.prior_eff_sym = w->prior_eff_sym; a.effmult = w->effmult;
+  a.inject = w->vac_inject_on ? w->vac_inject : nullptr;
+  k_vaccinate<<<(w->N + 255) / 256, 256, 0, w->stream>>>(a);
+  KCHECK("k_vaccinate", w->stream);
+  w->launches++;
+  return JB_OK;
+}
+
+extern "C" int jb_inject_vaccination_uniforms(JbWorld* w, const double* u) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  w->vac_inject_on = u != nullptr;
+  if (!u) return JB_OK;
+  std::vector<double> v(std::max(1u, w->N), 2.0);
+  for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = u[p];
+  if (!w->vac_inject) TRY(dev_alloc(&w->vac_inject, v.size()));
+  CK(cudaMemcpy(w->vac_inject, v.data(), v.size() * 8, cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
+extern "C" int jb_fetch_vaccination(JbWorld* w, int8_t* dose, int8_t* vaccine, double* effmult) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  if (!w->vac_dose) {
+    for (uint32_t p = 0; p < w->N_ext; ++p) { if (dose) dose[p] = -1; if (vaccine) vaccine[p] = -1; }
+    if (effmult) for (size_t i = 0; i < (size_t)w->N_ext * w->V; ++i) effmult[i] = 1.0;
+    return JB_OK;
+  }
+  if (dose) TRY(fetch_permuted(w, w->vac_dose, dose));
+  if (vaccine) TRY(fetch_permuted(w, w->vac_type, vaccine));
+  if (effmult)
+    for (uint32_t v = 0; v < w->V; ++v) TRY(fetch_permuted(w, w->effmult + (size_t)v * w->N, effmult + (size_t)v * w->N_ext));
+  return JB_OK;
+}
+
 // ---- commute ---------------------------------------------------------------------------------
 extern "C" int jb_set_commute(JbWorld* w, const JbCommuteDesc* d) {
   if (!w || !d) { jb_set_error("null argument"); return JB_EINVAL; }
@@ -597,6 +698,7 @@ static NewInfArgs make_newinf_args(JbWorld* w) {
   a.summary = w->summary; a.pregion = w->pregion;
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
   a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.pmed = w->pmed;
+  a.effmult = w->effmult;
   return a;
 }
 

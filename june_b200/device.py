@@ -12,7 +12,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (JbCommuteDesc, JbDisease, JbDist, JbIndividualPolicy, JbInfectionRow, JbLeisureDesc, JbStepParams, JbStepStats,
+from ._lib import (JbVaccine, JbVaccinationCampaign, JbCommuteDesc, JbDisease, JbDist, JbIndividualPolicy, JbInfectionRow, JbLeisureDesc, JbStepParams, JbStepStats,
                    JbSupergroup, JbWorldDesc, SimulatorError, ptr)
 from .disease import DiseaseConfig, health_index_cum
 from .interaction import Interaction
@@ -146,6 +146,50 @@ class Engine:
         g = np.ascontiguousarray(group_per_person, dtype=np.int32)
         assert g.shape == (self.world.n_people,)
         self._check(self._f("inject_leisure")(self._h, ptr(g)))
+
+    # ---- vaccination -------------------------------------------------------------------------------
+    def set_vaccination(self, vaccines: Sequence[dict], campaigns: Sequence[dict]):
+        """Tables produced by ``VaccinationCampaigns.device_tables``."""
+        va = (JbVaccine * max(1, len(vaccines)))()
+        keep = []
+        for k, v in enumerate(vaccines):
+            va[k].n_doses, va[k].waning_factor = int(v["n_doses"]), float(v["waning_factor"])
+            for q in range(v["n_doses"]):
+                va[k].days_administered_to_effective[q] = int(v["days_administered_to_effective"][q])
+                va[k].days_effective_to_waning[q] = int(v["days_effective_to_waning"][q])
+                va[k].days_waning[q] = int(v["days_waning"][q])
+            for name in ("sterilisation", "symptomatic"):
+                arr = np.ascontiguousarray(v[name], dtype=np.float64)
+                assert arr.shape == (v["n_doses"], self.n_variants, 100), arr.shape
+                keep.append(arr)
+                setattr(va[k], name, arr.ctypes.data)
+        ca = (JbVaccinationCampaign * max(1, len(campaigns)))()
+        for k, c in enumerate(campaigns):
+            ca[k].vaccine, ca[k].group_by, ca[k].lo, ca[k].hi = int(c["vaccine"]), int(c["group_by"]), int(c["lo"]), int(c["hi"])
+            ca[k].n_doses = len(c["dose_numbers"])
+            for q, (dn, dd) in enumerate(zip(c["dose_numbers"], c["days_to_next_dose"])):
+                ca[k].dose_numbers[q], ca[k].days_to_next_dose[q] = int(dn), int(dd)
+            ca[k].start_day, ca[k].end_day = int(c["start_day"]), int(c["end_day"])
+            ca[k].last_dose_vaccines, ca[k].coverage = int(c.get("last_dose_vaccines", 0)), float(c["coverage"])
+        self._check(self._f("set_vaccination")(self._h, va, len(vaccines), ca, len(campaigns)))
+
+    def vaccinate(self, today: int, seed: int = 0):
+        """One simulated day of ``VaccinationCampaigns.apply`` + ``update_vaccine_effect`` for everybody."""
+        self._check(self._f("vaccinate")(self._h, int(today), int(seed)))
+
+    def inject_vaccination_uniforms(self, u: Optional[np.ndarray]):
+        if u is None:
+            self._check(self._f("inject_vaccination_uniforms")(self._h, None))
+            return
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.shape == (self.world.n_people,)
+        self._check(self._f("inject_vaccination_uniforms")(self._h, ptr(u)))
+
+    def fetch_vaccination(self) -> Dict[str, np.ndarray]:
+        n = self.world.n_people
+        out = dict(dose=np.zeros(n, np.int8), vaccine=np.zeros(n, np.int8), effective_multiplier=np.ones((self.n_variants, n)))
+        self._check(self._f("fetch_vaccination")(self._h, ptr(out["dose"]), ptr(out["vaccine"]), ptr(out["effective_multiplier"])))
+        return out
 
     # ---- commute --------------------------------------------------------------------------------
     def _set_commute(self, world: WorldSoA):

@@ -118,6 +118,8 @@ class Epidemiology:
                  immunity_setter=None, medical_care_policies=None, vaccination_campaigns=None):
         self.infection_selectors = infection_selectors
         self.infection_seeds = list(infection_seeds or [])
+        self.vaccination_campaigns = vaccination_campaigns
+        self.current_date = None
 
     def infection_seeds_timestep(self, sim: "Simulator", timer: Timer) -> None:
         for s in self.infection_seeds:
@@ -189,6 +191,8 @@ class Simulator:
             ptr = self.device._f("stream_handle")(self.device.handle)
             self._ext_stream = torch.cuda.ExternalStream(int(ptr), device=torch.device("cuda", self.device.device_index))
         self._policy_key_on_device = None
+        self._vaccination_on_device = False
+        self.variant_names = ["Covid19"]  # infection class names, in variant order (vaccines.yaml keys)
         self.activity_manager.policies.init_policies(world)
         self._leisure_tables: dict = {}   # time-slot key -> table index on the device
         self._leisure_stack: List[tuple] = []
@@ -313,6 +317,17 @@ class Simulator:
             h.exchange_infections()
             stats = dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
         self.step_ordinal += 1
+        ep = self.epidemiology
+        if ep is not None and ep.vaccination_campaigns is not None and (
+                ep.current_date is None or self.timer.date.date() != ep.current_date.date()):
+            # once per simulated day, behind the day's first health update (epidemiology.py:127-135,295-303)
+            ep.current_date = self.timer.date
+            if not self._vaccination_on_device:
+                first = self.timer.initial_date.date()
+                self._vaccination_first_day = first
+                dev.set_vaccination(*ep.vaccination_campaigns.device_tables(first, self.variant_names))
+                self._vaccination_on_device = True
+            dev.vaccinate((self.timer.date.date() - self._vaccination_first_day).days, seed=self.seed)
         if stats is not None:
             self.last_stats = stats
             self.history.append(dict(date=self.timer.date, now=self.timer.now, **stats))

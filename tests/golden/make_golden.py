@@ -57,7 +57,7 @@ ROW_LEN = 5 + 5 + 2 * MAX_STAGES
 
 
 def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000,
-              with_leisure=False, lockdown=False, with_commute=False):
+              with_leisure=False, lockdown=False, with_commute=False, vaccination=False):
     pyrandom.seed(seed)
     np.random.seed(seed)
     sink = io.StringIO()
@@ -65,7 +65,7 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         world, dc = ref_world.build_world(n_people, seed=seed, with_leisure=with_leisure, with_commute=with_commute)
         sim = ref_world.make_simulator(world, dc, total_days=total_days, cases_per_capita=cases_per_capita,
                                        schedule=schedule, with_leisure=with_leisure, lockdown=lockdown,
-                                       with_commute=with_commute)
+                                       with_commute=with_commute, vaccination=vaccination)
     import june.interaction.interaction as inter_mod
     import june.policy.individual_policies as indiv_mod
     from june.epidemiology.infection import InfectionSelector
@@ -147,6 +147,26 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
                         return _f(person, *a, **kw)
                     setattr(pol, meth, wrapped)
 
+    # ---- vaccination: the uniform each person consumes in VaccinationCampaigns.apply -------------
+    vac_state = {"person": None, "u": {}}
+    if vaccination:
+        import june.epidemiology.vaccines.vaccination_campaign as vac_mod
+        vrng = np.random.default_rng(99 + seed)
+
+        def vac_random():
+            u = float(vrng.random())
+            vac_state["u"][pidx[vac_state["person"].id]] = u
+            return u
+
+        vac_mod.random = vac_random
+        orig_apply = vac_mod.VaccinationCampaigns.apply
+
+        def apply(self, person, date, record=None):
+            vac_state["person"] = person
+            return orig_apply(self, person=person, date=date, record=record)
+
+        vac_mod.VaccinationCampaigns.apply = apply
+
     steps = []
     orig_step = Simulator.do_timestep
     orig_am = type(sim.activity_manager).do_timestep
@@ -183,7 +203,11 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
             mf = p.subgroups.medical_facility if p.subgroups is not None else None
             if mf is not None:
                 med[i] = (gidx[id(mf.group)] << 8) | mf.group.subgroups.index(mf)
-        return dict(infected=inf, dead=dead, tag=tag, trans=trans, susc=susc, med=med, stage=stage)
+        out = dict(infected=inf, dead=dead, tag=tag, trans=trans, susc=susc, med=med, stage=stage)
+        if vaccination:
+            out["vac_dose"] = np.array([-1 if p.vaccinated is None else int(p.vaccinated) for p in people], np.int8)
+            out["effmult"] = np.array([p.immunity.effective_multiplier_dict.get(iid, 1.0) for p in people])
+        return out
 
     def do_timestep(self):
         rec = {}
@@ -191,7 +215,9 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         state["rows"] = []
         state["draw_person"], state["draw_lambda"], state["draw_u"] = [], [], []
         pol_state["draws"] = []
+        vac_state["u"] = {}
         timer = self.timer
+        vac_day = self.epidemiology.current_date is None or timer.date.date() != self.epidemiology.current_date.date()
         rec["now"], rec["dt"] = float(timer.now), float(timer.duration)
         mask = 0
         for a in timer.activities:
@@ -211,6 +237,12 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
                                         np.float64).reshape(-1, 4)
             rec["pol_active"] = np.array([type(p).__name__ for p in
                                           self.activity_manager.policies.individual_policies.get_active(date=timer.date).policies] or ["-"])
+        if vaccination and vac_day:
+            rec["vac_today"] = np.array((timer.date.date() - self.timer.initial_date.date()).days)
+            u = np.full(len(people), np.nan)
+            for k, v in vac_state["u"].items():
+                u[k] = v
+            rec["vac_u"] = u
         rec["post"] = snapshot()
         steps.append(rec)
 
@@ -290,6 +322,9 @@ def spot_values(out_name="spot"):
 if __name__ == "__main__":
     if "leisure" in sys.argv[1:]:  # leisure placement (pubs, cinemas, groceries) on top of the w3k recipe
         run_trace(2500, 9, 2, "w2k_leisure", cases_per_capita=0.04, with_leisure=True)
+        sys.exit(0)
+    if "vaccination" in sys.argv[1:]:  # two campaigns, doses 0 and 1, waning
+        run_trace(2500, 14, 5, "w2k_vaccination", cases_per_capita=0.04, vaccination=True)
         sys.exit(0)
     if "commute" in sys.argv[1:]:  # city / inter-city transports on the two commute steps of a weekday
         run_trace(2500, 9, 4, "w2k_commute", cases_per_capita=0.05, with_commute=True)

@@ -272,9 +272,21 @@ def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
     return world, dc
 
 
+VACCINES = {
+    "Pfizer": dict(days_administered_to_effective=[2, 2, 5], days_effective_to_waning=[1, 2, 1], days_waning=[2, 2, 1],
+                   waning_factor=0.8,
+                   sterilisation_efficacies=[{"Covid19": {"0-100": 0.52}}, {"Covid19": {"0-70": 0.95, "70-100": 0.85}}, {"Covid19": {"0-100": 0.98}}],
+                   symptomatic_efficacies=[{"Covid19": {"0-100": 0.6}}, {"Covid19": {"0-100": 0.9}}, {"Covid19": {"0-100": 0.98}}]),
+    "AstraZeneca": dict(days_administered_to_effective=[3, 7, 5], days_effective_to_waning=[2, 1, 1], days_waning=[3, 1, 1],
+                        waning_factor=1.0,
+                        sterilisation_efficacies=[{"Covid19": {"0-100": 0.32}}, {"Covid19": {"0-100": 0.75}}, {"Covid19": {"0-100": 0.88}}],
+                        symptomatic_efficacies=[{"Covid19": {"0-100": 0.4}}, {"Covid19": {"0-100": 0.75}}, {"Covid19": {"0-100": 0.88}}]),
+}
+
+
 def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policies=True,
                    initial_day="2020-03-02 0:00", schedule="default", with_leisure=False, lockdown=False,
-                   with_commute=False):
+                   with_commute=False, vaccination=False):
     """Reference Simulator wired as ``example_scripts/run_simulation.py:332-512`` does, minus
     leisure / travel / records."""
     ref_harness.setup()
@@ -294,8 +306,22 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
                                             cases_per_capita=cases_per_capita,
                                             date=initial_day.split(" ")[0],
                                             seed_past_infections=False)
+    campaigns = None
+    if vaccination:
+        # two campaigns over disjoint target groups (so that np.random.choice is never needed):
+        # the over-60s get doses 0 and 1 three days apart, care-home residents a single dose
+        from june.epidemiology.vaccines.vaccination_campaign import VaccinationCampaign, VaccinationCampaigns
+        from june.epidemiology.vaccines.vaccines import Vaccine
+        pfizer = Vaccine.from_config_dict("Pfizer", VACCINES["Pfizer"])
+        az = Vaccine.from_config_dict("AstraZeneca", VACCINES["AstraZeneca"])
+        campaigns = VaccinationCampaigns([
+            VaccinationCampaign(vaccine=pfizer, days_to_next_dose=[0, 3], dose_numbers=[0, 1], start_time="2020-03-03",
+                                end_time="2020-03-08", group_by="age", group_type="60-100", group_coverage=0.6),
+            VaccinationCampaign(vaccine=az, days_to_next_dose=[0], dose_numbers=[0], start_time="2020-03-04",
+                                end_time="2020-03-07", group_by="age", group_type="30-45", group_coverage=0.5),
+        ])
     epidemiology = Epidemiology(infection_selectors=InfectionSelectors([selector]),
-                                infection_seeds=InfectionSeeds([seed]))
+                                infection_seeds=InfectionSeeds([seed]), vaccination_campaigns=campaigns)
     interaction = Interaction.from_file()
     if schedule == "default":
         # config_simulation.yaml:15-41 without commute/leisure activities

@@ -37,6 +37,30 @@ def policy_records(names, ratios):
     return [(n, table[n]) for n in names if n in table]
 
 
+# the campaigns of the w2k_vaccination trace (tests/golden/ref_world.py: VACCINES, make_simulator)
+def vaccination_tables():
+    import datetime
+
+    from june_b200.vaccination import Vaccine, VaccinationCampaign, VaccinationCampaigns
+    cfg = {
+        "Pfizer": dict(days_administered_to_effective=[2, 2, 5], days_effective_to_waning=[1, 2, 1], days_waning=[2, 2, 1],
+                       waning_factor=0.8,
+                       sterilisation_efficacies=[{"Covid19": {"0-100": 0.52}}, {"Covid19": {"0-70": 0.95, "70-100": 0.85}}, {"Covid19": {"0-100": 0.98}}],
+                       symptomatic_efficacies=[{"Covid19": {"0-100": 0.6}}, {"Covid19": {"0-100": 0.9}}, {"Covid19": {"0-100": 0.98}}]),
+        "AstraZeneca": dict(days_administered_to_effective=[3, 7, 5], days_effective_to_waning=[2, 1, 1], days_waning=[3, 1, 1],
+                            waning_factor=1.0,
+                            sterilisation_efficacies=[{"Covid19": {"0-100": 0.32}}, {"Covid19": {"0-100": 0.75}}, {"Covid19": {"0-100": 0.88}}],
+                            symptomatic_efficacies=[{"Covid19": {"0-100": 0.4}}, {"Covid19": {"0-100": 0.75}}, {"Covid19": {"0-100": 0.88}}]),
+    }
+    pf, az = (Vaccine.from_config_dict(k, cfg[k]) for k in ("Pfizer", "AstraZeneca"))
+    camps = VaccinationCampaigns([
+        VaccinationCampaign(vaccine=pf, days_to_next_dose=[0, 3], dose_numbers=[0, 1], start_time="2020-03-03",
+                            end_time="2020-03-08", group_by="age", group_type="60-100", group_coverage=0.6),
+        VaccinationCampaign(vaccine=az, days_to_next_dose=[0], dose_numbers=[0], start_time="2020-03-04",
+                            end_time="2020-03-07", group_by="age", group_type="30-45", group_coverage=0.5)])
+    return camps.device_tables(datetime.date(2020, 3, 2), ["Covid19"])
+
+
 def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     g = Golden(name)
     if launch_modes is not None:  # exercise the other kernel flavour on the same trace
@@ -51,6 +75,8 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     sg_act = np.array([sg.activity for sg in g.world.supergroups])
     total_draws = total_inf = 0
     worst = 0.0
+    if "s0_vac_today" in g.z.files:
+        eng.set_vaccination(*vaccination_tables())
     for i in range(g.n_steps if max_steps is None else min(max_steps, g.n_steps)):
         s = g.step(i)
         if len(s["pre_rows"]):
@@ -127,6 +153,12 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
             eng.upload_infections(rows_to_dicts(s["new_rows"]))
         stats = eng.step_finish()
         assert stats["n_draws"] == len(dp)
+        if "vac_today" in s:
+            # the day's vaccinations follow the health update (epidemiology.py:295-303); the reference's
+            # own random() per person is replayed
+            eng.inject_vaccination_uniforms(np.where(np.isnan(s["vac_u"]), 2.0, s["vac_u"]))
+            eng.vaccinate(int(s["vac_today"]))
+            run_trace.vaccine_draws = getattr(run_trace, "vaccine_draws", 0) + int((~np.isnan(s["vac_u"])).sum())
         # -- placement -------------------------------------------------------------------------------
         st = eng.fetch_person_state()
         act = st["pstate"] & PS_ACT_MASK
@@ -152,6 +184,10 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
             worst = max(worst, float(terr.max()))
             assert terr.max() <= REL, f"step {i}: transmission probability differs by {terr.max():.3e}"
         assert np.array_equal(st["susceptibility"][0], s["post_susc"]), f"step {i}: susceptibilities"
+        if "post_vac_dose" in s:
+            vs = eng.fetch_vaccination()
+            assert np.array_equal(vs["dose"], s["post_vac_dose"]), f"step {i}: person.vaccinated"
+            assert np.array_equal(vs["effective_multiplier"][0], s["post_effmult"]), f"step {i}: effective multipliers"
         assert stats["n_infected"] == int(inf.sum())
         total_draws += len(dp)
         total_inf += len(ref_new)
@@ -159,14 +195,16 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     return total_draws, total_inf, worst
 
 
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute", "w2k_vaccination"])
 def test_oracle_matches_reference_trace(name):
-    run_trace.policy_draws = run_trace.commuters = 0
+    run_trace.policy_draws = run_trace.commuters = run_trace.vaccine_draws = 0
     draws, infections, worst = run_trace("oracle", name)
     if name == "w2k_policies":
         assert run_trace.policy_draws > 5000, "the lockdown policies must have drawn"
     if name == "w2k_commute":
         assert run_trace.commuters > 2000, "commuters must have travelled"
+    if name == "w2k_vaccination":
+        assert run_trace.vaccine_draws > 1500, "eligible people must have drawn for their jab"
     assert draws > 10000 and infections > 100
     assert worst <= REL
 
@@ -182,7 +220,7 @@ LAUNCH_MODES = {
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("modes", ["tiles", "warps", "mixed"])
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute"])
+@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute", "w2k_vaccination"])
 def test_cuda_matches_reference_trace(name, modes):
     assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
     draws, infections, worst = run_trace("cuda", name, launch_modes=LAUNCH_MODES[modes])
