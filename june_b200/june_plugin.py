@@ -65,7 +65,10 @@ def make_b200_simulator_class(reference_simulator_cls):
                 ig = g.get_interactive_group(None)
                 sector_betas = dict(type(ig).sector_betas)
                 break
-            self._soa = compile_world(self.world, a2sg, sector_betas)
+            self._soa = compile_world(self.world, a2sg, sector_betas, leisure=am.leisure, travel=am.travel)
+            self._leisure_cache = {}
+            self._leisure_stack = []
+            self._policy_key = None
             ref_inter = self.interaction
             self._inter = Interaction.__new__(Interaction)
             self._inter.alpha_physical = ref_inter.alpha_physical
@@ -146,6 +149,78 @@ def make_b200_simulator_class(reference_simulator_cls):
                     inf.transmission.probability = float(st["trans_prob"][i])
                     inf.symptoms.tag = int(st["tag"][i])
 
+        # ---- leisure tables from the reference's own Leisure object ----------------------------------
+        def _b200_leisure_table(self, activities, pol):
+            """``ActivityManager.do_timestep`` (``activity_manager.py:200-209``): leisure policies, then
+            ``generate_leisure_probabilities_for_timestep``.  The reference's nested dict is flattened
+            into ``does[R][2][100]`` / ``cum[R][2][100][K]`` over the device's activities; the mass of
+            activities without device support (residence visits) counts as "stays at home"."""
+            leisure = self.activity_manager.leisure
+            if leisure is None or not self._soa.has_leisure or "leisure" not in activities:
+                return 0
+            date = self.timer.date
+            if pol is not None:
+                pol.leisure_policies.apply(date=date, leisure=leisure)
+            key = (round(self.timer.duration, 9), "primary_activity" in activities, date.weekday(), date.hour, self._policy_key)
+            idx = self._leisure_cache.get(key)
+            if idx is None:
+                leisure.generate_leisure_probabilities_for_timestep(
+                    delta_time=self.timer.duration, date=date, working_hours="primary_activity" in activities)
+                table = leisure.probabilities_by_region_sex_age
+                specs, R = self._soa.leisure_activities, self._soa.n_regions
+                does, cum = np.zeros((R, 2, 100)), np.zeros((R, 2, 100, len(specs)))
+                for r, name in enumerate(self._soa.region_names):
+                    per = table.get(name, table) if isinstance(table, dict) and name in table else table
+                    for si, sex in enumerate("fm"):
+                        for age in range(100):
+                            e = per[sex][age]
+                            probs = np.array([e["activities"].get(sp, 0.0) for sp in specs], np.float64)
+                            kept = probs.sum()
+                            does[r, si, age] = e["does_activity"] * kept
+                            cum[r, si, age] = np.cumsum(probs / kept) if kept > 0 else 1.0
+                self._leisure_stack.append((does, cum))
+                idx = self._leisure_cache[key] = len(self._leisure_stack) - 1
+                self._eng.set_leisure_tables(np.stack([t[0] for t in self._leisure_stack]),
+                                             np.stack([t[1] for t in self._leisure_stack]))
+            return idx + 1
+
+        # ---- individual policies of the reference -> device records -----------------------------------
+        def _b200_policy_records(self, pol, comp):
+            date = self.timer.date
+            active = [p for p in pol.individual_policies.policies if p.is_active(date)] if pol is not None else []
+            key = tuple(id(p) for p in active) + tuple(comp)
+            if key == self._policy_key:
+                return
+            nan = float("nan")
+
+            def opt(x):
+                return nan if x is None else x
+
+            recs = []
+            for p in active:
+                name = type(p).__name__
+                if name == "Quarantine":
+                    recs.append(dict(type=_lib.POL_QUARANTINE, mask=self._dc.tag_mask("stay_at_home_stage"), p=[p.n_days, p.compliance]))
+                elif name == "Shielding":
+                    recs.append(dict(type=_lib.POL_SHIELDING, p=[p.min_age, opt(p.compliance)]))
+                elif name == "CloseSchools":
+                    mask = 0
+                    for y in p.years_to_close or []:
+                        if 0 <= int(y) < 32:
+                            mask |= 1 << int(y)
+                    recs.append(dict(type=_lib.POL_CLOSE_SCHOOLS, flags=1 if p.full_closure else 0, mask=mask, p=[p.attending_compliance]))
+                elif name == "CloseUniversities":
+                    recs.append(dict(type=_lib.POL_CLOSE_UNIVERSITIES))
+                elif name == "CloseCompanies":
+                    recs.append(dict(type=_lib.POL_CLOSE_COMPANIES, flags=1 if p.full_closure else 0,
+                                     p=[opt(p.avoid_work_probability), opt(p.furlough_probability), opt(p.key_probability),
+                                        opt(type(p).furlough_ratio), opt(type(p).key_ratio), opt(type(p).random_ratio)]))
+                elif name != "SevereSymptomsStayHome":
+                    raise NotImplementedError(f"individual policy {name} has no device implementation (INTEGRATION.md section 4)")
+            if recs or self._policy_key is not None:
+                self._eng.set_individual_policies(recs, comp)
+            self._policy_key = key
+
         # ---- the replaced method --------------------------------------------------------------------
         def do_timestep(self):
             if not hasattr(self, "_eng"):
@@ -174,8 +249,10 @@ def make_b200_simulator_class(reference_simulator_cls):
                     flags |= _lib.STEP_SEVERE_STAY_HOME
                 if any(type(p).__name__ == "Hospitalisation" and p.is_active(date) for p in pol.medical_care_policies.policies):
                     flags |= _lib.STEP_HOSPITALISATION
+            self._b200_policy_records(pol, comp)
             params = self._eng.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self._step,
-                                           activity_mask=mask, seed=self.b200_seed, flags=flags, beta=beta)
+                                           activity_mask=mask, seed=self.b200_seed, flags=flags, beta=beta,
+                                           leisure_table=self._b200_leisure_table(activities, pol))
             self.b200_last_stats = self._eng.step(params)
             self._step += 1
             self._b200_write_back()

@@ -212,6 +212,17 @@ class Policies:
 
     def __init__(self, policies: Optional[Sequence[Policy]] = None):
         self.policies: List[Policy] = list(policies or [])
+        self._edges: Optional[List[datetime.datetime]] = None
+
+    def active_key(self, date: datetime.datetime) -> int:
+        """Index of the interval between two consecutive policy start / end times that holds
+        ``date``: the set of active policies is constant inside an interval, so this integer keys
+        everything derived from it (one bisection per step instead of one comparison per policy)."""
+        if self._edges is None or self._edges_n != len(self.policies):
+            self._edges = sorted({t for p in self.policies for t in (p.start_time, p.end_time)})
+            self._edges_n = len(self.policies)
+        import bisect
+        return bisect.bisect_right(self._edges, date)
 
     def _of(self, ptype: str) -> List[Policy]:
         return [p for p in self.policies if p.policy_type == ptype]

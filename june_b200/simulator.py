@@ -225,7 +225,7 @@ class Simulator:
         cached per active-policy set."""
         date = self.timer.date
         policies = self.activity_manager.policies
-        key = tuple(p.is_active(date) for p in policies.policies)
+        key = policies.active_key(date)
         hit = self._policy_cache.get(key)
         if hit is None:
             self.interaction.beta_reductions = policies.beta_reductions(date)
@@ -259,7 +259,7 @@ class Simulator:
             end = self.timer.date + datetime.timedelta(days=days)
             upload, self.device.set_leisure_tables = self.device.set_leisure_tables, lambda *a: None
             while self.timer.date < end and self.timer.date < self.timer.final_date:
-                self.leisure_table(tuple(p.is_active(self.timer.date) for p in policies.policies))
+                self.leisure_table(policies.active_key(self.timer.date))
                 next(self.timer)
         finally:
             self.timer = saved

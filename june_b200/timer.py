@@ -79,9 +79,11 @@ class Timer:
                    weekday_activities=t["step_activities"]["weekday"],
                    weekend_activities=t["step_activities"]["weekend"], day_types=day_types)
 
+    _DAY_NAMES = ("Monday", "Tuesday", "Wednesday", "Thursday", "Friday", "Saturday", "Sunday")
+
     @property
     def day_of_week(self) -> str:
-        return calendar.day_name[self.date.weekday()]
+        return self._DAY_NAMES[self.date.weekday()]  # calendar.day_name goes through strftime on every access
 
     @property
     def is_weekend(self) -> bool:

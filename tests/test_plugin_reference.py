@@ -48,3 +48,44 @@ def test_reference_simulator_subclass_runs_on_the_abi():
     assert n_inf == int(((st["pstate"] & 0x08) != 0).sum())
     # subgroup lists of the reference objects stay untouched (placement lives on the device)
     assert all(len(sg.people) == 0 for g in world.companies.members for sg in g.subgroups)
+
+
+def test_reference_simulator_subclass_with_leisure_commute_and_lockdown():
+    """The same binding with the reference's own Leisure / Travel objects and lockdown policies: venues,
+    transports and the policy records are compiled from the reference objects."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_world
+    from june_b200.june_plugin import make_b200_simulator_class
+    from helpers import make_engine
+
+    random.seed(4)
+    np.random.seed(4)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        world, dc = ref_world.build_world(2500, seed=4, with_leisure=True)
+        ref_sim = ref_world.make_simulator(world, dc, total_days=8, cases_per_capita=0.04, with_leisure=True, lockdown=True)
+    from june.simulator import Simulator
+    B200Simulator = make_b200_simulator_class(Simulator)
+    B200Simulator.b200_engine = staticmethod(lambda soa, inter, dcfg, prob: make_engine("oracle", soa, prob, interaction=inter, disease=dcfg))
+    sim = B200Simulator(world=world, interaction=ref_sim.interaction, timer=ref_sim.timer,
+                        activity_manager=ref_sim.activity_manager, epidemiology=ref_sim.epidemiology,
+                        tracker=None, record=None)
+    seen = {"leisure": 0, "skipped_work": 0}
+    orig = B200Simulator.do_timestep
+
+    def step(self):
+        orig(self)
+        st = self.b200_last_stats
+        seen["leisure"] += st["n_by_activity"][3]
+        if "primary_activity" in self.timer.activities and self.timer.date.day >= 6:
+            seen["skipped_work"] += 1 if st["n_by_activity"][2] < 0.8 * first_work[0] else 0
+        elif "primary_activity" in self.timer.activities and not first_work:
+            first_work.append(st["n_by_activity"][2])
+
+    first_work = []
+    B200Simulator.do_timestep = step
+    with contextlib.redirect_stdout(sink):
+        sim.run()
+    assert sim._soa.has_leisure and sim._soa.leisure_activities == ["pub", "cinema", "grocery"]
+    assert seen["leisure"] > 1000, "people must have gone to pubs / cinemas / groceries"
+    assert seen["skipped_work"] >= 1, "CloseCompanies / CloseSchools must keep people away from work"
