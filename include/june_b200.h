@@ -403,6 +403,25 @@ int jb_set_person_attributes(JbWorld* w, const uint8_t* attr);
  * [JB_POLICY_DRAWS][n_people]; replaces Python's random() in individual_policies.py. */
 int jb_inject_policy_uniforms(JbWorld* w, const double* u);
 
+/* ---- halo exchange over peer memory (NVLink P2P) instead of host-issued collectives ----------
+ * One process per GPU.  Every rank allocates an exchange window (inbound person records, inbound
+ * "infected abroad" bytes, arrival flags), exports it as a CUDA IPC handle and opens its peers'
+ * windows.  From then on jb_step runs halo worlds as ONE replayed graph: the pack kernel stores
+ * the outbound records straight into the destination GPU's window and raises that GPU's flag;
+ * the consumer spins on its own flag (bounded) before unpacking.  The two exchanges of a step
+ * fence each other, so one window per direction suffices.
+ *   jb_p2p_window : allocate the window of this world; writes 80 bytes: its 64-byte IPC handle
+ *                   followed by two uint64 section sizes
+ *   jb_p2p_connect: `handles` = the 64-byte handles of all ranks, [world_size][64], followed by the
+ *                   section sizes of all ranks, [world_size][2] uint64; out_counts / in_counts
+ *                   as for the all-to-all; peer_recv_base[q] = first record of this rank's segment
+ *                   in rank q's inbound window, peer_ret_base[q] = first byte of this rank's
+ *                   segment in rank q's return window (= q's outbound offset for this rank). */
+#define JB_MAX_RANKS 16
+int jb_p2p_window(JbWorld* w, void* ipc_handle_out);
+int jb_p2p_connect(JbWorld* w, int rank, int world_size, const void* handles, const uint32_t* out_counts,
+                   const uint32_t* in_counts, const uint32_t* peer_recv_base, const uint32_t* peer_ret_base);
+
 int jb_sync(JbWorld* w);
 
 /* Readback (synchronises).  `cap` = capacity of the caller's arrays, `*n` = entries written. */
@@ -432,6 +451,9 @@ int jb_timing_enable(JbWorld* w, int on);
 int jb_set_concurrency(JbWorld* w, int on);
 int jb_timing_read(JbWorld* w, double* interaction_ms, double* step_ms, uint64_t* n_steps,
                    uint64_t* n_launches, int reset);
+/* Benchmark aid: overwrite `bytes` of scratch on the library's stream (evicts the L2 between timed
+ * steps; enqueued in front of, i.e. outside, the next step's event bracket; no host wait). */
+int jb_flush_l2(JbWorld* w, size_t bytes);
 /* Algorithmic bytes of the interaction kernels for the last step. */
 int jb_last_step_bytes(JbWorld* w, uint64_t* interaction_bytes, uint64_t* step_bytes);
 

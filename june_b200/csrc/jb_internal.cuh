@@ -112,7 +112,18 @@ struct StepDev {
   double now, dt, t_now;
   uint64_t seed;
   uint32_t step, activity_mask, flags, n_inject;
-  uint32_t leisure_table, pad_[3];
+  uint32_t leisure_table, epoch, pad_[2];   // epoch: steps since create (arrival-flag value of the P2P exchange)
+};
+
+// Peer-memory halo exchange (jb_p2p_connect): windows of all ranks as seen from this GPU.
+struct P2PDev {
+  int rank, ws;
+  unsigned char* recv[JB_MAX_RANKS];   // inbound person records of rank q
+  uint8_t* ret[JB_MAX_RANKS];          // inbound "infected abroad" bytes of rank q
+  uint32_t* flag_people[JB_MAX_RANKS]; // flag_people[q][r]: records of rank r have arrived at q
+  uint32_t* flag_ret[JB_MAX_RANKS];
+  uint32_t out_off[JB_MAX_RANKS + 1], in_off[JB_MAX_RANKS + 1];
+  uint32_t peer_recv_base[JB_MAX_RANKS], peer_ret_base[JB_MAX_RANKS];
 };
 
 // Arguments of the interaction (group) kernels; passed by value as a __grid_constant__.
@@ -258,6 +269,14 @@ struct JbWorld {
   uint32_t *lz_parea = nullptr, *lz_off = nullptr, *lz_venue = nullptr;
   double *lz_does = nullptr, *lz_cum = nullptr;
   int32_t* lz_inject = nullptr;
+  // peer-memory halo exchange
+  bool p2p_on = false;
+  P2PDev p2p = {};
+  unsigned char* p2p_window = nullptr;   // this rank's window (cudaMalloc, IPC-exported)
+  std::vector<void*> p2p_opened;         // peers' windows opened with cudaIpcOpenMemHandle
+  uint32_t* p2p_done = nullptr;          // last-block tickets of the two push kernels
+  uint8_t* p2p_ret_local = nullptr;      // [H] variant+1 of halo persons infected here (before it is pushed home)
+  size_t p2p_recv_bytes = 0, p2p_ret_bytes = 0;
   // vaccination
   VaccDev* d_vacc = nullptr;
   std::vector<double*> vacc_tables;
@@ -305,6 +324,12 @@ struct JbWorld {
   double acc_int_ms = 0, acc_step_ms = 0;
   uint64_t acc_steps = 0, acc_launches = 0;
   bool ev_pending = false;
+  // timing level 1 keeps a ring of event pairs so that timed steps can be queued without a host
+  // synchronisation per step; pairs are folded into acc_step_ms when the ring wraps or on read
+  std::vector<cudaEvent_t> ring0, ring1;
+  uint64_t ring_head = 0, ring_tail = 0;
+  unsigned char* flush_buf = nullptr;
+  size_t flush_bytes = 0;
   uint64_t last_int_bytes = 0, last_step_bytes = 0;
   uint64_t launches = 0;
 };

@@ -809,6 +809,76 @@ __global__ void k_halo_unpack(const unsigned char* __restrict__ recv, uint32_t H
   if (halo_ret) halo_ret[j] = 0;
 }
 
+// ---- the same exchange over peer memory ------------------------------------------------------------
+// k_halo_push: like k_halo_pack, but every record is stored straight into the destination GPU's window
+// (NVLink P2P store); the last block to finish publishes this rank's arrival flag on every peer.
+__device__ __forceinline__ void jb_p2p_signal(uint32_t* const* flags, const P2PDev& P, uint32_t* done, uint32_t epoch) {
+  __threadfence_system();  // this block's remote stores are visible system-wide before the ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t ticket = atomicAdd(done, 1u);
+    if (ticket == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      for (int q = 0; q < P.ws; ++q)
+        if (q != P.rank) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags[q] + P.rank), "r"(epoch) : "memory");
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_halo_push(const __grid_constant__ P2PDev P, const uint32_t* __restrict__ out_person,
+                                                  uint32_t n_out, const uint8_t* __restrict__ phot,
+                                                  const double* __restrict__ susc, const double* __restrict__ trans,
+                                                  uint32_t NP, int V, const StepDev* sp, uint32_t* done) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_out) {
+    int q = 0;
+    while (q + 1 < P.ws && i >= P.out_off[q + 1]) ++q;
+    const uint32_t p = out_person[i];
+    const size_t rec = 8 + (size_t)8 * V;
+    unsigned char* r = P.recv[q] + ((size_t)P.peer_recv_base[q] + (i - P.out_off[q])) * rec;
+    const uint32_t st = phot[p];
+    *(uint64_t*)r = (uint64_t)st;
+    double* d = (double*)(r + 8);
+    if (st & JB_PS_INFECTED) {
+      d[0] = trans[p];
+      for (int v = 1; v < V; ++v) d[v] = 0.0;
+    } else {
+      for (int v = 0; v < V; ++v) d[v] = susc[(size_t)v * NP + p];
+    }
+  }
+  jb_p2p_signal(P.flag_people, P, done, sp->epoch);
+}
+
+// One thread per peer spins (bounded) until that peer's flag for this step has arrived.
+__global__ void k_halo_wait(const uint32_t* flags_self, int ws, int rank, const StepDev* sp, uint32_t* counters) {
+  const int q = threadIdx.x;
+  if (q >= ws || q == rank) return;
+  const uint32_t epoch = sp->epoch;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags_self + q) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) { atomicAdd(&counters[CNT_OVERFLOW], 1u); break; }  // 20 s: a peer is gone
+    __nanosleep(200);
+  }
+}
+
+// Bytes of the halo persons infected here go to their home GPU's return window.
+__global__ void __launch_bounds__(256) k_halo_ret_push(const __grid_constant__ P2PDev P, const uint8_t* __restrict__ ret_local,
+                                                      uint32_t H, const StepDev* sp, uint32_t* done) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < H) {
+    int s = 0;
+    while (s + 1 < P.ws && j >= P.in_off[s + 1]) ++s;
+    P.ret[s][(size_t)P.peer_ret_base[s] + (j - P.in_off[s])] = ret_local[j];
+  }
+  jb_p2p_signal(P.flag_ret, P, done, sp->epoch);
+}
+
 // Returned bytes (variant+1 per outbound slot) -> list of residents to infect.
 __global__ void k_halo_return(const uint8_t* __restrict__ ret, const uint32_t* __restrict__ out_person, uint32_t n_out,
                               uint32_t* __restrict__ member, uint8_t* __restrict__ variant, uint32_t cap,

@@ -366,6 +366,13 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (double* q : w->vacc_tables) cudaFree(q);
+  for (void* q : w->p2p_opened) cudaIpcCloseMemHandle(q);
+  if (w->p2p_window) cudaFree(w->p2p_window);
+  if (w->flush_buf) cudaFree(w->flush_buf);
+  for (cudaEvent_t e : w->ring0) cudaEventDestroy(e);
+  for (cudaEvent_t e : w->ring1) cudaEventDestroy(e);
+  if (w->p2p_done) cudaFree(w->p2p_done);
+  if (w->p2p_ret_local) cudaFree(w->p2p_ret_local);
   for (SgTiles& t : w->tiles) {
     if (t.tile_group0) cudaFree(t.tile_group0);
     if (t.tp_member) cudaFree(t.tp_member);
@@ -507,6 +514,75 @@ extern "C" int jb_inject_leisure(JbWorld* w, const int32_t* group_per_person) {
 
 template <typename T>
 static int fetch_permuted(JbWorld* w, const T* dev, T* out);
+
+// ---- peer-memory halo exchange ---------------------------------------------------------------------
+// Window layout: [recv: H records][ret: n_out bytes, 256-aligned][flag_people: JB_MAX_RANKS u32][flag_ret: JB_MAX_RANKS u32]
+static size_t p2p_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int jb_p2p_window(JbWorld* w, void* handle_out) {
+  if (!w || !handle_out) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  if (!w->p2p_window) {
+    w->p2p_recv_bytes = p2p_align((size_t)std::max(1u, w->H) * (8 + (size_t)8 * w->V));
+    w->p2p_ret_bytes = p2p_align(std::max(1u, w->n_out));
+    const size_t bytes = w->p2p_recv_bytes + w->p2p_ret_bytes + 2 * JB_MAX_RANKS * 4;
+    CK(cudaMalloc((void**)&w->p2p_window, bytes));
+    CK(cudaMemset(w->p2p_window, 0, bytes));
+    TRY(dev_alloc(&w->p2p_done, 2));
+    CK(cudaMemset(w->p2p_done, 0, 8));
+    TRY(dev_alloc(&w->p2p_ret_local, std::max(1u, w->H)));
+    CK(cudaMemset(w->p2p_ret_local, 0, std::max(1u, w->H)));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, w->p2p_window));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  // followed by the two section sizes of this rank's window (the peers need them to find the flags)
+  const uint64_t sizes[2] = {w->p2p_recv_bytes, w->p2p_ret_bytes};
+  memcpy((unsigned char*)handle_out + 64, sizes, 16);
+  return JB_OK;
+}
+
+extern "C" int jb_p2p_connect(JbWorld* w, int rank, int ws, const void* handles, const uint32_t* out_counts,
+                              const uint32_t* in_counts, const uint32_t* peer_recv_base, const uint32_t* peer_ret_base) {
+  if (!w || !handles || !out_counts || !in_counts || !peer_recv_base || !peer_ret_base) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(ws >= 1 && ws <= JB_MAX_RANKS && rank >= 0 && rank < ws, "bad rank / world size");
+  REQUIRE(w->p2p_window != nullptr, "jb_p2p_connect before jb_p2p_window");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);
+  P2PDev& P = w->p2p;
+  memset(&P, 0, sizeof(P));
+  P.rank = rank; P.ws = ws;
+  uint32_t so = 0, si = 0;
+  for (int q = 0; q < ws; ++q) {
+    P.out_off[q] = so; P.in_off[q] = si;
+    so += out_counts[q]; si += in_counts[q];
+    P.peer_recv_base[q] = peer_recv_base[q]; P.peer_ret_base[q] = peer_ret_base[q];
+  }
+  for (int q = ws; q <= JB_MAX_RANKS; ++q) { P.out_off[q] = so; P.in_off[q] = si; }
+  REQUIRE(so == w->n_out && si == w->H, "out_counts / in_counts do not match the halo of this world");
+  for (int q = 0; q < ws; ++q) {
+    unsigned char* base = w->p2p_window;
+    if (q != rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const unsigned char*)handles + (size_t)q * 64, 64);
+      void* ptr = nullptr;
+      CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      w->p2p_opened.push_back(ptr);
+      base = (unsigned char*)ptr;
+    }
+    // every rank lays its window out with ITS OWN sizes: they travel in the first words of the handle blob
+    const uint64_t* sizes = reinterpret_cast<const uint64_t*>((const unsigned char*)handles + (size_t)ws * 64 + (size_t)q * 16);
+    P.recv[q] = base;
+    P.ret[q] = base + sizes[0];
+    P.flag_people[q] = reinterpret_cast<uint32_t*>(base + sizes[0] + sizes[1]);
+    P.flag_ret[q] = P.flag_people[q] + JB_MAX_RANKS;
+  }
+  w->p2p_on = true;
+  return JB_OK;
+}
 
 // ---- vaccination -------------------------------------------------------------------------------
 extern "C" int jb_set_vaccination(JbWorld* w, const JbVaccine* vac, uint32_t nv, const JbVaccinationCampaign* cam, uint32_t nc) {
@@ -940,8 +1016,24 @@ static int launch_groups(JbWorld* w, int mode) {
   return JB_OK;
 }
 
+#define JB_EVENT_RING 512
+static int ring_fold_oldest(JbWorld* w) {
+  const size_t i = (size_t)(w->ring_tail % JB_EVENT_RING);
+  CK(cudaEventSynchronize(w->ring1[i]));
+  float b = 0;
+  CK(cudaEventElapsedTime(&b, w->ring0[i], w->ring1[i]));
+  w->acc_step_ms += b; w->acc_steps++;
+  w->ring_tail++;
+  return JB_OK;
+}
+// Start / stop of a step's event bracket.  Level 1: ring (no host wait unless it wraps); level 2: the
+// single detailed pair, folded before the next step.
+static int timing_begin(JbWorld* w, cudaStream_t s);
+static int timing_end(JbWorld* w, cudaStream_t s);
+
 // Fold finished event pairs into the accumulators (called with the stream idle or synchronised).
 static int harvest_timing(JbWorld* w) {
+  while (w->ring_tail < w->ring_head) TRY(ring_fold_oldest(w));
   if (!w->ev_pending) return JB_OK;
   CK(cudaEventSynchronize(w->ev_step1));
   float a = 0, b = 0;
@@ -956,6 +1048,31 @@ static int harvest_timing(JbWorld* w) {
       w->sg_pending[k] = false;
     }
   w->ev_pending = false;
+  return JB_OK;
+}
+
+static int timing_begin(JbWorld* w, cudaStream_t s) {
+  if (w->timing == 1) {
+    if (w->ring0.empty()) {
+      w->ring0.resize(JB_EVENT_RING); w->ring1.resize(JB_EVENT_RING);
+      for (int i = 0; i < JB_EVENT_RING; ++i) { CK(cudaEventCreate(&w->ring0[i])); CK(cudaEventCreate(&w->ring1[i])); }
+    }
+    if (w->ring_head - w->ring_tail == JB_EVENT_RING) TRY(ring_fold_oldest(w));
+    CK(cudaEventRecord(w->ring0[w->ring_head % JB_EVENT_RING], s));
+  } else if (w->timing) {
+    TRY(harvest_timing(w));
+    CK(cudaEventRecord(w->ev_step0, s));
+  }
+  return JB_OK;
+}
+static int timing_end(JbWorld* w, cudaStream_t s) {
+  if (w->timing == 1) {
+    CK(cudaEventRecord(w->ring1[w->ring_head % JB_EVENT_RING], s));
+    w->ring_head++;
+  } else if (w->timing) {
+    CK(cudaEventRecord(w->ev_step1, s));
+    w->ev_pending = true; w->ev_detail = w->timing >= 2;
+  }
   return JB_OK;
 }
 
@@ -994,7 +1111,12 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     KCHECK("k_place", s);
     w->launches++;
   }
-  if (w->n_out && d_send) {
+  if (w->p2p_on) {
+    k_halo_push<<<std::max(1u, (w->n_out + 255) / 256), 256, 0, s>>>(w->p2p, w->out_person, w->n_out, w->phot, w->susc, w->trans,
+                                                                    w->NP, (int)w->V, step_dev(w), w->p2p_done);
+    KCHECK("k_halo_push", s);
+    w->launches++;
+  } else if (w->n_out && d_send) {
     k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->phot, w->susc, w->trans,
                                                        w->NP, (int)w->V, (unsigned char*)d_send);
     KCHECK("k_halo_pack", s);
@@ -1005,10 +1127,11 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
 
 // The infections created in a step get their first health update from k_newinf itself, so
 // k_health only walks the slots that existed at step start.  Single-domain steps run both as one
-// launch (k_finish).  (With halos the step is three separately captured phases; when the host
-// creates the infections, JB_STEP_NO_NEW_INFECTIONS, k_health walks every slot.)
+// launch (k_finish); residents infected abroad arrive later in the step and get their first update
+// from k_newinf as well.  (With host-issued collectives the step is three separately captured
+// phases; when the host creates the infections, JB_STEP_NO_NEW_INFECTIONS, k_health walks every slot.)
 static inline bool fused_finish(const JbWorld* w) {
-  return !(w->H || w->n_out) && !(w->cur.flags & JB_STEP_NO_NEW_INFECTIONS);
+  return (!(w->H || w->n_out) || w->p2p_on) && !(w->cur.flags & JB_STEP_NO_NEW_INFECTIONS);
 }
 
 static HealthArgs make_health_args(JbWorld* w, int old_only) {
@@ -1038,6 +1161,13 @@ static int launch_health(JbWorld* w, cudaStream_t s) {
 static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
+  if (w->p2p_on) {
+    d_recv = w->p2p.recv[w->p2p.rank];
+    d_ret_send = w->p2p_ret_local;
+    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_people[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters);
+    KCHECK("k_halo_wait", s);
+    w->launches++;
+  }
   if (w->H && d_recv) {
     k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
                                                      w->phot, w->susc, w->trans, (uint8_t*)d_ret_send);
@@ -1071,12 +1201,23 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     }
     w->launches++;
   }
+  if (w->p2p_on) {
+    k_halo_ret_push<<<std::max(1u, (w->H + 255) / 256), 256, 0, s>>>(w->p2p, w->p2p_ret_local, w->H, step_dev(w), w->p2p_done + 1);
+    KCHECK("k_halo_ret_push", s);
+    w->launches++;
+  }
   return JB_OK;
 }
 
 static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
+  if (w->p2p_on) {
+    d_ret_recv = w->p2p.ret[w->p2p.rank];
+    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_ret[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters);
+    KCHECK("k_halo_wait(ret)", s);
+    w->launches++;
+  }
   if (w->n_out && d_ret_recv) {
     // residents infected abroad: reuse the new-infection list
     // (tell_domains_to_infect, epidemiology.py:359-401)
@@ -1152,10 +1293,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   CK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
   w->cur = *p;
-  if (w->timing) {
-    TRY(harvest_timing(w));
-    CK(cudaEventRecord(w->ev_step0, s));
-  }
+  TRY(timing_begin(w, s));
   if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
   TRY(ensure_event_buffers(w, p->flags));
   // per-step parameter block: pinned ring slot -> device (the h2d payload of every step)
@@ -1163,7 +1301,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));  // the copy that last used this slot has finished
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
-  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
   CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(w->ev_step_buf[slot], s));
@@ -1185,7 +1323,7 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
   CK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
   TRY(run_phase(w, 2, d_ret_recv, nullptr, [&]() { return enqueue_finish(w, d_ret_recv); }));
-  if (w->timing) { CK(cudaEventRecord(w->ev_step1, s)); w->ev_pending = true; w->ev_detail = w->timing >= 2; }
+  TRY(timing_end(w, s));
   w->in_step = false;
   if (out) {
     CK(cudaStreamSynchronize(s));
@@ -1217,7 +1355,7 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
 
 // Single-GPU step: the three phases are captured as ONE graph.
 extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
-  if (w && (w->H || w->n_out)) {  // halo worlds need the exchange between the phases
+  if (w && (w->H || w->n_out) && !w->p2p_on) {  // host-issued collectives run between the phases
     TRY(jb_step_begin(w, p, nullptr));
     TRY(jb_step_interact(w, nullptr, nullptr));
     return jb_step_finish(w, nullptr, out);
@@ -1230,17 +1368,14 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
   CK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
   w->cur = *p;
-  if (w->timing) {
-    TRY(harvest_timing(w));
-    CK(cudaEventRecord(w->ev_step0, s));
-  }
+  TRY(timing_begin(w, s));
   if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
   TRY(ensure_event_buffers(w, p->flags));
   const int slot = (int)(w->step_seq++ & 3);
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
-  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
   CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(w->ev_step_buf[slot], s));
@@ -1250,7 +1385,7 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
     return enqueue_finish(w, nullptr);
   }));
   w->in_step = true;  // jb_step_finish_tail expects it
-  if (w->timing) { CK(cudaEventRecord(w->ev_step1, s)); w->ev_pending = true; w->ev_detail = w->timing >= 2; }
+  TRY(timing_end(w, s));
   w->in_step = false;
   if (!out) return JB_OK;
   CK(cudaStreamSynchronize(s));
@@ -1278,6 +1413,21 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
       return JB_ECAP;
     }
   }
+  return JB_OK;
+}
+
+// Evict the L2 between timed steps: a memset larger than the cache on the library's stream, in
+// front of (= outside) the next step's event bracket, without a host synchronisation.
+extern "C" int jb_flush_l2(JbWorld* w, size_t bytes) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  if (bytes > w->flush_bytes) {
+    CK(cudaStreamSynchronize(w->stream));
+    if (w->flush_buf) cudaFree(w->flush_buf);
+    CK(cudaMalloc((void**)&w->flush_buf, bytes));
+    w->flush_bytes = bytes;
+  }
+  CK(cudaMemsetAsync(w->flush_buf, 0, bytes, w->stream));
   return JB_OK;
 }
 

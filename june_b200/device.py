@@ -379,6 +379,10 @@ class Engine:
         self._check(self._f("fetch_summary")(self._h, ptr(out)))
         return out
 
+    def flush_l2(self, n_bytes: int = 256 << 20):
+        """Evict the L2 on the library's stream, in front of the next step's event bracket."""
+        self._check(self._f("flush_l2")(self._h, int(n_bytes)))
+
     def set_concurrency(self, on: bool = True):
         self._check(self._f("set_concurrency")(self._h, 1 if on else 0))
 

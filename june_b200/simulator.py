@@ -9,6 +9,7 @@ struct.  Nothing here loops over people or groups.
 from __future__ import annotations
 
 import datetime
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -186,6 +187,9 @@ class Simulator:
             self.halo = HaloExchange(world, self.device.halo_record_size(),
                                      device=torch.device("cuda", self.device.device_index) if on_gpu else None)
         self._ext_stream = None
+        self.p2p = False
+        if self.halo is not None and isinstance(self.device, DeviceWorld) and os.environ.get("JB_HALO", "p2p") != "nccl":
+            self._connect_peer_windows()
         if self.halo is not None and isinstance(self.device, DeviceWorld):
             import torch
             ptr = self.device._f("stream_handle")(self.device.handle)
@@ -200,6 +204,31 @@ class Simulator:
         self.region_history: List[tuple] = []
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
+
+    def _connect_peer_windows(self) -> None:
+        """Halo exchange over peer memory (``jb_p2p_window`` / ``jb_p2p_connect``): the ranks swap the
+        IPC handles of their exchange windows once; afterwards ``jb_step`` runs the whole halo step as
+        one graph whose pack kernels store into the peers' HBM over NVLink -- no host-issued collective.
+        ``JB_HALO=nccl`` keeps the ``all_to_all_single`` path."""
+        import ctypes as C
+        dist = self.halo.dist
+        ws, rank = dist.get_world_size(), dist.get_rank()
+        dev = self.device
+        blob = (C.c_ubyte * 80)()
+        dev._check(dev._f("p2p_window")(dev.handle, blob))
+        out_counts, in_counts = np.array(self.halo.out_counts, np.uint32), np.array(self.halo.in_counts, np.uint32)
+        mine = dict(blob=bytes(blob), in_off=np.concatenate([[0], np.cumsum(in_counts)[:-1]]).tolist(),
+                    out_off=np.concatenate([[0], np.cumsum(out_counts)[:-1]]).tolist())
+        everyone: List[object] = [None] * ws
+        dist.all_gather_object(everyone, mine)
+        handles = b"".join(e["blob"][:64] for e in everyone) + b"".join(e["blob"][64:80] for e in everyone)
+        hbuf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        recv_base = np.array([everyone[q]["in_off"][rank] for q in range(ws)], np.uint32)
+        ret_base = np.array([everyone[q]["out_off"][rank] for q in range(ws)], np.uint32)
+        dev._check(dev._f("p2p_connect")(dev.handle, rank, ws, hbuf, out_counts.ctypes.data, in_counts.ctypes.data,
+                                         recv_base.ctypes.data, ret_base.ctypes.data))
+        dist.barrier()
+        self.p2p = True
 
     @classmethod
     def from_file(cls, world: WorldSoA, interaction: Interaction, policies: Optional[Policies] = None,
@@ -297,7 +326,7 @@ class Simulator:
             return  # simulator.py:377-379
         params = self.step_params(_lib.STEP_RECORD_EVENTS if self.record is not None else 0)
         dev = self.device
-        if self.halo is None:
+        if self.halo is None or self.p2p:
             stats = dev.step(params, want_stats=want_stats)
         elif self._ext_stream is not None:
             # GPU ranks: the NCCL all-to-alls are issued with the library's stream current, so
