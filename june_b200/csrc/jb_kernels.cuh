@@ -851,9 +851,13 @@ __global__ void __launch_bounds__(256) k_halo_push(const __grid_constant__ P2PDe
 }
 
 // One thread per peer spins (bounded) until that peer's flag for this step has arrived.
-__global__ void k_halo_wait(const uint32_t* flags_self, int ws, int rank, const StepDev* sp, uint32_t* counters) {
+// `dead` is sticky: after one timeout (a peer is gone or out of step) later waits return at once,
+// every step reports JB_ECAP, and a queued run drains instead of waiting again and again.
+__global__ void k_halo_wait(const uint32_t* flags_self, int ws, int rank, const StepDev* sp, uint32_t* counters,
+                            uint32_t* dead) {
   const int q = threadIdx.x;
   if (q >= ws || q == rank) return;
+  if (*(volatile uint32_t*)dead) { atomicAdd(&counters[CNT_OVERFLOW], 1u); return; }
   const uint32_t epoch = sp->epoch;
   unsigned long long t0, t1;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -862,7 +866,7 @@ __global__ void k_halo_wait(const uint32_t* flags_self, int ws, int rank, const 
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags_self + q) : "memory");
     if ((int32_t)(v - epoch) >= 0) break;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 20000000000ull) { atomicAdd(&counters[CNT_OVERFLOW], 1u); break; }  // 20 s: a peer is gone
+    if (t1 - t0 > 10000000000ull) { *dead = 1u; atomicAdd(&counters[CNT_OVERFLOW], 1u); break; }  // 10 s
     __nanosleep(200);
   }
 }

@@ -529,8 +529,8 @@ extern "C" int jb_p2p_window(JbWorld* w, void* handle_out) {
     const size_t bytes = w->p2p_recv_bytes + w->p2p_ret_bytes + 2 * JB_MAX_RANKS * 4;
     CK(cudaMalloc((void**)&w->p2p_window, bytes));
     CK(cudaMemset(w->p2p_window, 0, bytes));
-    TRY(dev_alloc(&w->p2p_done, 2));
-    CK(cudaMemset(w->p2p_done, 0, 8));
+    TRY(dev_alloc(&w->p2p_done, 4));  // [0], [1] last-block tickets of the two push kernels, [2] sticky "peer lost"
+    CK(cudaMemset(w->p2p_done, 0, 16));
     TRY(dev_alloc(&w->p2p_ret_local, std::max(1u, w->H)));
     CK(cudaMemset(w->p2p_ret_local, 0, std::max(1u, w->H)));
   }
@@ -1164,7 +1164,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   if (w->p2p_on) {
     d_recv = w->p2p.recv[w->p2p.rank];
     d_ret_send = w->p2p_ret_local;
-    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_people[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters);
+    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_people[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters, w->p2p_done + 2);
     KCHECK("k_halo_wait", s);
     w->launches++;
   }
@@ -1214,7 +1214,7 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
   const JbStepParams& p = w->cur;
   if (w->p2p_on) {
     d_ret_recv = w->p2p.ret[w->p2p.rank];
-    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_ret[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters);
+    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_ret[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters, w->p2p_done + 2);
     KCHECK("k_halo_wait(ret)", s);
     w->launches++;
   }
