@@ -208,7 +208,6 @@ def run_gpu(args):
     t_wall1 = time.perf_counter()
     n_alive_last = n_people - sim.last_stats["n_dead_total"]
     person_steps = n_alive_last * args.steps
-    clocks = sampler.stop()
     tim = dev.timing_read()
     step_ms = tim["step_ms"] / max(1, tim["n_steps"])
     launches = int(tim["n_launches"])
@@ -244,6 +243,16 @@ def run_gpu(args):
         e2e_person_steps += n_people - sim.last_stats["n_dead_total"]
         next(sim.timer)
     barrier()
+
+    clocks = sampler.stop()  # sampled across the three timed legs (a 20 ms leg alone yields < 1 sample at 100 ms)
+    if not clocks.get("samples"):
+        try:
+            q = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=clocks.sm,clocks.max.sm",
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout.split(",")
+            clocks = {"sm_mhz": float(q[0]), "sm_max_mhz": float(q[1]), "reasons": [], "samples": 1,
+                      "note": "single sample right after the timed legs"}
+        except Exception:
+            pass
 
     # ---- reduce over ranks -----------------------------------------------------------------------
     vals = torch.tensor([step_ms * args.steps, e2e_steps_s * 1e3, float(person_steps), float(e2e_person_steps)],
