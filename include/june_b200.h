@@ -381,6 +381,9 @@ int jb_fetch_vaccination(JbWorld* w, int8_t* dose, int8_t* vaccine, double* effe
 #define JB_POL_CLOSE_COMPANIES 6   /* CloseCompanies (:604-770): flags bit0 full_closure, p0
                                     * avoid_work_probability, p1 furlough_probability, p2
                                     * key_probability, p3..p5 furlough / key / random ratios    */
+#define JB_POL_LIMIT_LONG_COMMUTE 7 /* LimitLongCommute (:773-824): p0 going_to_work_probability; applies
+                                    * to persons flagged JB_PA_LONG_COMMUTER.  As in the reference,
+                                    * the activity is skipped when random() < p0.               */
 typedef struct {
   int32_t type;
   uint32_t flags;
@@ -394,10 +397,11 @@ int jb_set_individual_policies(JbWorld* w, const JbIndividualPolicy* policies, u
 /* Static per-person facts the policies read: bits 0-1 lockdown_status (0 none, 1 key_worker,
  * 2 random, 3 furlough; person.py), bits 2-4 spec of the primary-activity group (0 none, 1 school,
  * 2 company, 3 university, 4 other), bit 5 = at least two key workers among the household's
- * residents (CloseSchools._check_kid_goes_to_school, :497-510). */
+ * residents (CloseSchools._check_kid_goes_to_school, :497-510), bit 6 = long-distance commuter. */
 #define JB_PA_LOCKDOWN(x) ((x) & 3u)
 #define JB_PA_KIND(x) (((x) >> 2) & 7u)
 #define JB_PA_TWO_KEY_WORKERS 0x20u
+#define JB_PA_LONG_COMMUTER 0x40u  /* person.id in LimitLongCommute.long_distance_commuter_ids (:795-813) */
 int jb_set_person_attributes(JbWorld* w, const uint8_t* attr);
 /* Test mode (JB_STEP_INJECT_POLICY): the uniforms the policies consume, [JB_MAX_POLICIES]
  * [JB_POLICY_DRAWS][n_people]; replaces Python's random() in individual_policies.py. */

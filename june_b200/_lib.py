@@ -27,6 +27,7 @@ STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE, STEP_INJECT_POL
 STEP_RECORD_EVENTS, STEP_INJECT_COMMUTE = 0x80, 0x100
 MAX_POLICIES, POLICY_DRAWS = 8, 3
 POL_SEVERE_STAY_HOME, POL_QUARANTINE, POL_SHIELDING, POL_CLOSE_SCHOOLS, POL_CLOSE_UNIVERSITIES, POL_CLOSE_COMPANIES = 1, 2, 3, 4, 5, 6
+POL_LIMIT_LONG_COMMUTE = 7
 
 
 class SimulatorError(BaseException):

@@ -66,8 +66,15 @@ WARP_MODE_SPECS = ("school", "hospital", "university")
 LEISURE_BIN_CAP = 2048  # visitors per social venue and step
 
 
+def _haversine(origin, destination) -> float:
+    """Great-circle distance in km between (lat, lon) pairs in degrees (``june/utils/distances.py``)."""
+    lat1, lon1, lat2, lon2 = map(np.radians, (origin[0], origin[1], destination[0], destination[1]))
+    a = np.sin((lat2 - lat1) / 2) ** 2 + np.cos(lat1) * np.cos(lat2) * np.sin((lon2 - lon1) / 2) ** 2
+    return float(6371 * 2 * np.arcsin(np.sqrt(a)))
+
+
 def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sector_betas: Dict[str, float],
-                  warp_mode_specs=WARP_MODE_SPECS, leisure=None, travel=None) -> WorldSoA:
+                  warp_mode_specs=WARP_MODE_SPECS, leisure=None, travel=None, long_commute_distance=None) -> WorldSoA:
     """``leisure``: the reference's ``Leisure`` object (or None).  Its social-venue distributors
     (``leisure.leisure_distributors``, in order) become the leisure activities of the device world;
     ``area.social_venues[spec]`` (``social_venue_distributor.py:258``) the per-area candidates."""
@@ -228,7 +235,15 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
         res = getattr(p.subgroups, "residence", None) if p.subgroups is not None else None
         if res is not None and hasattr(res.group, "residents"):
             kw2[i] = sum(1 for m in res.group.residents if getattr(m, "lockdown_status", None) == "key_worker") > 1
-    w.person_attr = make_person_attr(lock, kind, kw2)
+    # LimitLongCommute._does_long_commute (individual_policies.py:803-813): haversine distance between
+    # the home area and the work super area above the class-level threshold
+    long_c = np.zeros(n, bool)
+    if long_commute_distance is not None:
+        for i, p in enumerate(people):
+            wsa = getattr(p, "work_super_area", None)
+            if wsa is not None and getattr(p, "area", None) is not None:
+                long_c[i] = _haversine(p.area.coordinates, wsa.coordinates) > long_commute_distance
+    w.person_attr = make_person_attr(lock, kind, kw2, long_c)
     if travel is not None and getattr(world, "cities", None) is not None:
         # Travel.get_commute_subgroup (travel.py:125-131): work city, public transport, internal commuter
         # of the city or commuter of the home super area's inter-city station (city.py:83-102)

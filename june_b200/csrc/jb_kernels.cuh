@@ -143,6 +143,10 @@ __device__ __noinline__ uint32_t jb_apply_policies(const PlaceArgs& a, uint32_t 
         if (kind == 2u && jb_close_companies_skips(a, p, k, q, (int)JB_PA_LOCKDOWN(attr)))
           allowed &= ~((1u << JB_ACT_PRIMARY) | (1u << JB_ACT_COMMUTE));
         break;
+      case JB_POL_LIMIT_LONG_COMMUTE:  // :815-824: skips when random() < going_to_work_probability
+        if ((attr & JB_PA_LONG_COMMUTER) && jb_policy_uniform(a, p, k, 0) < q.p[0])
+          allowed &= ~((1u << JB_ACT_PRIMARY) | (1u << JB_ACT_COMMUTE));
+        break;
       default: break;
     }
   }
@@ -295,6 +299,18 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
     return act | (st & JB_PS_INFECTED) | ((st & JB_PST_CODE_MASK) << 4) | (a.pvar ? (uint32_t)a.pvar[p] << 6 : 0u);
   };
   uint32_t iters = 0;
+  if (FULL) {
+    // one person per thread: policies, commute and leisure walk per-person tables and draw Philox
+    // numbers -- a dependent chain per person that 16 persons per thread would serialise
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < a.N; p += gridDim.x * blockDim.x) {
+      a.phot[p] = (uint8_t)one(p, a.pstate[p], a.phas[p]);
+      if (++iters == 240) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&s_cnt[k], (uint32_t)((cnt >> (8 * k)) & 0xFFull));
+        cnt = 0ull; iters = 0;
+      }
+    }
+  } else
   for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
     const uint32_t p0 = c * 16;
     if (p0 + 16 <= a.N) {

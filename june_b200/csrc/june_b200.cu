@@ -1106,7 +1106,7 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     const uint32_t chunks = (w->N + 15) / 16;
     const bool full = w->n_pol != 0 || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
                       pa.cmt.person != nullptr || pa.cmt.inject != nullptr;
-    if (full) k_place<true><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
+    if (full) k_place<true><<<(w->N + 255) / 256, 256, 0, s>>>(pa);
     else k_place<false><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     KCHECK("k_place", s);
     w->launches++;

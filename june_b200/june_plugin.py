@@ -65,7 +65,10 @@ def make_b200_simulator_class(reference_simulator_cls):
                 ig = g.get_interactive_group(None)
                 sector_betas = dict(type(ig).sector_betas)
                 break
-            self._soa = compile_world(self.world, a2sg, sector_betas, leisure=am.leisure, travel=am.travel)
+            llc = [p for p in (am.policies.individual_policies.policies if am.policies is not None else [])
+                   if type(p).__name__ == "LimitLongCommute"]
+            self._soa = compile_world(self.world, a2sg, sector_betas, leisure=am.leisure, travel=am.travel,
+                                      long_commute_distance=type(llc[0]).apply_from_distance if llc else None)
             self._leisure_cache = {}
             self._leisure_stack = []
             self._policy_key = None
@@ -215,6 +218,8 @@ def make_b200_simulator_class(reference_simulator_cls):
                     recs.append(dict(type=_lib.POL_CLOSE_COMPANIES, flags=1 if p.full_closure else 0,
                                      p=[opt(p.avoid_work_probability), opt(p.furlough_probability), opt(p.key_probability),
                                         opt(type(p).furlough_ratio), opt(type(p).key_ratio), opt(type(p).random_ratio)]))
+                elif name == "LimitLongCommute":
+                    recs.append(dict(type=_lib.POL_LIMIT_LONG_COMMUTE, p=[p.going_to_work_probability]))
                 elif name != "SevereSymptomsStayHome":
                     raise NotImplementedError(f"individual policy {name} has no device implementation (INTEGRATION.md section 4)")
             if recs or self._policy_key is not None:

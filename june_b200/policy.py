@@ -198,9 +198,24 @@ class CloseCompanies(Policy):
                        self.furlough_ratio, self.key_ratio, self.random_ratio])
 
 
+class LimitLongCommute(Policy):
+    """``individual_policies.py:773-824``.  The set of long-distance commuters is a static person
+    attribute (``JB_PA_LONG_COMMUTER``, computed by the world compiler from the home-area / work-super-area
+    distance).  As in the reference, the activity is skipped when ``random() < going_to_work_probability``."""
+    policy_type = "individual"
+
+    def __init__(self, start_time: DateLike = "1000-01-01", end_time: DateLike = "9999-12-31", apply_from_distance: float = 150,
+                 going_to_work_probability: float = 0.2):
+        super().__init__(start_time, end_time)
+        self.apply_from_distance, self.going_to_work_probability = apply_from_distance, going_to_work_probability
+
+    def device_record(self, ctx) -> dict:
+        return dict(type=_lib.POL_LIMIT_LONG_COMMUTE, p=[self.going_to_work_probability])
+
+
 _CLASSES = {c.__name__: c for c in (SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
                                     SevereSymptomsStayHome, Hospitalisation, Quarantine, Shielding, CloseSchools,
-                                    CloseUniversities, CloseCompanies)}
+                                    CloseUniversities, CloseCompanies, LimitLongCommute)}
 
 
 def _camel(key: str) -> str:

@@ -42,12 +42,15 @@ KIND_MATRIX, KIND_SCHOOL = 0, 1
 # person_attr fields
 LOCKDOWN_CODES = {None: 0, "key_worker": 1, "random": 2, "furlough": 3}
 PRIMARY_KIND_CODES = {"school": 1, "company": 2, "university": 3}
-PA_TWO_KEY_WORKERS = 0x20
+PA_TWO_KEY_WORKERS, PA_LONG_COMMUTER = 0x20, 0x40
 
 
-def make_person_attr(lockdown, kind, two_key_workers):
-    return (np.asarray(lockdown, np.uint8) | (np.asarray(kind, np.uint8) << 2)
-            | np.where(np.asarray(two_key_workers, bool), PA_TWO_KEY_WORKERS, 0).astype(np.uint8)).astype(np.uint8)
+def make_person_attr(lockdown, kind, two_key_workers, long_commuter=None):
+    out = (np.asarray(lockdown, np.uint8) | (np.asarray(kind, np.uint8) << 2)
+           | np.where(np.asarray(two_key_workers, bool), PA_TWO_KEY_WORKERS, 0).astype(np.uint8))
+    if long_commuter is not None:
+        out = out | np.where(np.asarray(long_commuter, bool), PA_LONG_COMMUTER, 0).astype(np.uint8)
+    return out.astype(np.uint8)
 SCHOOL_DIM = 32
 MAX_STAGES = 8
 N_TPAR = 5

@@ -86,7 +86,7 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
     if with_commute:
         a2sg["commute"] = ["city_transports", "inter_city_transports"]
     soa = compile_world(world, a2sg, InteractiveCompany.sector_betas, leisure=sim.activity_manager.leisure,
-                        travel=sim.activity_manager.travel)
+                        travel=sim.activity_manager.travel, long_commute_distance=150 if lockdown else None)
     people = list(world.people)
     pidx = {p.id: i for i, p in enumerate(people)}
     gidx = {}

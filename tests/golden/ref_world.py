@@ -365,7 +365,12 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
                       weekday_activities=wd_act, weekend_activities=we_act)
     pol = [Hospitalisation(disease_config=dc), SevereSymptomsStayHome(start_time="1900-01-01", end_time="2100-01-01")] if with_policies else []
     if lockdown:
-        from june.policy import CloseCompanies, CloseSchools, Quarantine, Shielding
+        from june.policy import CloseCompanies, CloseSchools, LimitLongCommute, Quarantine, Shielding
+        for p in world.people:  # LimitLongCommute needs the work super area (set by the commute builder otherwise)
+            if p.primary_activity is not None and p.primary_activity.group.spec == "company" and p.work_super_area is None:
+                p.work_super_area = p.primary_activity.group.super_area
+        llc = LimitLongCommute(start_time="2020-03-07", end_time="2100-01-01", apply_from_distance=150, going_to_work_probability=0.4)
+        llc.initialize(world, None, None)
         pol += [
             Quarantine(start_time="2020-03-03", end_time="2100-01-01", n_days=7, n_days_household=14, compliance=0.8,
                        household_compliance=0.9),
@@ -374,6 +379,7 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
                          attending_compliance=0.7),
             CloseCompanies(start_time="2020-03-06", end_time="2100-01-01", avoid_work_probability=0.3,
                            furlough_probability=0.2, key_probability=0.2),
+            llc,
         ]
         CloseCompanies.initialize(world, None, None)
     policies = Policies(pol)

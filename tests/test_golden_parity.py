@@ -33,6 +33,7 @@ def policy_records(names, ratios):
         "Shielding": dict(type=_lib.POL_SHIELDING, p=[70, 0.6]),
         "CloseSchools": dict(type=_lib.POL_CLOSE_SCHOOLS, mask=sum(1 << y for y in (5, 6, 7, 12, 13, 17)), p=[0.7]),
         "CloseCompanies": dict(type=_lib.POL_CLOSE_COMPANIES, p=[0.3, 0.2, 0.2, f, k, r]),
+        "LimitLongCommute": dict(type=_lib.POL_LIMIT_LONG_COMMUTE, p=[0.4]),
     }
     return [(n, table[n]) for n in names if n in table]
 
