@@ -61,46 +61,52 @@ def measured_peak():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi DURING the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML polled every 5 ms from a
+    thread (the timed legs last tens of milliseconds, `nvidia-smi -lms 100` would see one sample);
+    falls back to one `nvidia-smi` query if NVML is unavailable."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.thread = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+        if self.sm:
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, bit in self.REASONS.items() if self.mask & bit), "samples": len(self.sm)}
         try:
-            self.proc.wait(timeout=2)
+            q = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": float(q[0]), "sm_max_mhz": float(q[1]), "reasons": [], "samples": 1,
+                    "note": "NVML unavailable: single nvidia-smi sample right after the timed legs"}
         except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = set()
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 def build_setup(n_people: int, rank: int, world_size: int, dist=None, leisure: bool = False):
@@ -194,12 +200,16 @@ def run_gpu(args):
     # step's event bracket, nothing waits on the host between steps (statistics are read once, with
     # the last step), so on N > 1 GPUs the ranks are kept in step by the halo exchange itself and not
     # by host jitter.  person-steps use the alive count at the END of the leg (a lower bound).
+    phase0 = []
+
     def rewind():
         """Every timed leg walks the SAME sequence of time slots (the cost of a step depends on its
-        activities: one weekday step in five has the primary activity)."""
-        sim.timer = Timer.from_config(cfg)
-        sim.activity_manager.timer = sim.timer
-        for _ in range(args.warmup):
+        activities: one weekday step in five has the primary activity): the clock is advanced, without
+        stepping the device, to the next slot with the weekday and shift the first leg started on."""
+        if not phase0:
+            phase0.append((sim.timer.date.weekday(), sim.timer.shift))
+            return
+        while (sim.timer.date.weekday(), sim.timer.shift) != phase0[0]:
             next(sim.timer)
 
     rewind()
@@ -255,15 +265,7 @@ def run_gpu(args):
         next(sim.timer)
     barrier()
 
-    clocks = sampler.stop()  # sampled across the three timed legs (a 20 ms leg alone yields < 1 sample at 100 ms)
-    if not clocks.get("samples"):
-        try:
-            q = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=clocks.sm,clocks.max.sm",
-                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout.split(",")
-            clocks = {"sm_mhz": float(q[0]), "sm_max_mhz": float(q[1]), "reasons": [], "samples": 1,
-                      "note": "single sample right after the timed legs"}
-        except Exception:
-            pass
+    clocks = sampler.stop()  # sampled across the three timed legs
 
     # ---- reduce over ranks -----------------------------------------------------------------------
     vals = torch.tensor([step_ms * args.steps, e2e_steps_s * 1e3, float(person_steps), float(e2e_person_steps)],
