@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
   double* row_l = T_w + (size_t)WPG * V * L;
   uint32_t* dyn_s = (uint32_t*)(row_l + (size_t)V * L);
 
-  const uint32_t b = a.grp_off[g], ns = a.grp_off[g + 1] - b;
+  // registered slots can only hold someone when their feeding activity takes place in this step
+  // (hospital workers on a residence-only step: the group is just its patients)
+  const bool any_static = (a.static_acts & a.sp->activity_mask) != 0u;
+  const uint32_t b = a.grp_off[g], ns = any_static ? a.grp_off[g + 1] - b : 0u;
   uint32_t nd = 0;
   if (a.dyn_cnt) {
     // stage this group's bin and sort it: members arrive in arbitrary (atomic) order, the
@@ -437,7 +440,9 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
   const uint8_t* s_info = reinterpret_cast<const uint8_t*>(s_info4);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_n = 0;
-  if (threadIdx.x < a.dim * a.dim) s_cm[threadIdx.x] = a.cm[threadIdx.x];
+  // contact matrix: requested now, parked in shared memory behind phase A (not a DRAM round trip
+  // in front of the block's first barrier)
+  const double cm_mine = threadIdx.x < a.dim * a.dim ? a.cm[threadIdx.x] : 0.0;
   __syncthreads();
 
   // ---- phase A ---------------------------------------------------------------------------
@@ -523,6 +528,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
     draws = __reduce_add_sync(JB_FULL, draws);
     if (lane == 0 && draws) atomicAdd(&a.counters[CNT_DRAWS], draws);
   }
+  if (threadIdx.x < a.dim * a.dim) s_cm[threadIdx.x] = cm_mine;
   __syncthreads();
   const uint32_t n_work = s_n;
   if (n_work == 0 || a.mode == 2) return;  // mode 2: detection only (profiling aid)

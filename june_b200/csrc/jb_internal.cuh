@@ -154,6 +154,7 @@ struct GroupArgs {
   const uint8_t* tp_info;
   uint32_t n_tiles, stream_base;
   int dim, kind, L;
+  uint32_t static_acts;       // activities that feed registered slots of this supergroup (bit per JB_ACT_*)
   uint32_t N, NP;
   int V, R;
   const StepDev* sp;         // dt, seed, step, n_inject
@@ -219,6 +220,7 @@ struct JbWorld {
   uint64_t id_base = 0;
   std::vector<JbSupergroup> sgs;
   std::vector<int> sg_L;          // max local subgroups per supergroup
+  std::vector<uint32_t> sg_static_acts;  // feeding activities of the supergroup's registered slots
   DiseaseDev dis_host;
   // static device arrays
   uint8_t *age = nullptr, *sex = nullptr, *ch = nullptr, *phas = nullptr, *school_years = nullptr;

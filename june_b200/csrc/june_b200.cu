@@ -157,6 +157,12 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     REQUIRE(sg.cm_offset >= 0 && (uint32_t)(sg.cm_offset + sg.dim * sg.dim) <= d->n_cm_doubles, "cm offset out of range");
     REQUIRE(sg.activity >= 0 && sg.activity < JB_N_ACT, "bad supergroup activity");
     w->sg_L.push_back(L);
+    {
+      uint32_t acts = 0;
+      for (uint32_t m = d->grp_offset[sg.first_group]; m < d->grp_offset[sg.first_group + sg.n_groups]; ++m)
+        acts |= 1u << JB_INFO_ACT(d->reg_info[m]);
+      w->sg_static_acts.push_back(acts);
+    }
     if (sg.has_dynamic) w->any_dynamic = true;
   }
   REQUIRE(expect == w->G, "supergroups do not cover all groups");
@@ -933,6 +939,7 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   a.g0 = sg.first_group; a.g1 = sg.first_group + sg.n_groups;
   a.group_list = nullptr; a.n_list = sg.n_groups; a.int2ext = w->int2ext; a.ext2int = w->ext2int;
   a.dim = sg.dim; a.kind = sg.kind; a.L = L;
+  a.static_acts = w->sg_static_acts[&sg - w->sgs.data()];
   a.N = w->N; a.NP = w->NP; a.V = (int)w->V; a.R = (int)w->R;
   a.sp = step_dev(w); a.gid_base = (uint32_t)w->id_base;
   a.counters = w->counters; a.newinf_member = w->newinf_member; a.newinf_var = w->newinf_var;
