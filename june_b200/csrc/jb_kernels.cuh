@@ -318,13 +318,46 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
       const uint4 hv = *reinterpret_cast<const uint4*>(a.phas + p0);
       uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
       const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+      if (!a.pvar) {
+        // Four persons per 32-bit word, no table: candidate activities = (fixed subgroups | medical)
+        // & the step's mask, restricted for severe stay-at-home cases, none for the dead; the chosen
+        // activity is the lowest set bit of each byte (hierarchy order == bit order).
+        const uint32_t M4 = (mask & 0x1Fu) * 0x01010101u;
+        const uint32_t keep_sev = ((1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE)) * 0x01010101u;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t o = 0;
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t st4 = sw[q];
+          const uint32_t med4 = (st4 >> 6) & 0x01010101u, dead4 = (st4 >> 4) & 0x01010101u, sev4 = (st4 >> 5) & 0x01010101u;
+          uint32_t cand4 = ((hw[q] & 0x1F1F1F1Fu) | med4) & M4;
+          if (flags & JB_STEP_SEVERE_STAY_HOME) cand4 &= ~((sev4 * 0xFFu) & ~keep_sev);
+          cand4 &= ~(dead4 * 0xFFu);
+          const uint32_t low4 = cand4 & ~((cand4 | 0x80808080u) - 0x01010101u);  // lowest set bit of every byte
+          const uint32_t none4 = (~(((low4 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | low4) >> 7) & 0x01010101u;  // 1 where no candidate
+          uint32_t act4 = (((low4 >> 1) | (low4 >> 3)) & 0x01010101u) | ((((low4 >> 2) | (low4 >> 3)) & 0x01010101u) << 1) |
+                          (((low4 >> 4) & 0x01010101u) << 2);
+          act4 |= none4 * 7u;  // JB_ACT_NONE
+          noact += __popc(none4 & ~dead4);
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          o |= one(p0 + q * 4 + b, (sw[q] >> (8 * b)) & 0xFFu, (hw[q] >> (8 * b)) & 0xFFu) << (8 * b);
-        sw[q] = o;
+          for (int k = 0; k < JB_N_ACT; ++k) cnt += (unsigned long long)__popc(low4 & (0x01010101u << k)) << (8 * k);
+          uint32_t medm = low4 & 0x01010101u;  // rare: patients go into their ward's bin
+          while (medm) {
+            const uint32_t b = (uint32_t)(__ffs(medm) - 1) >> 3;
+            medm &= medm - 1;
+            const uint32_t p = p0 + q * 4 + b;
+            const uint32_t med = (uint32_t)a.pmed[p];
+            jb_dyn_scatter(a, med >> 8, med & 0xFu, p);
+          }
+          sw[q] = act4 | (st4 & 0x08080808u) | ((st4 & 0x03030303u) << 4);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            o |= one(p0 + q * 4 + b, (sw[q] >> (8 * b)) & 0xFFu, (hw[q] >> (8 * b)) & 0xFFu) << (8 * b);
+          sw[q] = o;
+        }
       }
       *reinterpret_cast<uint4*>(a.phot + p0) = make_uint4(sw[0], sw[1], sw[2], sw[3]);
     } else {
