@@ -441,6 +441,19 @@ int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap, size_t* n)
  * (halo persons: n_people + halo index); sorted by infected person. */
 int jb_fetch_infection_events(JbWorld* w, uint32_t* infected, uint32_t* infector, uint32_t* group,
                               uint32_t* variant, size_t cap, size_t* n);
+/* Health events of the last step run with JB_STEP_RECORD_EVENTS: rows of the reference's `deaths`
+ * (epidemiology.py:176-186: location = hospital if the person had a medical facility, else the
+ * residence), `recoveries` (:209-214), `hospital_admissions` (status ward_admitted only),
+ * `icu_admissions` (status icu_transferred only) and `discharges` tables
+ * (medical_care_policies.py:463-515, hospital.py:62-122).  group = -1 where the table has no location.
+ * Sorted by (person, kind). */
+#define JB_HEV_DEATH 1
+#define JB_HEV_RECOVERY 2
+#define JB_HEV_HOSPITAL_ADMISSION 3
+#define JB_HEV_ICU_ADMISSION 4
+#define JB_HEV_DISCHARGE 5
+#define JB_HEV_SYMPTOMS 6 /* `symptoms` table (epidemiology.py:256-266): the tag changed; group = new tag */
+int jb_fetch_health_events(JbWorld* w, uint32_t* person, uint32_t* kind, int32_t* group, size_t cap, size_t* n);
 /* per-region summary: counts[n_regions][JB_N_SUMMARY] (records_writer.py:151-164) */
 #define JB_N_SUMMARY 8
 int jb_fetch_summary(JbWorld* w, uint32_t* counts);

@@ -23,6 +23,7 @@ enum {
   CNT_DEATHS_STEP,
   CNT_HALO_INF,
   CNT_OVERFLOW,        // a capacity was exceeded
+  CNT_HEV,             // health events appended this step (JB_STEP_RECORD_EVENTS)
   CNT_INFECTED,        // currently infected / in hospital / in icu (recomputed by k_health)
   CNT_HOSP,
   CNT_ICU,
@@ -254,7 +255,11 @@ struct JbWorld {
   uint8_t* newinf_var = nullptr;
   uint32_t *ev_infected = nullptr, *ev_infector = nullptr, *ev_group = nullptr;  // allocated on first use
   uint8_t* ev_var = nullptr;
-  uint32_t ev_count = 0;  // events of the last step that recorded them
+  uint32_t ev_count = 0;
+  uint32_t *hev_person = nullptr, *hev_kind = nullptr;   // health events (deaths, recoveries, admissions, discharges)
+  int32_t* hev_group = nullptr;
+  uint32_t hev_cap = 0;
+  int32_t* pres_group = nullptr;                         // residence group of every resident (death location)  // events of the last step that recorded them
   double* beta = nullptr;
   double* lambda = nullptr;
   double* inject = nullptr;

@@ -459,7 +459,16 @@ struct HealthArgs {
   uint32_t* summary;        // [R][JB_N_SUMMARY]
   int R;
   int old_only;             // 1: only the slots that existed at step start (k_newinf updates its own)
+  // health events (null unless JB_STEP_RECORD_EVENTS)
+  uint32_t* hev_person; uint32_t* hev_kind; int32_t* hev_group; uint32_t hev_cap;
+  const int32_t* pres_group;
 };
+
+__device__ __forceinline__ void jb_health_event(const HealthArgs& a, uint32_t p, uint32_t kind, int32_t group) {
+  const uint32_t i = atomicAdd(&a.counters[CNT_HEV], 1u);
+  if (i < a.hev_cap) { a.hev_person[i] = p; a.hev_kind[i] = kind; a.hev_group[i] = group; }
+  else atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+}
 
 struct HealthAcc {
   uint32_t inf, hosp, icu;  // currently infected / in hospital / in intensive care
@@ -508,7 +517,9 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
   bool changed = false;
   if (stage + 1 < nst && t > a.inf_next[s]) {
     ++stage;
+    const int tag_old = tag;
     tag = a.traj_tag[(size_t)stage * a.C + s];
+    if (a.hev_person && tag != tag_old) jb_health_event(a, (uint32_t)p, JB_HEV_SYMPTOMS, tag);
     a.inf_stage[s] = (uint8_t)stage;
     a.inf_tag[s] = (int8_t)tag;
     a.inf_next[s] = (stage + 1 < JB_MAX_STAGES) ? a.traj_time[(size_t)(stage + 1) * a.C + s] : 1e300;
@@ -524,7 +535,14 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
     if (bit & D.hosp_mask) {
       const int32_t hg = was_med ? (med_old >> 8) : a.inf_hosp[s];
       if (hg >= 0) med_new = (hg << 8) | ((bit & D.icu_mask) ? 2 : 1);
+      if (a.hev_person && hg >= 0) {
+        // "ward_admitted" -> hospital_admissions, "icu_transferred" -> icu_admissions; a direct ICU
+        // admission is not recorded by the reference (medical_care_policies.py:463-475)
+        if (!was_med && (med_new & 0xFF) == 1) jb_health_event(a, (uint32_t)p, JB_HEV_HOSPITAL_ADMISSION, hg);
+        else if (was_med && (med_old & 0xFF) == 1 && (med_new & 0xFF) == 2) jb_health_event(a, (uint32_t)p, JB_HEV_ICU_ADMISSION, hg);
+      }
     } else if (was_med && !(bit & D.dead_mask)) {
+      if (a.hev_person) jb_health_event(a, (uint32_t)p, JB_HEV_DISCHARGE, med_old >> 8);
       med_new = -1;
     }
   }
@@ -554,6 +572,9 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
     a.ptag[p] = (rec || dead) ? (int8_t)-1 : (int8_t)tag;
     a.pstate[p] = (uint8_t)st;
   }
+  if (a.hev_person && (rec || dead))
+    jb_health_event(a, (uint32_t)p, rec ? JB_HEV_RECOVERY : JB_HEV_DEATH,
+                    rec ? -1 : (med_new >= 0 ? (med_new >> 8) : a.pres_group[p]));
   if (rec) {
     atomicAdd(&a.counters[CNT_RECOVERED_STEP], 1u);
     atomicAdd(&sum[SUM_RECOVERED], 1u);
@@ -1086,6 +1107,15 @@ __global__ void k_refresh_codes(uint8_t* __restrict__ pstate, const double* __re
   const double s = susc[i];
   const uint32_t code = s == 0.0 ? JB_SC_ZERO : s == 1.0 ? JB_SC_ONE : JB_SC_READ;
   pstate[i] = (uint8_t)((pstate[i] & ~JB_PST_CODE_MASK) | code);
+}
+
+// Residence group of every resident (the location of a death outside hospital), one thread per group.
+__global__ void k_res_group(const uint32_t* __restrict__ grp_off, const uint32_t* __restrict__ reg_member,
+                            const uint16_t* __restrict__ reg_info, uint32_t G, uint32_t N, int32_t* __restrict__ pres_group) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  for (uint32_t m = grp_off[g]; m < grp_off[g + 1]; ++m)
+    if (JB_INFO_ACT(reg_info[m]) == JB_ACT_RESIDENCE && reg_member[m] < N) pres_group[reg_member[m]] = (int32_t)g;
 }
 
 __global__ void k_fill_f64(double* x, size_t n, double v) {

@@ -368,7 +368,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
                   w->cub_tmp, w->int2ext, w->ext2int, w->d_vacc, w->vac_dose, w->vac_type, w->traj_camp, w->traj_day0, w->traj_stage,
-                  w->prior_eff_inf, w->prior_eff_sym, w->effmult, w->vac_inject, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
+                  w->prior_eff_inf, w->prior_eff_sym, w->effmult, w->vac_inject, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->hev_person, w->hev_kind, w->hev_group, w->pres_group, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (double* q : w->vacc_tables) cudaFree(q);
@@ -1154,6 +1154,10 @@ static HealthArgs make_health_args(JbWorld* w, int old_only) {
   a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
   a.summary = w->summary; a.R = (int)w->R;
+  if ((w->cur.flags & JB_STEP_RECORD_EVENTS) && w->hev_person) {
+    a.hev_person = w->hev_person; a.hev_kind = w->hev_kind; a.hev_group = w->hev_group; a.hev_cap = w->hev_cap;
+    a.pres_group = w->pres_group;
+  }
   return a;
 }
 
@@ -1289,6 +1293,16 @@ static int ensure_event_buffers(JbWorld* w, uint32_t flags) {
   TRY(dev_alloc(&w->ev_infector, w->newinf_cap));
   TRY(dev_alloc(&w->ev_group, w->newinf_cap));
   TRY(dev_alloc(&w->ev_var, w->newinf_cap));
+  // health events: at most four per infected person and step (symptoms, admission/transfer, recovery or death)
+  w->hev_cap = (uint32_t)std::min<uint64_t>(4ull * w->N, 0x7FFFFFFFull);
+  TRY(dev_alloc(&w->hev_person, w->hev_cap));
+  TRY(dev_alloc(&w->hev_kind, w->hev_cap));
+  TRY(dev_alloc(&w->hev_group, w->hev_cap));
+  TRY(dev_alloc(&w->pres_group, w->NP));
+  CK(cudaMemsetAsync(w->pres_group, 0xFF, (size_t)w->NP * 4, w->stream));
+  k_res_group<<<(w->G + 255) / 256, 256, 0, w->stream>>>(w->grp_off, w->reg_member, w->reg_info, w->G, w->N, w->pres_group);
+  KCHECK("k_res_group", w->stream);
+  drop_graphs(w);
   return JB_OK;
 }
 
@@ -1504,6 +1518,34 @@ extern "C" int jb_fetch_infection_events(JbWorld* w, uint32_t* infected, uint32_
     if (infector) infector[i] = b[k];
     if (group) group[i] = g[k];
     if (variant) variant[i] = v[k];
+  }
+  return JB_OK;
+}
+
+extern "C" int jb_fetch_health_events(JbWorld* w, uint32_t* person, uint32_t* kind, int32_t* group, size_t cap, size_t* n) {
+  if (!w || !n) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  *n = 0;
+  if (!w->hev_person || !(w->cur.flags & JB_STEP_RECORD_EVENTS)) return JB_OK;
+  uint32_t cnt = 0;
+  CK(cudaMemcpy(&cnt, w->counters + CNT_HEV, 4, cudaMemcpyDeviceToHost));
+  cnt = std::min(cnt, w->hev_cap);
+  REQUIRE(cnt <= cap, "jb_fetch_health_events: caller buffers too small");
+  *n = cnt;
+  if (!cnt) return JB_OK;
+  std::vector<uint32_t> a(cnt), k(cnt), order(cnt);
+  std::vector<int32_t> g(cnt);
+  CK(cudaMemcpy(a.data(), w->hev_person, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(k.data(), w->hev_kind, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(g.data(), w->hev_group, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < cnt; ++i) { order[i] = i; a[i] = w->h_int2ext[a[i]]; }
+  std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return a[x] != a[y] ? a[x] < a[y] : k[x] < k[y]; });
+  for (uint32_t i = 0; i < cnt; ++i) {
+    const uint32_t j = order[i];
+    if (person) person[i] = a[j];
+    if (kind) kind[i] = k[j];
+    if (group) group[i] = g[j];
   }
   return JB_OK;
 }

@@ -342,6 +342,18 @@ class Engine:
         return dict(infected=a[0][: n.value].copy(), infector=a[1][: n.value].copy(), group=a[2][: n.value].copy(),
                     variant=a[3][: n.value].copy())
 
+    HEALTH_EVENT_KINDS = {1: "deaths", 2: "recoveries", 3: "hospital_admissions", 4: "icu_admissions", 5: "discharges", 6: "symptoms"}
+
+    def fetch_health_events(self) -> Dict[str, np.ndarray]:
+        """Rows of the reference's ``deaths`` / ``recoveries`` / ``hospital_admissions`` /
+        ``icu_admissions`` / ``discharges`` record tables for the last step that ran with
+        ``STEP_RECORD_EVENTS``: ``person``, ``kind`` (``HEALTH_EVENT_KINDS``), ``group`` (-1: no location)."""
+        cap = 4 * self.world.n_people
+        a = [np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.int32)]
+        n = C.c_size_t()
+        self._check(self._f("fetch_health_events")(self._h, ptr(a[0]), ptr(a[1]), ptr(a[2]), cap, C.byref(n)))
+        return dict(person=a[0][: n.value].copy(), kind=a[1][: n.value].copy(), group=a[2][: n.value].copy())
+
     def fetch_person_state(self) -> Dict[str, np.ndarray]:
         n = self.world.n_people
         out = dict(pstate=np.zeros(n, np.uint8), tag=np.zeros(n, np.int8), trans_prob=np.zeros(n, np.float64),

@@ -201,6 +201,7 @@ class Simulator:
         self._leisure_tables: dict = {}   # time-slot key -> table index on the device
         self._leisure_stack: List[tuple] = []
         self.infection_events: List[tuple] = []
+        self.health_events: List[tuple] = []
         self.region_history: List[tuple] = []
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
@@ -365,6 +366,9 @@ class Simulator:
                 ev = dev.fetch_infection_events()
                 if len(ev["infected"]):
                     self.infection_events.append((self.timer.date, ev))
+                hev = dev.fetch_health_events()
+                if len(hev["person"]):
+                    self.health_events.append((self.timer.date, hev))
 
     def run(self) -> None:
         """``Simulator.run`` (``simulator.py:628-707``)."""
@@ -407,6 +411,30 @@ class Simulator:
                                  infector_ids=int(pid[b]) if b != 0xFFFFFFFF else -1, infected_ids=int(pid[a]),
                                  infection_ids=int(v)))
         return rows
+
+    def health_event_rows(self) -> Dict[str, List[Dict[str, object]]]:
+        """Rows of the reference's ``deaths`` (``epidemiology.py:176-186``), ``recoveries`` (``:209-214``),
+        ``hospital_admissions`` / ``icu_admissions`` / ``discharges`` (``medical_care_policies.py:463-515``)
+        record tables, keyed by table name; columns follow ``records/event_records_writer.py``."""
+        w = self.world
+        grp_sg = w.group_supergroup()
+        pid = w.person_ids if w.person_ids is not None else np.arange(w.n_people, dtype=np.int64) + w.person_id_base
+        gid = w.group_ids if w.group_ids is not None else np.arange(w.n_groups, dtype=np.int64)
+        names = self.device.HEALTH_EVENT_KINDS
+        out: Dict[str, List[Dict[str, object]]] = {n: [] for n in names.values()}
+        for date, ev in self.health_events:
+            for p, k, g in zip(ev["person"], ev["kind"], ev["group"]):
+                table = names[int(k)]
+                if table == "recoveries":
+                    out[table].append(dict(time_stamp=date, recovered_person_ids=int(pid[p]), infection_ids=-1))
+                elif table == "symptoms":
+                    out[table].append(dict(time_stamp=date, infected_ids=int(pid[p]), new_symptoms=int(g), infection_ids=-1))
+                elif table == "deaths":
+                    out[table].append(dict(time_stamp=date, location_specs=w.supergroups[grp_sg[g]].spec if g >= 0 else "",
+                                           location_ids=int(gid[g]) if g >= 0 else -1, dead_person_ids=int(pid[p])))
+                else:
+                    out[table].append(dict(time_stamp=date, hospital_ids=int(gid[g]), patient_ids=int(pid[p])))
+        return out
 
     def write_summary_csv(self, path: str) -> None:
         import csv
