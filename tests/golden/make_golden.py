@@ -57,7 +57,7 @@ ROW_LEN = 5 + 5 + 2 * MAX_STAGES
 
 
 def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000,
-              with_leisure=False, lockdown=False, with_commute=False, vaccination=False):
+              with_leisure=False, lockdown=False, with_commute=False, vaccination=False, records=False):
     pyrandom.seed(seed)
     np.random.seed(seed)
     sink = io.StringIO()
@@ -167,6 +167,48 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
 
         vac_mod.VaccinationCampaigns.apply = apply
 
+    # ---- records: every Record.accumulate call of the step, through a duck-typed recorder ----------
+    rec_state = {"rows": [], "inf": []}
+    if records:
+        kinds = {"deaths": 1, "recoveries": 2, "hospital_admissions": 3, "icu_admissions": 4, "discharges": 5, "symptoms": 6}
+        gid_of = {}
+        for sg in soa.supergroups:
+            for g in getattr(world, sg.name).members:
+                gid_of[(g.spec, g.id)] = gidx[id(g)]
+
+        class Recorder:
+            record_static_data = False
+
+            def accumulate(self, table_name, **kw):
+                if table_name == "infections":
+                    if kw["location_spec"] == "infection_seed":
+                        return
+                    g = gid_of[(kw["location_spec"], kw["location_id"])]
+                    for a, b in zip(kw["infected_ids"], kw["infector_ids"]):
+                        rec_state["inf"].append((pidx[a], pidx[b], g))
+                elif table_name == "deaths":
+                    rec_state["rows"].append((pidx[kw["dead_person_id"]], 1, gid_of[(kw["location_spec"], kw["location_id"])]))
+                elif table_name == "recoveries":
+                    rec_state["rows"].append((pidx[kw["recovered_person_id"]], 2, -1))
+                elif table_name in ("hospital_admissions", "icu_admissions", "discharges"):
+                    rec_state["rows"].append((pidx[kw["patient_id"]], kinds[table_name], gid_of[("hospital", kw["hospital_id"])]))
+                elif table_name == "symptoms":
+                    rec_state["rows"].append((pidx[kw["infected_id"]], 6, int(kw["symptoms"])))
+
+            def summarise_time_step(self, timestamp, world):
+                pass
+
+            def time_step(self, timestamp):
+                pass
+
+            def parameters(self, **kw):
+                pass
+
+            def combine_outputs(self):
+                pass
+
+        sim.record = Recorder()
+
     steps = []
     orig_step = Simulator.do_timestep
     orig_am = type(sim.activity_manager).do_timestep
@@ -216,6 +258,7 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         state["draw_person"], state["draw_lambda"], state["draw_u"] = [], [], []
         pol_state["draws"] = []
         vac_state["u"] = {}
+        rec_state["rows"], rec_state["inf"] = [], []
         timer = self.timer
         vac_day = self.epidemiology.current_date is None or timer.date.date() != self.epidemiology.current_date.date()
         rec["now"], rec["dt"] = float(timer.now), float(timer.duration)
@@ -243,6 +286,9 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
             for k, v in vac_state["u"].items():
                 u[k] = v
             rec["vac_u"] = u
+        if records:
+            rec["health_events"] = np.array(sorted(rec_state["rows"]), np.int64).reshape(-1, 3)
+            rec["infection_events"] = np.array(sorted(rec_state["inf"]), np.int64).reshape(-1, 3)
         rec["post"] = snapshot()
         steps.append(rec)
 
@@ -328,6 +374,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "commute" in sys.argv[1:]:  # city / inter-city transports on the two commute steps of a weekday
         run_trace(2500, 9, 4, "w2k_commute", cases_per_capita=0.05, with_commute=True)
+        sys.exit(0)
+    if "records" in sys.argv[1:]:  # the Record.accumulate rows of every step (infections, symptoms, deaths, ...)
+        run_trace(2000, 30, 6, "w2k_records", cases_per_capita=0.15, schedule="simple", records=True)
         sys.exit(0)
     if "policies" in sys.argv[1:]:  # Quarantine, Shielding, CloseSchools, CloseCompanies switching on day by day
         run_trace(2500, 9, 3, "w2k_policies", cases_per_capita=0.05, lockdown=True)

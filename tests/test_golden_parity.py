@@ -128,6 +128,8 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
             flags |= _lib.STEP_INJECT_POLICY
             n_policy_draws = getattr(run_trace, "policy_draws", 0) + len(s["pol_draws"])
             run_trace.policy_draws = n_policy_draws
+        if "health_events" in s:
+            flags |= _lib.STEP_RECORD_EVENTS
         p = eng.make_params(now=float(s["now"]), delta_time=float(s["dt"]), step=i,
                             activity_mask=int(s["activity_mask"]), seed=0, flags=flags, beta=beta)
         eng.step_begin(p)
@@ -150,10 +152,28 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
         member, variant = eng.fetch_new_infections()
         ref_new = np.sort(s["new_rows"][:, 0].astype(np.int64)) if len(s["new_rows"]) else np.zeros(0, np.int64)
         assert np.array_equal(member.astype(np.int64), ref_new), f"step {i}: infected set differs"
+        if "infection_events" in s:
+            # rows of the reference's `infections` table (interaction.py:664-683): who was infected where.  The
+            # infector is np.random.choice in the reference (interaction.py:643-662), so only its validity is checked
+            ev = eng.fetch_infection_events()
+            ref_ev = s["infection_events"]
+            assert np.array_equal(ev["infected"].astype(np.int64), ref_ev[:, 0]), f"step {i}: infections table, infected ids"
+            assert np.array_equal(ev["group"].astype(np.int64), ref_ev[:, 2]), f"step {i}: infections table, locations"
+            before = eng.fetch_person_state()
+            assert ((before["pstate"][ev["infector"]] & PS_INFECTED) != 0).all() and (before["trans_prob"][ev["infector"]] > 0).all()
+            assert np.array_equal(s["place_group"][ev["infector"]], s["place_group"][ref_ev[:, 1]]), f"step {i}: infector not in the reference's group"
+            run_trace.infection_rows = getattr(run_trace, "infection_rows", 0) + len(ref_ev)
         if len(s["new_rows"]):
             eng.upload_infections(rows_to_dicts(s["new_rows"]))
         stats = eng.step_finish()
         assert stats["n_draws"] == len(dp)
+        if "health_events" in s:
+            # rows of the symptoms / deaths / recoveries / hospital_admissions / icu_admissions / discharges tables
+            hev = eng.fetch_health_events()
+            got = np.stack([hev["person"].astype(np.int64), hev["kind"].astype(np.int64), hev["group"].astype(np.int64)], axis=1)
+            assert np.array_equal(got, s["health_events"]), f"step {i}: health event tables differ"
+            for k_ in got[:, 1]:
+                run_trace.health_rows[int(k_)] = run_trace.health_rows.get(int(k_), 0) + 1
         if "vac_today" in s:
             # the day's vaccinations follow the health update (epidemiology.py:295-303); the reference's
             # own random() per person is replayed
@@ -196,10 +216,18 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     return total_draws, total_inf, worst
 
 
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute", "w2k_vaccination"])
+FIXTURES = ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute", "w2k_vaccination", "w2k_records"]
+run_trace.health_rows = {}
+
+
+@pytest.mark.parametrize("name", FIXTURES)
 def test_oracle_matches_reference_trace(name):
-    run_trace.policy_draws = run_trace.commuters = run_trace.vaccine_draws = 0
+    run_trace.policy_draws = run_trace.commuters = run_trace.vaccine_draws = run_trace.infection_rows = 0
+    run_trace.health_rows = {}
     draws, infections, worst = run_trace("oracle", name)
+    if name == "w2k_records":
+        assert run_trace.infection_rows > 500
+        assert all(run_trace.health_rows.get(k, 0) > 0 for k in range(1, 7)), run_trace.health_rows
     if name == "w2k_policies":
         assert run_trace.policy_draws > 5000, "the lockdown policies must have drawn"
     if name == "w2k_commute":
@@ -221,7 +249,7 @@ LAUNCH_MODES = {
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("modes", ["tiles", "warps", "mixed"])
-@pytest.mark.parametrize("name", ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute", "w2k_vaccination"])
+@pytest.mark.parametrize("name", FIXTURES)
 def test_cuda_matches_reference_trace(name, modes):
     assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
     draws, infections, worst = run_trace("cuda", name, launch_modes=LAUNCH_MODES[modes])
