@@ -256,14 +256,18 @@ def run_gpu(args):
     barrier()
     e2e_steps_s = 0.0
     e2e_person_steps = 0
+    per_step = {"n_new_infections": 0, "n_infected": 0, "n_draws": 0}
     for _ in range(args.steps):
         flush_l2()
         t0 = time.perf_counter()
         sim.do_timestep(want_stats=True)
         e2e_steps_s += time.perf_counter() - t0
         e2e_person_steps += n_people - sim.last_stats["n_dead_total"]
+        for k_ in per_step:
+            per_step[k_] += sim.last_stats[k_]
         next(sim.timer)
     barrier()
+    per_step = {k_: round(v / args.steps, 1) for k_, v in per_step.items()}
 
     clocks = sampler.stop()  # sampled across the three timed legs
 
@@ -329,6 +333,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_ps / (e2e_ms * 1e-3), "unit": "person-timesteps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
+        "per_step_mean": per_step,
         "clocks": clocks,
         "roofline": roofline,
         "wall_s_leg1": round(t_wall1 - t_wall0, 3),

@@ -233,7 +233,12 @@ struct JbWorld {
   // person state
   uint8_t *pstate = nullptr, *phot = nullptr, *pvar = nullptr;
   int8_t* ptag = nullptr;
-  double *susc = nullptr, *trans = nullptr;
+  double* susc = nullptr;
+  // Transmission probabilities are double buffered: the interaction kernels of a step read trans[trans_par]
+  // (written by the previous step's health update) while this step's health update writes trans[trans_par ^ 1]
+  // concurrently; the buffers swap when the step finishes.  Only infected people's entries are meaningful.
+  double* trans[2] = {nullptr, nullptr};
+  uint32_t trans_par = 0;
   int32_t *pmed = nullptr, *pslot = nullptr;
   uint32_t* halo_gid = nullptr;
   uint32_t* out_person = nullptr;

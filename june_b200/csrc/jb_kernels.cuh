@@ -509,6 +509,8 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
       prob = a.inf_par[(size_t)3 * a.C + s] * (pow(tau, a.inf_par[s]) * exp(-tau / a.inf_par[(size_t)1 * a.C + s]));
     }
     a.trans[p] = prob;
+  } else {
+    a.trans[p] = a.inf_par[s];  // constant profile: carried over into the buffer the next step reads
   }
   // symptoms.update_trajectory_stage: at most one stage per call (symptoms.py:152-154)
   int stage = a.inf_stage[s];
@@ -648,7 +650,9 @@ struct NewInfArgs {
   const uint8_t* age; const uint8_t* sex; const uint8_t* ch;
   const double* hi_cum;
   const DiseaseDev* dis;
-  uint8_t* pstate; uint8_t* pvar; int8_t* ptag; double* susc; double* trans; int32_t* pslot;
+  uint8_t* pstate; uint8_t* pvar; int8_t* ptag; double* susc; int32_t* pslot;
+  double* trans;            // the buffer the NEXT step reads
+  double* trans_other;      // the current one: written as well when no step is running (seeding)
   int32_t* inf_person; double* inf_start; double* inf_par; double* inf_next; double* traj_time;
   uint8_t* inf_stage; uint8_t* inf_nst; uint8_t* inf_var; int8_t* inf_tag; int8_t* inf_maxtag; int8_t* traj_tag;
   uint8_t* inf_region; int32_t* inf_hosp; int32_t* inf_med; uint8_t* inf_sev;  // slot-resident person facts
@@ -666,22 +670,17 @@ struct NewInfArgs {
 // sample with its own Philox stream (JB_STREAM_SAMPLE0 + slot), so the lanes draw them in
 // parallel and lane 0 assembles the infection.  Slots: 0 max_severity; 1..8 stage s = slot-1;
 // 9..14 transmission parameter k = slot-9; 15 the second `alpha()` call of the xnexp profile.
-__device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, uint32_t bid, uint32_t nb) {
-  // the disease tables are walked with data-dependent indices: stage them in shared memory once
-  // per block instead of chasing them through L2 for every sample
-  __shared__ __align__(8) unsigned char s_dis[sizeof(DiseaseDev)];
+// The disease tables (6 KB, walked with data-dependent indices) travel as a kernel parameter: constant
+// bank reads instead of a per-block staging copy behind a barrier.  The chain of dependent DRAM round
+// trips is kept short: everything indexed by the person is requested in one go, and lane 0 takes its
+// infection slot before the sampling, not after it.
+__device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const DiseaseDev& D, uint32_t bid, uint32_t nb) {
   const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap) : a.count_host;
   if ((uint64_t)bid * (blockDim.x / 16) >= n) return;  // nothing for this block
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.dis);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(s_dis);
-    for (uint32_t i = threadIdx.x; i < sizeof(DiseaseDev) / 4; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  const DiseaseDev& D = *reinterpret_cast<const DiseaseDev*>(s_dis);
   const int lane = threadIdx.x & 31, j = lane & 15;
   const uint32_t segmask = 0xFFFFu << (lane & 16);
   const uint32_t n_seg = nb * blockDim.x / 16;
+  const uint32_t step_flags = a.sp->flags;
   for (uint32_t i = (bid * blockDim.x + threadIdx.x) / 16; i < n; i += n_seg) {
     const uint32_t p = a.member[i];
     const uint32_t var = a.variant ? a.variant[i] : 0u;
@@ -692,17 +691,29 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, uint32_t bid
       }
       continue;
     }
-    if (a.sp->flags & JB_STEP_NO_NEW_INFECTIONS) continue;  // only route halo infections (the host creates the local ones)
+    if (step_flags & JB_STEP_NO_NEW_INFECTIONS) continue;  // only route halo infections (the host creates the local ones)
+    // one round trip for everything indexed by the person
     const uint32_t st = a.pstate[p];
+    const uint32_t ext = a.int2ext[p];
+    const uint32_t age_raw = a.age[p], sex_p = a.sex[p], ch_p = a.ch[p];
+    uint32_t region_p = 0, sa_p = 0;
+    int32_t med_p = -1;
+    if (j == 0) { region_p = a.pregion[p]; sa_p = a.psa[p]; med_p = a.pmed[p]; }
     if (st & (JB_PS_INFECTED | JB_PS_DEAD)) continue;  // cannot happen within a step; guards seeding
-    const uint32_t gid = a.gid_base + a.int2ext[p];
+    uint32_t slot = 0;
+    int32_t hosp_p = -1;
+    if (j == 0) {
+      slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);  // in flight while the segment samples
+      hosp_p = a.sa_hospital[sa_p];
+    }
+    const uint32_t gid = a.gid_base + ext;
     // symptoms: max_severity -> outcome slot (symptoms.py:47,110-120; health_index.py:151-182)
     JbStream r0;
     jb_stream_init(r0, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0);
     const double max_sev = jb_stream_next(r0);
-    const int age = a.age[p] > 99 ? 99 : a.age[p];
-    const int pop = (a.ch[p] && age >= 50) ? 1 : 0;
-    const double* cum = a.hi_cum + ((size_t)(pop * 2 + a.sex[p]) * 100 + age) * D.n_tags;
+    const int age = age_raw > 99u ? 99 : (int)age_raw;
+    const int pop = (ch_p && age >= 50) ? 1 : 0;
+    const double* cum = a.hi_cum + ((size_t)(pop * 2 + sex_p) * 100 + age) * D.n_tags;
     // np.searchsorted(side="left"): the 16 lanes of the segment test one table entry each
     double my_cum = j < D.n_tags ? cum[j] : 2.0;
     const double mult = a.effmult ? a.effmult[(size_t)var * a.N + p] : 1.0;
@@ -740,14 +751,16 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, uint32_t bid
     {
       JbStream rs;
       jb_stream_init(rs, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
+      const JbDist* dist = nullptr;  // one call site: the sampler is a real function (instruction footprint)
       if (j >= 1 && j <= 8) {
         const int s = j - 1;
-        if (s < nst) x = jb_sample_dist(rs, D.traj_stage_time[k][s].type, D.traj_stage_time[k][s].p);
+        if (s < nst) dist = &D.traj_stage_time[k][s];
       } else if (j >= 9) {
         const int q = (j == 15) ? 3 : j - 9;
         const int need = D.trans_type == JB_TRANS_GAMMA ? 4 : D.trans_type == JB_TRANS_XNEXP ? 5 : 1;
-        if (q < need && (j != 15 || D.trans_type == JB_TRANS_XNEXP)) x = jb_sample_dist(rs, D.trans_par[q].type, D.trans_par[q].p);
+        if (q < need && (j != 15 || D.trans_type == JB_TRANS_XNEXP)) dist = &D.trans_par[q];
       }
+      if (dist) x = jb_sample_dist(rs, dist->type, dist->p);
     }
     // lane 0 of the segment assembles the infection
     double tstage[JB_MAX_STAGES], tp[7];
@@ -756,7 +769,6 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, uint32_t bid
 #pragma unroll
     for (int q = 0; q < 7; ++q) tp[q] = __shfl_sync(segmask, x, 9 + q, 16);
     if (j != 0) continue;
-    const uint32_t slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);
     if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
     // trajectory: cumulative stage start times (trajectory_maker.py:215-227)
     double cumt = 0.0, t_exposed = 0.0;
@@ -798,18 +810,19 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, uint32_t bid
     a.inf_var[slot] = (uint8_t)var;
     a.inf_tag[slot] = (int8_t)D.tag_exposed;
     a.inf_maxtag[slot] = (int8_t)idx;
-    a.inf_region[slot] = a.pregion[p];
-    a.inf_hosp[slot] = a.sa_hospital[a.psa[p]];
-    a.inf_med[slot] = a.pmed[p];
+    a.inf_region[slot] = (uint8_t)region_p;
+    a.inf_hosp[slot] = hosp_p;
+    a.inf_med[slot] = med_p;
     a.inf_sev[slot] = 0;
     a.pslot[p] = (int32_t)slot;
     a.pvar[p] = (uint8_t)var;
     a.ptag[p] = (int8_t)D.tag_exposed;
     a.trans[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
+    if (!a.fuse_health) a.trans_other[p] = a.trans[p];
     // immunity.add_immunity(infection.immunity_ids()) (infection_selector.py:160-162)
     for (int v = 0; v < a.V; ++v) a.susc[(size_t)v * a.NP + p] = 0.0;
     a.pstate[p] = (uint8_t)((st & ~JB_PST_CODE_MASK) | JB_PS_INFECTED);  // susceptibility code: 0.0
-    atomicAdd(&a.summary[a.pregion[p] * JB_N_SUMMARY + SUM_NEW_INFECTED], 1u);
+    atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_NEW_INFECTED], 1u);
     if (a.fuse_health) {
       // update_health_status also covers the infections created in this step
       // (epidemiology.py:217-303 runs after infect_people); k_health handles the older slots
@@ -822,17 +835,8 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, uint32_t bid
   }
 }
 
-__global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a) {
-  jb_newinf_body(a, blockIdx.x, gridDim.x);
-}
-
-// Stage C as ONE launch: the first `nb_new` blocks create this step's infections (and give them
-// their first health update), the others update the infections that existed at step start.  The
-// two halves touch disjoint people and slots; one grid lets the short health update run in the
-// shadow of the latency-bound infection sampler instead of behind it.
-__global__ void __launch_bounds__(128) k_finish(const __grid_constant__ NewInfArgs a, uint32_t nb_new) {
-  if (blockIdx.x < nb_new) jb_newinf_body(a, blockIdx.x, nb_new);
-  else jb_health_body(a.h, blockIdx.x - nb_new, gridDim.x - nb_new);
+__global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
+  jb_newinf_body(a, D, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------

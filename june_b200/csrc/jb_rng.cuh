@@ -79,7 +79,10 @@ __host__ __device__ __forceinline__ void jb_stream_init(JbStream& s, uint64_t se
   s.have = 0; s.spare = 0.0;
 }
 
-__host__ __device__ __forceinline__ double jb_stream_next(JbStream& s) {
+// (The samplers below are deliberately NOT inlined: the infection sampler runs a few thousand warps
+// once per step through straight-line code, so its time is instruction fetch -- one copy of Philox
+// and of each transcendental instead of a dozen.)
+__host__ __device__ __noinline__ double jb_stream_next(JbStream& s) {
   if (s.have) { s.have = 0; return s.spare; }
   JbPhilox4 r = jb_philox4x32_10(s.gid, s.step, s.stream, s.k++, s.k0, s.k1);
   s.spare = jb_u52(r.x[2], r.x[3]);
@@ -88,13 +91,13 @@ __host__ __device__ __forceinline__ double jb_stream_next(JbStream& s) {
 }
 
 // Box-Muller (cosine branch only): consumes two uniforms.
-__host__ __device__ __forceinline__ double jb_normal(JbStream& s) {
+__host__ __device__ __noinline__ double jb_normal(JbStream& s) {
   double u1 = jb_stream_next(s), u2 = jb_stream_next(s);
   return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
 }
 
 // Marsaglia & Tsang (2000) gamma(k, 1).
-__host__ __device__ inline double jb_gamma(JbStream& s, double k) {
+__host__ __device__ __noinline__ double jb_gamma(JbStream& s, double k) {
   double boost = 1.0;
   if (k < 1.0) {
     boost = pow(jb_stream_next(s), 1.0 / k);
@@ -114,7 +117,7 @@ __host__ __device__ inline double jb_gamma(JbStream& s, double k) {
 }
 
 // One completion time (JbDist; trajectory_maker.py:62-132).
-__host__ __device__ inline double jb_sample_dist(JbStream& s, int type, const double* p) {
+__host__ __device__ __noinline__ double jb_sample_dist(JbStream& s, int type, const double* p) {
   switch (type) {
     case 0: return p[0];                                            // constant
     case 1: return p[0] - p[1] * log(jb_stream_next(s));            // expon(loc, scale)

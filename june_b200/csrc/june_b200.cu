@@ -231,7 +231,8 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_alloc(&w->pvar, w->NP));
   TRY(dev_alloc(&w->ptag, w->N));
   TRY(dev_alloc(&w->susc, (size_t)w->V * w->NP));
-  TRY(dev_alloc(&w->trans, w->NP));
+  TRY(dev_alloc(&w->trans[0], w->NP));
+  TRY(dev_alloc(&w->trans[1], w->NP));
   TRY(dev_alloc(&w->pmed, w->N));
   TRY(dev_alloc(&w->pslot, w->N));
   TRY(dev_alloc(&w->halo_gid, w->H));
@@ -246,7 +247,8 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   }
   CK(cudaMemsetAsync(w->pvar, 0, w->NP, s));
   CK(cudaMemsetAsync(w->ptag, 0xFF, w->N, s));  // -1 = healthy
-  CK(cudaMemsetAsync(w->trans, 0, (size_t)w->NP * 8, s));
+  CK(cudaMemsetAsync(w->trans[0], 0, (size_t)w->NP * 8, s));
+  CK(cudaMemsetAsync(w->trans[1], 0, (size_t)w->NP * 8, s));
   CK(cudaMemsetAsync(w->pmed, 0xFF, (size_t)w->N * 4, s));
   CK(cudaMemsetAsync(w->pslot, 0xFF, (size_t)w->N * 4, s));
   CK(cudaMemsetAsync(w->halo_gid, 0, (size_t)std::max(1u, w->H) * 4, s));
@@ -363,7 +365,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   cudaStreamSynchronize(w->stream);
   void* ptrs[] = {w->age, w->sex, w->ch, w->phas, w->school_years, w->psa, w->grp_off, w->grp_info, w->grp_aux,
                   w->reg_member, w->reg_info, w->sa_region, w->sa_hospital, w->cm, w->beta_scale, w->hi_cum, w->dis,
-                  w->pstate, w->phot, w->pvar, w->ptag, w->susc, w->trans, w->pmed, w->pslot, w->halo_gid, w->out_person,
+                  w->pstate, w->phot, w->pvar, w->ptag, w->susc, w->trans[0], w->trans[1], w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
@@ -773,7 +775,8 @@ static NewInfArgs make_newinf_args(JbWorld* w) {
   memset(&a, 0, sizeof(a));
   a.N = w->N; a.NP = w->NP; a.C = w->C; a.V = (int)w->V; a.gid_base = (uint32_t)w->id_base; a.int2ext = w->int2ext;
   a.age = w->age; a.sex = w->sex; a.ch = w->ch; a.hi_cum = w->hi_cum; a.dis = w->dis;
-  a.pstate = w->pstate; a.pvar = w->pvar; a.ptag = w->ptag; a.susc = w->susc; a.trans = w->trans; a.pslot = w->pslot;
+  a.pstate = w->pstate; a.pvar = w->pvar; a.ptag = w->ptag; a.susc = w->susc; a.pslot = w->pslot;
+  a.trans = w->trans[w->trans_par ^ 1]; a.trans_other = w->trans[w->trans_par];
   a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
   a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_var = w->inf_var;
   a.inf_tag = w->inf_tag; a.inf_maxtag = w->inf_maxtag; a.traj_tag = w->traj_tag; a.counters = w->counters;
@@ -809,7 +812,7 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   CK(cudaStreamSynchronize(w->stream));
   a.sp = reinterpret_cast<const StepDev*>(w->d_step_aux);
   unsigned blocks = (unsigned)std::min<size_t>((n * 16 + 127) / 128, 148 * 8);
-  k_newinf<<<blocks, 128, 0, w->stream>>>(a);
+  k_newinf<<<blocks, 128, 0, w->stream>>>(a, w->dis_host);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(w->stream));
   cudaFree(d_p);
@@ -890,7 +893,8 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
     CK(cudaMemcpy(w->pslot + r.person, &slot, 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->ptag + r.person, &tg, 1, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->pvar + r.person, &vr, 1, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(w->trans + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->trans[0] + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->trans[1] + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
     for (uint32_t v = 0; v < w->V; ++v)
       CK(cudaMemcpy(w->susc + (size_t)v * w->NP + r.person, &zero, 8, cudaMemcpyHostToDevice));
   }
@@ -929,7 +933,7 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   const JbStepParams& p = w->cur;
   a.grp_off = w->grp_off; a.grp_info = w->grp_info; a.grp_aux = w->grp_aux;
   a.reg_member = w->reg_member; a.reg_info = w->reg_info;
-  a.phot = w->phot; a.susc = w->susc; a.trans = w->trans; a.halo_gid = w->halo_gid;
+  a.phot = w->phot; a.susc = w->susc; a.trans = w->trans[w->trans_par]; a.halo_gid = w->halo_gid;
   a.school_years = w->school_years; a.cm = w->cm + sg.cm_offset; a.beta = w->beta; a.beta_scale = w->beta_scale;
   a.dyn_cnt = sg.has_dynamic ? w->dyn_cnt : nullptr;
   const size_t ksg = &sg - w->sgs.data();
@@ -1119,12 +1123,12 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     w->launches++;
   }
   if (w->p2p_on) {
-    k_halo_push<<<std::max(1u, (w->n_out + 255) / 256), 256, 0, s>>>(w->p2p, w->out_person, w->n_out, w->phot, w->susc, w->trans,
+    k_halo_push<<<std::max(1u, (w->n_out + 255) / 256), 256, 0, s>>>(w->p2p, w->out_person, w->n_out, w->phot, w->susc, w->trans[w->trans_par],
                                                                     w->NP, (int)w->V, step_dev(w), w->p2p_done);
     KCHECK("k_halo_push", s);
     w->launches++;
   } else if (w->n_out && d_send) {
-    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->phot, w->susc, w->trans,
+    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->phot, w->susc, w->trans[w->trans_par],
                                                        w->NP, (int)w->V, (unsigned char*)d_send);
     KCHECK("k_halo_pack", s);
     w->launches++;
@@ -1133,10 +1137,11 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
 }
 
 // The infections created in a step get their first health update from k_newinf itself, so
-// k_health only walks the slots that existed at step start.  Single-domain steps run both as one
-// launch (k_finish); residents infected abroad arrive later in the step and get their first update
-// from k_newinf as well.  (With host-issued collectives the step is three separately captured
-// phases; when the host creates the infections, JB_STEP_NO_NEW_INFECTIONS, k_health walks every slot.)
+// k_health only walks the slots that existed at step start.  Single-domain and peer-memory steps
+// launch it beside the interaction kernels (enqueue_interact); residents infected abroad arrive
+// later in the step and get their first update from k_newinf as well.  (With host-issued
+// collectives the step is three separately captured phases and k_health runs in the last one; when
+// the host creates the infections, JB_STEP_NO_NEW_INFECTIONS, k_health walks every slot there.)
 static inline bool fused_finish(const JbWorld* w) {
   return (!(w->H || w->n_out) || w->p2p_on) && !(w->cur.flags & JB_STEP_NO_NEW_INFECTIONS);
 }
@@ -1150,7 +1155,7 @@ static HealthArgs make_health_args(JbWorld* w, int old_only) {
   a.masks.icu_mask = w->dis_host.icu_mask; a.masks.severe_mask = w->dis_host.severe_mask;
   a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
   a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
-  a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans; a.pmed = w->pmed;
+  a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans[w->trans_par ^ 1]; a.pmed = w->pmed;
   a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
   a.summary = w->summary; a.R = (int)w->R;
@@ -1181,7 +1186,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   }
   if (w->H && d_recv) {
     k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
-                                                     w->phot, w->susc, w->trans, (uint8_t*)d_ret_send);
+                                                     w->phot, w->susc, w->trans[w->trans_par], (uint8_t*)d_ret_send);
     KCHECK("k_halo_unpack", s);
     w->launches++;
   }
@@ -1193,6 +1198,23 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     CK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->draw_cnt, w->draw_base, (int)(w->G + 1), s));
     w->launches += 2;
   }
+  // The health update of the infections that existed at step start reads nothing the interaction
+  // writes and writes nothing it reads (transmission probabilities are double buffered), so it runs
+  // beside the interaction kernels instead of behind them.
+  const bool health_beside = fused_finish(w);
+  static const int health_early = jb_env_flag("JB_HEALTH_EARLY", 1);
+  static const int health_blocks = jb_env_flag("JB_HEALTH_BLOCKS", 4);
+  auto fork_health = [&]() -> int {
+    cudaStream_t hs = w->serial ? s : w->side_health;
+    if (!w->serial) { CK(cudaEventRecord(w->ev_fork_health, s)); CK(cudaStreamWaitEvent(hs, w->ev_fork_health, 0)); }
+    const HealthArgs ha = make_health_args(w, 1);
+    k_health<<<148 * health_blocks, 256, 0, hs>>>(ha);
+    KCHECK("k_health", hs);
+    w->launches++;
+    if (!w->serial) CK(cudaEventRecord(w->ev_join_health, hs));
+    return JB_OK;
+  };
+  if (health_beside && health_early) TRY(fork_health());
   TRY(launch_groups(w, 0));
   if (w->timing >= 2) CK(cudaEventRecord(w->ev_int1, s));
   // create infections for residents infected here; flag halo persons for their home domain
@@ -1202,16 +1224,12 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     a.cap = w->newinf_cap; a.sp = step_dev(w);
     a.halo_ret = (uint8_t*)d_ret_send;
     a.fuse_health = 1; a.h = make_health_args(w, 0);
-    if (fused_finish(w)) {
-      a.h.old_only = 1;
-      k_finish<<<148 * 8 + 148 * 8, 128, 0, s>>>(a, 148 * 8);
-      KCHECK("k_finish", s);
-    } else {
-      k_newinf<<<148 * 8, 128, 0, s>>>(a);
-      KCHECK("k_newinf", s);
-    }
+    if (health_beside && !health_early) TRY(fork_health());
+    k_newinf<<<148 * 8, 128, 0, s>>>(a, w->dis_host);
+    KCHECK("k_newinf", s);
     w->launches++;
   }
+  if (health_beside && !w->serial) CK(cudaStreamWaitEvent(s, w->ev_join_health, 0));
   if (w->p2p_on) {
     k_halo_ret_push<<<std::max(1u, (w->H + 255) / 256), 256, 0, s>>>(w->p2p, w->p2p_ret_local, w->H, step_dev(w), w->p2p_done + 1);
     KCHECK("k_halo_ret_push", s);
@@ -1243,7 +1261,7 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
       a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_HALO_INF;
       a.cap = w->newinf_cap; a.sp = step_dev(w);
       a.fuse_health = 1; a.h = make_health_args(w, 0);
-      k_newinf<<<148 * 2, 128, 0, s>>>(a);
+      k_newinf<<<148 * 2, 128, 0, s>>>(a, w->dis_host);
       KCHECK("k_newinf(halo)", s);
       w->launches++;
     }
@@ -1262,7 +1280,7 @@ static int run_phase(JbWorld* w, int phase, const void* p0, const void* p1, F&& 
   const bool plain = !w->use_graphs || w->timing >= 2 || jb_debug_sync() ||
                      (p.flags & (JB_STEP_INJECT_UNIFORMS | JB_STEP_RECORD_LAMBDA));
   if (plain) return enqueue();
-  const uint64_t k0 = ((uint64_t)phase << 56) | ((uint64_t)(w->serial ? 1 : 0) << 48) | ((uint64_t)(p.leisure_table ? 1 : 0) << 49) |
+  const uint64_t k0 = ((uint64_t)phase << 56) | ((uint64_t)(w->serial ? 1 : 0) << 48) | ((uint64_t)(p.leisure_table ? 1 : 0) << 49) | ((uint64_t)w->trans_par << 50) |
                       ((uint64_t)p.activity_mask << 32) | p.flags;
   const uint64_t k1 = (uint64_t)(uintptr_t)p0, k2 = (uint64_t)(uintptr_t)p1;
   for (const JbWorld::GraphEntry& e : w->graphs)
@@ -1346,6 +1364,7 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
   TRY(run_phase(w, 2, d_ret_recv, nullptr, [&]() { return enqueue_finish(w, d_ret_recv); }));
   TRY(timing_end(w, s));
   w->in_step = false;
+  w->trans_par ^= 1u;  // the health update has filled the other transmission buffer
   if (out) {
     CK(cudaStreamSynchronize(s));
     const uint32_t* c = w->h_counters;
@@ -1408,6 +1427,7 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
   w->in_step = true;  // jb_step_finish_tail expects it
   TRY(timing_end(w, s));
   w->in_step = false;
+  w->trans_par ^= 1u;  // the health update has filled the other transmission buffer
   if (!out) return JB_OK;
   CK(cudaStreamSynchronize(s));
   {
@@ -1570,7 +1590,13 @@ extern "C" int jb_fetch_person_state(JbWorld* w, uint8_t* pstate, int8_t* tag, d
     for (uint32_t p = 0; p < w->N_ext; ++p) pstate[p] = (uint8_t)((pstate[p] & 0x78u) | (hot[p] & JB_PS_ACT_MASK));
   }
   if (tag) TRY(fetch_permuted(w, w->ptag, tag));
-  if (trans_prob) TRY(fetch_permuted(w, w->trans, trans_prob));
+  if (trans_prob) {  // the buffer the next step reads; entries of people without an infection are stale by design
+    std::vector<uint8_t> st(w->N_ext);
+    TRY(fetch_permuted(w, w->trans[w->trans_par], trans_prob));
+    TRY(fetch_permuted(w, w->pstate, st.data()));
+    for (uint32_t p = 0; p < w->N_ext; ++p)
+      if (!(st[p] & JB_PS_INFECTED)) trans_prob[p] = 0.0;
+  }
   if (susceptibility)
     for (uint32_t v = 0; v < w->V; ++v) TRY(fetch_permuted(w, w->susc + (size_t)v * w->NP, susceptibility + (size_t)v * w->N_ext));
   if (medical) TRY(fetch_permuted(w, w->pmed, medical));
@@ -1615,7 +1641,7 @@ extern "C" int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap,
       CK(cudaMemcpy(tt.data() + (size_t)q * hw, w->traj_time + (size_t)q * C, (size_t)hw * 8, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(ttag.data() + (size_t)q * hw, w->traj_tag + (size_t)q * C, hw, cudaMemcpyDeviceToHost));
     }
-    CK(cudaMemcpy(trans.data(), w->trans, (size_t)w->N * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(trans.data(), w->trans[w->trans_par], (size_t)w->N * 8, cudaMemcpyDeviceToHost));
   }
   size_t k = 0;
   for (uint32_t s = 0; s < hw; ++s) {
