@@ -164,7 +164,8 @@ def make_b200_simulator_class(reference_simulator_cls):
             date = self.timer.date
             if pol is not None:
                 pol.leisure_policies.apply(date=date, leisure=leisure)
-            key = (round(self.timer.duration, 9), "primary_activity" in activities, date.weekday(), date.hour, self._policy_key)
+            lkey = tuple(id(p) for p in pol.leisure_policies.get_active(date)) if pol is not None else ()
+            key = (round(self.timer.duration, 9), "primary_activity" in activities, date.weekday(), date.hour, self._policy_key, lkey)
             idx = self._leisure_cache.get(key)
             if idx is None:
                 leisure.generate_leisure_probabilities_for_timestep(

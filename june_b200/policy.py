@@ -213,7 +213,69 @@ class LimitLongCommute(Policy):
         return dict(type=_lib.POL_LIMIT_LONG_COMMUTE, p=[self.going_to_work_probability])
 
 
-_CLASSES = {c.__name__: c for c in (SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
+class CloseLeisureVenue(Policy):
+    """``CloseLeisureVenue`` (``leisure_policies.py:69-100``): the listed venue types are closed in every
+    region (``region.policy["global_closed_venues"]``); a closed venue's Poisson rate is 0
+    (``social_venue_distributor.py:195-196``).  Names are the reference's: the venue *spec* ("pub",
+    "cinema", ...), which is what ``get_poisson_parameter`` compares against."""
+
+    policy_type = "leisure"
+    policy_subtype = "close_venues"
+
+    def __init__(self, start_time: DateLike = "1900-01-01", end_time: DateLike = "2100-01-01",
+                 venues_to_close: Sequence[str] = ("cinemas", "groceries")):
+        super().__init__(start_time, end_time)
+        self.venues_to_close = tuple(venues_to_close)
+
+    def apply(self, leisure) -> None:
+        for region in leisure.region_names:
+            leisure.closed_venues.setdefault(region, set()).update(self.venues_to_close)
+
+
+class ChangeLeisureProbability(Policy):
+    """``ChangeLeisureProbability`` (``leisure_policies.py:103-180``): per activity, day type, sex and age
+    a factor on the Poisson rate, softened by the regional compliance
+    (``rate * (1 + compliance * (factor - 1))``, ``social_venue_distributor.py:199-204``)."""
+
+    policy_type = "leisure"
+    policy_subtype = "change_leisure_probability"
+
+    def __init__(self, start_time: DateLike = "1900-01-01", end_time: DateLike = "2100-01-01",
+                 activity_reductions: Optional[Dict[str, dict]] = None):
+        super().__init__(start_time, end_time)
+        self.activity_reductions = self._read_activity_reductions(activity_reductions or {})
+
+    @staticmethod
+    def _read_activity_reductions(activity_reductions: Dict[str, dict]) -> Dict[str, dict]:
+        from .leisure import parse_age_probabilities
+        sexes = (("male", "m"), ("female", "f"))
+        ret: Dict[str, dict] = {}
+        for activity, pp in activity_reductions.items():
+            out = ret[activity] = {"weekday": {}, "weekend": {}}
+            for first in pp:
+                if first in ("weekday", "weekend"):
+                    for long, short in sexes:
+                        src = pp[first]["both_sexes"] if "both_sexes" in pp[first] else pp[first][long]
+                        out[first][short] = parse_age_probabilities(src)
+                elif first in ("any", "male", "female"):
+                    for long, short in sexes:
+                        for day_type in out:
+                            out[day_type][short] = parse_age_probabilities(pp[long])
+                elif first == "both_sexes":
+                    for _, short in sexes:
+                        for day_type in out:
+                            out[day_type][short] = parse_age_probabilities(pp["both_sexes"])
+                else:
+                    for day_type in out:
+                        for long, short in sexes:
+                            out[day_type][short] = parse_age_probabilities(pp[day_type][long])
+        return ret
+
+    def apply(self, leisure) -> Dict[str, dict]:
+        return self.activity_reductions
+
+
+_CLASSES = {c.__name__: c for c in (CloseLeisureVenue, ChangeLeisureProbability, SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
                                     SevereSymptomsStayHome, Hospitalisation, Quarantine, Shielding, CloseSchools,
                                     CloseUniversities, CloseCompanies, LimitLongCommute)}
 
@@ -249,6 +311,27 @@ class Policies:
     @property
     def individual_policies(self):
         return self._of("individual")
+
+    @property
+    def leisure_policies(self):
+        return self._of("leisure")
+
+    def apply_leisure_policies(self, date: datetime.datetime, leisure) -> None:
+        """``LeisurePolicies.apply`` (``leisure_policies.py:23-66``): reset the closed venues and the
+        probability reductions, then apply the active policies (at most one change of probabilities)."""
+        leisure.closed_venues = {r: set() for r in leisure.region_names}
+        leisure.policy_reductions = {}
+        n_change = 0
+        for p in self.leisure_policies:
+            if not p.is_active(date):
+                continue
+            if p.policy_subtype == "change_leisure_probability":
+                n_change += 1
+                if n_change > 1:
+                    raise ValueError("Having more than one change leisure probability policy active is not supported.")
+                leisure.policy_reductions = p.apply(leisure=leisure)
+            else:
+                p.apply(leisure=leisure)
 
     @property
     def medical_care_policies(self):

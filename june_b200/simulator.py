@@ -314,6 +314,7 @@ class Simulator:
         if idx is None:
             comp, _ = self.activity_manager.policies.regional_scalars(date, self.world.region_names, self._region_state)
             leisure.regional_compliance = dict(zip(self.world.region_names, comp))
+            self.activity_manager.policies.apply_leisure_policies(date, leisure)  # activity_manager.py:200-204
             self._leisure_stack.append(leisure.generate_leisure_probabilities_for_timestep(
                 delta_time=self.timer.duration, working_hours="primary_activity" in acts, date=date))
             idx = self._leisure_tables[key] = len(self._leisure_stack) - 1

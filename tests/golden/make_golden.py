@@ -365,7 +365,57 @@ def spot_values(out_name="spot"):
     print("spot values written")
 
 
+LEISURE_POLICY_CASE = dict(
+    venues_to_close=["cinema"],
+    activity_reductions={"pub": {"weekday": {"male": {"0-50": 0.5, "50-100": 0.2}, "female": {"0-70": 0.3, "70-100": 0.8}},
+                                 "weekend": {"both_sexes": {"0-100": 0.6}}},
+                         "grocery": {"both_sexes": {"0-65": 0.9, "65-100": 0.4}}},
+    compliance=[1.0, 0.7, 0.35],
+    slots=[("2020-03-03 09:00", 8 / 24, True), ("2020-03-03 18:00", 3 / 24, False), ("2020-03-07 12:00", 4 / 24, False)],
+)
+
+
+def leisure_policy_tables(out_name="leisure_policy_tables"):
+    """The reference's leisure probabilities with CloseLeisureVenue + ChangeLeisureProbability active and
+    region-dependent compliance (leisure_policies.py, social_venue_distributor.py:176-205, leisure.py:205-228)."""
+    import datetime
+    sink = io.StringIO()
+    pyrandom.seed(2); np.random.seed(2)
+    with contextlib.redirect_stdout(sink):
+        world, dc = ref_world.build_world(2500, seed=2, with_leisure=True)
+        sim = ref_world.make_simulator(world, dc, total_days=2, with_leisure=True)
+    from june.policy import ChangeLeisureProbability, CloseLeisureVenue, LeisurePolicies
+    leisure = sim.activity_manager.leisure
+    case = LEISURE_POLICY_CASE
+    pols = LeisurePolicies([CloseLeisureVenue("2020-01-01", "2021-01-01", venues_to_close=case["venues_to_close"]),
+                            ChangeLeisureProbability("2020-01-01", "2021-01-01", activity_reductions=case["activity_reductions"])])
+    regions = list(world.regions)
+    for k, region in enumerate(regions):
+        region.regional_compliance = case["compliance"][k % len(case["compliance"])]
+    acts = list(leisure.leisure_distributors)
+    does = np.zeros((len(case["slots"]), len(regions), 2, 100))
+    probs = np.zeros((len(case["slots"]), len(regions), 2, 100, len(acts)))
+    for t, (when, dt, wh) in enumerate(case["slots"]):
+        date = datetime.datetime.strptime(when, "%Y-%m-%d %H:%M")
+        with contextlib.redirect_stdout(sink):
+            pols.apply(date=date, leisure=leisure)
+            leisure.generate_leisure_probabilities_for_timestep(delta_time=dt, working_hours=wh, date=date)
+        table = leisure.probabilities_by_region_sex_age
+        for r, region in enumerate(regions):
+            for si, sex in enumerate("fm"):
+                for age in range(100):
+                    e = table[region.name][sex][age]
+                    does[t, r, si, age] = e["does_activity"]
+                    probs[t, r, si, age] = [e["activities"][a] for a in acts]
+    np.savez_compressed(os.path.join(HERE, out_name + ".npz"), does=does, probs=probs, activities=np.array(acts),
+                        regions=np.array([r.name for r in regions]))
+    print("leisure policy tables:", acts, does.shape, float(does.mean()))
+
+
 if __name__ == "__main__":
+    if "leisure_policies" in sys.argv[1:]:
+        leisure_policy_tables()
+        sys.exit(0)
     if "leisure" in sys.argv[1:]:  # leisure placement (pubs, cinemas, groceries) on top of the w3k recipe
         run_trace(2500, 9, 2, "w2k_leisure", cases_per_capita=0.04, with_leisure=True)
         sys.exit(0)
