@@ -253,6 +253,11 @@ int jb_inject_uniforms(JbWorld* w, const double* u, size_t n);
 int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* variants, size_t n,
               double time, uint64_t seed, uint32_t step);
 
+/* Restore person.subgroups.medical_facility: medical[n_people] = (hospital group << 8 | ward subgroup) or -1.
+ * The reference's checkpoint does not carry it (patients are simply re-admitted by the next
+ * Hospitalisation.apply, hdf5_savers/checkpoint_saver.py:162-218); it is restorable here so that a resumed
+ * run continues bit for bit.  Call before jb_upload_infections. */
+int jb_set_medical(JbWorld* w, const int32_t* medical);
 /* Install host-created infections (the reference's own sampler, or a checkpoint). */
 int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size_t n);
 

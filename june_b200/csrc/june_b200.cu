@@ -425,6 +425,14 @@ extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const doub
     }
     CK(cudaMemcpy(w->pstate, st.data(), w->N, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->phot, hot.data(), w->N, cudaMemcpyHostToDevice));
+    // the dead take part in nothing (Activities(None, ...)) and are counted
+    std::vector<uint8_t> has(w->N);
+    CK(cudaMemcpy(has.data(), w->phas, w->N, cudaMemcpyDeviceToHost));
+    uint32_t n_dead = 0;
+    for (uint32_t p = 0; p < w->N_ext; ++p)
+      if (pstate[p] & JB_PS_DEAD) { has[w->h_ext2int[p]] = 0; ++n_dead; }
+    CK(cudaMemcpy(w->phas, has.data(), w->N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->counters + CNT_DEAD_TOTAL, &n_dead, 4, cudaMemcpyHostToDevice));
   }
   if (susceptibility) {
     std::vector<double> su(w->N, 1.0);
@@ -438,6 +446,23 @@ extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const doub
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(w->stream));
   }
+  return JB_OK;
+}
+
+extern "C" int jb_set_medical(JbWorld* w, const int32_t* medical) {
+  if (!w || !medical) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  std::vector<int32_t> med(w->N, -1);
+  std::vector<uint8_t> st(w->N);
+  CK(cudaMemcpy(st.data(), w->pstate, w->N, cudaMemcpyDeviceToHost));
+  for (uint32_t p = 0; p < w->N_ext; ++p) {
+    const uint32_t i = w->h_ext2int[p];
+    med[i] = medical[p];
+    st[i] = (uint8_t)(medical[p] >= 0 ? (st[i] | JB_PS_MEDICAL) : (st[i] & ~JB_PS_MEDICAL));
+  }
+  CK(cudaMemcpy(w->pmed, med.data(), (size_t)w->N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w->pstate, st.data(), w->N, cudaMemcpyHostToDevice));
   return JB_OK;
 }
 

@@ -266,6 +266,13 @@ class Engine:
             susceptibility = np.ascontiguousarray(susceptibility, dtype=np.float64).reshape(self.n_variants, self.world.n_people)
         self._check(self._f("set_person_state")(self._h, ptr(pstate), ptr(susceptibility)))
 
+    def set_medical(self, medical: np.ndarray):
+        """Restore ``person.subgroups.medical_facility`` (``hospital group << 8 | ward``, -1 = none); call
+        before ``upload_infections``."""
+        medical = np.ascontiguousarray(medical, dtype=np.int32)
+        assert medical.shape == (self.world.n_people,)
+        self._check(self._f("set_medical")(self._h, ptr(medical)))
+
     def inject_uniforms(self, u: np.ndarray):
         u = np.ascontiguousarray(u, dtype=np.float64)
         self._check(self._f("inject_uniforms")(self._h, ptr(u), u.size))

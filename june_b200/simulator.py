@@ -158,18 +158,37 @@ class HaloExchange:
                                     output_split_sizes=self.out_counts, input_split_sizes=self.in_counts)
 
 
+def _read_checkpoint_dates(dates) -> List[datetime.date]:
+    """``_read_checkpoint_dates`` (``simulator.py:61-76``): a date, a "YYYY-MM-DD" string or a list of either."""
+    if dates is None:
+        return []
+    if isinstance(dates, (str, datetime.date)):
+        dates = [dates]
+    out = []
+    for d in dates:
+        if isinstance(d, str):
+            d = datetime.datetime.strptime(d, "%Y-%m-%d").date()
+        elif isinstance(d, datetime.datetime):
+            d = d.date()
+        out.append(d)
+    return out
+
+
 class Simulator:
     ActivityManager = ActivityManager
 
     def __init__(self, world: WorldSoA, interaction: Interaction, timer: Timer, activity_manager: ActivityManager,
                  epidemiology: Optional[Epidemiology] = None, tracker=None, events=None, record=None,
                  disease_config: Optional[DiseaseConfig] = None, outcome_prob: Optional[np.ndarray] = None,
-                 device: int = 0, seed: int = 0, engine: Optional[Engine] = None, distributed: bool = False):
+                 device: int = 0, seed: int = 0, engine: Optional[Engine] = None, distributed: bool = False,
+                 checkpoint_save_dates=None, checkpoint_save_path: Optional[str] = None):
         self.world, self.interaction, self.timer = world, interaction, timer
         self.activity_manager, self.epidemiology, self.record = activity_manager, epidemiology, record
         self.disease_config = disease_config or DiseaseConfig("covid19")
         self.seed = int(seed)
         self.step_ordinal = 0
+        self.checkpoint_save_dates = tuple(_read_checkpoint_dates(checkpoint_save_dates))
+        self.checkpoint_save_path = checkpoint_save_path or "results/checkpoints"
         self.rank = 0
         self._region_state: dict = {}
         self._policy_cache: dict = {}
@@ -242,6 +261,7 @@ class Simulator:
                 config = yaml.safe_load(f)
         timer = Timer.from_config(config)
         am = cls.ActivityManager.from_config(config, world, policies, timer)
+        kw.setdefault("checkpoint_save_dates", config.get("checkpoint_save_dates"))
         return cls(world=world, interaction=interaction, timer=timer, activity_manager=am, epidemiology=epidemiology, **kw)
 
     def clear_world(self) -> None:
@@ -372,12 +392,32 @@ class Simulator:
                     self.health_events.append((self.timer.date, hev))
 
     def run(self) -> None:
-        """``Simulator.run`` (``simulator.py:628-707``)."""
+        """``Simulator.run`` (``simulator.py:628-707``), including the checkpoints written after the last
+        step of every day listed in ``checkpoint_save_dates`` (``:681-690``)."""
         while self.timer.date < self.timer.final_date:
             if self.epidemiology is not None:
                 self.epidemiology.infection_seeds_timestep(self, self.timer)
             self.do_timestep()
+            if (self.timer.date.date() in self.checkpoint_save_dates
+                    and float(self.timer.now + self.timer.duration).is_integer()):
+                self.save_checkpoint(self.timer.date.date())
             next(self.timer)
+
+    def save_checkpoint(self, saving_date, path: Optional[str] = None) -> str:
+        """``Simulator.save_checkpoint`` (``simulator.py:709-735``): ``checkpoint_<date>.<rank>`` under
+        ``checkpoint_save_path`` (NumPy container, see ``june_b200.checkpoint``)."""
+        import os
+        from .checkpoint import save_checkpoint
+        if path is None:
+            os.makedirs(self.checkpoint_save_path, exist_ok=True)
+            path = os.path.join(self.checkpoint_save_path, f"checkpoint_{saving_date}.{self.rank}.npz")
+        save_checkpoint(self, path)
+        return path
+
+    def restore_checkpoint(self, path: str, reset_infections: bool = False, exact: bool = True) -> None:
+        """``restore_simulator_to_checkpoint`` (``hdf5_savers/checkpoint_saver.py:162-218``)."""
+        from .checkpoint import restore_checkpoint
+        restore_checkpoint(self, path, reset_infections=reset_infections, exact=exact)
 
     def summary_rows(self) -> List[Dict[str, object]]:
         """Rows of the reference's ``summary.csv`` (``records_writer.py:151-164,693-790``): one per
