@@ -264,6 +264,9 @@ struct JbWorld {
   uint32_t *hev_person = nullptr, *hev_kind = nullptr;   // health events (deaths, recoveries, admissions, discharges)
   int32_t* hev_group = nullptr;
   uint32_t hev_cap = 0;
+  uint32_t* pol_subjects = nullptr;                      // long-distance commuters (subjects of LimitLongCommute)
+  uint32_t n_pol_subjects = 0;
+  bool pol_subject_mode = false;                         // every active individual policy has a static subject list
   int32_t* pres_group = nullptr;                         // residence group of every resident (death location)  // events of the last step that recorded them
   double* beta = nullptr;
   double* lambda = nullptr;

@@ -439,6 +439,32 @@ __device__ __forceinline__ void jb_blame_uniforms(const GroupArgs& a, uint32_t p
 
 #include "jb_groups.cuh"
 
+// Fix-up pass of the table-driven placement for policies whose subjects are a static, short list of
+// people (LimitLongCommute: the long-distance commuters, individual_policies.py:773-824): everyone is
+// placed by the fast path, then the listed people are re-evaluated with the full policy logic.  Nobody
+// else can be touched by such a policy and nobody else draws, so the result equals the full path's.
+__global__ void __launch_bounds__(256) k_place_subjects(const __grid_constant__ PlaceArgs a, const uint32_t* __restrict__ subjects,
+                                                        uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = subjects[i];
+  const uint32_t st = a.pstate[p];
+  if (st & JB_PS_DEAD) return;
+  const uint32_t mask = a.sp->activity_mask, flags = a.sp->flags, has = a.phas[p];
+  uint32_t allowed = mask;
+  if ((flags & JB_STEP_SEVERE_STAY_HOME) && (st & JB_PS_SEVERE)) allowed &= (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
+  else allowed = jb_apply_policies(a, p, st, allowed);
+  const uint32_t cand = allowed & ((has & 0x1Fu) | ((st & JB_PS_MEDICAL) ? 1u << JB_ACT_MEDICAL : 0u));
+  const uint32_t hot = a.phot[p], old_act = hot & JB_PS_ACT_MASK;
+  uint32_t act = cand ? (uint32_t)__ffs(cand) - 1u : (uint32_t)JB_ACT_NONE;
+  if (act == old_act) return;
+  // (a medical facility precedes every activity a policy can remove: ward bins are unaffected)
+  if (old_act < JB_N_ACT) atomicSub(&a.counters[CNT_ACT0 + old_act], 1u);
+  if (act < JB_N_ACT) atomicAdd(&a.counters[CNT_ACT0 + act], 1u);
+  else atomicAdd(&a.counters[CNT_NOACT], 1u);
+  a.phot[p] = (uint8_t)((hot & ~JB_PS_ACT_MASK) | act);
+}
+
 // ------------------------------------------------------------------------------------------
 // Stage C2: health update for every active infection slot (epidemiology.py:217-303).
 // ------------------------------------------------------------------------------------------

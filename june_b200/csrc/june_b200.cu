@@ -370,7 +370,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
                   w->cub_tmp, w->int2ext, w->ext2int, w->d_vacc, w->vac_dose, w->vac_type, w->traj_camp, w->traj_day0, w->traj_stage,
-                  w->prior_eff_inf, w->prior_eff_sym, w->effmult, w->vac_inject, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->hev_person, w->hev_kind, w->hev_group, w->pres_group, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
+                  w->prior_eff_inf, w->prior_eff_sym, w->effmult, w->vac_inject, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->hev_person, w->hev_kind, w->hev_group, w->pres_group, w->pol_subjects, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (double* q : w->vacc_tables) cudaFree(q);
@@ -764,8 +764,11 @@ extern "C" int jb_set_individual_policies(JbWorld* w, const JbIndividualPolicy* 
   for (uint32_t r = 0; r < w->R && r < JB_MAX_REGIONS_POLICY; ++r) h.rc[r] = rc ? rc[r] : 1.0;
   if (!w->d_pol) TRY(dev_alloc(&w->d_pol, 1));
   CK(cudaMemcpy(w->d_pol, &h, sizeof(h), cudaMemcpyHostToDevice));
-  if (w->n_pol != n) drop_graphs(w);  // the count is a launch argument
+  bool subject_mode = n > 0;
+  for (uint32_t k = 0; k < n; ++k) subject_mode = subject_mode && pol[k].type == JB_POL_LIMIT_LONG_COMMUTE;
+  if (w->n_pol != n || subject_mode != w->pol_subject_mode) drop_graphs(w);  // both shape the launch sequence
   w->n_pol = n;
+  w->pol_subject_mode = subject_mode;
   return JB_OK;
 }
 
@@ -775,8 +778,17 @@ extern "C" int jb_set_person_attributes(JbWorld* w, const uint8_t* attr) {
   CK(cudaStreamSynchronize(w->stream));
   std::vector<uint8_t> v(std::max(1u, w->N), 0);
   for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = attr[p];
-  if (!w->pattr) { TRY(dev_alloc(&w->pattr, v.size())); drop_graphs(w); }
+  if (!w->pattr) TRY(dev_alloc(&w->pattr, v.size()));
   CK(cudaMemcpy(w->pattr, v.data(), v.size(), cudaMemcpyHostToDevice));
+  // the static subject list of LimitLongCommute
+  std::vector<uint32_t> subj;
+  for (uint32_t i = 0; i < w->N; ++i)
+    if (v[i] & JB_PA_LONG_COMMUTER) subj.push_back(i);
+  if (w->pol_subjects) { cudaFree(w->pol_subjects); w->pol_subjects = nullptr; }
+  w->n_pol_subjects = (uint32_t)subj.size();
+  if (!subj.empty()) TRY(dev_upload(&w->pol_subjects, subj.data(), subj.size(), w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);
   return JB_OK;
 }
 
@@ -1140,12 +1152,17 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     pa.pol_inject = (p.flags & JB_STEP_INJECT_POLICY) ? w->pol_inject : nullptr;
     pa.severe_mask = w->dis_host.severe_mask;
     const uint32_t chunks = (w->N + 15) / 16;
-    const bool full = w->n_pol != 0 || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
+    const bool full = (w->n_pol != 0 && !w->pol_subject_mode) || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
                       pa.cmt.person != nullptr || pa.cmt.inject != nullptr;
     if (full) k_place<true><<<(w->N + 255) / 256, 256, 0, s>>>(pa);
     else k_place<false><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     KCHECK("k_place", s);
     w->launches++;
+    if (!full && w->pol_subject_mode && w->n_pol_subjects) {
+      k_place_subjects<<<(w->n_pol_subjects + 255) / 256, 256, 0, s>>>(pa, w->pol_subjects, w->n_pol_subjects);
+      KCHECK("k_place_subjects", s);
+      w->launches++;
+    }
   }
   if (w->p2p_on) {
     k_halo_push<<<std::max(1u, (w->n_out + 255) / 256), 256, 0, s>>>(w->p2p, w->out_person, w->n_out, w->phot, w->susc, w->trans[w->trans_par],

@@ -194,3 +194,44 @@ def test_cuda_matches_oracle_with_lockdown_policies_and_leisure():
             stayed += int((((pa["pstate"] & 7) != 2) & has_primary & ((pa["pstate"] & 0x10) == 0)).sum())
         now += dt
     assert stayed > 20_000, "closures and shielding must keep people away from their primary activity"
+
+
+@pytest.mark.gpu
+def test_limit_long_commute_alone_uses_the_subject_list_and_equals_the_oracle():
+    """The default policy file keeps ``limit_long_commute`` always on (policy_covid19.yaml:129-135): the device
+    places everyone with the table-free fast path and re-evaluates only the long-distance commuters."""
+    assert have_gpu()
+    from june_b200.world import PA_LONG_COMMUTER
+    w = generate_world(50_000, seed=9, sector_betas=load_defaults()["company_sector_betas"])
+    rng = np.random.default_rng(3)
+    workers = np.nonzero((w.has_activity & 0b100) != 0)[0]
+    long_c = rng.choice(workers, 4000, replace=False)
+    w.person_attr = w.person_attr.copy() if w.person_attr is not None else np.zeros(w.n_people, np.uint8)
+    w.person_attr[long_c] |= PA_LONG_COMMUTER
+    (a, b), beta = engines(w, ["cuda", "oracle"])
+    recs = [dict(type=_lib.POL_LIMIT_LONG_COMMUTE, p=[0.3])]
+    seeds = np.sort(rng.choice(w.n_people, 2500, replace=False)).astype(np.uint32)
+    for e in (a, b):
+        e.set_individual_policies(recs, np.ones(w.n_regions))
+        e.infect(seeds, time=-6.0, seed=3, step=999)
+    now, skipped = 0.5, 0
+    launches0 = a.launch_count() if hasattr(a, "launch_count") else None
+    for i in range(8):
+        m, dt = (MASK_WORK & ~0b1000, 8 / 24) if i % 2 == 0 else (0b10001, 16 / 24)
+        flags = _lib.STEP_SEVERE_STAY_HOME | _lib.STEP_HOSPITALISATION
+        sa = a.step(a.make_params(now, dt, i, m, seed=4, flags=flags, beta=beta))
+        sb = b.step(b.make_params(now, dt, i, m, seed=4, flags=flags, beta=beta))
+        for key in ("n_new_infections", "n_infected", "n_draws", "n_by_activity", "n_no_activity"):
+            assert sa[key] == sb[key], (i, key, sa[key], sb[key])
+        pa, pb = a.fetch_person_state(), b.fetch_person_state()
+        assert np.array_equal(pa["pstate"], pb["pstate"]), f"step {i}"
+        if i % 2 == 0:
+            act = pa["pstate"][long_c] & 7
+            alive = (pa["pstate"][long_c] & 0x10) == 0
+            skipped += int(((act != 2) & alive).sum())
+            others = np.setdiff1d(workers, long_c)
+            healthy = (pa["pstate"][others] & 0x78) == 0
+            assert ((pa["pstate"][others] & 7)[healthy] == 2).all(), "nobody else is touched by the policy"
+        now += dt
+    # as in the reference, the activity is skipped when random() < going_to_work_probability (0.3)
+    assert 0.25 * 4 * 4000 < skipped < 0.36 * 4 * 4000, skipped
