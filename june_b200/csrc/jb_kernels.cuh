@@ -852,11 +852,24 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
     if (a.fuse_health) {
       // update_health_status also covers the infections created in this step
       // (epidemiology.py:217-303 runs after infect_people); k_health handles the older slots
-      HealthAcc acc = {0u, 0u, 0u};
-      jb_health_slot(a.h, slot, a.sp->t_now, a.sp->flags, a.summary, acc);
-      if (acc.inf) atomicAdd(&a.counters[CNT_INFECTED], acc.inf);
-      if (acc.hosp) atomicAdd(&a.counters[CNT_HOSP], acc.hosp);
-      if (acc.icu) atomicAdd(&a.counters[CNT_ICU], acc.icu);
+      // Common case decided from registers: still in its first stage, not yet infectious, not in a
+      // ward -> the update changes nothing but the "currently infected" counts (same result as the
+      // call below, without walking its code and re-reading the slot).
+      const double t_inf = a.sp->t_now - a.sp->now;
+      const bool quiet = med_p < 0 && nst > 1 && !(t_inf > tstage[0]) &&
+                         ((D.trans_type == JB_TRANS_GAMMA && t_inf < par[1]) ||
+                          (D.trans_type == JB_TRANS_XNEXP && !(t_inf > par[2])) || D.trans_type == JB_TRANS_CONSTANT);
+      if (quiet) {
+        if (D.trans_type == JB_TRANS_GAMMA) a.trans[p] = par[3] * 0.0;  // norm * gamma_pdf(x < loc)
+        atomicAdd(&a.counters[CNT_INFECTED], 1u);
+        atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_CUR_INFECTED], 1u);
+      } else {
+        HealthAcc acc = {0u, 0u, 0u};
+        jb_health_slot(a.h, slot, a.sp->t_now, a.sp->flags, a.summary, acc);
+        if (acc.inf) atomicAdd(&a.counters[CNT_INFECTED], acc.inf);
+        if (acc.hosp) atomicAdd(&a.counters[CNT_HOSP], acc.hosp);
+        if (acc.icu) atomicAdd(&a.counters[CNT_ICU], acc.icu);
+      }
     }
   }
 }
