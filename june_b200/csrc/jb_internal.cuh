@@ -316,6 +316,11 @@ struct JbWorld {
   // per-step parameter block: device copy + pinned ring (written by the host, copied h2d per step)
   unsigned char* d_step = nullptr;   // StepDev + beta table
   unsigned char* d_step_aux = nullptr;  // StepDev for jb_infect (seeding outside a step)
+  unsigned char* h_step_ring = nullptr;   // pinned, 4 slots of step_stride bytes; read by k_step_begin (zero copy)
+  uint32_t* d_step_ring = nullptr;        // the same memory as seen from the device
+  size_t step_stride = 0;
+  uint32_t* d_step_seq = nullptr;         // device-side count of executed k_step_begin (ring slot = count & 3)
+  uint32_t* d_h_counters = nullptr;       // h_counters as seen from the device
   unsigned char* h_step[4] = {};
   cudaEvent_t ev_step_buf[4] = {};
   size_t step_bytes = 0;

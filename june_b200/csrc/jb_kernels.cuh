@@ -1143,6 +1143,29 @@ __global__ void __launch_bounds__(256) k_vaccinate(const __grid_constant__ VaccA
   if (num != number_before) a.vac_dose[p] = (int8_t)num;
 }
 
+// First node of a step: block 0 pulls the step's parameter block out of the pinned host ring
+// (zero-copy reads over PCIe; the slot is chosen by a device-side step count that advances with every
+// execution, mirroring the host's), all blocks zero the per-step counters.  One kernel node instead of
+// a DMA copy and a memset node in front of the placement.
+__global__ void __launch_bounds__(256) k_step_begin(const uint32_t* host_ring, uint32_t slot_words, uint32_t* __restrict__ d_step,
+                                                    uint32_t n_words, uint32_t* __restrict__ seq,
+                                                    uint32_t* __restrict__ zero_base, uint32_t n_zero) {
+  if (blockIdx.x == 0) {
+    const uint32_t sq = *seq;
+    const volatile uint32_t* src = host_ring + (size_t)(sq & 3u) * slot_words;
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) d_step[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) *seq = sq + 1u;
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero_base[i] = 0u;
+}
+
+// Last node of a step: the counter block goes straight into pinned host memory (posted writes; visible
+// to the host once the stream has been synchronised).
+__global__ void __launch_bounds__(256) k_step_end(const uint32_t* __restrict__ counters, uint32_t n, uint32_t* host_out) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) host_out[i] = counters[i];
+}
+
 // Recompute the susceptibility codes kept in `pstate` after the host replaced susceptibilities.
 __global__ void k_refresh_codes(uint8_t* __restrict__ pstate, const double* __restrict__ susc, uint32_t N) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

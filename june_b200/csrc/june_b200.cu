@@ -322,11 +322,17 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     w->cub_tmp_bytes = b2 + 256;
     CK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
   }
+  w->step_stride = (w->step_bytes + 63) & ~(size_t)63;
+  CK(cudaHostAlloc((void**)&w->h_step_ring, 4 * w->step_stride, cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void**)&w->d_step_ring, w->h_step_ring, 0));
   for (int i = 0; i < 4; ++i) {
-    CK(cudaMallocHost((void**)&w->h_step[i], w->step_bytes));
+    w->h_step[i] = w->h_step_ring + i * w->step_stride;
     CK(cudaEventCreateWithFlags(&w->ev_step_buf[i], cudaEventDisableTiming));
   }
-  CK(cudaMallocHost((void**)&w->h_counters, sizeof(uint32_t) * (CNT_N + (size_t)w->R * JB_N_SUMMARY)));
+  TRY(dev_alloc(&w->d_step_seq, 1));
+  CK(cudaMemsetAsync(w->d_step_seq, 0, 4, s));
+  CK(cudaHostAlloc((void**)&w->h_counters, sizeof(uint32_t) * (CNT_N + (size_t)w->R * JB_N_SUMMARY), cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void**)&w->d_h_counters, w->h_counters, 0));
   memset(w->h_counters, 0, sizeof(uint32_t) * (CNT_N + (size_t)w->R * JB_N_SUMMARY));
   CK(cudaEventCreate(&w->ev_step0));
   CK(cudaEventCreate(&w->ev_step1));
@@ -389,11 +395,12 @@ extern "C" void jb_world_destroy(JbWorld* w) {
     if (t.list_c) cudaFree(t.list_c);
   }
   for (int i = 0; i < 4; ++i) {
-    if (w->h_step[i]) cudaFreeHost(w->h_step[i]);
     if (w->ev_step_buf[i]) cudaEventDestroy(w->ev_step_buf[i]);
   }
   for (JbWorld::GraphEntry& e : w->graphs) cudaGraphExecDestroy(e.exec);
   if (w->h_counters) cudaFreeHost(w->h_counters);
+  if (w->h_step_ring) cudaFreeHost(w->h_step_ring);
+  if (w->d_step_seq) cudaFree(w->d_step_seq);
   if (w->ev_step0) cudaEventDestroy(w->ev_step0);
   if (w->ev_step1) cudaEventDestroy(w->ev_step1);
   if (w->ev_int0) cudaEventDestroy(w->ev_int0);
@@ -1129,7 +1136,14 @@ static int timing_end(JbWorld* w, cudaStream_t s) {
 static int enqueue_begin(JbWorld* w, void* d_send) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
-  CK(cudaMemsetAsync(w->counters + CNT_STEP_BEGIN, 0, (w->counter_words - CNT_STEP_BEGIN) * 4, s));
+  {
+    const uint32_t n_zero = (uint32_t)(w->counter_words - CNT_STEP_BEGIN);
+    k_step_begin<<<std::max(1u, std::min(148u, (n_zero + 1023) / 1024)), 256, 0, s>>>(
+        w->d_step_ring, (uint32_t)(w->step_stride / 4), reinterpret_cast<uint32_t*>(w->d_step), (uint32_t)((w->step_bytes + 3) / 4),
+        w->d_step_seq, w->counters + CNT_STEP_BEGIN, n_zero);
+    KCHECK("k_step_begin", s);
+    w->launches++;
+  }
   if (p.flags & JB_STEP_RECORD_LAMBDA) {
     k_fill_f64<<<(w->NP + 255) / 256, 256, 0, s>>>(w->lambda, w->NP, std::numeric_limits<double>::quiet_NaN());
     w->launches++;
@@ -1309,7 +1323,9 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
     }
   }
   if (!fused_finish(w)) TRY(launch_health(w, s));
-  CK(cudaMemcpyAsync(w->h_counters, w->counters, (CNT_N + (size_t)w->R * JB_N_SUMMARY) * 4, cudaMemcpyDeviceToHost, s));
+  k_step_end<<<1, 256, 0, s>>>(w->counters, (uint32_t)(CNT_N + (size_t)w->R * JB_N_SUMMARY), w->d_h_counters);
+  KCHECK("k_step_end", s);
+  w->launches++;
   return JB_OK;
 }
 
@@ -1377,16 +1393,15 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   TRY(timing_begin(w, s));
   if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
   TRY(ensure_event_buffers(w, p->flags));
-  // per-step parameter block: pinned ring slot -> device (the h2d payload of every step)
+  // per-step parameter block: written into a pinned ring slot, pulled by k_step_begin (the h2d payload of every step)
   const int slot = (int)(w->step_seq++ & 3);
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));  // the copy that last used this slot has finished
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
   h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
-  CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
-  CK(cudaEventRecord(w->ev_step_buf[slot], s));
   TRY(run_phase(w, 0, d_send, nullptr, [&]() { return enqueue_begin(w, d_send); }));
+  CK(cudaEventRecord(w->ev_step_buf[slot], s));  // k_step_begin has read the slot once this fires
   w->in_step = true;
   return JB_OK;
 }
@@ -1459,13 +1474,12 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
   h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
-  CK(cudaMemcpyAsync(w->d_step, w->h_step[slot], w->step_bytes, cudaMemcpyHostToDevice, s));
-  CK(cudaEventRecord(w->ev_step_buf[slot], s));
   TRY(run_phase(w, 3, nullptr, nullptr, [&]() {
     TRY(enqueue_begin(w, nullptr));
     TRY(enqueue_interact(w, nullptr, nullptr));
     return enqueue_finish(w, nullptr);
   }));
+  CK(cudaEventRecord(w->ev_step_buf[slot], s));
   w->in_step = true;  // jb_step_finish_tail expects it
   TRY(timing_end(w, s));
   w->in_step = false;
