@@ -143,6 +143,7 @@ __device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, uint32_t p, 
 // instantiation, so that the rare blame path costs the common launch neither registers nor stack.
 template <int VM, int WPG, bool EV>
 __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ GroupArgs a) {
+  jb_stamp(3); jb_stamp(4);
   extern __shared__ __align__(8) unsigned char smem_raw[];
   constexpr int GT = 32 * WPG;                 // threads per group
   constexpr int GPC = JB_CTA_WARPS / WPG;      // groups per CTA
@@ -428,6 +429,7 @@ template <bool STREAM, int VM, bool EV>
 // (stream tiles are occupancy hungry: 48 registers measured 20 % faster than 70; the gather
 // flavour keeps its registers for the 16 gathers in flight per thread)
 __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(const __grid_constant__ GroupArgs a) {
+  if (STREAM) jb_stamp(2);
   __shared__ uint2 s_items[JB_TILE_ITEMS];  // {(block-local first slot << 5) | (len - 1), group}
   __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
   __shared__ uint32_t s_mem[STREAM ? 1 : JB_TILE_SLOTS];

@@ -109,6 +109,37 @@ struct CommuteDev {
 // Per-step scalars, resident on the device so that a captured CUDA graph of the step can be
 // replayed: one h2d copy from a pinned ring buffer precedes every step.  The processed beta
 // table [n_beta][n_regions] follows the struct in the same allocation.
+// Debug timeline (JB_STAMPS=1): every kernel's first thread stamps %globaltimer at entry; printed per
+// step shape when the world is destroyed.  IDs: 0 begin, 1 place, 2 tiles, 3 groups (first), 4 groups
+// (last), 5 health, 6 newinf, 7 end.
+__device__ unsigned long long* g_stamps = nullptr;
+__device__ unsigned int g_stamp_seq = 0;
+#define JB_STAMP_RING 256
+__device__ __forceinline__ unsigned long long jb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void jb_stamp(int id) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long* s = g_stamps;
+    if (s) {
+      const unsigned long long t = jb_globaltimer();
+      unsigned long long* slot = s + (size_t)(g_stamp_seq % JB_STAMP_RING) * 8;
+      if (id == 0) {
+        const unsigned int q = ++g_stamp_seq;
+        slot = s + (size_t)(q % JB_STAMP_RING) * 8;
+        for (int k = 1; k < 8; ++k) slot[k] = (k == 4) ? 0ull : ~0ull;
+        slot[0] = t;
+      } else if (id == 4) {
+        atomicMax(slot + 4, t);
+      } else {
+        atomicMin(slot + id, t);
+      }
+    }
+  }
+}
+
 struct StepDev {
   double now, dt, t_now;
   uint64_t seed;
@@ -319,6 +350,7 @@ struct JbWorld {
   unsigned char* h_step_ring = nullptr;   // pinned, 4 slots of step_stride bytes; read by k_step_begin (zero copy)
   uint32_t* d_step_ring = nullptr;        // the same memory as seen from the device
   size_t step_stride = 0;
+  unsigned long long* stamps = nullptr;    // JB_STAMPS=1 debug timeline
   uint32_t* d_step_seq = nullptr;         // device-side count of executed k_step_begin (ring slot = count & 3)
   uint32_t* d_h_counters = nullptr;       // h_counters as seen from the device
   unsigned char* h_step[4] = {};

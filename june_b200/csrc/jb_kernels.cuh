@@ -234,6 +234,7 @@ __device__ __forceinline__ uint32_t jb_place_key(uint32_t st, uint32_t has) {
 // table lookup per byte (the common weekday-night / no-lockdown step keeps its 48 registers).
 template <bool FULL>
 __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
+  jb_stamp(1);
   __shared__ uint8_t s_act[512];      // 0..4 activity, 7 none (dead), 15 alive without any activity
   __shared__ uint32_t s_cnt[8];
   const uint32_t mask = a.sp->activity_mask, flags = a.sp->flags;
@@ -656,6 +657,7 @@ __device__ __forceinline__ void jb_health_body(const HealthArgs& a, uint32_t bid
 }
 
 __global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthArgs a) {
+  jb_stamp(5);
   jb_health_body(a, blockIdx.x, gridDim.x);
 }
 
@@ -875,6 +877,7 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
 }
 
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
+  jb_stamp(6);
   jb_newinf_body(a, D, blockIdx.x, gridDim.x);
 }
 
@@ -1150,6 +1153,7 @@ __global__ void __launch_bounds__(256) k_vaccinate(const __grid_constant__ VaccA
 __global__ void __launch_bounds__(256) k_step_begin(const uint32_t* host_ring, uint32_t slot_words, uint32_t* __restrict__ d_step,
                                                     uint32_t n_words, uint32_t* __restrict__ seq,
                                                     uint32_t* __restrict__ zero_base, uint32_t n_zero) {
+  jb_stamp(0);
   if (blockIdx.x == 0) {
     const uint32_t sq = *seq;
     const volatile uint32_t* src = host_ring + (size_t)(sq & 3u) * slot_words;
@@ -1163,6 +1167,7 @@ __global__ void __launch_bounds__(256) k_step_begin(const uint32_t* host_ring, u
 // Last node of a step: the counter block goes straight into pinned host memory (posted writes; visible
 // to the host once the stream has been synchronised).
 __global__ void __launch_bounds__(256) k_step_end(const uint32_t* __restrict__ counters, uint32_t n, uint32_t* host_out) {
+  jb_stamp(7);
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) host_out[i] = counters[i];
 }
 

@@ -329,6 +329,13 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     w->h_step[i] = w->h_step_ring + i * w->step_stride;
     CK(cudaEventCreateWithFlags(&w->ev_step_buf[i], cudaEventDisableTiming));
   }
+  if (jb_env_flag("JB_STAMPS", 0)) {
+    unsigned long long* st = nullptr;
+    CK(cudaMalloc((void**)&st, JB_STAMP_RING * 8 * 8));
+    CK(cudaMemset(st, 0xFF, JB_STAMP_RING * 8 * 8));
+    CK(cudaMemcpyToSymbol(g_stamps, &st, sizeof(st)));
+    w->stamps = st;
+  }
   TRY(dev_alloc(&w->d_step_seq, 1));
   CK(cudaMemsetAsync(w->d_step_seq, 0, 4, s));
   CK(cudaHostAlloc((void**)&w->h_counters, sizeof(uint32_t) * (CNT_N + (size_t)w->R * JB_N_SUMMARY), cudaHostAllocMapped));
@@ -398,6 +405,31 @@ extern "C" void jb_world_destroy(JbWorld* w) {
     if (w->ev_step_buf[i]) cudaEventDestroy(w->ev_step_buf[i]);
   }
   for (JbWorld::GraphEntry& e : w->graphs) cudaGraphExecDestroy(e.exec);
+  if (w->stamps) {
+    // average start offsets (us, relative to k_step_begin) over the recorded steps, split by whether the step
+    // ran a gather-tile / company kernel (primary-activity steps are longer)
+    std::vector<unsigned long long> h(JB_STAMP_RING * 8);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h.data(), w->stamps, h.size() * 8, cudaMemcpyDeviceToHost);
+    double acc[8] = {0}; int n = 0; double total = 0; int nt = 0;
+    for (int r = 0; r < JB_STAMP_RING; ++r) {
+      const unsigned long long* q = &h[(size_t)r * 8];
+      bool ok = q[0] != ~0ull;
+      for (int k = 1; k < 8; ++k) ok = ok && q[k] != ~0ull && q[k] != 0ull;
+      if (!ok) continue;
+      for (int k = 0; k < 8; ++k) acc[k] += (double)(q[k] - q[0]) * 1e-3;
+      ++n;
+      const unsigned long long* nx = &h[(size_t)((r + 1) % JB_STAMP_RING) * 8];
+      if (nx[0] != ~0ull && nx[0] > q[0] && nx[0] - q[0] < 1000000ull) { total += (double)(nx[0] - q[0]) * 1e-3; ++nt; }
+    }
+    if (n) {
+      fprintf(stderr, "[jb stamps] %d steps: place %.1f tiles %.1f groups_first %.1f groups_last %.1f health %.1f newinf %.1f end %.1f | begin-to-begin %.1f us (%d)\n",
+              n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n, acc[7] / n, nt ? total / nt : 0.0, nt);
+    }
+    unsigned long long* null_ptr = nullptr;
+    cudaMemcpyToSymbol(g_stamps, &null_ptr, sizeof(null_ptr));
+    cudaFree(w->stamps);
+  }
   if (w->h_counters) cudaFreeHost(w->h_counters);
   if (w->h_step_ring) cudaFreeHost(w->h_step_ring);
   if (w->d_step_seq) cudaFree(w->d_step_seq);
@@ -1260,9 +1292,11 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   const bool health_beside = fused_finish(w);
   static const int health_early = jb_env_flag("JB_HEALTH_EARLY", 1);
   static const int health_blocks = jb_env_flag("JB_HEALTH_BLOCKS", 4);
-  auto fork_health = [&]() -> int {
+  auto fork_health = [&](int phase) -> int {  // phase 1: dependency point only; 2: launch only; 3: both
     cudaStream_t hs = w->serial ? s : w->side_health;
-    if (!w->serial) { CK(cudaEventRecord(w->ev_fork_health, s)); CK(cudaStreamWaitEvent(hs, w->ev_fork_health, 0)); }
+    if (!w->serial && (phase & 1)) CK(cudaEventRecord(w->ev_fork_health, s));
+    if (!(phase & 2)) return JB_OK;
+    if (!w->serial) CK(cudaStreamWaitEvent(hs, w->ev_fork_health, 0));
     const HealthArgs ha = make_health_args(w, 1);
     k_health<<<148 * health_blocks, 256, 0, hs>>>(ha);
     KCHECK("k_health", hs);
@@ -1270,8 +1304,12 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     if (!w->serial) CK(cudaEventRecord(w->ev_join_health, hs));
     return JB_OK;
   };
-  if (health_beside && health_early) TRY(fork_health());
+  // the kernels that become ready together are started in the order their nodes were created: the
+  // interaction kernels (the critical path) first, the health update (which has slack) last
+  if (health_beside && health_early == 1) TRY(fork_health(3));
+  if (health_beside && health_early == 2) TRY(fork_health(1));
   TRY(launch_groups(w, 0));
+  if (health_beside && health_early == 2) TRY(fork_health(2));
   if (w->timing >= 2) CK(cudaEventRecord(w->ev_int1, s));
   // create infections for residents infected here; flag halo persons for their home domain
   if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS) || w->H) {
@@ -1280,7 +1318,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     a.cap = w->newinf_cap; a.sp = step_dev(w);
     a.halo_ret = (uint8_t*)d_ret_send;
     a.fuse_health = 1; a.h = make_health_args(w, 0);
-    if (health_beside && !health_early) TRY(fork_health());
+    if (health_beside && !health_early) TRY(fork_health(3));
     k_newinf<<<148 * 8, 128, 0, s>>>(a, w->dis_host);
     KCHECK("k_newinf", s);
     w->launches++;
