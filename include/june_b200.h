@@ -253,6 +253,12 @@ int jb_inject_uniforms(JbWorld* w, const double* u, size_t n);
 int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* variants, size_t n,
               double time, uint64_t seed, uint32_t step);
 
+/* Activities (bit a = JB_ACT_a) under which halo persons are registered in ANY domain; every rank must pass
+ * the same value (OR over the ranks of the activities of registrations whose member is a halo person).  A step
+ * whose activity mask does not intersect it exchanges nothing: commuters who are at home are present in no
+ * group of another domain (the reference still sends its empty MovablePeople buffers,
+ * activity_manager.py:404-447), and such a step may be run with jb_step on any world.  Default: all activities. */
+int jb_set_halo_activities(JbWorld* w, uint32_t activity_mask);
 /* Restore person.subgroups.medical_facility: medical[n_people] = (hospital group << 8 | ward subgroup) or -1.
  * The reference's checkpoint does not carry it (patients are simply re-admitted by the next
  * Hospitalisation.apply, hdf5_savers/checkpoint_saver.py:162-218); it is restorable here so that a resumed

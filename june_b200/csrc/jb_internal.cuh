@@ -297,6 +297,7 @@ struct JbWorld {
   uint32_t hev_cap = 0;
   uint32_t* pol_subjects = nullptr;                      // long-distance commuters (subjects of LimitLongCommute)
   uint32_t n_pol_subjects = 0;
+  uint32_t halo_act_mask = 0xFFFFFFFFu;                  // activities under which halo persons are registered anywhere (jb_set_halo_activities)
   bool pol_subject_mode = false;                         // every active individual policy has a static subject list
   int32_t* pres_group = nullptr;                         // residence group of every resident (death location)  // events of the last step that recorded them
   double* beta = nullptr;

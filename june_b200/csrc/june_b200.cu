@@ -488,6 +488,16 @@ extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const doub
   return JB_OK;
 }
 
+static void drop_graphs(JbWorld* w);
+extern "C" int jb_set_halo_activities(JbWorld* w, uint32_t activity_mask) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  w->halo_act_mask = activity_mask;
+  drop_graphs(w);
+  return JB_OK;
+}
+
 extern "C" int jb_set_medical(JbWorld* w, const int32_t* medical) {
   if (!w || !medical) { jb_set_error("null argument"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
@@ -1165,6 +1175,7 @@ static int timing_end(JbWorld* w, cudaStream_t s) {
 
 // ---- device work of the three step phases (no host synchronisation: capturable) ----------
 
+static inline bool halo_step(const JbWorld* w);
 static int enqueue_begin(JbWorld* w, void* d_send) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
@@ -1210,12 +1221,12 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
       w->launches++;
     }
   }
-  if (w->p2p_on) {
+  if (w->p2p_on && halo_step(w)) {
     k_halo_push<<<std::max(1u, (w->n_out + 255) / 256), 256, 0, s>>>(w->p2p, w->out_person, w->n_out, w->phot, w->susc, w->trans[w->trans_par],
                                                                     w->NP, (int)w->V, step_dev(w), w->p2p_done);
     KCHECK("k_halo_push", s);
     w->launches++;
-  } else if (w->n_out && d_send) {
+  } else if (w->n_out && d_send && halo_step(w)) {
     k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->phot, w->susc, w->trans[w->trans_par],
                                                        w->NP, (int)w->V, (unsigned char*)d_send);
     KCHECK("k_halo_pack", s);
@@ -1230,8 +1241,16 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
 // later in the step and get their first update from k_newinf as well.  (With host-issued
 // collectives the step is three separately captured phases and k_health runs in the last one; when
 // the host creates the infections, JB_STEP_NO_NEW_INFECTIONS, k_health walks every slot there.)
+// Does this step exchange halo persons?  Only when one of the activities under which halo persons are
+// registered (in any domain) takes place: a commuter at home is present in no group of the other domain,
+// and the supergroups that hold halo registrations are not even processed.
+static inline bool halo_step_for(const JbWorld* w, uint32_t activity_mask) {
+  return (w->H || w->n_out) && (activity_mask & w->halo_act_mask) != 0u;
+}
+static inline bool halo_step(const JbWorld* w) { return halo_step_for(w, w->cur.activity_mask); }
+
 static inline bool fused_finish(const JbWorld* w) {
-  return (!(w->H || w->n_out) || w->p2p_on) && !(w->cur.flags & JB_STEP_NO_NEW_INFECTIONS);
+  return (!halo_step(w) || w->p2p_on) && !(w->cur.flags & JB_STEP_NO_NEW_INFECTIONS);
 }
 
 static HealthArgs make_health_args(JbWorld* w, int old_only) {
@@ -1265,14 +1284,15 @@ static int launch_health(JbWorld* w, cudaStream_t s) {
 static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
-  if (w->p2p_on) {
+  const bool halo_now = halo_step(w);
+  if (w->p2p_on && halo_now) {
     d_recv = w->p2p.recv[w->p2p.rank];
     d_ret_send = w->p2p_ret_local;
     k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_people[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters, w->p2p_done + 2);
     KCHECK("k_halo_wait", s);
     w->launches++;
   }
-  if (w->H && d_recv) {
+  if (w->H && d_recv && halo_now) {
     k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
                                                      w->phot, w->susc, w->trans[w->trans_par], (uint8_t*)d_ret_send);
     KCHECK("k_halo_unpack", s);
@@ -1312,7 +1332,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   if (health_beside && health_early == 2) TRY(fork_health(2));
   if (w->timing >= 2) CK(cudaEventRecord(w->ev_int1, s));
   // create infections for residents infected here; flag halo persons for their home domain
-  if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS) || w->H) {
+  if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS) || (w->H && halo_now)) {
     NewInfArgs a = make_newinf_args(w);
     a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_NEWINF;
     a.cap = w->newinf_cap; a.sp = step_dev(w);
@@ -1324,7 +1344,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     w->launches++;
   }
   if (health_beside && !w->serial) CK(cudaStreamWaitEvent(s, w->ev_join_health, 0));
-  if (w->p2p_on) {
+  if (w->p2p_on && halo_now) {
     k_halo_ret_push<<<std::max(1u, (w->H + 255) / 256), 256, 0, s>>>(w->p2p, w->p2p_ret_local, w->H, step_dev(w), w->p2p_done + 1);
     KCHECK("k_halo_ret_push", s);
     w->launches++;
@@ -1335,13 +1355,14 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
 static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
-  if (w->p2p_on) {
+  const bool halo_now = halo_step(w);
+  if (w->p2p_on && halo_now) {
     d_ret_recv = w->p2p.ret[w->p2p.rank];
     k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_ret[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters, w->p2p_done + 2);
     KCHECK("k_halo_wait(ret)", s);
     w->launches++;
   }
-  if (w->n_out && d_ret_recv) {
+  if (w->n_out && d_ret_recv && halo_now) {
     // residents infected abroad: reuse the new-infection list
     // (tell_domains_to_infect, epidemiology.py:359-401)
     CK(cudaMemsetAsync(w->counters + CNT_HALO_INF, 0, 4, s));
@@ -1490,7 +1511,7 @@ extern "C" int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* o
 
 // Single-GPU step: the three phases are captured as ONE graph.
 extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
-  if (w && (w->H || w->n_out) && !w->p2p_on) {  // host-issued collectives run between the phases
+  if (w && p && halo_step_for(w, p->activity_mask) && !w->p2p_on) {  // host-issued collectives run between the phases
     TRY(jb_step_begin(w, p, nullptr));
     TRY(jb_step_interact(w, nullptr, nullptr));
     return jb_step_finish(w, nullptr, out);

@@ -266,6 +266,10 @@ class Engine:
             susceptibility = np.ascontiguousarray(susceptibility, dtype=np.float64).reshape(self.n_variants, self.world.n_people)
         self._check(self._f("set_person_state")(self._h, ptr(pstate), ptr(susceptibility)))
 
+    def set_halo_activities(self, activity_mask: int):
+        """Activities under which halo persons are registered in any domain (same value on every rank)."""
+        self._check(self._f("set_halo_activities")(self._h, int(activity_mask)))
+
     def set_medical(self, medical: np.ndarray):
         """Restore ``person.subgroups.medical_facility`` (``hospital group << 8 | ward``, -1 = none); call
         before ``upload_infections``."""

@@ -207,6 +207,17 @@ class Simulator:
                                      device=torch.device("cuda", self.device.device_index) if on_gpu else None)
         self._ext_stream = None
         self.p2p = False
+        self.halo_activity_mask = 0
+        if self.halo is not None:
+            # activities under which halo persons are registered, OR-ed over the ranks: only steps with one
+            # of them exchange anything (a commuter at home is present in no group of another domain)
+            import torch
+            halo_regs = world.reg_member >= world.n_people
+            local = int(np.bitwise_or.reduce(1 << ((world.reg_info[halo_regs].astype(np.int64) >> 8) & 7))) if halo_regs.any() else 0
+            masks = [None] * self.halo.dist.get_world_size()
+            self.halo.dist.all_gather_object(masks, local)
+            self.halo_activity_mask = int(np.bitwise_or.reduce(np.array(masks, np.int64)))
+            self.device.set_halo_activities(self.halo_activity_mask)
         if self.halo is not None and isinstance(self.device, DeviceWorld) and os.environ.get("JB_HALO", "p2p") != "nccl":
             self._connect_peer_windows()
         if self.halo is not None and isinstance(self.device, DeviceWorld):
@@ -348,7 +359,7 @@ class Simulator:
             return  # simulator.py:377-379
         params = self.step_params(_lib.STEP_RECORD_EVENTS if self.record is not None else 0)
         dev = self.device
-        if self.halo is None or self.p2p:
+        if self.halo is None or self.p2p or not (self.activity_manager.activity_mask() & self.halo_activity_mask):
             stats = dev.step(params, want_stats=want_stats)
         elif self._ext_stream is not None:
             # GPU ranks: the NCCL all-to-alls are issued with the library's stream current, so
