@@ -219,8 +219,18 @@ def run_gpu(args):
     sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
+    align = None
+    if dist is not None and sim._ext_stream is not None:
+        # Only one step in five exchanges halo persons, so queued ranks drift apart between exchanges and a
+        # rank that reaches the next exchange early would count its peer's L2 flush (which is outside every
+        # bracket) as step time.  A one-word all-reduce on the library's stream, between the flush and the
+        # step's bracket, lines the ranks up on the device -- no host synchronisation, not timed.
+        align = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", local_rank))
     for k in range(args.steps):
         dev.flush_l2()
+        if align is not None:
+            with torch.cuda.stream(sim._ext_stream):
+                dist.all_reduce(align)
         sim.do_timestep(want_stats=(k == args.steps - 1))
         next(sim.timer)
     barrier()
@@ -329,7 +339,7 @@ def run_gpu(args):
                                + "), default 5/4-step day schedule, ~3% seeded prevalence",
                    "people_per_gpu": n_people, "people_total": n_people * world_size,
                    "l2": "flushed between steps (256 MiB memset on the library stream, outside the event brackets)",
-                   "parallelism": "1 domain per GPU" + (", halo all-to-all over NCCL" if world_size > 1 else "")},
+                   "parallelism": "1 domain per GPU" + (", halo exchange over peer memory on primary-activity steps; ranks aligned by a one-word all-reduce before each timed bracket" if world_size > 1 else "")},
         "e2e": {"value": e2e_ps / (e2e_ms * 1e-3), "unit": "person-timesteps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
