@@ -248,7 +248,7 @@ def make_b200_simulator_class(reference_simulator_cls):
             for a in activities:
                 if a in ACTIVITY_CODES:
                     mask |= 1 << ACTIVITY_CODES[a]
-            flags = 0
+            flags = _lib.STEP_RECORD_EVENTS if self.record is not None else 0
             if pol is not None:
                 date = self.timer.date
                 if any(type(p).__name__ == "SevereSymptomsStayHome" and p.is_active(date) for p in pol.individual_policies.policies):
@@ -262,6 +262,52 @@ def make_b200_simulator_class(reference_simulator_cls):
             self.b200_last_stats = self._eng.step(params)
             self._step += 1
             self._b200_write_back()
+            if self.record is not None:
+                self._b200_feed_record()
+
+        # ---- device events -> the reference's Record (records_writer.py:203-246) ----------------------
+        def _b200_feed_record(self):
+            """What the reference's stages accumulate during a step, fed from the device's event lists with the
+            reference's own keyword arguments: ``infections`` (``interaction.py:664-683``, one call per location),
+            ``symptoms`` / ``deaths`` / ``recoveries`` (``epidemiology.py:176-186,209-214,256-266``),
+            ``hospital_admissions`` / ``icu_admissions`` / ``discharges`` (``medical_care_policies.py:463-515``);
+            then ``summarise_time_step`` / ``time_step`` as ``Epidemiology.do_timestep`` does (``:161-166``)."""
+            soa, rec = self._soa, self.record
+            if not hasattr(self, "_b200_grp_sg"):
+                self._b200_grp_sg = soa.group_supergroup()
+            grp_sg = self._b200_grp_sg
+            iid = self._selector.infection_class.infection_id()
+            pid = lambda i: self._people[int(i)].id
+            gspec = lambda g: soa.supergroups[grp_sg[g]].spec
+            gid = lambda g: int(soa.group_ids[g])
+            ev = self._eng.fetch_infection_events()
+            if len(ev["infected"]):
+                order = np.argsort(ev["group"], kind="stable")
+                groups = ev["group"][order]
+                cuts = np.nonzero(np.diff(groups))[0] + 1
+                for sel in np.split(order, cuts):
+                    g = int(ev["group"][sel[0]])
+                    rec.accumulate(table_name="infections", location_spec=gspec(g), location_id=gid(g),
+                                   region_name=soa.region_names[int(soa.grp_info[g] >> 16)],
+                                   infected_ids=[pid(i) for i in ev["infected"][sel]], infection_ids=[iid] * len(sel),
+                                   infector_ids=[pid(i) for i in ev["infector"][sel]])
+            hev = self._eng.fetch_health_events()
+            for p, k, g in zip(hev["person"], hev["kind"], hev["group"]):
+                k, g = int(k), int(g)
+                if k == 1:
+                    rec.accumulate(table_name="deaths", location_spec=gspec(g), location_id=gid(g), dead_person_id=pid(p))
+                elif k == 2:
+                    rec.accumulate(table_name="recoveries", recovered_person_id=pid(p), infection_id=iid)
+                elif k == 3:
+                    rec.accumulate(table_name="hospital_admissions", hospital_id=gid(g), patient_id=pid(p))
+                elif k == 4:
+                    rec.accumulate(table_name="icu_admissions", hospital_id=gid(g), patient_id=pid(p))
+                elif k == 5:
+                    rec.accumulate(table_name="discharges", hospital_id=gid(g), patient_id=pid(p))
+                elif k == 6:
+                    rec.accumulate(table_name="symptoms", infected_id=pid(p), symptoms=g, infection_id=iid)
+            rec.summarise_time_step(timestamp=self.timer.date, world=self.world)
+            rec.time_step(timestamp=self.timer.date)
 
         def clear_world(self):
             """The reference empties every subgroup list after each step (``simulator.py:305-343``).

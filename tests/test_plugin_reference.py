@@ -89,3 +89,62 @@ def test_reference_simulator_subclass_with_leisure_commute_and_lockdown():
     assert sim._soa.has_leisure and sim._soa.leisure_activities == ["pub", "cinema", "grocery"]
     assert seen["leisure"] > 1000, "people must have gone to pubs / cinemas / groceries"
     assert seen["skipped_work"] >= 1, "CloseCompanies / CloseSchools must keep people away from work"
+
+
+def test_reference_simulator_subclass_feeds_the_record():
+    """With a ``record``, the subclass reports the step's events through ``Record.accumulate`` with the
+    reference's own table names and keyword arguments (a duck-typed recorder: PyTables is absent here)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_world
+    from june_b200.june_plugin import make_b200_simulator_class
+    from helpers import make_engine
+
+    class Recorder:
+        record_static_data = False
+
+        def __init__(self):
+            self.rows, self.steps, self.summaries = {}, 0, 0
+
+        def accumulate(self, table_name, **kw):
+            self.rows.setdefault(table_name, []).append(kw)
+
+        def summarise_time_step(self, timestamp, world):
+            self.summaries += 1
+
+        def time_step(self, timestamp):
+            self.steps += 1
+
+        def parameters(self, **kw):
+            pass
+
+        def combine_outputs(self):
+            pass
+
+    random.seed(6)
+    np.random.seed(6)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        world, dc = ref_world.build_world(2000, seed=6)
+        ref_sim = ref_world.make_simulator(world, dc, total_days=25, cases_per_capita=0.15, schedule="simple")
+    from june.simulator import Simulator
+    B200Simulator = make_b200_simulator_class(Simulator)
+    B200Simulator.b200_engine = staticmethod(lambda soa, inter, dcfg, prob: make_engine("oracle", soa, prob, interaction=inter, disease=dcfg))
+    rec = Recorder()
+    sim = B200Simulator(world=world, interaction=ref_sim.interaction, timer=ref_sim.timer,
+                        activity_manager=ref_sim.activity_manager, epidemiology=ref_sim.epidemiology,
+                        tracker=None, record=rec)
+    with contextlib.redirect_stdout(sink):
+        sim.run()
+    people = {p.id: p for p in world.people}
+    assert rec.steps == rec.summaries == sim._step
+    inf = [r for r in rec.rows["infections"] if r["location_spec"] != "infection_seed"]
+    assert sum(len(r["infected_ids"]) for r in inf) > 300
+    specs = {g.spec for sg in ("households", "companies", "schools", "care_homes", "hospitals") for g in getattr(world, sg).members}
+    for r in inf:
+        assert r["location_spec"] in specs and len(r["infected_ids"]) == len(r["infector_ids"]) == len(r["infection_ids"])
+        assert all(i in people for i in r["infected_ids"] + r["infector_ids"])
+    dead = {p.id for p in world.people if p.dead}
+    assert {r["dead_person_id"] for r in rec.rows.get("deaths", [])} == dead and len(dead) > 0
+    hospital_ids = {h.id for h in world.hospitals.members}
+    assert all(r["hospital_id"] in hospital_ids for t in ("hospital_admissions", "icu_admissions", "discharges") for r in rec.rows.get(t, []))
+    assert len(rec.rows["recoveries"]) > 100 and len(rec.rows["symptoms"]) > 500 and len(rec.rows["hospital_admissions"]) > 0
