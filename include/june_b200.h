@@ -259,6 +259,17 @@ int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* variants, siz
  * group of another domain (the reference still sends its empty MovablePeople buffers,
  * activity_manager.py:404-447), and such a step may be run with jb_step on any world.  Default: all activities. */
 int jb_set_halo_activities(JbWorld* w, uint32_t activity_mask);
+/* Variants (infection classes): per-variant transmission-parameter distributions trans_par[n_variants][6]
+ * (the reference gives every infection class its own selector, infection_selector.py:44-144; b117.yaml differs
+ * from covid19.yaml in max_infectiousness) and cross immunity (Infection.immunity_ids, infection.py:136-191):
+ * bit u of cross_immunity[v] set = an infection with variant v leaves the person immune to variant u.
+ * Either pointer may be null.  Defaults: every variant samples from JbDisease.trans_par and protects against all. */
+int jb_set_variants(JbWorld* w, uint32_t n_variants, const JbDist* trans_par, const uint32_t* cross_immunity);
+/* Mutation event (event/mutation.py:9-66): every current infection of a resident of region r becomes `variant`
+ * with probability regional_probability[r] (uniform: Philox stream 7 of (seed, step, person)): a complete new
+ * infection of that variant is sampled and only its transmission is kept -- symptoms and start time stay, the
+ * transmission probability restarts at its initial value until the next health update. */
+int jb_mutate(JbWorld* w, uint32_t variant, const double* regional_probability, uint64_t seed, uint32_t step);
 /* Restore person.subgroups.medical_facility: medical[n_people] = (hospital group << 8 | ward subgroup) or -1.
  * The reference's checkpoint does not carry it (patients are simply re-admitted by the next
  * Hospitalisation.apply, hdf5_savers/checkpoint_saver.py:162-218); it is restorable here so that a resumed

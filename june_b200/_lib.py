@@ -138,7 +138,7 @@ ABI_SYMBOLS = [
     "set_individual_policies", "set_person_attributes", "inject_policy_uniforms", "fetch_infection_events",
     "set_commute", "inject_commute",
     "set_vaccination", "vaccinate", "inject_vaccination_uniforms", "fetch_vaccination",
-    "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities",
+    "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities", "set_variants", "mutate",
 ]
 
 
@@ -204,6 +204,8 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("flush_l2").argtypes = [vp, C.c_size_t]
     f("set_medical").argtypes = [vp, vp]
     f("set_halo_activities").argtypes = [vp, C.c_uint32]
+    f("set_variants").argtypes = [vp, C.c_uint32, vp, vp]
+    f("mutate").argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32]
     f("fetch_health_events").argtypes = [vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     f("p2p_window").argtypes = [vp, vp]
     f("p2p_connect").argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]

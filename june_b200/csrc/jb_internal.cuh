@@ -215,6 +215,8 @@ struct DiseaseDev {
   JbDist traj_stage_time[16][JB_MAX_STAGES];
   int trans_type;
   JbDist trans_par[6];
+  JbDist trans_par_v[JB_MAX_VARIANTS][6];   // per-variant distributions (copies of trans_par unless jb_set_variants)
+  uint32_t cross[JB_MAX_VARIANTS];          // bit u of cross[v]: an infection with v protects against u
 };
 
 // Tile decomposition of one supergroup (built once at world create).

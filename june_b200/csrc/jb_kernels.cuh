@@ -689,6 +689,8 @@ struct NewInfArgs {
   uint32_t* summary;        // [R][JB_N_SUMMARY]
   const uint8_t* pregion;
   uint8_t* halo_ret;        // per halo person: variant+1 if infected here (or null)
+  int mutate;               // 1: Mutation event -- the listed people are infected; only their transmission is replaced
+  uint32_t mutate_variant;
   const double* effmult;    // [V][N] immunity.effective_multiplier_dict, or null (no vaccination)
   int fuse_health;          // 1 inside a step: the creating lane also runs the slot's first health update
   HealthArgs h;
@@ -711,7 +713,7 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
   const uint32_t step_flags = a.sp->flags;
   for (uint32_t i = (bid * blockDim.x + threadIdx.x) / 16; i < n; i += n_seg) {
     const uint32_t p = a.member[i];
-    const uint32_t var = a.variant ? a.variant[i] : 0u;
+    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[i] : 0u;
     if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
       if (j == 0) {
         if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
@@ -727,11 +729,13 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
     uint32_t region_p = 0, sa_p = 0;
     int32_t med_p = -1;
     if (j == 0) { region_p = a.pregion[p]; sa_p = a.psa[p]; med_p = a.pmed[p]; }
-    if (st & (JB_PS_INFECTED | JB_PS_DEAD)) continue;  // cannot happen within a step; guards seeding
+    if (!a.mutate && (st & (JB_PS_INFECTED | JB_PS_DEAD))) continue;  // cannot happen within a step; guards seeding
+    if (a.mutate && !(st & JB_PS_INFECTED)) continue;
     uint32_t slot = 0;
     int32_t hosp_p = -1;
     if (j == 0) {
-      slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);  // in flight while the segment samples
+      if (a.mutate) slot = (uint32_t)a.pslot[p];
+      else slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);  // in flight while the segment samples
       hosp_p = a.sa_hospital[sa_p];
     }
     const uint32_t gid = a.gid_base + ext;
@@ -786,7 +790,7 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
       } else if (j >= 9) {
         const int q = (j == 15) ? 3 : j - 9;
         const int need = D.trans_type == JB_TRANS_GAMMA ? 4 : D.trans_type == JB_TRANS_XNEXP ? 5 : 1;
-        if (q < need && (j != 15 || D.trans_type == JB_TRANS_XNEXP)) dist = &D.trans_par[q];
+        if (q < need && (j != 15 || D.trans_type == JB_TRANS_XNEXP)) dist = &D.trans_par_v[var][q];
       }
       if (dist) x = jb_sample_dist(rs, dist->type, dist->p);
     }
@@ -810,8 +814,10 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
         cumt += tstage[s];
       }
       if (s == 1) t_exposed = tt;
-      a.traj_time[(size_t)s * a.C + slot] = tt;
-      a.traj_tag[(size_t)s * a.C + slot] = (int8_t)tg;
+      if (!a.mutate) {  // (a mutation keeps the person's symptoms)
+        a.traj_time[(size_t)s * a.C + slot] = tt;
+        a.traj_tag[(size_t)s * a.C + slot] = (int8_t)tg;
+      }
     }
     // transmission (infection_selector.py:280-332)
     double par[JB_N_TPAR] = {0, 0, 0, 0, 0};
@@ -830,6 +836,12 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
       par[0] = tp[0];
     }
     for (int q = 0; q < JB_N_TPAR; ++q) a.inf_par[(size_t)q * a.C + slot] = par[q];
+    if (a.mutate) {  // event/mutation.py:53-66: new transmission, old symptoms
+      a.inf_var[slot] = (uint8_t)var;
+      a.pvar[p] = (uint8_t)var;
+      a.trans[p] = a.trans_other[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
+      continue;
+    }
     a.inf_person[slot] = (int32_t)p;
     a.inf_start[slot] = a.sp->now;
     a.inf_next[slot] = nst > 1 ? tstage[0] : 1e300;  // == traj_time[1]
@@ -848,8 +860,11 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
     a.trans[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
     if (!a.fuse_health) a.trans_other[p] = a.trans[p];
     // immunity.add_immunity(infection.immunity_ids()) (infection_selector.py:160-162)
-    for (int v = 0; v < a.V; ++v) a.susc[(size_t)v * a.NP + p] = 0.0;
-    a.pstate[p] = (uint8_t)((st & ~JB_PST_CODE_MASK) | JB_PS_INFECTED);  // susceptibility code: 0.0
+    // (cross immunity: Infection.immunity_ids, infection.py:136-191)
+    const uint32_t cross = D.cross[var];
+    for (int v = 0; v < a.V; ++v)
+      if ((cross >> v) & 1u) a.susc[(size_t)v * a.NP + p] = 0.0;
+    a.pstate[p] = (uint8_t)(((cross & 1u) ? (st & ~JB_PST_CODE_MASK) : st) | JB_PS_INFECTED);  // susceptibility code of variant 0: 0.0
     atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_NEW_INFECTED], 1u);
     if (a.fuse_health) {
       // update_health_status also covers the infections created in this step
@@ -879,6 +894,23 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
   jb_stamp(6);
   jb_newinf_body(a, D, blockIdx.x, gridDim.x);
+}
+
+// Mutation event, selection pass (event/mutation.py:53-58): one thread per infection slot; the chosen people
+// are appended to the new-infection list, which k_newinf then walks in mutation mode.
+__global__ void __launch_bounds__(256) k_mutate_select(const int32_t* __restrict__ inf_person, const uint8_t* __restrict__ inf_region,
+                                                       uint32_t n_slots, const double* __restrict__ prob, const uint32_t* __restrict__ int2ext,
+                                                       uint32_t gid_base, uint64_t seed, uint32_t step, uint32_t* __restrict__ member,
+                                                       uint32_t cap, uint32_t* __restrict__ count) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int32_t p = inf_person[s];
+  if (p < 0) return;
+  const JbPhilox4 r = jb_philox4x32_10(gid_base + int2ext[p], step, 7u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  if (jb_u52(r.x[0], r.x[1]) < prob[inf_region[s]]) {
+    const uint32_t i = atomicAdd(count, 1u);
+    if (i < cap) member[i] = (uint32_t)p;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

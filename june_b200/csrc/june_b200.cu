@@ -105,6 +105,10 @@ static void copy_disease(const JbDisease& d, DiseaseDev& o) {
   }
   o.trans_type = d.trans_type;
   for (int k = 0; k < 6; ++k) o.trans_par[k] = d.trans_par[k];
+  for (int v = 0; v < JB_MAX_VARIANTS; ++v) {
+    for (int k = 0; k < 6; ++k) o.trans_par_v[v][k] = d.trans_par[k];
+    o.cross[v] = 0xFFFFFFFFu;
+  }
 }
 
 extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) {
@@ -489,6 +493,21 @@ extern "C" int jb_set_person_state(JbWorld* w, const uint8_t* pstate, const doub
 }
 
 static void drop_graphs(JbWorld* w);
+extern "C" int jb_set_variants(JbWorld* w, uint32_t n_variants, const JbDist* trans_par, const uint32_t* cross_immunity) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(n_variants == w->V, "jb_set_variants: n_variants differs from the world's");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  for (uint32_t v = 0; v < JB_MAX_VARIANTS; ++v) {
+    for (int k = 0; k < 6; ++k)
+      w->dis_host.trans_par_v[v][k] = (trans_par && v < n_variants) ? trans_par[(size_t)v * 6 + k] : w->dis_host.trans_par[k];
+    w->dis_host.cross[v] = (cross_immunity && v < n_variants) ? cross_immunity[v] : 0xFFFFFFFFu;
+  }
+  CK(cudaMemcpy(w->dis, &w->dis_host, sizeof(w->dis_host), cudaMemcpyHostToDevice));
+  drop_graphs(w);  // the disease tables travel as a kernel parameter
+  return JB_OK;
+}
+
 extern "C" int jb_set_halo_activities(JbWorld* w, uint32_t activity_mask) {
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
@@ -906,6 +925,37 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   return JB_OK;
 }
 
+extern "C" int jb_mutate(JbWorld* w, uint32_t variant, const double* regional_probability, uint64_t seed, uint32_t step) {
+  if (!w || !regional_probability) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(variant < w->V, "jb_mutate: variant out of range");
+  REQUIRE(!w->in_step, "jb_mutate inside a step");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  uint32_t hw = 0;
+  CK(cudaMemcpy(&hw, w->counters + CNT_SLOTS_HW, 4, cudaMemcpyDeviceToHost));
+  if (!hw) return JB_OK;
+  double* d_prob = nullptr;
+  TRY(dev_upload(&d_prob, regional_probability, w->R, w->stream));
+  CK(cudaMemsetAsync(w->counters + CNT_NEWINF, 0, 4, w->stream));
+  k_mutate_select<<<(hw + 255) / 256, 256, 0, w->stream>>>(w->inf_person, w->inf_region, hw, d_prob, w->int2ext, (uint32_t)w->id_base,
+                                                           seed, step, w->newinf_member, w->newinf_cap, w->counters + CNT_NEWINF);
+  CK(cudaGetLastError());
+  NewInfArgs a = make_newinf_args(w);
+  a.member = w->newinf_member; a.variant = nullptr; a.count_dev = w->counters + CNT_NEWINF; a.cap = w->newinf_cap;
+  a.mutate = 1; a.mutate_variant = variant;
+  StepDev sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.seed = seed; sd.step = step;
+  CK(cudaMemcpyAsync(w->d_step_aux, &sd, sizeof(sd), cudaMemcpyHostToDevice, w->stream));
+  a.sp = reinterpret_cast<const StepDev*>(w->d_step_aux);
+  k_newinf<<<148 * 8, 128, 0, w->stream>>>(a, w->dis_host);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(w->counters + CNT_NEWINF, 0, 4, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  cudaFree(d_prob);
+  return JB_OK;
+}
+
 extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size_t n) {
   if (!w) { jb_set_error("null world"); return JB_EINVAL; }
   if (n == 0) return JB_OK;
@@ -969,7 +1019,8 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
     r.person = w->h_ext2int[r.person];
     uint8_t st = 0;
     CK(cudaMemcpy(&st, w->pstate + r.person, 1, cudaMemcpyDeviceToHost));
-    st = (uint8_t)((st & ~JB_PST_CODE_MASK) | JB_PS_INFECTED);  // susceptibility 0.0 from now on
+    const uint32_t cross_r = w->dis_host.cross[r.variant < JB_MAX_VARIANTS ? r.variant : 0];
+    st = (uint8_t)(((cross_r & 1u) ? (st & ~JB_PST_CODE_MASK) : st) | JB_PS_INFECTED);  // susceptibility to variant 0: 0.0 from now on
     if (JB_TAG_BIT(r.tag) & w->dis_host.severe_mask) st |= JB_PS_SEVERE;
     CK(cudaMemcpy(w->pstate + r.person, &st, 1, cudaMemcpyHostToDevice));
     int32_t slot = (int32_t)(hw + i);
@@ -982,7 +1033,8 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
     CK(cudaMemcpy(w->trans[0] + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->trans[1] + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
     for (uint32_t v = 0; v < w->V; ++v)
-      CK(cudaMemcpy(w->susc + (size_t)v * w->NP + r.person, &zero, 8, cudaMemcpyHostToDevice));
+      if ((w->dis_host.cross[r.variant < JB_MAX_VARIANTS ? r.variant : 0] >> v) & 1u)
+        CK(cudaMemcpy(w->susc + (size_t)v * w->NP + r.person, &zero, 8, cudaMemcpyHostToDevice));
   }
   hw += (uint32_t)n;
   CK(cudaMemcpy(w->counters + CNT_SLOTS_HW, &hw, 4, cudaMemcpyHostToDevice));

@@ -270,6 +270,30 @@ class Engine:
         """Activities under which halo persons are registered in any domain (same value on every rank)."""
         self._check(self._f("set_halo_activities")(self._h, int(activity_mask)))
 
+    def set_variants(self, trans_par: Optional[Sequence[Sequence[tuple]]] = None, cross_immunity: Optional[Sequence[int]] = None):
+        """Per-variant transmission distributions (``[(type code, p[4])] * 6`` per variant, as
+        ``DiseaseConfig.transmission_table`` returns them) and cross-immunity bit masks."""
+        from ._lib import JbDist
+        V = self.n_variants
+        tp = None
+        if trans_par is not None:
+            assert len(trans_par) == V
+            tp = (JbDist * (6 * V))()
+            for v, row in enumerate(trans_par):
+                for k, (code, p) in enumerate(row):
+                    tp[v * 6 + k].type = int(code)
+                    for q in range(4):
+                        tp[v * 6 + k].p[q] = float(p[q])
+        ci = None if cross_immunity is None else np.ascontiguousarray(cross_immunity, dtype=np.uint32)
+        assert ci is None or ci.shape == (V,)
+        self._check(self._f("set_variants")(self._h, V, tp, ptr(ci)))
+
+    def mutate(self, variant: int, regional_probability: Sequence[float], seed: int, step: int):
+        """``Mutation.apply`` (``event/mutation.py:53-66``)."""
+        pr = np.ascontiguousarray(regional_probability, dtype=np.float64)
+        assert pr.shape == (self.world.n_regions,)
+        self._check(self._f("mutate")(self._h, int(variant), ptr(pr), int(seed), int(step)))
+
     def set_medical(self, medical: np.ndarray):
         """Restore ``person.subgroups.medical_facility`` (``hospital group << 8 | ward``, -1 = none); call
         before ``upload_infections``."""

@@ -184,6 +184,9 @@ class Simulator:
                  checkpoint_save_dates=None, checkpoint_save_path: Optional[str] = None):
         self.world, self.interaction, self.timer = world, interaction, timer
         self.activity_manager, self.epidemiology, self.record = activity_manager, epidemiology, record
+        self.events = events
+        if events is not None:
+            events.init_events(world=world)
         self.disease_config = disease_config or DiseaseConfig("covid19")
         self.seed = int(seed)
         self.step_ordinal = 0
@@ -355,6 +358,9 @@ class Simulator:
 
     def do_timestep(self, want_stats: bool = True) -> None:
         activities = self.timer.activities
+        if self.events is not None:  # simulator.py:368-376
+            self.events.apply(date=self.timer.date, world=self.world, activities=activities,
+                              day_type=self.timer.day_type, simulator=self)
         if not activities:
             return  # simulator.py:377-379
         params = self.step_params(_lib.STEP_RECORD_EVENTS if self.record is not None else 0)
