@@ -262,8 +262,41 @@ def make_b200_simulator_class(reference_simulator_cls):
             self.b200_last_stats = self._eng.step(params)
             self._step += 1
             self._b200_write_back()
+            self._b200_vaccinate()
             if self.record is not None:
                 self._b200_feed_record()
+
+        # ---- the reference's vaccination campaigns -> device tables ----------------------------------
+        def _b200_vaccinate(self):
+            """``Epidemiology.do_timestep`` applies the campaigns once per simulated day, after the day's first
+            health update (``epidemiology.py:127-135,295-303``).  The reference's ``VaccinationCampaigns`` object
+            is compiled into the device tables on first use; ``person.vaccinated`` and the immunity dicts of the
+            vaccinated people are written back."""
+            ep = self.epidemiology
+            camp = getattr(ep, "vaccination_campaigns", None) if ep is not None else None
+            if camp is None:
+                return
+            today = self.timer.date.date()
+            if getattr(self, "_b200_vac_day", None) == today:
+                return
+            self._b200_vac_day = today
+            if not hasattr(self, "_b200_vac_first"):
+                from .vaccination import campaigns_from_reference
+                cls = self._selector.infection_class
+                self._b200_vac_first = self.timer.initial_date.date()
+                mine = campaigns_from_reference(camp, {cls.infection_id(): cls.__name__})
+                self._eng.set_vaccination(*mine.device_tables(self._b200_vac_first, [cls.__name__]))
+                self._b200_vac_names = [v.name for v in mine.vaccines()]
+            self._eng.vaccinate((today - self._b200_vac_first).days, seed=self.b200_seed)
+            vs = self._eng.fetch_vaccination()
+            st = self._eng.fetch_person_state()
+            iid = self._selector.infection_class.infection_id()
+            for i in np.nonzero(vs["dose"] >= 0)[0]:
+                p = self._people[i]
+                p.vaccinated = int(vs["dose"][i])
+                p.vaccine_type = self._b200_vac_names[int(vs["vaccine"][i])]
+                p.immunity.susceptibility_dict[iid] = float(st["susceptibility"][0][i])
+                p.immunity.effective_multiplier_dict[iid] = float(vs["effective_multiplier"][0][i])
 
         # ---- device events -> the reference's Record (records_writer.py:203-246) ----------------------
         def _b200_feed_record(self):

@@ -84,6 +84,13 @@ class VaccinationCampaigns:
     def get_active(self, date: datetime.datetime) -> List[VaccinationCampaign]:
         return [vc for vc in self.vaccination_campaigns if vc.is_active(date)]
 
+    def vaccines(self) -> List[Vaccine]:
+        out: List[Vaccine] = []
+        for vc in self.vaccination_campaigns:
+            if vc.vaccine not in out:
+                out.append(vc.vaccine)
+        return out
+
     def device_tables(self, first_day: datetime.date, variant_names: Sequence[str]):
         """``(vaccine dicts, campaign dicts)`` for ``Engine.set_vaccination``; days are counted from
         ``first_day`` (the date of the simulation's first step)."""
@@ -117,3 +124,34 @@ class VaccinationCampaigns:
                              start_day=(vc.start_time.date() - first_day).days, end_day=(vc.end_time.date() - first_day).days,
                              last_dose_vaccines=mask, coverage=vc.group_coverage))
         return vrec, crec
+
+
+def campaigns_from_reference(ref_campaigns, infection_names: Dict[int, str]) -> VaccinationCampaigns:
+    """The reference's own ``VaccinationCampaigns`` / ``VaccinationCampaign`` / ``Vaccine`` objects
+    (``vaccination_campaign.py:36-119,266-300``, ``vaccines.py:380-513``) as this module's classes.  The
+    reference keys efficacies by infection id (``_parse_efficacies``); ``infection_names`` maps them back to
+    the class names the device tables are ordered by."""
+    vaccines: Dict[int, Vaccine] = {}
+    out = []
+    for rc in ref_campaigns.vaccination_campaigns:
+        rv = rc.vaccine
+        if id(rv) not in vaccines:
+            v = Vaccine.__new__(Vaccine)
+            v.name = rv.name
+            v.days_administered_to_effective = list(rv.days_administered_to_effective)
+            v.days_effective_to_waning = list(rv.days_effective_to_waning)
+            v.days_waning = list(rv.days_waning)
+            v.waning_factor = 1.0 if rv.waning_factor is None else rv.waning_factor
+            conv = lambda doses: [{infection_names[k]: list(x) for k, x in d.items() if k in infection_names} for d in doses]
+            v.sterilisation_efficacies, v.symptomatic_efficacies = conv(rv.sterilisation_efficacies), conv(rv.symptomatic_efficacies)
+            vaccines[id(rv)] = v
+        attr = rc.group_attribute
+        group_by = "residence" if attr.startswith("residence") else "primary_activity" if attr.startswith("primary_activity") else attr
+        c = VaccinationCampaign.__new__(VaccinationCampaign)
+        c.vaccine, c.days_to_next_dose, c.dose_numbers = vaccines[id(rv)], list(rc.days_to_next_dose), list(rc.dose_numbers)
+        c.start_time, c.end_time = rc.start_time, rc.end_time
+        c.group_by, c.group_type, c.group_coverage = group_by, rc.group_value, rc.group_coverage
+        c.last_dose_type = list(rc.last_dose_type or [])
+        c.total_days = (c.end_time - c.start_time).days
+        out.append(c)
+    return VaccinationCampaigns(out)

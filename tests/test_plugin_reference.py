@@ -148,3 +148,42 @@ def test_reference_simulator_subclass_feeds_the_record():
     hospital_ids = {h.id for h in world.hospitals.members}
     assert all(r["hospital_id"] in hospital_ids for t in ("hospital_admissions", "icu_admissions", "discharges") for r in rec.rows.get(t, []))
     assert len(rec.rows["recoveries"]) > 100 and len(rec.rows["symptoms"]) > 500 and len(rec.rows["hospital_admissions"]) > 0
+
+
+def test_reference_simulator_subclass_vaccinates_from_the_reference_campaigns():
+    """The reference's own ``VaccinationCampaigns`` object is compiled into the device tables; people of the
+    target groups get their doses at the configured coverage and their immunity dicts follow."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_world
+    from june_b200.june_plugin import make_b200_simulator_class
+    from helpers import make_engine
+
+    random.seed(5)
+    np.random.seed(5)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        world, dc = ref_world.build_world(2500, seed=5)
+        ref_sim = ref_world.make_simulator(world, dc, total_days=10, cases_per_capita=0.02, vaccination=True)
+    from june.simulator import Simulator
+    B200Simulator = make_b200_simulator_class(Simulator)
+    B200Simulator.b200_engine = staticmethod(lambda soa, inter, dcfg, prob: make_engine("oracle", soa, prob, interaction=inter, disease=dcfg))
+    sim = B200Simulator(world=world, interaction=ref_sim.interaction, timer=ref_sim.timer,
+                        activity_manager=ref_sim.activity_manager, epidemiology=ref_sim.epidemiology,
+                        tracker=None, record=None)
+    with contextlib.redirect_stdout(sink):
+        sim.run()
+    iid = sim._selector.infection_class.infection_id()
+    people = [p for p in world.people if not p.dead]
+    old = [p for p in people if 60 <= p.age < 100]
+    mid = [p for p in people if 30 <= p.age < 45]
+    rest = [p for p in people if p.age < 30 or 45 <= p.age < 60]
+    vacc = lambda ps: [p for p in ps if p.vaccinated is not None]
+    # ref_world: Pfizer for 60-100 at coverage 0.6 (doses 0, 1), AstraZeneca for 30-45 at coverage 0.5 (dose 0)
+    f_old, f_mid = len(vacc(old)) / len(old), len(vacc(mid)) / len(mid)
+    assert abs(f_old - 0.6) < 4 * np.sqrt(0.24 / len(old)) + 0.02, f_old
+    assert abs(f_mid - 0.5) < 4 * np.sqrt(0.25 / len(mid)) + 0.02, f_mid
+    assert not vacc(rest)
+    assert {p.vaccine_type for p in vacc(old)} == {"Pfizer"} and {p.vaccine_type for p in vacc(mid)} == {"AstraZeneca"}
+    assert max(p.vaccinated for p in vacc(old)) == 1 and max(p.vaccinated for p in vacc(mid)) == 0
+    never_infected = [p for p in vacc(old) if p.infection is None and p.immunity.susceptibility_dict.get(iid, 1.0) > 0]
+    assert len(never_infected) > 20 and all(p.immunity.susceptibility_dict[iid] < 1.0 for p in never_infected)
