@@ -291,8 +291,11 @@ def make_b200_simulator_class(reference_simulator_cls):
             vs = self._eng.fetch_vaccination()
             st = self._eng.fetch_person_state()
             iid = self._selector.infection_class.infection_id()
+            events = getattr(self.record, "events", None) if self.record is not None else None
             for i in np.nonzero(vs["dose"] >= 0)[0]:
                 p = self._people[i]
+                if events is not None and p.vaccinated != int(vs["dose"][i]):  # vaccines.py:309-313
+                    events["vaccines"].accumulate(p.id, self._b200_vac_names[int(vs["vaccine"][i])], int(vs["dose"][i]))
                 p.vaccinated = int(vs["dose"][i])
                 p.vaccine_type = self._b200_vac_names[int(vs["vaccine"][i])]
                 p.immunity.susceptibility_dict[iid] = float(st["susceptibility"][0][i])

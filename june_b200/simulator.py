@@ -235,6 +235,7 @@ class Simulator:
         self._leisure_stack: List[tuple] = []
         self.infection_events: List[tuple] = []
         self.health_events: List[tuple] = []
+        self.vaccine_events: List[tuple] = []
         self.region_history: List[tuple] = []
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
@@ -396,6 +397,16 @@ class Simulator:
                 dev.set_vaccination(*ep.vaccination_campaigns.device_tables(first, self.variant_names))
                 self._vaccination_on_device = True
             dev.vaccinate((self.timer.date.date() - self._vaccination_first_day).days, seed=self.seed)
+            if self.record is not None:
+                # `vaccines` table (vaccines.py:309-313): a row whenever somebody's dose number changes
+                vs = dev.fetch_vaccination()
+                prev = getattr(self, "_vaccination_dose_prev", None)
+                if prev is None:
+                    prev = np.full(self.world.n_people, -1, np.int8)
+                changed = np.nonzero(vs["dose"] != prev)[0]
+                if len(changed):
+                    self.vaccine_events.append((self.timer.date, changed, vs["vaccine"][changed].copy(), vs["dose"][changed].copy()))
+                self._vaccination_dose_prev = vs["dose"].copy()
         if stats is not None:
             self.last_stats = stats
             self.history.append(dict(date=self.timer.date, now=self.timer.now, **stats))
@@ -493,6 +504,15 @@ class Simulator:
                 else:
                     out[table].append(dict(time_stamp=date, hospital_ids=int(gid[g]), patient_ids=int(pid[p])))
         return out
+
+    def vaccine_rows(self) -> List[Dict[str, object]]:
+        """Rows of the reference's ``vaccines`` record table (``vaccines.py:309-313``,
+        ``event_records_writer.py:180-190``): ``time_stamp, vaccinated_ids, vaccine_names, dose_numbers``."""
+        w = self.world
+        pid = w.person_ids if w.person_ids is not None else np.arange(w.n_people, dtype=np.int64) + w.person_id_base
+        names = [v.name for v in self.epidemiology.vaccination_campaigns.vaccines()]
+        return [dict(time_stamp=date, vaccinated_ids=int(pid[p]), vaccine_names=names[int(v)], dose_numbers=int(d))
+                for date, persons, vacs, doses in self.vaccine_events for p, v, d in zip(persons, vacs, doses)]
 
     def write_summary_csv(self, path: str) -> None:
         import csv

@@ -99,3 +99,27 @@ def test_cuda_matches_oracle_with_vaccination():
     assert n_frac > 10_000, "the fractional-susceptibility path of the interaction kernels must be exercised"
     ia, ib = a.fetch_infections(), b.fetch_infections()
     assert [(r["person"], r["max_tag"]) for r in ia] == [(r["person"], r["max_tag"]) for r in ib]
+
+
+def test_simulator_records_the_vaccines_table():
+    """``vaccines`` record rows (vaccines.py:309-313): one per administered dose, through ``Simulator``."""
+    from test_leisure_policies import make_sim
+    from june_b200.policy import Policies
+    w = generate_world(12_000, seed=3, leisure=True, sector_betas=load_defaults()["company_sector_betas"])
+    sim = make_sim("oracle", w, Policies.from_file(), total_days=12, seed=2)
+    sim.epidemiology.vaccination_campaigns = campaigns()
+    sim.record = object()
+    sim.run()
+    rows = sim.vaccine_rows()
+    assert len(rows) > 3000
+    assert {r["vaccine_names"] for r in rows} == {"Test"} and {r["dose_numbers"] for r in rows} == {0, 1}
+    vs = sim.device.fetch_vaccination()
+    last = {}
+    for r in rows:
+        assert r["dose_numbers"] == last.get(r["vaccinated_ids"], -1) + 1, "doses come in order, one row each"
+        last[r["vaccinated_ids"]] = r["dose_numbers"]
+    assert len(last) == int((vs["dose"] >= 0).sum())
+    assert all(vs["dose"][p] == d for p, d in last.items())
+    second = [r for r in rows if r["dose_numbers"] == 1]
+    first_day = {r["vaccinated_ids"]: r["time_stamp"] for r in rows if r["dose_numbers"] == 0}
+    assert second and all((r["time_stamp"].date() - first_day[r["vaccinated_ids"]].date()).days == 5 for r in second)
