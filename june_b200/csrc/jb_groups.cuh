@@ -533,7 +533,8 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
   if (threadIdx.x < a.dim * a.dim) s_cm[threadIdx.x] = cm_mine;
   __syncthreads();
   const uint32_t n_work = s_n;
-  if (n_work == 0 || a.mode == 2) return;  // mode 2: detection only (profiling aid)
+  if (STREAM) jb_stamp_max(0);
+  if (n_work == 0 || a.mode == 2) { if (STREAM) jb_stamp_max(1); return; }  // mode 2: detection only (profiling aid)
 
   // ---- phase B ---------------------------------------------------------------------------
   const int V = (VM > 1) ? a.V : 1;
@@ -742,4 +743,5 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
     }
   }
   if (qn) drain(qn);
+  if (STREAM) jb_stamp_max(1);
 }

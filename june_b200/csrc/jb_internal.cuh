@@ -120,6 +120,13 @@ __device__ __forceinline__ unsigned long long jb_globaltimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// Latest time any block passed a point (id 0: tiles phase A done, 1: tiles done, 2: place done, 3: newinf done).
+__device__ __forceinline__ void jb_stamp_max(int id) {
+  if (threadIdx.x == 0) {
+    unsigned long long* s = g_stamps;
+    if (s) atomicMax(s + (size_t)JB_STAMP_RING * 8 + (size_t)(g_stamp_seq % JB_STAMP_RING) * 4 + id, jb_globaltimer());
+  }
+}
 __device__ __forceinline__ void jb_stamp(int id) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long* s = g_stamps;
@@ -131,6 +138,8 @@ __device__ __forceinline__ void jb_stamp(int id) {
         slot = s + (size_t)(q % JB_STAMP_RING) * 8;
         for (int k = 1; k < 8; ++k) slot[k] = (k == 4) ? 0ull : ~0ull;
         slot[0] = t;
+        unsigned long long* ext = s + (size_t)JB_STAMP_RING * 8 + (size_t)(q % JB_STAMP_RING) * 4;
+        ext[0] = ext[1] = ext[2] = ext[3] = 0ull;
       } else if (id == 4) {
         atomicMax(slot + 4, t);
       } else {

@@ -894,6 +894,7 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
   jb_stamp(6);
   jb_newinf_body(a, D, blockIdx.x, gridDim.x);
+  jb_stamp_max(3);
 }
 
 // Mutation event, selection pass (event/mutation.py:53-58): one thread per infection slot; the chosen people

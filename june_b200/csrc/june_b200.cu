@@ -335,8 +335,9 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   }
   if (jb_env_flag("JB_STAMPS", 0)) {
     unsigned long long* st = nullptr;
-    CK(cudaMalloc((void**)&st, JB_STAMP_RING * 8 * 8));
+    CK(cudaMalloc((void**)&st, JB_STAMP_RING * 12 * 8));
     CK(cudaMemset(st, 0xFF, JB_STAMP_RING * 8 * 8));
+    CK(cudaMemset(st + JB_STAMP_RING * 8, 0, JB_STAMP_RING * 4 * 8));
     CK(cudaMemcpyToSymbol(g_stamps, &st, sizeof(st)));
     w->stamps = st;
   }
@@ -412,16 +413,17 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   if (w->stamps) {
     // average start offsets (us, relative to k_step_begin) over the recorded steps, split by whether the step
     // ran a gather-tile / company kernel (primary-activity steps are longer)
-    std::vector<unsigned long long> h(JB_STAMP_RING * 8);
+    std::vector<unsigned long long> h(JB_STAMP_RING * 12);
     cudaDeviceSynchronize();
     cudaMemcpy(h.data(), w->stamps, h.size() * 8, cudaMemcpyDeviceToHost);
-    double acc[8] = {0}; int n = 0; double total = 0; int nt = 0;
+    double acc[8] = {0}, ext[4] = {0}; int n = 0; double total = 0; int nt = 0;
     for (int r = 0; r < JB_STAMP_RING; ++r) {
       const unsigned long long* q = &h[(size_t)r * 8];
       bool ok = q[0] != ~0ull;
       for (int k = 1; k < 8; ++k) ok = ok && q[k] != ~0ull && q[k] != 0ull;
       if (!ok) continue;
       for (int k = 0; k < 8; ++k) acc[k] += (double)(q[k] - q[0]) * 1e-3;
+      for (int k = 0; k < 4; ++k) { const unsigned long long e = h[(size_t)JB_STAMP_RING * 8 + (size_t)r * 4 + k]; if (e > q[0]) ext[k] += (double)(e - q[0]) * 1e-3; }
       ++n;
       const unsigned long long* nx = &h[(size_t)((r + 1) % JB_STAMP_RING) * 8];
       if (nx[0] != ~0ull && nx[0] > q[0] && nx[0] - q[0] < 1000000ull) { total += (double)(nx[0] - q[0]) * 1e-3; ++nt; }
@@ -429,6 +431,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
     if (n) {
       fprintf(stderr, "[jb stamps] %d steps: place %.1f tiles %.1f groups_first %.1f groups_last %.1f health %.1f newinf %.1f end %.1f | begin-to-begin %.1f us (%d)\n",
               n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n, acc[7] / n, nt ? total / nt : 0.0, nt);
+      fprintf(stderr, "[jb stamps] last block: tiles phase A done %.1f, tiles done %.1f, newinf done %.1f\n", ext[0] / n, ext[1] / n, ext[3] / n);
     }
     unsigned long long* null_ptr = nullptr;
     cudaMemcpyToSymbol(g_stamps, &null_ptr, sizeof(null_ptr));
