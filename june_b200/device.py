@@ -328,13 +328,19 @@ class Engine:
     # ---- stepping --------------------------------------------------------------------------------
     def make_params(self, now: float, delta_time: float, step: int, activity_mask: int, seed: int, flags: int,
                     beta: np.ndarray, leisure_table: int = 0) -> JbStepParams:
-        beta = np.ascontiguousarray(beta, dtype=np.float64)
-        assert beta.shape == (len(self.world.beta_rules), self.world.n_regions), beta.shape
+        cache = self.__dict__.setdefault("_beta_cache", {})
+        hit = cache.get(id(beta))
+        if hit is None or hit[0] is not beta:  # callers pass the same table object while the policies do not change
+            b = np.ascontiguousarray(beta, dtype=np.float64)
+            assert b.shape == (len(self.world.beta_rules), self.world.n_regions), b.shape
+            if len(cache) > 64:
+                cache.clear()
+            hit = cache[id(beta)] = (beta, b, b.ctypes.data)
         p = JbStepParams()
-        p.now, p.delta_time, p.step, p.activity_mask = float(now), float(delta_time), int(step), int(activity_mask)
-        p.seed, p.flags, p.leisure_table = int(seed), int(flags), int(leisure_table)
-        p.beta = beta.ctypes.data
-        p._beta_keep = beta
+        p.now, p.delta_time, p.step, p.activity_mask = now, delta_time, step, activity_mask
+        p.seed, p.flags, p.leisure_table = seed, flags, leisure_table
+        p.beta = hit[2]
+        p._beta_keep = hit[1]
         return p
 
     def step(self, params: JbStepParams, want_stats: bool = True) -> Optional[Dict[str, int]]:

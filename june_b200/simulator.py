@@ -78,12 +78,17 @@ class ActivityManager:
         return self.activities_to_super_groups(self.timer.activities)
 
     def activity_mask(self) -> int:
-        mask = 0
-        for a in self.timer.activities:
-            code = ACTIVITY_CODES.get(a)
-            if code is not None:
-                mask |= 1 << code
-        return mask
+        acts = self.timer.activities
+        cache = self.__dict__.setdefault("_mask_cache", {})
+        hit = cache.get(id(acts))
+        if hit is None or hit[0] is not acts or hit[1] != len(acts):  # the schedule's own lists: stable objects
+            mask = 0
+            for a in acts:
+                code = ACTIVITY_CODES.get(a)
+                if code is not None:
+                    mask |= 1 << code
+            hit = cache[id(acts)] = (acts, len(acts), mask)
+        return hit[2]
 
 
 class InfectionSeed:

@@ -81,17 +81,30 @@ class Timer:
 
     _DAY_NAMES = ("Monday", "Tuesday", "Wednesday", "Thursday", "Friday", "Saturday", "Sunday")
 
+    # `date` is assigned by reset / __next__ / a checkpoint restore: everything derived from the calendar
+    # day is refreshed there once instead of on each of the several reads a time step makes
+    @property
+    def date(self) -> datetime.datetime:
+        return self._date
+
+    @date.setter
+    def date(self, value: datetime.datetime) -> None:
+        self._date = value
+        self._day_of_week = self._DAY_NAMES[value.weekday()]  # calendar.day_name goes through strftime
+        self._is_weekend = self._day_of_week in self.day_types["weekend"]
+        self._day_type = "weekend" if self._is_weekend else "weekday"
+
     @property
     def day_of_week(self) -> str:
-        return self._DAY_NAMES[self.date.weekday()]  # calendar.day_name goes through strftime on every access
+        return self._day_of_week
 
     @property
     def is_weekend(self) -> bool:
-        return self.day_of_week in self.day_types["weekend"]
+        return self._is_weekend
 
     @property
     def day_type(self) -> str:
-        return "weekend" if self.is_weekend else "weekday"
+        return self._day_type
 
     @property
     def now(self) -> float:
