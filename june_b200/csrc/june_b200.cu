@@ -1477,6 +1477,16 @@ static int run_phase(JbWorld* w, int phase, const void* p0, const void* p1, F&& 
   return JB_OK;
 }
 
+// A step that failed while it was being enqueued may or may not have run k_step_begin (a failed graph
+// capture runs nothing): put the device's count of begun steps, which selects the parameter ring slot, back
+// in line with the host's.
+static int resync_step_count(JbWorld* w, int rc) {
+  cudaStreamSynchronize(w->stream);
+  const uint32_t seq = (uint32_t)w->step_seq;
+  cudaMemcpy(w->d_step_seq, &seq, 4, cudaMemcpyHostToDevice);
+  return rc;
+}
+
 static int ensure_event_buffers(JbWorld* w, uint32_t flags) {
   if (!(flags & JB_STEP_RECORD_EVENTS) || w->ev_group) return JB_OK;
   TRY(dev_alloc(&w->ev_infected, w->newinf_cap));
@@ -1514,7 +1524,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
   h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
-  TRY(run_phase(w, 0, d_send, nullptr, [&]() { return enqueue_begin(w, d_send); }));
+  if (int rc = run_phase(w, 0, d_send, nullptr, [&]() { return enqueue_begin(w, d_send); })) return resync_step_count(w, rc);
   CK(cudaEventRecord(w->ev_step_buf[slot], s));  // k_step_begin has read the slot once this fires
   w->in_step = true;
   return JB_OK;
@@ -1588,11 +1598,12 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
   h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
-  TRY(run_phase(w, 3, nullptr, nullptr, [&]() {
-    TRY(enqueue_begin(w, nullptr));
-    TRY(enqueue_interact(w, nullptr, nullptr));
-    return enqueue_finish(w, nullptr);
-  }));
+  if (int rc = run_phase(w, 3, nullptr, nullptr, [&]() {
+        TRY(enqueue_begin(w, nullptr));
+        TRY(enqueue_interact(w, nullptr, nullptr));
+        return enqueue_finish(w, nullptr);
+      }))
+    return resync_step_count(w, rc);
   CK(cudaEventRecord(w->ev_step_buf[slot], s));
   w->in_step = true;  // jb_step_finish_tail expects it
   TRY(timing_end(w, s));

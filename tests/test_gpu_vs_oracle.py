@@ -244,3 +244,32 @@ def test_two_variants_match_oracle():
         compare_state(a, b, f"step {i}")
         now += dt
     assert seen.min() > 5
+
+
+@pytest.mark.gpu
+def test_a_rejected_step_leaves_the_world_usable():
+    """Error behaviour at the boundary: a step the library refuses (here: injected leisure placement that was
+    never supplied) raises, changes nothing, and the following steps run exactly as if it had not happened."""
+    assert have_gpu()
+    w = generate_world(20_000, seed=3, sector_betas=load_defaults()["company_sector_betas"])
+    a, b, beta = setup(w)
+    b.close()
+    inter, dc = Interaction.from_file(), DiseaseConfig("covid19")
+    b = make_engine("cuda", w, outcome_probabilities(dc, *synthetic_rates()), interaction=inter, disease=dc)
+    seeds = np.arange(0, w.n_people, 9, dtype=np.uint32)
+    flags = _lib.STEP_SEVERE_STAY_HOME | _lib.STEP_HOSPITALISATION
+    for e in (a, b):
+        e.infect(seeds, time=-4.0, seed=5, step=900)
+    now = 0.0
+    for i in range(6):
+        m, dt = MASKS[i % 5], DTS[i % 5]
+        if i in (0, 3):  # first use of this step shape, and a shape whose graph already exists
+            with pytest.raises(Exception) as err:
+                a.step(a.make_params(now, dt, i, m, seed=1, flags=flags | _lib.STEP_INJECT_LEISURE, beta=beta))
+            assert "jb_inject_leisure" in str(err.value)
+        sa = a.step(a.make_params(now, dt, i, m, seed=1, flags=flags, beta=beta))
+        sb = b.step(b.make_params(now, dt, i, m, seed=1, flags=flags, beta=beta))
+        assert sa == sb, i
+        compare_state(a, b, f"step {i}")
+        now += dt
+    assert sa["n_infected"] > 1000
