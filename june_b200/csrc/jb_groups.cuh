@@ -25,6 +25,10 @@ __device__ __forceinline__ double jb_cm_elem(const GroupArgs& a, int i, int j, c
   return yi == yj ? x / 4.0 : x;
 }
 
+__device__ __forceinline__ void jb_prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 // Susceptibility of person p to variant v given its hot byte.
 template <int VM>
 __device__ __forceinline__ double jb_susc(const GroupArgs& a, uint32_t p, uint32_t hot, int v) {
@@ -75,6 +79,10 @@ __device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t 
   } else {
     const uint32_t k = dyn_s[idx - ns];  // (lsg << 28) | caller's person index
     mbr.p = a.ext2int[k & 0x0FFFFFFFu];
+    // (few, scattered members: their value and id start their trips together with the hot byte's; for the
+    // static members of the big company lists the extra sectors cost more than the latency they hide)
+    jb_prefetch_l2(a.trans + mbr.p);
+    if (mbr.p < a.N) jb_prefetch_l2(a.int2ext + mbr.p);
     const uint32_t hot = a.phot[mbr.p];
     mbr.k = (k >> 28) | (hot << 16) | (1u << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
   }
@@ -165,6 +173,15 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 
   // registered slots can only hold someone when their feeding activity takes place in this step
   // (hospital workers on a residence-only step: the group is just its patients)
+  // everything that only depends on the group index starts its trip now, instead of one DRAM latency after
+  // the other along the kernel (offsets, bin fill and bin, group word)
+  if (tg == 0) {
+    jb_prefetch_l2(a.grp_info + g);
+    if (a.dyn_cnt) {
+      jb_prefetch_l2(a.dyn_cnt + a.dyn_bin_base + (g - a.g0));
+      jb_prefetch_l2(a.dyn_bin + (size_t)(g - a.g0) * bin_cap);
+    }
+  }
   const bool any_static = (a.static_acts & a.sp->activity_mask) != 0u;
   const uint32_t b = a.grp_off[g], ns = any_static ? a.grp_off[g + 1] - b : 0u;
   uint32_t nd = 0;
@@ -421,9 +438,6 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 #define JB_TILE_ITEMS (JB_TILE_SLOTS / 2)  // a listed group has >= 2 slots
 #define JB_DRAW_QUEUE 64
 
-__device__ __forceinline__ void jb_prefetch_l2(const void* ptr) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-}
 
 template <bool STREAM, int VM, bool EV>
 // (stream tiles are occupancy hungry: 48 registers measured 20 % faster than 70; the gather
