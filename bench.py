@@ -157,6 +157,13 @@ def interaction_bytes(world, sg, n_present: int) -> int:
     return int(14 * n_present + 8 * n_sub * f + 8 * n_grp * f)
 
 
+def workload_name(n_people: int, leisure: bool) -> str:
+    """The workload both arms run (same generator, schedule and seeding)."""
+    return (f"synthetic {n_people / 1e6:.1f}M-person region per GPU (households, schools, companies, care homes, hospitals"
+            + (", pubs, cinemas, groceries, gyms with leisure" if leisure else "")
+            + "), default 5/4-step day schedule, ~3% seeded prevalence")
+
+
 def run_gpu(args):
     import torch
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
@@ -334,9 +341,7 @@ def run_gpu(args):
         "metric": METRIC, "value": ps / (total_ms * 1e-3), "unit": "person-timesteps/s", "n_gpus": world_size,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {n_people / 1e6:.1f}M-person region per GPU (households, schools, companies, "
-                               "care homes, hospitals" + (", pubs, cinemas, groceries, gyms with leisure" if args.leisure else "")
-                               + "), default 5/4-step day schedule, ~3% seeded prevalence",
+        "config": {"workload": workload_name(n_people, args.leisure),
                    "people_per_gpu": n_people, "people_total": n_people * world_size,
                    "l2": "flushed between steps (256 MiB memset on the library stream, outside the event brackets)",
                    "parallelism": "1 domain per GPU" + (", halo exchange over peer memory on primary-activity steps; ranks aligned by a one-word all-reduce before each timed bracket" if world_size > 1 else "")},
@@ -407,8 +412,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "person-timesteps/s", "n_gpus": world_size,
            "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"synthetic {n_people / 1e6:.1f}M-person region (same generator and schedule as the GPU arm)",
-                      "people_per_gpu": n_people},
+           "config": {"workload": workload_name(n_people, args.leisure), "people_per_gpu": n_people, "people_total": n_people,
+                      "parallelism": "rank 0 only: one world of people_per_gpu people on the host cores (OpenMP)"},
            "cpu_baseline": {"value": v, "unit": "person-timesteps/s", "cores": threads, "kind": "port",
                             "sample": f"{steps} steps of the {n_people}-person world on rank 0"},
            "e2e": {"value": v, "unit": "person-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
