@@ -24,8 +24,14 @@ beta = inter.beta_table(world.beta_rules, [1.0] * world.n_regions, [None] * worl
 mask = 0b10101 if primary else 0b10001
 now = 0.0
 for i in range(60):
+    if i == 20:  # CUDA-event brackets (what bench.py reports) over the last 40 steps, for comparison with the stamps
+        dev.sync()
+        dev.timing_enable(1)
+        dev.timing_read(reset=True)
     dev.flush_l2()
     dev.step(dev.make_params(now, 1 / 24, i, mask, seed=3, flags=3, beta=beta), want_stats=False)
     now += 1 / 24
 dev.sync()
+tim = dev.timing_read()
+print("event brackets: %.1f us per step over %d steps" % (1e3 * tim["step_ms"] / max(1, tim["n_steps"]), tim["n_steps"]), file=sys.stderr)
 dev.close()
