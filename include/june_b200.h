@@ -403,6 +403,11 @@ int jb_fetch_vaccination(JbWorld* w, int8_t* dose, int8_t* vaccine, double* effe
 #define JB_POL_CLOSE_COMPANIES 6   /* CloseCompanies (:604-770): flags bit0 full_closure, p0
                                     * avoid_work_probability, p1 furlough_probability, p2
                                     * key_probability, p3..p5 furlough / key / random ratios    */
+#define JB_POL_CLOSE_COMPANIES_TIERS 8 /* CloseCompaniesLockdownTiers (:551-601): mask bit r = region r is in lockdown
+                                        * tier 3 or 4; a company worker with lockdown_status "random" whose work super
+                                        * area is not the home one (jb_set_person_work_regions) skips work with
+                                        * probability regional_compliance[home] when the work or the home region is
+                                        * in such a tier */
 #define JB_POL_LIMIT_LONG_COMMUTE 7 /* LimitLongCommute (:773-824): p0 going_to_work_probability; applies
                                     * to persons flagged JB_PA_LONG_COMMUTER.  As in the reference,
                                     * the activity is skipped when random() < p0.               */
@@ -413,6 +418,9 @@ typedef struct {
   uint32_t _pad;
   double p[6];
 } JbIndividualPolicy;
+/* work_region[n_people]: region of person.work_super_area when it differs from the home super area, else 0xFF
+ * (CloseCompaniesLockdownTiers, individual_policies.py:570-599). */
+int jb_set_person_work_regions(JbWorld* w, const uint8_t* work_region);
 /* regional_compliance: [n_regions] (region.regional_compliance, regional_compliance.py:21-30) */
 int jb_set_individual_policies(JbWorld* w, const JbIndividualPolicy* policies, uint32_t n,
                                const double* regional_compliance);

@@ -27,7 +27,7 @@ STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE, STEP_INJECT_POL
 STEP_RECORD_EVENTS, STEP_INJECT_COMMUTE = 0x80, 0x100
 MAX_POLICIES, POLICY_DRAWS = 8, 3
 POL_SEVERE_STAY_HOME, POL_QUARANTINE, POL_SHIELDING, POL_CLOSE_SCHOOLS, POL_CLOSE_UNIVERSITIES, POL_CLOSE_COMPANIES = 1, 2, 3, 4, 5, 6
-POL_LIMIT_LONG_COMMUTE = 7
+POL_LIMIT_LONG_COMMUTE, POL_CLOSE_COMPANIES_TIERS = 7, 8
 
 
 class SimulatorError(BaseException):
@@ -138,7 +138,7 @@ ABI_SYMBOLS = [
     "set_individual_policies", "set_person_attributes", "inject_policy_uniforms", "fetch_infection_events",
     "set_commute", "inject_commute",
     "set_vaccination", "vaccinate", "inject_vaccination_uniforms", "fetch_vaccination",
-    "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities", "set_variants", "mutate",
+    "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities", "set_variants", "mutate", "set_person_work_regions",
 ]
 
 
@@ -204,6 +204,7 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("flush_l2").argtypes = [vp, C.c_size_t]
     f("set_medical").argtypes = [vp, vp]
     f("set_halo_activities").argtypes = [vp, C.c_uint32]
+    f("set_person_work_regions").argtypes = [vp, vp]
     f("set_variants").argtypes = [vp, C.c_uint32, vp, vp]
     f("mutate").argtypes = [vp, C.c_uint32, vp, C.c_uint64, C.c_uint32]
     f("fetch_health_events").argtypes = [vp, vp, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]

@@ -244,6 +244,16 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
             if wsa is not None and getattr(p, "area", None) is not None:
                 long_c[i] = _haversine(p.area.coordinates, wsa.coordinates) > long_commute_distance
     w.person_attr = make_person_attr(lock, kind, kw2, long_c)
+    # CloseCompaniesLockdownTiers (individual_policies.py:570-599): the work super area's region, when the
+    # person works outside the home super area
+    work_region = np.full(n, 0xFF, np.uint8)
+    for i, p in enumerate(people):
+        wsa = getattr(p, "work_super_area", None)
+        home = getattr(getattr(p, "area", None), "super_area", None)
+        reg = getattr(getattr(wsa, "region", None), "name", None)
+        if wsa is not None and wsa is not home and reg in w.region_names:
+            work_region[i] = w.region_names.index(reg)
+    w.person_work_region = work_region
     if travel is not None and getattr(world, "cities", None) is not None:
         # Travel.get_commute_subgroup (travel.py:125-131): work city, public transport, internal commuter
         # of the city or commuter of the home super area's inter-city station (city.py:83-102)

@@ -352,6 +352,7 @@ struct JbWorld {
   PolicyDev* d_pol = nullptr;
   uint32_t n_pol = 0;
   uint8_t* pattr = nullptr;
+  uint8_t* pwork_region = nullptr;
   double* pol_inject = nullptr;
   bool any_dynamic = false;
   void* cub_tmp = nullptr;

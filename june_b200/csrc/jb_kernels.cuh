@@ -52,6 +52,7 @@ struct PlaceArgs {
   uint32_t n_pol;
   const int8_t* ptag;
   const uint8_t* pattr;
+  const uint8_t* pwork_region;
   const double* pol_inject;  // [JB_MAX_POLICIES][JB_POLICY_DRAWS][N] or null
   int severe_mask;
 };
@@ -143,6 +144,15 @@ __device__ __noinline__ uint32_t jb_apply_policies(const PlaceArgs& a, uint32_t 
         if (kind == 2u && jb_close_companies_skips(a, p, k, q, (int)JB_PA_LOCKDOWN(attr)))
           allowed &= ~((1u << JB_ACT_PRIMARY) | (1u << JB_ACT_COMMUTE));
         break;
+      case JB_POL_CLOSE_COMPANIES_TIERS: {  // :556-601: one draw, whichever of the two conditions holds
+        const uint32_t wr = a.pwork_region ? a.pwork_region[p] : 0xFFu;
+        if (kind == 2u && JB_PA_LOCKDOWN(attr) == 2u && wr != 0xFFu) {
+          const uint32_t home_t = (q.mask >> a.pregion[p]) & 1u, work_t = (q.mask >> wr) & 1u;
+          if ((work_t || home_t) && jb_policy_uniform(a, p, k, 0) < rc)
+            allowed &= ~((1u << JB_ACT_PRIMARY) | (1u << JB_ACT_COMMUTE));
+        }
+        break;
+      }
       case JB_POL_LIMIT_LONG_COMMUTE:  // :815-824: skips when random() < going_to_work_probability
         if ((attr & JB_PA_LONG_COMMUTER) && jb_policy_uniform(a, p, k, 0) < q.p[0])
           allowed &= ~((1u << JB_ACT_PRIMARY) | (1u << JB_ACT_COMMUTE));

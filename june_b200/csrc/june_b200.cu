@@ -388,7 +388,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
                   w->cub_tmp, w->int2ext, w->ext2int, w->d_vacc, w->vac_dose, w->vac_type, w->traj_camp, w->traj_day0, w->traj_stage,
-                  w->prior_eff_inf, w->prior_eff_sym, w->effmult, w->vac_inject, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->hev_person, w->hev_kind, w->hev_group, w->pres_group, w->pol_subjects, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
+                  w->prior_eff_inf, w->prior_eff_sym, w->effmult, w->vac_inject, w->cm_person, w->cm_inject, w->cm_cs_off, w->cm_cs, w->cm_st_off, w->cm_st, w->ev_infected, w->ev_infector, w->ev_group, w->ev_var, w->hev_person, w->hev_kind, w->hev_group, w->pres_group, w->pol_subjects, w->pwork_region, w->d_pol, w->pattr, w->pol_inject, w->lz_parea, w->lz_off, w->lz_venue, w->lz_does, w->lz_cum, w->lz_inject};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (double* q : w->vacc_tables) cudaFree(q);
@@ -863,6 +863,17 @@ extern "C" int jb_set_person_attributes(JbWorld* w, const uint8_t* attr) {
   return JB_OK;
 }
 
+extern "C" int jb_set_person_work_regions(JbWorld* w, const uint8_t* work_region) {
+  if (!w || !work_region) { jb_set_error("null argument"); return JB_EINVAL; }
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  std::vector<uint8_t> v(std::max(1u, w->N), 0xFF);
+  for (uint32_t p = 0; p < w->N_ext; ++p) v[w->h_ext2int[p]] = work_region[p];
+  if (!w->pwork_region) { TRY(dev_alloc(&w->pwork_region, v.size())); drop_graphs(w); }
+  CK(cudaMemcpy(w->pwork_region, v.data(), v.size(), cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
 extern "C" int jb_inject_policy_uniforms(JbWorld* w, const double* u) {
   if (!w || !u) { jb_set_error("null argument"); return JB_EINVAL; }
   CK(cudaSetDevice(w->device));
@@ -1260,7 +1271,7 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     pa.cmt = w->cmt;
     pa.cmt.inject = (p.flags & JB_STEP_INJECT_COMMUTE) ? w->cm_inject : nullptr;
     if (!(p.activity_mask & (1u << JB_ACT_COMMUTE))) { pa.cmt.person = nullptr; pa.cmt.inject = nullptr; }
-    pa.pol = w->d_pol; pa.n_pol = w->n_pol; pa.ptag = w->ptag; pa.pattr = w->pattr;
+    pa.pol = w->d_pol; pa.n_pol = w->n_pol; pa.ptag = w->ptag; pa.pattr = w->pattr; pa.pwork_region = w->pwork_region;
     pa.pol_inject = (p.flags & JB_STEP_INJECT_POLICY) ? w->pol_inject : nullptr;
     pa.severe_mask = w->dis_host.severe_mask;
     const uint32_t chunks = (w->N + 15) / 16;

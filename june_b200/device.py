@@ -111,6 +111,9 @@ class Engine:
         if world.person_attr is not None:
             pa = np.ascontiguousarray(world.person_attr, dtype=np.uint8)
             self._check(self._f("set_person_attributes")(self._h, ptr(pa)))
+        if getattr(world, "person_work_region", None) is not None:
+            wr = np.ascontiguousarray(world.person_work_region, dtype=np.uint8)
+            self._check(self._f("set_person_work_regions")(self._h, ptr(wr)))
         if world.n_halo:
             hg = np.ascontiguousarray(world.halo_gid, dtype=np.uint32)
             self._check(self._f("set_halo_gids")(self._h, ptr(hg), hg.size))

@@ -189,10 +189,10 @@ def make_b200_simulator_class(reference_simulator_cls):
             return idx + 1
 
         # ---- individual policies of the reference -> device records -----------------------------------
-        def _b200_policy_records(self, pol, comp):
+        def _b200_policy_records(self, pol, comp, tiers=()):
             date = self.timer.date
             active = [p for p in pol.individual_policies.policies if p.is_active(date)] if pol is not None else []
-            key = tuple(id(p) for p in active) + tuple(comp)
+            key = tuple(id(p) for p in active) + tuple(comp) + tuple(tiers)
             if key == self._policy_key:
                 return
             nan = float("nan")
@@ -221,6 +221,9 @@ def make_b200_simulator_class(reference_simulator_cls):
                                         opt(type(p).furlough_ratio), opt(type(p).key_ratio), opt(type(p).random_ratio)]))
                 elif name == "LimitLongCommute":
                     recs.append(dict(type=_lib.POL_LIMIT_LONG_COMMUTE, p=[p.going_to_work_probability]))
+                elif name == "CloseCompaniesLockdownTiers":
+                    recs.append(dict(type=_lib.POL_CLOSE_COMPANIES_TIERS,
+                                     mask=sum(1 << r for r, t in enumerate(tiers) if t in type(p).TIERS)))
                 elif name != "SevereSymptomsStayHome":
                     raise NotImplementedError(f"individual policy {name} has no device implementation (INTEGRATION.md section 4)")
             if recs or self._policy_key is not None:
@@ -255,7 +258,7 @@ def make_b200_simulator_class(reference_simulator_cls):
                     flags |= _lib.STEP_SEVERE_STAY_HOME
                 if any(type(p).__name__ == "Hospitalisation" and p.is_active(date) for p in pol.medical_care_policies.policies):
                     flags |= _lib.STEP_HOSPITALISATION
-            self._b200_policy_records(pol, comp)
+            self._b200_policy_records(pol, comp, tiers)
             params = self._eng.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self._step,
                                            activity_mask=mask, seed=self.b200_seed, flags=flags, beta=beta,
                                            leisure_table=self._b200_leisure_table(activities, pol))

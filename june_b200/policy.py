@@ -198,6 +198,25 @@ class CloseCompanies(Policy):
                        self.furlough_ratio, self.key_ratio, self.random_ratio])
 
 
+class CloseCompaniesLockdownTiers(Policy):
+    """``CloseCompaniesLockdownTiers`` (``individual_policies.py:551-601``): company workers with lockdown
+    status "random" who work outside their home super area skip work (and the commute) with probability
+    ``regional_compliance`` of the home region when the work region or the home region is in lockdown tier 3
+    or 4 (``Region.policy["lockdown_tier"]``, set by ``TieredLockdown``)."""
+    policy_type = "individual"
+    TIERS = (3, 4)
+
+    def __init__(self, start_time: DateLike = "1900-01-01", end_time: DateLike = "2100-01-01"):
+        super().__init__(start_time, end_time)
+
+    def device_record(self, ctx) -> dict:
+        mask = 0
+        for r, tier in enumerate(ctx.get("lockdown_tiers") or []):
+            if tier in self.TIERS:
+                mask |= 1 << r
+        return dict(type=_lib.POL_CLOSE_COMPANIES_TIERS, mask=mask)
+
+
 class LimitLongCommute(Policy):
     """``individual_policies.py:773-824``.  The set of long-distance commuters is a static person
     attribute (``JB_PA_LONG_COMMUTER``, computed by the world compiler from the home-area / work-super-area
@@ -277,7 +296,7 @@ class ChangeLeisureProbability(Policy):
 
 _CLASSES = {c.__name__: c for c in (CloseLeisureVenue, ChangeLeisureProbability, SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
                                     SevereSymptomsStayHome, Hospitalisation, Quarantine, Shielding, CloseSchools,
-                                    CloseUniversities, CloseCompanies, LimitLongCommute)}
+                                    CloseUniversities, CloseCompanies, CloseCompaniesLockdownTiers, LimitLongCommute)}
 
 
 def _camel(key: str) -> str:

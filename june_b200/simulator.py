@@ -301,7 +301,7 @@ class Simulator:
             self.interaction.beta_reductions = policies.beta_reductions(date)
             comp, tiers = policies.regional_scalars(date, self.world.region_names, self._region_state)
             beta = np.ascontiguousarray(self.interaction.beta_table(self.world.beta_rules, comp, tiers))
-            ctx = dict(stay_at_home_mask=self.disease_config.tag_mask("stay_at_home_stage"))
+            ctx = dict(stay_at_home_mask=self.disease_config.tag_mask("stay_at_home_stage"), lockdown_tiers=list(tiers))
             hit = (beta, policies.step_flags(date), dict(self.interaction.beta_reductions),
                    policies.device_policies(date, ctx), list(comp))
             self._policy_cache[key] = hit

@@ -148,11 +148,14 @@ class WorldSoA:
     # static facts the individual policies read (include/june_b200.h: JB_PA_*): lockdown status,
     # spec of the primary-activity group, ">= 2 key workers among the household's residents"
     person_attr: Optional[np.ndarray] = None      # uint8 [n_people]
+    # region of person.work_super_area when it differs from the home super area, else 0xFF
+    # (CloseCompaniesLockdownTiers, individual_policies.py:570-599)
+    person_work_region: Optional[np.ndarray] = None  # uint8 [n_people]
 
     _ARRAYS = ("age", "sex", "care_home_resident", "has_activity", "super_area", "sa_hospital", "sa_region",
                "grp_offset", "grp_info", "grp_aux", "reg_member", "reg_info", "school_years", "beta_scale",
                "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids", "grp_super_area",
-               "person_area", "area_venue_off", "area_venue", "person_attr",
+               "person_area", "area_venue_off", "area_venue", "person_attr", "person_work_region",
                "person_commute", "city_station_off", "city_station", "station_transport_off", "station_transport")
 
     @property
