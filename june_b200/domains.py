@@ -124,6 +124,11 @@ def partition(world: WorldSoA, n_domains: int) -> List[WorldSoA]:
             out_counts=out_counts, in_counts=in_counts,
             grp_super_area=world.grp_super_area[groups].copy(),
         )
+        # per-person facts the individual policies read travel with the residents
+        if world.person_attr is not None:
+            w.person_attr = world.person_attr[lo:hi].copy()
+        if getattr(world, "person_work_region", None) is not None:
+            w.person_work_region = world.person_work_region[lo:hi].copy()
         w.validate()
         out.append(w)
     return out
