@@ -936,6 +936,13 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   CK(cudaStreamSynchronize(w->stream));
   cudaFree(d_p);
   cudaFree(d_v);
+  uint32_t hw = 0;
+  CK(cudaMemcpy(&hw, w->counters + CNT_SLOTS_HW, 4, cudaMemcpyDeviceToHost));
+  if (hw > w->C) {  // the infections beyond the table were dropped by the kernel: report it, keep the table consistent
+    CK(cudaMemcpy(w->counters + CNT_SLOTS_HW, &w->C, 4, cudaMemcpyHostToDevice));
+    jb_set_error("jb_infect: infection slot capacity exceeded (JbWorldDesc.slot_capacity)");
+    return JB_ECAP;
+  }
   return JB_OK;
 }
 
