@@ -335,8 +335,11 @@ def run_gpu(args):
 
     cpu = (cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s=args.cpu_seconds)
            if world_size == 1 and args.cpu_seconds > 0 else None)
-    h2d = int(world.n_regions * len(world.beta_rules) * 8 + 48)
-    d2h = int(16 * 4)
+    # per step: the parameter block (StepDev header of 64 B + the beta table [rule][region] of doubles) is pulled
+    # from pinned host memory by k_step_begin; the counter block (20 step counters + 8 per region) is pushed
+    # into pinned host memory by k_step_end
+    h2d = int(64 + world.n_regions * len(world.beta_rules) * 8)
+    d2h = int((20 + 8 * world.n_regions) * 4)
     out = {
         "metric": METRIC, "value": ps / (total_ms * 1e-3), "unit": "person-timesteps/s", "n_gpus": world_size,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
