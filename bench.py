@@ -3,11 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--people P]
 
-Metric (BASELINE.json): person-timesteps / second.  A "step" is one ``do_timestep`` of the
-default schedule (config_simulation.yaml: 5 weekday / 4 weekend steps) over a synthetic world
-built by ``june_b200.synth`` (SURVEY.md section 8d recipe).  N=1 runs BASELINE.json configs[1]
-(2.7 M people on one B200); N>1 is weak scaling: one 2.7 M-person domain per GPU, 5 % of the
-workers commuting to a neighbouring domain, two NCCL all-to-all exchanges per step.
+Metric (BASELINE.json): person-timesteps / second at 56 M agents on 1 / 2 / 4 / 8 B200.  A "step" is one
+``do_timestep`` of the default schedule (config_simulation.yaml: 5 weekday / 4 weekend steps) over a
+synthetic world built by ``june_b200.synth`` (SURVEY.md section 8d recipe).  The workload is BASELINE.json
+configs[2]: the 56 M-person England world, STRONG-scaled: N GPUs hold N domains of 56 M / N people, 5 % of
+the workers commute to a company of a neighbouring domain and are exchanged over peer memory (NVLink) on
+the steps with the primary activity.  ``--people P`` sets another total (2 700 000 = configs[1]);
+``--people-per-gpu P`` fixes the people per GPU instead (weak scaling, the configs[4] sweep).
 
 Prints ONE JSON line on rank 0 (contract in the task statement):
   value     device-resident throughput: K steps timed with CUDA events on the library stream,
@@ -46,7 +48,7 @@ from june_b200.timer import Timer  # noqa: E402
 from june_b200.world import ACT_RESIDENCE  # noqa: E402
 
 METRIC = "person-timesteps/sec"
-PEOPLE_PER_GPU = 2_700_000
+PEOPLE_TOTAL = 56_000_000  # BASELINE.json: the metric is quoted at 56 M agents
 HBM_FALLBACK_GBS = 6650.0
 
 
@@ -157,11 +159,26 @@ def interaction_bytes(world, sg, n_present: int) -> int:
     return int(14 * n_present + 8 * n_sub * f + 8 * n_grp * f)
 
 
-def workload_name(n_people: int, leisure: bool) -> str:
+def workload_name(n_total: int, leisure: bool) -> str:
     """The workload both arms run (same generator, schedule and seeding)."""
-    return (f"synthetic {n_people / 1e6:.1f}M-person region per GPU (households, schools, companies, care homes, hospitals"
+    return (f"synthetic {n_total / 1e6:.1f}M-person world (households, schools, companies, care homes, hospitals"
             + (", pubs, cinemas, groceries, gyms with leisure" if leisure else "")
-            + "), default 5/4-step day schedule, ~3% seeded prevalence")
+            + "), default 5/4-step day schedule from Monday 2020-03-02 08:00, default policy file, ~3% seeded prevalence")
+
+
+def config_dict(n_total: int, leisure: bool) -> dict:
+    """Identical in both arms (the driver compares the dicts): what is simulated, not how."""
+    return {"workload": workload_name(n_total, leisure), "people_total": n_total,
+            "l2": "inputs larger than the cache (>= 14 GB at 56 M people against 126 MB of L2) and the L2 flushed between "
+                  "timed steps"}
+
+
+def sizes(args, world_size: int):
+    """(people per GPU, total, scaling).  Default: 56 M people in total, strong-scaled over the GPUs."""
+    if args.people_per_gpu:
+        return args.people_per_gpu, args.people_per_gpu * world_size, "weak"
+    total = args.people or PEOPLE_TOTAL
+    return total // world_size, (total // world_size) * world_size, "strong"
 
 
 def run_gpu(args):
@@ -174,7 +191,7 @@ def run_gpu(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_people = args.people or PEOPLE_PER_GPU
+    n_people, n_total, scaling = sizes(args, world_size)
     world, inter, dc, prob, cfg, policies = build_setup(n_people, rank, world_size, dist, leisure=args.leisure)
     sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, device=local_rank,
                               seed=2020, distributed=world_size > 1)
@@ -182,6 +199,8 @@ def run_gpu(args):
     sim.activity_manager.timer = sim.timer
     seed_epidemic(sim, rank)
     sim.prepare_leisure_tables(days=14)
+    # every step graph the schedule needs is captured and instantiated here, before anything is timed
+    n_shapes = sim.prepare_steps(days=8)
     dev = sim.device
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))
 
@@ -305,31 +324,39 @@ def run_gpu(args):
         return
 
     peak, peak_src = measured_peak()
-    # dominant interaction kernel = the supergroup with the largest accumulated kernel time
-    # (by algorithmic bytes: the supergroup with the most registered slots -- households, which
-    #  also run in every step)
+    # Roofline of every supergroup's interaction kernel(s): SURVEY.md 8(d) algorithmic bytes of one launch over
+    # the mean CUDA-event time of the supergroup's launches (serialised leg).  The headline object is the
+    # supergroup with the most registered slots (households: it also runs in every step).
     slots = [int(world.grp_offset[g.first_group + g.n_groups]) - int(world.grp_offset[g.first_group]) for g in world.supergroups]
     k_top = int(np.argmax(slots))
-    sg = world.supergroups[k_top]
-    n_launch = max(1, per_sg[k_top]["launches"])
-    if sg.name == "households":
-        care = int((world.care_home_resident != 0).sum())
-        present = max(0, int(np.mean(act_res)) - care)
-    else:
-        present = int(world.grp_offset[sg.first_group + sg.n_groups] - world.grp_offset[sg.first_group])
-    a_bytes = interaction_bytes(world, sg, present)
-    t_launch_s = per_sg[k_top]["ms"] / n_launch * 1e-3
-    achieved = a_bytes / t_launch_s / 1e9 if t_launch_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": ("k_tiles" if sg.launch_mode == 0 else "k_groups"),
-                "supergroup": sg.name, "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                "bytes_per_launch": a_bytes, "us_per_launch": round(t_launch_s * 1e6, 2),
+    care = int((world.care_home_resident != 0).sum())
+    by_sg = {}
+    for k, sg in enumerate(world.supergroups):
+        n_launch = per_sg[k]["launches"]
+        if not n_launch or not slots[k]:
+            continue
+        present = max(0, int(np.mean(act_res)) - care) if sg.name == "households" else slots[k]
+        a_bytes = interaction_bytes(world, sg, present)
+        t_s = per_sg[k]["ms"] / n_launch * 1e-3
+        gbs = a_bytes / t_s / 1e9 if t_s > 0 else 0.0
+        by_sg[sg.name] = {"kernel": "k_tiles" if sg.launch_mode == 0 else "k_groups", "bytes_per_launch": a_bytes,
+                          "us_per_launch": round(t_s * 1e6, 2), "achieved": round(gbs, 1), "frac": round(gbs / peak, 4),
+                          "launches": int(n_launch)}
+    top = by_sg[world.supergroups[k_top].name]
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "supergroup": world.supergroups[k_top].name,
+                "achieved": top["achieved"], "peak": peak, "peak_source": peak_src,
+                "unit": "GB/s", "frac": top["frac"], "traffic": None,
+                "bytes_per_launch": top["bytes_per_launch"], "us_per_launch": top["us_per_launch"],
+                "by_supergroup": by_sg,
                 "interaction_ms_per_step_serial": round(tim_serial["interaction_ms"] / max(1, tim_serial["n_steps"]), 4),
                 "timing": "CUDA events on the launch stream, supergroup kernels serialised, L2 flushed between steps"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(f"{roofline['kernel']}@{n_people}")
+            tf = json.load(open(traffic_file))
+            roofline["traffic"] = tf.get(f"{roofline['kernel']}@{n_people}")
+            for name, o in by_sg.items():
+                o["traffic"] = tf.get(f"{name}@{n_people}")
         except Exception:
             pass
 
@@ -343,14 +370,15 @@ def run_gpu(args):
     out = {
         "metric": METRIC, "value": ps / (total_ms * 1e-3), "unit": "person-timesteps/s", "n_gpus": world_size,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n_people, args.leisure),
-                   "people_per_gpu": n_people, "people_total": n_people * world_size,
-                   "l2": "flushed between steps (256 MiB memset on the library stream, outside the event brackets)",
-                   "parallelism": "1 domain per GPU" + (", halo exchange over peer memory on primary-activity steps; ranks aligned by a one-word all-reduce before each timed bracket" if world_size > 1 else "")},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(n_total, args.leisure),
+        "people_per_gpu": n_people,
+        "parallelism": "1 domain per GPU" + (", halo exchange over peer memory on primary-activity steps; ranks aligned by a "
+                                              "one-word all-reduce before each timed bracket" if world_size > 1 else ""),
         "e2e": {"value": e2e_ps / (e2e_ms * 1e-3), "unit": "person-timesteps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
+        "step_graphs_prepared": n_shapes,
         "per_step_mean": per_step,
         "clocks": clocks,
         "roofline": roofline,
@@ -367,18 +395,27 @@ def run_gpu(args):
 def oracle_engine(world, inter, dc, prob):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import make_engine  # the oracle is loaded here only as the timed CPU baseline
-    return make_engine("oracle", world, prob, interaction=inter, disease=dc)
+    eng = make_engine("oracle", world, prob, interaction=inter, disease=dc)
+    # all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    eng._lib.jo_set_num_threads(int(os.cpu_count() or 1))
+    return eng
 
 
-def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int):
+def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int, budget_s: float = 0.0):
+    """Time `steps` steps of the CPU port after `warmup` steps; with a budget, as many steps as fit in
+    ~budget_s seconds (at least 3, at most `steps`), decided from the duration of the warm-up."""
     eng = oracle_engine(world, inter, dc, prob)
     sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, engine=eng, seed=2020)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
     seed_epidemic(sim, 0)
+    t0 = time.perf_counter()
     for _ in range(warmup):
         sim.do_timestep()
         next(sim.timer)
+    if budget_s > 0 and warmup:
+        per = (time.perf_counter() - t0) / warmup
+        steps = int(max(3, min(steps, budget_s / max(per, 1e-6))))
     ps, t0 = 0, time.perf_counter()
     for _ in range(steps):
         sim.do_timestep()
@@ -387,38 +424,37 @@ def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int):
     dt = time.perf_counter() - t0
     threads = int(eng._lib.jo_num_threads())
     eng.close()
-    return ps, dt, threads
+    return ps, dt, threads, steps
 
 
 def cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s: float = 15.0):
     """Oracle port on the host cores, bounded sample: as many steps of the same world as fit in
     ~budget_s seconds (at least 3)."""
-    ps, dt, threads = cpu_run(world, inter, dc, prob, cfg, policies, steps=2, warmup=1)
-    per_step = dt / 2
-    steps = int(max(3, min(40, budget_s / max(per_step, 1e-6))))
-    ps, dt, threads = cpu_run(world, inter, dc, prob, cfg, policies, steps=steps, warmup=1)
+    ps, dt, threads, steps = cpu_run(world, inter, dc, prob, cfg, policies, steps=40, warmup=2, budget_s=budget_s)
     return {"value": ps / dt, "unit": "person-timesteps/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} steps of the same {world.n_people}-person world (oracle/june_oracle.c, OpenMP)"}
+            "sample": f"{steps} steps of the same {world.n_people}-person world (oracle/june_oracle.c, OpenMP, {threads} threads)"}
 
 
 def run_reference(args):
+    """The reference arm: the CPU port of the reference algorithm (the reference itself is pure Python at
+    ~9e4 person-steps/s per core: DESIGN.md) on ALL host cores of the box, on the same total population as
+    the GPU arm (one undivided world on rank 0 -- the GPU arm's N domains are a partition of the same
+    recipe), same schedule, seeding, steps and warm-up."""
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    n_people = args.people or PEOPLE_PER_GPU
-    world, inter, dc, prob, cfg, policies = build_setup(n_people, 0, 1, leisure=args.leisure)
-    # bounded: the CPU port needs ~0.1-1 s per step of a 2.7 M world
-    steps = min(args.steps, 40)
-    ps, dt, threads = cpu_run(world, inter, dc, prob, cfg, policies, steps=steps, warmup=min(args.warmup, 3))
+    _, n_total, scaling = sizes(args, world_size)
+    world, inter, dc, prob, cfg, policies = build_setup(n_total, 0, 1, leisure=args.leisure)
+    ps, dt, threads, steps = cpu_run(world, inter, dc, prob, cfg, policies, steps=args.steps, warmup=args.warmup)
     v = ps / dt
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "person-timesteps/s", "n_gpus": world_size,
-           "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(n_people, args.leisure), "people_per_gpu": n_people, "people_total": n_people,
-                      "parallelism": "rank 0 only: one world of people_per_gpu people on the host cores (OpenMP)"},
+           "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+           "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(n_total, args.leisure),
+           "parallelism": f"rank 0 only: the undivided {n_total}-person world on {threads} OpenMP threads (all host cores)",
            "cpu_baseline": {"value": v, "unit": "person-timesteps/s", "cores": threads, "kind": "port",
-                            "sample": f"{steps} steps of the {n_people}-person world on rank 0"},
+                            "sample": f"{steps} steps of the {n_total}-person world on rank 0, {threads} threads"},
            "e2e": {"value": v, "unit": "person-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -426,10 +462,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=180)
-    ap.add_argument("--warmup", type=int, default=9)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--people", type=int, default=0, help="people per GPU (default 2.7 M = BASELINE.json configs[1])")
+    ap.add_argument("--people", type=int, default=0,
+                    help="TOTAL people over all GPUs (default 56 M = the metric's configuration; 2700000 = BASELINE.json configs[1])")
+    ap.add_argument("--people-per-gpu", type=int, default=0, help="fix the people per GPU instead (weak scaling)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--leisure", action="store_true",
                     help="add pubs / cinemas / groceries / gyms and the leisure placement (BASELINE.json configs[3])")

@@ -287,6 +287,11 @@ int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size_t n);
  *   jb_step_finish: applies d_ret_recv (infections of our residents abroad), health update.
  */
 int jb_step(JbWorld* w, const JbStepParams* params, JbStepStats* stats_out);
+/* Set-up aid: build whatever jb_step would build on the FIRST step with these activities / flags (the CUDA
+ * library captures and instantiates the step's graph) without running anything, so that no later jb_step
+ * pays for it.  The reference has no counterpart (its step has no set-up cost); a no-op is a valid
+ * implementation. */
+int jb_step_prepare(JbWorld* w, const JbStepParams* params);
 int jb_step_begin(JbWorld* w, const JbStepParams* params, void* d_send);
 int jb_step_interact(JbWorld* w, const void* d_recv, void* d_ret_send);
 int jb_step_finish(JbWorld* w, const void* d_ret_recv, JbStepStats* stats_out);

@@ -139,6 +139,7 @@ ABI_SYMBOLS = [
     "set_commute", "inject_commute",
     "set_vaccination", "vaccinate", "inject_vaccination_uniforms", "fetch_vaccination",
     "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities", "set_variants", "mutate", "set_person_work_regions",
+    "step_prepare",
 ]
 
 
@@ -176,6 +177,7 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("infect").argtypes = [vp, vp, vp, C.c_size_t, C.c_double, C.c_uint64, C.c_uint32]
     f("upload_infections").argtypes = [vp, C.POINTER(JbInfectionRow), C.c_size_t]
     f("step").argtypes = [vp, C.POINTER(JbStepParams), C.POINTER(JbStepStats)]
+    f("step_prepare").argtypes = [vp, C.POINTER(JbStepParams)]
     f("step_begin").argtypes = [vp, C.POINTER(JbStepParams), vp]
     f("step_interact").argtypes = [vp, vp, vp]
     f("step_finish").argtypes = [vp, vp, C.POINTER(JbStepStats)]

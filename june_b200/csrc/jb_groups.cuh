@@ -64,7 +64,7 @@ struct JbMember {
 
 // Member `idx` of group (static registered slots first, then the sorted dynamic members, which
 // the CTA has staged in shared memory as (lsg << 28) | person, sorted).
-__device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t idx, uint32_t b, uint32_t ns,
+__device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, const double* trans, uint32_t idx, uint32_t b, uint32_t ns,
                                                    const uint32_t* dyn_s, uint32_t ntot) {
   JbMember mbr;
   mbr.p = 0; mbr.k = 0xFFFFu;
@@ -81,7 +81,7 @@ __device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, uint32_t 
     mbr.p = a.ext2int[k & 0x0FFFFFFFu];
     // (few, scattered members: their value and id start their trips together with the hot byte's; for the
     // static members of the big company lists the extra sectors cost more than the latency they hide)
-    jb_prefetch_l2(a.trans + mbr.p);
+    jb_prefetch_l2(trans + mbr.p);
     if (mbr.p < a.N) jb_prefetch_l2(a.int2ext + mbr.p);
     const uint32_t hot = a.phot[mbr.p];
     mbr.k = (k >> 28) | (hot << 16) | (1u << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
@@ -115,7 +115,7 @@ __device__ __forceinline__ void jb_grp_sync() {
 // probability ~ its term of the susceptible's row; _blame_individuals (:647-662): infector with
 // probability ~ transmission probability inside that subgroup, in member order.
 template <int VM>
-__device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, uint32_t p, int i, int v, uint32_t b, uint32_t ns,
+__device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, const double* trans, uint32_t p, int i, int v, uint32_t b, uint32_t ns,
                                                 uint32_t ntot, const uint32_t* dyn_s, int Lg, const uint8_t* years,
                                                 int n_years, const uint32_t* n_l, const double* T, double row,
                                                 double beta, double dt) {
@@ -138,9 +138,9 @@ __device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, uint32_t p, 
   double c2 = 0.0;
   uint32_t infector = 0xFFFFFFFFu;
   for (uint32_t idx = 0; idx < ntot; ++idx) {
-    const JbMember o = jb_load_member(a, idx, b, ns, dyn_s, ntot);
+    const JbMember o = jb_load_member(a, trans, idx, b, ns, dyn_s, ntot);
     if (!o.infector() || (int)o.lsg() != jb || (VM > 1 && (int)JB_HOT_VAR(o.hot()) != v)) continue;
-    c2 += a.trans[o.p];
+    c2 += trans[o.p];
     infector = o.p;
     if (c2 > target2) break;
   }
@@ -152,6 +152,7 @@ __device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, uint32_t p, 
 template <int VM, int WPG, bool EV>
 __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ GroupArgs a) {
   jb_stamp(3); jb_stamp(4);
+  const double* const trans = jb_trans_read(a.trans, a.NP, a.sp);
   extern __shared__ __align__(8) unsigned char smem_raw[];
   constexpr int GT = 32 * WPG;                 // threads per group
   constexpr int GPC = JB_CTA_WARPS / WPG;      // groups per CTA
@@ -249,10 +250,10 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 #pragma unroll
       for (int u = 0; u < JB_UB; ++u) {
         const uint32_t idx = it0 + 32 * u + lane;
-        mbs[u] = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
+        mbs[u] = jb_load_member(a, trans, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
       }
 #pragma unroll
-      for (int u = 0; u < JB_UB; ++u) tvs[u] = mbs[u].infector() ? a.trans[mbs[u].p] : 0.0;
+      for (int u = 0; u < JB_UB; ++u) tvs[u] = mbs[u].infector() ? trans[mbs[u].p] : 0.0;
       if (resident) {
 #pragma unroll
         for (int u = 0; u < JB_UB; ++u) keep[u] = mbs[u];
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 #pragma unroll
           for (int u = 0; u < JB_UB; ++u) {
             const uint32_t idx = it0 + 32 * u + lane;
-            mbs[u] = jb_load_member(a, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
+            mbs[u] = jb_load_member(a, trans, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
           }
         }
 #pragma unroll
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
               if (v >= 0) {
                 uint32_t infector = 0xFFFFFFFFu;
                 if (EV)
-                  infector = jb_blame_group<VM>(a, mb.p, (int)mb.lsg(), v, b, ns, ntot, dyn_s, Lg, years, n_years, n_l,
+                  infector = jb_blame_group<VM>(a, trans, mb.p, (int)mb.lsg(), v, b, ns, ntot, dyn_s, Lg, years, n_years, n_l,
                                                 T_w + (size_t)v * L, row_l[v * L + mb.lsg()], beta, dt);
                 jb_emit(a, mb.p, (uint32_t)v, g, infector);
               }
@@ -444,6 +445,7 @@ template <bool STREAM, int VM, bool EV>
 // flavour keeps its registers for the 16 gathers in flight per thread)
 __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(const __grid_constant__ GroupArgs a) {
   if (STREAM) jb_stamp(2);
+  const double* const trans = jb_trans_read(a.trans, a.NP, a.sp);
   __shared__ uint2 s_items[JB_TILE_ITEMS];  // {(block-local first slot << 5) | (len - 1), group}
   __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
   __shared__ uint32_t s_mem[STREAM ? 1 : JB_TILE_SLOTS];
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
             npk += 1u << (8 * l);
             if (q == p) my_i = (uint32_t)l;
             if ((hot & JB_PS_INFECTED) && (VM == 1 || (int)JB_HOT_VAR(hot) == v)) {
-              const double t = a.trans[q];
+              const double t = trans[q];
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (j == l) Tj[j] += t;
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
             if (((hot ^ info) & JB_PS_ACT_MASK) != 0u || !(hot & JB_PS_INFECTED) || (int)JB_TI_LSG(info) != jb) continue;
             if (VM > 1 && (int)JB_HOT_VAR(hot) != v) continue;
             const uint32_t q = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
-            c2 += a.trans[q];
+            c2 += trans[q];
             infector = q;
             if (c2 > target2) break;
           }
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
       if (m < len) {
         const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
         if (((hot ^ info) & JB_PS_ACT_MASK) == 0u && (hot & JB_PS_INFECTED))
-          jb_prefetch_l2(a.trans + (STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m]));
+          jb_prefetch_l2(trans + (STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m]));
       }
     }
     double beta = 0.0;
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
           npk += 1u << (8 * l);
           if (hot & JB_PS_INFECTED) {
             const uint32_t p = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
-            const double t = a.trans[p];
+            const double t = trans[p];
             const int pv = (VM > 1) ? (int)JB_HOT_VAR(hot) : 0;
 #pragma unroll
             for (int v = 0; v < VM; ++v)

@@ -153,7 +153,8 @@ struct StepDev {
   double now, dt, t_now;
   uint64_t seed;
   uint32_t step, activity_mask, flags, n_inject;
-  uint32_t leisure_table, epoch, pad_[2];   // epoch: steps since create (arrival-flag value of the P2P exchange)
+  uint32_t leisure_table, epoch;   // epoch: steps since create (arrival-flag value of the P2P exchange)
+  uint32_t tpar, pad_;             // tpar: which half of the double-buffered transmission probabilities this step READS
 };
 
 // Peer-memory halo exchange (jb_p2p_connect): windows of all ranks as seen from this GPU.
@@ -176,7 +177,7 @@ struct GroupArgs {
   const uint16_t* reg_info;
   const uint8_t* phot;       // per-step person byte (see above)
   const double* susc;
-  const double* trans;
+  const double* trans;       // both halves of the double buffer ([2][NP]); the step reads half sp->tpar
   const uint32_t* halo_gid;
   const uint8_t* school_years;
   const double* cm;

@@ -17,6 +17,17 @@
 
 #define JB_FULL 0xFFFFFFFFu
 
+// Transmission probabilities are double buffered ([2][NP] in one allocation): the interaction kernels of a
+// step read half `tpar` (filled by the previous step's health update) while this step's health update fills
+// the other half.  The half is a per-step scalar in the parameter block, not a kernel argument, so one
+// captured graph serves both parities.
+__device__ __forceinline__ const double* jb_trans_read(const double* base, uint32_t NP, const StepDev* sp) {
+  return base + (size_t)(sp->tpar & 1u) * NP;
+}
+__device__ __forceinline__ double* jb_trans_write(double* base, uint32_t NP, const StepDev* sp) {
+  return base + (size_t)((sp->tpar & 1u) ^ 1u) * NP;
+}
+
 // ------------------------------------------------------------------------------------------
 // Stage A: placement.  The reference walks the activity hierarchy per person and takes the first
 // activity with a non-None subgroup (activity_manager.py:380-398); stay-home policies reduce the
@@ -491,7 +502,7 @@ struct HealthArgs {
   int32_t* inf_person; const double* inf_start; const double* inf_par; double* inf_next; const double* traj_time;
   uint8_t* inf_stage; const uint8_t* inf_nst; int8_t* inf_tag; const int8_t* traj_tag;
   const uint8_t* inf_region; const int32_t* inf_hosp; int32_t* inf_med; uint8_t* inf_sev;
-  uint8_t* pstate; int8_t* ptag; double* trans; int32_t* pmed; int32_t* pslot; uint8_t* phas;
+  uint8_t* pstate; int8_t* ptag; double* trans; uint32_t NP; int32_t* pmed; int32_t* pslot; uint8_t* phas;  // trans: [2][NP], written half = tpar ^ 1
   uint32_t* counters;
   uint32_t* summary;        // [R][JB_N_SUMMARY]
   int R;
@@ -528,7 +539,7 @@ __device__ __forceinline__ double jb_gamma_pdf(double x, double a, double loc, d
 // hospital, ward, severe flag) is mirrored in the slot, so the only per-step access indexed by
 // person is the write of the new transmission probability; the person's state byte, ward and
 // tag are touched only when they change.  `sum_base` = per-region counters (shared or global).
-__device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, double t_now, uint32_t flags,
+__device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* trans, uint32_t s, double t_now, uint32_t flags,
                                                uint32_t* sum_base, HealthAcc& acc) {
   const DiseaseMasks D = a.masks;
   const int32_t p = a.inf_person[s];
@@ -536,7 +547,7 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
   const double t = t_now - a.inf_start[s];
   // transmission.update_infection_probability (infection.py:91)
   if (D.trans_type == JB_TRANS_GAMMA) {
-    a.trans[p] = a.inf_par[(size_t)3 * a.C + s] *
+    trans[p] = a.inf_par[(size_t)3 * a.C + s] *
                  jb_gamma_pdf(t, a.inf_par[s], a.inf_par[(size_t)1 * a.C + s], a.inf_par[(size_t)2 * a.C + s]);
   } else if (D.trans_type == JB_TRANS_XNEXP) {
     const double tfi = a.inf_par[(size_t)2 * a.C + s];
@@ -545,9 +556,9 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
       const double tau = (t - tfi) / a.inf_par[(size_t)4 * a.C + s];
       prob = a.inf_par[(size_t)3 * a.C + s] * (pow(tau, a.inf_par[s]) * exp(-tau / a.inf_par[(size_t)1 * a.C + s]));
     }
-    a.trans[p] = prob;
+    trans[p] = prob;
   } else {
-    a.trans[p] = a.inf_par[s];  // constant profile: carried over into the buffer the next step reads
+    trans[p] = a.inf_par[s];  // constant profile: carried over into the buffer the next step reads
   }
   // symptoms.update_trajectory_stage: at most one stage per call (symptoms.py:152-154)
   int stage = a.inf_stage[s];
@@ -597,7 +608,7 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
       st &= ~(JB_PS_INFECTED | JB_PS_SEVERE);
       a.inf_person[s] = -1;
       a.pslot[p] = -1;
-      a.trans[p] = 0.0;
+      trans[p] = 0.0;
     } else if (dead) {  // bury_the_dead (epidemiology.py:168-195)
       st &= ~(JB_PS_INFECTED | JB_PS_SEVERE | JB_PS_MEDICAL);
       st |= JB_PS_DEAD;
@@ -605,7 +616,7 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, uint32_t s, 
       a.pslot[p] = -1;
       a.pmed[p] = -1;
       a.phas[p] = 0;
-      a.trans[p] = 0.0;
+      trans[p] = 0.0;
     }
     // ptag mirrors person.infection.tag; -1 ("healthy") once the infection object is gone
     a.ptag[p] = (rec || dead) ? (int8_t)-1 : (int8_t)tag;
@@ -647,9 +658,10 @@ __device__ __forceinline__ void jb_health_body(const HealthArgs& a, uint32_t bid
   const uint32_t hw = min(a.old_only ? a.counters[CNT_SLOTS_PREV] : a.counters[CNT_SLOTS_HW], a.C);
   const double t_now = a.sp->t_now;
   const uint32_t flags = a.sp->flags;
+  double* const trans = jb_trans_write(a.trans, a.NP, a.sp);
   HealthAcc acc = {0u, 0u, 0u};
   for (uint32_t s = bid * blockDim.x + threadIdx.x; s < hw; s += nb * blockDim.x)
-    jb_health_slot(a, s, t_now, flags, sum_smem ? s_sum : a.summary, acc);
+    jb_health_slot(a, trans, s, t_now, flags, sum_smem ? s_sum : a.summary, acc);
   // block-level reduction of the "current" counters
   uint32_t c_inf = __reduce_add_sync(JB_FULL, acc.inf);
   uint32_t c_hosp = __reduce_add_sync(JB_FULL, acc.hosp);
@@ -689,8 +701,8 @@ struct NewInfArgs {
   const double* hi_cum;
   const DiseaseDev* dis;
   uint8_t* pstate; uint8_t* pvar; int8_t* ptag; double* susc; int32_t* pslot;
-  double* trans;            // the buffer the NEXT step reads
-  double* trans_other;      // the current one: written as well when no step is running (seeding)
+  double* trans;            // [2][NP]; half sp->tpar ^ 1 is the one the NEXT step reads, half sp->tpar the current one
+                            // (written as well when no step is running: seeding)
   int32_t* inf_person; double* inf_start; double* inf_par; double* inf_next; double* traj_time;
   uint8_t* inf_stage; uint8_t* inf_nst; uint8_t* inf_var; int8_t* inf_tag; int8_t* inf_maxtag; int8_t* traj_tag;
   uint8_t* inf_region; int32_t* inf_hosp; int32_t* inf_med; uint8_t* inf_sev;  // slot-resident person facts
@@ -721,6 +733,8 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
   const uint32_t segmask = 0xFFFFu << (lane & 16);
   const uint32_t n_seg = nb * blockDim.x / 16;
   const uint32_t step_flags = a.sp->flags;
+  double* const trans_next = jb_trans_write(a.trans, a.NP, a.sp);
+  double* const trans_cur = a.trans + (size_t)(a.sp->tpar & 1u) * a.NP;
   for (uint32_t i = (bid * blockDim.x + threadIdx.x) / 16; i < n; i += n_seg) {
     const uint32_t p = a.member[i];
     const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[i] : 0u;
@@ -849,7 +863,7 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
     if (a.mutate) {  // event/mutation.py:53-66: new transmission, old symptoms
       a.inf_var[slot] = (uint8_t)var;
       a.pvar[p] = (uint8_t)var;
-      a.trans[p] = a.trans_other[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
+      trans_next[p] = trans_cur[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
       continue;
     }
     a.inf_person[slot] = (int32_t)p;
@@ -867,8 +881,8 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
     a.pslot[p] = (int32_t)slot;
     a.pvar[p] = (uint8_t)var;
     a.ptag[p] = (int8_t)D.tag_exposed;
-    a.trans[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
-    if (!a.fuse_health) a.trans_other[p] = a.trans[p];
+    trans_next[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
+    if (!a.fuse_health) trans_cur[p] = trans_next[p];
     // immunity.add_immunity(infection.immunity_ids()) (infection_selector.py:160-162)
     // (cross immunity: Infection.immunity_ids, infection.py:136-191)
     const uint32_t cross = D.cross[var];
@@ -887,12 +901,12 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
                          ((D.trans_type == JB_TRANS_GAMMA && t_inf < par[1]) ||
                           (D.trans_type == JB_TRANS_XNEXP && !(t_inf > par[2])) || D.trans_type == JB_TRANS_CONSTANT);
       if (quiet) {
-        if (D.trans_type == JB_TRANS_GAMMA) a.trans[p] = par[3] * 0.0;  // norm * gamma_pdf(x < loc)
+        if (D.trans_type == JB_TRANS_GAMMA) trans_next[p] = par[3] * 0.0;  // norm * gamma_pdf(x < loc)
         atomicAdd(&a.counters[CNT_INFECTED], 1u);
         atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_CUR_INFECTED], 1u);
       } else {
         HealthAcc acc = {0u, 0u, 0u};
-        jb_health_slot(a.h, slot, a.sp->t_now, a.sp->flags, a.summary, acc);
+        jb_health_slot(a.h, trans_next, slot, a.sp->t_now, a.sp->flags, a.summary, acc);
         if (acc.inf) atomicAdd(&a.counters[CNT_INFECTED], acc.inf);
         if (acc.hosp) atomicAdd(&a.counters[CNT_HOSP], acc.hosp);
         if (acc.icu) atomicAdd(&a.counters[CNT_ICU], acc.icu);
@@ -931,9 +945,10 @@ __global__ void __launch_bounds__(256) k_mutate_select(const int32_t* __restrict
 // ------------------------------------------------------------------------------------------
 __global__ void k_halo_pack(const uint32_t* __restrict__ out_person, uint32_t n_out, const uint8_t* __restrict__ phot,
                             const double* __restrict__ susc,
-                            const double* __restrict__ trans, uint32_t NP, int V, unsigned char* __restrict__ send) {
+                            const double* __restrict__ trans2, uint32_t NP, int V, unsigned char* __restrict__ send, const StepDev* sp) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
+  const double* trans = jb_trans_read(trans2, NP, sp);
   uint32_t p = out_person[i];
   size_t rec = 8 + (size_t)8 * V;
   unsigned char* r = send + (size_t)i * rec;
@@ -950,9 +965,10 @@ __global__ void k_halo_pack(const uint32_t* __restrict__ out_person, uint32_t n_
 
 __global__ void k_halo_unpack(const unsigned char* __restrict__ recv, uint32_t H, uint32_t N, uint32_t NP, int V,
                               uint8_t* __restrict__ phot, double* __restrict__ susc,
-                              double* __restrict__ trans, uint8_t* __restrict__ halo_ret) {
+                              double* __restrict__ trans2, uint8_t* __restrict__ halo_ret, const StepDev* sp) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= H) return;
+  double* trans = trans2 + (size_t)(sp->tpar & 1u) * NP;
   size_t rec = 8 + (size_t)8 * V;
   const unsigned char* r = recv + (size_t)j * rec;
   uint64_t hdr = *(const uint64_t*)r;
@@ -987,9 +1003,10 @@ __device__ __forceinline__ void jb_p2p_signal(uint32_t* const* flags, const P2PD
 
 __global__ void __launch_bounds__(256) k_halo_push(const __grid_constant__ P2PDev P, const uint32_t* __restrict__ out_person,
                                                   uint32_t n_out, const uint8_t* __restrict__ phot,
-                                                  const double* __restrict__ susc, const double* __restrict__ trans,
+                                                  const double* __restrict__ susc, const double* __restrict__ trans2,
                                                   uint32_t NP, int V, const StepDev* sp, uint32_t* done) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* trans = jb_trans_read(trans2, NP, sp);
   if (i < n_out) {
     int q = 0;
     while (q + 1 < P.ws && i >= P.out_off[q + 1]) ++q;

@@ -235,8 +235,8 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   TRY(dev_alloc(&w->pvar, w->NP));
   TRY(dev_alloc(&w->ptag, w->N));
   TRY(dev_alloc(&w->susc, (size_t)w->V * w->NP));
-  TRY(dev_alloc(&w->trans[0], w->NP));
-  TRY(dev_alloc(&w->trans[1], w->NP));
+  TRY(dev_alloc(&w->trans[0], (size_t)2 * w->NP));   // [2][NP], one allocation (the half in use is a per-step scalar)
+  w->trans[1] = w->trans[0] + w->NP;
   TRY(dev_alloc(&w->pmed, w->N));
   TRY(dev_alloc(&w->pslot, w->N));
   TRY(dev_alloc(&w->halo_gid, w->H));
@@ -383,7 +383,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   cudaStreamSynchronize(w->stream);
   void* ptrs[] = {w->age, w->sex, w->ch, w->phas, w->school_years, w->psa, w->grp_off, w->grp_info, w->grp_aux,
                   w->reg_member, w->reg_info, w->sa_region, w->sa_hospital, w->cm, w->beta_scale, w->hi_cum, w->dis,
-                  w->pstate, w->phot, w->pvar, w->ptag, w->susc, w->trans[0], w->trans[1], w->pmed, w->pslot, w->halo_gid, w->out_person,
+                  w->pstate, w->phot, w->pvar, w->ptag, w->susc, w->trans[0], w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
@@ -895,7 +895,7 @@ static NewInfArgs make_newinf_args(JbWorld* w) {
   a.N = w->N; a.NP = w->NP; a.C = w->C; a.V = (int)w->V; a.gid_base = (uint32_t)w->id_base; a.int2ext = w->int2ext;
   a.age = w->age; a.sex = w->sex; a.ch = w->ch; a.hi_cum = w->hi_cum; a.dis = w->dis;
   a.pstate = w->pstate; a.pvar = w->pvar; a.ptag = w->ptag; a.susc = w->susc; a.pslot = w->pslot;
-  a.trans = w->trans[w->trans_par ^ 1]; a.trans_other = w->trans[w->trans_par];
+  a.trans = w->trans[0];
   a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
   a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_var = w->inf_var;
   a.inf_tag = w->inf_tag; a.inf_maxtag = w->inf_maxtag; a.traj_tag = w->traj_tag; a.counters = w->counters;
@@ -926,7 +926,7 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   a.member = d_p; a.variant = d_v; a.count_dev = nullptr; a.count_host = (uint32_t)n; a.cap = (uint32_t)n;
   StepDev sd;
   memset(&sd, 0, sizeof(sd));
-  sd.now = time; sd.seed = seed; sd.step = step;
+  sd.now = time; sd.seed = seed; sd.step = step; sd.tpar = w->trans_par;
   CK(cudaMemcpyAsync(w->d_step_aux, &sd, sizeof(sd), cudaMemcpyHostToDevice, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   a.sp = reinterpret_cast<const StepDev*>(w->d_step_aux);
@@ -966,7 +966,7 @@ extern "C" int jb_mutate(JbWorld* w, uint32_t variant, const double* regional_pr
   a.mutate = 1; a.mutate_variant = variant;
   StepDev sd;
   memset(&sd, 0, sizeof(sd));
-  sd.seed = seed; sd.step = step;
+  sd.seed = seed; sd.step = step; sd.tpar = w->trans_par;
   CK(cudaMemcpyAsync(w->d_step_aux, &sd, sizeof(sd), cudaMemcpyHostToDevice, w->stream));
   a.sp = reinterpret_cast<const StepDev*>(w->d_step_aux);
   k_newinf<<<148 * 8, 128, 0, w->stream>>>(a, w->dis_host);
@@ -1092,7 +1092,7 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   const JbStepParams& p = w->cur;
   a.grp_off = w->grp_off; a.grp_info = w->grp_info; a.grp_aux = w->grp_aux;
   a.reg_member = w->reg_member; a.reg_info = w->reg_info;
-  a.phot = w->phot; a.susc = w->susc; a.trans = w->trans[w->trans_par]; a.halo_gid = w->halo_gid;
+  a.phot = w->phot; a.susc = w->susc; a.trans = w->trans[0]; a.halo_gid = w->halo_gid;
   a.school_years = w->school_years; a.cm = w->cm + sg.cm_offset; a.beta = w->beta; a.beta_scale = w->beta_scale;
   a.dyn_cnt = sg.has_dynamic ? w->dyn_cnt : nullptr;
   const size_t ksg = &sg - w->sgs.data();
@@ -1295,13 +1295,13 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     }
   }
   if (w->p2p_on && halo_step(w)) {
-    k_halo_push<<<std::max(1u, (w->n_out + 255) / 256), 256, 0, s>>>(w->p2p, w->out_person, w->n_out, w->phot, w->susc, w->trans[w->trans_par],
+    k_halo_push<<<std::max(1u, (w->n_out + 255) / 256), 256, 0, s>>>(w->p2p, w->out_person, w->n_out, w->phot, w->susc, w->trans[0],
                                                                     w->NP, (int)w->V, step_dev(w), w->p2p_done);
     KCHECK("k_halo_push", s);
     w->launches++;
   } else if (w->n_out && d_send && halo_step(w)) {
-    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->phot, w->susc, w->trans[w->trans_par],
-                                                       w->NP, (int)w->V, (unsigned char*)d_send);
+    k_halo_pack<<<(w->n_out + 255) / 256, 256, 0, s>>>(w->out_person, w->n_out, w->phot, w->susc, w->trans[0],
+                                                       w->NP, (int)w->V, (unsigned char*)d_send, step_dev(w));
     KCHECK("k_halo_pack", s);
     w->launches++;
   }
@@ -1335,7 +1335,7 @@ static HealthArgs make_health_args(JbWorld* w, int old_only) {
   a.masks.icu_mask = w->dis_host.icu_mask; a.masks.severe_mask = w->dis_host.severe_mask;
   a.inf_person = w->inf_person; a.inf_start = w->inf_start; a.inf_par = w->inf_par; a.inf_next = w->inf_next;
   a.traj_time = w->traj_time; a.inf_stage = w->inf_stage; a.inf_nst = w->inf_nst; a.inf_tag = w->inf_tag;
-  a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans[w->trans_par ^ 1]; a.pmed = w->pmed;
+  a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans[0]; a.NP = w->NP; a.pmed = w->pmed;
   a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
   a.summary = w->summary; a.R = (int)w->R;
@@ -1367,7 +1367,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   }
   if (w->H && d_recv && halo_now) {
     k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
-                                                     w->phot, w->susc, w->trans[w->trans_par], (uint8_t*)d_ret_send);
+                                                     w->phot, w->susc, w->trans[0], (uint8_t*)d_ret_send, step_dev(w));
     KCHECK("k_halo_unpack", s);
     w->launches++;
   }
@@ -1461,37 +1461,50 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
   return JB_OK;
 }
 
-// Run one phase: replay its captured CUDA graph, capturing it on first use.  Graphs are keyed by
-// everything that shapes the launch sequence (phase, activity mask, flags, exchange buffers);
-// the per-step scalars live in the device parameter block, so a replay needs no patching.
+// Step graphs: every phase is captured once per key and replayed.  Graphs are keyed by everything that
+// shapes the launch sequence (phase, activity mask, flags, exchange buffers); the per-step scalars --
+// including which half of the transmission double buffer is read -- live in the device parameter block,
+// so a replay needs no patching and one graph serves every step with the same activities.
+static inline bool plain_launch(const JbWorld* w) {
+  return !w->use_graphs || w->timing >= 2 || jb_debug_sync() ||
+         (w->cur.flags & (JB_STEP_INJECT_UNIFORMS | JB_STEP_RECORD_LAMBDA));
+}
+
+// Index of the phase's graph in w->graphs, capturing and instantiating it first if it does not exist yet
+// (nothing is executed here: the capture happens OUTSIDE the step's timing bracket).
 template <typename F>
-static int run_phase(JbWorld* w, int phase, const void* p0, const void* p1, F&& enqueue) {
+static int ensure_graph(JbWorld* w, int phase, const void* p0, const void* p1, F&& enqueue, size_t* index) {
   const JbStepParams& p = w->cur;
-  const bool plain = !w->use_graphs || w->timing >= 2 || jb_debug_sync() ||
-                     (p.flags & (JB_STEP_INJECT_UNIFORMS | JB_STEP_RECORD_LAMBDA));
-  if (plain) return enqueue();
-  const uint64_t k0 = ((uint64_t)phase << 56) | ((uint64_t)(w->serial ? 1 : 0) << 48) | ((uint64_t)(p.leisure_table ? 1 : 0) << 49) | ((uint64_t)w->trans_par << 50) |
+  const uint64_t k0 = ((uint64_t)phase << 56) | ((uint64_t)(w->serial ? 1 : 0) << 48) | ((uint64_t)(p.leisure_table ? 1 : 0) << 49) |
                       ((uint64_t)p.activity_mask << 32) | p.flags;
   const uint64_t k1 = (uint64_t)(uintptr_t)p0, k2 = (uint64_t)(uintptr_t)p1;
-  for (const JbWorld::GraphEntry& e : w->graphs)
-    if (e.k0 == k0 && e.k1 == k1 && e.k2 == k2) {
-      CK(cudaGraphLaunch(e.exec, w->stream));
-      w->launches += e.launches;
-      return JB_OK;
-    }
+  for (size_t i = 0; i < w->graphs.size(); ++i)
+    if (w->graphs[i].k0 == k0 && w->graphs[i].k1 == k1 && w->graphs[i].k2 == k2) { *index = i; return JB_OK; }
   const uint64_t before = w->launches;
   cudaGraph_t graph = nullptr;
   CK(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
   int rc = enqueue();
   cudaError_t ce = cudaStreamEndCapture(w->stream, &graph);
-  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-  if (ce != cudaSuccess) { jb_set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return JB_ECUDA; }
   JbWorld::GraphEntry e;
   e.k0 = k0; e.k1 = k1; e.k2 = k2; e.exec = nullptr; e.launches = w->launches - before;
+  w->launches = before;  // counted when the graph is launched
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) { jb_set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return JB_ECUDA; }
   CK(cudaGraphInstantiate(&e.exec, graph, 0));
   CK(cudaGraphDestroy(graph));
+  CK(cudaGraphUpload(e.exec, w->stream));
   w->graphs.push_back(e);
-  CK(cudaGraphLaunch(e.exec, w->stream));
+  *index = w->graphs.size() - 1;
+  return JB_OK;
+}
+
+template <typename F>
+static int run_phase(JbWorld* w, int phase, const void* p0, const void* p1, F&& enqueue) {
+  if (plain_launch(w)) return enqueue();
+  size_t i = 0;
+  TRY(ensure_graph(w, phase, p0, p1, enqueue, &i));
+  CK(cudaGraphLaunch(w->graphs[i].exec, w->stream));
+  w->launches += w->graphs[i].launches;
   return JB_OK;
 }
 
@@ -1540,7 +1553,7 @@ extern "C" int jb_step_begin(JbWorld* w, const JbStepParams* p, void* d_send) {
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));  // the copy that last used this slot has finished
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
-  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq; h->tpar = w->trans_par;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
   if (int rc = run_phase(w, 0, d_send, nullptr, [&]() { return enqueue_begin(w, d_send); })) return resync_step_count(w, rc);
   CK(cudaEventRecord(w->ev_step_buf[slot], s));  // k_step_begin has read the slot once this fires
@@ -1607,21 +1620,29 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
   CK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
   w->cur = *p;
-  TRY(timing_begin(w, s));
   if ((p->flags & JB_STEP_RECORD_LAMBDA) && !w->lambda) TRY(dev_alloc(&w->lambda, w->NP));
   TRY(ensure_event_buffers(w, p->flags));
+  auto whole_step = [&]() {
+    TRY(enqueue_begin(w, nullptr));
+    TRY(enqueue_interact(w, nullptr, nullptr));
+    return enqueue_finish(w, nullptr);
+  };
+  const bool plain = plain_launch(w);
+  size_t gi = 0;
+  if (!plain) TRY(ensure_graph(w, 3, nullptr, nullptr, whole_step, &gi));  // first use of this key: captured before the bracket opens
+  TRY(timing_begin(w, s));
   const int slot = (int)(w->step_seq++ & 3);
   CK(cudaEventSynchronize(w->ev_step_buf[slot]));
   StepDev* h = reinterpret_cast<StepDev*>(w->h_step[slot]);
   h->now = p->now; h->dt = p->delta_time; h->t_now = p->now + p->delta_time; h->seed = p->seed;
-  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq;
+  h->step = p->step; h->activity_mask = p->activity_mask; h->flags = p->flags; h->n_inject = (uint32_t)w->n_inject; h->leisure_table = p->leisure_table; h->epoch = (uint32_t)w->step_seq; h->tpar = w->trans_par;
   memcpy(w->h_step[slot] + sizeof(StepDev), p->beta, sizeof(double) * (size_t)w->n_beta * w->R);
-  if (int rc = run_phase(w, 3, nullptr, nullptr, [&]() {
-        TRY(enqueue_begin(w, nullptr));
-        TRY(enqueue_interact(w, nullptr, nullptr));
-        return enqueue_finish(w, nullptr);
-      }))
-    return resync_step_count(w, rc);
+  if (plain) {
+    if (int rc = whole_step()) return resync_step_count(w, rc);
+  } else {
+    CK(cudaGraphLaunch(w->graphs[gi].exec, s));
+    w->launches += w->graphs[gi].launches;
+  }
   CK(cudaEventRecord(w->ev_step_buf[slot], s));
   w->in_step = true;  // jb_step_finish_tail expects it
   TRY(timing_end(w, s));
@@ -1654,6 +1675,30 @@ extern "C" int jb_step(JbWorld* w, const JbStepParams* p, JbStepStats* out) {
     }
   }
   return JB_OK;
+}
+
+// Capture and instantiate the graph of a step with these parameters without running it, so that no later
+// jb_step pays for a capture (bench / production set-up walks the schedule once).  Steps that exchange halo
+// persons through host-issued collectives are captured phase by phase on first use instead.
+extern "C" int jb_step_prepare(JbWorld* w, const JbStepParams* p) {
+  if (!w || !p) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(!w->in_step, "jb_step_prepare inside a step");
+  CK(cudaSetDevice(w->device));
+  const JbStepParams saved = w->cur;
+  w->cur = *p;
+  int rc = JB_OK;
+  if (!plain_launch(w) && !(halo_step_for(w, p->activity_mask) && !w->p2p_on)) {
+    rc = ensure_event_buffers(w, p->flags);
+    size_t gi = 0;
+    if (!rc)
+      rc = ensure_graph(w, 3, nullptr, nullptr, [&]() {
+        TRY(enqueue_begin(w, nullptr));
+        TRY(enqueue_interact(w, nullptr, nullptr));
+        return enqueue_finish(w, nullptr);
+      }, &gi);
+  }
+  w->cur = saved;
+  return rc;
 }
 
 // Evict the L2 between timed steps: a memset larger than the cache on the library's stream, in

@@ -351,6 +351,10 @@ class Engine:
         self._check(self._f("step")(self._h, C.byref(params), C.byref(stats) if want_stats else None))
         return stats.as_dict() if want_stats else None
 
+    def step_prepare(self, params: JbStepParams) -> None:
+        """Build (capture + instantiate) the graph of a step with these activities / flags without running it."""
+        self._check(self._f("step_prepare")(self._h, C.byref(params)))
+
     def step_begin(self, params: JbStepParams, d_send: int = 0):
         self._check(self._f("step_begin")(self._h, C.byref(params), C.c_void_p(d_send or None)))
 

@@ -315,6 +315,32 @@ class Simulator:
                                        activity_mask=self.activity_manager.activity_mask(), seed=self.seed,
                                        flags=flags | extra_flags, beta=beta, leisure_table=self.leisure_table(key))
 
+    def prepare_steps(self, days: int = 7) -> int:
+        """Build the device's step graph for every distinct (activities, flags) combination of the next
+        ``days`` days under the currently active policy set (``jb_step_prepare``: capture + instantiate,
+        nothing runs), so that no ``do_timestep`` pays for a graph capture.  Returns the number of
+        distinct step shapes."""
+        import copy
+        saved, saved_am = self.timer, self.activity_manager.timer
+        policies = self.activity_manager.policies
+        key0 = policies.active_key(saved.date)
+        extra = _lib.STEP_RECORD_EVENTS if self.record is not None else 0
+        seen = set()
+        try:
+            self.timer = self.activity_manager.timer = copy.deepcopy(saved)
+            end = self.timer.date + datetime.timedelta(days=days)
+            while self.timer.date < end and self.timer.date < self.timer.final_date:
+                if self.timer.activities and policies.active_key(self.timer.date) == key0:
+                    params = self.step_params(extra)
+                    sig = (int(params.activity_mask), int(params.flags), bool(params.leisure_table))
+                    if sig not in seen:
+                        seen.add(sig)
+                        self.device.step_prepare(params)
+                next(self.timer)
+        finally:
+            self.timer, self.activity_manager.timer = saved, saved_am
+        return len(seen)
+
     def prepare_leisure_tables(self, days: int = 7) -> int:
         """Compute and upload the leisure tables of every time slot of the next ``days`` days in one
         go (otherwise each new slot is appended -- and the captured step graphs dropped -- the first
