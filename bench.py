@@ -202,6 +202,8 @@ def run_gpu(args):
     # every step graph the schedule needs is captured and instantiated here, before anything is timed
     n_shapes = sim.prepare_steps(days=8)
     dev = sim.device
+    if rank == 0:
+        print(dev.describe(), file=sys.stderr, flush=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))
 
     def barrier():

@@ -462,6 +462,8 @@ int jb_p2p_connect(JbWorld* w, int rank, int world_size, const void* handles, co
                    const uint32_t* in_counts, const uint32_t* peer_recv_base, const uint32_t* peer_ret_base);
 
 int jb_sync(JbWorld* w);
+/* Diagnostic: text summary of the device layout (kernel flavour per supergroup) into buf[cap]. */
+int jb_world_describe(JbWorld* w, char* buf, size_t cap);
 
 /* Readback (synchronises).  `cap` = capacity of the caller's arrays, `*n` = entries written. */
 int jb_fetch_new_infections(JbWorld* w, uint32_t* member, uint32_t* variant, size_t cap, size_t* n);

@@ -139,7 +139,7 @@ ABI_SYMBOLS = [
     "set_commute", "inject_commute",
     "set_vaccination", "vaccinate", "inject_vaccination_uniforms", "fetch_vaccination",
     "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities", "set_variants", "mutate", "set_person_work_regions",
-    "step_prepare",
+    "step_prepare", "world_describe",
 ]
 
 
@@ -178,6 +178,7 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("upload_infections").argtypes = [vp, C.POINTER(JbInfectionRow), C.c_size_t]
     f("step").argtypes = [vp, C.POINTER(JbStepParams), C.POINTER(JbStepStats)]
     f("step_prepare").argtypes = [vp, C.POINTER(JbStepParams)]
+    f("world_describe").argtypes = [vp, C.c_char_p, C.c_size_t]
     f("step_begin").argtypes = [vp, C.POINTER(JbStepParams), vp]
     f("step_interact").argtypes = [vp, vp, vp]
     f("step_finish").argtypes = [vp, vp, C.POINTER(JbStepStats)]

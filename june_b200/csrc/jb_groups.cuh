@@ -62,26 +62,35 @@ struct JbMember {
   __device__ __forceinline__ bool susceptible() const { return (k >> 30) == 1u; }  // present, not infected
 };
 
+// What the member loads of one group need besides the launch arguments.
+struct JbGrp {
+  const double* trans;
+  const uint32_t* dyn_s;    // the group's sorted dynamic members (shared memory)
+  uint32_t b, ns, ntot;     // first registration, static members, static + dynamic members
+  uint32_t slot0, absmask;  // mirrored supergroup: the group's first slot in `marr`, absence bits of this step
+};
+
 // Member `idx` of group (static registered slots first, then the sorted dynamic members, which
 // the CTA has staged in shared memory as (lsg << 28) | person, sorted).
-__device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, const double* trans, uint32_t idx, uint32_t b, uint32_t ns,
-                                                   const uint32_t* dyn_s, uint32_t ntot) {
+// In a mirrored supergroup the member's byte is read from the slot-ordered array: coalesced, and in the same
+// round trip as the member index instead of behind it.
+__device__ __forceinline__ JbMember jb_load_member(const GroupArgs& a, const JbGrp& c, uint32_t idx) {
   JbMember mbr;
   mbr.p = 0; mbr.k = 0xFFFFu;
-  if (idx >= ntot) return mbr;
-  if (idx < ns) {
-    const uint32_t m = b + idx;
-    mbr.p = a.reg_member[m];
+  if (idx >= c.ntot) return mbr;
+  if (idx < c.ns) {
+    const uint32_t m = c.b + idx;
     const uint32_t info = a.reg_info[m];
-    const uint32_t hot = a.phot[mbr.p];
+    mbr.p = a.reg_member[m];
+    const uint32_t hot = a.marr ? jb_mirror_to_hot(a.marr[c.slot0 + idx], c.absmask, JB_INFO_ACT(info)) : a.phot[mbr.p];
     const uint32_t pres = (hot & JB_PS_ACT_MASK) == JB_INFO_ACT(info) ? 1u : 0u;
     mbr.k = JB_INFO_LSG(info) | (hot << 16) | (pres << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
   } else {
-    const uint32_t k = dyn_s[idx - ns];  // (lsg << 28) | caller's person index
+    const uint32_t k = c.dyn_s[idx - c.ns];  // (lsg << 28) | caller's person index
     mbr.p = a.ext2int[k & 0x0FFFFFFFu];
     // (few, scattered members: their value and id start their trips together with the hot byte's; for the
     // static members of the big company lists the extra sectors cost more than the latency they hide)
-    jb_prefetch_l2(trans + mbr.p);
+    jb_prefetch_l2(c.trans + mbr.p);
     if (mbr.p < a.N) jb_prefetch_l2(a.int2ext + mbr.p);
     const uint32_t hot = a.phot[mbr.p];
     mbr.k = (k >> 28) | (hot << 16) | (1u << 30) | ((hot & JB_PS_INFECTED) ? 1u << 31 : 0u);
@@ -115,10 +124,11 @@ __device__ __forceinline__ void jb_grp_sync() {
 // probability ~ its term of the susceptible's row; _blame_individuals (:647-662): infector with
 // probability ~ transmission probability inside that subgroup, in member order.
 template <int VM>
-__device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, const double* trans, uint32_t p, int i, int v, uint32_t b, uint32_t ns,
-                                                uint32_t ntot, const uint32_t* dyn_s, int Lg, const uint8_t* years,
+__device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, const JbGrp& gc, uint32_t p, int i, int v, int Lg, const uint8_t* years,
                                                 int n_years, const uint32_t* n_l, const double* T, double row,
                                                 double beta, double dt) {
+  const double* trans = gc.trans;
+  const uint32_t ntot = gc.ntot;
   double u_sub, u_ind;
   jb_blame_uniforms(a, p, u_sub, u_ind);
   const double target = u_sub * row;
@@ -138,7 +148,7 @@ __device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, const double
   double c2 = 0.0;
   uint32_t infector = 0xFFFFFFFFu;
   for (uint32_t idx = 0; idx < ntot; ++idx) {
-    const JbMember o = jb_load_member(a, trans, idx, b, ns, dyn_s, ntot);
+    const JbMember o = jb_load_member(a, gc, idx);
     if (!o.infector() || (int)o.lsg() != jb || (VM > 1 && (int)JB_HOT_VAR(o.hot()) != v)) continue;
     c2 += trans[o.p];
     infector = o.p;
@@ -215,6 +225,10 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
     if (a.mode == 1 && tg == 0) a.draw_cnt[g] = 0;
     return;
   }
+  JbGrp c;
+  c.trans = trans; c.dyn_s = dyn_s; c.b = b; c.ns = ns; c.ntot = ntot;
+  c.slot0 = a.marr ? a.stream_base + a.list_slot[gi_] : 0u;
+  c.absmask = a.marr ? jb_mirror_absmask(a.sp->activity_mask, a.sp->flags) : 0u;
   // number of local subgroups of this group
   int Lg = a.dim;
   const uint8_t* years = nullptr;
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 #pragma unroll
       for (int u = 0; u < JB_UB; ++u) {
         const uint32_t idx = it0 + 32 * u + lane;
-        mbs[u] = jb_load_member(a, trans, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
+        mbs[u] = jb_load_member(a, c, idx < hi ? idx : ntot);
       }
 #pragma unroll
       for (int u = 0; u < JB_UB; ++u) tvs[u] = mbs[u].infector() ? trans[mbs[u].p] : 0.0;
@@ -366,7 +380,7 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 #pragma unroll
           for (int u = 0; u < JB_UB; ++u) {
             const uint32_t idx = it0 + 32 * u + lane;
-            mbs[u] = jb_load_member(a, trans, idx < hi ? idx : ntot, b, ns, dyn_s, ntot);
+            mbs[u] = jb_load_member(a, c, idx < hi ? idx : ntot);
           }
         }
 #pragma unroll
@@ -377,6 +391,7 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
           if (it0 + 32 * u >= hi) break;
           const JbMember mb = mbs[u];
           const bool sus = mb.susceptible() && mb.lsg() < (uint32_t)Lg;
+          const uint32_t midx = it0 + 32 * u + lane;  // member index inside the group
           uint32_t ordinal = 0;
           if (a.inject) {
             const uint32_t key = mb.lsg();
@@ -400,11 +415,13 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
             }
             if (a.lambda) a.lambda[mb.p] = lam;
             if (lam != 0.0) {  // lambda == 0 can never infect
-              const int v = jb_draw_core<VM>(a, mb.p, lam_v, lam, ordinal);
+              // the Philox counter word: in a mirrored supergroup a coalesced read of the slot-ordered ids
+              const uint32_t gid = a.inject ? 0u : a.marr ? a.mgid[c.slot0 + midx] : jb_gid(a, mb.p);
+              const int v = jb_draw_core<VM>(a, gid, lam_v, lam, ordinal);
               if (v >= 0) {
                 uint32_t infector = 0xFFFFFFFFu;
                 if (EV)
-                  infector = jb_blame_group<VM>(a, trans, mb.p, (int)mb.lsg(), v, b, ns, ntot, dyn_s, Lg, years, n_years, n_l,
+                  infector = jb_blame_group<VM>(a, c, mb.p, (int)mb.lsg(), v, Lg, years, n_years, n_l,
                                                 T_w + (size_t)v * L, row_l[v * L + mb.lsg()], beta, dt);
                 jb_emit(a, mb.p, (uint32_t)v, g, infector);
               }
@@ -440,19 +457,27 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 #define JB_DRAW_QUEUE 64
 
 
-template <bool STREAM, int VM, bool EV>
+// TM: where a slot's person byte comes from.  JB_TM_GATHER: the slot holds a person index, the byte is gathered from
+// `phot`; JB_TM_STREAM: slot == person index (households), `phot` is streamed; JB_TM_MIRROR: the supergroup owns a
+// slot-ordered copy of its members' state bytes (`marr`, kept current by the placement), streamed like `phot`, and
+// slot-ordered copies of the members' ids -- nothing is gathered per slot.
+#define JB_TM_GATHER 0
+#define JB_TM_STREAM 1
+#define JB_TM_MIRROR 2
+template <int TM, int VM, bool EV>
 // (stream tiles are occupancy hungry: 48 registers measured 20 % faster than 70; the gather
 // flavour keeps its registers for the 16 gathers in flight per thread)
-__global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(const __grid_constant__ GroupArgs a) {
+__global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) k_tiles(const __grid_constant__ GroupArgs a) {
+  constexpr bool STREAM = TM == JB_TM_STREAM;
   if (STREAM) jb_stamp(2);
   const double* const trans = jb_trans_read(a.trans, a.NP, a.sp);
   __shared__ uint2 s_items[JB_TILE_ITEMS];  // {(block-local first slot << 5) | (len - 1), group}
   __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
-  __shared__ uint32_t s_mem[STREAM ? 1 : JB_TILE_SLOTS];
+  __shared__ uint32_t s_mem[TM == JB_TM_GATHER ? JB_TILE_SLOTS : 1];
   __shared__ double s_cm[16];
   __shared__ uint32_t s_n;
   __shared__ double q_lam[JB_TILE_WARPS][VM][JB_DRAW_QUEUE];
-  __shared__ uint32_t q_p[JB_TILE_WARPS][JB_DRAW_QUEUE], q_ord[JB_TILE_WARPS][JB_DRAW_QUEUE];
+  __shared__ uint32_t q_x[JB_TILE_WARPS][JB_DRAW_QUEUE], q_ord[JB_TILE_WARPS][JB_DRAW_QUEUE];  // block-local slot, ordinal
   __shared__ uint16_t q_item[JB_TILE_WARPS][JB_DRAW_QUEUE];  // work item of the queued draw (blame)
   const uint8_t* s_hot = reinterpret_cast<const uint8_t*>(s_hot4);
   const uint8_t* s_info = reinterpret_cast<const uint8_t*>(s_info4);
@@ -465,6 +490,17 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
 
   // ---- phase A ---------------------------------------------------------------------------
   const uint32_t slot_base = blockIdx.x * JB_TILE_SLOTS;  // first slot of this block
+  // person index of block-local slot x
+  auto person = [&](uint32_t x) -> uint32_t {
+    if (TM == JB_TM_STREAM) return a.stream_base + slot_base + x;
+    if (TM == JB_TM_MIRROR) return a.tp_member[slot_base + x];
+    return s_mem[x];
+  };
+  // global id (Philox counter word) of the person in block-local slot x
+  auto gid_of = [&](uint32_t x) -> uint32_t {
+    if (TM == JB_TM_MIRROR) return a.mgid[a.stream_base + slot_base + x];
+    return jb_gid(a, person(x));
+  };
   {
     const uint32_t n_chunks = a.n_tiles * 2;
     const uint32_t c = blockIdx.x * JB_TILE_THREADS + threadIdx.x;
@@ -476,8 +512,20 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
     if (ok) {
       if (!(lane & 1)) tg0 = a.tile_group0[c >> 1];  // with the other loads, not behind the bit logic
       iv = *reinterpret_cast<const uint4*>(a.tp_info + slot0);
-      if (STREAM) {
+      if (TM == JB_TM_STREAM) {
         sv = *reinterpret_cast<const uint4*>(a.phot + a.stream_base + slot0);
+      } else if (TM == JB_TM_MIRROR) {
+        // state bytes -> hot bytes, four at a time: absent (any bit of the step's absence mask) -> no activity
+        const uint4 mv = *reinterpret_cast<const uint4*>(a.marr + a.stream_base + slot0);
+        const uint32_t abs4 = jb_mirror_absmask(a.sp->activity_mask, a.sp->flags) * 0x01010101u;
+        const uint32_t act4 = (uint32_t)JB_ACT_PRIMARY * 0x01010101u  /* mirrored slots are fed by the primary activity */;
+        auto cvt = [&](uint32_t w) -> uint32_t {
+          const uint32_t ab = w & abs4;
+          const uint32_t nz = ((((ab & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | ab) >> 7) & 0x01010101u;  // 1 where absent
+          return (act4 ^ (nz * ((uint32_t)JB_ACT_PRIMARY ^ (uint32_t)JB_ACT_NONE))) | (w & 0x88888888u) |
+                 ((w & 0x07070707u) << 4);
+        };
+        sv = make_uint4(cvt(mv.x), cvt(mv.y), cvt(mv.z), cvt(mv.w));
       } else {
         uint32_t mem[16];
 #pragma unroll
@@ -565,9 +613,10 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
       double lam = 0.0;
 #pragma unroll
       for (int v = 0; v < VM; ++v) { lam_v[v] = q_lam[wib][v][lane]; lam += lam_v[v]; }
-      const uint32_t p = q_p[wib][lane];
-      const int v = jb_draw_core<VM>(a, p, lam_v, lam, q_ord[wib][lane]);
+      const uint32_t x = q_x[wib][lane];
+      const int v = jb_draw_core<VM>(a, a.inject ? 0u : gid_of(x), lam_v, lam, q_ord[wib][lane]);
       if (v >= 0) {
+        const uint32_t p = person(x);
         const uint2 it = s_items[q_item[wib][lane]];
         uint32_t infector = 0xFFFFFFFFu;
         if (EV) {
@@ -579,7 +628,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
           for (uint32_t m = 0; m < len; ++m) {
             const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
             if (((hot ^ info) & JB_PS_ACT_MASK) != 0u) continue;
-            const uint32_t q = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+            const uint32_t q = person(loc + m);
             const int l = (int)JB_TI_LSG(info);
             npk += 1u << (8 * l);
             if (q == p) my_i = (uint32_t)l;
@@ -622,7 +671,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
             const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
             if (((hot ^ info) & JB_PS_ACT_MASK) != 0u || !(hot & JB_PS_INFECTED) || (int)JB_TI_LSG(info) != jb) continue;
             if (VM > 1 && (int)JB_HOT_VAR(hot) != v) continue;
-            const uint32_t q = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+            const uint32_t q = person(loc + m);
             c2 += trans[q];
             infector = q;
             if (c2 > target2) break;
@@ -645,14 +694,18 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
     // L2 first so that the DRAM latencies overlap instead of chaining.
     if (have_item) {
       jb_prefetch_l2(a.grp_info + g);
-      const uint32_t pf = STREAM ? a.stream_base + slot_base + loc : s_mem[loc];
-      if (pf < a.N) jb_prefetch_l2(a.int2ext + pf);
+      if (TM == JB_TM_MIRROR) {
+        jb_prefetch_l2(a.mgid + a.stream_base + slot_base + loc);
+      } else {
+        const uint32_t pf = person(loc);
+        if (pf < a.N) jb_prefetch_l2(a.int2ext + pf);
+      }
     }
     for (uint32_t m = 0; m < max_len; ++m) {
       if (m < len) {
         const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
         if (((hot ^ info) & JB_PS_ACT_MASK) == 0u && (hot & JB_PS_INFECTED))
-          jb_prefetch_l2(trans + (STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m]));
+          jb_prefetch_l2(trans + person(loc + m));
       }
     }
     double beta = 0.0;
@@ -676,7 +729,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
           const int l = (int)JB_TI_LSG(info);
           npk += 1u << (8 * l);
           if (hot & JB_PS_INFECTED) {
-            const uint32_t p = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+            const uint32_t p = person(loc + m);
             const double t = trans[p];
             const int pv = (VM > 1) ? (int)JB_HOT_VAR(hot) : 0;
 #pragma unroll
@@ -691,7 +744,6 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
     // pass 2: Lambda of every susceptible (interaction.py:594-631), draws queued
     for (uint32_t m = 0; m < max_len; ++m) {
       bool sus = false;
-      uint32_t p = 0;
       double lam_v[VM];
       double lam = 0.0;
 #pragma unroll
@@ -700,7 +752,8 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
         const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
         if (((hot ^ info) & JB_PS_ACT_MASK) == 0u && !(hot & JB_PS_INFECTED)) {
           sus = true;
-          p = STREAM ? a.stream_base + slot_base + loc + m : s_mem[loc + m];
+          // the person index is only needed for a susceptibility that is neither 0 nor 1 (and in test modes)
+          const uint32_t p = (TM != JB_TM_MIRROR || VM > 1 || a.lambda || JB_HOT_CODE(hot) == JB_SC_READ) ? person(loc + m) : 0u;
           const int i = (int)JB_TI_LSG(info);
 #pragma unroll
           for (int v = 0; v < VM; ++v) {
@@ -727,7 +780,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
       if (wm) {
         if (want) {
           const uint32_t pos = qn + __popc(wm & lane_lt);
-          q_p[wib][pos] = p;
+          q_x[wib][pos] = loc + m;
           q_ord[wib][pos] = ord;
           if (EV) q_item[wib][pos] = (uint16_t)w;
 #pragma unroll
@@ -741,13 +794,13 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, STREAM ? 10 : 1) k_tiles(cons
           uint32_t mp = 0, mo = 0, mi = 0;
           double ml[VM];
           if ((uint32_t)lane < rest) {
-            mp = q_p[wib][32 + lane]; mo = q_ord[wib][32 + lane]; mi = q_item[wib][32 + lane];
+            mp = q_x[wib][32 + lane]; mo = q_ord[wib][32 + lane]; mi = q_item[wib][32 + lane];
 #pragma unroll
             for (int v = 0; v < VM; ++v) ml[v] = q_lam[wib][v][32 + lane];
           }
           __syncwarp();
           if ((uint32_t)lane < rest) {
-            q_p[wib][lane] = mp; q_ord[wib][lane] = mo; q_item[wib][lane] = (uint16_t)mi;
+            q_x[wib][lane] = mp; q_ord[wib][lane] = mo; q_item[wib][lane] = (uint16_t)mi;
 #pragma unroll
             for (int v = 0; v < VM; ++v) q_lam[wib][v][lane] = ml[v];
           }

@@ -51,6 +51,29 @@ enum { SUM_NEW_INFECTED = 0, SUM_CUR_INFECTED, SUM_CUR_HOSP, SUM_CUR_ICU, SUM_DE
 #define JB_HOT_CODE(x) (((x) >> 4) & 3u)
 #define JB_HOT_VAR(x) ((x) >> 6)
 
+// Mirror byte (slot-ordered copy of the person state for the primary-activity supergroups): the persistent
+// pstate bits -- 0-1 susceptibility code, 3 INFECTED, 4 DEAD (= absent), 5 SEVERE, 6 MEDICAL -- plus the
+// variant in bits 2 and 7.  Whether the member is present follows from the byte and the step's activity mask /
+// flags; a placement with per-person policies writes a per-step copy with bit 4 = "not at this slot".
+#define JB_MB_ABSENT 0x10u
+#define JB_MB_NONE 0xFFFFFFFFu
+__host__ __device__ inline uint32_t jb_mirror_byte(uint32_t pstate, uint32_t var) {
+  return (pstate & 0x7Bu) | ((var & 1u) << 2) | ((var & 2u) << 6);
+}
+// absent if any of these bits is set: dead, in hospital (when medical facilities are open), severe + stay-home flag
+__host__ __device__ inline uint32_t jb_mirror_absmask(uint32_t activity_mask, uint32_t flags) {
+  return JB_MB_ABSENT | ((activity_mask & (1u << JB_ACT_MEDICAL)) ? (uint32_t)JB_PS_MEDICAL : 0u) |
+         ((flags & JB_STEP_SEVERE_STAY_HOME) ? (uint32_t)JB_PS_SEVERE : 0u);
+}
+// -> the hot-byte format of `phot` (activity | INFECTED | code << 4 | variant << 6)
+__host__ __device__ inline uint32_t jb_mirror_to_hot(uint32_t mb, uint32_t absmask, uint32_t act) {
+  return ((mb & absmask) ? (uint32_t)JB_ACT_NONE : act) | (mb & 0x08u) | ((mb & 0x03u) << 4) | ((mb & 0x04u) << 4) | (mb & 0x80u);
+}
+// hot byte of a halo person (as its home domain sent it) -> mirror byte for a slot fed by `act`
+__host__ __device__ inline uint32_t jb_hot_to_mirror(uint32_t hot, uint32_t act) {
+  return ((hot & 7u) == act ? 0u : JB_MB_ABSENT) | (hot & 0x08u) | ((hot >> 4) & 0x03u) | ((hot >> 4) & 0x04u) | (hot & 0x80u);
+}
+
 // tile slot descriptor (uint8): bits 0-2 feeding activity, 3 VALID, 4 FIRST slot of its group,
 // 5-6 local subgroup (tile mode needs dim <= 4)
 #define JB_TI_VALID 0x08u
@@ -195,6 +218,13 @@ struct GroupArgs {
   const uint32_t* tp_member;
   const uint8_t* tp_info;
   uint32_t n_tiles, stream_base;
+  // mirrored supergroup (null otherwise): slot-ordered state bytes of this step (JB_MB_*), the supergroup's first
+  // slot is stream_base; list_slot[i] = first slot (relative to stream_base) of group group_list[i]
+  const uint8_t* marr;
+  const uint32_t* mgid;      // [mirror slots] global person id of the slot's member (the Philox counter word)
+  const uint32_t* list_slot;
+  const uint2* span_items;   // k_span work items: {first slot, JB_SPAN_SMALL | tiles} or {first slot, group}
+  uint32_t n_span;
   int dim, kind, L;
   uint32_t static_acts;       // activities that feed registered slots of this supergroup (bit per JB_ACT_*)
   uint32_t N, NP;
@@ -231,7 +261,11 @@ struct DiseaseDev {
 
 // Tile decomposition of one supergroup (built once at world create).
 struct SgTiles {
-  int mode = 0;               // 0 = warp per group only, 1 = gather tiles, 2 = stream tiles
+  int mode = 0;               // 0 = warp per group only, 1 = gather tiles, 2 = stream tiles, 3 = mirror tiles
+  bool has_small = false;     // some group is processed by the tile kernel
+  uint32_t *list_w_slot = nullptr, *list_c_slot = nullptr;  // mirror: first slot of the listed groups
+  uint2* span_items = nullptr;  // mirror, contact matrix <= 4x4: work items of k_span (replaces the tile kernel and the warp list)
+  uint32_t n_span = 0;
   uint32_t n_tiles = 0, stream_base = 0;
   uint32_t* tile_group0 = nullptr;
   uint32_t* tp_member = nullptr;
@@ -275,6 +309,12 @@ struct JbWorld {
   DiseaseDev* dis = nullptr;
   // person state
   uint8_t *pstate = nullptr, *phot = nullptr, *pvar = nullptr;
+  // mirror (primary-activity supergroups): persistent slot-ordered state, per-step copy written by the placement
+  // with per-person policies, the byte last pushed per person, person -> slot
+  uint8_t *mstate = nullptr, *mstep = nullptr, *pmir = nullptr;
+  uint32_t* pmslot = nullptr;
+  uint32_t* mgid = nullptr;   // [mir_slots] global id of the slot's member
+  uint32_t mir_slots = 0;
   int8_t* ptag = nullptr;
   double* susc = nullptr;
   // Transmission probabilities are double buffered: the interaction kernels of a step read trans[trans_par]

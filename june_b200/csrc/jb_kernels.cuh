@@ -66,6 +66,10 @@ struct PlaceArgs {
   const uint8_t* pwork_region;
   const double* pol_inject;  // [JB_MAX_POLICIES][JB_POLICY_DRAWS][N] or null
   int severe_mask;
+  // mirror of the primary-activity supergroups (all null when the step has no mirrored supergroup to run):
+  // table-driven placement: `pmir` = byte last pushed per person, changed bytes go to `mstate[pmslot[p]]`;
+  // per-person placement: every mirrored person's byte of THIS step goes to `mstep[pmslot[p]]`
+  uint8_t* mstate; uint8_t* mstep; uint8_t* pmir; const uint32_t* pmslot;
 };
 
 // Uniform number j of policy k for person p in this step (or the injected one, test mode).
@@ -317,8 +321,21 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
       const uint32_t med = (uint32_t)a.pmed[p];  // (hospital group << 8) | local subgroup
       jb_dyn_scatter(a, med >> 8, med & 0xFu, p);
     }
+    const uint32_t var = a.pvar ? (uint32_t)a.pvar[p] : 0u;
+    if (FULL && a.mstep) {  // this step's byte of every mirrored person (policies / leisure / commute decide per person)
+      const uint32_t slot = a.pmslot[p];
+      if (slot != JB_MB_NONE) a.mstep[slot] = (uint8_t)(jb_mirror_byte(st, var) | (act != JB_ACT_PRIMARY ? JB_MB_ABSENT : 0u));
+    }
+    if (!FULL && a.pmir) {  // persistent mirror: push the byte if it changed since it was last pushed
+      const uint32_t mb = jb_mirror_byte(st, var);
+      if (a.pmir[p] != mb) {
+        a.pmir[p] = (uint8_t)mb;
+        const uint32_t slot = a.pmslot[p];
+        if (slot != JB_MB_NONE) a.mstate[slot] = (uint8_t)mb;
+      }
+    }
     // the step's hot byte: activity | INFECTED | susceptibility code | variant
-    return act | (st & JB_PS_INFECTED) | ((st & JB_PST_CODE_MASK) << 4) | (a.pvar ? (uint32_t)a.pvar[p] << 6 : 0u);
+    return act | (st & JB_PS_INFECTED) | ((st & JB_PST_CODE_MASK) << 4) | (var << 6);
   };
   uint32_t iters = 0;
   if (FULL) {
@@ -346,6 +363,28 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
         // activity is the lowest set bit of each byte (hierarchy order == bit order).
         const uint32_t M4 = (mask & 0x1Fu) * 0x01010101u;
         const uint32_t keep_sev = ((1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE)) * 0x01010101u;
+        if (a.pmir) {
+          // persistent mirror of the primary-activity supergroups: state bytes that changed since they were last
+          // pushed (new infections, recoveries, hospital, death, vaccination: a few per cent of the people
+          // between two primary-activity steps) go to their slot
+          const uint4 pm = *reinterpret_cast<const uint4*>(a.pmir + p0);
+          const uint32_t pw[4] = {pm.x, pm.y, pm.z, pm.w};
+          uint32_t nw[4];
+          bool any = false;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            nw[q] = sw[q] & 0x7B7B7B7Bu;
+            uint32_t diff = nw[q] ^ pw[q];
+            while (diff) {
+              const uint32_t b = (uint32_t)(__ffs(diff) - 1) >> 3;
+              diff &= ~(0xFFu << (8 * b));
+              any = true;
+              const uint32_t slot = a.pmslot[p0 + q * 4 + b];
+              if (slot != JB_MB_NONE) a.mstate[slot] = (uint8_t)(nw[q] >> (8 * b));
+            }
+          }
+          if (any) *reinterpret_cast<uint4*>(a.pmir + p0) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t st4 = sw[q];
@@ -425,20 +464,21 @@ __device__ __forceinline__ void jb_emit(const GroupArgs& a, uint32_t p, uint32_t
 
 // Bernoulli draw + variant choice for one susceptible (interaction.py:610-641).  Returns the
 // variant the person caught, or -1.
+// `gid` = the person's global id (jb_gid, or the slot-ordered copy of it in a mirrored supergroup).
 template <int VM>
-__device__ __forceinline__ int jb_draw_core(const GroupArgs& a, uint32_t p, const double* lam_v, double lam,
+__device__ __forceinline__ int jb_draw_core(const GroupArgs& a, uint32_t gid, const double* lam_v, double lam,
                                             uint32_t ordinal) {
   double u;
   if (a.inject) {
     u = ordinal < a.sp->n_inject ? a.inject[ordinal] : 2.0;
   } else {
-    u = jb_bernoulli_uniform(a.sp->seed, a.sp->step, jb_gid(a, p));
+    u = jb_bernoulli_uniform(a.sp->seed, a.sp->step, gid);
   }
   if (!(u < 1.0 - exp(-lam))) return -1;
   uint32_t v = 0;
   if (VM > 1 && a.V > 1) {
     // np.random.choice(ids, p=lam_v/lam): inverse CDF on a second, independent uniform
-    double u2 = jb_variant_uniform(a.sp->seed, a.sp->step, jb_gid(a, p)) * lam;
+    double u2 = jb_variant_uniform(a.sp->seed, a.sp->step, gid) * lam;
     double c = 0.0;
     v = a.V - 1;
     for (int k = 0; k < a.V; ++k) {
@@ -460,6 +500,7 @@ __device__ __forceinline__ void jb_blame_uniforms(const GroupArgs& a, uint32_t p
 }
 
 #include "jb_groups.cuh"
+#include "jb_span.cuh"
 
 // Fix-up pass of the table-driven placement for policies whose subjects are a static, short list of
 // people (LimitLongCommute: the long-distance commuters, individual_policies.py:773-824): everyone is
@@ -479,6 +520,12 @@ __global__ void __launch_bounds__(256) k_place_subjects(const __grid_constant__ 
   const uint32_t cand = allowed & ((has & 0x1Fu) | ((st & JB_PS_MEDICAL) ? 1u << JB_ACT_MEDICAL : 0u));
   const uint32_t hot = a.phot[p], old_act = hot & JB_PS_ACT_MASK;
   uint32_t act = cand ? (uint32_t)__ffs(cand) - 1u : (uint32_t)JB_ACT_NONE;
+  if (a.mstate && (mask & (1u << JB_ACT_PRIMARY)) && act != JB_ACT_PRIMARY) {
+    // absent from its mirrored slot in this step only: the invalidated `pmir` makes the next table-driven placement
+    // push the person's byte again
+    const uint32_t slot = a.pmslot[p];
+    if (slot != JB_MB_NONE) { a.mstate[slot] = (uint8_t)(a.mstate[slot] | JB_MB_ABSENT); a.pmir[p] = 0xFFu; }
+  }
   if (act == old_act) return;
   // (a medical facility precedes every activity a policy can remove: ward bins are unaffected)
   if (old_act < JB_N_ACT) atomicSub(&a.counters[CNT_ACT0 + old_act], 1u);
@@ -963,9 +1010,19 @@ __global__ void k_halo_pack(const uint32_t* __restrict__ out_person, uint32_t n_
   }
 }
 
+// jb_set_halo_gids: the global id of every visitor that owns a slot in a mirrored supergroup.
+__global__ void k_mirror_halo_gids(const uint32_t* __restrict__ halo_mslot, const uint32_t* __restrict__ gids, uint32_t H,
+                                   uint32_t* __restrict__ mgid) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H) return;
+  const uint32_t slot = halo_mslot[j];
+  if (slot != JB_MB_NONE) mgid[slot] = gids[j];
+}
+
 __global__ void k_halo_unpack(const unsigned char* __restrict__ recv, uint32_t H, uint32_t N, uint32_t NP, int V,
                               uint8_t* __restrict__ phot, double* __restrict__ susc,
-                              double* __restrict__ trans2, uint8_t* __restrict__ halo_ret, const StepDev* sp) {
+                              double* __restrict__ trans2, uint8_t* __restrict__ halo_ret, const StepDev* sp,
+                              const uint32_t* __restrict__ pmslot, uint8_t* __restrict__ marr) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= H) return;
   double* trans = trans2 + (size_t)(sp->tpar & 1u) * NP;
@@ -976,6 +1033,10 @@ __global__ void k_halo_unpack(const unsigned char* __restrict__ recv, uint32_t H
   uint32_t p = N + j;
   uint32_t st = (uint32_t)(hdr & 0xFFu);
   phot[p] = (uint8_t)st;
+  if (marr) {  // a visitor registered in a mirrored supergroup: its byte goes to its slot as well
+    const uint32_t slot = pmslot[p];
+    if (slot != JB_MB_NONE) marr[slot] = (uint8_t)jb_hot_to_mirror(st, JB_ACT_PRIMARY);
+  }
   if (st & JB_PS_INFECTED) {
     trans[p] = d[0];
   } else {

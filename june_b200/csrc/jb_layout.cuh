@@ -13,8 +13,9 @@
 
 
 struct HostTiles {
-  int mode = 0;  // 0 warp only, 1 gather tiles, 2 stream tiles
+  int mode = 0;  // 0 warp only, 1 gather tiles, 2 stream tiles (slot == person), 3 mirror tiles (slot-ordered state copy)
   std::vector<uint32_t> tile_group0, tp_member, big;
+  std::vector<uint32_t> big_slot0;  // stream / mirror: first slot of every group in `big`
   std::vector<uint8_t> tp_info;
 };
 
@@ -24,6 +25,12 @@ struct HostLayout {
   std::vector<uint8_t> age, sex, ch, phas;
   std::vector<uint32_t> psa, reg_member;
   std::vector<HostTiles> tiles;
+  // Mirror: slot-ordered copy of the person state for the supergroups of the primary activity whose members
+  // are registered once (companies, schools).  One slot space over all mirrored supergroups:
+  // supergroup k owns [mir_base[k], mir_base[k] + tiles[k].tp_member.size()).
+  std::vector<uint32_t> mir_base;   // per supergroup (0xFFFFFFFF = not mirrored)
+  std::vector<uint32_t> pmslot;     // [N_int + H] slot of the person's mirrored registration, or 0xFFFFFFFF
+  uint32_t mir_slots = 0;
 };
 
 // Groups of more than `tile_max` slots are left to the per-group kernels (a tile lane group walks
@@ -41,10 +48,12 @@ static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool str
       pad();
       fill = 32;
       if (stream) {  // big groups still own a contiguous block of person indices (not tile-valid)
+        T.big_slot0.push_back((uint32_t)T.tp_member.size());
         for (uint32_t m = b; m < e; ++m) {
           if ((m - b) % 32 == 0) T.tile_group0.push_back(g);
           T.tp_member.push_back(d->reg_member[m]);
-          T.tp_info.push_back((uint8_t)JB_INFO_ACT(d->reg_info[m]));  // not VALID: handled by the CTA kernel
+          // not VALID: handled by the per-group kernels (the span kernel reads the subgroup bits)
+          T.tp_info.push_back((uint8_t)(JB_INFO_ACT(d->reg_info[m]) | ((JB_INFO_LSG(d->reg_info[m]) & 3u) << 5)));
         }
         pad();
       }
@@ -63,9 +72,32 @@ static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool str
 
 // Returns an error string or nullptr.
 static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSupergroup>& sgs, uint32_t tile_max_gather,
-                                   HostLayout& L) {
+                                   bool mirror_on, HostLayout& L) {
   const uint32_t N = d->n_people;
   L.tiles.assign(sgs.size(), HostTiles());
+  L.mir_base.assign(sgs.size(), 0xFFFFFFFFu);
+  // Mirrored supergroups: primary activity, static members only, every slot fed by the primary activity, every
+  // resident member has the primary activity among its fixed ones, nobody registered twice over all of them
+  // (the reference's Person.subgroups holds ONE primary_activity subgroup, person.py:20-27).  Presence of a
+  // member can then be decided from its state byte and the step's activity mask alone.
+  std::vector<uint8_t> mirrored(sgs.size(), 0);
+  if (mirror_on) {
+    std::vector<uint8_t> seen((size_t)N + d->n_halo, 0);
+    for (size_t k = 0; k < sgs.size(); ++k) {
+      const JbSupergroup& sg = sgs[k];
+      if (sg.activity != JB_ACT_PRIMARY || sg.has_dynamic || sg.n_groups == 0) continue;
+      const uint32_t m0 = d->grp_offset[sg.first_group], m1 = d->grp_offset[sg.first_group + sg.n_groups];
+      bool ok = m1 > m0;
+      for (uint32_t m = m0; ok && m < m1; ++m) {
+        const uint32_t p = d->reg_member[m];
+        if (JB_INFO_ACT(d->reg_info[m]) != JB_ACT_PRIMARY || p >= N + d->n_halo || seen[p]) ok = false;
+        else if (p < N && !(d->has_activity[p] & (1u << JB_ACT_PRIMARY))) ok = false;
+      }
+      if (!ok) continue;
+      for (uint32_t m = m0; m < m1; ++m) seen[d->reg_member[m]] = 1;
+      mirrored[k] = 1;
+    }
+  }
   // the streamed supergroup: first tile-mode residence supergroup whose slots are distinct residents
   int ks = -1;
   for (size_t k = 0; k < sgs.size() && ks < 0; ++k) {
@@ -81,11 +113,15 @@ static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSup
   }
   for (size_t k = 0; k < sgs.size(); ++k) {
     const JbSupergroup& sg = sgs[k];
-    if (sg.launch_mode != 0) continue;
+    if (sg.launch_mode != 0) {
+      // per-group kernels only; a mirrored supergroup still gets slots: every group owns a contiguous block
+      if (mirrored[k]) { L.tiles[k].mode = 3; jb_pack_tiles(d, sg, true, 0u, L.tiles[k]); }
+      continue;
+    }
     for (uint32_t m = d->grp_offset[sg.first_group]; m < d->grp_offset[sg.first_group + sg.n_groups]; ++m)
       if ((int)JB_INFO_LSG(d->reg_info[m]) >= sg.dim) return "registered member has a subgroup index >= contact matrix dimension";
-    L.tiles[k].mode = ((int)k == ks) ? 2 : 1;
-    jb_pack_tiles(d, sg, (int)k == ks, (int)k == ks ? 32u : tile_max_gather, L.tiles[k]);
+    L.tiles[k].mode = ((int)k == ks) ? 2 : mirrored[k] ? 3 : 1;
+    jb_pack_tiles(d, sg, (int)k == ks || mirrored[k], ((int)k == ks || mirrored[k]) ? 32u : tile_max_gather, L.tiles[k]);
   }
   // internal numbering
   L.ext2int.assign(N, 0xFFFFFFFFu);
@@ -113,8 +149,18 @@ static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSup
   L.reg_member.resize(d->n_members);
   for (uint32_t m = 0; m < d->n_members; ++m) L.reg_member[m] = remap(d->reg_member[m]);
   for (size_t k = 0; k < sgs.size(); ++k)
-    if (L.tiles[k].mode == 1)
+    if (L.tiles[k].mode == 1 || L.tiles[k].mode == 3)
       for (uint32_t& x : L.tiles[k].tp_member)
         if (x != 0xFFFFFFFFu) x = remap(x);
+  // mirror slot space + person -> slot map
+  L.pmslot.assign((size_t)L.N_int + d->n_halo, 0xFFFFFFFFu);
+  for (size_t k = 0; k < sgs.size(); ++k) {
+    if (L.tiles[k].mode != 3) continue;
+    L.mir_base[k] = L.mir_slots;
+    const HostTiles& T = L.tiles[k];
+    for (uint32_t s = 0; s < T.tp_member.size(); ++s)
+      if (T.tp_member[s] != 0xFFFFFFFFu) L.pmslot[T.tp_member[s]] = L.mir_slots + s;
+    L.mir_slots += (uint32_t)T.tp_member.size();
+  }
   return nullptr;
 }

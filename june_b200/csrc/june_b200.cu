@@ -174,7 +174,8 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   // internal numbering + tiles (jb_layout.cuh)
   HostLayout lay;
   {
-    const char* err = jb_build_layout(d, w->sgs, (uint32_t)std::min(32, std::max(1, jb_env_flag("JB_TILE_MAX_GATHER", 16))), lay);
+    const char* err = jb_build_layout(d, w->sgs, (uint32_t)std::min(32, std::max(1, jb_env_flag("JB_TILE_MAX_GATHER", 16))),
+                                      jb_env_flag("JB_MIRROR", 1) != 0, lay);
     REQUIRE(err == nullptr, err ? err : "");
   }
   w->N = lay.N_int; w->NP = w->N + w->H;
@@ -197,20 +198,77 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     auto gsize = [&](uint32_t g) { return d->grp_offset[g + 1] - d->grp_offset[g]; };
     std::stable_sort(rest.begin(), rest.end(), [&](uint32_t x, uint32_t y) { return gsize(x) > gsize(y); });
     std::vector<uint32_t> lw, lc;
-    for (uint32_t g : rest) ((sg.has_dynamic || gsize(g) > 32 * JB_UB) ? lc : lw).push_back(g);
+    // JB_WARP_MAX: largest group one warp processes (the warp keeps <= 128 members in registers and streams the rest)
+    static const uint32_t warp_max = (uint32_t)std::max(32, jb_env_flag("JB_WARP_MAX", 4096));
+    // A mirrored supergroup with a contact matrix of dimension <= 4 is processed by k_span: spans of small-group
+    // tiles and the groups of more than 32 slots (up to JB_SPAN_BIG_MAX) are its work items, longest first.
+    const bool span = T.mode == 3 && sg.launch_mode == 0 && sg.kind == JB_KIND_MATRIX && sg.dim <= 4 && jb_env_flag("JB_SPAN", 1) != 0;
+    static const uint32_t span_big_max = (uint32_t)std::max(32, jb_env_flag("JB_SPAN_BIG_MAX", 4096));
+    std::vector<uint32_t> span_big;
+    for (uint32_t g : rest) {
+      if (span && gsize(g) <= span_big_max) span_big.push_back(g);
+      else ((sg.has_dynamic || gsize(g) > warp_max) ? lc : lw).push_back(g);
+    }
     D.n_w = (uint32_t)lw.size(); D.n_c = (uint32_t)lc.size();
     if (D.n_w) TRY(dev_upload(&D.list_w, lw.data(), lw.size(), s));
     if (D.n_c) TRY(dev_upload(&D.list_c, lc.data(), lc.size(), s));
+    std::vector<uint32_t> lws, lcs;
+    if (T.mode == 3) {  // mirrored: first slot of every listed group
+      std::vector<uint32_t> slot_of(sg.n_groups, 0u);
+      for (size_t i = 0; i < T.big.size(); ++i) slot_of[T.big[i] - sg.first_group] = T.big_slot0[i];
+      for (uint32_t g : lw) lws.push_back(slot_of[g - sg.first_group]);
+      for (uint32_t g : lc) lcs.push_back(slot_of[g - sg.first_group]);
+      if (D.n_w) TRY(dev_upload(&D.list_w_slot, lws.data(), lws.size(), s));
+      if (D.n_c) TRY(dev_upload(&D.list_c_slot, lcs.data(), lcs.size(), s));
+      D.stream_base = lay.mir_base[k];
+      if (span) {
+        std::vector<uint2> items;
+        for (uint32_t g : span_big) items.push_back(make_uint2(slot_of[g - sg.first_group], g));
+        // runs of consecutive tiles that hold small groups
+        const uint32_t nt = (uint32_t)(T.tp_info.size() / 32);
+        auto tile_valid = [&](uint32_t t) { return (T.tp_info[(size_t)t * 32] & JB_TI_VALID) != 0; };  // a tile's first slot is valid or the tile is not
+        for (uint32_t t = 0; t < nt;) {
+          if (!tile_valid(t)) { ++t; continue; }
+          uint32_t run = 1;
+          while (run < JB_SPAN_TILES && t + run < nt && tile_valid(t + run)) ++run;
+          items.push_back(make_uint2(t * 32, JB_SPAN_SMALL | run));
+          t += run;
+        }
+        D.n_span = (uint32_t)items.size();
+        if (D.n_span) TRY(dev_upload(&D.span_items, items.data(), items.size(), s));
+      }
+    }
     CK(cudaStreamSynchronize(s));  // lw / lc are locals
     if (T.mode == 0) continue;
     D.n_tiles = (uint32_t)(T.tp_info.size() / 32);
     REQUIRE(T.tile_group0.size() == D.n_tiles, "internal: tile table size mismatch");
     TRY(dev_upload(&D.tile_group0, T.tile_group0.data(), T.tile_group0.size(), s));
     TRY(dev_upload(&D.tp_info, T.tp_info.data(), T.tp_info.size(), s));
-    if (T.mode == 1) TRY(dev_upload(&D.tp_member, T.tp_member.data(), T.tp_member.size(), s));
+    if (T.mode == 1 || T.mode == 3) TRY(dev_upload(&D.tp_member, T.tp_member.data(), T.tp_member.size(), s));
     size_t n_first = 0, n_valid = 0;
     for (uint8_t x : T.tp_info) { n_first += (x & JB_TI_FIRST) ? 1 : 0; n_valid += (x & JB_TI_VALID) ? 1 : 0; }
     D.mean_len = n_first ? (double)n_valid / (double)n_first : 0.0;
+    D.has_small = n_valid != 0;
+  }
+  if (lay.mir_slots) {
+    // slot-ordered state mirror of the primary-activity supergroups.  `pmir` starts invalid, so the first
+    // placement of a step with the primary activity pushes everybody's byte; halo slots are filled by the exchange.
+    w->mir_slots = lay.mir_slots;
+    TRY(dev_alloc(&w->mstate, (size_t)w->mir_slots + 16));
+    TRY(dev_alloc(&w->mstep, (size_t)w->mir_slots + 16));
+    TRY(dev_alloc(&w->pmir, (size_t)lay.N_int + 16));
+    TRY(dev_upload(&w->pmslot, lay.pmslot.data(), lay.pmslot.size(), s));
+    {
+      // slot-ordered global ids (the Philox counter word of a draw): residents now, visitors in jb_set_halo_gids
+      std::vector<uint32_t> mg((size_t)w->mir_slots, 0u);
+      for (uint32_t p = 0; p < lay.N_int; ++p)
+        if (lay.pmslot[p] != JB_MB_NONE) mg[lay.pmslot[p]] = (uint32_t)w->id_base + lay.int2ext[p];
+      TRY(dev_upload(&w->mgid, mg.data(), mg.size(), s));
+    }
+    CK(cudaMemsetAsync(w->mstate, JB_MB_ABSENT, (size_t)w->mir_slots + 16, s));
+    CK(cudaMemsetAsync(w->mstep, JB_MB_ABSENT, (size_t)w->mir_slots + 16, s));
+    CK(cudaMemsetAsync(w->pmir, 0xFF, (size_t)lay.N_int + 16, s));
+    CK(cudaStreamSynchronize(s));
   }
   TRY(dev_upload(&w->age, lay.age.data(), w->N, s));
   TRY(dev_upload(&w->sex, lay.sex.data(), w->N, s));
@@ -383,7 +441,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   cudaStreamSynchronize(w->stream);
   void* ptrs[] = {w->age, w->sex, w->ch, w->phas, w->school_years, w->psa, w->grp_off, w->grp_info, w->grp_aux,
                   w->reg_member, w->reg_info, w->sa_region, w->sa_hospital, w->cm, w->beta_scale, w->hi_cum, w->dis,
-                  w->pstate, w->phot, w->pvar, w->ptag, w->susc, w->trans[0], w->pmed, w->pslot, w->halo_gid, w->out_person,
+                  w->mstate, w->mstep, w->pmir, w->pmslot, w->mgid, w->pstate, w->phot, w->pvar, w->ptag, w->susc, w->trans[0], w->pmed, w->pslot, w->halo_gid, w->out_person,
                   w->inf_person, w->inf_start, w->inf_par, w->inf_next, w->traj_time, w->inf_stage, w->inf_nst,
                   w->inf_var, w->inf_tag, w->inf_maxtag, w->traj_tag, w->inf_region, w->inf_sev, w->inf_hosp, w->inf_med, w->counters, w->newinf_member, w->newinf_var,
                   w->d_step, w->d_step_aux, w->lambda, w->inject, w->draw_cnt, w->draw_base, w->dyn_bin, w->pregion,
@@ -405,6 +463,9 @@ extern "C" void jb_world_destroy(JbWorld* w) {
     if (t.tp_info) cudaFree(t.tp_info);
     if (t.list_w) cudaFree(t.list_w);
     if (t.list_c) cudaFree(t.list_c);
+    if (t.list_w_slot) cudaFree(t.list_w_slot);
+    if (t.list_c_slot) cudaFree(t.list_c_slot);
+    if (t.span_items) cudaFree(t.span_items);
   }
   for (int i = 0; i < 4; ++i) {
     if (w->ev_step_buf[i]) cudaEventDestroy(w->ev_step_buf[i]);
@@ -1082,6 +1143,11 @@ extern "C" int jb_set_halo_gids(JbWorld* w, const uint32_t* gids, size_t n) {
   REQUIRE(n == w->H, "jb_set_halo_gids: need n_halo entries");
   CK(cudaSetDevice(w->device));
   if (n) CK(cudaMemcpy(w->halo_gid, gids, n * 4, cudaMemcpyHostToDevice));
+  if (n && w->mgid) {  // visitors registered in a mirrored supergroup: their id goes to their slot as well
+    k_mirror_halo_gids<<<(unsigned)((n + 255) / 256), 256, 0, w->stream>>>(w->pmslot + w->N, w->halo_gid, (uint32_t)n, w->mgid);
+    KCHECK("k_mirror_halo_gids", w->stream);
+    CK(cudaStreamSynchronize(w->stream));
+  }
   return JB_OK;
 }
 
@@ -1092,7 +1158,7 @@ static GroupArgs make_group_args(JbWorld* w, const JbSupergroup& sg, int L) {
   const JbStepParams& p = w->cur;
   a.grp_off = w->grp_off; a.grp_info = w->grp_info; a.grp_aux = w->grp_aux;
   a.reg_member = w->reg_member; a.reg_info = w->reg_info;
-  a.phot = w->phot; a.susc = w->susc; a.trans = w->trans[0]; a.halo_gid = w->halo_gid;
+  a.phot = w->phot; a.susc = w->susc; a.trans = w->trans[0]; a.halo_gid = w->halo_gid; a.mgid = w->mgid;
   a.school_years = w->school_years; a.cm = w->cm + sg.cm_offset; a.beta = w->beta; a.beta_scale = w->beta_scale;
   a.dyn_cnt = sg.has_dynamic ? w->dyn_cnt : nullptr;
   const size_t ksg = &sg - w->sgs.data();
@@ -1130,13 +1196,31 @@ static int launch_list(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_
   return JB_OK;
 }
 
-template <bool STREAM, int VM>
+template <int VM>
+static int launch_span(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
+  const unsigned blocks = (a.n_span + JB_SPAN_WARPS - 1) / JB_SPAN_WARPS;
+  if (a.ev_group) k_span<VM, true><<<blocks, JB_SPAN_THREADS, 0, st>>>(a);
+  else k_span<VM, false><<<blocks, JB_SPAN_THREADS, 0, st>>>(a);
+  KCHECK("k_span", st);
+  return JB_OK;
+}
+
+template <int TM, int VM>
 static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
   const unsigned blocks = (a.n_tiles * 2 + JB_TILE_THREADS - 1) / JB_TILE_THREADS;
-  if (a.ev_group) k_tiles<STREAM, VM, true><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
-  else k_tiles<STREAM, VM, false><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
-  KCHECK(STREAM ? "k_tiles<stream>" : "k_tiles<gather>", st);
+  if (a.ev_group) k_tiles<TM, VM, true><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
+  else k_tiles<TM, VM, false><<<blocks, JB_TILE_THREADS, 0, st>>>(a);
+  KCHECK(TM == JB_TM_STREAM ? "k_tiles<stream>" : TM == JB_TM_MIRROR ? "k_tiles<mirror>" : "k_tiles<gather>", st);
   return JB_OK;
+}
+
+// Does this step place people one by one (individual policies, leisure or commute draws)?  Then the mirrored
+// supergroups read the per-step copy the placement writes instead of the persistent mirror.
+static inline bool step_places_per_person(const JbWorld* w) {
+  const JbStepParams& p = w->cur;
+  const bool commute = (p.activity_mask & (1u << JB_ACT_COMMUTE)) &&
+                       (w->cmt.person != nullptr || ((p.flags & JB_STEP_INJECT_COMMUTE) && w->cm_inject != nullptr));
+  return (w->n_pol != 0 && !w->pol_subject_mode) || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) || commute;
 }
 
 static int launch_groups(JbWorld* w, int mode) {
@@ -1154,8 +1238,9 @@ static int launch_groups(JbWorld* w, int mode) {
     if (tme) CK(cudaEventRecord(w->ev_sg0[k], w->stream));
     const SgTiles& T = w->tiles[k];
     const bool multi = w->V > 1;
+    if (T.mode == 3) { a.marr = step_places_per_person(w) ? w->mstep : w->mstate; a.stream_base = T.stream_base; }
     for (int u = 0; u < 3; ++u) {
-      if ((u == 0 && (T.mode == 0 || T.n_tiles == 0)) || (u == 1 && T.n_w == 0) || (u == 2 && T.n_c == 0)) continue;
+      if ((u == 0 && !T.n_span && (T.mode == 0 || T.n_tiles == 0 || !T.has_small)) || (u == 1 && T.n_w == 0) || (u == 2 && T.n_c == 0)) continue;
       static const int unit_streams = jb_env_flag("JB_UNIT_STREAMS", 1);
       cudaStream_t st = w->serial ? w->stream : w->side[k][unit_streams ? u : 0];
       if (!w->serial) CK(cudaStreamWaitEvent(st, w->ev_fork, 0));
@@ -1164,13 +1249,16 @@ static int launch_groups(JbWorld* w, int mode) {
         if (skip_b && mode == 0) a.mode = 2;
         a.tile_group0 = T.tile_group0; a.tp_member = T.tp_member; a.tp_info = T.tp_info;
         a.n_tiles = T.n_tiles; a.stream_base = T.stream_base;
-        if (T.mode == 2) { if (!multi) TRY((launch_tiles<true, 1>(w, a, st))); else TRY((launch_tiles<true, JB_MAX_VARIANTS>(w, a, st))); }
-        else { if (!multi) TRY((launch_tiles<false, 1>(w, a, st))); else TRY((launch_tiles<false, JB_MAX_VARIANTS>(w, a, st))); }
+        a.span_items = T.span_items; a.n_span = T.n_span;
+        if (T.n_span) { if (!multi) TRY((launch_span<1>(w, a, st))); else TRY((launch_span<JB_MAX_VARIANTS>(w, a, st))); }
+        else if (T.mode == 2) { if (!multi) TRY((launch_tiles<JB_TM_STREAM, 1>(w, a, st))); else TRY((launch_tiles<JB_TM_STREAM, JB_MAX_VARIANTS>(w, a, st))); }
+        else if (T.mode == 3) { if (!multi) TRY((launch_tiles<JB_TM_MIRROR, 1>(w, a, st))); else TRY((launch_tiles<JB_TM_MIRROR, JB_MAX_VARIANTS>(w, a, st))); }
+        else { if (!multi) TRY((launch_tiles<JB_TM_GATHER, 1>(w, a, st))); else TRY((launch_tiles<JB_TM_GATHER, JB_MAX_VARIANTS>(w, a, st))); }
       } else if (u == 1) {
-        a.group_list = T.list_w; a.n_list = T.n_w;
+        a.group_list = T.list_w; a.n_list = T.n_w; a.list_slot = T.list_w_slot;
         if (!multi) TRY((launch_list<1, 1>(w, a, false, st))); else TRY((launch_list<JB_MAX_VARIANTS, 1>(w, a, false, st)));
       } else {
-        a.group_list = T.list_c; a.n_list = T.n_c;
+        a.group_list = T.list_c; a.n_list = T.n_c; a.list_slot = T.list_c_slot;
         if (!multi) TRY((launch_list<1, JB_CTA_WARPS>(w, a, sg.has_dynamic != 0, st)));
         else TRY((launch_list<JB_MAX_VARIANTS, JB_CTA_WARPS>(w, a, sg.has_dynamic != 0, st)));
       }
@@ -1284,6 +1372,12 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     const uint32_t chunks = (w->N + 15) / 16;
     const bool full = (w->n_pol != 0 && !w->pol_subject_mode) || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
                       pa.cmt.person != nullptr || pa.cmt.inject != nullptr;
+    if (full != step_places_per_person(w)) { jb_set_error("internal: placement flavour mismatch"); return JB_EINVAL; }
+    if (w->mir_slots && (p.activity_mask & (1u << JB_ACT_PRIMARY))) {  // the mirrored supergroups run in this step
+      pa.pmslot = w->pmslot;
+      if (full) pa.mstep = w->mstep;
+      else { pa.mstate = w->mstate; pa.pmir = w->pmir; }
+    }
     if (full) k_place<true><<<(w->N + 255) / 256, 256, 0, s>>>(pa);
     else k_place<false><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
     KCHECK("k_place", s);
@@ -1367,7 +1461,8 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   }
   if (w->H && d_recv && halo_now) {
     k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
-                                                     w->phot, w->susc, w->trans[0], (uint8_t*)d_ret_send, step_dev(w));
+                                                     w->phot, w->susc, w->trans[0], (uint8_t*)d_ret_send, step_dev(w),
+                                                     w->pmslot, w->mir_slots ? (step_places_per_person(w) ? w->mstep : w->mstate) : nullptr);
     KCHECK("k_halo_unpack", s);
     w->launches++;
   }
@@ -1713,6 +1808,25 @@ extern "C" int jb_flush_l2(JbWorld* w, size_t bytes) {
     w->flush_bytes = bytes;
   }
   CK(cudaMemsetAsync(w->flush_buf, 0, bytes, w->stream));
+  return JB_OK;
+}
+
+// Human-readable summary of the device layout (one line per supergroup): which kernels process it and how
+// its members' bytes are read.  Diagnostic only.
+extern "C" int jb_world_describe(JbWorld* w, char* buf, size_t cap) {
+  if (!w || !buf || !cap) { jb_set_error("null argument"); return JB_EINVAL; }
+  std::string o;
+  char line[512];
+  snprintf(line, sizeof line, "people %u (internal %u, halo %u), groups %u, registrations %u, mirror slots %u\n", w->N_ext, w->N, w->H, w->G, w->M, w->mir_slots);
+  o += line;
+  static const char* modes[] = {"per-group kernels (gather)", "gather tiles", "stream tiles (slot == person)", "mirror (slot-ordered state)"};
+  for (size_t k = 0; k < w->sgs.size(); ++k) {
+    const SgTiles& T = w->tiles[k];
+    snprintf(line, sizeof line, "supergroup %zu: groups %u, activity %d, dynamic %d, %s, tiles %u%s, span items %u, warp-list %u, cta-list %u, mean tiled group %.2f\n", k,
+             w->sgs[k].n_groups, w->sgs[k].activity, w->sgs[k].has_dynamic, modes[T.mode], T.n_tiles, T.has_small ? "" : " (none valid)", T.n_span, T.n_w, T.n_c, T.mean_len);
+    o += line;
+  }
+  snprintf(buf, cap, "%s", o.c_str());
   return JB_OK;
 }
 

@@ -351,6 +351,12 @@ class Engine:
         self._check(self._f("step")(self._h, C.byref(params), C.byref(stats) if want_stats else None))
         return stats.as_dict() if want_stats else None
 
+    def describe(self) -> str:
+        """Text summary of the device layout (kernel flavour per supergroup)."""
+        buf = C.create_string_buffer(8192)
+        self._check(self._f("world_describe")(self._h, buf, len(buf)))
+        return buf.value.decode()
+
     def step_prepare(self, params: JbStepParams) -> None:
         """Build (capture + instantiate) the graph of a step with these activities / flags without running it."""
         self._check(self._f("step_prepare")(self._h, C.byref(params)))

@@ -69,7 +69,14 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
             if sg.spec in launch_modes:
                 sg.launch_mode = launch_modes[sg.spec]
     inter = Interaction.from_file()
-    eng = make_engine(kind, g.world, g.outcome_prob, interaction=inter)
+    # JB_MIRROR=0: companies / schools gather their members' bytes through the person index instead of
+    # streaming the slot-ordered state mirror (read by the CUDA library when the world is created)
+    import os
+    os.environ["JB_MIRROR"] = str((launch_modes or {}).get("_mirror", 1))
+    try:
+        eng = make_engine(kind, g.world, g.outcome_prob, interaction=inter)
+    finally:
+        os.environ.pop("JB_MIRROR", None)
     beta = default_beta_table(g.world, inter)
     n = g.world.n_people
     grp_sg = g.world.group_supergroup()
@@ -244,11 +251,13 @@ LAUNCH_MODES = {
     "tiles": {"household": 0, "company": 0, "care_home": 0},
     "warps": {"household": 1, "company": 1, "care_home": 1},
     "mixed": {"household": 1, "company": 0, "care_home": 0},
+    "tiles_gather": {"household": 0, "company": 0, "care_home": 0, "_mirror": 0},
+    "warps_gather": {"household": 1, "company": 1, "care_home": 1, "_mirror": 0},
 }
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("modes", ["tiles", "warps", "mixed"])
+@pytest.mark.parametrize("modes", ["tiles", "warps", "mixed", "tiles_gather", "warps_gather"])
 @pytest.mark.parametrize("name", FIXTURES)
 def test_cuda_matches_reference_trace(name, modes):
     assert have_gpu(), "CUDA library or device missing: the product path has no fallback"
