@@ -81,6 +81,11 @@ __host__ __device__ inline uint32_t jb_hot_to_mirror(uint32_t hot, uint32_t act)
 #define JB_TI_LSG(x) (((x) >> 5) & 3u)
 #define JB_TI_ACT(x) ((x) & 7u)
 
+// Work item kinds of k_span (item.y): bits 28-31 kind, low bits count.
+#define JB_SPAN_KIND_SMALL 1u  // count = tiles of small groups (<= 16); tile_group0 = ordinal of the tile's first group in span_group
+#define JB_SPAN_KIND_CLASS 2u  // count = groups, bits 8-15 = lanes per group (4, 8, 16 or 32: 16 slots per lane); item.z = first ordinal
+#define JB_SPAN_KIND_BIG 3u    // one group of more than 512 slots; item.z = its ordinal
+
 // Dynamic-member bins: one bin of `cap` entries per group of every supergroup with has_dynamic.
 #define JB_MAX_DYN_RANGES 12
 struct DynRanges {
@@ -223,7 +228,8 @@ struct GroupArgs {
   const uint8_t* marr;
   const uint32_t* mgid;      // [mirror slots] global person id of the slot's member (the Philox counter word)
   const uint32_t* list_slot;
-  const uint2* span_items;   // k_span work items: {first slot, JB_SPAN_SMALL | tiles} or {first slot, group}
+  const uint4* span_items;   // k_span work items (jb_pack_span): {first slot, kind | count, first ordinal, 0}
+  const uint32_t* span_group; // groups of the supergroup in slot order
   uint32_t n_span;
   int dim, kind, L;
   uint32_t static_acts;       // activities that feed registered slots of this supergroup (bit per JB_ACT_*)
@@ -264,7 +270,8 @@ struct SgTiles {
   int mode = 0;               // 0 = warp per group only, 1 = gather tiles, 2 = stream tiles, 3 = mirror tiles
   bool has_small = false;     // some group is processed by the tile kernel
   uint32_t *list_w_slot = nullptr, *list_c_slot = nullptr;  // mirror: first slot of the listed groups
-  uint2* span_items = nullptr;  // mirror, contact matrix <= 4x4: work items of k_span (replaces the tile kernel and the warp list)
+  uint4* span_items = nullptr;  // mirror, one subgroup per group: work items of k_span (replaces the tile kernel and the warp list)
+  uint32_t* span_group = nullptr;
   uint32_t n_span = 0;
   uint32_t n_tiles = 0, stream_base = 0;
   uint32_t* tile_group0 = nullptr;

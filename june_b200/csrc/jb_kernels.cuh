@@ -474,6 +474,9 @@ __device__ __forceinline__ int jb_draw_core(const GroupArgs& a, uint32_t gid, co
   } else {
     u = jb_bernoulli_uniform(a.sp->seed, a.sp->step, gid);
   }
+  // 1 - exp(-lam) <= lam: a uniform above lam (plus a margin for the rounding of exp and of the subtraction, < 4e-16)
+  // cannot succeed -- the common case, decided without the exponential; the outcome is the same either way
+  if (!(u < lam + 1e-15)) return -1;
   if (!(u < 1.0 - exp(-lam))) return -1;
   uint32_t v = 0;
   if (VM > 1 && a.V > 1) {

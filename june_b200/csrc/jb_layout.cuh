@@ -17,7 +17,83 @@ struct HostTiles {
   std::vector<uint32_t> tile_group0, tp_member, big;
   std::vector<uint32_t> big_slot0;  // stream / mirror: first slot of every group in `big`
   std::vector<uint8_t> tp_info;
+  // span layout (k_span): work items {first slot, kind | count, first entry of span_group, 0} and the groups in slot order
+  bool span = false;
+  std::vector<uint4> span_items;
+  std::vector<uint32_t> span_group;
 };
+
+// Slot layout of a mirrored supergroup with one subgroup per group, built for k_span: every warp-sized work item is
+// full.  Groups of more than 512 slots first (longest first, whole 32-slot tiles each), then the size classes
+// 257-512 / 129-256 / 65-128 / 33-64 (every group padded to 512 / 256 / 128 / 64 slots, so that 1 / 2 / 4 / 8 groups
+// fill the 512 slots a warp loads at once), then the groups of <= 32 slots packed into tiles that never split a group.
+// Groups above `big_max` slots are laid out like the others but left to the CTA-per-group kernel (no work item).
+static void jb_pack_span(const JbWorldDesc* d, const JbSupergroup& sg, uint32_t big_max, HostTiles& T) {
+  T.span = true;
+  auto gsize = [&](uint32_t g) { return d->grp_offset[g + 1] - d->grp_offset[g]; };
+  auto pad_to = [&](size_t mult) {
+    while (T.tp_member.size() % mult) { T.tp_member.push_back(0xFFFFFFFFu); T.tp_info.push_back(0); }
+  };
+  auto put_group = [&](uint32_t g) {  // members in registration order; not VALID: no tile logic applies
+    for (uint32_t m = d->grp_offset[g]; m < d->grp_offset[g + 1]; ++m) {
+      T.tp_member.push_back(d->reg_member[m]);
+      T.tp_info.push_back((uint8_t)JB_INFO_ACT(d->reg_info[m]));
+    }
+  };
+  std::vector<uint32_t> cls[5], small;  // cls[0]: > 512, cls[1]: 257-512 (32 lanes), cls[2]: 16 lanes, cls[3]: 8, cls[4]: 4
+  for (uint32_t g = sg.first_group; g < sg.first_group + sg.n_groups; ++g) {
+    const uint32_t sz = gsize(g);
+    if (sz == 0) continue;
+    if (sz <= 32) small.push_back(g);
+    else cls[sz > 512 ? 0 : sz > 256 ? 1 : sz > 128 ? 2 : sz > 64 ? 3 : 4].push_back(g);
+  }
+  std::stable_sort(cls[0].begin(), cls[0].end(), [&](uint32_t x, uint32_t y) { return gsize(x) > gsize(y); });
+  for (uint32_t g : cls[0]) {
+    pad_to(32);
+    T.big.push_back(g); T.big_slot0.push_back((uint32_t)T.tp_member.size());
+    if (gsize(g) <= big_max) {
+      T.span_items.push_back(make_uint4((uint32_t)T.tp_member.size(), JB_SPAN_KIND_BIG << 28, (uint32_t)T.span_group.size(), 0u));
+      T.span_group.push_back(g);
+    }
+    put_group(g);
+  }
+  for (int c = 1; c <= 4; ++c) {
+    const uint32_t lanes = 64u >> c, per_span = 32u / lanes;  // 32, 16, 8, 4 lanes per group
+    for (size_t i = 0; i < cls[c].size(); i += per_span) {
+      pad_to(512);
+      const uint32_t cnt = (uint32_t)std::min<size_t>(per_span, cls[c].size() - i);
+      T.span_items.push_back(make_uint4((uint32_t)T.tp_member.size(), (JB_SPAN_KIND_CLASS << 28) | (lanes << 8) | cnt, (uint32_t)T.span_group.size(), 0u));
+      for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t g = cls[c][i + j];
+        pad_to((size_t)lanes * 16);
+        T.big.push_back(g); T.big_slot0.push_back((uint32_t)T.tp_member.size());
+        T.span_group.push_back(g);
+        put_group(g);
+      }
+    }
+  }
+  pad_to(512);
+  // small groups: tiles that never split a group, 16 tiles per work item
+  const size_t small0 = T.tp_member.size();
+  T.tile_group0.assign(small0 / 32, 0u);
+  uint32_t fill = 32;
+  for (uint32_t g : small) {
+    const uint32_t sz = gsize(g);
+    if (fill + sz > 32) { pad_to(32); T.tile_group0.push_back((uint32_t)T.span_group.size()); fill = 0; }
+    T.span_group.push_back(g);
+    for (uint32_t m = d->grp_offset[g]; m < d->grp_offset[g + 1]; ++m) {
+      T.tp_member.push_back(d->reg_member[m]);
+      T.tp_info.push_back((uint8_t)(JB_INFO_ACT(d->reg_info[m]) | JB_TI_VALID | (m == d->grp_offset[g] ? JB_TI_FIRST : 0u)));
+    }
+    fill += sz;
+  }
+  pad_to(32);
+  const uint32_t n_small_tiles = (uint32_t)((T.tp_member.size() - small0) / 32);
+  for (uint32_t t = 0; t < n_small_tiles; t += 16)
+    T.span_items.push_back(make_uint4((uint32_t)small0 + t * 32, (JB_SPAN_KIND_SMALL << 28) | std::min(16u, n_small_tiles - t), 0u, 0u));
+  pad_to(512);  // the last work item may load a whole span
+  T.tile_group0.resize(T.tp_member.size() / 32, 0u);
+}
 
 struct HostLayout {
   uint32_t N_int = 0;
@@ -72,7 +148,7 @@ static void jb_pack_tiles(const JbWorldDesc* d, const JbSupergroup& sg, bool str
 
 // Returns an error string or nullptr.
 static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSupergroup>& sgs, uint32_t tile_max_gather,
-                                   bool mirror_on, HostLayout& L) {
+                                   bool mirror_on, bool span_on, uint32_t span_big_max, HostLayout& L) {
   const uint32_t N = d->n_people;
   L.tiles.assign(sgs.size(), HostTiles());
   L.mir_base.assign(sgs.size(), 0xFFFFFFFFu);
@@ -121,6 +197,7 @@ static const char* jb_build_layout(const JbWorldDesc* d, const std::vector<JbSup
     for (uint32_t m = d->grp_offset[sg.first_group]; m < d->grp_offset[sg.first_group + sg.n_groups]; ++m)
       if ((int)JB_INFO_LSG(d->reg_info[m]) >= sg.dim) return "registered member has a subgroup index >= contact matrix dimension";
     L.tiles[k].mode = ((int)k == ks) ? 2 : mirrored[k] ? 3 : 1;
+    if (mirrored[k] && span_on && sg.kind == JB_KIND_MATRIX && sg.dim == 1) { jb_pack_span(d, sg, span_big_max, L.tiles[k]); continue; }
     jb_pack_tiles(d, sg, (int)k == ks || mirrored[k], ((int)k == ks || mirrored[k]) ? 32u : tile_max_gather, L.tiles[k]);
   }
   // internal numbering

@@ -52,7 +52,13 @@ __host__ __device__ __forceinline__ JbPhilox4 jb_philox4x32_10(uint32_t c0, uint
 // 52 random bits -> double strictly inside (0,1):  (b + 0.5) * 2^-52
 __host__ __device__ __forceinline__ double jb_u52(uint32_t hi, uint32_t lo) {
   uint64_t b = (((uint64_t)hi << 32) | (uint64_t)lo) >> 12;
+#ifdef __CUDA_ARCH__
+  // the same value without the 64-bit integer -> double conversion: 1.b - 1 = b * 2^-52 and the sum
+  // (2b + 1) * 2^-53 are both exact
+  return (__longlong_as_double((long long)(0x3FF0000000000000ull | b)) - 1.0) + 1.1102230246251565e-16;
+#else
   return ((double)b + 0.5) * 2.220446049250313e-16;
+#endif
 }
 
 // The uniform a given person consumes for its Bernoulli draw in a given step.

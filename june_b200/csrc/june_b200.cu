@@ -175,7 +175,8 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   HostLayout lay;
   {
     const char* err = jb_build_layout(d, w->sgs, (uint32_t)std::min(32, std::max(1, jb_env_flag("JB_TILE_MAX_GATHER", 16))),
-                                      jb_env_flag("JB_MIRROR", 1) != 0, lay);
+                                      jb_env_flag("JB_MIRROR", 1) != 0, jb_env_flag("JB_SPAN", 1) != 0,
+                                      (uint32_t)std::max(512, jb_env_flag("JB_SPAN_BIG_MAX", 4096)), lay);
     REQUIRE(err == nullptr, err ? err : "");
   }
   w->N = lay.N_int; w->NP = w->N + w->H;
@@ -200,13 +201,12 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
     std::vector<uint32_t> lw, lc;
     // JB_WARP_MAX: largest group one warp processes (the warp keeps <= 128 members in registers and streams the rest)
     static const uint32_t warp_max = (uint32_t)std::max(32, jb_env_flag("JB_WARP_MAX", 4096));
-    // A mirrored supergroup with a contact matrix of dimension <= 4 is processed by k_span: spans of small-group
-    // tiles and the groups of more than 32 slots (up to JB_SPAN_BIG_MAX) are its work items, longest first.
-    const bool span = T.mode == 3 && sg.launch_mode == 0 && sg.kind == JB_KIND_MATRIX && sg.dim <= 4 && jb_env_flag("JB_SPAN", 1) != 0;
-    static const uint32_t span_big_max = (uint32_t)std::max(32, jb_env_flag("JB_SPAN_BIG_MAX", 4096));
-    std::vector<uint32_t> span_big;
+    // A mirrored supergroup with one subgroup per group (1x1 contact matrix: companies) is processed by k_span, whose
+    // work items the layout has built (jb_pack_span); only groups above JB_SPAN_BIG_MAX slots are left to the CTA list.
+    const bool span = T.span;
+    static const uint32_t span_big_max = (uint32_t)std::max(512, jb_env_flag("JB_SPAN_BIG_MAX", 4096));
     for (uint32_t g : rest) {
-      if (span && gsize(g) <= span_big_max) span_big.push_back(g);
+      if (span) { if (gsize(g) > span_big_max) lc.push_back(g); }
       else ((sg.has_dynamic || gsize(g) > warp_max) ? lc : lw).push_back(g);
     }
     D.n_w = (uint32_t)lw.size(); D.n_c = (uint32_t)lc.size();
@@ -222,20 +222,9 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
       if (D.n_c) TRY(dev_upload(&D.list_c_slot, lcs.data(), lcs.size(), s));
       D.stream_base = lay.mir_base[k];
       if (span) {
-        std::vector<uint2> items;
-        for (uint32_t g : span_big) items.push_back(make_uint2(slot_of[g - sg.first_group], g));
-        // runs of consecutive tiles that hold small groups
-        const uint32_t nt = (uint32_t)(T.tp_info.size() / 32);
-        auto tile_valid = [&](uint32_t t) { return (T.tp_info[(size_t)t * 32] & JB_TI_VALID) != 0; };  // a tile's first slot is valid or the tile is not
-        for (uint32_t t = 0; t < nt;) {
-          if (!tile_valid(t)) { ++t; continue; }
-          uint32_t run = 1;
-          while (run < JB_SPAN_TILES && t + run < nt && tile_valid(t + run)) ++run;
-          items.push_back(make_uint2(t * 32, JB_SPAN_SMALL | run));
-          t += run;
-        }
-        D.n_span = (uint32_t)items.size();
-        if (D.n_span) TRY(dev_upload(&D.span_items, items.data(), items.size(), s));
+        D.n_span = (uint32_t)T.span_items.size();
+        if (D.n_span) TRY(dev_upload(&D.span_items, T.span_items.data(), T.span_items.size(), s));
+        if (!T.span_group.empty()) TRY(dev_upload(&D.span_group, T.span_group.data(), T.span_group.size(), s));
       }
     }
     CK(cudaStreamSynchronize(s));  // lw / lc are locals
@@ -466,6 +455,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
     if (t.list_w_slot) cudaFree(t.list_w_slot);
     if (t.list_c_slot) cudaFree(t.list_c_slot);
     if (t.span_items) cudaFree(t.span_items);
+    if (t.span_group) cudaFree(t.span_group);
   }
   for (int i = 0; i < 4; ++i) {
     if (w->ev_step_buf[i]) cudaEventDestroy(w->ev_step_buf[i]);
@@ -1198,9 +1188,10 @@ static int launch_list(JbWorld* w, const GroupArgs& a, bool dynamic, cudaStream_
 
 template <int VM>
 static int launch_span(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
-  const unsigned blocks = (a.n_span + JB_SPAN_WARPS - 1) / JB_SPAN_WARPS;
-  if (a.ev_group) k_span<VM, true><<<blocks, JB_SPAN_THREADS, 0, st>>>(a);
-  else k_span<VM, false><<<blocks, JB_SPAN_THREADS, 0, st>>>(a);
+  constexpr unsigned warps = JB_SPAN_WARPS_OF(VM);
+  const unsigned blocks = (a.n_span + warps - 1) / warps;
+  if (a.ev_group) k_span<VM, true><<<blocks, 32 * warps, 0, st>>>(a);
+  else k_span<VM, false><<<blocks, 32 * warps, 0, st>>>(a);
   KCHECK("k_span", st);
   return JB_OK;
 }
@@ -1249,7 +1240,7 @@ static int launch_groups(JbWorld* w, int mode) {
         if (skip_b && mode == 0) a.mode = 2;
         a.tile_group0 = T.tile_group0; a.tp_member = T.tp_member; a.tp_info = T.tp_info;
         a.n_tiles = T.n_tiles; a.stream_base = T.stream_base;
-        a.span_items = T.span_items; a.n_span = T.n_span;
+        a.span_items = T.span_items; a.n_span = T.n_span; a.span_group = T.span_group;
         if (T.n_span) { if (!multi) TRY((launch_span<1>(w, a, st))); else TRY((launch_span<JB_MAX_VARIANTS>(w, a, st))); }
         else if (T.mode == 2) { if (!multi) TRY((launch_tiles<JB_TM_STREAM, 1>(w, a, st))); else TRY((launch_tiles<JB_TM_STREAM, JB_MAX_VARIANTS>(w, a, st))); }
         else if (T.mode == 3) { if (!multi) TRY((launch_tiles<JB_TM_MIRROR, 1>(w, a, st))); else TRY((launch_tiles<JB_TM_MIRROR, JB_MAX_VARIANTS>(w, a, st))); }
