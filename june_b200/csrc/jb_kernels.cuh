@@ -765,6 +765,7 @@ struct NewInfArgs {
   uint32_t mutate_variant;
   const double* effmult;    // [V][N] immunity.effective_multiplier_dict, or null (no vaccination)
   int fuse_health;          // 1 inside a step: the creating lane also runs the slot's first health update
+  uint32_t lane_min;        // from this many entries on: one lane per infection instead of sixteen
   HealthArgs h;
 };
 
@@ -776,8 +777,202 @@ struct NewInfArgs {
 // bank reads instead of a per-block staging copy behind a barrier.  The chain of dependent DRAM round
 // trips is kept short: everything indexed by the person is requested in one go, and lane 0 takes its
 // infection slot before the sampling, not after it.
-__device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const DiseaseDev& D, uint32_t bid, uint32_t nb) {
-  const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap) : a.count_host;
+// Assemble one infection from its samples (InfectionSelector._make_infection, infection_selector.py:146-332) and give
+// it its first health update; run by one lane per infection.
+__device__ __forceinline__ void jb_newinf_assemble(const NewInfArgs& a, const DiseaseDev& D, uint32_t p, uint32_t var, uint32_t st,
+                                                   uint32_t slot, uint32_t region_p, int32_t hosp_p, int32_t med_p, int idx, int k,
+                                                   int nst, const double* tstage, const double* tp, double* trans_next,
+                                                   double* trans_cur) {
+  if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); return; }
+  // trajectory: cumulative stage start times (trajectory_maker.py:215-227)
+  double cumt = 0.0, t_exposed = 0.0;
+#pragma unroll
+  for (int s = 0; s < JB_MAX_STAGES; ++s) {
+    double tt = 1e300;
+    int tg = 0;
+    if (s < nst) {
+      tt = cumt;
+      tg = D.traj_stage_tag[k][s];
+      cumt += tstage[s];
+    }
+    if (s == 1) t_exposed = tt;
+    if (!a.mutate) {  // (a mutation keeps the person's symptoms)
+      a.traj_time[(size_t)s * a.C + slot] = tt;
+      a.traj_tag[(size_t)s * a.C + slot] = (int8_t)tg;
+    }
+  }
+  // transmission (infection_selector.py:280-332)
+  double par[JB_N_TPAR] = {0, 0, 0, 0, 0};
+  if (D.trans_type == JB_TRANS_GAMMA) {
+    par[0] = tp[1]; par[1] = tp[3] + t_exposed; par[2] = 1.0 / tp[2]; par[3] = tp[0];
+  } else if (D.trans_type == JB_TRANS_XNEXP) {
+    const double tfi = tp[1] + t_exposed;
+    const double peak = t_exposed - tfi + tp[2];
+    const double norm_time = tp[4];
+    const double nn = peak / tp[3];
+    const double alpha = tp[6];
+    const double max_tau = nn * alpha * norm_time / norm_time;  // transmission_xnexp.py:119-121
+    par[0] = nn; par[1] = alpha; par[2] = tfi; par[4] = norm_time;
+    par[3] = tp[0] / (pow(max_tau, nn) * exp(-max_tau / alpha));
+  } else {
+    par[0] = tp[0];
+  }
+  for (int q = 0; q < JB_N_TPAR; ++q) a.inf_par[(size_t)q * a.C + slot] = par[q];
+  if (a.mutate) {  // event/mutation.py:53-66: new transmission, old symptoms
+    a.inf_var[slot] = (uint8_t)var;
+    a.pvar[p] = (uint8_t)var;
+    trans_next[p] = trans_cur[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
+    return;
+  }
+  a.inf_person[slot] = (int32_t)p;
+  a.inf_start[slot] = a.sp->now;
+  a.inf_next[slot] = nst > 1 ? tstage[0] : 1e300;  // == traj_time[1]
+  a.inf_stage[slot] = 0;
+  a.inf_nst[slot] = (uint8_t)nst;
+  a.inf_var[slot] = (uint8_t)var;
+  a.inf_tag[slot] = (int8_t)D.tag_exposed;
+  a.inf_maxtag[slot] = (int8_t)idx;
+  a.inf_region[slot] = (uint8_t)region_p;
+  a.inf_hosp[slot] = hosp_p;
+  a.inf_med[slot] = med_p;
+  a.inf_sev[slot] = 0;
+  a.pslot[p] = (int32_t)slot;
+  a.pvar[p] = (uint8_t)var;
+  a.ptag[p] = (int8_t)D.tag_exposed;
+  trans_next[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
+  if (!a.fuse_health) trans_cur[p] = trans_next[p];
+  // immunity.add_immunity(infection.immunity_ids()) (infection_selector.py:160-162)
+  // (cross immunity: Infection.immunity_ids, infection.py:136-191)
+  const uint32_t cross = D.cross[var];
+  for (int v = 0; v < a.V; ++v)
+    if ((cross >> v) & 1u) a.susc[(size_t)v * a.NP + p] = 0.0;
+  a.pstate[p] = (uint8_t)(((cross & 1u) ? (st & ~JB_PST_CODE_MASK) : st) | JB_PS_INFECTED);  // susceptibility code of variant 0: 0.0
+  atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_NEW_INFECTED], 1u);
+  if (a.fuse_health) {
+    // update_health_status also covers the infections created in this step
+    // (epidemiology.py:217-303 runs after infect_people); k_health handles the older slots
+    // Common case decided from registers: still in its first stage, not yet infectious, not in a
+    // ward -> the update changes nothing but the "currently infected" counts (same result as the
+    // call below, without walking its code and re-reading the slot).
+    const double t_inf = a.sp->t_now - a.sp->now;
+    const bool quiet = med_p < 0 && nst > 1 && !(t_inf > tstage[0]) &&
+                       ((D.trans_type == JB_TRANS_GAMMA && t_inf < par[1]) ||
+                        (D.trans_type == JB_TRANS_XNEXP && !(t_inf > par[2])) || D.trans_type == JB_TRANS_CONSTANT);
+    if (quiet) {
+      if (D.trans_type == JB_TRANS_GAMMA) trans_next[p] = par[3] * 0.0;  // norm * gamma_pdf(x < loc)
+      atomicAdd(&a.counters[CNT_INFECTED], 1u);
+      atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_CUR_INFECTED], 1u);
+    } else {
+      HealthAcc acc = {0u, 0u, 0u};
+      jb_health_slot(a.h, trans_next, slot, a.sp->t_now, a.sp->flags, a.summary, acc);
+      if (acc.inf) atomicAdd(&a.counters[CNT_INFECTED], acc.inf);
+      if (acc.hosp) atomicAdd(&a.counters[CNT_HOSP], acc.hosp);
+      if (acc.icu) atomicAdd(&a.counters[CNT_ICU], acc.icu);
+    }
+  }
+}
+
+// Which trajectory a new infection follows: max_severity -> outcome slot (symptoms.py:47,110-120;
+// health_index.py:151-182), np.searchsorted(side="left") over the person's cumulative outcome probabilities, after
+// HealthIndexGenerator.apply_effective_multiplier (health_index.py:183-204) when the person's multiplier is not 1:
+// the mass of the outcomes from "severe" upwards (+ the residual) is scaled, the milder ones renormalised; the sums
+// run in index order, like the sequential reference.  One lane does it all (the variant of the 16-lane code below).
+__device__ __forceinline__ int jb_newinf_outcome(const DiseaseDev& D, const double* cum, double mult, double max_sev) {
+  int idx = 0;
+  if (mult == 1.0) {
+    for (int j = 0; j < D.n_tags; ++j) idx += cum[j] < max_sev ? 1 : 0;
+  } else {
+    const int max_mild = __ffs(D.severe_mask) - 1 - 2;
+    double total = 0.0, mild = 0.0, severe = 0.0, prev = 0.0;
+    for (int j = 0; j < D.n_tags; ++j) {
+      const double c = cum[j], x = c - (j ? prev : 0.0);
+      prev = c;
+      total += x;
+      if (j < max_mild) mild += x; else severe += x;
+    }
+    severe += 1 - total;
+    const double mod_severe = severe * mult, mod_mild = 1.0 - mod_severe;
+    double run = 0.0;
+    prev = 0.0;
+    for (int j = 0; j < D.n_tags; ++j) {
+      const double c = cum[j], pr = c - (j ? prev : 0.0);
+      prev = c;
+      run += j < max_mild ? pr * mod_mild / mild : pr * mod_severe / severe;
+      idx += run < max_sev ? 1 : 0;
+    }
+  }
+  return idx >= D.n_tags ? D.n_tags - 1 : idx;  // residual mass of a cumsum ending at 1-eps
+}
+
+// The distribution sample slot j (1..15) of a new infection draws from, or null: 1..8 stage j-1 of trajectory k,
+// 9..14 transmission parameter j-9, 15 the second `alpha()` call of the xnexp profile.
+__device__ __forceinline__ const JbDist* jb_newinf_dist(const DiseaseDev& D, int j, int k, int nst, uint32_t var) {
+  if (j >= 1 && j <= 8) return (j - 1 < nst) ? &D.traj_stage_time[k][j - 1] : nullptr;
+  if (j >= 9) {
+    const int q = (j == 15) ? 3 : j - 9;
+    const int need = D.trans_type == JB_TRANS_GAMMA ? 4 : D.trans_type == JB_TRANS_XNEXP ? 5 : 1;
+    if (q < need && (j != 15 || D.trans_type == JB_TRANS_XNEXP)) return &D.trans_par_v[var][q];
+  }
+  return nullptr;
+}
+
+// One LANE per new infection: the lane draws the infection's samples one after the other.  Sixteen times fewer
+// warp instructions than the 16-lane form below (whose lanes run different samplers, one branch after the other);
+// the price is a sixteen times longer chain per infection, so this form is used when there are enough new
+// infections to fill the device with one infection per lane.  Same Philox streams, same results.
+__device__ __forceinline__ void jb_newinf_lanes(const NewInfArgs& a, const DiseaseDev& D, uint32_t n) {
+  const uint32_t step_flags = a.sp->flags;
+  double* const trans_next = jb_trans_write(a.trans, a.NP, a.sp);
+  double* const trans_cur = a.trans + (size_t)(a.sp->tpar & 1u) * a.NP;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = a.member[i];
+    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[i] : 0u;
+    if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
+      if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
+      atomicAdd(&a.counters[CNT_HALO_INF], 1u);
+      continue;
+    }
+    if (step_flags & JB_STEP_NO_NEW_INFECTIONS) continue;
+    const uint32_t st = a.pstate[p];
+    const uint32_t ext = a.int2ext[p];
+    const uint32_t age_raw = a.age[p], sex_p = a.sex[p], ch_p = a.ch[p];
+    const uint32_t region_p = a.pregion[p], sa_p = a.psa[p];
+    const int32_t med_p = a.pmed[p];
+    if (!a.mutate && (st & (JB_PS_INFECTED | JB_PS_DEAD))) continue;
+    if (a.mutate && !(st & JB_PS_INFECTED)) continue;
+    const uint32_t slot = a.mutate ? (uint32_t)a.pslot[p] : atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);
+    const int32_t hosp_p = a.sa_hospital[sa_p];
+    const uint32_t gid = a.gid_base + ext;
+    JbStream r0;
+    jb_stream_init(r0, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0);
+    const double max_sev = jb_stream_next(r0);
+    const int age = age_raw > 99u ? 99 : (int)age_raw;
+    const int pop = (ch_p && age >= 50) ? 1 : 0;
+    const double* cum = a.hi_cum + ((size_t)(pop * 2 + sex_p) * 100 + age) * D.n_tags;
+    const double mult = a.effmult ? a.effmult[(size_t)var * a.N + p] : 1.0;
+    const int idx = jb_newinf_outcome(D, cum, mult, max_sev);
+    int k = 0;
+    for (int t = 0; t < D.n_traj; ++t)
+      if (D.traj_max_tag[t] == idx) k = t;
+    const int nst = D.traj_n_stages[k];
+    double xs[16];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) {
+      const JbDist* dist = jb_newinf_dist(D, j, k, nst, var);
+      double x = 0.0;
+      if (dist) {
+        JbStream rs;
+        jb_stream_init(rs, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
+        x = jb_sample_dist(rs, dist->type, dist->p);
+      }
+      xs[j] = x;
+    }
+    if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
+    jb_newinf_assemble(a, D, p, var, st, slot, region_p, hosp_p, med_p, idx, k, nst, xs + 1, xs + 9, trans_next, trans_cur);
+  }
+}
+
+__device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const DiseaseDev& D, uint32_t bid, uint32_t nb, uint32_t n) {
   if ((uint64_t)bid * (blockDim.x / 16) >= n) return;  // nothing for this block
   const int lane = threadIdx.x & 31, j = lane & 15;
   const uint32_t segmask = 0xFFFFu << (lane & 16);
@@ -857,15 +1052,7 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
     {
       JbStream rs;
       jb_stream_init(rs, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
-      const JbDist* dist = nullptr;  // one call site: the sampler is a real function (instruction footprint)
-      if (j >= 1 && j <= 8) {
-        const int s = j - 1;
-        if (s < nst) dist = &D.traj_stage_time[k][s];
-      } else if (j >= 9) {
-        const int q = (j == 15) ? 3 : j - 9;
-        const int need = D.trans_type == JB_TRANS_GAMMA ? 4 : D.trans_type == JB_TRANS_XNEXP ? 5 : 1;
-        if (q < need && (j != 15 || D.trans_type == JB_TRANS_XNEXP)) dist = &D.trans_par_v[var][q];
-      }
+      const JbDist* dist = jb_newinf_dist(D, j, k, nst, var);  // one call site: the sampler is a real function (instruction footprint)
       if (dist) x = jb_sample_dist(rs, dist->type, dist->p);
     }
     // lane 0 of the segment assembles the infection
@@ -876,98 +1063,19 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
     for (int q = 0; q < 7; ++q) tp[q] = __shfl_sync(segmask, x, 9 + q, 16);
     if (j != 0) continue;
     if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
-    // trajectory: cumulative stage start times (trajectory_maker.py:215-227)
-    double cumt = 0.0, t_exposed = 0.0;
-#pragma unroll
-    for (int s = 0; s < JB_MAX_STAGES; ++s) {
-      double tt = 1e300;
-      int tg = 0;
-      if (s < nst) {
-        tt = cumt;
-        tg = D.traj_stage_tag[k][s];
-        cumt += tstage[s];
-      }
-      if (s == 1) t_exposed = tt;
-      if (!a.mutate) {  // (a mutation keeps the person's symptoms)
-        a.traj_time[(size_t)s * a.C + slot] = tt;
-        a.traj_tag[(size_t)s * a.C + slot] = (int8_t)tg;
-      }
-    }
-    // transmission (infection_selector.py:280-332)
-    double par[JB_N_TPAR] = {0, 0, 0, 0, 0};
-    if (D.trans_type == JB_TRANS_GAMMA) {
-      par[0] = tp[1]; par[1] = tp[3] + t_exposed; par[2] = 1.0 / tp[2]; par[3] = tp[0];
-    } else if (D.trans_type == JB_TRANS_XNEXP) {
-      const double tfi = tp[1] + t_exposed;
-      const double peak = t_exposed - tfi + tp[2];
-      const double norm_time = tp[4];
-      const double nn = peak / tp[3];
-      const double alpha = tp[6];
-      const double max_tau = nn * alpha * norm_time / norm_time;  // transmission_xnexp.py:119-121
-      par[0] = nn; par[1] = alpha; par[2] = tfi; par[4] = norm_time;
-      par[3] = tp[0] / (pow(max_tau, nn) * exp(-max_tau / alpha));
-    } else {
-      par[0] = tp[0];
-    }
-    for (int q = 0; q < JB_N_TPAR; ++q) a.inf_par[(size_t)q * a.C + slot] = par[q];
-    if (a.mutate) {  // event/mutation.py:53-66: new transmission, old symptoms
-      a.inf_var[slot] = (uint8_t)var;
-      a.pvar[p] = (uint8_t)var;
-      trans_next[p] = trans_cur[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
-      continue;
-    }
-    a.inf_person[slot] = (int32_t)p;
-    a.inf_start[slot] = a.sp->now;
-    a.inf_next[slot] = nst > 1 ? tstage[0] : 1e300;  // == traj_time[1]
-    a.inf_stage[slot] = 0;
-    a.inf_nst[slot] = (uint8_t)nst;
-    a.inf_var[slot] = (uint8_t)var;
-    a.inf_tag[slot] = (int8_t)D.tag_exposed;
-    a.inf_maxtag[slot] = (int8_t)idx;
-    a.inf_region[slot] = (uint8_t)region_p;
-    a.inf_hosp[slot] = hosp_p;
-    a.inf_med[slot] = med_p;
-    a.inf_sev[slot] = 0;
-    a.pslot[p] = (int32_t)slot;
-    a.pvar[p] = (uint8_t)var;
-    a.ptag[p] = (int8_t)D.tag_exposed;
-    trans_next[p] = (D.trans_type == JB_TRANS_CONSTANT) ? par[0] : 0.0;
-    if (!a.fuse_health) trans_cur[p] = trans_next[p];
-    // immunity.add_immunity(infection.immunity_ids()) (infection_selector.py:160-162)
-    // (cross immunity: Infection.immunity_ids, infection.py:136-191)
-    const uint32_t cross = D.cross[var];
-    for (int v = 0; v < a.V; ++v)
-      if ((cross >> v) & 1u) a.susc[(size_t)v * a.NP + p] = 0.0;
-    a.pstate[p] = (uint8_t)(((cross & 1u) ? (st & ~JB_PST_CODE_MASK) : st) | JB_PS_INFECTED);  // susceptibility code of variant 0: 0.0
-    atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_NEW_INFECTED], 1u);
-    if (a.fuse_health) {
-      // update_health_status also covers the infections created in this step
-      // (epidemiology.py:217-303 runs after infect_people); k_health handles the older slots
-      // Common case decided from registers: still in its first stage, not yet infectious, not in a
-      // ward -> the update changes nothing but the "currently infected" counts (same result as the
-      // call below, without walking its code and re-reading the slot).
-      const double t_inf = a.sp->t_now - a.sp->now;
-      const bool quiet = med_p < 0 && nst > 1 && !(t_inf > tstage[0]) &&
-                         ((D.trans_type == JB_TRANS_GAMMA && t_inf < par[1]) ||
-                          (D.trans_type == JB_TRANS_XNEXP && !(t_inf > par[2])) || D.trans_type == JB_TRANS_CONSTANT);
-      if (quiet) {
-        if (D.trans_type == JB_TRANS_GAMMA) trans_next[p] = par[3] * 0.0;  // norm * gamma_pdf(x < loc)
-        atomicAdd(&a.counters[CNT_INFECTED], 1u);
-        atomicAdd(&a.summary[region_p * JB_N_SUMMARY + SUM_CUR_INFECTED], 1u);
-      } else {
-        HealthAcc acc = {0u, 0u, 0u};
-        jb_health_slot(a.h, trans_next, slot, a.sp->t_now, a.sp->flags, a.summary, acc);
-        if (acc.inf) atomicAdd(&a.counters[CNT_INFECTED], acc.inf);
-        if (acc.hosp) atomicAdd(&a.counters[CNT_HOSP], acc.hosp);
-        if (acc.icu) atomicAdd(&a.counters[CNT_ICU], acc.icu);
-      }
-    }
+    jb_newinf_assemble(a, D, p, var, st, slot, region_p, hosp_p, med_p, idx, k, nst, tstage, tp, trans_next, trans_cur);
   }
 }
 
+// JB_NEWINF_LANE_MIN: from this many new infections on, one lane per infection (jb_newinf_lanes); below, sixteen.
+#ifndef JB_NEWINF_LANE_MIN
+#define JB_NEWINF_LANE_MIN 16384u
+#endif
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
   jb_stamp(6);
-  jb_newinf_body(a, D, blockIdx.x, gridDim.x);
+  const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap) : a.count_host;
+  if (n >= a.lane_min) jb_newinf_lanes(a, D, n);
+  else jb_newinf_body(a, D, blockIdx.x, gridDim.x, n);
   jb_stamp_max(3);
 }
 

@@ -28,6 +28,9 @@
 // warps per CTA: the parking area is 4 KB per warp and variant, and static shared memory ends at 48 KB
 #define JB_SPAN_WARPS_OF(VM) ((VM) == 1 ? 4 : 2)
 #define JB_SPAN_QUEUE 64
+#ifndef JB_SPAN_MINB
+#define JB_SPAN_MINB 10  // resident CTAs per SM the single-variant kernel is compiled for (48 registers; measured: 8 -> 317 us, 10 -> 285 us, 12 -> 299 us at 56 M people)
+#endif
 
 __device__ __forceinline__ uint32_t jb_mb_var(uint32_t mb) { return ((mb >> 2) & 1u) | ((mb >> 6) & 2u); }
 
@@ -157,7 +160,7 @@ __device__ __noinline__ void jb_span_drain(const GroupArgs& a, uint32_t n, uint3
 }
 
 template <int VM, bool EV>
-__global__ void __launch_bounds__(32 * JB_SPAN_WARPS_OF(VM), VM == 1 && !EV ? 8 : 1) k_span(const __grid_constant__ GroupArgs a) {
+__global__ void __launch_bounds__(32 * JB_SPAN_WARPS_OF(VM), VM == 1 && !EV ? JB_SPAN_MINB : 1) k_span(const __grid_constant__ GroupArgs a) {
   jb_stamp(3); jb_stamp(4);
   JbSpanSmem<VM, EV>& s = jb_span_smem<VM, EV>();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

@@ -954,6 +954,7 @@ static NewInfArgs make_newinf_args(JbWorld* w) {
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
   a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.pmed = w->pmed;
   a.effmult = w->effmult;
+  a.lane_min = (uint32_t)std::max(0, jb_env_flag("JB_NEWINF_LANE_MIN", (int)JB_NEWINF_LANE_MIN));  // (read when a step graph is built)
   return a;
 }
 
