@@ -294,6 +294,11 @@ struct JbWorld {
   cudaEvent_t ev_fork = nullptr, ev_join[JB_MAX_SUPERGROUPS][3] = {};
   cudaStream_t side_health = nullptr;
   cudaEvent_t ev_fork_health = nullptr, ev_join_health = nullptr;
+  // arrival of the visitors (wait + unpack) runs beside the supergroups that hold no visitor registration
+  cudaStream_t side_halo = nullptr;
+  cudaEvent_t ev_fork_halo = nullptr, ev_halo_ready = nullptr;
+  bool halo_async = false;                 // this step: ev_halo_ready gates the supergroups with visitors
+  std::vector<uint8_t> sg_has_halo;        // supergroup has registrations of visitors (persons >= N)
   bool serial = false;
   // N = residents in the INTERNAL numbering (includes padding slots of the streamed supergroup),
   // N_ext = residents as the caller numbers them

@@ -740,6 +740,7 @@ struct NewInfArgs {
   const uint32_t* member;   // person indices (local, or >= N for halo: skipped here)
   const uint8_t* variant;
   const uint32_t* count_dev;  // number of entries (device) or null -> count_host
+  const uint32_t* first_dev;  // first entry of the list to walk (device; residents infected abroad follow the step's own list) or null = 0
   uint32_t count_host;
   uint32_t cap;
   uint32_t N, NP, C;
@@ -920,13 +921,13 @@ __device__ __forceinline__ const JbDist* jb_newinf_dist(const DiseaseDev& D, int
 // warp instructions than the 16-lane form below (whose lanes run different samplers, one branch after the other);
 // the price is a sixteen times longer chain per infection, so this form is used when there are enough new
 // infections to fill the device with one infection per lane.  Same Philox streams, same results.
-__device__ __forceinline__ void jb_newinf_lanes(const NewInfArgs& a, const DiseaseDev& D, uint32_t n) {
+__device__ __forceinline__ void jb_newinf_lanes(const NewInfArgs& a, const DiseaseDev& D, uint32_t first, uint32_t n) {
   const uint32_t step_flags = a.sp->flags;
   double* const trans_next = jb_trans_write(a.trans, a.NP, a.sp);
   double* const trans_cur = a.trans + (size_t)(a.sp->tpar & 1u) * a.NP;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = a.member[i];
-    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[i] : 0u;
+    const uint32_t p = a.member[first + i];
+    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[first + i] : 0u;
     if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
       if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
       atomicAdd(&a.counters[CNT_HALO_INF], 1u);
@@ -972,7 +973,7 @@ __device__ __forceinline__ void jb_newinf_lanes(const NewInfArgs& a, const Disea
   }
 }
 
-__device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const DiseaseDev& D, uint32_t bid, uint32_t nb, uint32_t n) {
+__device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const DiseaseDev& D, uint32_t bid, uint32_t nb, uint32_t first, uint32_t n) {
   if ((uint64_t)bid * (blockDim.x / 16) >= n) return;  // nothing for this block
   const int lane = threadIdx.x & 31, j = lane & 15;
   const uint32_t segmask = 0xFFFFu << (lane & 16);
@@ -981,8 +982,8 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
   double* const trans_next = jb_trans_write(a.trans, a.NP, a.sp);
   double* const trans_cur = a.trans + (size_t)(a.sp->tpar & 1u) * a.NP;
   for (uint32_t i = (bid * blockDim.x + threadIdx.x) / 16; i < n; i += n_seg) {
-    const uint32_t p = a.member[i];
-    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[i] : 0u;
+    const uint32_t p = a.member[first + i];
+    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[first + i] : 0u;
     if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
       if (j == 0) {
         if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
@@ -1073,9 +1074,10 @@ __device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const Diseas
 #endif
 __global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
   jb_stamp(6);
-  const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap) : a.count_host;
-  if (n >= a.lane_min) jb_newinf_lanes(a, D, n);
-  else jb_newinf_body(a, D, blockIdx.x, gridDim.x, n);
+  const uint32_t first = a.first_dev ? min(*a.first_dev, a.cap) : 0u;
+  const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap - first) : a.count_host;
+  if (n >= a.lane_min) jb_newinf_lanes(a, D, first, n);
+  else jb_newinf_body(a, D, blockIdx.x, gridDim.x, first, n);
   jb_stamp_max(3);
 }
 
@@ -1201,10 +1203,15 @@ __global__ void __launch_bounds__(256) k_halo_push(const __grid_constant__ P2PDe
 // One thread per peer spins (bounded) until that peer's flag for this step has arrived.
 // `dead` is sticky: after one timeout (a peer is gone or out of step) later waits return at once,
 // every step reports JB_ECAP, and a queued run drains instead of waiting again and again.
-__global__ void k_halo_wait(const uint32_t* flags_self, int ws, int rank, const StepDev* sp, uint32_t* counters,
-                            uint32_t* dead) {
+// `cnt_off`: per-rank record offsets of the direction waited for (inbound persons, or outbound persons for the
+// return bytes); a rank that exchanges nothing with this one is not waited for (it may not run the exchange at all).
+__global__ void k_halo_wait(const uint32_t* flags_self, const __grid_constant__ P2PDev P, int ret, const StepDev* sp,
+                            uint32_t* counters, uint32_t* dead) {
   const int q = threadIdx.x;
+  const int ws = P.ws, rank = P.rank;
   if (q >= ws || q == rank) return;
+  const uint32_t* off = ret ? P.out_off : P.in_off;
+  if (off[q + 1] == off[q]) return;
   if (*(volatile uint32_t*)dead) { atomicAdd(&counters[CNT_OVERFLOW], 1u); return; }
   const uint32_t epoch = sp->epoch;
   unsigned long long t0, t1;
@@ -1232,14 +1239,16 @@ __global__ void __launch_bounds__(256) k_halo_ret_push(const __grid_constant__ P
 }
 
 // Returned bytes (variant+1 per outbound slot) -> list of residents to infect.
+// They are appended BEHIND the step's own new infections (`first` = their count, final by now), which stay readable
+// (jb_fetch_new_infections).
 __global__ void k_halo_return(const uint8_t* __restrict__ ret, const uint32_t* __restrict__ out_person, uint32_t n_out,
                               uint32_t* __restrict__ member, uint8_t* __restrict__ variant, uint32_t cap,
-                              uint32_t* __restrict__ counter) {
+                              const uint32_t* __restrict__ first, uint32_t* __restrict__ counter) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   uint32_t v = ret[i];
   if (!v) return;
-  uint32_t k = atomicAdd(counter, 1u);
+  uint32_t k = min(*first, cap) + atomicAdd(counter, 1u);
   if (k < cap) { member[k] = out_person[i]; variant[k] = (uint8_t)(v - 1); }
 }
 

@@ -167,6 +167,12 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
         acts |= 1u << JB_INFO_ACT(d->reg_info[m]);
       w->sg_static_acts.push_back(acts);
     }
+    {
+      uint8_t hh = 0;
+      for (uint32_t m = d->grp_offset[sg.first_group]; m < d->grp_offset[sg.first_group + sg.n_groups] && !hh; ++m)
+        if (d->reg_member[m] >= d->n_people) hh = 1;
+      w->sg_has_halo.push_back(hh);
+    }
     if (sg.has_dynamic) w->any_dynamic = true;
   }
   REQUIRE(expect == w->G, "supergroups do not cover all groups");
@@ -409,6 +415,9 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
   CK(cudaStreamCreateWithFlags(&w->side_health, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&w->ev_fork_health, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&w->ev_join_health, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&w->side_halo, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&w->ev_fork_halo, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&w->ev_halo_ready, cudaEventDisableTiming));
   // the CTA kernel may need > 48 KB of dynamic shared memory for very large schools
   CK(cudaFuncSetAttribute(k_groups<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_groups<1, JB_CTA_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -505,6 +514,9 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   if (w->side_health) cudaStreamDestroy(w->side_health);
   if (w->ev_fork_health) cudaEventDestroy(w->ev_fork_health);
   if (w->ev_join_health) cudaEventDestroy(w->ev_join_health);
+  if (w->side_halo) cudaStreamDestroy(w->side_halo);
+  if (w->ev_fork_halo) cudaEventDestroy(w->ev_fork_halo);
+  if (w->ev_halo_ready) cudaEventDestroy(w->ev_halo_ready);
   cudaStreamDestroy(w->stream);
   delete w;
 }
@@ -1236,6 +1248,7 @@ static int launch_groups(JbWorld* w, int mode) {
       static const int unit_streams = jb_env_flag("JB_UNIT_STREAMS", 1);
       cudaStream_t st = w->serial ? w->stream : w->side[k][unit_streams ? u : 0];
       if (!w->serial) CK(cudaStreamWaitEvent(st, w->ev_fork, 0));
+      if (!w->serial && w->halo_async && w->sg_has_halo[k]) CK(cudaStreamWaitEvent(st, w->ev_halo_ready, 0));  // its visitors have arrived
       if (u == 0) {
         static const int skip_b = jb_env_flag("JB_TILES_SKIP_B", 0);
         if (skip_b && mode == 0) a.mode = 2;
@@ -1444,20 +1457,28 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   cudaStream_t s = w->stream;
   const JbStepParams& p = w->cur;
   const bool halo_now = halo_step(w);
+  // The arrival of the visitors (spin on the peers' flags, unpack) runs on its own stream: only the supergroups that
+  // hold visitor registrations wait for it (launch_groups), the others start right behind the placement.
+  static const int halo_async_on = jb_env_flag("JB_HALO_ASYNC", 1);
+  w->halo_async = halo_async_on && !w->serial && halo_now && w->H && (w->p2p_on || d_recv) &&
+                  !(p.flags & JB_STEP_INJECT_UNIFORMS);
+  cudaStream_t hs = w->halo_async ? w->side_halo : s;
+  if (w->halo_async) { CK(cudaEventRecord(w->ev_fork_halo, s)); CK(cudaStreamWaitEvent(hs, w->ev_fork_halo, 0)); }
   if (w->p2p_on && halo_now) {
     d_recv = w->p2p.recv[w->p2p.rank];
     d_ret_send = w->p2p_ret_local;
-    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_people[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters, w->p2p_done + 2);
-    KCHECK("k_halo_wait", s);
+    k_halo_wait<<<1, 32, 0, hs>>>(w->p2p.flag_people[w->p2p.rank], w->p2p, 0, step_dev(w), w->counters, w->p2p_done + 2);
+    KCHECK("k_halo_wait", hs);
     w->launches++;
   }
   if (w->H && d_recv && halo_now) {
-    k_halo_unpack<<<(w->H + 255) / 256, 256, 0, s>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
+    k_halo_unpack<<<(w->H + 255) / 256, 256, 0, hs>>>((const unsigned char*)d_recv, w->H, w->N, w->NP, (int)w->V,
                                                      w->phot, w->susc, w->trans[0], (uint8_t*)d_ret_send, step_dev(w),
                                                      w->pmslot, w->mir_slots ? (step_places_per_person(w) ? w->mstep : w->mstate) : nullptr);
-    KCHECK("k_halo_unpack", s);
+    KCHECK("k_halo_unpack", hs);
     w->launches++;
   }
+  if (w->halo_async) CK(cudaEventRecord(w->ev_halo_ready, hs));
   if (w->timing >= 2) CK(cudaEventRecord(w->ev_int0, s));
   if (p.flags & JB_STEP_INJECT_UNIFORMS) {
     CK(cudaMemsetAsync(w->draw_cnt, 0, ((size_t)w->G + 1) * 4, s));
@@ -1490,6 +1511,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
   if (health_beside && health_early == 2) TRY(fork_health(1));
   TRY(launch_groups(w, 0));
   if (health_beside && health_early == 2) TRY(fork_health(2));
+  if (w->halo_async) CK(cudaStreamWaitEvent(s, w->ev_halo_ready, 0));  // join (also when no active supergroup holds visitors)
   if (w->timing >= 2) CK(cudaEventRecord(w->ev_int1, s));
   // create infections for residents infected here; flag halo persons for their home domain
   if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS) || (w->H && halo_now)) {
@@ -1518,7 +1540,7 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
   const bool halo_now = halo_step(w);
   if (w->p2p_on && halo_now) {
     d_ret_recv = w->p2p.ret[w->p2p.rank];
-    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_ret[w->p2p.rank], w->p2p.ws, w->p2p.rank, step_dev(w), w->counters, w->p2p_done + 2);
+    k_halo_wait<<<1, 32, 0, s>>>(w->p2p.flag_ret[w->p2p.rank], w->p2p, 1, step_dev(w), w->counters, w->p2p_done + 2);
     KCHECK("k_halo_wait(ret)", s);
     w->launches++;
   }
@@ -1528,12 +1550,13 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
     CK(cudaMemsetAsync(w->counters + CNT_HALO_INF, 0, 4, s));
     k_halo_return<<<(w->n_out + 255) / 256, 256, 0, s>>>((const uint8_t*)d_ret_recv, w->out_person, w->n_out,
                                                          w->newinf_member, w->newinf_var, w->newinf_cap,
-                                                         w->counters + CNT_HALO_INF);
+                                                         w->counters + CNT_NEWINF, w->counters + CNT_HALO_INF);
     KCHECK("k_halo_return", s);
     w->launches++;
     if (!(p.flags & JB_STEP_NO_NEW_INFECTIONS)) {
       NewInfArgs a = make_newinf_args(w);
       a.member = w->newinf_member; a.variant = w->newinf_var; a.count_dev = w->counters + CNT_HALO_INF;
+      a.first_dev = w->counters + CNT_NEWINF;  // behind the step's own new infections
       a.cap = w->newinf_cap; a.sp = step_dev(w);
       a.fuse_health = 1; a.h = make_health_args(w, 0);
       k_newinf<<<148 * 2, 128, 0, s>>>(a, w->dis_host);
