@@ -391,6 +391,22 @@ int jb_inject_vaccination_uniforms(JbWorld* w, const double* u);
  * effective_multiplier: [n_variants][n_people] (immunity.effective_multiplier_dict). */
 int jb_fetch_vaccination(JbWorld* w, int8_t* dose, int8_t* vaccine, double* effective_multiplier);
 
+/* The whole per-person vaccination state, for checkpoints (the reference pickles person.vaccinated, vaccine_type and
+ * vaccine_trajectory with the person, hdf5_savers/population_saver.py:261-278): read it (store = 0) or write it back
+ * (store = 1, after jb_set_vaccination).  All arrays in the caller's person order; the three double arrays are
+ * [n_variants][n_people].  Before jb_set_vaccination a read returns the "nobody vaccinated" state. */
+typedef struct JbVaccinationState {
+  int8_t* dose;             /* person.vaccinated (-1 = None)                                   */
+  int8_t* vaccine;          /* index of person.vaccine_type (-1 = None)                        */
+  int8_t* campaign;         /* campaign of the running vaccine_trajectory (-1 = None)          */
+  int32_t* first_day;       /* day the trajectory started                                      */
+  uint8_t* stage;           /* dose of the trajectory reached so far                           */
+  double* prior_infection;  /* Dose.prior_efficacy of the running dose (vaccines.py:109-150)   */
+  double* prior_symptoms;
+  double* effective_multiplier;
+} JbVaccinationState;
+int jb_vaccination_state(JbWorld* w, int store, const JbVaccinationState* s);
+
 /* ---- individual policies (policy/individual_policies.py:36-84) ---------------------------
  * The active individual policies, in the reference's list order, evaluated per person by the
  * placement stage.  A stay-home policy that fires reduces the person's activities to

@@ -91,6 +91,12 @@ class JbVaccine(C.Structure):
                 ("waning_factor", C.c_double), ("sterilisation", C.c_void_p), ("symptomatic", C.c_void_p)]
 
 
+class JbVaccinationState(C.Structure):
+    _fields_ = [("dose", C.c_void_p), ("vaccine", C.c_void_p), ("campaign", C.c_void_p), ("first_day", C.c_void_p),
+                ("stage", C.c_void_p), ("prior_infection", C.c_void_p), ("prior_symptoms", C.c_void_p),
+                ("effective_multiplier", C.c_void_p)]
+
+
 class JbVaccinationCampaign(C.Structure):
     _fields_ = [("vaccine", C.c_int32), ("group_by", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32),
                 ("n_doses", C.c_int32), ("dose_numbers", C.c_int32 * MAX_DOSES),
@@ -139,7 +145,7 @@ ABI_SYMBOLS = [
     "set_commute", "inject_commute",
     "set_vaccination", "vaccinate", "inject_vaccination_uniforms", "fetch_vaccination",
     "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities", "set_variants", "mutate", "set_person_work_regions",
-    "step_prepare", "world_describe",
+    "step_prepare", "world_describe", "vaccination_state",
 ]
 
 
@@ -204,6 +210,7 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("vaccinate").argtypes = [vp, C.c_int32, C.c_uint64]
     f("inject_vaccination_uniforms").argtypes = [vp, vp]
     f("fetch_vaccination").argtypes = [vp, vp, vp, vp]
+    f("vaccination_state").argtypes = [vp, C.c_int, C.POINTER(JbVaccinationState)]
     f("flush_l2").argtypes = [vp, C.c_size_t]
     f("set_medical").argtypes = [vp, vp]
     f("set_halo_activities").argtypes = [vp, C.c_uint32]

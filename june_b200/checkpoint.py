@@ -9,9 +9,12 @@ length trajectories as ``trajectory_times / trajectory_symptoms / trajectory_len
 immunities (``immunity_saver.py``: susceptibilities).  h5py is not available in this environment, so the
 container is a NumPy ``.npz`` with the reference's dataset names as keys ("group/dataset").
 
-Two additions make a resumed run continue bit for bit instead of "from the next day" as the reference
-does: the clock (``time/shift``, ``time/now``, ``time/step_ordinal``) and ``people_data/medical``
-(``person.subgroups.medical_facility``, which the reference drops and re-creates by re-admission)."""
+Additions that make a resumed run continue bit for bit instead of "from the next day" as the reference does:
+the clock (``time/shift``, ``time/now``, ``time/step_ordinal`` and ``time/step_executed``: ``Simulator.run`` writes
+its checkpoints after the day's last ``do_timestep`` and BEFORE the clock advances, so a restore has to advance it),
+``people_data/medical`` (``person.subgroups.medical_facility``, which the reference drops and re-creates by
+re-admission) and the per-person vaccination state (``vaccination/*``: dose, vaccine, running trajectory, prior
+efficacies, effective multipliers -- the reference pickles them with the person)."""
 from __future__ import annotations
 
 import datetime
@@ -38,6 +41,8 @@ def checkpoint_arrays(sim) -> Dict[str, np.ndarray]:
         "time/date": np.array(sim.timer.date.strftime("%Y-%m-%d %H:%M:%S")),
         "time/shift": np.array(sim.timer.shift), "time/now": np.array(sim.timer.now),
         "time/step_ordinal": np.array(sim.step_ordinal),
+        # the step of the saved clock has already been executed (checkpoint written between do_timestep and next(timer))
+        "time/step_executed": np.array(int(getattr(sim, "_last_step_date", None) == sim.timer.date)),
         "people_data/people_id": np.asarray(pid, np.int64),
         "people_data/infected_id": np.asarray([pid[r["person"]] for r in rows], np.int64),
         "people_data/dead_id": np.asarray(pid[(st["pstate"] & PS_DEAD) != 0], np.int64),
@@ -56,6 +61,12 @@ def checkpoint_arrays(sim) -> Dict[str, np.ndarray]:
     }
     for k, name in enumerate(TRANSMISSION_COLUMNS[ttype]):
         out[f"infections/transmissions/{name}"] = np.asarray([r["tpar"][k] for r in rows], np.float64).reshape(n)
+    ep = getattr(sim, "epidemiology", None)
+    if ep is not None and getattr(ep, "vaccination_campaigns", None) is not None and getattr(sim, "_vaccination_on_device", False):
+        for k, v in dev.fetch_vaccination_state().items():
+            out[f"vaccination/{k}"] = v
+        out["vaccination/campaign_day0"] = np.array(sim._vaccination_first_day.isoformat())
+        out["vaccination/current_date"] = np.array("" if ep.current_date is None else ep.current_date.strftime("%Y-%m-%d %H:%M:%S"))
     return out
 
 
@@ -109,6 +120,30 @@ def restore_checkpoint(sim, path: str, reset_infections: bool = False, exact: bo
                              traj_tag=z["infections/symptoms/trajectory_symptoms"][lo:hi].tolist()))
         if rows:
             dev.upload_infections(rows)
+    if "vaccination/dose" in z.files and not reset_infections:
+        ep = sim.epidemiology
+        if ep is None or ep.vaccination_campaigns is None:
+            raise ValueError("the checkpoint holds a vaccination state, the simulator has no vaccination campaigns")
+        first = datetime.date.fromisoformat(str(z["vaccination/campaign_day0"]))
+        sim._vaccination_first_day = first
+        dev.set_vaccination(*ep.vaccination_campaigns.device_tables(first, sim.variant_names))
+        sim._vaccination_on_device = True
+        state = {}
+        for k in dev.fetch_vaccination_state():
+            a = z[f"vaccination/{k}"]
+            cur = dev.fetch_vaccination_state()[k] if not keep.all() else None
+            if a.ndim == 2:
+                full = cur if cur is not None else np.zeros((a.shape[0], w.n_people), a.dtype)
+                full[:, ours[keep]] = a[:, keep]
+            else:
+                full = cur if cur is not None else np.zeros(w.n_people, a.dtype)
+                full[ours[keep]] = a[keep]
+            state[k] = full
+        dev.set_vaccination_state(state)
+        cd = str(z["vaccination/current_date"])
+        ep.current_date = datetime.datetime.strptime(cd, "%Y-%m-%d %H:%M:%S") if cd else None
+        if getattr(sim, "record", None) is not None:
+            sim._vaccination_dose_prev = state["dose"].copy()
     date = datetime.datetime.strptime(str(z["time/date"]), "%Y-%m-%d %H:%M:%S")
     if exact:
         sim.timer.date = date
@@ -116,6 +151,8 @@ def restore_checkpoint(sim, path: str, reset_infections: bool = False, exact: bo
         sim.timer.shift = int(z["time/shift"])
         sim.timer.delta_time = datetime.timedelta(hours=sim.timer.shift_duration)
         sim.step_ordinal = int(z["time/step_ordinal"])
+        if "time/step_executed" in z.files and int(z["time/step_executed"]):
+            next(sim.timer)  # the saved step has run: continue with the one after it
     else:
         sim.timer.reset_to_new_date(datetime.datetime(date.year, date.month, date.day) + datetime.timedelta(days=1))
         sim.step_ordinal = int(z["time/step_ordinal"])

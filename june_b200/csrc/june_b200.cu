@@ -847,6 +847,48 @@ extern "C" int jb_fetch_vaccination(JbWorld* w, int8_t* dose, int8_t* vaccine, d
   return JB_OK;
 }
 
+template <typename T>
+static int store_permuted(JbWorld* w, T* dev, const T* in, T pad) {
+  std::vector<T> tmp(w->N, pad);
+  for (uint32_t p = 0; p < w->N_ext; ++p) tmp[w->h_ext2int[p]] = in[p];
+  CK(cudaMemcpy(dev, tmp.data(), (size_t)w->N * sizeof(T), cudaMemcpyHostToDevice));
+  return JB_OK;
+}
+
+extern "C" int jb_vaccination_state(JbWorld* w, int store, const JbVaccinationState* st) {
+  if (!w || !st) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(st->dose && st->vaccine && st->campaign && st->first_day && st->stage && st->prior_infection && st->prior_symptoms &&
+          st->effective_multiplier, "jb_vaccination_state: null array");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  if (!w->vac_dose) {
+    REQUIRE(!store, "jb_vaccination_state: jb_set_vaccination first");
+    for (uint32_t p = 0; p < w->N_ext; ++p) { st->dose[p] = -1; st->vaccine[p] = -1; st->campaign[p] = -1; st->first_day[p] = 0; st->stage[p] = 0; }
+    for (size_t i = 0; i < (size_t)w->N_ext * w->V; ++i) { st->prior_infection[i] = 0.0; st->prior_symptoms[i] = 0.0; st->effective_multiplier[i] = 1.0; }
+    return JB_OK;
+  }
+  if (!store) {
+    TRY(fetch_permuted(w, w->vac_dose, st->dose)); TRY(fetch_permuted(w, w->vac_type, st->vaccine));
+    TRY(fetch_permuted(w, w->traj_camp, st->campaign)); TRY(fetch_permuted(w, w->traj_day0, st->first_day));
+    TRY(fetch_permuted(w, w->traj_stage, st->stage));
+    for (uint32_t v = 0; v < w->V; ++v) {
+      TRY(fetch_permuted(w, w->prior_eff_inf + (size_t)v * w->N, st->prior_infection + (size_t)v * w->N_ext));
+      TRY(fetch_permuted(w, w->prior_eff_sym + (size_t)v * w->N, st->prior_symptoms + (size_t)v * w->N_ext));
+      TRY(fetch_permuted(w, w->effmult + (size_t)v * w->N, st->effective_multiplier + (size_t)v * w->N_ext));
+    }
+    return JB_OK;
+  }
+  TRY(store_permuted<int8_t>(w, w->vac_dose, st->dose, -1)); TRY(store_permuted<int8_t>(w, w->vac_type, st->vaccine, -1));
+  TRY(store_permuted<int8_t>(w, w->traj_camp, st->campaign, -1)); TRY(store_permuted<int32_t>(w, w->traj_day0, st->first_day, 0));
+  TRY(store_permuted<uint8_t>(w, w->traj_stage, st->stage, 0));
+  for (uint32_t v = 0; v < w->V; ++v) {
+    TRY(store_permuted<double>(w, w->prior_eff_inf + (size_t)v * w->N, st->prior_infection + (size_t)v * w->N_ext, 0.0));
+    TRY(store_permuted<double>(w, w->prior_eff_sym + (size_t)v * w->N, st->prior_symptoms + (size_t)v * w->N_ext, 0.0));
+    TRY(store_permuted<double>(w, w->effmult + (size_t)v * w->N, st->effective_multiplier + (size_t)v * w->N_ext, 1.0));
+  }
+  return JB_OK;
+}
+
 // ---- commute ---------------------------------------------------------------------------------
 extern "C" int jb_set_commute(JbWorld* w, const JbCommuteDesc* d) {
   if (!w || !d) { jb_set_error("null argument"); return JB_EINVAL; }

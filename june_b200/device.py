@@ -194,6 +194,26 @@ class Engine:
         self._check(self._f("fetch_vaccination")(self._h, ptr(out["dose"]), ptr(out["vaccine"]), ptr(out["effective_multiplier"])))
         return out
 
+    _VACC_STATE = (("dose", np.int8, False), ("vaccine", np.int8, False), ("campaign", np.int8, False),
+                   ("first_day", np.int32, False), ("stage", np.uint8, False), ("prior_infection", np.float64, True),
+                   ("prior_symptoms", np.float64, True), ("effective_multiplier", np.float64, True))
+
+    def fetch_vaccination_state(self) -> Dict[str, np.ndarray]:
+        """Everything the device keeps per person about vaccination (checkpoints)."""
+        n = self.world.n_people
+        out = {k: np.zeros((self.n_variants, n) if per_variant else n, dt) for k, dt, per_variant in self._VACC_STATE}
+        st = _lib.JbVaccinationState(*(out[k].ctypes.data for k, _, _ in self._VACC_STATE))
+        self._check(self._f("vaccination_state")(self._h, 0, C.byref(st)))
+        return out
+
+    def set_vaccination_state(self, state: Dict[str, np.ndarray]) -> None:
+        """Write a saved vaccination state back (after ``set_vaccination``)."""
+        n = self.world.n_people
+        arrs = {k: np.ascontiguousarray(state[k], dt).reshape((self.n_variants, n) if per_variant else n)
+                for k, dt, per_variant in self._VACC_STATE}
+        st = _lib.JbVaccinationState(*(arrs[k].ctypes.data for k, _, _ in self._VACC_STATE))
+        self._check(self._f("vaccination_state")(self._h, 1, C.byref(st)))
+
     # ---- commute --------------------------------------------------------------------------------
     def _set_commute(self, world: WorldSoA):
         arrs = [np.ascontiguousarray(world.person_commute, dtype=np.int32)] + [

@@ -306,9 +306,23 @@ def _camel(key: str) -> str:
 class Policies:
     """Collection with the reference's category views (``policy/policy.py:56-99``)."""
 
-    def __init__(self, policies: Optional[Sequence[Policy]] = None):
+    def __init__(self, policies: Optional[Sequence[Policy]] = None, apply_tiered_lockdown: bool = False,
+                 not_evaluated: Optional[Sequence[tuple]] = None):
         self.policies: List[Policy] = list(policies or [])
         self._edges: Optional[List[datetime.datetime]] = None
+        # False = what the running reference does (see ``regional_scalars``)
+        self.apply_tiered_lockdown = apply_tiered_lockdown
+        # (key, start, end) of the policies of a configuration file this package does not evaluate
+        self.not_evaluated: List[tuple] = list(not_evaluated or [])
+
+    def check_window(self, start: datetime.datetime, end: datetime.datetime) -> None:
+        """Refuse a run during which a policy this package does not evaluate would be active: its effect would
+        silently be missing from the results (the plugin raises for the same reason)."""
+        hit = sorted({k for k, s, e in self.not_evaluated if s < end and e > start})
+        if hit:
+            raise NotImplementedError(
+                "policies active between %s and %s that june_b200 does not evaluate: %s (remove them from the "
+                "policy file, or pass strict=False to Policies.from_file to ignore them knowingly)" % (start, end, ", ".join(hit)))
 
     def active_key(self, date: datetime.datetime) -> int:
         """Index of the interval between two consecutive policy start / end times that holds
@@ -340,6 +354,13 @@ class Policies:
         probability reductions, then apply the active policies (at most one change of probabilities)."""
         leisure.closed_venues = {r: set() for r in leisure.region_names}
         leisure.policy_reductions = {}
+        if self.apply_tiered_lockdown:
+            # TieredLockdown.apply, ``regional_compliance.py:42-52`` (tier 2's ``update("residence_visits")`` adds the
+            # string's letters to the set, i.e. closes nothing)
+            _, tiers = self.regional_scalars(date, leisure.region_names)
+            closures = {3: {"cinema", "residence_visits"}, 4: {"pub", "cinema", "gym", "residence_visits"}}
+            for r, t in zip(leisure.region_names, tiers):
+                leisure.closed_venues[r] |= closures.get(t, set())
         n_change = 0
         for p in self.leisure_policies:
             if not p.is_active(date):
@@ -357,29 +378,34 @@ class Policies:
         return self._of("medical_care")
 
     @classmethod
-    def from_file(cls, config_file: Optional[str] = None, disease: str = "covid19", disease_config=None) -> "Policies":
+    def from_file(cls, config_file: Optional[str] = None, disease: str = "covid19", disease_config=None,
+                  strict: bool = True) -> "Policies":
         """YAML key -> CamelCase class; numbered sub-entries expand to several instances
-        (``policy/policy.py:137-229``).  Keys of policies this package does not evaluate are
-        skipped (they are out of the hot-path scope)."""
+        (``policy/policy.py:137-229``).  Policies this package does not evaluate (test-and-trace, school
+        class quarantines, ...: outside the hot-path scope) are remembered with their dates: ``Simulator`` refuses a
+        run window in which one of them would be active (``check_window``) unless ``strict`` is False."""
         if config_file is None:
             cfg = load_defaults()["policy"][disease]
         else:
             with open(config_file) as f:
                 cfg = yaml.safe_load(f)
         out: List[Policy] = []
+        skipped: List[tuple] = []
         for key, data in (cfg or {}).items():
             klass = _CLASSES.get(_camel(key))
-            if klass is None:
-                continue
             entries = [data]
             if isinstance(data, dict) and data and all(str(k).isdigit() for k in data):
                 entries = [data[k] for k in sorted(data, key=lambda x: int(x))]
             for e in entries:
                 kw = dict(e or {})
+                if klass is None:
+                    if strict:
+                        skipped.append((key, read_date(kw.get("start_time", "1900-01-01")), read_date(kw.get("end_time", "2100-01-01"))))
+                    continue
                 if klass is Hospitalisation:
                     kw["disease_config"] = disease_config
                 out.append(klass(**kw))
-        return cls(out)
+        return cls(out, not_evaluated=skipped)
 
     # ---- what do_timestep needs every step -------------------------------------------------------
     def beta_reductions(self, date: datetime.datetime) -> Dict[str, float]:
@@ -406,7 +432,12 @@ class Policies:
             if p.is_active(date):
                 for r in region_names:
                     comp[r] = p.compliances_per_region[r]
-        tl = self._of("tiered_lockdown")
+        # The running reference never applies its TieredLockdowns collection: ``Simulator.do_timestep`` calls
+        # ``interaction_policies.apply`` and ``regional_compliance.apply`` only (``simulator.py:359-366``), so
+        # ``Region.policy["lockdown_tier"]`` stays None for a whole run.  That is the default here too (the drop-in
+        # must equal the reference); ``apply_tiered_lockdown = True`` switches the intended behaviour on (tier-4
+        # beta reduction, ``CloseCompaniesLockdownTiers``, the tier 3 / 4 venue closures).
+        tl = self._of("tiered_lockdown") if self.apply_tiered_lockdown else []
         if tl:
             for r in region_names:
                 tiers[r] = None

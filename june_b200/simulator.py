@@ -417,6 +417,7 @@ class Simulator:
             h.exchange_infections()
             stats = dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
         self.step_ordinal += 1
+        self._last_step_date = self.timer.date
         ep = self.epidemiology
         if ep is not None and ep.vaccination_campaigns is not None and (
                 ep.current_date is None or self.timer.date.date() != ep.current_date.date()):
@@ -453,6 +454,9 @@ class Simulator:
     def run(self) -> None:
         """``Simulator.run`` (``simulator.py:628-707``), including the checkpoints written after the last
         step of every day listed in ``checkpoint_save_dates`` (``:681-690``)."""
+        pol = self.activity_manager.policies
+        if pol is not None and hasattr(pol, "check_window"):
+            pol.check_window(self.timer.date, self.timer.final_date)  # a policy this package does not evaluate would be active
         while self.timer.date < self.timer.final_date:
             if self.epidemiology is not None:
                 self.epidemiology.infection_seeds_timestep(self, self.timer)

@@ -87,6 +87,54 @@ def test_reference_style_restore_restarts_the_next_day_and_can_drop_infections(t
     assert (st["susceptibility"][0] == 0).sum() >= n_inf, "immunities survive a reset of the infections"
 
 
+def run_written_case(kind, tmp_path, vaccination):
+    """The checkpoint ``Simulator.run`` writes itself (after the day's last step, before the clock advances),
+    restored with the defaults: the continuation must equal the uninterrupted run step for step."""
+    from test_vaccination import campaigns
+    w = generate_world(8_000, seed=8, sector_betas=load_defaults()["company_sector_betas"], leisure=True)
+
+    def build():
+        s = make_sim(kind, w, Policies.from_file(), total_days=12, seed=5)
+        s.epidemiology.infection_seeds[0].cases_per_capita = 0.05
+        if vaccination:
+            s.epidemiology.vaccination_campaigns = campaigns()
+        return s
+    a = build()
+    a.checkpoint_save_dates = (datetime.date(2020, 3, 6),)
+    a.checkpoint_save_path = str(tmp_path)
+    a.run()
+    path = os.path.join(str(tmp_path), "checkpoint_2020-03-06.0.npz")
+    z = np.load(path)
+    assert int(z["time/step_executed"]) == 1
+    b = build()
+    b.restore_checkpoint(path)
+    assert b.timer.date == datetime.datetime(2020, 3, 7) and b.timer.shift == 0, "continues with the step AFTER the saved one"
+    n_done = int(z["time/step_ordinal"])
+    assert b.step_ordinal == n_done
+    b.run()
+    key = lambda h: (h["date"], h["n_new_infections"], h["n_infected"], h["n_hospitalised"], h["n_dead_total"], tuple(h["n_by_activity"]))
+    assert [key(h) for h in a.history[n_done:]] == [key(h) for h in b.history]
+    fa, fb = a.device.fetch_person_state(), b.device.fetch_person_state()
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]), k
+    if vaccination:
+        va, vb = a.device.fetch_vaccination_state(), b.device.fetch_vaccination_state()
+        for k in va:
+            assert np.array_equal(va[k], vb[k]), k
+        assert (va["dose"] >= 0).sum() > 500 and (np.load(path)["vaccination/dose"] >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("vaccination", [False, True])
+def test_oracle_resumes_the_checkpoint_run_writes(tmp_path, vaccination):
+    run_written_case("oracle", tmp_path, vaccination)
+
+
+@pytest.mark.gpu
+def test_cuda_resumes_the_checkpoint_run_writes_with_vaccination(tmp_path):
+    assert have_gpu()
+    run_written_case("cuda", tmp_path, True)
+
+
 @pytest.mark.gpu
 def test_cuda_resumes_bit_for_bit(tmp_path):
     assert have_gpu()

@@ -116,3 +116,22 @@ def test_summary_csv_rows(tmp_path):
     assert sum(per_day.values()) == tot > 0
     sim.write_summary_csv(str(tmp_path / "summary.csv"))
     assert (tmp_path / "summary.csv").read_text().startswith("time_stamp,region,current_infected,daily_infected")
+
+
+def test_policy_file_with_a_policy_that_is_not_evaluated_is_refused_for_its_window(tmp_path):
+    """A policy key this package does not evaluate must not silently vanish from a run in which it would be active."""
+    import datetime
+    import yaml
+    from june_b200.policy import Policies
+    path = tmp_path / "policy.yaml"
+    path.write_text(yaml.safe_dump({
+        "social_distancing": {"start_time": "2020-03-16", "end_time": "2020-03-24", "beta_factors": {"pub": 0.5}},
+        "school_quarantine": {"start_time": "2020-04-01", "end_time": "2020-05-01", "compliance": 0.5, "n_days": 7},
+    }))
+    pol = Policies.from_file(str(path))
+    assert [p.policy_type for p in pol.policies] == ["interaction"] and [k for k, _, _ in pol.not_evaluated] == ["school_quarantine"]
+    pol.check_window(datetime.datetime(2020, 3, 1), datetime.datetime(2020, 4, 1))  # ends when the policy starts: fine
+    with pytest.raises(NotImplementedError, match="school_quarantine"):
+        pol.check_window(datetime.datetime(2020, 3, 1), datetime.datetime(2020, 4, 2))
+    assert Policies.from_file(str(path), strict=False).not_evaluated == []
+    Policies.from_file().check_window(datetime.datetime(2020, 3, 1), datetime.datetime(2021, 3, 1))  # the shipped defaults

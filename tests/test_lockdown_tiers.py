@@ -81,6 +81,9 @@ def test_policy_class_builds_the_region_mask_from_the_tiers():
     rec = p.device_record(dict(lockdown_tiers=[None, 3, 2, 4, 1]))
     assert rec["type"] == _lib.POL_CLOSE_COMPANIES_TIERS and rec["mask"] == (1 << 1) | (1 << 3)
     pols = Policies([p, TieredLockdown("2020-01-01", "2021-01-01", tiers_per_region={"a": 4, "b": 1})])
+    # default: what the running reference does -- its do_timestep never applies the tiers (simulator.py:359-366)
+    assert pols.regional_scalars(datetime.datetime(2020, 6, 1), ["a", "b"], {})[1] == [None, None]
+    pols.apply_tiered_lockdown = True
     comp, tiers = pols.regional_scalars(datetime.datetime(2020, 6, 1), ["a", "b"], {})
     assert tiers == [4, 1]
     recs = pols.device_policies(datetime.datetime(2020, 6, 1), dict(stay_at_home_mask=0, lockdown_tiers=tiers))
