@@ -507,8 +507,17 @@ int jb_fetch_infection_events(JbWorld* w, uint32_t* infected, uint32_t* infector
 #define JB_HEV_DISCHARGE 5
 #define JB_HEV_SYMPTOMS 6 /* `symptoms` table (epidemiology.py:256-266): the tag changed; group = new tag */
 int jb_fetch_health_events(JbWorld* w, uint32_t* person, uint32_t* kind, int32_t* group, size_t cap, size_t* n);
-/* per-region summary: counts[n_regions][JB_N_SUMMARY] (records_writer.py:151-164) */
-#define JB_N_SUMMARY 8
+/* per-region summary of the last step: counts[n_regions][JB_N_SUMMARY], the quantities of a summary.csv row
+ * (records_writer.py:151-164,248-376,764-773) with the reference's attribution:
+ *   0 infections created in this domain, by the person's region (the reference's daily_infected goes by the region of
+ *     the group an infection happened in: the host derives it from the infection events, Simulator.summary_rows);
+ *   1 currently infected, by the person's region;
+ *   2 / 3 patients placed in a ward / in intensive care by this step's placement, by the HOSPITAL's region
+ *     (len(hospital.ward), len(hospital.icu): people admitted during the step's health update count from the next step);
+ *   4 deaths, by the person's region;   5 deaths in hospital, by the hospital's region;   6 recoveries (person's region);
+ *   7 ward admissions ("ward_admitted") and 8 transfers to intensive care ("icu_transferred"), by the hospital's region
+ *     -- the two events the reference records (medical_care_policies.py:463-475). */
+#define JB_N_SUMMARY 9
 int jb_fetch_summary(JbWorld* w, uint32_t* counts);
 
 /* Kernel timing hooks for bench.py: CUDA-event time (ms) of the interaction kernels and of

@@ -33,7 +33,7 @@ enum {
 };
 
 // per-region summary columns (records_writer.py:151-164)
-enum { SUM_NEW_INFECTED = 0, SUM_CUR_INFECTED, SUM_CUR_HOSP, SUM_CUR_ICU, SUM_DEATHS, SUM_HOSP_DEATHS, SUM_RECOVERED, SUM_ADMISSIONS };
+enum { SUM_NEW_INFECTED = 0, SUM_CUR_INFECTED, SUM_CUR_HOSP, SUM_CUR_ICU, SUM_DEATHS, SUM_HOSP_DEATHS, SUM_RECOVERED, SUM_ADMISSIONS, SUM_ICU_ADMISSIONS };
 
 #define JB_TAG_BIT(tag) (1 << ((tag) + 2))
 

@@ -70,6 +70,8 @@ struct PlaceArgs {
   // table-driven placement: `pmir` = byte last pushed per person, changed bytes go to `mstate[pmslot[p]]`;
   // per-person placement: every mirrored person's byte of THIS step goes to `mstep[pmslot[p]]`
   uint8_t* mstate; uint8_t* mstep; uint8_t* pmir; const uint32_t* pmslot;
+  const uint32_t* grp_info;  // region of a hospital
+  uint32_t* summary;         // [R][JB_N_SUMMARY]: ward / intensive-care patients placed, by the hospital's region
 };
 
 // Uniform number j of policy k for person p in this step (or the injected one, test mode).
@@ -190,6 +192,16 @@ __device__ __forceinline__ void jb_dyn_scatter(const PlaceArgs& a, uint32_t g, u
     }
   }
   atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+}
+
+// A patient goes into its ward's bin; len(hospital.ward) / len(hospital.icu) of the step's summary row count the
+// people PLACED there (records_writer.py:290-294), by the hospital's region.
+__device__ __forceinline__ void jb_place_patient(const PlaceArgs& a, uint32_t p) {
+  const uint32_t med = (uint32_t)a.pmed[p];  // (hospital group << 8) | local subgroup
+  const uint32_t hg = med >> 8, lsg = med & 0xFu;
+  jb_dyn_scatter(a, hg, lsg, p);
+  if (a.summary && lsg >= 1u && lsg <= 2u)
+    atomicAdd(&a.summary[JB_GINFO_REGION(a.grp_info[hg]) * JB_N_SUMMARY + (lsg == 2u ? SUM_CUR_ICU : SUM_CUR_HOSP)], 1u);
 }
 
 // Travel.get_commute_subgroup (travel.py:125-131) -> City.get_commute_subgroup (city.py:83-102) ->
@@ -317,10 +329,7 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
     }
     if (act == 15u) { ++noact; act = JB_ACT_NONE; }
     cnt += 1ull << (8 * act);
-    if (act == JB_ACT_MEDICAL) {  // rare: scatter the patient into its ward's bin
-      const uint32_t med = (uint32_t)a.pmed[p];  // (hospital group << 8) | local subgroup
-      jb_dyn_scatter(a, med >> 8, med & 0xFu, p);
-    }
+    if (act == JB_ACT_MEDICAL) jb_place_patient(a, p);  // rare: the patient goes into its ward's bin
     const uint32_t var = a.pvar ? (uint32_t)a.pvar[p] : 0u;
     if (FULL && a.mstep) {  // this step's byte of every mirrored person (policies / leisure / commute decide per person)
       const uint32_t slot = a.pmslot[p];
@@ -404,9 +413,7 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
           while (medm) {
             const uint32_t b = (uint32_t)(__ffs(medm) - 1) >> 3;
             medm &= medm - 1;
-            const uint32_t p = p0 + q * 4 + b;
-            const uint32_t med = (uint32_t)a.pmed[p];
-            jb_dyn_scatter(a, med >> 8, med & 0xFu, p);
+            jb_place_patient(a, p0 + q * 4 + b);
           }
           sw[q] = act4 | (st4 & 0x08080808u) | ((st4 & 0x03030303u) << 4);
         }
@@ -555,6 +562,7 @@ struct HealthArgs {
   uint8_t* pstate; int8_t* ptag; double* trans; uint32_t NP; int32_t* pmed; int32_t* pslot; uint8_t* phas;  // trans: [2][NP], written half = tpar ^ 1
   uint32_t* counters;
   uint32_t* summary;        // [R][JB_N_SUMMARY]
+  const uint32_t* grp_info; // region of a hospital
   int R;
   int old_only;             // 1: only the slots that existed at step start (k_newinf updates its own)
   // health events (null unless JB_STEP_RECORD_EVENTS)
@@ -627,6 +635,8 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
   }
   const int bit = JB_TAG_BIT(tag);
   uint32_t* sum = sum_base + (size_t)a.inf_region[s] * JB_N_SUMMARY;
+  // what happens in a hospital is counted for the HOSPITAL's region (records_writer.py:272-294,369-373)
+  auto hsum = [&](int32_t hg) -> uint32_t* { return sum_base + (size_t)JB_GINFO_REGION(a.grp_info[hg]) * JB_N_SUMMARY; };
   // Hospitalisation.apply (medical_care_policies.py:413-526; hospital.py:62-122)
   const int32_t med_old = a.inf_med[s];
   const bool was_med = med_old >= 0;
@@ -635,11 +645,16 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
     if (bit & D.hosp_mask) {
       const int32_t hg = was_med ? (med_old >> 8) : a.inf_hosp[s];
       if (hg >= 0) med_new = (hg << 8) | ((bit & D.icu_mask) ? 2 : 1);
-      if (a.hev_person && hg >= 0) {
+      if (hg >= 0) {
         // "ward_admitted" -> hospital_admissions, "icu_transferred" -> icu_admissions; a direct ICU
         // admission is not recorded by the reference (medical_care_policies.py:463-475)
-        if (!was_med && (med_new & 0xFF) == 1) jb_health_event(a, (uint32_t)p, JB_HEV_HOSPITAL_ADMISSION, hg);
-        else if (was_med && (med_old & 0xFF) == 1 && (med_new & 0xFF) == 2) jb_health_event(a, (uint32_t)p, JB_HEV_ICU_ADMISSION, hg);
+        if (!was_med && (med_new & 0xFF) == 1) {
+          atomicAdd(&hsum(hg)[SUM_ADMISSIONS], 1u);
+          if (a.hev_person) jb_health_event(a, (uint32_t)p, JB_HEV_HOSPITAL_ADMISSION, hg);
+        } else if (was_med && (med_old & 0xFF) == 1 && (med_new & 0xFF) == 2) {
+          atomicAdd(&hsum(hg)[SUM_ICU_ADMISSIONS], 1u);
+          if (a.hev_person) jb_health_event(a, (uint32_t)p, JB_HEV_ICU_ADMISSION, hg);
+        }
       }
     } else if (was_med && !(bit & D.dead_mask)) {
       if (a.hev_person) jb_health_event(a, (uint32_t)p, JB_HEV_DISCHARGE, med_old >> 8);
@@ -682,15 +697,13 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
     atomicAdd(&a.counters[CNT_DEATHS_STEP], 1u);
     atomicAdd(&a.counters[CNT_DEAD_TOTAL], 1u);
     atomicAdd(&sum[SUM_DEATHS], 1u);
-    if (was_med) atomicAdd(&sum[SUM_HOSP_DEATHS], 1u);
+    if (med_new >= 0) atomicAdd(&hsum(med_new >> 8)[SUM_HOSP_DEATHS], 1u);  // died in its ward (epidemiology.py:176-179)
   } else {
     ++acc.inf;
     atomicAdd(&sum[SUM_CUR_INFECTED], 1u);
     if (med_new >= 0) {
       ++acc.hosp;
-      atomicAdd(&sum[SUM_CUR_HOSP], 1u);
-      if (bit & D.icu_mask) { ++acc.icu; atomicAdd(&sum[SUM_CUR_ICU], 1u); }
-      if (!was_med) atomicAdd(&sum[SUM_ADMISSIONS], 1u);
+      if (bit & D.icu_mask) ++acc.icu;
     }
   }
 }

@@ -1416,6 +1416,7 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     pa.pol = w->d_pol; pa.n_pol = w->n_pol; pa.ptag = w->ptag; pa.pattr = w->pattr; pa.pwork_region = w->pwork_region;
     pa.pol_inject = (p.flags & JB_STEP_INJECT_POLICY) ? w->pol_inject : nullptr;
     pa.severe_mask = w->dis_host.severe_mask;
+    pa.grp_info = w->grp_info; pa.summary = w->summary;
     const uint32_t chunks = (w->N + 15) / 16;
     const bool full = (w->n_pol != 0 && !w->pol_subject_mode) || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
                       pa.cmt.person != nullptr || pa.cmt.inject != nullptr;
@@ -1479,7 +1480,7 @@ static HealthArgs make_health_args(JbWorld* w, int old_only) {
   a.traj_tag = w->traj_tag; a.pstate = w->pstate; a.ptag = w->ptag; a.trans = w->trans[0]; a.NP = w->NP; a.pmed = w->pmed;
   a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
-  a.summary = w->summary; a.R = (int)w->R;
+  a.summary = w->summary; a.R = (int)w->R; a.grp_info = w->grp_info;
   if ((w->cur.flags & JB_STEP_RECORD_EVENTS) && w->hev_person) {
     a.hev_person = w->hev_person; a.hev_kind = w->hev_kind; a.hev_group = w->hev_group; a.hev_cap = w->hev_cap;
     a.pres_group = w->pres_group;

@@ -455,13 +455,16 @@ class Engine:
                             traj_time=list(a.traj_time)[:ns], traj_tag=list(a.traj_tag)[:ns]))
         return out
 
+    # include/june_b200.h, JB_N_SUMMARY ("daily_infected" here = infections created in this domain by the PERSON's
+    # region; Simulator.summary_rows replaces it by the reference's count by the region of the infecting group)
     SUMMARY_COLUMNS = ("daily_infected", "current_infected", "current_hospitalised", "current_intensive_care",
-                       "daily_deaths", "daily_hospital_deaths", "daily_recovered", "daily_hospitalised")
+                       "daily_deaths", "daily_hospital_deaths", "daily_recovered", "daily_hospitalised",
+                       "daily_intensive_care")
 
     def fetch_summary(self) -> np.ndarray:
         """Per-region counts of the last step, columns ``SUMMARY_COLUMNS`` (the quantities of the
         reference's ``summary.csv``, ``records_writer.py:151-164``)."""
-        out = np.zeros((self.world.n_regions, 8), np.uint32)
+        out = np.zeros((self.world.n_regions, len(self.SUMMARY_COLUMNS)), np.uint32)
         self._check(self._f("fetch_summary")(self._h, ptr(out)))
         return out
 

@@ -116,6 +116,12 @@ class InfectionSeed:
         chosen = np.sort(rng.choice(n, size=k, replace=False)).astype(np.uint32)
         sim.device.infect(chosen, time=time, seed=sim.seed ^ 0x5EED, step=0xFFFF0000)
         self.done = True
+        if sim.record is not None:
+            # the seeds are rows of the `infections` table too (infection_seed.py:196-205, by the person's region):
+            # they count in the daily_infected of the step that follows
+            w = sim.world
+            sim._seeded_by_region = getattr(sim, "_seeded_by_region", 0) + np.bincount(
+                np.asarray(w.sa_region)[np.asarray(w.super_area)[chosen]], minlength=w.n_regions)
         return k
 
 
@@ -443,8 +449,16 @@ class Simulator:
             self.last_stats = stats
             self.history.append(dict(date=self.timer.date, now=self.timer.now, **stats))
             if self.record is not None:
-                self.region_history.append((self.timer.date, dev.fetch_summary()))
+                summ = dev.fetch_summary().astype(np.int64)
                 ev = dev.fetch_infection_events()
+                # daily_infected of summary.csv: rows of the `infections` table by the region of the group the infection
+                # happened in (interaction.py:679, records_writer.py:329-330) + the step's seeds (person's region)
+                w = self.world
+                by_group = np.bincount((np.asarray(w.grp_info)[ev["group"]] >> 16).astype(np.int64), minlength=w.n_regions) \
+                    if len(ev["infected"]) else np.zeros(w.n_regions, np.int64)
+                summ[:, 0] = by_group[:w.n_regions] + getattr(self, "_seeded_by_region", 0)
+                self._seeded_by_region = 0
+                self.region_history.append((self.timer.date, summ))
                 if len(ev["infected"]):
                     self.infection_events.append((self.timer.date, ev))
                 hev = dev.fetch_health_events()
@@ -482,18 +496,24 @@ class Simulator:
         from .checkpoint import restore_checkpoint
         restore_checkpoint(self, path, reset_infections=reset_infections, exact=exact)
 
+    SUMMARY_HEADER = ("time_stamp", "region", "current_infected", "daily_infected", "current_hospitalised",
+                      "daily_hospitalised", "current_intensive_care", "daily_intensive_care", "daily_hospital_deaths",
+                      "daily_deaths")  # records_writer.py:151-164
+
     def summary_rows(self) -> List[Dict[str, object]]:
-        """Rows of the reference's ``summary.csv`` (``records_writer.py:151-164,693-790``): one per
-        (day, region); ``daily_*`` columns are summed over the day's steps, ``current_*`` are taken
-        at the day's last step.  Needs ``record`` to be set (any truthy object or a file path)."""
+        """Rows of the reference's ``summary.csv`` (``records_writer.py:151-164,693-790``): the reference writes one
+        row per TIME STEP and region (``Epidemiology.do_timestep`` calls ``summarise_time_step`` every step,
+        ``epidemiology.py:164-166``; the ``daily_`` columns hold the events of that step), with the day as time stamp,
+        and skips rows whose eight numbers are all zero.  Same here; ``daily_recovered`` is an extra key of the
+        dictionaries that ``write_summary_csv`` does not write.  Needs ``record`` to be set."""
         cols = self.device.SUMMARY_COLUMNS
-        rows: Dict[tuple, Dict[str, object]] = {}
+        out = []
         for date, summ in self.region_history:
             for r, name in enumerate(self.world.region_names):
-                row = rows.setdefault((date.date(), name), dict(time_stamp=date.date(), region=name, **{c: 0 for c in cols}))
-                for k, c in enumerate(cols):
-                    row[c] = int(summ[r, k]) if c.startswith("current") else row[c] + int(summ[r, k])
-        return [rows[k] for k in sorted(rows, key=lambda x: (x[0], self.world.region_names.index(x[1])))]
+                row = dict(time_stamp=date.date(), region=name, **{c: int(summ[r, k]) for k, c in enumerate(cols)})
+                if sum(row[c] for c in self.SUMMARY_HEADER[2:]) > 0:
+                    out.append(row)
+        return out
 
     def infection_rows(self) -> List[Dict[str, object]]:
         """Rows of the reference's ``infections`` record table (``Record.accumulate(table_name=
@@ -552,13 +572,12 @@ class Simulator:
     def write_summary_csv(self, path: str) -> None:
         import csv
         rows = self.summary_rows()
-        header = ["time_stamp", "region", "current_infected", "daily_infected", "current_hospitalised",
-                  "daily_hospitalised", "current_intensive_care", "daily_hospital_deaths", "daily_deaths", "daily_recovered"]
+        header = list(self.SUMMARY_HEADER)
         with open(path, "w", newline="") as f:
             wr = csv.DictWriter(f, fieldnames=header)
             wr.writeheader()
             for r in rows:
-                wr.writerow({k: r[k] for k in header})
+                wr.writerow({k: (r[k].strftime("%Y-%m-%d") if k == "time_stamp" else r[k]) for k in header})
 
     def daily_summary(self) -> List[Dict[str, object]]:
         """Daily curves in the spirit of ``summary.csv`` (``records_writer.py:151-164``), whole domain."""

@@ -176,10 +176,30 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
             for g in getattr(world, sg.name).members:
                 gid_of[(g.spec, g.id)] = gidx[id(g)]
 
+        import types
+        from june.records.records_writer import Record as RefRecord
+
+        def fresh_events():
+            return {"infections": types.SimpleNamespace(region_names=[]),
+                    "hospital_admissions": types.SimpleNamespace(hospital_ids=[]),
+                    "icu_admissions": types.SimpleNamespace(hospital_ids=[]),
+                    "deaths": types.SimpleNamespace(dead_person_ids=[], location_specs=[], location_ids=[])}
+
         class Recorder:
             record_static_data = False
+            mpi_rank = None
+            events = fresh_events()
 
             def accumulate(self, table_name, **kw):
+                # what the reference's event tables keep for summarise_time_step (event_records_writer.py)
+                if table_name == "infections":
+                    self.events["infections"].region_names.extend([kw["region_name"]] * len(kw["infected_ids"]))
+                elif table_name in ("hospital_admissions", "icu_admissions"):
+                    self.events[table_name].hospital_ids.append(kw["hospital_id"])
+                elif table_name == "deaths":
+                    self.events["deaths"].dead_person_ids.append(kw["dead_person_id"])
+                    self.events["deaths"].location_specs.append(kw["location_spec"])
+                    self.events["deaths"].location_ids.append(kw["location_id"])
                 if table_name == "infections":
                     if kw["location_spec"] == "infection_seed":
                         return
@@ -196,10 +216,15 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
                     rec_state["rows"].append((pidx[kw["infected_id"]], 6, int(kw["symptoms"])))
 
             def summarise_time_step(self, timestamp, world):
-                pass
+                # the reference's OWN summary functions (records_writer.py:248-376) on the events of this step:
+                # the eight columns of a summary.csv row (:764-773), per region
+                di, ci = RefRecord.summarise_infections(self, world=world)
+                dh, dicu, ch, cicu = RefRecord.summarise_hospitalisations(self, world=world)
+                dd, ddh = RefRecord.summarise_deaths(self, world=world)
+                rec_state["summary"] = [[d.get(r, 0) for d in (ci, di, ch, dh, cicu, dicu, ddh, dd)] for r in soa.region_names]
 
             def time_step(self, timestamp):
-                pass
+                type(self).events = fresh_events()
 
             def parameters(self, **kw):
                 pass
@@ -289,6 +314,7 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         if records:
             rec["health_events"] = np.array(sorted(rec_state["rows"]), np.int64).reshape(-1, 3)
             rec["infection_events"] = np.array(sorted(rec_state["inf"]), np.int64).reshape(-1, 3)
+            rec["summary"] = np.array(rec_state.get("summary", []), np.int64).reshape(-1, 8)
         rec["post"] = snapshot()
         steps.append(rec)
 

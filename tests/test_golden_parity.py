@@ -181,6 +181,20 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
             assert np.array_equal(got, s["health_events"]), f"step {i}: health event tables differ"
             for k_ in got[:, 1]:
                 run_trace.health_rows[int(k_)] = run_trace.health_rows.get(int(k_), 0) + 1
+        if "summary" in s:
+            # the reference's own summarise_infections / _hospitalisations / _deaths on this step's events: the eight
+            # numbers of a summary.csv row per region (records_writer.py:764-773)
+            ref_sum = s["summary"]
+            got_sum = eng.fetch_summary().astype(np.int64)
+            # current_infected, current_hospitalised, daily_hospitalised, current_intensive_care, daily_intensive_care,
+            # daily_hospital_deaths, daily_deaths
+            assert np.array_equal(got_sum[:, [1, 2, 7, 3, 8, 5, 4]], ref_sum[:, [0, 2, 3, 4, 5, 6, 7]]), \
+                f"step {i}: summary row differs\n{got_sum}\n{ref_sum}"
+            if i > 0:  # daily_infected: rows of the infections table by the region of the group (step 0 holds the seeds)
+                ev = eng.fetch_infection_events()
+                by_group = np.bincount((g.world.grp_info[ev["group"]] >> 16).astype(np.int64), minlength=g.world.n_regions)
+                assert np.array_equal(by_group, ref_sum[:, 1]), f"step {i}: daily_infected"
+            run_trace.summary_rows = getattr(run_trace, "summary_rows", 0) + int((ref_sum.sum(axis=1) > 0).sum())
         if "vac_today" in s:
             # the day's vaccinations follow the health update (epidemiology.py:295-303); the reference's
             # own random() per person is replayed
@@ -229,11 +243,12 @@ run_trace.health_rows = {}
 
 @pytest.mark.parametrize("name", FIXTURES)
 def test_oracle_matches_reference_trace(name):
-    run_trace.policy_draws = run_trace.commuters = run_trace.vaccine_draws = run_trace.infection_rows = 0
+    run_trace.policy_draws = run_trace.commuters = run_trace.vaccine_draws = run_trace.infection_rows = run_trace.summary_rows = 0
     run_trace.health_rows = {}
     draws, infections, worst = run_trace("oracle", name)
     if name == "w2k_records":
         assert run_trace.infection_rows > 500
+        assert run_trace.summary_rows > 80, "summary.csv rows of the reference's own summarise_time_step must have been compared"
         assert all(run_trace.health_rows.get(k, 0) > 0 for k in range(1, 7)), run_trace.health_rows
     if name == "w2k_policies":
         assert run_trace.policy_draws > 5000, "the lockdown policies must have drawn"

@@ -105,7 +105,8 @@ def test_philox_mode_full_steps_match_oracle(lane_min, monkeypatch):
         # per-region summary (records_writer.py:151-164): identical, and consistent with the totals
         ra, rb = a.fetch_summary(), b.fetch_summary()
         assert np.array_equal(ra, rb), f"step {i}: per-region summary"
-        assert ra[:, 1].sum() == sa["n_infected"] and ra[:, 2].sum() == sa["n_hospitalised"]
+        # (ward + intensive-care patients of the summary are the people PLACED in their ward by this step, as in the reference)
+        assert ra[:, 1].sum() == sa["n_infected"] and ra[:, 2].sum() + ra[:, 3].sum() == sa["n_by_activity"][ACT_MEDICAL]
         assert ra[:, 4].sum() == sa["n_deaths_step"] and ra[:, 6].sum() == sa["n_recovered_step"]
         assert ra[:, 0].sum() == sa["n_new_infections"] - sa["n_halo_infected"]
         total_new += len(ma)

@@ -107,15 +107,21 @@ def test_summary_csv_rows(tmp_path):
     sim.activity_manager.timer = sim.timer
     sim.run()
     rows = sim.summary_rows()
-    assert len(rows) == 8 * len(w.region_names)
+    # one row per time step and region with anything to report (records_writer.py:764-778)
+    assert 8 * len(w.region_names) < len(rows) <= len(sim.history) * len(w.region_names)
+    assert set(rows[0]) >= set(Simulator.SUMMARY_HEADER)
     per_day = {}
     for r in rows:
         per_day.setdefault(r["time_stamp"], 0)
         per_day[r["time_stamp"]] += r["daily_infected"]
     tot = sum(h["n_new_infections"] for h in sim.history)
-    assert sum(per_day.values()) == tot > 0
+    n_seeds = int(round(0.02 * w.n_people))  # the seeds are rows of the infections table too (infection_seed.py:196-205)
+    assert sum(per_day.values()) == tot + n_seeds and tot > 0
     sim.write_summary_csv(str(tmp_path / "summary.csv"))
-    assert (tmp_path / "summary.csv").read_text().startswith("time_stamp,region,current_infected,daily_infected")
+    # the reference's header, column for column (records_writer.py:151-164)
+    assert (tmp_path / "summary.csv").read_text().splitlines()[0] == (
+        "time_stamp,region,current_infected,daily_infected,current_hospitalised,daily_hospitalised,"
+        "current_intensive_care,daily_intensive_care,daily_hospital_deaths,daily_deaths")
 
 
 def test_policy_file_with_a_policy_that_is_not_evaluated_is_refused_for_its_window(tmp_path):
