@@ -196,6 +196,9 @@ typedef struct {
 #define JB_STEP_INJECT_POLICY 0x40u   /* policy uniforms come from jb_inject_policy_uniforms        */
 #define JB_STEP_RECORD_EVENTS 0x80u   /* keep {where, infector} of every new infection (records)    */
 #define JB_STEP_INJECT_COMMUTE 0x100u /* transports come from jb_inject_commute (test mode)         */
+#define JB_STEP_RECORD_HEALTH 0x200u  /* keep the health events only (jb_fetch_health_events): what a caller needs to
+                                       * mirror deaths / recoveries / symptom changes on its own objects, without the
+                                       * cost of recording who infected whom (JB_STEP_RECORD_EVENTS implies it)  */
 
 /* Per-step outputs (the d2h payload of every step). */
 typedef struct {

@@ -24,7 +24,7 @@ ABI_VERSION = 1
 JB_OK, JB_EINVAL, JB_ECUDA, JB_ENOACT, JB_ECAP, JB_ENOGPU = 0, 1, 2, 3, 4, 5
 STEP_SEVERE_STAY_HOME, STEP_HOSPITALISATION, STEP_INJECT_UNIFORMS = 0x1, 0x2, 0x4
 STEP_NO_NEW_INFECTIONS, STEP_RECORD_LAMBDA, STEP_INJECT_LEISURE, STEP_INJECT_POLICY = 0x8, 0x10, 0x20, 0x40
-STEP_RECORD_EVENTS, STEP_INJECT_COMMUTE = 0x80, 0x100
+STEP_RECORD_EVENTS, STEP_INJECT_COMMUTE, STEP_RECORD_HEALTH = 0x80, 0x100, 0x200
 MAX_POLICIES, POLICY_DRAWS = 8, 3
 POL_SEVERE_STAY_HOME, POL_QUARANTINE, POL_SHIELDING, POL_CLOSE_SCHOOLS, POL_CLOSE_UNIVERSITIES, POL_CLOSE_COMPANIES = 1, 2, 3, 4, 5, 6
 POL_LIMIT_LONG_COMMUTE, POL_CLOSE_COMPANIES_TIERS = 7, 8

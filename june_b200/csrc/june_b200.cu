@@ -1481,7 +1481,7 @@ static HealthArgs make_health_args(JbWorld* w, int old_only) {
   a.pslot = w->pslot; a.phas = w->phas; a.counters = w->counters;
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
   a.summary = w->summary; a.R = (int)w->R; a.grp_info = w->grp_info;
-  if ((w->cur.flags & JB_STEP_RECORD_EVENTS) && w->hev_person) {
+  if ((w->cur.flags & (JB_STEP_RECORD_EVENTS | JB_STEP_RECORD_HEALTH)) && w->hev_person) {
     a.hev_person = w->hev_person; a.hev_kind = w->hev_kind; a.hev_group = w->hev_group; a.hev_cap = w->hev_cap;
     a.pres_group = w->pres_group;
   }
@@ -1672,11 +1672,14 @@ static int resync_step_count(JbWorld* w, int rc) {
 }
 
 static int ensure_event_buffers(JbWorld* w, uint32_t flags) {
-  if (!(flags & JB_STEP_RECORD_EVENTS) || w->ev_group) return JB_OK;
-  TRY(dev_alloc(&w->ev_infected, w->newinf_cap));
-  TRY(dev_alloc(&w->ev_infector, w->newinf_cap));
-  TRY(dev_alloc(&w->ev_group, w->newinf_cap));
-  TRY(dev_alloc(&w->ev_var, w->newinf_cap));
+  if ((flags & JB_STEP_RECORD_EVENTS) && !w->ev_group) {
+    TRY(dev_alloc(&w->ev_infected, w->newinf_cap));
+    TRY(dev_alloc(&w->ev_infector, w->newinf_cap));
+    TRY(dev_alloc(&w->ev_group, w->newinf_cap));
+    TRY(dev_alloc(&w->ev_var, w->newinf_cap));
+    drop_graphs(w);
+  }
+  if (!(flags & (JB_STEP_RECORD_EVENTS | JB_STEP_RECORD_HEALTH)) || w->hev_person) return JB_OK;
   // health events: at most four per infected person and step (symptoms, admission/transfer, recovery or death)
   w->hev_cap = (uint32_t)std::min<uint64_t>(4ull * w->N, 0x7FFFFFFFull);
   TRY(dev_alloc(&w->hev_person, w->hev_cap));
@@ -1963,7 +1966,7 @@ extern "C" int jb_fetch_health_events(JbWorld* w, uint32_t* person, uint32_t* ki
   CK(cudaSetDevice(w->device));
   CK(cudaStreamSynchronize(w->stream));
   *n = 0;
-  if (!w->hev_person || !(w->cur.flags & JB_STEP_RECORD_EVENTS)) return JB_OK;
+  if (!w->hev_person || !(w->cur.flags & (JB_STEP_RECORD_EVENTS | JB_STEP_RECORD_HEALTH))) return JB_OK;
   uint32_t cnt = 0;
   CK(cudaMemcpy(&cnt, w->counters + CNT_HEV, 4, cudaMemcpyDeviceToHost));
   cnt = std::min(cnt, w->hev_cap);

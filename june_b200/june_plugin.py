@@ -12,10 +12,16 @@ What it does
 * ``do_timestep`` (``simulator.py:346-626``): applies the reference's own interaction / regional
   policies to get ``beta_reductions`` and compliances (host scalars), builds the per-step beta
   table with the reference ``Interaction.betas``, and calls ``jb_step``.
-* Infections present on ``Person`` objects (seeding through the reference's ``InfectionSeed``,
-  ``infection_seed.py:209-278``) are uploaded before the step; after the step the people whose
-  state changed get light-weight views written back (``person.infection``, ``person.dead``,
-  immunity), so that seeding, records and checkpoints keep working on the reference's objects.
+* Infections the reference creates on ``Person`` objects (seeding through its ``InfectionSeed``,
+  ``infection_seed.py:209-278``) are caught where they are made (``InfectionSelector.infect_person_at_time``) and
+  uploaded before the step; after the step the people whose state CHANGED -- the step's new infections and its
+  health events, read as compact lists from the device -- get light-weight views written back
+  (``person.infection``, ``person.dead``, immunity), so that seeding, records and checkpoints keep working on the
+  reference's objects.  Per-step host work is proportional to what changed, not to the population;
+  ``b200_sync_people()`` refreshes every person on demand (transmission probabilities, waning vaccine effects).
+* ``b200_reference_rng = True`` makes a run reproduce the reference's own run bit for bit: the Bernoulli uniforms
+  are taken from Python's ``random`` in the reference's draw order, and the new infections are created by the
+  reference's own ``InfectionSelector`` (numpy / scipy) on the host and uploaded.  Slower (test and validation mode).
 """
 from __future__ import annotations
 
@@ -55,6 +61,7 @@ def make_b200_simulator_class(reference_simulator_cls):
         b200_engine: Optional[Engine] = None
         b200_device: int = 0
         b200_seed: int = 0
+        b200_reference_rng: bool = False   # uniforms from Python's `random`, infections from the reference's sampler
 
         # ---- one-off compilation ---------------------------------------------------------------
         def _b200_setup(self):
@@ -101,15 +108,29 @@ def make_b200_simulator_class(reference_simulator_cls):
             else:
                 self._eng = self.b200_engine(self._soa, self._inter, self._dc, prob)
             self._people = list(self.world.people)
+            self._index = {id(p): i for i, p in enumerate(self._people)}
             self._known_infected = np.zeros(len(self._people), bool)
             self._step = 0
+            # infections the reference creates from now on (seeds) are caught where they are made; the ones that
+            # exist already are found by one scan
+            self._pending = [p for p in self._people if p.infection is not None]
+            for sel in self.epidemiology.infection_selectors:
+                if getattr(sel, "_b200_wrapped", False):
+                    continue
+
+                def wrapped(person, time, _orig=sel.infect_person_at_time, _sim=self):
+                    _orig(person=person, time=time)
+                    _sim._pending.append(person)
+                sel.infect_person_at_time = wrapped
+                sel._b200_wrapped = True
 
         # ---- host -> device: infections created by the reference (seeding) -----------------------
         def _b200_upload_new_reference_infections(self):
             rows = []
-            for i, p in enumerate(self._people):
+            for p in self._pending:
+                i = self._index.get(id(p))
                 inf = p.infection
-                if inf is None or self._known_infected[i] or isinstance(inf, _InfectionView):
+                if i is None or inf is None or self._known_infected[i] or isinstance(inf, _InfectionView):
                     continue
                 tr = inf.transmission
                 name = type(tr).__name__
@@ -124,33 +145,50 @@ def make_b200_simulator_class(reference_simulator_cls):
                                  traj_time=[t for t, _ in traj], traj_tag=[int(g) for _, g in traj],
                                  stage=inf.symptoms.stage, max_tag=int(inf.symptoms.max_tag), tag=int(inf.symptoms.tag)))
                 self._known_infected[i] = True
+            self._pending = []
             if rows:
                 self._eng.upload_infections(rows)
 
         # ---- device -> host: views on the reference objects ---------------------------------------
-        def _b200_write_back(self):
-            st = self._eng.fetch_person_state()
-            infected = (st["pstate"] & PS_INFECTED) != 0
-            dead = (st["pstate"] & PS_DEAD) != 0
-            changed = np.nonzero((infected != self._known_infected) | dead)[0]
-            iid = self._selector.infection_class.infection_id()
-            for i in changed:
+        def _b200_write_back(self, new_members, hev):
+            """The people whose state changed in this step: its new infections (device-created ones get a view) and
+            its health events (symptom tag changes, recoveries, deaths)."""
+            cls = self._selector.infection_class
+            exposed = int(self._dc.symptom_tags.get(self._dc.default_lowest_stage, 0))
+            for i in new_members:
+                i = int(i)
+                if i >= len(self._people):
+                    continue  # a visitor from another domain
                 p = self._people[i]
-                if dead[i]:
-                    if not p.dead:
-                        p.dead, p.infection = True, None
-                elif infected[i]:
-                    p.infection = _InfectionView(self._selector.infection_class, st["trans_prob"][i], int(st["tag"][i]))
+                if p.infection is None:
+                    p.infection = _InfectionView(cls, 0.0, exposed)
                     p.immunity.add_immunity(p.infection.immunity_ids())
-                else:
+                self._known_infected[i] = True
+            for i, k, g in zip(hev["person"], hev["kind"], hev["group"]):
+                p, k = self._people[int(i)], int(k)
+                if k == 1:
+                    p.dead, p.infection = True, None
+                    self._known_infected[int(i)] = False
+                elif k == 2:
                     p.infection = None
-                    p.immunity.susceptibility_dict[iid] = float(st["susceptibility"][0][i])
-            self._known_infected = infected & ~dead
-            for i in np.nonzero(self._known_infected)[0]:
-                inf = self._people[i].infection
-                if isinstance(inf, _InfectionView):
+                    self._known_infected[int(i)] = False
+                elif k == 6 and p.infection is not None:
+                    p.infection.symptoms.tag = int(g)
+
+        def b200_sync_people(self):
+            """Refresh every person from the device (O(population); not part of a step): transmission probability and
+            tag of the infected, susceptibility and effective multiplier of everybody."""
+            st = self._eng.fetch_person_state()
+            vs = self._eng.fetch_vaccination()
+            iid = self._selector.infection_class.infection_id()
+            for i, p in enumerate(self._people):
+                inf = p.infection
+                if inf is not None:
                     inf.transmission.probability = float(st["trans_prob"][i])
                     inf.symptoms.tag = int(st["tag"][i])
+                p.immunity.susceptibility_dict[iid] = float(st["susceptibility"][0][i])
+                if vs["dose"][i] >= 0:
+                    p.immunity.effective_multiplier_dict[iid] = float(vs["effective_multiplier"][0][i])
 
         # ---- leisure tables from the reference's own Leisure object ----------------------------------
         def _b200_leisure_table(self, activities, pol):
@@ -239,6 +277,8 @@ def make_b200_simulator_class(reference_simulator_cls):
                 pol.interaction_policies.apply(date=self.timer.date, interaction=self.interaction)
                 pol.regional_compliance.apply(date=self.timer.date, regions=self.world.regions)
             activities = self.timer.activities
+            if getattr(self, "events", None) is not None:  # simulator.py:368-376
+                self._b200_apply_events(activities)
             if not activities:
                 return
             self._b200_upload_new_reference_infections()
@@ -251,7 +291,8 @@ def make_b200_simulator_class(reference_simulator_cls):
             for a in activities:
                 if a in ACTIVITY_CODES:
                     mask |= 1 << ACTIVITY_CODES[a]
-            flags = _lib.STEP_RECORD_EVENTS if self.record is not None else 0
+            # the step's health events (and, with a record, who infected whom) are what the write-back reads
+            flags = _lib.STEP_RECORD_EVENTS if self.record is not None else _lib.STEP_RECORD_HEALTH
             if pol is not None:
                 date = self.timer.date
                 if any(type(p).__name__ == "SevereSymptomsStayHome" and p.is_active(date) for p in pol.individual_policies.policies):
@@ -259,15 +300,77 @@ def make_b200_simulator_class(reference_simulator_cls):
                 if any(type(p).__name__ == "Hospitalisation" and p.is_active(date) for p in pol.medical_care_policies.policies):
                     flags |= _lib.STEP_HOSPITALISATION
             self._b200_policy_records(pol, comp, tiers)
-            params = self._eng.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self._step,
-                                           activity_mask=mask, seed=self.b200_seed, flags=flags, beta=beta,
-                                           leisure_table=self._b200_leisure_table(activities, pol))
-            self.b200_last_stats = self._eng.step(params)
+            table = self._b200_leisure_table(activities, pol)
+            eng = self._eng
+            if not self.b200_reference_rng:
+                params = eng.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self._step,
+                                         activity_mask=mask, seed=self.b200_seed, flags=flags, beta=beta, leisure_table=table)
+                self.b200_last_stats = eng.step(params)
+                new_members = eng.fetch_new_infections()[0]
+            else:
+                new_members = self._b200_step_with_reference_rng(mask, flags, beta, table)
             self._step += 1
-            self._b200_write_back()
+            self._b200_write_back(new_members, eng.fetch_health_events())
             self._b200_vaccinate()
             if self.record is not None:
                 self._b200_feed_record()
+
+        def _b200_apply_events(self, activities):
+            """``Events.apply`` (``event/event.py:93-107``).  The reference's events act on its Python objects
+            (``Mutation`` swaps ``person.infection``, ``DomesticCare`` moves people between households, ...), which
+            the device does not see: an active event is either one that brings its device form -- a method
+            ``b200_apply(simulator)``, e.g. calling ``simulator._eng.mutate`` -- or an error, never silently dropped."""
+            date = self.timer.date
+            for event in (self.events.events or []):
+                if not event.is_active(date=date):
+                    continue
+                hook = getattr(event, "b200_apply", None)
+                if hook is None:
+                    raise NotImplementedError(
+                        f"event {type(event).__name__} is active on {date} and has no device form (INTEGRATION.md "
+                        "section 4): give it a b200_apply(simulator) method, or run without it")
+                hook(self)
+
+        def _b200_step_with_reference_rng(self, mask, flags, beta, table):
+            """The reference's own random streams: every Bernoulli draw takes the next ``random.random()`` in the
+            reference's traversal order (``interaction.py:610-641``), and the newly infected get their infection from
+            the reference's ``InfectionSelector`` in the order ``Epidemiology.infect_people`` walks them
+            (``epidemiology.py:317-322``) -- a run equals the reference's run with the same seeds."""
+            import random
+            eng, soa = self._eng, self._soa
+            flags |= _lib.STEP_INJECT_UNIFORMS | _lib.STEP_NO_NEW_INFECTIONS | _lib.STEP_RECORD_LAMBDA | _lib.STEP_RECORD_EVENTS
+            state = random.getstate()
+            cap = len(self._people)  # nobody draws twice in a step
+            eng.inject_uniforms(np.array([random.random() for _ in range(cap)]))
+            params = eng.make_params(now=self.timer.now, delta_time=self.timer.duration, step=self._step,
+                                     activity_mask=mask, seed=self.b200_seed, flags=flags, beta=beta, leisure_table=table)
+            eng.step_begin(params)
+            eng.step_interact()
+            n_draws = int((~np.isnan(eng.fetch_lambda()[:cap])).sum())
+            random.setstate(state)  # the reference consumed exactly one uniform per draw
+            for _ in range(n_draws):
+                random.random()
+            ev = eng.fetch_infection_events()
+            # order of Simulator.do_timestep's infected_ids: group by group, inside a group in registration order
+            keys = []
+            for person, g in zip(ev["infected"], ev["group"]):
+                lo, hi = int(soa.grp_offset[g]), int(soa.grp_offset[g + 1])
+                pos = np.nonzero(soa.reg_member[lo:hi] == person)[0]
+                keys.append((int(g), int(pos[0]) if len(pos) else hi - lo + int(person)))
+            order = sorted(range(len(keys)), key=keys.__getitem__)
+            # numpy's global stream: the reference draws two numbers per new infection while it interacts (who is to
+            # blame: the infector's subgroup and the infector, interaction.py:643-662 -- np.random.choice with p takes
+            # one uniform), before any infection is created
+            np.random.random_sample(2 * len(order))
+            sel = self.epidemiology.infection_selectors
+            iid = self._selector.infection_class.infection_id()
+            for k in order:
+                i = int(ev["infected"][k])
+                if i < len(self._people):
+                    sel.infect_person_at_time(person=self._people[i], time=self.timer.now, infection_id=iid)
+            self._b200_upload_new_reference_infections()
+            self.b200_last_stats = eng.step_finish()
+            return ev["infected"]
 
         # ---- the reference's vaccination campaigns -> device tables ----------------------------------
         def _b200_vaccinate(self):
@@ -292,16 +395,23 @@ def make_b200_simulator_class(reference_simulator_cls):
                 self._b200_vac_names = [v.name for v in mine.vaccines()]
             self._eng.vaccinate((today - self._b200_vac_first).days, seed=self.b200_seed)
             vs = self._eng.fetch_vaccination()
-            st = self._eng.fetch_person_state()
+            prev = getattr(self, "_b200_vac_dose", None)
+            if prev is None:
+                prev = np.full(len(self._people), -1, np.int8)
+            changed = np.nonzero(vs["dose"] != prev)[0]  # the people who got a dose today
+            self._b200_vac_dose = vs["dose"].copy()
+            if not len(changed):
+                return
             iid = self._selector.infection_class.infection_id()
             events = getattr(self.record, "events", None) if self.record is not None else None
-            for i in np.nonzero(vs["dose"] >= 0)[0]:
+            susc = self._eng.fetch_person_state()["susceptibility"][0] if len(changed) else None
+            for i in changed:
                 p = self._people[i]
-                if events is not None and p.vaccinated != int(vs["dose"][i]):  # vaccines.py:309-313
+                if events is not None:  # vaccines.py:309-313
                     events["vaccines"].accumulate(p.id, self._b200_vac_names[int(vs["vaccine"][i])], int(vs["dose"][i]))
                 p.vaccinated = int(vs["dose"][i])
                 p.vaccine_type = self._b200_vac_names[int(vs["vaccine"][i])]
-                p.immunity.susceptibility_dict[iid] = float(st["susceptibility"][0][i])
+                p.immunity.susceptibility_dict[iid] = float(susc[i])
                 p.immunity.effective_multiplier_dict[iid] = float(vs["effective_multiplier"][0][i])
 
         # ---- device events -> the reference's Record (records_writer.py:203-246) ----------------------

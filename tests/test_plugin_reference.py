@@ -187,3 +187,120 @@ def test_reference_simulator_subclass_vaccinates_from_the_reference_campaigns():
     assert max(p.vaccinated for p in vacc(old)) == 1 and max(p.vaccinated for p in vacc(mid)) == 0
     never_infected = [p for p in vacc(old) if p.infection is None and p.immunity.susceptibility_dict.get(iid, 1.0) > 0]
     assert len(never_infected) > 20 and all(p.immunity.susceptibility_dict[iid] < 1.0 for p in never_infected)
+
+
+def _side_by_side(engine_kind, n_people=10_000, days=10):
+    """configs[0]: a programmatic world (households, schools, companies, care homes, hospital), the reference's own
+    CPU ``Simulator`` and the drop-in run side by side from the same seeds."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_world
+    from june_b200.june_plugin import make_b200_simulator_class
+    from helpers import make_engine
+
+    def build():
+        random.seed(11)
+        np.random.seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            world, dc = ref_world.build_world(n_people, seed=11)
+            sim = ref_world.make_simulator(world, dc, total_days=days, cases_per_capita=0.02)
+        return world, sim
+
+    def run(sim, world):
+        trace = []
+        orig = type(sim).do_timestep
+
+        def step(self):
+            orig(self)
+            trace.append(frozenset(i for i, p in enumerate(world.people) if p.infected))
+        type(sim).do_timestep = step
+        try:
+            random.seed(5)
+            np.random.seed(5)
+            with contextlib.redirect_stdout(io.StringIO()):
+                sim.run()
+        finally:
+            type(sim).do_timestep = orig
+        # (person ids are a process-wide counter in the reference: people are compared by their position in the world)
+        dead = frozenset(i for i, p in enumerate(world.people) if p.dead)
+        immune = frozenset(i for i, p in enumerate(world.people) if p.immunity.get_susceptibility(170852960) == 0.0)
+        return trace, dead, immune
+
+    world_a, ref_sim = build()
+    ages_a = [(p.age, p.sex) for p in world_a.people]
+    # The one rule of the path that the device does not evaluate: "a child under 15 who has to stay home fetches a random
+    # adult housemate" (individual_policies.py:57-77).  The reference itself switches it off when it runs domain
+    # decomposed (`if mpi_size == 1`): the comparison is made against that mode of the reference.
+    import june.policy.individual_policies as ref_ip
+    saved_mpi_size = ref_ip.mpi_size
+    ref_ip.mpi_size = 2
+    try:
+        ref_trace, ref_dead, ref_immune = run(ref_sim, world_a)
+    finally:
+        ref_ip.mpi_size = saved_mpi_size
+
+    world_b, proto = build()
+    assert [(p.age, p.sex) for p in world_b.people] == ages_a, "the two worlds must be built identically"
+    from june.simulator import Simulator
+    B200Simulator = make_b200_simulator_class(Simulator)
+    B200Simulator.b200_engine = staticmethod(lambda soa, inter, dcfg, prob: make_engine(engine_kind, soa, prob, interaction=inter, disease=dcfg))
+    B200Simulator.b200_reference_rng = True
+    sim = B200Simulator(world=world_b, interaction=proto.interaction, timer=proto.timer, activity_manager=proto.activity_manager,
+                        epidemiology=proto.epidemiology, tracker=None, record=None)
+    trace, dead, immune = run(sim, world_b)
+    assert len(trace) == len(ref_trace) >= 4 * days
+    for k, (a, b) in enumerate(zip(ref_trace, trace)):
+        assert a == b, f"step {k}: infected people differ ({len(a)} in the reference, {len(b)} here, {len(a ^ b)} apart)"
+    assert dead == ref_dead and immune == ref_immune
+    assert len(ref_trace[-1] | ref_immune) > 2 * int(0.02 * n_people), "the epidemic must have spread"
+    return len(ref_trace), len(ref_immune)
+
+
+def test_drop_in_equals_the_reference_simulator_step_for_step():
+    """``B200Simulator`` with the reference's random streams reproduces the reference ``Simulator``: identical sets of
+    infected people after every one of the run's steps, identical deaths and immunities at the end."""
+    _side_by_side("oracle")
+
+
+def test_active_events_are_applied_through_their_device_form_or_refused():
+    """``do_timestep`` applies ``self.events`` like the reference (simulator.py:368-376): an active event without a
+    device form is an error, not a silent no-op."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_world
+    from june_b200.june_plugin import make_b200_simulator_class
+    from helpers import make_engine
+    random.seed(6)
+    np.random.seed(6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        world, dc = ref_world.build_world(1500, seed=6)
+        ref_sim = ref_world.make_simulator(world, dc, total_days=2, cases_per_capita=0.03)
+    from june.event import Event, Events
+    from june.simulator import Simulator
+
+    class Plain(Event):
+        def initialise(self, world=None):
+            pass
+
+        def apply(self, world, simulator, activities, day_type):
+            raise AssertionError("the reference form must not run on the device path")
+
+    class WithDeviceForm(Plain):
+        calls = 0
+
+        def b200_apply(self, simulator):
+            type(self).calls += 1
+            assert simulator._eng is not None
+
+    B200Simulator = make_b200_simulator_class(Simulator)
+    B200Simulator.b200_engine = staticmethod(lambda soa, inter, dcfg, prob: make_engine("oracle", soa, prob, interaction=inter, disease=dcfg))
+
+    def make(events):
+        return B200Simulator(world=world, interaction=ref_sim.interaction, timer=ref_sim.timer, activity_manager=ref_sim.activity_manager,
+                             epidemiology=ref_sim.epidemiology, tracker=None, record=None, events=Events(events))
+    sim = make([WithDeviceForm(start_time="2020-03-02", end_time="2020-03-03"), Plain(start_time="2021-01-01", end_time="2021-02-01")])
+    with contextlib.redirect_stdout(io.StringIO()):
+        sim.do_timestep()
+    assert WithDeviceForm.calls == 1
+    sim.events = Events([Plain(start_time="2020-03-01", end_time="2020-04-01")])
+    with pytest.raises(NotImplementedError, match="Plain"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim.do_timestep()
