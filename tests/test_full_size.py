@@ -51,7 +51,9 @@ def test_full_size_parity_determinism_and_invariants():
         assert sum(sa["n_by_activity"]) + dead_before == w.n_people, "everybody alive is placed exactly once"
         dead_before = sa["n_dead_total"]  # placement precedes the step's health update
         assert sa["n_no_activity"] == 0
-        assert ga[:, 1].sum() == sa["n_infected"] and ga[:, 2].sum() == sa["n_hospitalised"] and ga[:, 3].sum() == sa["n_icu"]
+        # (the summary's ward / intensive-care columns count the people PLACED there by this step, like the reference's
+        # len(hospital.ward) / len(hospital.icu): records_writer.py:290-294)
+        assert ga[:, 1].sum() == sa["n_infected"] and ga[:, 2].sum() + ga[:, 3].sum() == sa["n_by_activity"][0]
         assert ga[:, 0].sum() == sa["n_new_infections"]
         total_new += len(ma)
     assert total_new > 20_000
