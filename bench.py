@@ -111,7 +111,46 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
-def build_setup(n_people: int, rank: int, world_size: int, dist=None, leisure: bool = False):
+def lockdown_policies(dc):
+    """The reference's default policy file (policy_covid19.yaml) with its dates moved from the years 3020 / 3021, where
+    the shipped file parks them, to 2020 / 2021: the UK's spring-2020 measures (quarantine, shielding, school /
+    company / venue closures, social distancing, reduced leisure)."""
+    import copy
+    import tempfile
+    import yaml
+
+    def shift(x):
+        if isinstance(x, dict):
+            return {k: shift(v) for k, v in x.items()}
+        if isinstance(x, str) and x[:4] in ("3020", "3021"):
+            return "2" + x[1:]
+        return x
+    cfg = shift(copy.deepcopy(load_defaults()["policy"]["covid19"]))
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
+        yaml.safe_dump(cfg, f)
+    try:
+        return Policies.from_file(f.name, disease_config=dc)
+    finally:
+        os.unlink(f.name)
+
+
+def vaccination_campaigns():
+    """Two campaigns running over the bench window: the over-50s (two doses), then everybody between 16 and 50."""
+    from june_b200.vaccination import Vaccine, VaccinationCampaign, VaccinationCampaigns
+    v = Vaccine.from_config_dict("Pfizer", dict(
+        days_administered_to_effective=[14, 7], days_effective_to_waning=[60, 180], days_waning=[30, 90], waning_factor=0.8,
+        sterilisation_efficacies=[{"Covid19": {"0-100": 0.52}}, {"Covid19": {"0-100": 0.90}}],
+        symptomatic_efficacies=[{"Covid19": {"0-100": 0.60}}, {"Covid19": {"0-100": 0.95}}]))
+    return VaccinationCampaigns([
+        VaccinationCampaign(vaccine=v, days_to_next_dose=[0, 21], dose_numbers=[0, 1], start_time="2020-03-20",
+                            end_time="2020-06-01", group_by="age", group_type="50-100", group_coverage=0.8),
+        VaccinationCampaign(vaccine=v, days_to_next_dose=[0, 21], dose_numbers=[0, 1], start_time="2020-03-27",
+                            end_time="2020-07-01", group_by="age", group_type="16-50", group_coverage=0.6),
+    ])
+
+
+def build_setup(n_people: int, rank: int, world_size: int, dist=None, leisure: bool = False, config4: bool = False):
+    leisure = leisure or config4
     defaults = load_defaults()
     sb = defaults["company_sector_betas"]
     if world_size == 1:
@@ -127,6 +166,9 @@ def build_setup(n_people: int, rank: int, world_size: int, dist=None, leisure: b
     cfg["time"]["total_days"] = 10_000
     cfg["time"]["initial_day"] = "2020-03-02 8:00"  # a Monday
     policies = Policies.from_file(disease_config=dc)
+    if config4:
+        cfg["time"]["initial_day"] = "2020-03-30 8:00"  # a Monday inside the spring-2020 lockdown
+        policies = lockdown_policies(dc)
     return world, inter, dc, prob, cfg, policies
 
 
@@ -159,16 +201,21 @@ def interaction_bytes(world, sg, n_present: int) -> int:
     return int(14 * n_present + 8 * n_sub * f + 8 * n_grp * f)
 
 
-def workload_name(n_total: int, leisure: bool) -> str:
+def workload_name(n_total: int, leisure: bool, config4: bool = False) -> str:
     """The workload both arms run (same generator, schedule and seeding)."""
+    if config4:
+        return (f"synthetic {n_total / 1e6:.1f}M-person world (households, schools, companies, care homes, hospitals, pubs, "
+                "cinemas, groceries, gyms with leisure), default 5/4-step day schedule from Monday 2020-03-30 08:00, the "
+                "reference's default policy file with its dates in 2020 (spring lockdown: quarantine, shielding, school / "
+                "company / venue closures, social distancing, reduced leisure), two vaccination campaigns, ~3% seeded prevalence")
     return (f"synthetic {n_total / 1e6:.1f}M-person world (households, schools, companies, care homes, hospitals"
             + (", pubs, cinemas, groceries, gyms with leisure" if leisure else "")
             + "), default 5/4-step day schedule from Monday 2020-03-02 08:00, default policy file, ~3% seeded prevalence")
 
 
-def config_dict(n_total: int, leisure: bool) -> dict:
+def config_dict(n_total: int, leisure: bool, config4: bool = False) -> dict:
     """Identical in both arms (the driver compares the dicts): what is simulated, not how."""
-    return {"workload": workload_name(n_total, leisure), "people_total": n_total,
+    return {"workload": workload_name(n_total, leisure, config4), "people_total": n_total,
             "l2": "inputs larger than the cache (>= 14 GB at 56 M people against 126 MB of L2) and the L2 flushed between "
                   "timed steps"}
 
@@ -192,11 +239,14 @@ def run_gpu(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_people, n_total, scaling = sizes(args, world_size)
-    world, inter, dc, prob, cfg, policies = build_setup(n_people, rank, world_size, dist, leisure=args.leisure)
+    world, inter, dc, prob, cfg, policies = build_setup(n_people, rank, world_size, dist, leisure=args.leisure, config4=args.config4)
     sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, device=local_rank,
                               seed=2020, distributed=world_size > 1)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
+    if args.config4:
+        from june_b200.simulator import Epidemiology
+        sim.epidemiology = Epidemiology(vaccination_campaigns=vaccination_campaigns())
     seed_epidemic(sim, rank)
     sim.prepare_leisure_tables(days=14)
     # every step graph the schedule needs is captured and instantiated here, before anything is timed
@@ -362,18 +412,18 @@ def run_gpu(args):
         except Exception:
             pass
 
-    cpu = (cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s=args.cpu_seconds)
+    cpu = (cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s=args.cpu_seconds, config4=args.config4)
            if world_size == 1 and args.cpu_seconds > 0 else None)
     # per step: the parameter block (StepDev header of 64 B + the beta table [rule][region] of doubles) is pulled
-    # from pinned host memory by k_step_begin; the counter block (20 step counters + 8 per region) is pushed
+    # from pinned host memory by k_step_begin; the counter block (20 step counters + 9 per region) is pushed
     # into pinned host memory by k_step_end
     h2d = int(64 + world.n_regions * len(world.beta_rules) * 8)
-    d2h = int((20 + 8 * world.n_regions) * 4)
+    d2h = int((20 + 9 * world.n_regions) * 4)
     out = {
         "metric": METRIC, "value": ps / (total_ms * 1e-3), "unit": "person-timesteps/s", "n_gpus": world_size,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(n_total, args.leisure),
+        "config": config_dict(n_total, args.leisure, args.config4),
         "people_per_gpu": n_people,
         "parallelism": "1 domain per GPU" + (", halo exchange over peer memory on primary-activity steps; ranks aligned by a "
                                               "one-word all-reduce before each timed bracket" if world_size > 1 else ""),
@@ -403,13 +453,16 @@ def oracle_engine(world, inter, dc, prob):
     return eng
 
 
-def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int, budget_s: float = 0.0):
+def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int, budget_s: float = 0.0, config4: bool = False):
     """Time `steps` steps of the CPU port after `warmup` steps; with a budget, as many steps as fit in
     ~budget_s seconds (at least 3, at most `steps`), decided from the duration of the warm-up."""
     eng = oracle_engine(world, inter, dc, prob)
     sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, engine=eng, seed=2020)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
+    if config4:
+        from june_b200.simulator import Epidemiology
+        sim.epidemiology = Epidemiology(vaccination_campaigns=vaccination_campaigns())
     seed_epidemic(sim, 0)
     t0 = time.perf_counter()
     for _ in range(warmup):
@@ -429,10 +482,10 @@ def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int, budg
     return ps, dt, threads, steps
 
 
-def cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s: float = 15.0):
+def cpu_baseline(world, inter, dc, prob, cfg, policies, budget_s: float = 15.0, config4: bool = False):
     """Oracle port on the host cores, bounded sample: as many steps of the same world as fit in
     ~budget_s seconds (at least 3)."""
-    ps, dt, threads, steps = cpu_run(world, inter, dc, prob, cfg, policies, steps=40, warmup=2, budget_s=budget_s)
+    ps, dt, threads, steps = cpu_run(world, inter, dc, prob, cfg, policies, steps=40, warmup=2, budget_s=budget_s, config4=config4)
     return {"value": ps / dt, "unit": "person-timesteps/s", "cores": threads, "kind": "port",
             "sample": f"{steps} steps of the same {world.n_people}-person world (oracle/june_oracle.c, OpenMP, {threads} threads)"}
 
@@ -447,13 +500,13 @@ def run_reference(args):
     if rank != 0:
         return
     _, n_total, scaling = sizes(args, world_size)
-    world, inter, dc, prob, cfg, policies = build_setup(n_total, 0, 1, leisure=args.leisure)
-    ps, dt, threads, steps = cpu_run(world, inter, dc, prob, cfg, policies, steps=args.steps, warmup=args.warmup)
+    world, inter, dc, prob, cfg, policies = build_setup(n_total, 0, 1, leisure=args.leisure, config4=args.config4)
+    ps, dt, threads, steps = cpu_run(world, inter, dc, prob, cfg, policies, steps=args.steps, warmup=args.warmup, config4=args.config4)
     v = ps / dt
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "person-timesteps/s", "n_gpus": world_size,
            "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": config_dict(n_total, args.leisure),
+           "config": config_dict(n_total, args.leisure, args.config4),
            "parallelism": f"rank 0 only: the undivided {n_total}-person world on {threads} OpenMP threads (all host cores)",
            "cpu_baseline": {"value": v, "unit": "person-timesteps/s", "cores": threads, "kind": "port",
                             "sample": f"{steps} steps of the {n_total}-person world on rank 0, {threads} threads"},
@@ -472,7 +525,9 @@ def main():
     ap.add_argument("--people-per-gpu", type=int, default=0, help="fix the people per GPU instead (weak scaling)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--leisure", action="store_true",
-                    help="add pubs / cinemas / groceries / gyms and the leisure placement (BASELINE.json configs[3])")
+                    help="add pubs / cinemas / groceries / gyms and the leisure placement")
+    ap.add_argument("--config4", action="store_true",
+                    help="BASELINE.json configs[3]: leisure + the lockdown / closure policies of spring 2020 + vaccination campaigns")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -82,36 +82,56 @@ __device__ __forceinline__ double jb_policy_uniform(const PlaceArgs& a, uint32_t
   return (j & 1u) ? jb_u52(r.x[2], r.x[3]) : jb_u52(r.x[0], r.x[1]);
 }
 
-// CloseCompanies.check_skips_activity (individual_policies.py:651-770).  NaN = None.
+// The first two uniforms of policy k for person p (one Philox block), or the injected ones.
+__device__ __forceinline__ void jb_policy_uniform01(const PlaceArgs& a, uint32_t p, uint32_t k, double& u0, double& u1) {
+  if (a.pol_inject) {
+    u0 = a.pol_inject[((size_t)k * JB_POLICY_DRAWS + 0) * a.N + p];
+    u1 = a.pol_inject[((size_t)k * JB_POLICY_DRAWS + 1) * a.N + p];
+    return;
+  }
+  const JbPhilox4 r = jb_philox4x32_10(a.gid_base + a.int2ext[p], a.sp->step, JB_STREAM_POLICY0 + k, 0u,
+                                       (uint32_t)a.sp->seed, (uint32_t)(a.sp->seed >> 32));
+  u0 = jb_u52(r.x[0], r.x[1]);
+  u1 = jb_u52(r.x[2], r.x[3]);
+}
+
+// CloseCompanies.check_skips_activity (individual_policies.py:651-770).  NaN = None.  The draws are consumed in order
+// (u0, u1, then a third one); the first two come from ONE Philox block computed up front, so the branches of the
+// decision tree hold no generator code (the lanes of a warp take different branches).
 __device__ bool jb_close_companies_skips(const PlaceArgs& a, uint32_t p, uint32_t k, const JbIndividualPolicy& q, int status) {
   const double awp = q.p[0], fp = q.p[1], kp = q.p[2], fr = q.p[3], kr = q.p[4], rr = q.p[5];
   const bool have_f = !isnan(fr) && !isnan(fp), have_k = !isnan(kr) && !isnan(kp), have_r = !isnan(rr);
-  uint32_t j = 0;
   if (q.flags & 1u) return true;  // full_closure
+  double u[2];
+  jb_policy_uniform01(a, p, k, u[0], u[1]);
+  uint32_t j = 0;
+  bool decided = false, skip = false;
   if (status == 3) {  // furlough
     if (!have_f) return true;
     if (fr < fp) return true;
-    if (jb_policy_uniform(a, p, k, j++) < fp / fr) return true;
-    return !isnan(awp) && jb_policy_uniform(a, p, k, j++) < awp;
+    if (u[j++] < fp / fr) return true;
+    return !isnan(awp) && u[j++] < awp;
   }
   if (status == 1 && have_k)  // key worker
-    return kr > kp && jb_policy_uniform(a, p, k, j++) > kp / kr;
+    return kr > kp && u[j++] > kp / kr;
   if (status == 2 && !isnan(awp)) {  // random
     if (have_f && have_k && have_r) {
       if (fr < fp && kr < kp) {
-        if (jb_policy_uniform(a, p, k, j++) < (fp - fr) / rr) return true;
-        else if (jb_policy_uniform(a, p, k, j++) < (kp - kr) / (rr - (fp - fr))) return false;
+        if (u[j++] < (fp - fr) / rr) { decided = true; skip = true; }
+        else if (u[j++] < (kp - kr) / (rr - (fp - fr))) { decided = true; skip = false; }
       } else if (fr < fp) {
-        if (jb_policy_uniform(a, p, k, j++) < (fp - fr) / rr) return true;
+        if (u[j++] < (fp - fr) / rr) { decided = true; skip = true; }
       } else if (kr < kp) {
-        if (jb_policy_uniform(a, p, k, j++) < (kp - kr) / rr) return false;
+        if (u[j++] < (kp - kr) / rr) { decided = true; skip = false; }
       }
     } else if (have_f && have_r) {
-      if (fr < fp && jb_policy_uniform(a, p, k, j++) < (fp - fr) / rr) return true;
+      if (fr < fp && u[j++] < (fp - fr) / rr) { decided = true; skip = true; }
     } else if (have_k && have_r) {
-      if (kr < kp && jb_policy_uniform(a, p, k, j++) < (kp - kr) / rr) return false;
+      if (kr < kp && u[j++] < (kp - kr) / rr) { decided = true; skip = false; }
     }
-    return jb_policy_uniform(a, p, k, j++) < awp;
+    if (decided) return skip;
+    const double last = j < 2 ? u[j] : jb_policy_uniform(a, p, k, j);  // (the third draw: both tests above failed)
+    return last < awp;
   }
   return false;
 }
@@ -125,8 +145,12 @@ __device__ __noinline__ uint32_t jb_apply_policies(const PlaceArgs& a, uint32_t 
   const uint32_t age = a.age[p];
   const bool infected = (st & JB_PS_INFECTED) != 0;
   const int tagbit = infected ? JB_TAG_BIT(a.ptag[p]) : 0;
+  // skip-activity policies only drop primary_activity / commute: when the step offers neither they are not evaluated
+  // (their draws are keyed per policy, nothing else depends on them)
+  const bool can_skip = (allowed & ((1u << JB_ACT_PRIMARY) | (1u << JB_ACT_COMMUTE))) != 0u;
   for (uint32_t k = 0; k < a.n_pol; ++k) {
     const JbIndividualPolicy& q = P.pol[k];
+    if (!can_skip && q.type != JB_POL_SEVERE_STAY_HOME && q.type != JB_POL_QUARANTINE && q.type != JB_POL_SHIELDING) continue;
     switch (q.type) {
       case JB_POL_SEVERE_STAY_HOME:
         if (tagbit & a.severe_mask) return allowed & stay;

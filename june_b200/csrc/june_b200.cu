@@ -1260,13 +1260,21 @@ static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
   return JB_OK;
 }
 
+// Individual policies only ever REMOVE activities other than medical_facility and residence (stay-home policies keep
+// exactly those two, skip-activity policies drop primary_activity / commute: individual_policies.py:87-119,441-824).
+// In a step that offers nothing else they cannot change anybody's placement, so the table-driven placement is exact.
+static inline bool policies_decide_per_person(const JbWorld* w, uint32_t activity_mask) {
+  const uint32_t stay = (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
+  return w->n_pol != 0 && !w->pol_subject_mode && (activity_mask & ~stay & ((1u << JB_N_ACT) - 1u)) != 0u;
+}
+
 // Does this step place people one by one (individual policies, leisure or commute draws)?  Then the mirrored
 // supergroups read the per-step copy the placement writes instead of the persistent mirror.
 static inline bool step_places_per_person(const JbWorld* w) {
   const JbStepParams& p = w->cur;
   const bool commute = (p.activity_mask & (1u << JB_ACT_COMMUTE)) &&
                        (w->cmt.person != nullptr || ((p.flags & JB_STEP_INJECT_COMMUTE) && w->cm_inject != nullptr));
-  return (w->n_pol != 0 && !w->pol_subject_mode) || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) || commute;
+  return policies_decide_per_person(w, p.activity_mask) || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) || commute;
 }
 
 static int launch_groups(JbWorld* w, int mode) {
@@ -1418,7 +1426,9 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     pa.severe_mask = w->dis_host.severe_mask;
     pa.grp_info = w->grp_info; pa.summary = w->summary;
     const uint32_t chunks = (w->N + 15) / 16;
-    const bool full = (w->n_pol != 0 && !w->pol_subject_mode) || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
+    const bool pol_now = policies_decide_per_person(w, p.activity_mask);
+    if (!pol_now) { pa.pol = nullptr; pa.n_pol = 0; }
+    const bool full = pol_now || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
                       pa.cmt.person != nullptr || pa.cmt.inject != nullptr;
     if (full != step_places_per_person(w)) { jb_set_error("internal: placement flavour mismatch"); return JB_EINVAL; }
     if (w->mir_slots && (p.activity_mask & (1u << JB_ACT_PRIMARY))) {  // the mirrored supergroups run in this step
