@@ -323,6 +323,33 @@ typedef struct {
   const uint32_t* area_venue;  /* [area_off[n_areas * K]] group indices                      */
 } JbLeisureDesc;
 int jb_set_leisure(JbWorld* w, const JbLeisureDesc* desc);
+
+/* ---- residence visits (groups/leisure/residence_visits.py:297-345, groups/household.py:110-149,202-205) ----
+ * One of the K leisure activities (`activity`, set up by jb_set_leisure with any supergroup: it is not used) sends a
+ * person to a residence its OWN household is linked to: a household (the visitor joins the subgroup of its age --
+ * kids < 18, young adults <= 25, adults < 65, old adults -- household.py:110-123) or a care home (subgroup
+ * `care_home_subgroup` of a group of `care_home_supergroup`, which must have has_dynamic set).  Which kind, when the
+ * household has both: residence_type_probabilities, normalised over the kinds it has (:308-322); which one: uniform.
+ * A visited household welcomes its visitors (Household.get_leisure_subgroup -> make_household_residents_stay_home):
+ * residents already out doing leisure come back home, residents not yet placed stay home instead of drawing a leisure
+ * activity -- the reference walks the people in world order, and so does this (by the caller's person index).
+ * CSR rows are indexed by the household's ordinal inside `household_supergroup` (group - first group). */
+typedef struct {
+  int32_t activity;              /* index of the residence_visits activity in the leisure tables          */
+  int32_t household_supergroup;
+  int32_t care_home_supergroup;  /* -1: no care-home visits                                                */
+  int32_t care_home_subgroup;
+  const uint32_t* household_off; /* [n_households + 1]                                                     */
+  const uint32_t* household_target; /* group indices of `household_supergroup`                            */
+  const uint32_t* care_home_off; /* [n_households + 1] or null                                             */
+  const uint32_t* care_home_target;
+  double p_household, p_care_home;  /* residence_type_probabilities                                        */
+  int32_t household_visits_beta; /* beta rule of a household that is being visited ("household_visits",
+                                  * InteractiveHousehold.get_processed_beta, household.py:279-289)        */
+} JbVisitsDesc;
+int jb_set_visits(JbWorld* w, const JbVisitsDesc* desc);
+/* ChangeVisitsProbability (policy/leisure_policies.py:180-220): new residence_type_probabilities. */
+int jb_set_visit_probabilities(JbWorld* w, double p_household, double p_care_home);
 /* Probability tables (Leisure.generate_leisure_probabilities_for_timestep, leisure.py:205-228,
  * 297-372): table t holds does[n_regions][2 (f, m)][100] = P(does any activity) and
  * cum[n_regions][2][100][K] = cumulative P(activity | does).  JbStepParams.leisure_table picks

@@ -91,6 +91,13 @@ class JbVaccine(C.Structure):
                 ("waning_factor", C.c_double), ("sterilisation", C.c_void_p), ("symptomatic", C.c_void_p)]
 
 
+class JbVisitsDesc(C.Structure):
+    _fields_ = [("activity", C.c_int32), ("household_supergroup", C.c_int32), ("care_home_supergroup", C.c_int32),
+                ("care_home_subgroup", C.c_int32), ("household_off", C.c_void_p), ("household_target", C.c_void_p),
+                ("care_home_off", C.c_void_p), ("care_home_target", C.c_void_p), ("p_household", C.c_double),
+                ("p_care_home", C.c_double), ("household_visits_beta", C.c_int32)]
+
+
 class JbVaccinationState(C.Structure):
     _fields_ = [("dose", C.c_void_p), ("vaccine", C.c_void_p), ("campaign", C.c_void_p), ("first_day", C.c_void_p),
                 ("stage", C.c_void_p), ("prior_infection", C.c_void_p), ("prior_symptoms", C.c_void_p),
@@ -145,7 +152,7 @@ ABI_SYMBOLS = [
     "set_commute", "inject_commute",
     "set_vaccination", "vaccinate", "inject_vaccination_uniforms", "fetch_vaccination",
     "p2p_window", "p2p_connect", "flush_l2", "fetch_health_events", "set_medical", "set_halo_activities", "set_variants", "mutate", "set_person_work_regions",
-    "step_prepare", "world_describe", "vaccination_state",
+    "step_prepare", "world_describe", "vaccination_state", "set_visits", "set_visit_probabilities",
 ]
 
 
@@ -211,6 +218,8 @@ def bind(lib: C.CDLL, prefix: str) -> C.CDLL:
     f("inject_vaccination_uniforms").argtypes = [vp, vp]
     f("fetch_vaccination").argtypes = [vp, vp, vp, vp]
     f("vaccination_state").argtypes = [vp, C.c_int, C.POINTER(JbVaccinationState)]
+    f("set_visits").argtypes = [vp, C.POINTER(JbVisitsDesc)]
+    f("set_visit_probabilities").argtypes = [vp, C.c_double, C.c_double]
     f("flush_l2").argtypes = [vp, C.c_size_t]
     f("set_medical").argtypes = [vp, vp]
     f("set_halo_activities").argtypes = [vp, C.c_uint32]

@@ -157,20 +157,18 @@ __device__ __noinline__ uint32_t jb_blame_group(const GroupArgs& a, const JbGrp&
   return infector;
 }
 
-// EV: record infection events (who infected whom, JB_STEP_RECORD_EVENTS).  A separate
-// instantiation, so that the rare blame path costs the common launch neither registers nor stack.
+// One group (entry `gi_` of the launch's list); called by the threads that share it (a warp, or the CTA).
 template <int VM, int WPG, bool EV>
-__global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ GroupArgs a) {
-  jb_stamp(3); jb_stamp(4);
+__device__ __forceinline__ void jb_group_one(const GroupArgs& a, const uint32_t gi_) {
   const double* const trans = jb_trans_read(a.trans, a.NP, a.sp);
   extern __shared__ __align__(8) unsigned char smem_raw[];
   constexpr int GT = 32 * WPG;                 // threads per group
-  constexpr int GPC = JB_CTA_WARPS / WPG;      // groups per CTA
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wl = wib % WPG, gs = wib / WPG, tg = threadIdx.x - gs * GT;
-  const uint32_t gi_ = blockIdx.x * GPC + gs;
-  if (gi_ >= a.n_list) return;  // uniform over the group's threads
   const uint32_t g = a.group_list ? a.group_list[gi_] : a.g0 + gi_;
+  // a household that is being visited belongs to the visited-list launch (which sets dyn_by_list)
+  if (a.vslot && !a.dyn_by_list && a.vslot[g - a.g0] != JB_VIS_NONE) return;
+  const uint32_t bi = a.dyn_by_list ? gi_ : g - a.g0;  // which bin holds the group's dynamic members
   const int L = a.L, V = (VM > 1) ? a.V : 1;
   const uint32_t bin_cap = a.dyn_cnt ? a.bin_cap : 0u;
   unsigned char* base = smem_raw + (size_t)gs * jb_grp_smem_bytes(L, V, bin_cap, WPG);
@@ -189,8 +187,8 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
   if (tg == 0) {
     jb_prefetch_l2(a.grp_info + g);
     if (a.dyn_cnt) {
-      jb_prefetch_l2(a.dyn_cnt + a.dyn_bin_base + (g - a.g0));
-      jb_prefetch_l2(a.dyn_bin + (size_t)(g - a.g0) * bin_cap);
+      jb_prefetch_l2(a.dyn_cnt + a.dyn_bin_base + bi);
+      jb_prefetch_l2(a.dyn_bin + (size_t)bi * bin_cap);
     }
   }
   const bool any_static = (a.static_acts & a.sp->activity_mask) != 0u;
@@ -199,11 +197,11 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
   if (a.dyn_cnt) {
     // stage this group's bin and sort it: members arrive in arbitrary (atomic) order, the
     // reference order is (subgroup, person) -- bitonic sort in shared memory
-    nd = min(a.dyn_cnt[a.dyn_bin_base + (g - a.g0)], bin_cap);
+    nd = min(a.dyn_cnt[a.dyn_bin_base + bi], bin_cap);
     if (nd) {
       uint32_t npad = 32;
       while (npad < nd) npad <<= 1;
-      const uint32_t* src = a.dyn_bin + (size_t)(g - a.g0) * bin_cap;  // dyn_bin = the supergroup's first bin
+      const uint32_t* src = a.dyn_bin + (size_t)bi * bin_cap;  // dyn_bin = the supergroup's first bin
       for (uint32_t i = tg; i < npad; i += GT) dyn_s[i] = i < nd ? src[i] : 0xFFFFFFFFu;
       jb_grp_sync<WPG>();
       for (uint32_t k = 2; k <= npad; k <<= 1)
@@ -330,7 +328,9 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
     __syncthreads();
   }
   const uint32_t gi = a.grp_info[g];
-  const double beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
+  // (a household that is being visited takes the "household_visits" rule, household.py:279-289)
+  const uint32_t rule = a.beta_rule ? (uint32_t)a.beta_rule - 1u : JB_GINFO_BETA(gi);
+  const double beta = a.beta[rule * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
   const double dt = a.sp->dt;
   for (int i = tg; i < Lg; i += GT) {
     for (int v = 0; v < V; ++v) {
@@ -432,6 +432,26 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
     }
   }
   if (tg == 0) atomicAdd(&a.counters[CNT_DRAWS], nsus);
+}
+
+// EV: record infection events (who infected whom, JB_STEP_RECORD_EVENTS).  A separate
+// instantiation, so that the rare blame path costs the common launch neither registers nor stack.
+template <int VM, int WPG, bool EV>
+__global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ GroupArgs a) {
+  jb_stamp(3); jb_stamp(4);
+  constexpr int GPC = JB_CTA_WARPS / WPG;      // groups per CTA
+  const uint32_t gs = (threadIdx.x >> 5) / WPG;
+  if (!a.n_list_dev) {
+    const uint32_t gi_ = blockIdx.x * GPC + gs;
+    if (gi_ < a.n_list) jb_group_one<VM, WPG, EV>(a, gi_);  // uniform over the group's threads
+    return;
+  }
+  // the list's length lives on the device (households being visited in this step): a fixed grid walks it
+  const uint32_t n = min(*a.n_list_dev, a.n_list);
+  for (uint32_t gi_ = blockIdx.x * GPC + gs; gi_ < n; gi_ += gridDim.x * GPC) {
+    jb_group_one<VM, WPG, EV>(a, gi_);
+    jb_grp_sync<WPG>();  // the group's shared memory is reused
+  }
 }
 
 // ---- tile kernel ----------------------------------------------------------------------------
@@ -585,6 +605,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
         const uint32_t nsus = __popc(gmask & sus32);
         if (!nsus) continue;  // must_timestep needs a susceptible too (interactive.py:136)
         const uint32_t g = tg0 + __popc(below) - 1u;
+        if (a.vslot && a.vslot[g - a.g0] != JB_VIS_NONE) continue;  // being visited: the visited-list launch has it
         if (a.mode == 1) { a.draw_cnt[g] = nsus; continue; }
         draws += nsus;
         const uint32_t pos = atomicAdd(&s_n, 1u);

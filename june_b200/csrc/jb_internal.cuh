@@ -29,6 +29,8 @@ enum {
   CNT_ICU,
   CNT_ACT0,            // persons placed per activity (5 words: JB_ACT_MEDICAL..JB_ACT_RESIDENCE)
   CNT_ACT4 = CNT_ACT0 + 4,
+  CNT_VIS_LIST,        // residence visits: people who chose a leisure destination this step (deferred placement)
+  CNT_VIS_N,           // households being visited this step
   CNT_N                // followed by summary[R][JB_N_SUMMARY], then dyn_cnt[n_bins]
 };
 
@@ -115,6 +117,31 @@ struct PolicyDev {
   uint32_t n, pad_;
   JbIndividualPolicy pol[JB_MAX_POLICIES];
   double rc[JB_MAX_REGIONS_POLICY];
+};
+
+// Residence visits on the device (jb_set_visits).  A step with visits places its leisure-goers in three moves:
+// everybody draws a destination (k_place, nothing is scattered yet), the order-dependent part of the reference --
+// "a household that is being visited keeps its residents home; the people are walked in world order" -- is resolved
+// by a fixed-point iteration over the (few) people who drew one, then they are scattered or sent home.
+#define JB_VIS_NONE 0xFFFFFFFFu
+#define JB_VIS_DONE (1u << 27)  // `choice`: lsg << 28 | DONE | group (group indices stay below 2^27)
+#define JB_VIS_BIN 32          // visitors per household and step (= the smallest bin the group kernel sorts)
+#define JB_VIS_ITERATIONS 8    // chains "my household is visited by somebody whose household is visited by ..." longer
+                               // than this do not occur (each link has a probability of a few per cent)
+struct VisitsDev {
+  int32_t activity = -1;       // index among the leisure activities, -1 = no visits
+  uint32_t hh_first, hh_count; // groups of the households supergroup
+  uint32_t ch_first, ch_count; // groups of the care-home supergroup (count 0: none)
+  uint32_t ch_lsg;
+  const uint32_t *hh_off, *hh, *ch_off, *ch;
+  double p_household;          // P(household | the person's household is linked to both kinds)
+  const int32_t* pres_group;   // residence group of every resident
+  uint32_t* choice;            // [N] this step's leisure destination (lsg << 28 | group) or JB_VIS_NONE
+  uint32_t* list;              // [N] the people with a destination (count: CNT_VIS_LIST)
+  uint32_t* hv[3];             // [households] smallest caller's index of an EXECUTED visitor (rotating buffers)
+  uint32_t* vslot;             // [households] index in the visited list, or JB_VIS_NONE
+  uint32_t *vis_group, *vis_cnt, *vis_bin;  // visited list: group, visitors, their (lsg << 28 | caller's index)
+  uint32_t vis_cap;
 };
 
 // Vaccines and campaigns on the device (jb_set_vaccination); efficacy tables as device pointers.
@@ -228,6 +255,13 @@ struct GroupArgs {
   const uint8_t* marr;
   const uint32_t* mgid;      // [mirror slots] global person id of the slot's member (the Philox counter word)
   const uint32_t* list_slot;
+  // residence visits: groups with a slot in `vslot` (indexed by group - g0) are left to the visited-list launch;
+  // that launch takes its groups from `group_list` with the count on the device, the visitors of list entry i from
+  // dyn_bin[i * bin_cap ...] / dyn_cnt[i], and the beta rule `beta_rule - 1` instead of the group's own
+  const uint32_t* vslot;
+  const uint32_t* n_list_dev;
+  int dyn_by_list;
+  int beta_rule;
   const uint4* span_items;   // k_span work items (jb_pack_span): {first slot, kind | count, first ordinal, 0}
   const uint32_t* span_group; // groups of the supergroup in slot order
   uint32_t n_span;
@@ -376,6 +410,8 @@ struct JbWorld {
   uint32_t sg_bin_cap[JB_MAX_SUPERGROUPS] = {};    // entries per bin
   DynRanges dyn_ranges = {};
   // leisure
+  VisitsDev vz = {};
+  int visits_beta = 0, visits_sg = -1;     // beta rule of a visited household; the households' supergroup
   LeisureDev lz = {};
   uint32_t *lz_parea = nullptr, *lz_off = nullptr, *lz_venue = nullptr;
   double *lz_does = nullptr, *lz_cum = nullptr;

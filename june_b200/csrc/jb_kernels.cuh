@@ -72,6 +72,8 @@ struct PlaceArgs {
   uint8_t* mstate; uint8_t* mstep; uint8_t* pmir; const uint32_t* pmslot;
   const uint32_t* grp_info;  // region of a hospital
   uint32_t* summary;         // [R][JB_N_SUMMARY]: ward / intensive-care patients placed, by the hospital's region
+  VisitsDev vz;              // residence visits (activity < 0: none)
+  int vis_defer;             // this step resolves visits: leisure destinations are recorded, not scattered
 };
 
 // Uniform number j of policy k for person p in this step (or the injected one, test mode).
@@ -252,15 +254,23 @@ __device__ __noinline__ int32_t jb_commute_transport(const PlaceArgs& a, uint32_
   return (int32_t)c.st[o + (j < n ? j : n - 1)];
 }
 
+// Household._get_leisure_subgroup_for_person (household.py:110-123): the subgroup a visitor joins.
+__device__ __forceinline__ uint32_t jb_visitor_subgroup(uint32_t age) { return age < 18u ? 0u : age <= 25u ? 1u : age < 65u ? 2u : 3u; }
+
 // Leisure.get_subgroup_for_person_and_housemates (leisure.py:230-275) for social venues: does the
 // person go out, which activity, which of its area's candidate venues
 // (social_venue_distributor.py:257-266).  Returns the venue group (and its subgroup) or -1.
 __device__ __noinline__ int32_t jb_leisure_venue(const PlaceArgs& a, uint32_t p, uint32_t& lsg) {
   const LeisureDev& z = a.lz;
   if (a.ch[p]) return -1;  // care-home residents stay (leisure.py:246-248)
+  const VisitsDev& vz = a.vz;
   if (z.inject) {
     const int32_t g = z.inject[p];
     if (g < 0) return -1;
+    if (vz.activity >= 0) {  // a residence visit: household (subgroup by age, household.py:110-123) or care home
+      if ((uint32_t)g - vz.hh_first < vz.hh_count) { lsg = jb_visitor_subgroup(a.age[p]); return g; }
+      if ((uint32_t)g - vz.ch_first < vz.ch_count) { lsg = vz.ch_lsg; return g; }
+    }
     for (uint32_t k = 0; k < z.K; ++k)
       if ((uint32_t)g - z.sg_first[k] < z.sg_count[k]) { lsg = (uint32_t)z.lsg[k]; return g; }
     return -1;
@@ -276,6 +286,23 @@ __device__ __noinline__ int32_t jb_leisure_venue(const PlaceArgs& a, uint32_t p,
   const double* cum = z.cum + row * K;
   uint32_t k = 0;
   while (k + 1 < K && !(u_act < cum[k])) ++k;
+  if ((int32_t)k == vz.activity) {
+    // ResidenceVisitsDistributor.get_leisure_group (residence_visits.py:297-331): the kinds of residence the person's
+    // household is linked to, one of them by residence_type_probabilities, one of its candidates uniformly
+    const uint32_t h = (uint32_t)vz.pres_group[p] - vz.hh_first;
+    if (h >= vz.hh_count) return -1;
+    const uint32_t n_hh = vz.hh_off[h + 1] - vz.hh_off[h];
+    const uint32_t n_ch = vz.ch_off ? vz.ch_off[h + 1] - vz.ch_off[h] : 0u;
+    if (!n_hh && !n_ch) return -1;
+    const JbPhilox4 rv = jb_philox4x32_10(gid, a.sp->step, JB_STREAM_LEISURE, 1u, (uint32_t)a.sp->seed, (uint32_t)(a.sp->seed >> 32));
+    const bool to_ch = !n_hh || (n_ch && !(jb_u52(rv.x[2], rv.x[3]) < vz.p_household));
+    const uint32_t nc = to_ch ? n_ch : n_hh;
+    uint32_t j = (uint32_t)(jb_u52(rv.x[0], rv.x[1]) * (double)nc);
+    if (j >= nc) j = nc - 1;
+    if (to_ch) { lsg = vz.ch_lsg; return (int32_t)vz.ch[vz.ch_off[h] + j]; }
+    lsg = jb_visitor_subgroup(a.age[p]);
+    return (int32_t)vz.hh[vz.hh_off[h] + j];
+  }
   const uint32_t o = z.off[(size_t)z.parea[p] * K + k], n = z.off[(size_t)z.parea[p] * K + k + 1] - o;
   if (n == 0) return -1;  // get_leisure_group returns None: the person falls through to residence
   const JbPhilox4 r1 = jb_philox4x32_10(gid, a.sp->step, JB_STREAM_LEISURE, 1u, (uint32_t)a.sp->seed, (uint32_t)(a.sp->seed >> 32));
@@ -349,7 +376,18 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
       act &= 0x7Fu;
       uint32_t lsg = 0;
       const int32_t g = jb_leisure_venue(a, p, lsg);
-      if (g >= 0) { act = JB_ACT_LEISURE; jb_dyn_scatter(a, (uint32_t)g, lsg, p); }
+      if (g >= 0) {
+        act = JB_ACT_LEISURE;
+        if (!a.vis_defer) {
+          jb_dyn_scatter(a, (uint32_t)g, lsg, p);
+        } else {
+          // residence visits: whether the person really goes depends on who visits whom -- remember the destination,
+          // and tell a household it is being visited (by the caller's index of the visitor: world order)
+          a.vz.choice[p] = (lsg << 28) | (uint32_t)g;
+          a.vz.list[atomicAdd(&a.counters[CNT_VIS_LIST], 1u)] = p;
+          if ((uint32_t)g - a.vz.hh_first < a.vz.hh_count) atomicMin(&a.vz.hv[0][(uint32_t)g - a.vz.hh_first], a.int2ext[p]);
+        }
+      }
     }
     if (act == 15u) { ++noact; act = JB_ACT_NONE; }
     cnt += 1ull << (8 * act);
@@ -470,6 +508,90 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
   if ((threadIdx.x & 31) == 0 && noact) atomicAdd(&a.counters[CNT_NOACT], noact);
   __syncthreads();
   if (threadIdx.x < JB_N_ACT && s_cnt[threadIdx.x]) atomicAdd(&a.counters[CNT_ACT0 + threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// ---- residence visits: who really goes (household.py:124-149,202-205; activity_manager.py:275-292,380-383) ------------
+// The reference walks the people in world order.  A person whose household has ALREADY received a visitor when its turn
+// comes stays home without drawing a leisure activity ("not executed"); a visitor who chose household t marks t as being
+// visited (its residents who are out doing leisure come back, the ones still to come stay).  With one Philox stream per
+// person every draw is a function of (person, step), so the only order-dependent fact is which draws are executed:
+//     executed(i) = no executed visitor k < i chose i's household.
+// k_place has recorded every destination and, per household, the smallest index of ANY visitor (hv[0]); each pass below
+// recomputes the minima over the visitors that are executed according to the previous pass.  A person's status is final
+// after as many passes as its chain of "visited by somebody who is visited by ..." is long.
+__global__ void __launch_bounds__(256) k_visit_iter(const __grid_constant__ VisitsDev z, const uint32_t* __restrict__ counters,
+                                                    const uint32_t* __restrict__ int2ext, int src, int dst, int clr) {
+  const uint32_t n = counters[CNT_VIS_LIST];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = z.list[i];
+    const uint32_t t = (z.choice[p] & 0x07FFFFFFu) - z.hh_first;
+    if (t >= z.hh_count) continue;  // a venue or a care home: nobody is kept home by it
+    z.hv[clr][t] = JB_VIS_NONE;     // the buffer the NEXT pass accumulates into
+    const uint32_t ext = int2ext[p];
+    const uint32_t h = (uint32_t)z.pres_group[p] - z.hh_first;
+    if (h >= z.hh_count || !(z.hv[src][h] < ext)) atomicMin(&z.hv[dst][t], ext);
+  }
+}
+
+// Everybody with a destination is placed: home if its household is being visited (whether it was kept from drawing or
+// fetched back), else into the bin of its venue / care home, or -- visitors of a household -- left for k_visit_scatter.
+// The first executed visitor of a household opens its entry in the visited list.
+__global__ void __launch_bounds__(256) k_visit_final(const __grid_constant__ PlaceArgs a, int fin) {
+  const VisitsDev& z = a.vz;
+  const uint32_t n = a.counters[CNT_VIS_LIST];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = z.list[i];
+    const uint32_t c = z.choice[p], g = c & 0x07FFFFFFu, lsg = c >> 28;
+    const uint32_t ext = a.int2ext[p];
+    const uint32_t h = (uint32_t)z.pres_group[p] - z.hh_first, t = g - z.hh_first;
+    const uint32_t first_home = h < z.hh_count ? z.hv[fin][h] : JB_VIS_NONE;
+    const bool executed = !(first_home < ext);
+    if (t < z.hh_count && executed && z.hv[fin][t] == ext) {  // Household.being_visited = True
+      const uint32_t v = atomicAdd(&a.counters[CNT_VIS_N], 1u);
+      if (v < z.vis_cap) { z.vis_group[v] = g; z.vslot[t] = v; }
+      else atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+    }
+    if (first_home == JB_VIS_NONE) {  // goes
+      if (t >= z.hh_count) { jb_dyn_scatter(a, g, lsg, p); z.choice[p] = c | JB_VIS_DONE; }
+    } else {                          // stays / comes back home
+      a.phot[p] = (uint8_t)((a.phot[p] & ~JB_PS_ACT_MASK) | JB_ACT_RESIDENCE);
+      atomicSub(&a.counters[CNT_ACT0 + JB_ACT_LEISURE], 1u);
+      atomicAdd(&a.counters[CNT_ACT0 + JB_ACT_RESIDENCE], 1u);
+      z.choice[p] = c | JB_VIS_DONE;
+    }
+  }
+}
+
+// Visitors of households join the visited household's entry: (subgroup << 28 | caller's index), sorted by the group kernel.
+__global__ void __launch_bounds__(256) k_visit_scatter(const __grid_constant__ VisitsDev z, uint32_t* __restrict__ counters,
+                                                       const uint32_t* __restrict__ int2ext) {
+  const uint32_t n = counters[CNT_VIS_LIST];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = z.list[i], c = z.choice[p];
+    if (c & JB_VIS_DONE) continue;  // placed already (home, venue or care home)
+    const uint32_t v = z.vslot[(c & 0x07FFFFFFu) - z.hh_first];
+    if (v == JB_VIS_NONE) continue;  // (visited list full: already reported)
+    const uint32_t k = atomicAdd(&z.vis_cnt[v], 1u);
+    if (k < JB_VIS_BIN) z.vis_bin[(size_t)v * JB_VIS_BIN + k] = (c & 0xF0000000u) | int2ext[p];
+    else atomicAdd(&counters[CNT_OVERFLOW], 1u);
+  }
+}
+
+// End of the step: everything the step's visitors touched goes back to "nobody" (no full-array clears per step).
+__global__ void __launch_bounds__(256) k_visit_cleanup(const __grid_constant__ VisitsDev z, const uint32_t* __restrict__ counters) {
+  const uint32_t n = counters[CNT_VIS_LIST], nv = min(counters[CNT_VIS_N], z.vis_cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < max(n, nv); i += gridDim.x * blockDim.x) {
+    if (i < nv) {
+      z.vis_cnt[i] = 0u;
+      z.vslot[z.vis_group[i] - z.hh_first] = JB_VIS_NONE;
+    }
+    if (i < n) {
+      const uint32_t p = z.list[i];
+      const uint32_t t = (z.choice[p] & 0x07FFFFFFu) - z.hh_first;
+      if (t < z.hh_count) z.hv[0][t] = z.hv[1][t] = z.hv[2][t] = JB_VIS_NONE;
+      z.choice[p] = JB_VIS_NONE;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -448,6 +448,9 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (double* q : w->vacc_tables) cudaFree(q);
+  for (void* q : {(void*)w->vz.hh_off, (void*)w->vz.hh, (void*)w->vz.ch_off, (void*)w->vz.ch, (void*)w->vz.choice, (void*)w->vz.list,
+                  (void*)w->vz.hv[0], (void*)w->vz.vslot, (void*)w->vz.vis_group, (void*)w->vz.vis_cnt, (void*)w->vz.vis_bin})
+    if (q) cudaFree(q);
   for (void* q : w->p2p_opened) cudaIpcCloseMemHandle(q);
   if (w->p2p_window) cudaFree(w->p2p_window);
   if (w->flush_buf) cudaFree(w->flush_buf);
@@ -630,10 +633,11 @@ extern "C" int jb_set_leisure(JbWorld* w, const JbLeisureDesc* d) {
   LeisureDev& z = w->lz;
   const uint32_t K = d->n_activities;
   for (uint32_t k = 0; k < K; ++k) {
-    REQUIRE(d->supergroup[k] >= 0 && (size_t)d->supergroup[k] < w->sgs.size() && w->sgs[d->supergroup[k]].has_dynamic,
-            "leisure supergroup must exist and have dynamic members");
+    REQUIRE(d->supergroup[k] < 0 || ((size_t)d->supergroup[k] < w->sgs.size() && w->sgs[d->supergroup[k]].has_dynamic),
+            "leisure supergroup must exist and have dynamic members");  // (-1: no venues -- residence visits, jb_set_visits)
     REQUIRE(d->subgroup[k] >= 0 && d->subgroup[k] < 16, "leisure subgroup out of range");
-    z.sg_first[k] = w->sgs[d->supergroup[k]].first_group; z.sg_count[k] = w->sgs[d->supergroup[k]].n_groups;
+    z.sg_first[k] = d->supergroup[k] < 0 ? 0u : w->sgs[d->supergroup[k]].first_group;
+    z.sg_count[k] = d->supergroup[k] < 0 ? 0u : w->sgs[d->supergroup[k]].n_groups;
     z.lsg[k] = d->subgroup[k];
   }
   const size_t n_off = (size_t)d->n_areas * K + 1;
@@ -649,6 +653,85 @@ extern "C" int jb_set_leisure(JbWorld* w, const JbLeisureDesc* d) {
   TRY(dev_upload(&w->lz_venue, d->area_venue, (size_t)d->area_off[n_off - 1], w->stream));
   CK(cudaStreamSynchronize(w->stream));
   z.K = K; z.parea = w->lz_parea; z.off = w->lz_off; z.venue = w->lz_venue;
+  return JB_OK;
+}
+
+static int ensure_res_group(JbWorld* w) {
+  if (w->pres_group) return JB_OK;
+  TRY(dev_alloc(&w->pres_group, w->NP));
+  CK(cudaMemsetAsync(w->pres_group, 0xFF, (size_t)w->NP * 4, w->stream));
+  k_res_group<<<(w->G + 255) / 256, 256, 0, w->stream>>>(w->grp_off, w->reg_member, w->reg_info, w->G, w->N, w->pres_group);
+  KCHECK("k_res_group", w->stream);
+  return JB_OK;
+}
+
+extern "C" int jb_set_visits(JbWorld* w, const JbVisitsDesc* d) {
+  if (!w || !d) { jb_set_error("null argument"); return JB_EINVAL; }
+  REQUIRE(w->lz.K != 0, "jb_set_visits before jb_set_leisure");
+  REQUIRE(d->activity >= 0 && (uint32_t)d->activity < w->lz.K && d->household_supergroup >= 0 &&
+          (size_t)d->household_supergroup < w->sgs.size() && d->household_off && d->household_target, "jb_set_visits: bad argument");
+  REQUIRE(d->care_home_supergroup < 0 || ((size_t)d->care_home_supergroup < w->sgs.size() && w->sgs[d->care_home_supergroup].has_dynamic),
+          "care-home visits need a care-home supergroup with dynamic members");
+  REQUIRE(d->household_visits_beta >= 0 && (uint32_t)d->household_visits_beta < w->n_beta, "household_visits_beta out of range");
+  REQUIRE(d->p_household + d->p_care_home > 0.0, "residence_type_probabilities must not both be zero");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);
+  const JbSupergroup& hs = w->sgs[d->household_supergroup];
+  REQUIRE(w->sg_L[d->household_supergroup] >= 4, "the household supergroup needs the four age subgroups");
+  VisitsDev& z = w->vz;
+  for (void* q : {(void*)z.hh_off, (void*)z.hh, (void*)z.ch_off, (void*)z.ch, (void*)z.choice, (void*)z.list, (void*)z.hv[0], (void*)z.vslot,
+                  (void*)z.vis_group, (void*)z.vis_cnt, (void*)z.vis_bin})
+    if (q) cudaFree(q);
+  z = VisitsDev();
+  const uint32_t nh = hs.n_groups;
+  for (uint32_t i = 0; i < d->household_off[nh]; ++i)
+    REQUIRE(d->household_target[i] - hs.first_group < nh, "household_target outside the household supergroup");
+  z.activity = d->activity; z.hh_first = hs.first_group; z.hh_count = nh;
+  uint32_t *p1 = nullptr, *p2 = nullptr;
+  TRY(dev_upload(&p1, d->household_off, (size_t)nh + 1, w->stream));
+  TRY(dev_upload(&p2, d->household_target, std::max<size_t>(1, d->household_off[nh]), w->stream));
+  z.hh_off = p1; z.hh = p2;
+  if (d->care_home_supergroup >= 0 && d->care_home_off) {
+    const JbSupergroup& cs = w->sgs[d->care_home_supergroup];
+    for (uint32_t i = 0; i < d->care_home_off[nh]; ++i)
+      REQUIRE(d->care_home_target[i] - cs.first_group < cs.n_groups, "care_home_target outside the care-home supergroup");
+    z.ch_first = cs.first_group; z.ch_count = cs.n_groups; z.ch_lsg = (uint32_t)d->care_home_subgroup;
+    uint32_t *p3 = nullptr, *p4 = nullptr;
+    TRY(dev_upload(&p3, d->care_home_off, (size_t)nh + 1, w->stream));
+    TRY(dev_upload(&p4, d->care_home_target, std::max<size_t>(1, d->care_home_off[nh]), w->stream));
+    z.ch_off = p3; z.ch = p4;
+  }
+  z.p_household = d->p_household / (d->p_household + d->p_care_home);
+  TRY(ensure_res_group(w));
+  z.pres_group = w->pres_group;
+  TRY(dev_alloc(&z.choice, std::max(1u, w->N)));
+  TRY(dev_alloc(&z.list, std::max(1u, w->N)));
+  TRY(dev_alloc(&z.hv[0], (size_t)3 * nh));
+  z.hv[1] = z.hv[0] + nh; z.hv[2] = z.hv[1] + nh;
+  TRY(dev_alloc(&z.vslot, nh));
+  z.vis_cap = std::max(1u, nh);  // on a weekend afternoon a quarter of the households and more receive somebody
+  TRY(dev_alloc(&z.vis_group, z.vis_cap));
+  TRY(dev_alloc(&z.vis_cnt, z.vis_cap));
+  TRY(dev_alloc(&z.vis_bin, (size_t)z.vis_cap * JB_VIS_BIN));
+  CK(cudaMemsetAsync(z.choice, 0xFF, (size_t)std::max(1u, w->N) * 4, w->stream));
+  CK(cudaMemsetAsync(z.hv[0], 0xFF, (size_t)3 * nh * 4, w->stream));
+  CK(cudaMemsetAsync(z.vslot, 0xFF, (size_t)nh * 4, w->stream));
+  CK(cudaMemsetAsync(z.vis_cnt, 0, (size_t)z.vis_cap * 4, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  w->visits_beta = d->household_visits_beta;
+  w->visits_sg = d->household_supergroup;
+  return JB_OK;
+}
+
+extern "C" int jb_set_visit_probabilities(JbWorld* w, double p_household, double p_care_home) {
+  if (!w) { jb_set_error("null world"); return JB_EINVAL; }
+  REQUIRE(w->vz.hh_off != nullptr, "jb_set_visit_probabilities before jb_set_visits");
+  REQUIRE(p_household + p_care_home > 0.0, "residence_type_probabilities must not both be zero");
+  CK(cudaSetDevice(w->device));
+  CK(cudaStreamSynchronize(w->stream));
+  drop_graphs(w);  // (the value is a kernel argument of the captured placement)
+  w->vz.p_household = p_household / (p_household + p_care_home);
   return JB_OK;
 }
 
@@ -1268,6 +1351,14 @@ static inline bool policies_decide_per_person(const JbWorld* w, uint32_t activit
   return w->n_pol != 0 && !w->pol_subject_mode && (activity_mask & ~stay & ((1u << JB_N_ACT) - 1u)) != 0u;
 }
 
+// Does this step draw leisure activities with residence visits among them?  Then the leisure-goers are placed in three
+// moves (k_place records the destinations, k_visit_* resolve who is kept home, the rest are scattered).
+static inline bool visits_step(const JbWorld* w) {
+  const JbStepParams& p = w->cur;
+  return w->vz.activity >= 0 && w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE)) &&
+         (p.activity_mask & (1u << JB_ACT_LEISURE)) != 0u;
+}
+
 // Does this step place people one by one (individual policies, leisure or commute draws)?  Then the mirrored
 // supergroups read the per-step copy the placement writes instead of the persistent mirror.
 static inline bool step_places_per_person(const JbWorld* w) {
@@ -1293,6 +1384,8 @@ static int launch_groups(JbWorld* w, int mode) {
     const SgTiles& T = w->tiles[k];
     const bool multi = w->V > 1;
     if (T.mode == 3) { a.marr = step_places_per_person(w) ? w->mstep : w->mstate; a.stream_base = T.stream_base; }
+    const bool visited_here = (int)k == w->visits_sg && visits_step(w);
+    if (visited_here) a.vslot = w->vz.vslot;  // households that are being visited are left to the visited-list launch
     for (int u = 0; u < 3; ++u) {
       if ((u == 0 && !T.n_span && (T.mode == 0 || T.n_tiles == 0 || !T.has_small)) || (u == 1 && T.n_w == 0) || (u == 2 && T.n_c == 0)) continue;
       static const int unit_streams = jb_env_flag("JB_UNIT_STREAMS", 1);
@@ -1321,6 +1414,30 @@ static int launch_groups(JbWorld* w, int mode) {
       if (!w->serial) {
         CK(cudaEventRecord(w->ev_join[k][u], st));
         CK(cudaStreamWaitEvent(w->stream, w->ev_join[k][u], 0));
+      }
+    }
+    if (visited_here) {
+      // the households being visited in this step, their visitors as dynamic members, beta rule "household_visits":
+      // one warp per household, the list's length is on the device
+      GroupArgs v = make_group_args(w, sg, w->sg_L[k]);
+      v.mode = mode;
+      v.group_list = w->vz.vis_group; v.n_list = w->vz.vis_cap; v.n_list_dev = w->counters + CNT_VIS_N;
+      v.dyn_cnt = w->vz.vis_cnt; v.dyn_bin = w->vz.vis_bin; v.bin_cap = JB_VIS_BIN; v.dyn_bin_base = 0; v.dyn_by_list = 1;
+      v.beta_rule = w->visits_beta + 1;
+      cudaStream_t st = w->serial ? w->stream : w->side[k][1];
+      if (!w->serial) CK(cudaStreamWaitEvent(st, w->ev_fork, 0));
+      {
+        constexpr int gpc = JB_CTA_WARPS;
+        const size_t smem = jb_grp_smem_bytes(v.L, (int)w->V, v.bin_cap, 1) * gpc;
+        const unsigned blocks = std::min<unsigned>((w->vz.vis_cap + gpc - 1) / gpc, 148u * 16u);
+        if (!multi) { if (v.ev_group) k_groups<1, 1, true><<<blocks, JB_CTA, smem, st>>>(v); else k_groups<1, 1, false><<<blocks, JB_CTA, smem, st>>>(v); }
+        else { if (v.ev_group) k_groups<JB_MAX_VARIANTS, 1, true><<<blocks, JB_CTA, smem, st>>>(v); else k_groups<JB_MAX_VARIANTS, 1, false><<<blocks, JB_CTA, smem, st>>>(v); }
+        KCHECK("k_groups<visited households>", st);
+      }
+      w->launches++;
+      if (!w->serial) {
+        CK(cudaEventRecord(w->ev_join[k][1], st));
+        CK(cudaStreamWaitEvent(w->stream, w->ev_join[k][1], 0));
       }
     }
     CK(cudaGetLastError());
@@ -1425,9 +1542,10 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
     pa.pol_inject = (p.flags & JB_STEP_INJECT_POLICY) ? w->pol_inject : nullptr;
     pa.severe_mask = w->dis_host.severe_mask;
     pa.grp_info = w->grp_info; pa.summary = w->summary;
+    pa.vz = w->vz; pa.vis_defer = visits_step(w) ? 1 : 0;
     const uint32_t chunks = (w->N + 15) / 16;
     const bool pol_now = policies_decide_per_person(w, p.activity_mask);
-    if (!pol_now) { pa.pol = nullptr; pa.n_pol = 0; }
+    if (!pol_now && !w->pol_subject_mode) { pa.pol = nullptr; pa.n_pol = 0; }  // (the subject list is re-evaluated by k_place_subjects)
     const bool full = pol_now || (w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE))) ||
                       pa.cmt.person != nullptr || pa.cmt.inject != nullptr;
     if (full != step_places_per_person(w)) { jb_set_error("internal: placement flavour mismatch"); return JB_EINVAL; }
@@ -1444,6 +1562,21 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
       k_place_subjects<<<(w->n_pol_subjects + 255) / 256, 256, 0, s>>>(pa, w->pol_subjects, w->n_pol_subjects);
       KCHECK("k_place_subjects", s);
       w->launches++;
+    }
+    if (pa.vis_defer) {
+      if (!full) { jb_set_error("internal: residence visits need the per-person placement"); return JB_EINVAL; }
+      // who is kept home by a visitor: JB_VIS_ITERATIONS passes over the people who drew a destination (buffers rotate:
+      // pass k reads k - 1 mod 3, accumulates into k mod 3, clears k + 1 mod 3), then everybody is placed
+      const unsigned vb = 148 * 4;
+      for (int k = 1; k <= JB_VIS_ITERATIONS; ++k) {
+        k_visit_iter<<<vb, 256, 0, s>>>(w->vz, w->counters, w->int2ext, (k - 1) % 3, k % 3, (k + 1) % 3);
+        KCHECK("k_visit_iter", s);
+      }
+      k_visit_final<<<vb, 256, 0, s>>>(pa, JB_VIS_ITERATIONS % 3);
+      KCHECK("k_visit_final", s);
+      k_visit_scatter<<<vb, 256, 0, s>>>(w->vz, w->counters, w->int2ext);
+      KCHECK("k_visit_scatter", s);
+      w->launches += JB_VIS_ITERATIONS + 2;
     }
   }
   if (w->p2p_on && halo_step(w)) {
@@ -1618,6 +1751,11 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
     }
   }
   if (!fused_finish(w)) TRY(launch_health(w, s));
+  if (visits_step(w)) {
+    k_visit_cleanup<<<148 * 4, 256, 0, s>>>(w->vz, w->counters);
+    KCHECK("k_visit_cleanup", s);
+    w->launches++;
+  }
   k_step_end<<<1, 256, 0, s>>>(w->counters, (uint32_t)(CNT_N + (size_t)w->R * JB_N_SUMMARY), w->d_h_counters);
   KCHECK("k_step_end", s);
   w->launches++;
@@ -1695,10 +1833,7 @@ static int ensure_event_buffers(JbWorld* w, uint32_t flags) {
   TRY(dev_alloc(&w->hev_person, w->hev_cap));
   TRY(dev_alloc(&w->hev_kind, w->hev_cap));
   TRY(dev_alloc(&w->hev_group, w->hev_cap));
-  TRY(dev_alloc(&w->pres_group, w->NP));
-  CK(cudaMemsetAsync(w->pres_group, 0xFF, (size_t)w->NP * 4, w->stream));
-  k_res_group<<<(w->G + 255) / 256, 256, 0, w->stream>>>(w->grp_off, w->reg_member, w->reg_info, w->G, w->N, w->pres_group);
-  KCHECK("k_res_group", w->stream);
+  TRY(ensure_res_group(w));
   drop_graphs(w);
   return JB_OK;
 }

@@ -16,7 +16,7 @@ from ._lib import (JbVaccine, JbVaccinationCampaign, JbCommuteDesc, JbDisease, J
                    JbSupergroup, JbWorldDesc, SimulatorError, ptr)
 from .disease import DiseaseConfig, health_index_cum
 from .interaction import Interaction
-from .world import KIND_SCHOOL, MAX_STAGES, N_TPAR, SCHOOL_DIM, WorldSoA
+from .world import CARE_HOME_VISITORS_SUBGROUP, KIND_SCHOOL, MAX_STAGES, N_TPAR, SCHOOL_DIM, VISITS_ACTIVITY, VISITS_SUPERGROUP, WorldSoA
 
 
 def fill_disease(dc: DiseaseConfig, hi_cum: np.ndarray) -> JbDisease:
@@ -125,7 +125,7 @@ class Engine:
     def _set_leisure(self, world: WorldSoA):
         names = [sg.name for sg in world.supergroups]
         K = len(world.leisure_activities)
-        sgi = np.array([names.index(n) for n in world.leisure_supergroups], np.int32)
+        sgi = np.array([-1 if n == VISITS_SUPERGROUP else names.index(n) for n in world.leisure_supergroups], np.int32)
         lsg = np.array(world.leisure_subgroups, np.int32)
         pa = np.ascontiguousarray(world.person_area, dtype=np.uint32)
         off = np.ascontiguousarray(world.area_venue_off, dtype=np.uint32)
@@ -136,6 +136,35 @@ class Engine:
         d.supergroup, d.subgroup = sgi.ctypes.data, lsg.ctypes.data
         d.person_area, d.area_off, d.area_venue = pa.ctypes.data, off.ctypes.data, (ven if ven.size else np.zeros(1, np.uint32)).ctypes.data
         self._check(self._f("set_leisure")(self._h, C.byref(d)))
+        if world.has_visits:
+            self._set_visits(world)
+
+    def _set_visits(self, world: WorldSoA, probabilities=(0.66, 0.34)):
+        """Residence visits (``residence_visits.py``): the households' links and ``residence_type_probabilities``
+        (defaults of ``configs/defaults/groups/leisure/visits.yaml``; ``set_visit_probabilities`` changes them)."""
+        names = [sg.name for sg in world.supergroups]
+        spec_of = {sg.spec: i for i, sg in enumerate(world.supergroups)}
+        d = _lib.JbVisitsDesc()
+        d.activity = world.leisure_activities.index(VISITS_ACTIVITY)
+        d.household_supergroup = spec_of["household"]
+        has_ch = world.visit_care_home_off is not None and int(world.visit_care_home_off[-1]) > 0
+        d.care_home_supergroup = spec_of["care_home"] if has_ch else -1
+        d.care_home_subgroup = CARE_HOME_VISITORS_SUBGROUP
+        arrs = [np.ascontiguousarray(world.visit_household_off, np.uint32), np.ascontiguousarray(world.visit_household, np.uint32)]
+        d.household_off, d.household_target = arrs[0].ctypes.data, (arrs[1] if arrs[1].size else np.zeros(1, np.uint32)).ctypes.data
+        if has_ch:
+            arrs += [np.ascontiguousarray(world.visit_care_home_off, np.uint32), np.ascontiguousarray(world.visit_care_home, np.uint32)]
+            d.care_home_off, d.care_home_target = arrs[2].ctypes.data, arrs[3].ctypes.data
+        d.p_household, d.p_care_home = float(probabilities[0]), float(probabilities[1])
+        keys = [r.key for r in world.beta_rules]
+        assert "household_visits" in keys, "a world with residence visits needs the beta rule 'household_visits'"
+        d.household_visits_beta = keys.index("household_visits")
+        assert arrs[0].size == world.supergroups[d.household_supergroup].n_groups + 1
+        self._check(self._f("set_visits")(self._h, C.byref(d)))
+
+    def set_visit_probabilities(self, p_household: float, p_care_home: float):
+        """``ChangeVisitsProbability`` (``leisure_policies.py:180-220``)."""
+        self._check(self._f("set_visit_probabilities")(self._h, float(p_household), float(p_care_home)))
 
     def set_leisure_tables(self, does: np.ndarray, cum: np.ndarray):
         """``does[T][R][2][100]``, ``cum[T][R][2][100][K]`` (see ``june_b200.leisure``)."""

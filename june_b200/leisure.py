@@ -126,6 +126,44 @@ class GymDistributor(SocialVenueDistributor):
     spec, config_key = "gym", "gyms"
 
 
+class ResidenceVisitsDistributor(SocialVenueDistributor):
+    """``ResidenceVisitsDistributor`` (``residence_visits.py:19-50,333-351``): visits between households and to care
+    homes.  No venues: the candidates are the residences the visitor's household is linked to
+    (``WorldSoA.visit_household`` / ``visit_care_home``).  Nobody visits during working hours."""
+
+    spec, config_key = "residence_visits", "visits"
+
+    def __init__(self, residence_type_probabilities: Optional[dict] = None, times_per_week: Optional[dict] = None,
+                 hours_per_day: Optional[dict] = None, daytypes: dict = DEFAULT_DAYTYPES,
+                 drags_household_probability: float = 0.0, invites_friends_probability: float = 0.0, social_venues=None):
+        self.residence_type_probabilities = dict(residence_type_probabilities or {"household": 0.66, "care_home": 0.34})
+        self.policy_reductions: dict = {}   # ChangeVisitsProbability: the probabilities in force while it is active
+        super().__init__(None, times_per_week=times_per_week, daytypes=daytypes, hours_per_day=hours_per_day,
+                         drags_household_probability=drags_household_probability,
+                         invites_friends_probability=invites_friends_probability)
+
+    @classmethod
+    def from_config(cls, social_venues=None, daytypes: dict = DEFAULT_DAYTYPES, config_filename: Optional[str] = None,
+                    config_override: Optional[dict] = None):
+        if config_filename is None:
+            config = dict(load_defaults()["leisure"][cls.config_key])
+        else:
+            with open(config_filename) as f:
+                config = yaml.safe_load(f)
+        config.update({k: v for k, v in (config_override or {}).items() if v is not None})
+        return cls(daytypes=daytypes, **config)
+
+    def get_poisson_parameter(self, sex: str, age: int, day_type: str, working_hours: bool, **kw) -> float:
+        if working_hours:
+            return 0.0
+        return super().get_poisson_parameter(sex=sex, age=age, day_type=day_type, working_hours=working_hours, **kw)
+
+    def type_probabilities(self):
+        """(household, care_home) as ``get_leisure_group`` reads them (``residence_visits.py:305-309``)."""
+        p = self.policy_reductions or self.residence_type_probabilities
+        return float(p.get("household", 0.0)), float(p.get("care_home", 0.0))
+
+
 DISTRIBUTORS = {"pubs": PubDistributor, "cinemas": CinemaDistributor, "groceries": GroceryDistributor,
                 "gyms": GymDistributor}
 
@@ -193,4 +231,6 @@ def generate_leisure_for_world(list_of_leisure_groups: Sequence[str], world, day
         if name in list_of_leisure_groups and name in have:
             d = DISTRIBUTORS[name].from_config(daytypes=daytypes)
             dists[d.spec] = d
+    if ("household_visits" in list_of_leisure_groups or "care_home_visits" in list_of_leisure_groups) and getattr(world, "has_visits", False):
+        dists["residence_visits"] = ResidenceVisitsDistributor.from_config(daytypes=daytypes)  # leisure.py:84-91
     return Leisure(dists, region_names=world.region_names)

@@ -294,7 +294,25 @@ class ChangeLeisureProbability(Policy):
         return self.activity_reductions
 
 
-_CLASSES = {c.__name__: c for c in (CloseLeisureVenue, ChangeLeisureProbability, SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
+class ChangeVisitsProbability(Policy):
+    """``ChangeVisitsProbability`` (``leisure_policies.py:180-220``): while active, the split between visits to
+    households and to care homes (``residence_type_probabilities``) is ``new_residence_type_probabilities``."""
+
+    policy_type = "leisure"
+    policy_subtype = "change_visits_probability"
+
+    def __init__(self, start_time: DateLike = "1900-01-01", end_time: DateLike = "2100-01-01",
+                 new_residence_type_probabilities: Optional[Dict[str, float]] = None):
+        super().__init__(start_time, end_time)
+        self.policy_reductions = dict(new_residence_type_probabilities or {})
+
+    def apply(self, leisure) -> None:
+        dist = leisure.leisure_distributors.get("residence_visits")
+        if dist is not None:
+            dist.policy_reductions = self.policy_reductions
+
+
+_CLASSES = {c.__name__: c for c in (CloseLeisureVenue, ChangeLeisureProbability, ChangeVisitsProbability, SocialDistancing, MaskWearing, RegionalCompliance, TieredLockdown,
                                     SevereSymptomsStayHome, Hospitalisation, Quarantine, Shielding, CloseSchools,
                                     CloseUniversities, CloseCompanies, CloseCompaniesLockdownTiers, LimitLongCommute)}
 
@@ -354,6 +372,8 @@ class Policies:
         probability reductions, then apply the active policies (at most one change of probabilities)."""
         leisure.closed_venues = {r: set() for r in leisure.region_names}
         leisure.policy_reductions = {}
+        if "residence_visits" in getattr(leisure, "leisure_distributors", {}):  # leisure_policies.py:46-48
+            leisure.leisure_distributors["residence_visits"].policy_reductions = {}
         if self.apply_tiered_lockdown:
             # TieredLockdown.apply, ``regional_compliance.py:42-52`` (tier 2's ``update("residence_visits")`` adds the
             # string's letters to the set, i.e. closes nothing)

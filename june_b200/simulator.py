@@ -312,6 +312,14 @@ class Simulator:
                    policies.device_policies(date, ctx), list(comp))
             self._policy_cache[key] = hit
         beta, flags, self.interaction.beta_reductions, records, comp = hit
+        if key != self._policy_key_on_device and self.activity_manager.leisure is not None and getattr(self.world, "has_visits", False):
+            # ChangeVisitsProbability: the split between household and care-home visits in force now
+            leisure = self.activity_manager.leisure
+            policies.apply_leisure_policies(date, leisure)
+            probs = leisure.leisure_distributors["residence_visits"].type_probabilities()
+            if probs != getattr(self, "_visit_probabilities_on_device", None):
+                self.device.set_visit_probabilities(*probs)
+                self._visit_probabilities_on_device = probs
         if key != self._policy_key_on_device:
             # the active set changed (a handful of times per run): refresh the device-resident table
             if records or self._policy_key_on_device is not None:

@@ -80,7 +80,10 @@ def _csr_from_rows(group: np.ndarray, lsg: np.ndarray, member: np.ndarray, act: 
 
 def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int = 0, commute_fraction: float = 0.05,
                     person_id_base: Optional[int] = None, sector_betas: Optional[Dict[str, float]] = None,
-                    leisure: bool = False, commute: bool = False) -> DomainDraft:
+                    leisure: bool = False, commute: bool = False, visits: bool = False) -> DomainDraft:
+    """``visits`` (with ``leisure``): households are linked to 2-4 households of their super area and, one household
+    per care-home resident, to that care home (``residence_visits.py:189-296``); "residence_visits" becomes the last
+    leisure activity."""
     rng = np.random.default_rng([seed, rank, 20200301])
     pmf = age_pmf()
     adult_pmf = pmf.copy()
@@ -350,10 +353,40 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
             grp_sa[g_ven0[i]: g_ven0[i] + nv] = ven_sa
             centre = np.clip((np.arange(n_areas) * nv) // n_areas - ncand // 2, 0, nv - ncand)
             cand.append(g_ven0[i] + centre[:, None] + np.arange(ncand)[None, :])
+        if visits:  # the visits activity has no venues: an empty column of the (area, activity) table
+            cand.append(np.zeros((n_areas, 0), np.int64))
+            K += 1
         counts = np.stack([np.full(n_areas, c.shape[1]) for c in cand], axis=1).ravel()  # (area, activity) order
         area_venue_off = np.zeros(n_areas * K + 1, np.uint32)
         area_venue_off[1:] = np.cumsum(counts)
         area_venue = np.concatenate([np.concatenate([cand[k][a] for k in range(K)]) for a in range(n_areas)]).astype(np.uint32)
+    visit_tables = None
+    if leisure and visits:
+        vrng = np.random.default_rng([seed, rank, 777])
+        # link_households_to_households: every household gets randint(2, 4) households of its super area
+        n_link = vrng.integers(2, 5, n_hh)
+        sa_first = np.searchsorted(sa_of_hh, np.arange(n_sa), side="left")
+        sa_cnt = np.bincount(sa_of_hh, minlength=n_sa)
+        src = np.repeat(np.arange(n_hh), n_link)
+        pick = sa_first[sa_of_hh[src]] + (vrng.random(len(src)) * sa_cnt[sa_of_hh[src]]).astype(np.int64)
+        pick = np.where(pick == src, sa_first[sa_of_hh[src]] + (pick - sa_first[sa_of_hh[src]] + 1) % np.maximum(1, sa_cnt[sa_of_hh[src]]), pick)
+        keep = pick != src
+        vh_off = np.zeros(n_hh + 1, np.uint32)
+        vh_off[1:] = np.cumsum(np.bincount(src[keep], minlength=n_hh))
+        vh = (g_hh0 + pick[keep]).astype(np.uint32)
+        # link_households_to_care_homes: one household of two or more people in the care home's super area per resident
+        big = np.nonzero(sizes >= 2)[0]
+        big_sa = sa_of_hh[big]
+        want_sa = ch_sa[ch_of_res]
+        lo = np.searchsorted(big_sa, want_sa, side="left")
+        hi = np.searchsorted(big_sa, want_sa, side="right")
+        ok = hi > lo
+        chosen = big[(lo[ok] + (vrng.random(int(ok.sum())) * (hi[ok] - lo[ok])).astype(np.int64))]
+        order = np.argsort(chosen, kind="stable")
+        vc_off = np.zeros(n_hh + 1, np.uint32)
+        vc_off[1:] = np.cumsum(np.bincount(chosen, minlength=n_hh))
+        vc = (g_ch0 + ch_of_res[ok][order]).astype(np.uint32)
+        visit_tables = (vh_off, vh, vc_off, vc)
 
     # ---- registrations ----------------------------------------------------------------------------
     add_rows(g_hosp0 + hosp_of_worker, np.zeros(len(hosp_workers)), hosp_workers, ACT_PRIMARY)
@@ -380,7 +413,8 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
     ] + [Supergroup(name, spec, ACT_LEISURE, g_ven0[i], n_venues[i], KIND_MATRIX, 1, LEISURE_BIN_CAP)
          for i, (name, spec, _, _) in enumerate(LEISURE_VENUES if leisure else [])] + [
         Supergroup("households", "household", ACT_RESIDENCE, g_hh0, n_hh, KIND_MATRIX, 0, 0),
-        Supergroup("care_homes", "care_home", ACT_RESIDENCE, g_ch0, n_ch, KIND_MATRIX, 0, 0),
+        # (care homes take visitors as dynamic members when residence visits are on)
+        Supergroup("care_homes", "care_home", ACT_RESIDENCE, g_ch0, n_ch, KIND_MATRIX, 1 if visit_tables else 0, 64 if visit_tables else 0),
     ]
     w = WorldSoA(
         age=age, sex=sex, care_home_resident=ch_res, has_activity=has_activity, super_area=psa,
@@ -417,6 +451,12 @@ def generate_domain(n_people: int, rank: int = 0, world_size: int = 1, seed: int
         w.leisure_activities = [dict((v[0], v[1]) for v in LEISURE_VENUES)[n_] for n_ in LEISURE_ORDER]
         w.leisure_subgroups = [0] * len(LEISURE_ORDER)
         w.area_venue_off, w.area_venue = area_venue_off, area_venue
+        if visit_tables:
+            from .world import VISITS_ACTIVITY, VISITS_SUPERGROUP
+            w.leisure_supergroups.append(VISITS_SUPERGROUP)
+            w.leisure_activities.append(VISITS_ACTIVITY)
+            w.leisure_subgroups.append(0)
+            w.visit_household_off, w.visit_household, w.visit_care_home_off, w.visit_care_home = visit_tables
     w.validate()
     return DomainDraft(world=w, out_person=out_person, company_first=g_comp0, company_count=n_comp,
                        company_size=csize, rank=rank, world_size=world_size, seed=seed)
@@ -484,8 +524,9 @@ def wire_halos_distributed(draft: DomainDraft, dist) -> WorldSoA:
 
 
 def generate_world(n_people: int, seed: int = 0, sector_betas: Optional[Dict[str, float]] = None,
-                   leisure: bool = False, commute: bool = False) -> WorldSoA:
-    """Single-domain world (configs 0/1 of BASELINE.json; ``leisure=True`` adds the venues of config 3)."""
-    d = generate_domain(n_people, 0, 1, seed, sector_betas=sector_betas, leisure=leisure, commute=commute)
+                   leisure: bool = False, commute: bool = False, visits: bool = False) -> WorldSoA:
+    """Single-domain world (configs 0/1 of BASELINE.json; ``leisure=True`` adds the venues of config 3,
+    ``visits=True`` its household and care-home visits)."""
+    d = generate_domain(n_people, 0, 1, seed, sector_betas=sector_betas, leisure=leisure, commute=commute, visits=visits)
     _attach_halo(d, [np.zeros(0, np.uint32)])
     return d.world

@@ -97,6 +97,11 @@ class BetaRule:
         return dict(self.__dict__)
 
 
+VISITS_ACTIVITY = "residence_visits"      # key of the reference's distributor (leisure.py:84-91)
+VISITS_SUPERGROUP = "residence_visits"    # entry of WorldSoA.leisure_supergroups for it (not a supergroup)
+CARE_HOME_VISITORS_SUBGROUP = 2           # CareHome.SubgroupType.visitors (care_home.py)
+
+
 @dataclass
 class WorldSoA:
     # persons
@@ -138,6 +143,13 @@ class WorldSoA:
     leisure_subgroups: List[int] = field(default_factory=list)      # leisure_subgroup_type per activity
     area_venue_off: Optional[np.ndarray] = None   # uint32 [n_areas * K + 1]
     area_venue: Optional[np.ndarray] = None       # uint32 group indices
+    # residence visits (residence_visits.py:189-345): the leisure activity "residence_visits" (supergroup name
+    # VISITS_SUPERGROUP: it has no venues) sends a person to a residence its household is linked to
+    # (Household.residences_to_visit); CSRs over the groups of the households supergroup
+    visit_household_off: Optional[np.ndarray] = None   # uint32 [n_households + 1]
+    visit_household: Optional[np.ndarray] = None       # uint32 group indices (households)
+    visit_care_home_off: Optional[np.ndarray] = None   # uint32 [n_households + 1]
+    visit_care_home: Optional[np.ndarray] = None       # uint32 group indices (care homes)
     # commute (travel.py:125-131): -1 | city << 1 | (station << 1) | 1 per person; city -> stations and
     # station -> transports (groups) as CSRs
     person_commute: Optional[np.ndarray] = None          # int32 [n_people]
@@ -156,6 +168,7 @@ class WorldSoA:
                "grp_offset", "grp_info", "grp_aux", "reg_member", "reg_info", "school_years", "beta_scale",
                "halo_gid", "out_person", "out_counts", "in_counts", "person_ids", "group_ids", "grp_super_area",
                "person_area", "area_venue_off", "area_venue", "person_attr", "person_work_region",
+               "visit_household_off", "visit_household", "visit_care_home_off", "visit_care_home",
                "person_commute", "city_station_off", "city_station", "station_transport_off", "station_transport")
 
     @property
@@ -177,6 +190,10 @@ class WorldSoA:
     @property
     def n_areas(self) -> int:
         return 0 if self.person_area is None or not len(self.person_area) else int(self.person_area.max()) + 1
+
+    @property
+    def has_visits(self) -> bool:
+        return VISITS_ACTIVITY in self.leisure_activities and self.visit_household_off is not None
 
     @property
     def has_leisure(self) -> bool:

@@ -58,7 +58,7 @@ def test_two_probability_changes_at_once_are_rejected_like_in_the_reference():
 def test_default_policy_file_carries_the_leisure_policies():
     pols = Policies.from_file()
     kinds = {type(p).__name__ for p in pols.leisure_policies}
-    assert kinds == {"CloseLeisureVenue", "ChangeLeisureProbability"}
+    assert kinds == {"CloseLeisureVenue", "ChangeLeisureProbability", "ChangeVisitsProbability"}
     assert all(not p.is_active(datetime.datetime(2020, 6, 1)) for p in pols.leisure_policies)  # dated 3020 in the defaults
 
 
