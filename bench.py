@@ -154,9 +154,9 @@ def build_setup(n_people: int, rank: int, world_size: int, dist=None, leisure: b
     defaults = load_defaults()
     sb = defaults["company_sector_betas"]
     if world_size == 1:
-        world = generate_world(n_people, seed=0, sector_betas=sb, leisure=leisure)
+        world = generate_world(n_people, seed=0, sector_betas=sb, leisure=leisure, visits=config4)
     else:
-        draft = generate_domain(n_people, rank, world_size, seed=0, sector_betas=sb, leisure=leisure)
+        draft = generate_domain(n_people, rank, world_size, seed=0, sector_betas=sb, leisure=leisure, visits=config4)
         world = wire_halos_distributed(draft, dist)
     inter = Interaction.from_file()
     dc = DiseaseConfig("covid19")
@@ -205,7 +205,7 @@ def workload_name(n_total: int, leisure: bool, config4: bool = False) -> str:
     """The workload both arms run (same generator, schedule and seeding)."""
     if config4:
         return (f"synthetic {n_total / 1e6:.1f}M-person world (households, schools, companies, care homes, hospitals, pubs, "
-                "cinemas, groceries, gyms with leisure), default 5/4-step day schedule from Monday 2020-03-30 08:00, the "
+                "cinemas, groceries, gyms, household and care-home visits with leisure), default 5/4-step day schedule from Monday 2020-03-30 08:00, the "
                 "reference's default policy file with its dates in 2020 (spring lockdown: quarantine, shielding, school / "
                 "company / venue closures, social distancing, reduced leisure), two vaccination campaigns, ~3% seeded prevalence")
     return (f"synthetic {n_total / 1e6:.1f}M-person world (households, schools, companies, care homes, hospitals"

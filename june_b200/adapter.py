@@ -21,7 +21,8 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 from .world import (ACT_MEDICAL, ACT_PRIMARY, ACT_RESIDENCE, ACTIVITY_CODES, KIND_MATRIX, KIND_SCHOOL, LOCKDOWN_CODES,
-                    PRIMARY_KIND_CODES, BetaRule, Supergroup, WorldSoA, make_ginfo, make_info, make_person_attr)
+                    PRIMARY_KIND_CODES, VISITS_ACTIVITY, VISITS_SUPERGROUP, BetaRule, Supergroup, WorldSoA, make_ginfo, make_info,
+                    make_person_attr)
 
 # activity hierarchy, june/activity/activity_manager.py:24-33 (activities without device support
 # in this round are listed so that the supergroup order stays the reference's)
@@ -162,10 +163,12 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
             scale_i.append(sc)
             aux.append(a)
         is_venue = act in ("leisure", "commute")
-        has_dyn = 1 if spec == "hospital" else LEISURE_BIN_CAP if is_venue else 0
+        # care homes take their visitors as dynamic members when the reference's Leisure has residence visits
+        visited_ch = spec == "care_home" and leisure is not None and VISITS_ACTIVITY in getattr(leisure, "leisure_distributors", {})
+        has_dyn = 1 if spec == "hospital" else LEISURE_BIN_CAP if is_venue else 64 if visited_ch else 0
         supergroups.append(Supergroup(name=name, spec=spec, activity=ACTIVITY_CODES[act], first_group=first,
                                       n_groups=len(members), kind=kind,
-                                      launch_mode=1 if (spec in warp_mode_specs or is_venue) else 0, has_dynamic=has_dyn))
+                                      launch_mode=1 if (spec in warp_mode_specs or is_venue or visited_ch) else 0, has_dynamic=has_dyn))
 
     # ---- registered members -----------------------------------------------------------------
     lsg_of: Dict[int, Tuple[int, int]] = {}
@@ -304,6 +307,32 @@ def compile_world(world, activity_to_super_groups: Dict[str, Sequence[str]], sec
         w.leisure_activities = specs
         w.leisure_supergroups = [by_spec[s_].name for s_ in specs]
         w.leisure_subgroups = [int(leisure.leisure_distributors[s_].leisure_subgroup_type) for s_ in specs]
+        hh_sg = by_spec.get("household")
+        if VISITS_ACTIVITY in leisure.leisure_distributors and hh_sg is not None:
+            # residence visits (residence_visits.py): the activity keeps its place in the distributor order (an empty
+            # column of the venue table); Household.residences_to_visit becomes two CSRs over the households
+            k_vis = [s_ for s_ in leisure.leisure_distributors if s_ in by_spec or s_ == VISITS_ACTIVITY].index(VISITS_ACTIVITY)
+            K = len(specs)
+            off2, pos = [0], 0
+            for a_i in range(len(areas)):
+                for k in range(K + 1):
+                    if k != k_vis:
+                        kk = k if k < k_vis else k - 1
+                        pos += off[a_i * K + kk + 1] - off[a_i * K + kk]
+                    off2.append(pos)
+            off = off2
+            specs.insert(k_vis, VISITS_ACTIVITY)
+            w.leisure_supergroups.insert(k_vis, VISITS_SUPERGROUP)
+            w.leisure_subgroups.insert(k_vis, 0)
+            vh_off, vh, vc_off, vc = [0], [], [0], []
+            for g in groups[hh_sg.first_group: hh_sg.first_group + hh_sg.n_groups]:
+                links = getattr(g, "residences_to_visit", None) or {}
+                vh.extend(gidx[id(t)] for t in links.get("household", ()) if id(t) in gidx)
+                vc.extend(gidx[id(t)] for t in links.get("care_home", ()) if id(t) in gidx)
+                vh_off.append(len(vh))
+                vc_off.append(len(vc))
+            w.visit_household_off, w.visit_household = np.array(vh_off, np.uint32), np.array(vh, np.uint32)
+            w.visit_care_home_off, w.visit_care_home = np.array(vc_off, np.uint32), np.array(vc, np.uint32)
         w.area_venue_off, w.area_venue = np.array(off, np.uint32), np.array(ven, np.uint32)
     w.validate()
     return w
