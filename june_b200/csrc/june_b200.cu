@@ -1347,8 +1347,12 @@ static int launch_tiles(JbWorld* w, const GroupArgs& a, cudaStream_t st) {
 // exactly those two, skip-activity policies drop primary_activity / commute: individual_policies.py:87-119,441-824).
 // In a step that offers nothing else they cannot change anybody's placement, so the table-driven placement is exact.
 static inline bool policies_decide_per_person(const JbWorld* w, uint32_t activity_mask) {
-  const uint32_t stay = (1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE);
-  return w->n_pol != 0 && !w->pol_subject_mode && (activity_mask & ~stay & ((1u << JB_N_ACT) - 1u)) != 0u;
+  const JbStepParams& p = w->cur;
+  uint32_t other = activity_mask & ~((1u << JB_ACT_MEDICAL) | (1u << JB_ACT_RESIDENCE)) & ((1u << JB_N_ACT) - 1u);
+  // (an activity nobody can take in this world / step is not an offer: commute without transports, leisure without tables)
+  if (!(w->cmt.person != nullptr || ((p.flags & JB_STEP_INJECT_COMMUTE) && w->cm_inject != nullptr))) other &= ~(1u << JB_ACT_COMMUTE);
+  if (!(w->lz.K != 0 && (p.leisure_table != 0 || (p.flags & JB_STEP_INJECT_LEISURE)))) other &= ~(1u << JB_ACT_LEISURE);
+  return w->n_pol != 0 && !w->pol_subject_mode && other != 0u;
 }
 
 // Does this step draw leisure activities with residence visits among them?  Then the leisure-goers are placed in three

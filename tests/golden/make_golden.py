@@ -57,15 +57,16 @@ ROW_LEN = 5 + 5 + 2 * MAX_STAGES
 
 
 def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, schedule="default", n_uniform=400000,
-              with_leisure=False, lockdown=False, with_commute=False, vaccination=False, records=False):
+              with_leisure=False, lockdown=False, with_commute=False, vaccination=False, records=False, with_visits=False):
     pyrandom.seed(seed)
     np.random.seed(seed)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink):
-        world, dc = ref_world.build_world(n_people, seed=seed, with_leisure=with_leisure, with_commute=with_commute)
+        world, dc = ref_world.build_world(n_people, seed=seed, with_leisure=with_leisure, with_commute=with_commute,
+                                          with_visits=with_visits)
         sim = ref_world.make_simulator(world, dc, total_days=total_days, cases_per_capita=cases_per_capita,
                                        schedule=schedule, with_leisure=with_leisure, lockdown=lockdown,
-                                       with_commute=with_commute, vaccination=vaccination)
+                                       with_commute=with_commute, vaccination=vaccination, with_visits=with_visits)
     import june.interaction.interaction as inter_mod
     import june.policy.individual_policies as indiv_mod
     from june.epidemiology.infection import InfectionSelector
@@ -82,7 +83,7 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
     a2sg = {"medical_facility": ["hospitals"], "primary_activity": ["schools", "companies"],
             "residence": ["households", "care_homes"]}
     if with_leisure:
-        a2sg["leisure"] = ["pubs", "cinemas", "groceries"]
+        a2sg["leisure"] = ["pubs", "cinemas", "groceries"] + (["household_visits", "care_home_visits"] if with_visits else [])
     if with_commute:
         a2sg["commute"] = ["city_transports", "inter_city_transports"]
     soa = compile_world(world, a2sg, InteractiveCompany.sector_betas, leisure=sim.activity_manager.leisure,
@@ -276,8 +277,23 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
             out["effmult"] = np.array([p.immunity.effective_multiplier_dict.get(iid, 1.0) for p in people])
         return out
 
+    # residence visits: the leisure destination every person DREW at its turn (leisure.py:230-275) -- the final placement
+    # does not tell who went out and was fetched back when a visitor came to its household (household.py:124-149)
+    lz_state = {"choice": None}
+    if with_visits:
+        leisure_cls = type(sim.activity_manager.leisure)
+        orig_lz = leisure_cls.get_subgroup_for_person_and_housemates
+
+        def lz(self, person, to_send_abroad=None):
+            sub = orig_lz(self, person=person, to_send_abroad=to_send_abroad)
+            if sub is not None:
+                lz_state["choice"][pidx[person.id]] = gidx[id(sub.group)]
+            return sub
+        leisure_cls.get_subgroup_for_person_and_housemates = lz
+
     def do_timestep(self):
         rec = {}
+        lz_state["choice"] = np.full(len(people), -1, np.int32)
         rec["pre_rows"] = np.array(state["rows"], np.float64).reshape(-1, ROW_LEN)
         state["rows"] = []
         state["draw_person"], state["draw_lambda"], state["draw_u"] = [], [], []
@@ -293,6 +309,8 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         rec["activity_mask"] = mask
         orig_step(self)
         rec["place_group"], rec["place_lsg"] = placement["group"], placement["lsg"]
+        if with_visits:
+            rec["lz_choice"] = lz_state["choice"]
         rec["draw_person"] = np.array(state["draw_person"], np.int64)
         rec["draw_lambda"] = np.array(state["draw_lambda"], np.float64)
         rec["draw_u"] = np.array(state["draw_u"], np.float64)
@@ -328,6 +346,8 @@ def run_trace(n_people, total_days, seed, out_name, cases_per_capita=0.02, sched
         Interaction._gets_infected = orig_gets
         Interaction._time_step_for_subgroup = orig_sub
         InfectionSelector.infect_person_at_time = orig_infect
+        if with_visits:
+            leisure_cls.get_subgroup_for_person_and_housemates = orig_lz
         from random import random as real_random
         inter_mod.random = real_random
 
@@ -442,6 +462,8 @@ if __name__ == "__main__":
     if "leisure_policies" in sys.argv[1:]:
         leisure_policy_tables()
         sys.exit(0)
+    if "visits" in sys.argv[1:]:  # + household and care-home visits (the residents of a visited household stay / come home)
+        run_trace(2500, 9, 8, "w2k_visits", cases_per_capita=0.05, with_leisure=True, with_visits=True)
     if "leisure" in sys.argv[1:]:  # leisure placement (pubs, cinemas, groceries) on top of the w3k recipe
         run_trace(2500, 9, 2, "w2k_leisure", cases_per_capita=0.04, with_leisure=True)
         sys.exit(0)

@@ -50,7 +50,7 @@ def synthetic_rates_df():
 
 
 def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
-                people_per_company=40, people_per_school=1000, n_super_areas=4, with_leisure=False,
+                people_per_company=40, people_per_school=1000, n_super_areas=4, with_leisure=False, with_visits=False,
                 with_commute=False):
     """Returns ``(world, disease_config)``.  People are created household by household so
     that person index order == household order."""
@@ -269,6 +269,27 @@ def build_world(n_people=3000, seed=0, with_hospital=True, with_care_homes=True,
         world.pubs = Pubs(pubs, make_tree=False)
         world.groceries = Groceries(groceries, make_tree=False)
         world.cinemas = Cinemas(cinemas, make_tree=False)
+    if with_visits:
+        # Household.residences_to_visit, as ResidenceVisitsDistributor.link_households_to_households / _to_care_homes
+        # set it (residence_visits.py:189-296; hand-wired here: the reference's linker wants census household types):
+        # two to three households of the same super area, and one household per care-home resident
+        vrng = np.random.default_rng([seed, 4242])
+        by_sa = {}
+        for hh in households:
+            by_sa.setdefault(id(hh.area.super_area), []).append(hh)
+        for hh in households:
+            pool = [h for h in by_sa[id(hh.area.super_area)] if h is not hh and h.n_residents > 0]
+            if hh.n_residents == 0 or not pool:
+                continue
+            k = int(vrng.integers(2, 4))
+            hh.residences_to_visit["household"] = tuple(pool[int(j)] for j in vrng.integers(0, len(pool), k))
+        if with_care_homes:
+            for ch in world.care_homes.members:
+                pool = [h for h in by_sa.get(id(ch.area.super_area), []) if h.n_residents >= 2]
+                for _ in ch.residents:
+                    if pool:
+                        h = pool[int(vrng.integers(0, len(pool)))]
+                        h.residences_to_visit["care_home"] = (*h.residences_to_visit["care_home"], ch)
     return world, dc
 
 
@@ -285,7 +306,7 @@ VACCINES = {
 
 
 def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policies=True,
-                   initial_day="2020-03-02 0:00", schedule="default", with_leisure=False, lockdown=False,
+                   initial_day="2020-03-02 0:00", schedule="default", with_leisure=False, with_visits=False, lockdown=False,
                    with_commute=False, vaccination=False):
     """Reference Simulator wired as ``example_scripts/run_simulation.py:332-512`` does, minus
     leisure / travel / records."""
@@ -392,7 +413,7 @@ def make_simulator(world, dc, total_days=10, cases_per_capita=0.01, with_policie
     leisure = None
     if with_leisure:
         from june.groups.leisure import generate_leisure_for_world
-        a2sg["leisure"] = ["pubs", "cinemas", "groceries"]
+        a2sg["leisure"] = ["pubs", "cinemas", "groceries"] + (["household_visits", "care_home_visits"] if with_visits else [])
         all_activities = ["medical_facility", "primary_activity", "leisure", "residence"]
         leisure = generate_leisure_for_world(
             a2sg["leisure"], world,

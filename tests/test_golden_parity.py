@@ -89,9 +89,30 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
         s = g.step(i)
         if len(s["pre_rows"]):
             eng.upload_infections(rows_to_dicts(s["pre_rows"]))
-        eng.inject_uniforms(s["draw_u"])
+        draw_u = s["draw_u"]
+        if "lz_choice" in s and len(draw_u):
+            # Residence visits.  The reference appends people to a subgroup as they are placed and re-appends the residents
+            # of a household every time a visitor arrives (household.py:124-149), so inside a visited household (or care
+            # home) its draws come in "last appended" order; the engines keep (subgroup, members before visitors, person).
+            # Same groups, same people, same uniforms per person: the uniforms are handed over in the engines' order.
+            dp_, pg_, pl_ = s["draw_person"], s["place_group"], s["place_lsg"]
+            grp = pg_[dp_]
+            block = np.cumsum(np.r_[0, grp[1:] != grp[:-1]])
+            visitor = (s["lz_choice"][dp_] == grp).astype(np.int64)
+            order = np.lexsort((dp_, visitor, pl_[dp_], block))
+            assert np.array_equal(block[order], block), "a group's draws are contiguous in both orders"
+            draw_u = draw_u[order]
+            run_trace.visit_reorders = getattr(run_trace, "visit_reorders", 0) + int((order != np.arange(len(order))).sum())
+        eng.inject_uniforms(draw_u)
         flags = FLAGS
-        if g.world.has_leisure:
+        if g.world.has_leisure and "lz_choice" in s:
+            # the destination every person drew at its turn (a venue, a household, a care home), -1 = none: who stays or
+            # comes back home because its household receives a visitor is decided by the engine, as in the reference
+            eng.inject_leisure(s["lz_choice"].astype(np.int32))
+            flags |= _lib.STEP_INJECT_LEISURE
+            run_trace.visits = getattr(run_trace, "visits", 0) + int(((s["lz_choice"] >= 0) & (sg_act[grp_sg[np.maximum(s["lz_choice"], 0)]] == 4)).sum())
+            run_trace.fetched_home = getattr(run_trace, "fetched_home", 0) + int(((s["lz_choice"] >= 0) & (s["place_group"] != s["lz_choice"])).sum())
+        elif g.world.has_leisure:
             # the reference's own leisure choices (leisure.py:253-263 draws from Python's / numba's
             # global generators) are replayed: venue per person, -1 = did not go out
             pg = s["place_group"]
@@ -209,6 +230,8 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
         # hospital workers sit in a hospital group through their primary activity
         mism = (act != exp_act) & (pg >= 0)
         for q in np.nonzero(mism)[0]:
+            if "lz_choice" in s and s["lz_choice"][q] == pg[q] and act[q] == ACT_LEISURE:
+                continue  # a visitor: in a household or care home through leisure
             lo, hi = g.world.grp_offset[pg[q]], g.world.grp_offset[pg[q] + 1]
             slot = lo + np.nonzero(g.world.reg_member[lo:hi] == q)[0]
             assert len(slot) and (g.world.reg_info[slot[0]] >> 8) == act[q], f"step {i}: person {q} misplaced"
@@ -237,19 +260,23 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     return total_draws, total_inf, worst
 
 
-FIXTURES = ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute", "w2k_vaccination", "w2k_records"]
+FIXTURES = ["w3k", "w1k_long", "w2k_leisure", "w2k_policies", "w2k_commute", "w2k_vaccination", "w2k_records", "w2k_visits"]
 run_trace.health_rows = {}
 
 
 @pytest.mark.parametrize("name", FIXTURES)
 def test_oracle_matches_reference_trace(name):
     run_trace.policy_draws = run_trace.commuters = run_trace.vaccine_draws = run_trace.infection_rows = run_trace.summary_rows = 0
+    run_trace.visits = run_trace.fetched_home = run_trace.visit_reorders = 0
     run_trace.health_rows = {}
     draws, infections, worst = run_trace("oracle", name)
     if name == "w2k_records":
         assert run_trace.infection_rows > 500
         assert run_trace.summary_rows > 80, "summary.csv rows of the reference's own summarise_time_step must have been compared"
         assert all(run_trace.health_rows.get(k, 0) > 0 for k in range(1, 7)), run_trace.health_rows
+    if name == "w2k_visits":
+        assert run_trace.visits > 1000, "people must have visited households and care homes"
+        assert run_trace.fetched_home > 50, "residents out doing leisure must have been fetched home by a visitor"
     if name == "w2k_policies":
         assert run_trace.policy_draws > 5000, "the lockdown policies must have drawn"
     if name == "w2k_commute":
