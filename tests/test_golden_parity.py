@@ -66,7 +66,7 @@ def run_trace(kind: str, name: str, max_steps=None, launch_modes=None):
     g = Golden(name)
     if launch_modes is not None:  # exercise the other kernel flavour on the same trace
         for sg in g.world.supergroups:
-            if sg.spec in launch_modes:
+            if sg.spec in launch_modes and not sg.has_dynamic:  # (care homes that take visitors stay on the per-group kernels)
                 sg.launch_mode = launch_modes[sg.spec]
     inter = Interaction.from_file()
     # JB_MIRROR=0: companies / schools gather their members' bytes through the person index instead of
