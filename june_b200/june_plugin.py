@@ -194,14 +194,21 @@ def make_b200_simulator_class(reference_simulator_cls):
         def _b200_leisure_table(self, activities, pol):
             """``ActivityManager.do_timestep`` (``activity_manager.py:200-209``): leisure policies, then
             ``generate_leisure_probabilities_for_timestep``.  The reference's nested dict is flattened
-            into ``does[R][2][100]`` / ``cum[R][2][100][K]`` over the device's activities; the mass of
-            activities without device support (residence visits) counts as "stays at home"."""
+            into ``does[R][2][100]`` / ``cum[R][2][100][K]`` over the device's activities (venues and residence
+            visits); ``ChangeVisitsProbability`` reaches the device as the residence-type split in force."""
             leisure = self.activity_manager.leisure
             if leisure is None or not self._soa.has_leisure or "leisure" not in activities:
                 return 0
             date = self.timer.date
             if pol is not None:
                 pol.leisure_policies.apply(date=date, leisure=leisure)
+            if self._soa.has_visits:
+                dist = leisure.leisure_distributors["residence_visits"]
+                split = dist.policy_reductions or dist.residence_type_probabilities  # residence_visits.py:305-309
+                split = (float(split.get("household", 0.0)), float(split.get("care_home", 0.0)))
+                if split != getattr(self, "_b200_visit_split", None):
+                    self._eng.set_visit_probabilities(*split)
+                    self._b200_visit_split = split
             lkey = tuple(id(p) for p in pol.leisure_policies.get_active(date)) if pol is not None else ()
             key = (round(self.timer.duration, 9), "primary_activity" in activities, date.weekday(), date.hour, self._policy_key, lkey)
             idx = self._leisure_cache.get(key)

@@ -62,8 +62,8 @@ def test_reference_simulator_subclass_with_leisure_commute_and_lockdown():
     np.random.seed(4)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink):
-        world, dc = ref_world.build_world(2500, seed=4, with_leisure=True)
-        ref_sim = ref_world.make_simulator(world, dc, total_days=8, cases_per_capita=0.04, with_leisure=True, lockdown=True)
+        world, dc = ref_world.build_world(2500, seed=4, with_leisure=True, with_visits=True)
+        ref_sim = ref_world.make_simulator(world, dc, total_days=8, cases_per_capita=0.04, with_leisure=True, with_visits=True, lockdown=True)
     from june.simulator import Simulator
     B200Simulator = make_b200_simulator_class(Simulator)
     B200Simulator.b200_engine = staticmethod(lambda soa, inter, dcfg, prob: make_engine("oracle", soa, prob, interaction=inter, disease=dcfg))
@@ -86,7 +86,9 @@ def test_reference_simulator_subclass_with_leisure_commute_and_lockdown():
     B200Simulator.do_timestep = step
     with contextlib.redirect_stdout(sink):
         sim.run()
-    assert sim._soa.has_leisure and sim._soa.leisure_activities == ["pub", "cinema", "grocery"]
+    assert sim._soa.has_leisure and sim._soa.leisure_activities == ["pub", "cinema", "grocery", "residence_visits"]
+    assert sim._soa.has_visits and int(sim._soa.visit_household_off[-1]) > 1000 and int(sim._soa.visit_care_home_off[-1]) > 10
+    assert sim._b200_visit_split == (0.66, 0.34)
     assert seen["leisure"] > 1000, "people must have gone to pubs / cinemas / groceries"
     assert seen["skipped_work"] >= 1, "CloseCompanies / CloseSchools must keep people away from work"
 
