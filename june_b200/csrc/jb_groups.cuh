@@ -25,10 +25,6 @@ __device__ __forceinline__ double jb_cm_elem(const GroupArgs& a, int i, int j, c
   return yi == yj ? x / 4.0 : x;
 }
 
-__device__ __forceinline__ void jb_prefetch_l2(const void* ptr) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-}
-
 // Susceptibility of person p to variant v given its hot byte.
 template <int VM>
 __device__ __forceinline__ double jb_susc(const GroupArgs& a, uint32_t p, uint32_t hot, int v) {
@@ -475,6 +471,12 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 #define JB_TILE_SLOTS (JB_TILE_THREADS * 16)
 #define JB_TILE_ITEMS (JB_TILE_SLOTS / 2)  // a listed group has >= 2 slots
 #define JB_DRAW_QUEUE 64
+// JB_TILE_PER_WARP = 1: every warp detects AND processes its own 512 slots (own work list, no block-wide barrier
+// between the phases).  Measured (profiles/README.md, round 2): 51 % more warp instructions (every warp runs its own,
+// two-thirds full, processing batch) for the same time at 56 M people and 6 % less at 7 M -- kept as an option.
+#ifndef JB_TILE_PER_WARP
+#define JB_TILE_PER_WARP 0
+#endif
 
 
 // TM: where a slot's person byte comes from.  JB_TM_GATHER: the slot holds a person index, the byte is gathered from
@@ -491,22 +493,26 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
   constexpr bool STREAM = TM == JB_TM_STREAM;
   if (STREAM) jb_stamp(2);
   const double* const trans = jb_trans_read(a.trans, a.NP, a.sp);
+  constexpr bool PW = JB_TILE_PER_WARP != 0;
+  constexpr int ITEMS_W = JB_TILE_ITEMS / JB_TILE_WARPS;  // work-list entries of one warp (per-warp lists)
   __shared__ uint2 s_items[JB_TILE_ITEMS];  // {(block-local first slot << 5) | (len - 1), group}
   __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
   __shared__ uint32_t s_mem[TM == JB_TM_GATHER ? JB_TILE_SLOTS : 1];
   __shared__ double s_cm[16];
-  __shared__ uint32_t s_n;
+  __shared__ uint32_t s_nw[JB_TILE_WARPS];  // work-list lengths (per-warp lists; [0] = the block's list otherwise)
   __shared__ double q_lam[JB_TILE_WARPS][VM][JB_DRAW_QUEUE];
   __shared__ uint32_t q_x[JB_TILE_WARPS][JB_DRAW_QUEUE], q_ord[JB_TILE_WARPS][JB_DRAW_QUEUE];  // block-local slot, ordinal
   __shared__ uint16_t q_item[JB_TILE_WARPS][JB_DRAW_QUEUE];  // work item of the queued draw (blame)
   const uint8_t* s_hot = reinterpret_cast<const uint8_t*>(s_hot4);
   const uint8_t* s_info = reinterpret_cast<const uint8_t*>(s_info4);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_n = 0;
+  uint32_t& s_n = s_nw[PW ? wib : 0];
+  uint2* const my_items = s_items + (PW ? wib * ITEMS_W : 0);
+  if (PW ? lane == 0 : threadIdx.x == 0) s_n = 0;
   // contact matrix: requested now, parked in shared memory behind phase A (not a DRAM round trip
-  // in front of the block's first barrier)
-  const double cm_mine = threadIdx.x < a.dim * a.dim ? a.cm[threadIdx.x] : 0.0;
-  __syncthreads();
+  // in front of the block's first barrier); per-warp lists: every warp parks the same 16 values
+  const double cm_mine = (PW ? lane : (int)threadIdx.x) < a.dim * a.dim ? a.cm[PW ? lane : threadIdx.x] : 0.0;
+  if (PW) __syncwarp(); else __syncthreads();
 
   // ---- phase A ---------------------------------------------------------------------------
   const uint32_t slot_base = blockIdx.x * JB_TILE_SLOTS;  // first slot of this block
@@ -609,14 +615,14 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
         if (a.mode == 1) { a.draw_cnt[g] = nsus; continue; }
         draws += nsus;
         const uint32_t pos = atomicAdd(&s_n, 1u);
-        s_items[pos] = make_uint2(((t * 32 + start - slot_base) << 5) | (end - start - 1), g);
+        my_items[pos] = make_uint2(((t * 32 + start - slot_base) << 5) | (end - start - 1), g);
       }
     }
     draws = __reduce_add_sync(JB_FULL, draws);
     if (lane == 0 && draws) atomicAdd(&a.counters[CNT_DRAWS], draws);
   }
-  if (threadIdx.x < a.dim * a.dim) s_cm[threadIdx.x] = cm_mine;
-  __syncthreads();
+  if ((PW ? lane : (int)threadIdx.x) < a.dim * a.dim) s_cm[PW ? lane : threadIdx.x] = cm_mine;
+  if (PW) __syncwarp(); else __syncthreads();
   const uint32_t n_work = s_n;
   if (STREAM) jb_stamp_max(0);
   if (n_work == 0 || a.mode == 2) { if (STREAM) jb_stamp_max(1); return; }  // mode 2: detection only (profiling aid)
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
       const int v = jb_draw_core<VM>(a, a.inject ? 0u : gid_of(x), lam_v, lam, q_ord[wib][lane]);
       if (v >= 0) {
         const uint32_t p = person(x);
-        const uint2 it = s_items[q_item[wib][lane]];
+        const uint2 it = my_items[q_item[wib][lane]];
         uint32_t infector = 0xFFFFFFFFu;
         if (EV) {
           // rare path: rebuild the group's sums from the block's shared-memory copy of the slots,
@@ -704,10 +710,10 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
     __syncwarp();
   };
 
-  for (uint32_t wbase = wib * 32; wbase < n_work; wbase += JB_TILE_WARPS * 32) {
+  for (uint32_t wbase = PW ? 0u : wib * 32u; wbase < n_work; wbase += PW ? 32u : JB_TILE_WARPS * 32u) {
     const uint32_t w = wbase + lane;
     const bool have_item = w < n_work;
-    const uint2 item = have_item ? s_items[w] : make_uint2(0u, 0u);
+    const uint2 item = have_item ? my_items[w] : make_uint2(0u, 0u);
     const uint32_t loc = item.x >> 5, len = have_item ? (item.x & 31u) + 1u : 0u, g = item.y;
     const uint32_t max_len = __reduce_max_sync(JB_FULL, len);
     // Everything phase B gathers per group (the infectors' transmission probabilities, the group

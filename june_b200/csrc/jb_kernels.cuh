@@ -21,6 +21,10 @@
 // step read half `tpar` (filled by the previous step's health update) while this step's health update fills
 // the other half.  The half is a per-step scalar in the parameter block, not a kernel argument, so one
 // captured graph serves both parities.
+__device__ __forceinline__ void jb_prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 __device__ __forceinline__ const double* jb_trans_read(const double* base, uint32_t NP, const StepDev* sp) {
   return base + (size_t)(sp->tpar & 1u) * NP;
 }
@@ -321,7 +325,7 @@ __device__ __forceinline__ uint32_t jb_place_key(uint32_t st, uint32_t has) {
 // FULL = false: neither leisure nor individual policies in this step -- the activity is a pure
 // table lookup per byte (the common weekday-night / no-lockdown step keeps its 48 registers).
 template <bool FULL>
-__global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs a) {
+__global__ void __launch_bounds__(256, FULL ? 1 : 6) k_place(const __grid_constant__ PlaceArgs a) {
   jb_stamp(1);
   __shared__ uint8_t s_act[512];      // 0..4 activity, 7 none (dead), 15 alive without any activity
   __shared__ uint32_t s_cnt[8];
@@ -409,6 +413,15 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
     return act | (st & JB_PS_INFECTED) | ((st & JB_PST_CODE_MASK) << 4) | (var << 6);
   };
   uint32_t iters = 0;
+  // SWAR path: byte-wide per-activity counters of the words handled since the last flush, chunks handled, persons without a candidate
+  uint32_t pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, n_none = 0, n_swar = 0;
+  auto flush_planes = [&]() {
+    const uint32_t c0 = (pl0 * 0x01010101u) >> 24, c1 = (pl1 * 0x01010101u) >> 24, c2 = (pl2 * 0x01010101u) >> 24, c3 = (pl3 * 0x01010101u) >> 24;
+    const uint32_t c4 = n_swar * 16u - n_none - c0 - c1 - c2 - c3;
+    cnt += (unsigned long long)c0 | ((unsigned long long)c1 << 8) | ((unsigned long long)c2 << 16) | ((unsigned long long)c3 << 24) |
+           ((unsigned long long)c4 << 32);
+    pl0 = pl1 = pl2 = pl3 = 0; n_none = 0; n_swar = 0;
+  };
   if (FULL) {
     // one person per thread: policies, commute and leisure walk per-person tables and draw Philox
     // numbers -- a dependent chain per person that 16 persons per thread would serialise
@@ -426,9 +439,14 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
     if (p0 + 16 <= a.N) {
       const uint4 sv = *reinterpret_cast<const uint4*>(a.pstate + p0);
       const uint4 hv = *reinterpret_cast<const uint4*>(a.phas + p0);
+      {  // this thread's next chunk starts its trip from DRAM now (the even lane asks for the pair's 32-byte sector)
+        const size_t pn = (size_t)p0 + (size_t)gridDim.x * blockDim.x * 16u;
+        if (!(threadIdx.x & 1) && pn < a.N) { jb_prefetch_l2(a.pstate + pn); jb_prefetch_l2(a.phas + pn); }
+      }
       uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
       const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
       if (!a.pvar) {
+        ++n_swar;
         // Four persons per 32-bit word, no table: candidate activities = (fixed subgroups | medical)
         // & the step's mask, restricted for severe stay-at-home cases, none for the dead; the chosen
         // activity is the lowest set bit of each byte (hierarchy order == bit order).
@@ -469,8 +487,10 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
                           (((low4 >> 4) & 0x01010101u) << 2);
           act4 |= none4 * 7u;  // JB_ACT_NONE
           noact += __popc(none4 & ~dead4);
-#pragma unroll
-          for (int k = 0; k < JB_N_ACT; ++k) cnt += (unsigned long long)__popc(low4 & (0x01010101u << k)) << (8 * k);
+          // persons per activity: four byte-wide counters per activity (one per person of the word); the residence,
+          // the last and most common activity, is what remains of the chunk's 16 persons
+          pl0 += low4 & 0x01010101u; pl1 += (low4 >> 1) & 0x01010101u; pl2 += (low4 >> 2) & 0x01010101u; pl3 += (low4 >> 3) & 0x01010101u;
+          n_none += __popc(none4);
           uint32_t medm = low4 & 0x01010101u;  // rare: patients go into their ward's bin
           while (medm) {
             const uint32_t b = (uint32_t)(__ffs(medm) - 1) >> 3;
@@ -493,12 +513,14 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PlaceArgs
     } else {
       for (uint32_t p = p0; p < a.N; ++p) a.phot[p] = (uint8_t)one(p, a.pstate[p], a.phas[p]);
     }
-    if (++iters == 15) {  // 15 * 16 = 240 < 256: flush the packed 8-bit counters
+    if (++iters == 15) {  // 15 * 16 = 240 < 256: flush the 8-bit counters
+      flush_planes();
 #pragma unroll
       for (int k = 0; k < 8; ++k) atomicAdd(&s_cnt[k], (uint32_t)((cnt >> (8 * k)) & 0xFFull));
       cnt = 0ull; iters = 0;
     }
   }
+  if (!FULL) flush_planes();
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const uint32_t v = __reduce_add_sync(JB_FULL, (uint32_t)((cnt >> (8 * k)) & 0xFFull));
@@ -925,18 +947,13 @@ struct NewInfArgs {
   uint32_t mutate_variant;
   const double* effmult;    // [V][N] immunity.effective_multiplier_dict, or null (no vaccination)
   int fuse_health;          // 1 inside a step: the creating lane also runs the slot's first health update
-  uint32_t lane_min;        // from this many entries on: one lane per infection instead of sixteen
   HealthArgs h;
 };
 
-// 16 lanes per new infection: every completion time / transmission parameter is an independent
-// sample with its own Philox stream (JB_STREAM_SAMPLE0 + slot), so the lanes draw them in
-// parallel and lane 0 assembles the infection.  Slots: 0 max_severity; 1..8 stage s = slot-1;
-// 9..14 transmission parameter k = slot-9; 15 the second `alpha()` call of the xnexp profile.
-// The disease tables (6 KB, walked with data-dependent indices) travel as a kernel parameter: constant
-// bank reads instead of a per-block staging copy behind a barrier.  The chain of dependent DRAM round
-// trips is kept short: everything indexed by the person is requested in one go, and lane 0 takes its
-// infection slot before the sampling, not after it.
+// Sixteen sample slots per new infection, each an independent sample with its own Philox stream
+// (JB_STREAM_SAMPLE0 + slot): 0 max_severity; 1..8 stage s = slot-1; 9..14 transmission parameter k = slot-9; 15 the
+// second `alpha()` call of the xnexp profile.  The disease tables (6 KB, walked with data-dependent indices) travel as
+// a kernel parameter: constant bank reads instead of a per-block staging copy behind a barrier.
 // Assemble one infection from its samples (InfectionSelector._make_infection, infection_selector.py:146-332) and give
 // it its first health update; run by one lane per infection.
 __device__ __forceinline__ void jb_newinf_assemble(const NewInfArgs& a, const DiseaseDev& D, uint32_t p, uint32_t var, uint32_t st,
@@ -1076,167 +1093,99 @@ __device__ __forceinline__ const JbDist* jb_newinf_dist(const DiseaseDev& D, int
   return nullptr;
 }
 
-// One LANE per new infection: the lane draws the infection's samples one after the other.  Sixteen times fewer
-// warp instructions than the 16-lane form below (whose lanes run different samplers, one branch after the other);
-// the price is a sixteen times longer chain per infection, so this form is used when there are enough new
-// infections to fill the device with one infection per lane.  Same Philox streams, same results.
-__device__ __forceinline__ void jb_newinf_lanes(const NewInfArgs& a, const DiseaseDev& D, uint32_t first, uint32_t n) {
+// Sample-major form: a CTA of 16 warps takes 32 new infections at a time; LANE = infection, WARP = sample slot, so a
+// warp draws the same quantity for 32 different infections (lanes differ in parameters, seldom in the sampler they
+// run) and the sixteen samples of an infection are drawn side by side.  Every warp repeats the short prologue (person
+// facts, max_severity, outcome, trajectory: their loads hit L1 after the first warp) instead of waiting for a
+// broadcast behind a barrier; the samples meet in shared memory and warp 0 -- whose own slot, max_severity, is part of
+// the prologue -- takes the infection slots and the assembling lane's person facts while the others sample, then
+// assembles.  Same Philox streams as ever: (person, step, JB_STREAM_SAMPLE0 + slot).
+#define JB_NEWINF_THREADS 512
+#define JB_NEWINF_GRID (148 * 2)  // two resident CTAs per SM; a CTA walks the chunks blockIdx, blockIdx + grid, ...
+__global__ void __launch_bounds__(JB_NEWINF_THREADS, 2) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
+  jb_stamp(6);
+  __shared__ double s_x[16][32];
+  const uint32_t first = a.first_dev ? min(*a.first_dev, a.cap) : 0u;
+  const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap - first) : a.count_host;
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
   const uint32_t step_flags = a.sp->flags;
-  double* const trans_next = jb_trans_write(a.trans, a.NP, a.sp);
-  double* const trans_cur = a.trans + (size_t)(a.sp->tpar & 1u) * a.NP;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint32_t p = a.member[first + i];
-    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[first + i] : 0u;
-    if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
-      if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
-      atomicAdd(&a.counters[CNT_HALO_INF], 1u);
-      continue;
+  for (uint32_t i0 = blockIdx.x * 32u; i0 < n; i0 += gridDim.x * 32u) {
+    const uint32_t i = i0 + lane;
+    bool live = i < n;
+    uint32_t p = 0, var = 0, st = 0, gid = 0, region_p = 0, slot = 0;
+    int32_t med_p = -1, hosp_p = -1;
+    int idx = 0, k = 0, nst = 0;
+    if (live) {
+      p = a.member[first + i];
+      var = a.mutate ? a.mutate_variant : a.variant ? a.variant[first + i] : 0u;
+      if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
+        if (j == 0) {
+          if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
+          atomicAdd(&a.counters[CNT_HALO_INF], 1u);
+        }
+        live = false;
+      } else if (step_flags & JB_STEP_NO_NEW_INFECTIONS) {
+        live = false;  // only route halo infections (the host creates the local ones)
+      }
     }
-    if (step_flags & JB_STEP_NO_NEW_INFECTIONS) continue;
-    const uint32_t st = a.pstate[p];
-    const uint32_t ext = a.int2ext[p];
-    const uint32_t age_raw = a.age[p], sex_p = a.sex[p], ch_p = a.ch[p];
-    const uint32_t region_p = a.pregion[p], sa_p = a.psa[p];
-    const int32_t med_p = a.pmed[p];
-    if (!a.mutate && (st & (JB_PS_INFECTED | JB_PS_DEAD))) continue;
-    if (a.mutate && !(st & JB_PS_INFECTED)) continue;
-    const uint32_t slot = a.mutate ? (uint32_t)a.pslot[p] : atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);
-    const int32_t hosp_p = a.sa_hospital[sa_p];
-    const uint32_t gid = a.gid_base + ext;
-    JbStream r0;
-    jb_stream_init(r0, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0);
-    const double max_sev = jb_stream_next(r0);
-    const int age = age_raw > 99u ? 99 : (int)age_raw;
-    const int pop = (ch_p && age >= 50) ? 1 : 0;
-    const double* cum = a.hi_cum + ((size_t)(pop * 2 + sex_p) * 100 + age) * D.n_tags;
-    const double mult = a.effmult ? a.effmult[(size_t)var * a.N + p] : 1.0;
-    const int idx = jb_newinf_outcome(D, cum, mult, max_sev);
-    int k = 0;
-    for (int t = 0; t < D.n_traj; ++t)
-      if (D.traj_max_tag[t] == idx) k = t;
-    const int nst = D.traj_n_stages[k];
-    double xs[16];
-#pragma unroll
-    for (int j = 1; j < 16; ++j) {
+    if (live) {
+      // one round trip for everything indexed by the person
+      st = a.pstate[p];
+      const uint32_t ext = a.int2ext[p];
+      const uint32_t age_raw = a.age[p], sex_p = a.sex[p], ch_p = a.ch[p];
+      uint32_t sa_p = 0;
+      if (j == 0) { region_p = a.pregion[p]; sa_p = a.psa[p]; med_p = a.pmed[p]; }
+      if (!a.mutate && (st & (JB_PS_INFECTED | JB_PS_DEAD))) live = false;  // cannot happen within a step; guards seeding
+      if (a.mutate && !(st & JB_PS_INFECTED)) live = false;
+      if (live) {
+        if (j == 0) {
+          slot = a.mutate ? (uint32_t)a.pslot[p] : atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);  // in flight while the others sample
+          hosp_p = a.sa_hospital[sa_p];
+        }
+        gid = a.gid_base + ext;
+        if (j <= 8) {  // the trajectory decides the stage-time distributions (slots 1..8) and the assembly (warp 0)
+          // symptoms: max_severity -> outcome slot (symptoms.py:47,110-120; health_index.py:151-182)
+          JbStream r0;
+          jb_stream_init(r0, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0);
+          const double max_sev = jb_stream_next(r0);
+          const int age = age_raw > 99u ? 99 : (int)age_raw;
+          const int pop = (ch_p && age >= 50) ? 1 : 0;
+          const double* cum = a.hi_cum + ((size_t)(pop * 2 + sex_p) * 100 + age) * D.n_tags;
+          const double mult = a.effmult ? a.effmult[(size_t)var * a.N + p] : 1.0;
+          idx = jb_newinf_outcome(D, cum, mult, max_sev);
+          for (int t = 0; t < D.n_traj; ++t)
+            if (D.traj_max_tag[t] == idx) k = t;
+          nst = D.traj_n_stages[k];
+        }
+      }
+    }
+    double x = 0.0;
+    if (live && j) {
       const JbDist* dist = jb_newinf_dist(D, j, k, nst, var);
-      double x = 0.0;
       if (dist) {
         JbStream rs;
         jb_stream_init(rs, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
         x = jb_sample_dist(rs, dist->type, dist->p);
       }
-      xs[j] = x;
     }
-    if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
-    jb_newinf_assemble(a, D, p, var, st, slot, region_p, hosp_p, med_p, idx, k, nst, xs + 1, xs + 9, trans_next, trans_cur);
-  }
-}
-
-__device__ __forceinline__ void jb_newinf_body(const NewInfArgs& a, const DiseaseDev& D, uint32_t bid, uint32_t nb, uint32_t first, uint32_t n) {
-  if ((uint64_t)bid * (blockDim.x / 16) >= n) return;  // nothing for this block
-  const int lane = threadIdx.x & 31, j = lane & 15;
-  const uint32_t segmask = 0xFFFFu << (lane & 16);
-  const uint32_t n_seg = nb * blockDim.x / 16;
-  const uint32_t step_flags = a.sp->flags;
-  double* const trans_next = jb_trans_write(a.trans, a.NP, a.sp);
-  double* const trans_cur = a.trans + (size_t)(a.sp->tpar & 1u) * a.NP;
-  for (uint32_t i = (bid * blockDim.x + threadIdx.x) / 16; i < n; i += n_seg) {
-    const uint32_t p = a.member[first + i];
-    const uint32_t var = a.mutate ? a.mutate_variant : a.variant ? a.variant[first + i] : 0u;
-    if (p >= a.N) {  // halo person: tell the home domain (epidemiology.py:359-401)
-      if (j == 0) {
-        if (a.halo_ret) a.halo_ret[p - a.N] = (uint8_t)(var + 1);
-        atomicAdd(&a.counters[CNT_HALO_INF], 1u);
-      }
-      continue;
-    }
-    if (step_flags & JB_STEP_NO_NEW_INFECTIONS) continue;  // only route halo infections (the host creates the local ones)
-    // one round trip for everything indexed by the person
-    const uint32_t st = a.pstate[p];
-    const uint32_t ext = a.int2ext[p];
-    const uint32_t age_raw = a.age[p], sex_p = a.sex[p], ch_p = a.ch[p];
-    uint32_t region_p = 0, sa_p = 0;
-    int32_t med_p = -1;
-    if (j == 0) { region_p = a.pregion[p]; sa_p = a.psa[p]; med_p = a.pmed[p]; }
-    if (!a.mutate && (st & (JB_PS_INFECTED | JB_PS_DEAD))) continue;  // cannot happen within a step; guards seeding
-    if (a.mutate && !(st & JB_PS_INFECTED)) continue;
-    uint32_t slot = 0;
-    int32_t hosp_p = -1;
-    if (j == 0) {
-      if (a.mutate) slot = (uint32_t)a.pslot[p];
-      else slot = atomicAdd(&a.counters[CNT_SLOTS_HW], 1u);  // in flight while the segment samples
-      hosp_p = a.sa_hospital[sa_p];
-    }
-    const uint32_t gid = a.gid_base + ext;
-    // symptoms: max_severity -> outcome slot (symptoms.py:47,110-120; health_index.py:151-182)
-    JbStream r0;
-    jb_stream_init(r0, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0);
-    const double max_sev = jb_stream_next(r0);
-    const int age = age_raw > 99u ? 99 : (int)age_raw;
-    const int pop = (ch_p && age >= 50) ? 1 : 0;
-    const double* cum = a.hi_cum + ((size_t)(pop * 2 + sex_p) * 100 + age) * D.n_tags;
-    // np.searchsorted(side="left"): the 16 lanes of the segment test one table entry each
-    double my_cum = j < D.n_tags ? cum[j] : 2.0;
-    const double mult = a.effmult ? a.effmult[(size_t)var * a.N + p] : 1.0;
-    if (mult != 1.0) {
-      // HealthIndexGenerator.apply_effective_multiplier (health_index.py:183-204): the mass of the
-      // outcomes from "severe" upwards (+ the residual) is scaled, the milder ones renormalised.
-      // Lane j holds outcome j; the sums run in index order, like the sequential reference.
-      const int max_mild = __ffs(D.severe_mask) - 1 - 2;
-      const double prev = __shfl_up_sync(segmask, my_cum, 1, 16);
-      const double pr = j < D.n_tags ? my_cum - (j ? prev : 0.0) : 0.0;
-      double total = 0.0, mild = 0.0, severe = 0.0;
-      for (int k = 0; k < D.n_tags; ++k) {
-        const double x = __shfl_sync(segmask, pr, k, 16);
-        total += x;
-        if (k < max_mild) mild += x; else severe += x;
-      }
-      severe += 1 - total;
-      const double mod_severe = severe * mult, mod_mild = 1.0 - mod_severe;
-      const double mine = j < max_mild ? pr * mod_mild / mild : pr * mod_severe / severe;
-      double run = 0.0;
-      for (int k = 0; k < D.n_tags; ++k) {
-        run += __shfl_sync(segmask, mine, k, 16);
-        if (k == j) my_cum = run;
-      }
-    }
-    const bool below = j < D.n_tags && my_cum < max_sev;
-    int idx = __popc(__ballot_sync(segmask, below) & segmask);
-    if (idx >= D.n_tags) idx = D.n_tags - 1;  // residual mass of a cumsum ending at 1-eps
-    int k = 0;
-    for (int t = 0; t < D.n_traj; ++t)
-      if (D.traj_max_tag[t] == idx) k = t;
-    const int nst = D.traj_n_stages[k];
-    // my sample
-    double x = 0.0;
-    {
-      JbStream rs;
-      jb_stream_init(rs, a.sp->seed, a.sp->step, gid, JB_STREAM_SAMPLE0 + (uint32_t)j);
-      const JbDist* dist = jb_newinf_dist(D, j, k, nst, var);  // one call site: the sampler is a real function (instruction footprint)
-      if (dist) x = jb_sample_dist(rs, dist->type, dist->p);
-    }
-    // lane 0 of the segment assembles the infection
-    double tstage[JB_MAX_STAGES], tp[7];
+    s_x[j][lane] = x;
+    __syncthreads();
+    if (j == 0 && live) {
+      if (slot >= a.C) {
+        atomicAdd(&a.counters[CNT_OVERFLOW], 1u);
+      } else {
+        double tstage[JB_MAX_STAGES], tp[7];
 #pragma unroll
-    for (int s = 0; s < JB_MAX_STAGES; ++s) tstage[s] = __shfl_sync(segmask, x, 1 + s, 16);
+        for (int s = 0; s < JB_MAX_STAGES; ++s) tstage[s] = s_x[1 + s][lane];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) tp[q] = __shfl_sync(segmask, x, 9 + q, 16);
-    if (j != 0) continue;
-    if (slot >= a.C) { atomicAdd(&a.counters[CNT_OVERFLOW], 1u); continue; }
-    jb_newinf_assemble(a, D, p, var, st, slot, region_p, hosp_p, med_p, idx, k, nst, tstage, tp, trans_next, trans_cur);
+        for (int q = 0; q < 7; ++q) tp[q] = s_x[9 + q][lane];
+        double* const trans_next = jb_trans_write(a.trans, a.NP, a.sp);
+        double* const trans_cur = a.trans + (size_t)(a.sp->tpar & 1u) * a.NP;
+        jb_newinf_assemble(a, D, p, var, st, slot, region_p, hosp_p, med_p, idx, k, nst, tstage, tp, trans_next, trans_cur);
+      }
+    }
+    __syncthreads();  // s_x is reused by the next chunk
   }
-}
-
-// JB_NEWINF_LANE_MIN: from this many new infections on, one lane per infection (jb_newinf_lanes); below, sixteen.
-#ifndef JB_NEWINF_LANE_MIN
-#define JB_NEWINF_LANE_MIN 16384u
-#endif
-__global__ void __launch_bounds__(128) k_newinf(const __grid_constant__ NewInfArgs a, const __grid_constant__ DiseaseDev D) {
-  jb_stamp(6);
-  const uint32_t first = a.first_dev ? min(*a.first_dev, a.cap) : 0u;
-  const uint32_t n = a.count_dev ? min(*a.count_dev, a.cap - first) : a.count_host;
-  if (n >= a.lane_min) jb_newinf_lanes(a, D, first, n);
-  else jb_newinf_body(a, D, blockIdx.x, gridDim.x, first, n);
   jb_stamp_max(3);
 }
 

@@ -1091,7 +1091,6 @@ static NewInfArgs make_newinf_args(JbWorld* w) {
   a.inf_region = w->inf_region; a.inf_hosp = w->inf_hosp; a.inf_med = w->inf_med; a.inf_sev = w->inf_sev;
   a.psa = w->psa; a.sa_hospital = w->sa_hospital; a.pmed = w->pmed;
   a.effmult = w->effmult;
-  a.lane_min = (uint32_t)std::max(0, jb_env_flag("JB_NEWINF_LANE_MIN", (int)JB_NEWINF_LANE_MIN));  // (read when a step graph is built)
   return a;
 }
 
@@ -1119,8 +1118,8 @@ extern "C" int jb_infect(JbWorld* w, const uint32_t* persons, const uint32_t* va
   CK(cudaMemcpyAsync(w->d_step_aux, &sd, sizeof(sd), cudaMemcpyHostToDevice, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   a.sp = reinterpret_cast<const StepDev*>(w->d_step_aux);
-  unsigned blocks = (unsigned)std::min<size_t>((n * 16 + 127) / 128, 148 * 8);
-  k_newinf<<<blocks, 128, 0, w->stream>>>(a, w->dis_host);
+  unsigned blocks = (unsigned)std::min<size_t>((n + 31) / 32, JB_NEWINF_GRID);
+  k_newinf<<<blocks, JB_NEWINF_THREADS, 0, w->stream>>>(a, w->dis_host);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(w->stream));
   cudaFree(d_p);
@@ -1158,7 +1157,7 @@ extern "C" int jb_mutate(JbWorld* w, uint32_t variant, const double* regional_pr
   sd.seed = seed; sd.step = step; sd.tpar = w->trans_par;
   CK(cudaMemcpyAsync(w->d_step_aux, &sd, sizeof(sd), cudaMemcpyHostToDevice, w->stream));
   a.sp = reinterpret_cast<const StepDev*>(w->d_step_aux);
-  k_newinf<<<148 * 8, 128, 0, w->stream>>>(a, w->dis_host);
+  k_newinf<<<JB_NEWINF_GRID, JB_NEWINF_THREADS, 0, w->stream>>>(a, w->dis_host);
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(w->counters + CNT_NEWINF, 0, 4, w->stream));
   CK(cudaStreamSynchronize(w->stream));
@@ -1559,7 +1558,12 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
       else { pa.mstate = w->mstate; pa.pmir = w->pmir; }
     }
     if (full) k_place<true><<<(w->N + 255) / 256, 256, 0, s>>>(pa);
-    else k_place<false><<<std::min<uint32_t>((chunks + 255) / 256, 148 * 8), 256, 0, s>>>(pa);
+    else {
+      // (six CTAs of <= 42 registers are resident per SM; a finer grid than one wave measured faster: blocks that finish
+      // early are replaced while the others are still streaming)
+      static const uint32_t ctas = (uint32_t)std::max(1, jb_env_flag("JB_PLACE_CTAS", 16));
+      k_place<false><<<std::min<uint32_t>((chunks + 255) / 256, 148 * ctas), 256, 0, s>>>(pa);
+    }
     KCHECK("k_place", s);
     w->launches++;
     if (!full && w->pol_subject_mode && w->n_pol_subjects) {
@@ -1711,7 +1715,7 @@ static int enqueue_interact(JbWorld* w, const void* d_recv, void* d_ret_send) {
     a.halo_ret = (uint8_t*)d_ret_send;
     a.fuse_health = 1; a.h = make_health_args(w, 0);
     if (health_beside && !health_early) TRY(fork_health(3));
-    k_newinf<<<148 * 8, 128, 0, s>>>(a, w->dis_host);
+    k_newinf<<<JB_NEWINF_GRID, JB_NEWINF_THREADS, 0, s>>>(a, w->dis_host);
     KCHECK("k_newinf", s);
     w->launches++;
   }
@@ -1749,7 +1753,7 @@ static int enqueue_finish(JbWorld* w, const void* d_ret_recv) {
       a.first_dev = w->counters + CNT_NEWINF;  // behind the step's own new infections
       a.cap = w->newinf_cap; a.sp = step_dev(w);
       a.fuse_health = 1; a.h = make_health_args(w, 0);
-      k_newinf<<<148 * 2, 128, 0, s>>>(a, w->dis_host);
+      k_newinf<<<148, JB_NEWINF_THREADS, 0, s>>>(a, w->dis_host);
       KCHECK("k_newinf(halo)", s);
       w->launches++;
     }

@@ -5,9 +5,11 @@ Replaces ``june/domains`` (``DomainSplitter.generate_world_split``,
 
 * a person belongs to the domain of their home super area, a group to the domain of its super
   area (``WorldSoA.grp_super_area``);
-* domains are contiguous, population-balanced ranges of super areas (the reference scores
-  ``5*people + workers + pupils + commuters`` and clusters with a library that is not available;
-  for contiguous synthetic geographies a balanced prefix split is equivalent);
+* domains are contiguous ranges of super areas balanced by the reference's score
+  ``5*people + workers + pupils + commuters`` per super area (``domain_decomposition.py:22,107-113``;
+  the reference clusters the scored super areas with a library that is not available -- for
+  geographies numbered along a space-filling order a balanced prefix split of the same score plays
+  that role);
 * a registered member that lives in another domain becomes a HALO person of the group's domain
   (the static form of the reference's ``ExternalSubgroup`` + ``MovablePeople`` pair,
   ``groups/group/external.py``, ``mpi_wrapper.py:99-293``): its state arrives every step through
@@ -22,11 +24,33 @@ from typing import List, Sequence
 
 import numpy as np
 
-from .world import ACT_RESIDENCE, Supergroup, WorldSoA
+from .world import ACT_PRIMARY, ACT_RESIDENCE, Supergroup, WorldSoA
+
+
+#: ``default_weights`` of the reference (``domain_decomposition.py:22``)
+SCORE_WEIGHTS = {"population": 5.0, "workers": 1.0, "commuters": 1.0}
+
+
+def super_area_scores(world: WorldSoA, weights=None) -> np.ndarray:
+    """The reference's load score per super area (``DomainSplitter.get_score``, ``domain_decomposition.py:107-113``):
+    ``population * n_people + workers * (n_workers + n_pupils) + commuters * n_commuters``.  Workers and pupils are
+    counted where they work / learn (the primary-activity registrations of the groups of the super area,
+    ``geography_saver.py:111-121``), commuters where they live."""
+    w = dict(SCORE_WEIGHTS if weights is None else weights)
+    S = world.n_super_areas
+    psa = world.super_area.astype(np.int64)
+    score = w["population"] * np.bincount(psa, minlength=S).astype(np.float64)
+    if world.grp_super_area is not None and len(world.reg_member):
+        grp_of = np.repeat(np.arange(world.n_groups, dtype=np.int64), np.diff(world.grp_offset.astype(np.int64)))
+        primary = (world.reg_info >> 8) == ACT_PRIMARY
+        score += w["workers"] * np.bincount(world.grp_super_area.astype(np.int64)[grp_of[primary]], minlength=S)
+    if world.person_commute is not None:
+        score += w["commuters"] * np.bincount(psa[world.person_commute >= 0], minlength=S)
+    return score
 
 
 def balanced_split(sa_population: np.ndarray, n_domains: int) -> np.ndarray:
-    """First super area of every domain (+ end sentinel): contiguous, population balanced."""
+    """First super area of every domain (+ end sentinel): contiguous, balanced in the given per-super-area load."""
     cum = np.cumsum(sa_population)
     total = cum[-1]
     cuts = [0]
@@ -43,8 +67,7 @@ def partition(world: WorldSoA, n_domains: int) -> List[WorldSoA]:
     n, G = world.n_people, world.n_groups
     psa = world.super_area.astype(np.int64)
     assert np.all(np.diff(psa) >= 0), "people must be ordered by home super area"
-    sa_pop = np.bincount(psa, minlength=world.n_super_areas)
-    cuts = balanced_split(sa_pop, n_domains)
+    cuts = balanced_split(super_area_scores(world), n_domains)
     sa_dom = np.zeros(world.n_super_areas, np.int64)
     for d in range(n_domains):
         sa_dom[cuts[d]:cuts[d + 1]] = d

@@ -36,14 +36,22 @@ def common():
 def aligned_world(n_people, K):
     """Synthetic world whose hospital catchments do not cross the K-domain cuts (patients are
     dynamic members; cross-domain hospitalisation is out of scope, see june_b200/domains.py)."""
-    from june_b200.domains import balanced_split
+    from june_b200.domains import balanced_split, super_area_scores
     w = generate_world(n_people, seed=4, sector_betas=load_defaults()["company_sector_betas"])
-    sa_pop = np.bincount(w.super_area, minlength=w.n_super_areas)
-    cuts = balanced_split(sa_pop, K)
     hosp = w.supergroup("hospitals")
     assert hosp.n_groups >= K
-    for k in range(hosp.n_groups):  # put hospital k into domain k % K
-        w.grp_super_area[hosp.first_group + k] = cuts[k % K]
+    # the cuts follow the reference's load score, which counts workers where they work: moving a hospital moves its
+    # staff's weight, so place the hospitals and recompute until the cuts stay put
+    cuts = balanced_split(super_area_scores(w), K)
+    for _ in range(8):
+        for k in range(hosp.n_groups):  # put hospital k into domain k % K
+            w.grp_super_area[hosp.first_group + k] = cuts[k % K]
+        again = balanced_split(super_area_scores(w), K)
+        if np.array_equal(again, cuts):
+            break
+        cuts = again
+    else:
+        raise AssertionError("hospital placement does not settle")
     hsa = w.grp_super_area[hosp.first_group: hosp.first_group + hosp.n_groups].astype(np.int64)
     for d in range(K):
         inside = [hosp.first_group + k for k in range(hosp.n_groups) if cuts[d] <= hsa[k] < cuts[d + 1]]
@@ -180,3 +188,24 @@ def test_two_ranks_over_gloo_match_single_domain(tmp_path):
     assert np.array_equal(np.concatenate([r0["tag"], r1["tag"]]), ref["tag"])
     assert np.array_equal(r0["new"] + r1["new"], np.array([h["n_new_infections"] for h in sim.history]))
     assert (r0["halo"] + r1["halo"]).sum() > 0, "no resident was infected abroad: the return exchange was not exercised"
+
+
+def test_domain_score_follows_the_reference():
+    """domain_decomposition.py:22,107-113: 5 * people + workers + pupils + commuters per super area; the cuts balance it."""
+    from june_b200.domains import balanced_split, super_area_scores
+    from june_b200.world import ACT_PRIMARY
+    w = generate_world(40_000, seed=9, sector_betas=load_defaults()["company_sector_betas"])
+    score = super_area_scores(w)
+    S = w.n_super_areas
+    people = np.bincount(w.super_area, minlength=S)
+    grp_of = np.repeat(np.arange(w.n_groups), np.diff(w.grp_offset.astype(np.int64)))
+    prim = (w.reg_info >> 8) == ACT_PRIMARY
+    at_work = np.bincount(w.grp_super_area[grp_of[prim]], minlength=S)
+    expect = 5.0 * people + at_work
+    if w.person_commute is not None:
+        expect = expect + np.bincount(w.super_area[w.person_commute >= 0], minlength=S)
+    assert np.array_equal(score, expect) and at_work.sum() > 0
+    K = 4
+    cuts = balanced_split(score, K)
+    loads = np.array([score[cuts[d]:cuts[d + 1]].sum() for d in range(K)])
+    assert loads.max() - loads.min() <= 2 * score.max(), "prefix split balanced to within a super area"

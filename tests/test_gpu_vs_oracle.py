@@ -70,13 +70,8 @@ def test_graph_replay_matches_plain_launches_and_oracle():
     compare_state(a, b, "end")
 
 
-@pytest.mark.parametrize("lane_min", [None, "0"])
-def test_philox_mode_full_steps_match_oracle(lane_min, monkeypatch):
-    """`lane_min` = "0": the infection sampler runs one lane per new infection (the form used when a step creates tens
-    of thousands of infections) instead of sixteen -- same Philox streams, same infections."""
+def test_philox_mode_full_steps_match_oracle():
     assert have_gpu()
-    if lane_min is not None:
-        monkeypatch.setenv("JB_NEWINF_LANE_MIN", lane_min)
     w = generate_world(60_000, seed=3, sector_betas=load_defaults()["company_sector_betas"])
     a, b, beta = setup(w)
     seeds = np.random.default_rng(0).choice(w.n_people, 1500, replace=False).astype(np.uint32)

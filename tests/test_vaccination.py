@@ -65,12 +65,8 @@ def test_daily_probability_and_efficacy_shape_on_the_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lane_min", [None, "0"])
-def test_cuda_matches_oracle_with_vaccination(lane_min, monkeypatch):
-    """(`lane_min` = "0": one lane per new infection in the sampler, incl. its effective-multiplier outcome table.)"""
+def test_cuda_matches_oracle_with_vaccination():
     assert have_gpu()
-    if lane_min is not None:
-        monkeypatch.setenv("JB_NEWINF_LANE_MIN", lane_min)
     w = generate_world(60_000, seed=2, sector_betas=load_defaults()["company_sector_betas"])
     (a, b), beta = engines(w, ["cuda", "oracle"])
     tabs = campaigns().device_tables(datetime.date(2020, 3, 2), ["Covid19"])
