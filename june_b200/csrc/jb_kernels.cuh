@@ -750,11 +750,18 @@ struct HealthAcc {
 
 #define JB_SUM_SMEM_REGIONS 64
 
-__device__ __forceinline__ double jb_gamma_pdf(double x, double a, double loc, double scale) {
-  // transmission.py:47-75
+// Gamma transmission profile (transmission.py:47-75): probability(t) = norm * gamma.pdf(t, a, loc, scale)
+//   = norm / (Gamma(a) scale) * z^(a-1) e^(-z),  z = (t - loc) / scale.
+// The factor in front does not change during an infection: it is computed once, when the infection is created
+// (row 4 of inf_par, which the gamma profile does not otherwise use), and the health update of every step is left
+// with one logarithm and one exponential per infection instead of tgamma + pow + exp (the update is bound by fp64
+// arithmetic: ~3.5 M infectious people at 56 M).
+__device__ __forceinline__ double jb_gamma_front(double norm, double a, double scale) { return norm * (1.0 / tgamma(a)) / scale; }
+__device__ __forceinline__ double jb_gamma_profile(double front, double x, double a, double loc, double scale) {
   if (x < loc) return 0.0;
-  double z = (x - loc) / scale;
-  return 1.0 / tgamma(a) * pow(z, a - 1.0) * exp(-z) / scale;
+  const double z = (x - loc) / scale;
+  if (!(z > 0.0)) return front * pow(z, a - 1.0);  // z == 0: 0, 1 or inf depending on a -- pow's business
+  return front * exp((a - 1.0) * log(z) - z);
 }
 
 // One thread per infection slot.  Everything the update needs about the PERSON (region, closest
@@ -773,8 +780,8 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
   const double t = t_now - a.inf_start[s];
   // transmission.update_infection_probability (infection.py:91)
   if (D.trans_type == JB_TRANS_GAMMA) {
-    trans[p] = a.inf_par[(size_t)3 * a.C + s] *
-                 jb_gamma_pdf(t, a.inf_par[s], a.inf_par[(size_t)1 * a.C + s], a.inf_par[(size_t)2 * a.C + s]);
+    trans[p] = jb_gamma_profile(a.inf_par[(size_t)4 * a.C + s], t, a.inf_par[s], a.inf_par[(size_t)1 * a.C + s],
+                                a.inf_par[(size_t)2 * a.C + s]);
   } else if (D.trans_type == JB_TRANS_XNEXP) {
     const double tfi = a.inf_par[(size_t)2 * a.C + s];
     double prob = 0.0;
@@ -982,6 +989,7 @@ __device__ __forceinline__ void jb_newinf_assemble(const NewInfArgs& a, const Di
   double par[JB_N_TPAR] = {0, 0, 0, 0, 0};
   if (D.trans_type == JB_TRANS_GAMMA) {
     par[0] = tp[1]; par[1] = tp[3] + t_exposed; par[2] = 1.0 / tp[2]; par[3] = tp[0];
+    par[4] = jb_gamma_front(par[3], par[0], par[2]);
   } else if (D.trans_type == JB_TRANS_XNEXP) {
     const double tfi = tp[1] + t_exposed;
     const double peak = t_exposed - tfi + tp[2];
@@ -1187,6 +1195,15 @@ __global__ void __launch_bounds__(JB_NEWINF_THREADS, 2) k_newinf(const __grid_co
     __syncthreads();  // s_x is reused by the next chunk
   }
   jb_stamp_max(3);
+}
+
+// Row 4 of the gamma profile's parameters (jb_gamma_front) for uploaded infections [s0, s0 + n): derived on the device
+// by the expression the creating kernel uses, so that a restored run continues bit for bit.
+__global__ void k_gamma_front(double* __restrict__ inf_par, uint32_t C, uint32_t s0, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = s0 + i;
+  inf_par[(size_t)4 * C + s] = jb_gamma_front(inf_par[(size_t)3 * C + s], inf_par[s], inf_par[(size_t)2 * C + s]);
 }
 
 // Mutation event, selection pass (event/mutation.py:53-58): one thread per infection slot; the chosen people

@@ -1218,6 +1218,11 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
   }
   for (int q = 0; q < JB_N_TPAR; ++q)
     CK(cudaMemcpy(w->inf_par + (size_t)q * C + hw, par.data() + (size_t)q * n, n * 8, cudaMemcpyHostToDevice));
+  if (w->dis_host.trans_type == JB_TRANS_GAMMA) {  // the derived row of the gamma profile (jb_gamma_front)
+    k_gamma_front<<<(unsigned)((n + 255) / 256), 256, 0, w->stream>>>(w->inf_par, C, hw, (uint32_t)n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(w->stream));
+  }
   for (int q = 0; q < JB_MAX_STAGES; ++q) {
     CK(cudaMemcpy(w->traj_time + (size_t)q * C + hw, tt.data() + (size_t)q * n, n * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->traj_tag + (size_t)q * C + hw, ttag.data() + (size_t)q * n, n, cudaMemcpyHostToDevice));
@@ -2223,6 +2228,7 @@ extern "C" int jb_fetch_infections(JbWorld* w, JbInfectionRow* rows, size_t cap,
       memset(&r, 0, sizeof(r));
       r.person = w->h_int2ext[person[s]]; r.variant = var[s]; r.start_time = start[s];
       for (int q = 0; q < JB_N_TPAR; ++q) r.tpar[q] = par[(size_t)q * hw + s];
+      if (w->dis_host.trans_type == JB_TRANS_GAMMA) r.tpar[4] = 0.0;  // (device-internal: the profile's constant factor)
       r.probability = trans[person[s]];
       r.n_stages = nst[s]; r.stage = stage[s]; r.max_tag = maxtag[s]; r.tag = tag[s];
       for (int q = 0; q < JB_MAX_STAGES; ++q) { r.traj_time[q] = tt[(size_t)q * hw + s]; r.traj_tag[q] = ttag[(size_t)q * hw + s]; }
