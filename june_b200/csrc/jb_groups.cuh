@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
   __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
   __shared__ uint32_t s_mem[TM == JB_TM_GATHER ? JB_TILE_SLOTS : 1];
   __shared__ double s_cm[16];
+  __shared__ double s_rcp[33];  // 1 / n for the subgroup sizes a tile can hold: the row sums multiply instead of dividing
   __shared__ uint32_t s_nw[JB_TILE_WARPS];  // work-list lengths (per-warp lists; [0] = the block's list otherwise)
   __shared__ double q_lam[JB_TILE_WARPS][VM][JB_DRAW_QUEUE];
   __shared__ uint32_t q_x[JB_TILE_WARPS][JB_DRAW_QUEUE], q_ord[JB_TILE_WARPS][JB_DRAW_QUEUE];  // block-local slot, ordinal
@@ -622,6 +623,10 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
     if (lane == 0 && draws) atomicAdd(&a.counters[CNT_DRAWS], draws);
   }
   if ((PW ? lane : (int)threadIdx.x) < a.dim * a.dim) s_cm[PW ? lane : threadIdx.x] = cm_mine;
+  {
+    const int k = PW ? lane : (int)threadIdx.x;  // (per-warp lists: every warp parks the same values)
+    if (k < 32) s_rcp[k + 1] = 1.0 / (double)(k + 1);
+  }
   if (PW) __syncwarp(); else __syncthreads();
   const uint32_t n_work = s_n;
   if (STREAM) jb_stamp_max(0);
@@ -791,7 +796,9 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
                 if (j < dim && T[v][j] != 0.0) {
                   const int nj = (int)((npk >> (8 * j)) & 0xFFu);
                   const int nn = (i == j) ? max(1, nj - 1) : nj;  // interaction.py:469-471
-                  r += s_cm[i * dim + j] * T[v][j] / (double)nn * beta * dt;
+                  // (times 1/nn from the table: the fp64 division was a seventh of the kernel's instructions; the
+                  // quotient may differ from the reference's in the last bit)
+                  r += s_cm[i * dim + j] * T[v][j] * s_rcp[nn] * beta * dt;
                 }
               r *= jb_susc<VM>(a, p, hot, v);
             }

@@ -775,30 +775,39 @@ __device__ __forceinline__ double jb_gamma_profile(double front, double x, doubl
 __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* trans, uint32_t s, double t_now, uint32_t flags,
                                                uint32_t* sum_base, HealthAcc& acc) {
   const DiseaseMasks D = a.masks;
+  // Everything the slot holds is requested up front, in ONE round trip to DRAM: left where they are used, the loads
+  // sit behind the branch on the person and behind the store of the transmission probability (which the compiler
+  // must assume to alias them) and reach DRAM one after the other -- five latencies per slot instead of one.
   const int32_t p = a.inf_person[s];
-  if (p < 0) return;
-  const double t = t_now - a.inf_start[s];
-  // transmission.update_infection_probability (infection.py:91)
-  if (D.trans_type == JB_TRANS_GAMMA) {
-    trans[p] = jb_gamma_profile(a.inf_par[(size_t)4 * a.C + s], t, a.inf_par[s], a.inf_par[(size_t)1 * a.C + s],
-                                a.inf_par[(size_t)2 * a.C + s]);
-  } else if (D.trans_type == JB_TRANS_XNEXP) {
-    const double tfi = a.inf_par[(size_t)2 * a.C + s];
-    double prob = 0.0;
-    if (t > tfi) {
-      const double tau = (t - tfi) / a.inf_par[(size_t)4 * a.C + s];
-      prob = a.inf_par[(size_t)3 * a.C + s] * (pow(tau, a.inf_par[s]) * exp(-tau / a.inf_par[(size_t)1 * a.C + s]));
-    }
-    trans[p] = prob;
-  } else {
-    trans[p] = a.inf_par[s];  // constant profile: carried over into the buffer the next step reads
-  }
-  // symptoms.update_trajectory_stage: at most one stage per call (symptoms.py:152-154)
+  const double start_s = a.inf_start[s], next_s = a.inf_next[s];
+  const double par0 = a.inf_par[s], par1 = a.inf_par[(size_t)1 * a.C + s], par2 = a.inf_par[(size_t)2 * a.C + s];
+  const double par3 = D.trans_type == JB_TRANS_XNEXP ? a.inf_par[(size_t)3 * a.C + s] : 0.0;
+  const double par4 = D.trans_type != JB_TRANS_CONSTANT ? a.inf_par[(size_t)4 * a.C + s] : 0.0;
   int stage = a.inf_stage[s];
   int tag = a.inf_tag[s];
   const int nst = a.inf_nst[s];
+  const uint32_t region_s = a.inf_region[s];
+  const int32_t med_old = a.inf_med[s];
+  const uint32_t sev_old = a.inf_sev[s];
+  if (p < 0) return;
+  const double t = t_now - start_s;
+  // transmission.update_infection_probability (infection.py:91)
+  if (D.trans_type == JB_TRANS_GAMMA) {
+    trans[p] = jb_gamma_profile(par4, t, par0, par1, par2);
+  } else if (D.trans_type == JB_TRANS_XNEXP) {
+    const double tfi = par2;
+    double prob = 0.0;
+    if (t > tfi) {
+      const double tau = (t - tfi) / par4;
+      prob = par3 * (pow(tau, par0) * exp(-tau / par1));
+    }
+    trans[p] = prob;
+  } else {
+    trans[p] = par0;  // constant profile: carried over into the buffer the next step reads
+  }
+  // symptoms.update_trajectory_stage: at most one stage per call (symptoms.py:152-154)
   bool changed = false;
-  if (stage + 1 < nst && t > a.inf_next[s]) {
+  if (stage + 1 < nst && t > next_s) {
     ++stage;
     const int tag_old = tag;
     tag = a.traj_tag[(size_t)stage * a.C + s];
@@ -809,11 +818,10 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
     changed = true;
   }
   const int bit = JB_TAG_BIT(tag);
-  uint32_t* sum = sum_base + (size_t)a.inf_region[s] * JB_N_SUMMARY;
+  uint32_t* sum = sum_base + (size_t)region_s * JB_N_SUMMARY;
   // what happens in a hospital is counted for the HOSPITAL's region (records_writer.py:272-294,369-373)
   auto hsum = [&](int32_t hg) -> uint32_t* { return sum_base + (size_t)JB_GINFO_REGION(a.grp_info[hg]) * JB_N_SUMMARY; };
   // Hospitalisation.apply (medical_care_policies.py:413-526; hospital.py:62-122)
-  const int32_t med_old = a.inf_med[s];
   const bool was_med = med_old >= 0;
   int32_t med_new = med_old;
   if (flags & JB_STEP_HOSPITALISATION) {
@@ -838,7 +846,7 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
   }
   const uint32_t sev_new = (bit & D.severe_mask) ? 1u : 0u;
   const bool rec = (bit & D.rec_mask) != 0, dead = !rec && (bit & D.dead_mask) != 0;
-  if (rec || dead || changed || med_new != med_old || sev_new != a.inf_sev[s]) {
+  if (rec || dead || changed || med_new != med_old || sev_new != sev_old) {
     uint32_t st = a.pstate[p];
     st = (med_new >= 0) ? (st | JB_PS_MEDICAL) : (st & ~JB_PS_MEDICAL);
     st = sev_new ? (st | JB_PS_SEVERE) : (st & ~JB_PS_SEVERE);
@@ -916,7 +924,7 @@ __device__ __forceinline__ void jb_health_body(const HealthArgs& a, uint32_t bid
   }
 }
 
-__global__ void __launch_bounds__(256) k_health(const __grid_constant__ HealthArgs a) {
+__global__ void __launch_bounds__(256, 4) k_health(const __grid_constant__ HealthArgs a) {
   jb_stamp(5);
   jb_health_body(a, blockIdx.x, gridDim.x);
 }
