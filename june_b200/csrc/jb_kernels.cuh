@@ -791,6 +791,18 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
   const uint32_t sev_old = a.inf_sev[s];
   if (p < 0) return;
   const double t = t_now - start_s;
+  // An infection that moves on to its next stage in this step (a few per cent of them, but somebody in almost every
+  // warp) needs the stage's tag, the time of the stage after it and the person's state byte: a second trip to DRAM,
+  // requested here so that it overlaps the profile's arithmetic instead of following the store below.
+  const bool advance = stage + 1 < nst && t > next_s;
+  int tag_adv = tag;
+  double next_adv = 1e300;
+  uint32_t st_adv = 0;
+  if (advance) {
+    tag_adv = a.traj_tag[(size_t)(stage + 1) * a.C + s];
+    if (stage + 2 < JB_MAX_STAGES) next_adv = a.traj_time[(size_t)(stage + 2) * a.C + s];
+    st_adv = a.pstate[p];
+  }
   // transmission.update_infection_probability (infection.py:91)
   if (D.trans_type == JB_TRANS_GAMMA) {
     trans[p] = jb_gamma_profile(par4, t, par0, par1, par2);
@@ -807,14 +819,14 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
   }
   // symptoms.update_trajectory_stage: at most one stage per call (symptoms.py:152-154)
   bool changed = false;
-  if (stage + 1 < nst && t > next_s) {
+  if (advance) {
     ++stage;
     const int tag_old = tag;
-    tag = a.traj_tag[(size_t)stage * a.C + s];
+    tag = tag_adv;
     if (a.hev_person && tag != tag_old) jb_health_event(a, (uint32_t)p, JB_HEV_SYMPTOMS, tag);
     a.inf_stage[s] = (uint8_t)stage;
     a.inf_tag[s] = (int8_t)tag;
-    a.inf_next[s] = (stage + 1 < JB_MAX_STAGES) ? a.traj_time[(size_t)(stage + 1) * a.C + s] : 1e300;
+    a.inf_next[s] = next_adv;
     changed = true;
   }
   const int bit = JB_TAG_BIT(tag);
@@ -847,7 +859,7 @@ __device__ __forceinline__ void jb_health_slot(const HealthArgs& a, double* tran
   const uint32_t sev_new = (bit & D.severe_mask) ? 1u : 0u;
   const bool rec = (bit & D.rec_mask) != 0, dead = !rec && (bit & D.dead_mask) != 0;
   if (rec || dead || changed || med_new != med_old || sev_new != sev_old) {
-    uint32_t st = a.pstate[p];
+    uint32_t st = advance ? st_adv : (uint32_t)a.pstate[p];  // (nobody else writes this person's byte during the update)
     st = (med_new >= 0) ? (st | JB_PS_MEDICAL) : (st & ~JB_PS_MEDICAL);
     st = sev_new ? (st | JB_PS_SEVERE) : (st & ~JB_PS_SEVERE);
     if (med_new != med_old) { a.pmed[p] = med_new; a.inf_med[s] = med_new; }
