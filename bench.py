@@ -457,7 +457,8 @@ def cpu_run(world, inter, dc, prob, cfg, policies, steps: int, warmup: int, budg
     """Time `steps` steps of the CPU port after `warmup` steps; with a budget, as many steps as fit in
     ~budget_s seconds (at least 3, at most `steps`), decided from the duration of the warm-up."""
     eng = oracle_engine(world, inter, dc, prob)
-    sim = Simulator.from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, engine=eng, seed=2020)
+    from helpers import simulator_over  # (tests/ is on the path: oracle_engine) the product's host loop over the CPU port
+    sim = simulator_over(eng).from_file(world, inter, policies=policies, disease_config=dc, outcome_prob=prob, seed=2020)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
     if config4:

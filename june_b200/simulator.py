@@ -191,7 +191,7 @@ class Simulator:
     def __init__(self, world: WorldSoA, interaction: Interaction, timer: Timer, activity_manager: ActivityManager,
                  epidemiology: Optional[Epidemiology] = None, tracker=None, events=None, record=None,
                  disease_config: Optional[DiseaseConfig] = None, outcome_prob: Optional[np.ndarray] = None,
-                 device: int = 0, seed: int = 0, engine: Optional[Engine] = None, distributed: bool = False,
+                 device: int = 0, seed: int = 0, distributed: bool = False,
                  checkpoint_save_dates=None, checkpoint_save_path: Optional[str] = None):
         self.world, self.interaction, self.timer = world, interaction, timer
         self.activity_manager, self.epidemiology, self.record = activity_manager, epidemiology, record
@@ -210,15 +210,13 @@ class Simulator:
             from .disease import outcome_probabilities, synthetic_rates
             rates, bins = synthetic_rates()
             outcome_prob = outcome_probabilities(self.disease_config, rates, bins)
-        self.device = engine or DeviceWorld(world, interaction, self.disease_config, outcome_prob, device=device)
+        self.device = self._create_device(world, interaction, outcome_prob, device)
         self.halo: Optional[HaloExchange] = None
         if distributed:
-            import torch
             import torch.distributed as dist
             self.rank = dist.get_rank()
-            on_gpu = isinstance(self.device, DeviceWorld)
-            self.halo = HaloExchange(world, self.device.halo_record_size(),
-                                     device=torch.device("cuda", self.device.device_index) if on_gpu else None)
+            buffers_on = self._exchange_buffer_device()
+            self.halo = HaloExchange(world, self.device.halo_record_size(), device=buffers_on)
         self._ext_stream = None
         self.p2p = False
         self.halo_activity_mask = 0
@@ -232,9 +230,9 @@ class Simulator:
             self.halo.dist.all_gather_object(masks, local)
             self.halo_activity_mask = int(np.bitwise_or.reduce(np.array(masks, np.int64)))
             self.device.set_halo_activities(self.halo_activity_mask)
-        if self.halo is not None and isinstance(self.device, DeviceWorld) and os.environ.get("JB_HALO", "p2p") != "nccl":
+        if self.halo is not None and buffers_on is not None and os.environ.get("JB_HALO", "p2p") != "nccl":
             self._connect_peer_windows()
-        if self.halo is not None and isinstance(self.device, DeviceWorld):
+        if self.halo is not None and buffers_on is not None:
             import torch
             ptr = self.device._f("stream_handle")(self.device.handle)
             self._ext_stream = torch.cuda.ExternalStream(int(ptr), device=torch.device("cuda", self.device.device_index))
@@ -250,6 +248,27 @@ class Simulator:
         self.region_history: List[tuple] = []
         self.last_stats: Dict[str, int] = {}
         self.history: List[Dict[str, object]] = []
+
+    def _create_device(self, world, interaction, outcome_prob, device: int) -> Engine:
+        """The world on the GPU (``libjune_b200.so``; raises without the library or without a device)."""
+        return DeviceWorld(world, interaction, self.disease_config, outcome_prob, device=device)
+
+    def _exchange_buffer_device(self):
+        """Where the buffers of the NCCL fallback exchange live: the GPU of this rank."""
+        import torch
+        return torch.device("cuda", self.device.device_index)
+
+    def _step_with_exchange(self, params, want_stats: bool):
+        """A step whose two exchanges are host-issued collectives (``JB_HALO=nccl``): the all-to-alls are
+        issued with the library's stream current, so kernels and collectives are ordered on the device
+        -- no host synchronisation."""
+        dev, h = self.device, self.halo
+        with h.torch.cuda.stream(self._ext_stream):
+            dev.step_begin(params, h.send.data_ptr())
+            h.exchange_people()
+            dev.step_interact(h.recv.data_ptr(), h.ret_send.data_ptr())
+            h.exchange_infections()
+            return dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
 
     def _connect_peer_windows(self) -> None:
         """Halo exchange over peer memory (``jb_p2p_window`` / ``jb_p2p_connect``): the ranks swap the
@@ -413,23 +432,8 @@ class Simulator:
         dev = self.device
         if self.halo is None or self.p2p or not (self.activity_manager.activity_mask() & self.halo_activity_mask):
             stats = dev.step(params, want_stats=want_stats)
-        elif self._ext_stream is not None:
-            # GPU ranks: the NCCL all-to-alls are issued with the library's stream current, so
-            # kernels and collectives are ordered on the device -- no host synchronisation
-            h = self.halo
-            with self.halo.torch.cuda.stream(self._ext_stream):
-                dev.step_begin(params, h.send.data_ptr())
-                h.exchange_people()
-                dev.step_interact(h.recv.data_ptr(), h.ret_send.data_ptr())
-                h.exchange_infections()
-                stats = dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
         else:
-            h = self.halo  # CPU engine (tests): host buffers, gloo
-            dev.step_begin(params, h.send.data_ptr())
-            h.exchange_people()
-            dev.step_interact(h.recv.data_ptr(), h.ret_send.data_ptr())
-            h.exchange_infections()
-            stats = dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
+            stats = self._step_with_exchange(params, want_stats)
         self.step_ordinal += 1
         self._last_step_date = self.timer.date
         ep = self.epidemiology

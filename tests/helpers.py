@@ -73,3 +73,32 @@ def make_engine(kind: str, world: WorldSoA, outcome_prob: np.ndarray, interactio
 def default_beta_table(world: WorldSoA, interaction: Interaction) -> np.ndarray:
     r = world.n_regions
     return interaction.beta_table(world.beta_rules, [1.0] * r, [None] * r)
+
+
+def simulator_over(engine, base=None):
+    """A ``Simulator`` class whose device side is ``engine`` (the CPU oracle, or a CUDA engine the test built itself)
+    instead of a ``DeviceWorld`` it creates: the host loop under test is the product's, only the hooks that create the
+    device and run the exchange of a multi-domain step are replaced -- with host buffers over gloo for a CPU engine."""
+    from june_b200.device import DeviceWorld
+    from june_b200.simulator import Simulator
+    base = base or Simulator
+
+    class _Over(base):
+        def _create_device(self, world, interaction, outcome_prob, device):
+            return engine
+
+        def _exchange_buffer_device(self):
+            return super()._exchange_buffer_device() if isinstance(engine, DeviceWorld) else None
+
+        def _step_with_exchange(self, params, want_stats):
+            if isinstance(engine, DeviceWorld):
+                return super()._step_with_exchange(params, want_stats)
+            dev, h = self.device, self.halo
+            dev.step_begin(params, h.send.data_ptr())
+            h.exchange_people()
+            dev.step_interact(h.recv.data_ptr(), h.ret_send.data_ptr())
+            h.exchange_infections()
+            return dev.step_finish(h.ret_recv.data_ptr(), want_stats=want_stats)
+
+    _Over.__name__ = base.__name__
+    return _Over

@@ -27,7 +27,7 @@ from june_b200.policy import Policies
 from june_b200.simulator import Simulator
 from june_b200.timer import Timer
 
-from helpers import make_engine
+from helpers import make_engine, simulator_over
 from test_domains import aligned_world, common, seed_list
 
 
@@ -36,8 +36,8 @@ def make_sim(world, engine, distributed, days):
     cfg = load_defaults()["simulation"]
     cfg["time"]["initial_day"] = "2020-03-02 8:00"
     cfg["time"]["total_days"] = days
-    sim = Simulator.from_file(world, inter, policies=Policies.from_file(disease_config=dc), disease_config=dc,
-                              outcome_prob=prob, engine=engine, seed=13, distributed=distributed)
+    sim = simulator_over(engine).from_file(world, inter, policies=Policies.from_file(disease_config=dc), disease_config=dc,
+                                           outcome_prob=prob, seed=13, distributed=distributed)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
     return sim

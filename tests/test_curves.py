@@ -13,7 +13,7 @@ from june_b200.policy import Hospitalisation, Policies, SevereSymptomsStayHome
 from june_b200.simulator import ActivityManager, Epidemiology, InfectionSeed, Simulator
 from june_b200.timer import Timer
 
-from helpers import GOLDEN, Golden, have_gpu, make_engine
+from helpers import GOLDEN, Golden, have_gpu, make_engine, simulator_over
 
 import os
 
@@ -42,7 +42,7 @@ def run_seeds(kind, n_seeds=32):
                              {"medical_facility": ["hospitals"], "primary_activity": ["schools", "companies"],
                               "residence": ["households", "care_homes"]})
         epi = Epidemiology(infection_seeds=[InfectionSeed(cases, "2020-03-02", seed=s)])
-        sim = Simulator(world, inter, timer, am, epi, disease_config=dc, outcome_prob=prob, engine=eng, seed=1000 + s)
+        sim = simulator_over(eng)(world, inter, timer, am, epi, disease_config=dc, outcome_prob=prob, seed=1000 + s)
         sim.run()
         seeded = int(round(cases * world.n_people))
         for h in sim.history:

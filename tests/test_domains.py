@@ -18,7 +18,7 @@ from june_b200.domains import LoopbackExchange, partition
 from june_b200.interaction import Interaction, load_defaults
 from june_b200.synth import generate_world
 
-from helpers import default_beta_table, make_engine
+from helpers import default_beta_table, make_engine, simulator_over
 
 MASKS = [0b10001, 0b10101, 0b10001, 0b10001, 0b10101]
 DTS = [1 / 24, 8 / 24, 1 / 24, 3 / 24, 11 / 24]
@@ -147,8 +147,8 @@ def _gloo_worker(rank, world_size, port, n_people, out_dir):
     cfg = load_defaults()["simulation"]
     cfg["time"]["initial_day"] = "2020-03-02 8:00"
     cfg["time"]["total_days"] = 4
-    sim = Simulator.from_file(part, inter, policies=Policies.from_file(disease_config=dc), disease_config=dc,
-                              outcome_prob=prob, engine=eng, seed=13, distributed=True)
+    sim = simulator_over(eng).from_file(part, inter, policies=Policies.from_file(disease_config=dc), disease_config=dc,
+                                        outcome_prob=prob, seed=13, distributed=True)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
     seeds = seed_list(w.n_people)
@@ -176,8 +176,8 @@ def test_two_ranks_over_gloo_match_single_domain(tmp_path):
     cfg = load_defaults()["simulation"]
     cfg["time"]["initial_day"] = "2020-03-02 8:00"
     cfg["time"]["total_days"] = 4
-    sim = Simulator.from_file(w, inter, policies=Policies.from_file(disease_config=dc), disease_config=dc,
-                              outcome_prob=prob, engine=eng, seed=13)
+    sim = simulator_over(eng).from_file(w, inter, policies=Policies.from_file(disease_config=dc), disease_config=dc,
+                                        outcome_prob=prob, seed=13)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
     eng.infect(seed_list(n_people), time=-4.0, seed=9, step=999)

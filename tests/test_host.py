@@ -91,7 +91,7 @@ def test_summary_csv_rows(tmp_path):
     from june_b200.interaction import load_defaults
     from june_b200.simulator import Epidemiology, InfectionSeed, Simulator
     from june_b200.synth import generate_world
-    from helpers import make_engine
+    from helpers import make_engine, simulator_over
     w = generate_world(12_000, seed=2)
     inter = Interaction.from_file()
     dc = DiseaseConfig("covid19")
@@ -101,8 +101,8 @@ def test_summary_csv_rows(tmp_path):
     cfg["time"]["total_days"] = 8
     eng = make_engine("oracle", w, prob, interaction=inter, disease=dc)
     epi = Epidemiology(infection_seeds=[InfectionSeed(0.02, cfg["time"]["initial_day"])])
-    sim = Simulator.from_file(w, inter, policies=Policies.from_file(disease_config=dc), epidemiology=epi, engine=eng,
-                              disease_config=dc, outcome_prob=prob, record=True)
+    sim = simulator_over(eng).from_file(w, inter, policies=Policies.from_file(disease_config=dc), epidemiology=epi,
+                                        disease_config=dc, outcome_prob=prob, record=True)
     sim.timer = Timer.from_config(cfg)
     sim.activity_manager.timer = sim.timer
     sim.run()

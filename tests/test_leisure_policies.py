@@ -67,7 +67,7 @@ def make_sim(kind, world, policies, total_days, seed):
     from june_b200.interaction import Interaction
     from june_b200.simulator import ActivityManager, Epidemiology, InfectionSeed, Simulator
     from june_b200.timer import Timer
-    from helpers import make_engine
+    from helpers import make_engine, simulator_over
     inter, dc = Interaction.from_file(), DiseaseConfig("covid19")
     prob = outcome_probabilities(dc, *synthetic_rates())
     eng = make_engine(kind, world, prob, interaction=inter, disease=dc)
@@ -84,7 +84,7 @@ def make_sim(kind, world, policies, total_days, seed):
     timer = Timer.from_config(config)
     am = ActivityManager.from_config(config, world, policies, timer)
     epi = Epidemiology(infection_seeds=[InfectionSeed(0.01, "2020-03-02", seed=seed)])
-    return Simulator(world, inter, timer, am, epi, disease_config=dc, outcome_prob=prob, engine=eng, seed=seed)
+    return simulator_over(eng)(world, inter, timer, am, epi, disease_config=dc, outcome_prob=prob, seed=seed)
 
 
 def test_closed_venues_empty_out_and_reductions_reduce():

@@ -20,7 +20,7 @@ from june_b200.simulator import ActivityManager, Epidemiology, InfectionSeed, Si
 from june_b200.synth import generate_world
 from june_b200.timer import Timer
 
-from helpers import default_beta_table, have_gpu, make_engine
+from helpers import default_beta_table, have_gpu, make_engine, simulator_over
 
 ACT_LEISURE, ACT_RESIDENCE = 3, 4
 WD = [["medical_facility", "residence"], ["medical_facility", "primary_activity", "leisure", "residence"],
@@ -45,7 +45,7 @@ def make_sim(kind, world, policies=None, days=4, seed=3):
     timer = Timer.from_config(config)
     am = ActivityManager.from_config(config, world, policies or Policies.from_file(), timer)
     epi = Epidemiology(infection_seeds=[InfectionSeed(0.03, "2020-03-05", seed=seed)])
-    return Simulator(world, inter, timer, am, epi, disease_config=dc, outcome_prob=prob, engine=eng, seed=seed)
+    return simulator_over(eng)(world, inter, timer, am, epi, disease_config=dc, outcome_prob=prob, seed=seed)
 
 
 def household_of(world):
