@@ -201,6 +201,25 @@ def interaction_bytes(world, sg, n_present: int) -> int:
     return int(14 * n_present + 8 * n_sub * f + 8 * n_grp * f)
 
 
+def kernels_by_supergroup(described: str) -> dict:
+    """Which interaction kernels the library launches for every supergroup, from its own layout summary
+    (``jb_world_describe``): ``k_span`` for a mirrored single-subgroup supergroup packed into work items, ``k_tiles``
+    for tiled small groups, ``k_groups`` for the warp / CTA lists."""
+    import re
+    out = {}
+    for m in re.finditer(r"supergroup (\d+): .*?tiles (\d+)( \(none valid\))?, span items (\d+), warp-list (\d+), cta-list (\d+)", described):
+        k, tiles, none_valid, span, n_w, n_c = int(m.group(1)), int(m.group(2)), m.group(3), int(m.group(4)), int(m.group(5)), int(m.group(6))
+        names = []
+        if span:
+            names.append("k_span")
+        elif tiles and not none_valid:
+            names.append("k_tiles")
+        if n_w or n_c:
+            names.append("k_groups")
+        out[k] = " + ".join(names) if names else "k_groups"
+    return out
+
+
 def workload_name(n_total: int, leisure: bool, config4: bool = False) -> str:
     """The workload both arms run (same generator, schedule and seeding)."""
     if config4:
@@ -383,6 +402,7 @@ def run_gpu(args):
     k_top = int(np.argmax(slots))
     care = int((world.care_home_resident != 0).sum())
     by_sg = {}
+    kernels_of = kernels_by_supergroup(dev.describe())
     for k, sg in enumerate(world.supergroups):
         n_launch = per_sg[k]["launches"]
         if not n_launch or not slots[k]:
@@ -391,7 +411,7 @@ def run_gpu(args):
         a_bytes = interaction_bytes(world, sg, present)
         t_s = per_sg[k]["ms"] / n_launch * 1e-3
         gbs = a_bytes / t_s / 1e9 if t_s > 0 else 0.0
-        by_sg[sg.name] = {"kernel": "k_tiles" if sg.launch_mode == 0 else "k_groups", "bytes_per_launch": a_bytes,
+        by_sg[sg.name] = {"kernel": kernels_of.get(k, "k_tiles" if sg.launch_mode == 0 else "k_groups"), "bytes_per_launch": a_bytes,
                           "us_per_launch": round(t_s * 1e6, 2), "achieved": round(gbs, 1), "frac": round(gbs / peak, 4),
                           "launches": int(n_launch)}
     top = by_sg[world.supergroups[k_top].name]

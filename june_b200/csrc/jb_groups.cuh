@@ -489,7 +489,10 @@ __global__ void __launch_bounds__(JB_CTA) k_groups(const __grid_constant__ Group
 template <int TM, int VM, bool EV>
 // (stream tiles are occupancy hungry: 48 registers measured 20 % faster than 70; the gather
 // flavour keeps its registers for the 16 gathers in flight per thread)
-__global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) k_tiles(const __grid_constant__ GroupArgs a) {
+#ifndef JB_TILE_MINB
+#define JB_TILE_MINB 10
+#endif
+__global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_MINB : 1) k_tiles(const __grid_constant__ GroupArgs a) {
   constexpr bool STREAM = TM == JB_TM_STREAM;
   if (STREAM) jb_stamp(2);
   const double* const trans = jb_trans_read(a.trans, a.NP, a.sp);
@@ -499,6 +502,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
   __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
   __shared__ uint32_t s_mem[TM == JB_TM_GATHER ? JB_TILE_SLOTS : 1];
   __shared__ double s_cm[16];
+  __shared__ uint32_t s_tgi[JB_TILE_SLOTS / 32];  // the group word shared by the groups of each of the block's tiles, or MIXED
   __shared__ double s_rcp[33];  // 1 / n for the subgroup sizes a tile can hold: the row sums multiply instead of dividing
   __shared__ uint32_t s_nw[JB_TILE_WARPS];  // work-list lengths (per-warp lists; [0] = the block's list otherwise)
   __shared__ double q_lam[JB_TILE_WARPS][VM][JB_DRAW_QUEUE];
@@ -537,7 +541,10 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
     uint4 iv = make_uint4(0u, 0u, 0u, 0u), sv = make_uint4(0u, 0u, 0u, 0u);
     uint32_t tg0 = 0;
     if (ok) {
-      if (!(lane & 1)) tg0 = a.tile_group0[c >> 1];  // with the other loads, not behind the bit logic
+      if (!(lane & 1)) {  // with the other loads, not behind the bit logic
+        tg0 = a.tile_group0[c >> 1];
+        s_tgi[threadIdx.x >> 1] = a.tile_ginfo ? a.tile_ginfo[c >> 1] : JB_TILE_GINFO_MIXED;
+      }
       iv = *reinterpret_cast<const uint4*>(a.tp_info + slot0);
       if (TM == JB_TM_STREAM) {
         sv = *reinterpret_cast<const uint4*>(a.phot + a.stream_base + slot0);
@@ -724,8 +731,9 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
     // Everything phase B gathers per group (the infectors' transmission probabilities, the group
     // word, the members' global ids for the Philox counter) is independent: prefetch it all into
     // L2 first so that the DRAM latencies overlap instead of chaining.
+    const uint32_t tgi = have_item ? s_tgi[loc >> 5] : 0u;
     if (have_item) {
-      jb_prefetch_l2(a.grp_info + g);
+      if (tgi == JB_TILE_GINFO_MIXED) jb_prefetch_l2(a.grp_info + g);
       if (TM == JB_TM_MIRROR) {
         jb_prefetch_l2(a.mgid + a.stream_base + slot_base + loc);
       } else {
@@ -743,7 +751,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? 10 : 1) 
     double beta = 0.0;
     uint32_t ord = 0;
     if (have_item) {
-      const uint32_t gi = a.grp_info[g];
+      const uint32_t gi = tgi != JB_TILE_GINFO_MIXED ? tgi : a.grp_info[g];
       beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
       ord = a.inject ? a.draw_base[g] : 0u;
     }

@@ -84,6 +84,7 @@ __host__ __device__ inline uint32_t jb_hot_to_mirror(uint32_t hot, uint32_t act)
 #define JB_TI_ACT(x) ((x) & 7u)
 
 // Work item kinds of k_span (item.y): bits 28-31 kind, low bits count.
+#define JB_TILE_GINFO_MIXED 0xFFFFFFFFu  // tile_ginfo: the tile's groups do not share one group word
 #define JB_SPAN_KIND_SMALL 1u  // count = tiles of small groups (<= 16); tile_group0 = ordinal of the tile's first group in span_group
 #define JB_SPAN_KIND_CLASS 2u  // count = groups, bits 8-15 = lanes per group (4, 8, 16 or 32: 16 slots per lane); item.z = first ordinal
 #define JB_SPAN_KIND_BIG 3u    // one group of more than 512 slots; item.z = its ordinal
@@ -247,6 +248,7 @@ struct GroupArgs {
   const uint32_t* int2ext;    // internal -> caller person index
   const uint32_t* ext2int;    // caller -> internal person index
   const uint32_t* tile_group0;
+  const uint32_t* tile_ginfo;  // per tile: the grp_info word its groups share, or JB_TILE_GINFO_MIXED (null: always gather)
   const uint32_t* tp_member;
   const uint8_t* tp_info;
   uint32_t n_tiles, stream_base;
@@ -309,6 +311,7 @@ struct SgTiles {
   uint32_t n_span = 0;
   uint32_t n_tiles = 0, stream_base = 0;
   uint32_t* tile_group0 = nullptr;
+  uint32_t* tile_ginfo = nullptr;
   uint32_t* tp_member = nullptr;
   uint8_t* tp_info = nullptr;
   // groups not handled by tiles, longest first: <= 128 members and static -> one warp each,
