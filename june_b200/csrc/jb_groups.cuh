@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
   __shared__ uint4 s_hot4[JB_TILE_THREADS], s_info4[JB_TILE_THREADS];
   __shared__ uint32_t s_mem[TM == JB_TM_GATHER ? JB_TILE_SLOTS : 1];
   __shared__ double s_cm[16];
+  __shared__ uint4 s_tm[JB_TILE_SLOTS / 32];     // per tile of the block: present | infector | subgroup bit 0 | subgroup bit 1 (slot masks)
   __shared__ uint32_t s_tgi[JB_TILE_SLOTS / 32];  // the group word shared by the groups of each of the block's tiles, or MIXED
   __shared__ double s_rcp[33];  // 1 / n for the subgroup sizes a tile can hold: the row sums multiply instead of dividing
   __shared__ uint32_t s_nw[JB_TILE_WARPS];  // work-list lengths (per-warp lists; [0] = the block's list otherwise)
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
     const uint32_t c = blockIdx.x * JB_TILE_THREADS + threadIdx.x;
     const bool ok = c < n_chunks;
     const uint32_t slot0 = c * 16;
-    uint32_t valid = 0, first = 0, pres = 0, inf = 0;
+    uint32_t valid = 0, first = 0, pres = 0, inf = 0, lg0 = 0, lg1 = 0;
     uint4 iv = make_uint4(0u, 0u, 0u, 0u), sv = make_uint4(0u, 0u, 0u, 0u);
     uint32_t tg0 = 0;
     if (ok) {
@@ -591,6 +592,8 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
         first |= (((first4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
         pres |= (((pres4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
         inf |= (((inf4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        lg0 |= (((((hi4 >> 5) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu) << (4 * q);  // JB_TI_LSG, bit planes
+        lg1 |= (((((hi4 >> 6) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu) << (4 * q);
       }
     }
     s_hot4[threadIdx.x] = sv;
@@ -599,6 +602,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
     const uint32_t mine = first | (pres << 16);
     const uint32_t other = __shfl_xor_sync(JB_FULL, mine, 1);
     const uint32_t iv_o = __shfl_xor_sync(JB_FULL, inf | (valid << 16), 1);
+    const uint32_t lg_o = __shfl_xor_sync(JB_FULL, lg0 | (lg1 << 16), 1);
     uint32_t draws = 0;
     const uint32_t t = c >> 1;
     if (ok && !(lane & 1)) {  // the even lane of the pair owns the tile
@@ -607,6 +611,8 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
       const uint32_t inf32 = inf | (iv_o << 16);
       const uint32_t n_valid = 32 - __clz((valid & 0xFFFFu) | (iv_o & 0xFFFF0000u));  // valid slots are a prefix
       const uint32_t sus32 = pres32 & ~inf32;
+      // the processing phase works on these masks instead of walking the slots (bit b = slot b of the tile)
+      s_tm[threadIdx.x >> 1] = make_uint4(pres32, inf32, lg0 | (lg_o << 16), lg1 | (lg_o & 0xFFFF0000u));
       uint32_t rem = inf32;
       while (rem) {
         const uint32_t src = __ffs(rem) - 1;
@@ -727,7 +733,14 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
     const bool have_item = w < n_work;
     const uint2 item = have_item ? my_items[w] : make_uint2(0u, 0u);
     const uint32_t loc = item.x >> 5, len = have_item ? (item.x & 31u) + 1u : 0u, g = item.y;
-    const uint32_t max_len = __reduce_max_sync(JB_FULL, len);
+    // The group as slot masks of its tile (bit b = slot b): present, infectors, susceptibles, and the members of
+    // each subgroup.  Sizes are popcounts; only the infectors and the susceptibles are walked (set bits, in slot
+    // order -- the reference's left-to-right order) instead of every slot three times.
+    const uint32_t tile0 = loc & ~31u;  // block-local first slot of the group's tile
+    const uint4 tm = have_item ? s_tm[loc >> 5] : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t gm = have_item ? ((len >= 32u ? 0xFFFFFFFFu : ((1u << len) - 1u)) << (loc & 31u)) : 0u;
+    const uint32_t P = tm.x & gm, I = tm.y & gm;
+    uint32_t S = P & ~I;
     // Everything phase B gathers per group (the infectors' transmission probabilities, the group
     // word, the members' global ids for the Philox counter) is independent: prefetch it all into
     // L2 first so that the DRAM latencies overlap instead of chaining.
@@ -741,13 +754,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
         if (pf < a.N) jb_prefetch_l2(a.int2ext + pf);
       }
     }
-    for (uint32_t m = 0; m < max_len; ++m) {
-      if (m < len) {
-        const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
-        if (((hot ^ info) & JB_PS_ACT_MASK) == 0u && (hot & JB_PS_INFECTED))
-          jb_prefetch_l2(trans + person(loc + m));
-      }
-    }
+    for (uint32_t r = I; r; r &= r - 1u) jb_prefetch_l2(trans + person(tile0 + (uint32_t)__ffs(r) - 1u));
     double beta = 0.0;
     uint32_t ord = 0;
     if (have_item) {
@@ -755,66 +762,59 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
       beta = a.beta[JB_GINFO_BETA(gi) * a.R + JB_GINFO_REGION(gi)] * a.beta_scale[JB_GINFO_SCALE(gi)];
       ord = a.inject ? a.draw_base[g] : 0u;
     }
-    // pass 1: subgroup sizes (four 8-bit counters) and summed transmission probabilities
-    uint32_t npk = 0;
+    // subgroup sizes (four 8-bit counters) and summed transmission probabilities
+    const uint32_t npk = (uint32_t)__popc(P & ~tm.w & ~tm.z) | ((uint32_t)__popc(P & ~tm.w & tm.z) << 8) |
+                         ((uint32_t)__popc(P & tm.w & ~tm.z) << 16) | ((uint32_t)__popc(P & tm.w & tm.z) << 24);
     double T[VM][4];
 #pragma unroll
     for (int v = 0; v < VM; ++v)
 #pragma unroll
       for (int k = 0; k < 4; ++k) T[v][k] = 0.0;
-    for (uint32_t m = 0; m < max_len; ++m) {
-      if (m < len) {
-        const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
-        if (((hot ^ info) & JB_PS_ACT_MASK) == 0u) {  // present
-          const int l = (int)JB_TI_LSG(info);
-          npk += 1u << (8 * l);
-          if (hot & JB_PS_INFECTED) {
-            const uint32_t p = person(loc + m);
-            const double t = trans[p];
-            const int pv = (VM > 1) ? (int)JB_HOT_VAR(hot) : 0;
+    for (uint32_t r = I; r; r &= r - 1u) {
+      const uint32_t bit = (uint32_t)__ffs(r) - 1u;
+      const int l = (int)(((tm.z >> bit) & 1u) | (((tm.w >> bit) & 1u) << 1));
+      const double t = trans[person(tile0 + bit)];
+      const int pv = (VM > 1) ? (int)JB_HOT_VAR((uint32_t)s_hot[tile0 + bit]) : 0;
 #pragma unroll
-            for (int v = 0; v < VM; ++v)
+      for (int v = 0; v < VM; ++v)
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (v == pv && j == l) T[v][j] += t;
-          }
-        }
-      }
+        for (int j = 0; j < 4; ++j)
+          if (v == pv && j == l) T[v][j] += t;
     }
-    // pass 2: Lambda of every susceptible (interaction.py:594-631), draws queued
-    for (uint32_t m = 0; m < max_len; ++m) {
-      bool sus = false;
+    // Lambda of every susceptible (interaction.py:594-631), draws queued
+    while (__any_sync(JB_FULL, S != 0u)) {
+      const bool sus = S != 0u;
+      const uint32_t bit = sus ? (uint32_t)__ffs(S) - 1u : 0u;
+      S &= S - 1u;
+      const uint32_t x = tile0 + bit;  // block-local slot
       double lam_v[VM];
       double lam = 0.0;
 #pragma unroll
       for (int v = 0; v < VM; ++v) lam_v[v] = 0.0;
-      if (m < len) {
-        const uint32_t info = s_info[loc + m], hot = s_hot[loc + m];
-        if (((hot ^ info) & JB_PS_ACT_MASK) == 0u && !(hot & JB_PS_INFECTED)) {
-          sus = true;
-          // the person index is only needed for a susceptibility that is neither 0 nor 1 (and in test modes)
-          const uint32_t p = (TM != JB_TM_MIRROR || VM > 1 || a.lambda || JB_HOT_CODE(hot) == JB_SC_READ) ? person(loc + m) : 0u;
-          const int i = (int)JB_TI_LSG(info);
+      if (sus) {
+        const uint32_t hot = s_hot[x];
+        // the person index is only needed for a susceptibility that is neither 0 nor 1 (and in test modes)
+        const uint32_t p = (TM != JB_TM_MIRROR || VM > 1 || a.lambda || JB_HOT_CODE(hot) == JB_SC_READ) ? person(x) : 0u;
+        const int i = (int)(((tm.z >> bit) & 1u) | (((tm.w >> bit) & 1u) << 1));
 #pragma unroll
-          for (int v = 0; v < VM; ++v) {
-            double r = 0.0;
-            if (v < V) {
+        for (int v = 0; v < VM; ++v) {
+          double r = 0.0;
+          if (v < V) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < dim && T[v][j] != 0.0) {
-                  const int nj = (int)((npk >> (8 * j)) & 0xFFu);
-                  const int nn = (i == j) ? max(1, nj - 1) : nj;  // interaction.py:469-471
-                  // (times 1/nn from the table: the fp64 division was a seventh of the kernel's instructions; the
-                  // quotient may differ from the reference's in the last bit)
-                  r += s_cm[i * dim + j] * T[v][j] * s_rcp[nn] * beta * dt;
-                }
-              r *= jb_susc<VM>(a, p, hot, v);
-            }
-            lam_v[v] = r;
-            lam += r;
+            for (int j = 0; j < 4; ++j)
+              if (j < dim && T[v][j] != 0.0) {
+                const int nj = (int)((npk >> (8 * j)) & 0xFFu);
+                const int nn = (i == j) ? max(1, nj - 1) : nj;  // interaction.py:469-471
+                // (times 1/nn from the table: the fp64 division was a seventh of the kernel's instructions; the
+                // quotient may differ from the reference's in the last bit)
+                r += s_cm[i * dim + j] * T[v][j] * s_rcp[nn] * beta * dt;
+              }
+            r *= jb_susc<VM>(a, p, hot, v);
           }
-          if (a.lambda) a.lambda[p] = lam;
+          lam_v[v] = r;
+          lam += r;
         }
+        if (a.lambda) a.lambda[p] = lam;
       }
       // queue the draws that can succeed (lambda == 0 never infects)
       const bool want = sus && lam != 0.0;
@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
       if (wm) {
         if (want) {
           const uint32_t pos = qn + __popc(wm & lane_lt);
-          q_x[wib][pos] = loc + m;
+          q_x[wib][pos] = x;
           q_ord[wib][pos] = ord;
           if (EV) q_item[wib][pos] = (uint16_t)w;
 #pragma unroll
