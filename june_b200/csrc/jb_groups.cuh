@@ -541,6 +541,32 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
     uint32_t valid = 0, first = 0, pres = 0, inf = 0, lg0 = 0, lg1 = 0;
     uint4 iv = make_uint4(0u, 0u, 0u, 0u), sv = make_uint4(0u, 0u, 0u, 0u);
     uint32_t tg0 = 0;
+    // LEAN: what the slot descriptors say about a tile never changes -- which slots are valid, where the groups start,
+    // the subgroup planes -- and is read as four words per tile (`tile_static`, built with the layout) instead of being
+    // recomputed from 32 descriptor bytes by every launch; with one feeding activity for the whole supergroup (the
+    // households' residence) only the persons' bytes are streamed and turned into the present / infector masks.
+    const bool LEAN = STREAM && !EV && a.tile_static != nullptr;
+    uint4 ts = make_uint4(0u, 0u, 0u, 0u);
+    if (LEAN) {
+      if (ok) {
+        if (!(lane & 1)) {
+          tg0 = a.tile_group0[c >> 1];
+          s_tgi[threadIdx.x >> 1] = a.tile_ginfo ? a.tile_ginfo[c >> 1] : JB_TILE_GINFO_MIXED;
+          ts = a.tile_static[c >> 1];
+        }
+        sv = *reinterpret_cast<const uint4*>(a.phot + a.stream_base + slot0);
+        const uint32_t act4 = (uint32_t)a.uniform_act * 0x01010101u;
+        const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t st4 = sw[q];
+          const uint32_t pres4 = __vcmpeq4(st4 & 0x07070707u, act4) & 0x01010101u;
+          const uint32_t inf4 = (st4 >> 3) & pres4;
+          pres |= (((pres4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+          inf |= (((inf4 * 0x00204081u) >> 21) & 0xFu) << (4 * q);
+        }
+      }
+    } else
     if (ok) {
       if (!(lane & 1)) {  // with the other loads, not behind the bit logic
         tg0 = a.tile_group0[c >> 1];
@@ -602,17 +628,19 @@ __global__ void __launch_bounds__(JB_TILE_THREADS, TM != JB_TM_GATHER ? JB_TILE_
     const uint32_t mine = first | (pres << 16);
     const uint32_t other = __shfl_xor_sync(JB_FULL, mine, 1);
     const uint32_t iv_o = __shfl_xor_sync(JB_FULL, inf | (valid << 16), 1);
-    const uint32_t lg_o = __shfl_xor_sync(JB_FULL, lg0 | (lg1 << 16), 1);
+    const uint32_t lg_o = LEAN ? 0u : __shfl_xor_sync(JB_FULL, lg0 | (lg1 << 16), 1);
     uint32_t draws = 0;
     const uint32_t t = c >> 1;
     if (ok && !(lane & 1)) {  // the even lane of the pair owns the tile
-      const uint32_t first32 = (first & 0xFFFFu) | (other << 16);
-      const uint32_t pres32 = pres | (other & 0xFFFF0000u);
-      const uint32_t inf32 = inf | (iv_o << 16);
-      const uint32_t n_valid = 32 - __clz((valid & 0xFFFFu) | (iv_o & 0xFFFF0000u));  // valid slots are a prefix
+      // (LEAN: ts = {valid slots, first slots of the groups, subgroup plane 0, subgroup plane 1})
+      const uint32_t first32 = LEAN ? ts.y : (first & 0xFFFFu) | (other << 16);
+      const uint32_t pres32 = LEAN ? (pres | (other & 0xFFFF0000u)) & ts.x : pres | (other & 0xFFFF0000u);
+      const uint32_t inf32 = LEAN ? (inf | (iv_o << 16)) & ts.x : inf | (iv_o << 16);
+      const uint32_t n_valid = LEAN ? (uint32_t)__popc(ts.x) : 32 - __clz((valid & 0xFFFFu) | (iv_o & 0xFFFF0000u));  // valid slots are a prefix
       const uint32_t sus32 = pres32 & ~inf32;
       // the processing phase works on these masks instead of walking the slots (bit b = slot b of the tile)
-      s_tm[threadIdx.x >> 1] = make_uint4(pres32, inf32, lg0 | (lg_o << 16), lg1 | (lg_o & 0xFFFF0000u));
+      s_tm[threadIdx.x >> 1] = LEAN ? make_uint4(pres32, inf32, ts.z, ts.w)
+                                    : make_uint4(pres32, inf32, lg0 | (lg_o << 16), lg1 | (lg_o & 0xFFFF0000u));
       uint32_t rem = inf32;
       while (rem) {
         const uint32_t src = __ffs(rem) - 1;

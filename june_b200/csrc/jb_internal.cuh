@@ -248,6 +248,8 @@ struct GroupArgs {
   const uint32_t* int2ext;    // internal -> caller person index
   const uint32_t* ext2int;    // caller -> internal person index
   const uint32_t* tile_group0;
+  const uint4* tile_static;    // per tile: {valid slots, first slots of the groups, subgroup plane 0, subgroup plane 1}, or null
+  int uniform_act;             // the activity that feeds every slot of the supergroup (tile_static is only set when there is one)
   const uint32_t* tile_ginfo;  // per tile: the grp_info word its groups share, or JB_TILE_GINFO_MIXED (null: always gather)
   const uint32_t* tp_member;
   const uint8_t* tp_info;
@@ -312,6 +314,8 @@ struct SgTiles {
   uint32_t n_tiles = 0, stream_base = 0;
   uint32_t* tile_group0 = nullptr;
   uint32_t* tile_ginfo = nullptr;
+  uint4* tile_static = nullptr;
+  int uniform_act = -1;
   uint32_t* tp_member = nullptr;
   uint8_t* tp_info = nullptr;
   // groups not handled by tiles, longest first: <= 128 members and static -> one warp each,

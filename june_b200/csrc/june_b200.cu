@@ -256,7 +256,35 @@ extern "C" int jb_world_create(const JbWorldDesc* d, int device, JbWorld** out) 
         if (any && same) tgi[t] = word;
       }
       TRY(dev_upload(&D.tile_ginfo, tgi.data(), tgi.size(), s));
-      CK(cudaStreamSynchronize(s));  // tgi is a local
+      // what the descriptors say about a tile, as four words (k_tiles, LEAN): only for stream tiles whose slots are all
+      // fed by one activity
+      std::vector<uint4> tst;
+      int uni = -1;
+      bool uniform = T.mode == 2;
+      for (size_t x = 0; uniform && x < T.tp_info.size(); ++x) {
+        const uint8_t ti = T.tp_info[x];
+        if (!(ti & JB_TI_VALID)) continue;
+        if (uni < 0) uni = (int)JB_TI_ACT(ti); else if ((int)JB_TI_ACT(ti) != uni) uniform = false;
+      }
+      if (uniform && uni >= 0) {
+        tst.resize(D.n_tiles);
+        for (uint32_t t = 0; t < D.n_tiles; ++t) {
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);
+          for (uint32_t x = 0; x < 32; ++x) {
+            const uint8_t ti = T.tp_info[(size_t)t * 32 + x];
+            if (ti & JB_TI_VALID) {
+              m.x |= 1u << x;
+              if (ti & JB_TI_FIRST) m.y |= 1u << x;
+            }
+            if (JB_TI_LSG(ti) & 1u) m.z |= 1u << x;
+            if (JB_TI_LSG(ti) & 2u) m.w |= 1u << x;
+          }
+          tst[t] = m;
+        }
+        TRY(dev_upload(&D.tile_static, tst.data(), tst.size(), s));
+        D.uniform_act = uni;
+      }
+      CK(cudaStreamSynchronize(s));  // tgi, tst are locals
     }
     TRY(dev_upload(&D.tp_info, T.tp_info.data(), T.tp_info.size(), s));
     if (T.mode == 1 || T.mode == 3) TRY(dev_upload(&D.tp_member, T.tp_member.data(), T.tp_member.size(), s));
@@ -481,6 +509,7 @@ extern "C" void jb_world_destroy(JbWorld* w) {
   for (SgTiles& t : w->tiles) {
     if (t.tile_group0) cudaFree(t.tile_group0);
     if (t.tile_ginfo) cudaFree(t.tile_ginfo);
+    if (t.tile_static) cudaFree(t.tile_static);
     if (t.tp_member) cudaFree(t.tp_member);
     if (t.tp_info) cudaFree(t.tp_info);
     if (t.list_w) cudaFree(t.list_w);
@@ -1443,6 +1472,8 @@ static int launch_groups(JbWorld* w, int mode) {
         static const int skip_b = jb_env_flag("JB_TILES_SKIP_B", 0);
         if (skip_b && mode == 0) a.mode = 2;
         a.tile_group0 = T.tile_group0; a.tile_ginfo = T.tile_ginfo; a.tp_member = T.tp_member; a.tp_info = T.tp_info;
+        static const int lean_on = jb_env_flag("JB_TILES_LEAN", 1);
+        a.tile_static = lean_on ? T.tile_static : nullptr; a.uniform_act = T.uniform_act;
         a.n_tiles = T.n_tiles; a.stream_base = T.stream_base;
         a.span_items = T.span_items; a.n_span = T.n_span; a.span_group = T.span_group;
         if (T.n_span) { if (!multi) TRY((launch_span<1>(w, a, st))); else TRY((launch_span<JB_MAX_VARIANTS>(w, a, st))); }
