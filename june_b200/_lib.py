@@ -129,9 +129,16 @@ class JbStepStats(C.Structure):
         "n_icu", "n_draws", "n_no_activity", "n_slots_used", "n_halo_infected")] + [("n_by_activity", C.c_uint32 * 5)]
 
     def as_dict(self):
-        d = {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "n_by_activity"}
-        d["n_by_activity"] = [int(x) for x in self.n_by_activity]
+        # (one unpack of the 16 words instead of a getattr per field: this runs in every end-to-end step)
+        words = _STATS_STRUCT.unpack_from(self)
+        d = dict(zip(_STATS_NAMES, words))
+        d["n_by_activity"] = list(words[len(_STATS_NAMES):])
         return d
+
+
+_STATS_NAMES = tuple(n for n, _ in JbStepStats._fields_ if n != "n_by_activity")
+_STATS_STRUCT = __import__("struct").Struct("=%dI" % (len(_STATS_NAMES) + 5))
+assert _STATS_STRUCT.size == C.sizeof(JbStepStats)
 
 
 class JbInfectionRow(C.Structure):
