@@ -1632,7 +1632,13 @@ static int enqueue_begin(JbWorld* w, void* d_send) {
       if (full) pa.mstep = w->mstep;
       else { pa.mstate = w->mstate; pa.pmir = w->pmir; }
     }
-    if (full) k_place<true><<<(w->N + 255) / 256, 256, 0, s>>>(pa);
+    if (full) {
+      // a grid of a few waves, not one block per 256 people: every block ends with five atomics on the same five
+      // per-activity counters (a million same-address atomics at 56 M people: 12 % of the kernel's stall samples)
+      // and starts by building the 512-entry activity table
+      static const uint32_t full_ctas = (uint32_t)std::max(1, jb_env_flag("JB_PLACE_FULL_CTAS", 12));
+      k_place<true><<<std::min<uint32_t>((w->N + 255) / 256, 148 * full_ctas), 256, 0, s>>>(pa);
+    }
     else {
       // (six CTAs of <= 42 registers are resident per SM; a finer grid than one wave measured faster: blocks that finish
       // early are replaced while the others are still streaming)
