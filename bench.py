@@ -267,7 +267,7 @@ def run_gpu(args):
         from june_b200.simulator import Epidemiology
         sim.epidemiology = Epidemiology(vaccination_campaigns=vaccination_campaigns())
     seed_epidemic(sim, rank)
-    sim.prepare_leisure_tables(days=14)
+    sim.prepare_leisure_tables(days=45)  # every slot of every leg (warm-up, three timed legs, the rewinds between them)
     # every step graph the schedule needs is captured and instantiated here, before anything is timed
     n_shapes = sim.prepare_steps(days=8)
     dev = sim.device

@@ -109,6 +109,21 @@ class SocialVenueDistributor:
         rc = 1.0 if regional_compliance is None else regional_compliance
         return original * (1 + rc * (policy_reduction - 1))
 
+    def poisson_parameters_by_age(self, sex: str, day_type: str, working_hours: bool,
+                                  regional_compliance: Optional[float] = None, closed: bool = False,
+                                  policy_reduction=None) -> np.ndarray:
+        """``get_poisson_parameter`` for the ages 0..99 at once: the same arithmetic, element by element
+        (``policy_reduction``: a value per age, or None).  The tables of a time slot are 9 regions x 2 sexes x 100 ages
+        x K activities; the per-age Python calls were the host cost of every new slot."""
+        if closed:
+            return np.zeros(100)
+        original = np.asarray(self.poisson_parameters[day_type][sex], dtype=np.float64)
+        if policy_reduction is None:
+            return original
+        rc = 1.0 if regional_compliance is None else regional_compliance
+        red = np.array([policy_reduction[age] for age in range(100)], dtype=np.float64)
+        return original * (1 + rc * (red - 1))
+
 
 class PubDistributor(SocialVenueDistributor):
     spec, config_key = "pub", "pubs"
@@ -158,6 +173,11 @@ class ResidenceVisitsDistributor(SocialVenueDistributor):
             return 0.0
         return super().get_poisson_parameter(sex=sex, age=age, day_type=day_type, working_hours=working_hours, **kw)
 
+    def poisson_parameters_by_age(self, sex: str, day_type: str, working_hours: bool, **kw) -> np.ndarray:
+        if working_hours:
+            return np.zeros(100)
+        return super().poisson_parameters_by_age(sex=sex, day_type=day_type, working_hours=working_hours, **kw)
+
     def type_probabilities(self):
         """(household, care_home) as ``get_leisure_group`` reads them (``residence_visits.py:305-309``)."""
         p = self.policy_reductions or self.residence_type_probabilities
@@ -180,7 +200,7 @@ class Leisure:
         self.region_names = list(region_names or [])
         self.regional_compliance: Dict[str, float] = {}
         self.closed_venues: Dict[str, set] = {}
-        self.probabilities_by_region_sex_age = None
+        self._view_arrays = None
 
     @property
     def activities(self) -> List[str]:
@@ -188,38 +208,69 @@ class Leisure:
 
     def generate_leisure_probabilities_for_timestep(self, delta_time: float, working_hours: bool,
                                                     date: datetime.datetime):
-        """Returns ``(does[R][2][100], cum[R][2][100][K])`` and keeps the reference's nested-dict view
-        in ``probabilities_by_region_sex_age`` (``leisure.py:205-228``)."""
+        """Returns ``(does[R][2][100], cum[R][2][100][K])`` (``leisure.py:205-228``); the reference's nested-dict
+        view of the same numbers is built on demand (``probabilities_by_region_sex_age``).  The arithmetic is the
+        reference's, element by element, carried out on the 100 ages of a (region, sex) at once."""
         regions = self.region_names or [None]
         K = self.n_activities
         does = np.zeros((len(regions), 2, 100))
         cum = np.zeros((len(regions), 2, 100, max(1, K)))
+        probs_all = np.zeros((len(regions), 2, 100, max(1, K)))
         day = _DAY_NAMES[date.weekday()]
-        view = {}
+        per_activity = []  # day type and "open at this hour" do not depend on the person
+        for activity, dist in self.leisure_distributors.items():
+            day_type = "weekday" if day in dist.daytypes["weekday"] else "weekend"
+            ot = parse_opens(dist.open)[day_type]
+            is_open = 0 if (ot[1] - ot[0] == 0 or date.hour < ot[0] or date.hour >= ot[1]) else 1
+            per_activity.append((activity, dist, day_type, is_open))
         for r, region in enumerate(regions):
-            view[region] = {}
+            rc = None if region is None else self.regional_compliance.get(region, 1.0)
             for si, sex in enumerate(SEXES):
-                rows = []
-                for age in range(100):
-                    lam = []
-                    for activity, dist in self.leisure_distributors.items():
-                        day_type = "weekday" if day in dist.daytypes["weekday"] else "weekend"
-                        ot = parse_opens(dist.open)[day_type]
-                        is_open = 0 if (ot[1] - ot[0] == 0 or date.hour < ot[0] or date.hour >= ot[1]) else 1
-                        red = self.policy_reductions[activity][day_type][sex][age] if activity in self.policy_reductions else 1
-                        lam.append(dist.get_poisson_parameter(
-                            sex=sex, age=age, day_type=day_type, working_hours=working_hours,
-                            regional_compliance=None if region is None else self.regional_compliance.get(region, 1.0),
-                            closed=region is not None and dist.spec in self.closed_venues.get(region, ()),
-                            policy_reduction=red) * is_open)
-                    total = sum(lam)
-                    does[r, si, age] = 1.0 - np.exp(-delta_time * total)
-                    probs = [0.0 if x == 0 else x / total for x in lam]
-                    cum[r, si, age, :K] = np.cumsum(probs) if K else 0.0
-                    rows.append({"does_activity": does[r, si, age], "activities": dict(zip(self.leisure_distributors, probs))})
-                view[region][sex] = rows
-        self.probabilities_by_region_sex_age = view if self.region_names else view[None]
+                lam = []
+                for activity, dist, day_type, is_open in per_activity:
+                    red = self.policy_reductions[activity][day_type][sex] if activity in self.policy_reductions else None
+                    closed = region is not None and dist.spec in self.closed_venues.get(region, ())
+                    lam.append(self._poisson_by_age(dist, sex, day_type, working_hours, rc, closed, red) * is_open)
+                total = sum(lam) if lam else np.zeros(100)  # 0 + lam[0] + lam[1] + ...: the order of Python's sum
+                does[r, si] = 1.0 - np.exp(-delta_time * total)
+                if K:
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        probs = np.stack([np.where(x == 0, 0.0, x / total) for x in lam], axis=-1)
+                    probs_all[r, si, :, :K] = probs
+                    cum[r, si, :, :K] = np.cumsum(probs, axis=-1)
+        self._view_arrays = (does, probs_all)
         return does, cum
+
+    @staticmethod
+    def _poisson_by_age(dist, sex, day_type, working_hours, rc, closed, red) -> np.ndarray:
+        """The distributor's Poisson parameters for all ages: its vector method, unless a subclass overrides only the
+        per-person ``get_poisson_parameter`` (then that is what counts)."""
+        cls = type(dist)
+        scalar_owner = next(c for c in cls.__mro__ if "get_poisson_parameter" in vars(c))
+        vector_owner = next(c for c in cls.__mro__ if "poisson_parameters_by_age" in vars(c))
+        if issubclass(vector_owner, scalar_owner):
+            return dist.poisson_parameters_by_age(sex=sex, day_type=day_type, working_hours=working_hours,
+                                                  regional_compliance=rc, closed=closed, policy_reduction=red)
+        return np.array([dist.get_poisson_parameter(sex=sex, age=age, day_type=day_type, working_hours=working_hours,
+                                                    regional_compliance=rc, closed=closed,
+                                                    policy_reduction=1 if red is None else red[age])
+                         for age in range(100)], dtype=np.float64)
+
+    @property
+    def probabilities_by_region_sex_age(self):
+        """The reference's view of the last generated tables: ``[region][sex][age] -> {"does_activity",
+        "activities": {activity: probability}}`` (without regions: ``[sex][age]``)."""
+        if getattr(self, "_view_arrays", None) is None:
+            return None
+        does, probs = self._view_arrays
+        regions = self.region_names or [None]
+        names = list(self.leisure_distributors)
+        view = {region: {sex: [{"does_activity": does[r, si, age],
+                                "activities": dict(zip(names, (float(x) for x in probs[r, si, age, :len(names)])))}
+                               for age in range(100)]
+                         for si, sex in enumerate(SEXES)}
+                for r, region in enumerate(regions)}
+        return view if self.region_names else view[None]
 
 
 def generate_leisure_for_world(list_of_leisure_groups: Sequence[str], world, daytypes: dict = DEFAULT_DAYTYPES) -> Leisure:

@@ -483,6 +483,9 @@ class Simulator:
         pol = self.activity_manager.policies
         if pol is not None and hasattr(pol, "check_window"):
             pol.check_window(self.timer.date, self.timer.final_date)  # a policy this package does not evaluate would be active
+        # the leisure tables of every time slot of the run, computed and uploaded once (a slot met for the first time
+        # in the middle of the run re-uploads the stack and drops the captured step graphs)
+        self.prepare_leisure_tables(days=max(1, (self.timer.final_date - self.timer.date).days + 1))
         while self.timer.date < self.timer.final_date:
             if self.epidemiology is not None:
                 self.epidemiology.infection_seeds_timestep(self, self.timer)
