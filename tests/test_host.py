@@ -141,3 +141,53 @@ def test_policy_file_with_a_policy_that_is_not_evaluated_is_refused_for_its_wind
         pol.check_window(datetime.datetime(2020, 3, 1), datetime.datetime(2020, 4, 2))
     assert Policies.from_file(str(path), strict=False).not_evaluated == []
     Policies.from_file().check_window(datetime.datetime(2020, 3, 1), datetime.datetime(2021, 3, 1))  # the shipped defaults
+
+
+def test_leisure_tables_vector_path_equals_per_person_calls():
+    """``Leisure.generate_leisure_probabilities_for_timestep`` works on the 100 ages of a (region, sex) at once; a
+    distributor subclass that overrides only the per-person ``get_poisson_parameter`` takes the per-person path.
+    Both must give the same tables, bit for bit (the arithmetic is the reference's, ``leisure.py:205-228``,
+    ``social_venue_distributor.py:176-205``)."""
+    import datetime
+    from june_b200.leisure import SEXES, Leisure, PubDistributor, GroceryDistributor
+
+    class PerPersonPub(PubDistributor):
+        def get_poisson_parameter(self, sex, age, day_type, working_hours, **kw):  # same numbers, scalar path only
+            return super().get_poisson_parameter(sex=sex, age=age, day_type=day_type, working_hours=working_hours, **kw)
+
+    regions = ["North", "South"]
+    fast = Leisure({"pub": PubDistributor.from_config(), "grocery": GroceryDistributor.from_config()}, region_names=regions)
+    slow = Leisure({"pub": PerPersonPub.from_config(), "grocery": GroceryDistributor.from_config()}, region_names=regions)
+    red = {"pub": {dt: {s: [0.25 + 0.005 * a for a in range(100)] for s in ("m", "f")} for dt in ("weekday", "weekend")}}
+    for L in (fast, slow):
+        L.regional_compliance = {"North": 0.8, "South": 1.0}
+        L.policy_reductions = red
+        L.closed_venues = {"South": {"grocery"}}
+    for date in (datetime.datetime(2020, 3, 31, 19), datetime.datetime(2020, 4, 4, 13)):
+        for working_hours in (False, True):
+            a = fast.generate_leisure_probabilities_for_timestep(3 / 24, working_hours, date)
+            b = slow.generate_leisure_probabilities_for_timestep(3 / 24, working_hours, date)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            assert a[0].max() > 0 and (a[1][1, :, :, 1] == a[1][1, :, :, 0]).all(), "groceries closed in the South"
+    view = fast.probabilities_by_region_sex_age
+    row = view["North"]["f"][40]
+    assert row["does_activity"] == a[0][0, list(SEXES).index("f"), 40] and set(row["activities"]) == {"pub", "grocery"}
+
+
+def test_step_stats_as_dict_and_bench_kernel_names():
+    from june_b200 import _lib
+    st = _lib.JbStepStats()
+    st.n_new_infections, st.n_halo_infected = 3, 11
+    st.n_by_activity[0], st.n_by_activity[4] = 5, 9
+    d = st.as_dict()
+    assert d["n_new_infections"] == 3 and d["n_halo_infected"] == 11 and d["n_by_activity"] == [5, 0, 0, 0, 9]
+    assert set(d) == {n for n, _ in _lib.JbStepStats._fields_}
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    text = ("supergroup 2: groups 9, activity 2, dynamic 0, mirror (slot-ordered state), tiles 5, span items 7, warp-list 0, cta-list 3, mean tiled group 1.00\n"
+            "supergroup 3: groups 99, activity 4, dynamic 0, stream tiles (slot == person), tiles 40, span items 0, warp-list 0, cta-list 0, mean tiled group 2.34\n"
+            "supergroup 4: groups 5, activity 4, dynamic 0, gather tiles, tiles 0 (none valid), span items 0, warp-list 5, cta-list 0, mean tiled group 0.00\n")
+    assert bench.kernels_by_supergroup(text) == {2: "k_span + k_groups", 3: "k_tiles", 4: "k_groups"}
