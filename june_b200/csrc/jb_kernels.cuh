@@ -1226,6 +1226,35 @@ __global__ void k_gamma_front(double* __restrict__ inf_par, uint32_t C, uint32_t
   inf_par[(size_t)4 * C + s] = jb_gamma_front(inf_par[(size_t)3 * C + s], inf_par[s], inf_par[(size_t)2 * C + s]);
 }
 
+// jb_upload_infections, per-person side of the uploaded rows [0, n) -> slots [hw, hw + n): what the creating kernel
+// writes for an infection it makes itself (state byte, slot, tag, variant, both halves of the transmission
+// probability, cross immunity), plus the slot's mirror of the person's ward.
+struct JbCrossMasks { uint32_t c[JB_MAX_VARIANTS]; };
+__global__ void k_upload_person_side(const int32_t* __restrict__ person, const int8_t* __restrict__ tag, const uint8_t* __restrict__ var,
+                                     const double* __restrict__ prob, uint32_t n, uint32_t hw, uint32_t NP, int V,
+                                     const JbCrossMasks cross, int severe_mask, uint8_t* __restrict__ pstate,
+                                     int32_t* __restrict__ pslot, int8_t* __restrict__ ptag, uint8_t* __restrict__ pvar,
+                                     double* __restrict__ trans0, double* __restrict__ trans1, double* __restrict__ susc,
+                                     const int32_t* __restrict__ pmed, int32_t* __restrict__ inf_med) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = (uint32_t)person[i];
+  const uint32_t vr = var[i];
+  const uint32_t cross_r = cross.c[vr < JB_MAX_VARIANTS ? vr : 0];
+  uint32_t st = pstate[p];
+  st = ((cross_r & 1u) ? (st & ~JB_PST_CODE_MASK) : st) | JB_PS_INFECTED;  // susceptibility to variant 0: 0.0 from now on
+  if (JB_TAG_BIT(tag[i]) & severe_mask) st |= JB_PS_SEVERE;
+  pstate[p] = (uint8_t)st;
+  pslot[p] = (int32_t)(hw + i);
+  ptag[p] = tag[i];
+  pvar[p] = (uint8_t)vr;
+  trans0[p] = prob[i];
+  trans1[p] = prob[i];
+  for (int v = 0; v < V; ++v)
+    if ((cross_r >> v) & 1u) susc[(size_t)v * NP + p] = 0.0;
+  inf_med[hw + i] = pmed[p];
+}
+
 // Mutation event, selection pass (event/mutation.py:53-58): one thread per infection slot; the chosen people
 // are appended to the new-infection list, which k_newinf then walks in mutation mode.
 __global__ void __launch_bounds__(256) k_mutate_select(const int32_t* __restrict__ inf_person, const uint8_t* __restrict__ inf_region,

@@ -1259,12 +1259,11 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
       const uint32_t pi = (uint32_t)person[i];
       reg[i] = w->h_pregion[pi]; hosp[i] = w->h_phosp[pi];
       sev[i] = (JB_TAG_BIT(rows[i].tag) & w->dis_host.severe_mask) ? 1 : 0;
-      CK(cudaMemcpy(&med[i], w->pmed + pi, 4, cudaMemcpyDeviceToHost));
     }
     CK(cudaMemcpy(w->inf_region + hw, reg.data(), n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->inf_sev + hw, sev.data(), n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->inf_hosp + hw, hosp.data(), n * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(w->inf_med + hw, med.data(), n * 4, cudaMemcpyHostToDevice));
+    (void)med;  // (the slot's ward mirror is gathered from the person's ward by k_upload_person_side)
   }
   for (int q = 0; q < JB_N_TPAR; ++q)
     CK(cudaMemcpy(w->inf_par + (size_t)q * C + hw, par.data() + (size_t)q * n, n * 8, cudaMemcpyHostToDevice));
@@ -1277,28 +1276,25 @@ extern "C" int jb_upload_infections(JbWorld* w, const JbInfectionRow* rows, size
     CK(cudaMemcpy(w->traj_time + (size_t)q * C + hw, tt.data() + (size_t)q * n, n * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(w->traj_tag + (size_t)q * C + hw, ttag.data() + (size_t)q * n, n, cudaMemcpyHostToDevice));
   }
-  // per-person side: element-wise copies (cold path)
-  for (size_t i = 0; i < n; ++i) {
-    JbInfectionRow r = rows[i];
-    r.person = w->h_ext2int[r.person];
-    uint8_t st = 0;
-    CK(cudaMemcpy(&st, w->pstate + r.person, 1, cudaMemcpyDeviceToHost));
-    const uint32_t cross_r = w->dis_host.cross[r.variant < JB_MAX_VARIANTS ? r.variant : 0];
-    st = (uint8_t)(((cross_r & 1u) ? (st & ~JB_PST_CODE_MASK) : st) | JB_PS_INFECTED);  // susceptibility to variant 0: 0.0 from now on
-    if (JB_TAG_BIT(r.tag) & w->dis_host.severe_mask) st |= JB_PS_SEVERE;
-    CK(cudaMemcpy(w->pstate + r.person, &st, 1, cudaMemcpyHostToDevice));
-    int32_t slot = (int32_t)(hw + i);
-    int8_t tg = (int8_t)r.tag;
-    uint8_t vr = (uint8_t)r.variant;
-    double zero = 0.0;
-    CK(cudaMemcpy(w->pslot + r.person, &slot, 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(w->ptag + r.person, &tg, 1, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(w->pvar + r.person, &vr, 1, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(w->trans[0] + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(w->trans[1] + r.person, &r.probability, 8, cudaMemcpyHostToDevice));
-    for (uint32_t v = 0; v < w->V; ++v)
-      if ((w->dis_host.cross[r.variant < JB_MAX_VARIANTS ? r.variant : 0] >> v) & 1u)
-        CK(cudaMemcpy(w->susc + (size_t)v * w->NP + r.person, &zero, 8, cudaMemcpyHostToDevice));
+  // per-person side (state byte, slot, tag, variant, transmission probability, cross immunity, the slot's ward mirror):
+  // one scatter kernel over the staged rows instead of a dozen small copies per row (a checkpoint of a large world
+  // restores millions of rows)
+  {
+    std::vector<double> prob(n);
+    for (size_t i = 0; i < n; ++i) prob[i] = rows[i].probability;
+    int32_t* d_person = nullptr; int8_t* d_tag = nullptr; uint8_t* d_var = nullptr; double* d_prob = nullptr;
+    TRY(dev_upload(&d_person, person.data(), n, w->stream));
+    TRY(dev_upload(&d_tag, tag.data(), n, w->stream));
+    TRY(dev_upload(&d_var, var.data(), n, w->stream));
+    TRY(dev_upload(&d_prob, prob.data(), n, w->stream));
+    JbCrossMasks cm;
+    for (int v = 0; v < JB_MAX_VARIANTS; ++v) cm.c[v] = w->dis_host.cross[v];
+    k_upload_person_side<<<(unsigned)((n + 255) / 256), 256, 0, w->stream>>>(
+        d_person, d_tag, d_var, d_prob, (uint32_t)n, hw, w->NP, (int)w->V, cm, w->dis_host.severe_mask, w->pstate, w->pslot, w->ptag,
+        w->pvar, w->trans[0], w->trans[1], w->susc, w->pmed, w->inf_med);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(w->stream));
+    cudaFree(d_person); cudaFree(d_tag); cudaFree(d_var); cudaFree(d_prob);
   }
   hw += (uint32_t)n;
   CK(cudaMemcpy(w->counters + CNT_SLOTS_HW, &hw, 4, cudaMemcpyHostToDevice));
